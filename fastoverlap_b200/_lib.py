@@ -1,0 +1,421 @@
+"""ctypes binding of libfastoverlap_b200.so (include/fastoverlap_b200.h).
+
+This is the ONLY compute back end of the package: there is no CPU fallback.  Importing the
+package works without a GPU (so the host-side logic can be tested), but creating a Context
+raises FastOverlapError when the library or a CUDA device is missing.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_void_p = ctypes.c_void_p
+
+
+class FastOverlapError(RuntimeError):
+    pass
+
+
+class PerParams(ctypes.Structure):
+    """struct fo_per_params"""
+    _fields_ = [("natoms", ctypes.c_int64),
+                ("box", ctypes.c_double * 3),
+                ("nwave", ctypes.c_int64),
+                ("nfspace", ctypes.c_int64),
+                ("sigma", ctypes.c_double)]
+
+
+# name -> (restype, argtypes); every symbol include/fastoverlap_b200.h declares
+SIGNATURES = {
+    "fo_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_void_p)]),
+    "fo_destroy": (None, [c_void_p]),
+    "fo_last_error": (ctypes.c_char_p, [c_void_p]),
+    "fo_set_stream": (ctypes.c_int, [c_void_p, c_void_p]),
+    "fo_sync": (ctypes.c_int, [c_void_p]),
+    "fo_device_info": (ctypes.c_int, [c_void_p, c_i64p]),
+    "fo_launch_count": (ctypes.c_int64, [c_void_p]),
+    "fo_set_perm": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
+    "fo_next_fast_len": (ctypes.c_int64, [ctypes.c_int64]),
+    "fo_measure_fp64_peak": (ctypes.c_int, [c_void_p, c_f64p]),
+    "fo_per_defaults": (ctypes.c_int, [ctypes.c_int64, c_f64p, c_f64p, c_i64p, c_i64p]),
+    "fo_per_structure_factors": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p,
+                                                ctypes.c_int64, c_void_p]),
+    "fo_per_align_pairs": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
+                                          ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    "fo_per_align_pairs_dev": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p,
+                                              c_void_p, ctypes.c_int64, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p]),
+    "fo_per_align_coeffs": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
+                                           ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p]),
+    "fo_per_bank_create": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p,
+                                          ctypes.c_int64, ctypes.POINTER(c_void_p)]),
+    "fo_per_align_bank": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
+                                         ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p]),
+    "fo_bank_destroy": (None, [c_void_p, c_void_p]),
+    "fo_sph_isoft_argmax": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fo_sph_coeffs_direct": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                            c_void_p, c_void_p]),
+    "fo_sph_align_pairs": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                          ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    "fo_sph_align_pairs_dev": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                              ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p]),
+    "fo_sph_harm_coeffs": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                          ctypes.c_double, c_void_p, c_void_p]),
+    "fo_sph_bank_create": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                          ctypes.c_double, ctypes.POINTER(c_void_p)]),
+    "fo_sph_align_bank": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                         ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p]),
+    "fo_sph_wigner_table": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def library_path():
+    return _build.lib_path()
+
+
+def load_library():
+    """Load (building if absent and nvcc is available) the shared library. Fails loudly."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as exc:  # no nvcc, compile error ...
+                raise FastOverlapError(
+                    "libfastoverlap_b200.so is missing and could not be built (%s). "
+                    "Run `python -m fastoverlap_b200.build`. There is no CPU fallback." % exc)
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as exc:
+            raise FastOverlapError("cannot load %s: %s (no CPU fallback)" % (path, exc))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                raise FastOverlapError("%s does not export %s" % (path, name))
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Context(object):
+    """One fo_ctx: one per (host thread, GPU)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = c_void_p()
+        rc = self._lib.fo_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            msg = self._lib.fo_last_error(None)
+            raise FastOverlapError("fo_create(device=%d) failed: %s" %
+                                   (device, msg.decode() if msg else rc))
+        self._h = h
+        self.device = int(device)
+        self._perm_key = None
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.fo_last_error(self._h)
+            raise FastOverlapError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def sync(self):
+        self._check(self._lib.fo_sync(self._h), "fo_sync")
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.fo_set_stream(self._h, c_void_p(cuda_stream or 0)), "fo_set_stream")
+
+    def device_info(self):
+        out = np.zeros(4, np.int64)
+        self._check(self._lib.fo_device_info(self._h, out.ctypes.data_as(c_i64p)), "fo_device_info")
+        return {"sm_count": int(out[0]), "l2_bytes": int(out[1]), "smem_optin": int(out[2]),
+                "cc": int(out[3])}
+
+    def launch_count(self):
+        return int(self._lib.fo_launch_count(self._h))
+
+    def measure_fp64_peak(self):
+        v = ctypes.c_double()
+        self._check(self._lib.fo_measure_fp64_peak(self._h, ctypes.byref(v)), "fo_measure_fp64_peak")
+        return v.value
+
+    def set_perm(self, perm, natoms):
+        """perm: sequence of index arrays (0-based), as the reference's `perm`/`permlist`."""
+        groups = [np.asarray(p, dtype=np.int64).ravel() for p in perm]
+        key = (int(natoms), tuple(g.tobytes() for g in groups))
+        if key == self._perm_key:
+            return
+        off = np.zeros(len(groups) + 1, np.int32)
+        off[1:] = np.cumsum([len(g) for g in groups])
+        idx = (np.concatenate(groups) if groups else np.zeros(0, np.int64)).astype(np.int32)
+        if idx.size == 0:
+            idx = np.zeros(1, np.int32)
+        self._check(self._lib.fo_set_perm(self._h, _ptr(off), len(groups), _ptr(idx), int(natoms)),
+                    "fo_set_perm")
+        self._perm_key = key
+
+    # -- periodic
+    @staticmethod
+    def per_params(natoms, box, nwave, nfspace, sigma):
+        p = PerParams()
+        p.natoms = int(natoms)
+        b = np.asarray(box, dtype=float).ravel()
+        p.box[0], p.box[1], p.box[2] = float(b[0]), float(b[1]), float(b[2])
+        p.nwave = int(nwave)
+        p.nfspace = int(nfspace)
+        p.sigma = float(sigma)
+        return p
+
+    def per_structure_factors(self, params, pos):
+        pos = _f64(pos).reshape(-1, params.natoms, 3)
+        S = pos.shape[0]
+        W = 2 * params.nwave + 1
+        ng = len(self._perm_key[1]) if self._perm_key else 1
+        out = np.empty((S, ng, W, W, W), np.complex128)
+        self._check(self._lib.fo_per_structure_factors(self._h, ctypes.byref(params), _ptr(pos), S,
+                                                       _ptr(out)), "fo_per_structure_factors")
+        return out
+
+    def _per_outputs(self, P, F, want_grid, lead=()):
+        best_idx = np.empty(lead + (P, 3), np.int64)
+        best_val = np.empty(lead + (P,), np.float64)
+        frac = np.empty(lead + (P, 3), np.float64)
+        grid = np.empty((P, F, F, F), np.float64) if want_grid else None
+        status = np.zeros(P, np.int32)
+        return best_idx, best_val, frac, grid, status
+
+    def per_align_pairs(self, params, posA, posB, want_grid=False):
+        posA = _f64(posA).reshape(-1, params.natoms, 3)
+        posB = _f64(posB).reshape(-1, params.natoms, 3)
+        if posA.shape != posB.shape:
+            raise ValueError("posA and posB must have the same shape")
+        P = posA.shape[0]
+        bi, bv, fr, grid, st = self._per_outputs(P, params.nfspace, want_grid)
+        self._check(self._lib.fo_per_align_pairs(self._h, ctypes.byref(params), _ptr(posA),
+                                                 _ptr(posB), P, _ptr(bi), _ptr(bv), _ptr(fr),
+                                                 _ptr(grid), _ptr(st)), "fo_per_align_pairs")
+        return bi, bv, fr, grid, st
+
+    def per_align_pairs_dev(self, params, d_posA, d_posB, P, d_best_idx, d_best_val, d_frac,
+                            d_grid=0, d_status=0):
+        """All arguments are raw device addresses (ints); asynchronous on the ctx stream."""
+        self._check(self._lib.fo_per_align_pairs_dev(
+            self._h, ctypes.byref(params), c_void_p(d_posA), c_void_p(d_posB), int(P),
+            c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac), c_void_p(d_grid or 0),
+            c_void_p(d_status or 0)), "fo_per_align_pairs_dev")
+
+    def per_align_coeffs(self, params, CA, CB, want_grid=False):
+        W = 2 * params.nwave + 1
+        CA = np.ascontiguousarray(CA, dtype=np.complex128)
+        CB = np.ascontiguousarray(CB, dtype=np.complex128)
+        ng = len(self._perm_key[1]) if self._perm_key else 1
+        CA = CA.reshape(-1, ng, W, W, W)
+        CB = CB.reshape(-1, ng, W, W, W)
+        P = CA.shape[0]
+        bi, bv, fr, grid, st = self._per_outputs(P, params.nfspace, want_grid)
+        self._check(self._lib.fo_per_align_coeffs(self._h, ctypes.byref(params), _ptr(CA), _ptr(CB),
+                                                  P, _ptr(bi), _ptr(bv), _ptr(fr), _ptr(grid),
+                                                  _ptr(st)), "fo_per_align_coeffs")
+        return bi, bv, fr, grid, st
+
+    def per_bank_create(self, params, pos):
+        pos = _f64(pos).reshape(-1, params.natoms, 3)
+        h = c_void_p()
+        self._check(self._lib.fo_per_bank_create(self._h, ctypes.byref(params), _ptr(pos),
+                                                 pos.shape[0], ctypes.byref(h)),
+                    "fo_per_bank_create")
+        return Bank(self, h, pos.shape[0])
+
+    def per_align_bank(self, params, bank, pairs, want_grid=False):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        P = pairs.shape[0]
+        bi, bv, fr, grid, st = self._per_outputs(P, params.nfspace, want_grid)
+        self._check(self._lib.fo_per_align_bank(self._h, ctypes.byref(params), bank._h, _ptr(pairs),
+                                                P, _ptr(bi), _ptr(bv), _ptr(fr), _ptr(grid),
+                                                _ptr(st)), "fo_per_align_bank")
+        return bi, bv, fr, grid, st
+
+    # -- spherical
+    def sph_wigner_table(self, Jmax):
+        B = Jmax + 1
+        out = np.empty((B, 2 * B - 1, 2 * B - 1, 2 * B), np.float64)
+        self._check(self._lib.fo_sph_wigner_table(self._h, int(Jmax), _ptr(out)),
+                    "fo_sph_wigner_table")
+        return out
+
+    def _sph_outputs(self, P, Jmax, invert, want_grid):
+        O = 2 if invert else 1
+        n = 2 * (Jmax + 1)
+        bi = np.empty((P, O, 3), np.int64)
+        bv = np.empty((P, O), np.float64)
+        fr = np.empty((P, O, 3), np.float64)
+        grid = np.empty((P, O, n, n, n), np.float64) if want_grid else None
+        return bi, bv, fr, grid
+
+    def sph_isoft_argmax(self, Ilmm, Jmax, invert=False, want_grid=False):
+        L = int(Jmax)
+        Ilmm = np.ascontiguousarray(Ilmm, dtype=np.complex128).reshape(-1, L + 1, 2 * L + 1, 2 * L + 1)
+        P = Ilmm.shape[0]
+        bi, bv, fr, grid = self._sph_outputs(P, L, invert, want_grid)
+        self._check(self._lib.fo_sph_isoft_argmax(self._h, _ptr(Ilmm), P, L, int(bool(invert)),
+                                                  _ptr(bi), _ptr(bv), _ptr(fr), _ptr(grid)),
+                    "fo_sph_isoft_argmax")
+        return bi, bv, fr, grid
+
+    def sph_coeffs_direct(self, posA, posB, Jmax, sigma):
+        posA = _f64(posA)
+        posB = _f64(posB)
+        if posA.ndim == 2:
+            posA = posA[None]
+            posB = posB[None]
+        P, N, _ = posA.shape
+        L = int(Jmax)
+        out = np.empty((P, L + 1, 2 * L + 1, 2 * L + 1), np.complex128)
+        st = np.zeros(P, np.int32)
+        self._check(self._lib.fo_sph_coeffs_direct(self._h, _ptr(posA), _ptr(posB), P, N, L,
+                                                   float(sigma), _ptr(out), _ptr(st)),
+                    "fo_sph_coeffs_direct")
+        return out, st
+
+    def sph_align_pairs(self, posA, posB, Jmax, sigma, invert=True, want_grid=False):
+        posA = _f64(posA)
+        posB = _f64(posB)
+        if posA.ndim == 2:
+            posA = posA[None]
+            posB = posB[None]
+        P, N, _ = posA.shape
+        L = int(Jmax)
+        bi, bv, fr, grid = self._sph_outputs(P, L, invert, want_grid)
+        st = np.zeros(P, np.int32)
+        self._check(self._lib.fo_sph_align_pairs(self._h, _ptr(posA), _ptr(posB), P, N, L,
+                                                 float(sigma), int(bool(invert)), _ptr(bi), _ptr(bv),
+                                                 _ptr(fr), _ptr(grid), _ptr(st)),
+                    "fo_sph_align_pairs")
+        return bi, bv, fr, grid, st
+
+    def sph_align_pairs_dev(self, d_posA, d_posB, P, N, Jmax, sigma, invert, d_best_idx,
+                            d_best_val, d_frac, d_grid=0, d_status=0):
+        self._check(self._lib.fo_sph_align_pairs_dev(
+            self._h, c_void_p(d_posA), c_void_p(d_posB), int(P), int(N), int(Jmax), float(sigma),
+            int(bool(invert)), c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac),
+            c_void_p(d_grid or 0), c_void_p(d_status or 0)), "fo_sph_align_pairs_dev")
+
+    def sph_harm_coeffs(self, pos, nmax, Jmax, harmscale, sigma):
+        pos = _f64(pos)
+        if pos.ndim == 2:
+            pos = pos[None]
+        S, N, _ = pos.shape
+        ng = len(self._perm_key[1]) if self._perm_key and self._perm_key[0] == N else 1
+        L = int(Jmax)
+        out = np.empty((S, ng, nmax + 1, L + 1, 2 * L + 1), np.complex128)
+        st = np.zeros(S, np.int32)
+        self._check(self._lib.fo_sph_harm_coeffs(self._h, _ptr(pos), S, N, int(nmax), L,
+                                                 float(harmscale), float(sigma), _ptr(out), _ptr(st)),
+                    "fo_sph_harm_coeffs")
+        return out, st
+
+    def sph_bank_create(self, pos, nmax, Jmax, harmscale, sigma):
+        pos = _f64(pos)
+        if pos.ndim == 2:
+            pos = pos[None]
+        S, N, _ = pos.shape
+        h = c_void_p()
+        self._check(self._lib.fo_sph_bank_create(self._h, _ptr(pos), S, N, int(nmax), int(Jmax),
+                                                 float(harmscale), float(sigma), ctypes.byref(h)),
+                    "fo_sph_bank_create")
+        b = Bank(self, h, S)
+        b.Jmax = int(Jmax)
+        return b
+
+    def sph_align_bank(self, bank, pairs, invert=True, want_grid=False, want_avg=True):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        P = pairs.shape[0]
+        bi, bv, fr, grid = self._sph_outputs(P, bank.Jmax, invert, want_grid)
+        avg = np.empty(P, np.float64) if want_avg else None
+        self._check(self._lib.fo_sph_align_bank(self._h, bank._h, _ptr(pairs), P,
+                                                int(bool(invert)), _ptr(bi), _ptr(bv), _ptr(fr),
+                                                _ptr(avg), _ptr(grid)), "fo_sph_align_bank")
+        return bi, bv, fr, avg, grid
+
+
+class Bank(object):
+    """Device-resident coefficient bank (fo_bank)."""
+
+    def __init__(self, ctx, handle, nstruct):
+        self._ctx = ctx
+        self._h = handle
+        self.nstruct = nstruct
+
+    def close(self):
+        if self._h and self._ctx._h:
+            self._ctx._lib.fo_bank_destroy(self._ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device=None):
+    """Process-wide default Context per device (device from $FASTOVERLAP_DEVICE, LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("FASTOVERLAP_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        ctx = _default_ctx.get(device)
+        if ctx is None or ctx._h is None:
+            ctx = Context(device)
+            _default_ctx[device] = ctx
+        return ctx

@@ -1,0 +1,277 @@
+// Context, error handling, scratch memory, permutation groups, small utilities.
+#include <stdarg.h>
+#include <string.h>
+
+#include "fo_internal.h"
+
+static thread_local std::string g_create_err;
+
+int fo_fail(fo_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_create_err = buf;
+  // clear a sticky-free error so later calls are not poisoned by a recoverable failure
+  cudaGetLastError();
+  return code;
+}
+
+int fo_scratch(fo_ctx* ctx, int slot, size_t bytes, void** out) {
+  fo_devbuf& b = ctx->scratch[slot];
+  if (b.bytes < bytes) {
+    if (b.ptr) {
+      // work queued on the stream may still use the old buffer
+      FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      FO_CUDA(ctx, cudaFree(b.ptr));
+      b.ptr = nullptr;
+      b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+      b.ptr = nullptr;
+      return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want,
+                     cudaGetErrorString(e));
+    }
+    b.bytes = want;
+  }
+  *out = b.ptr;
+  return FO_OK;
+}
+
+int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out) {
+  fo_devbuf& b = ctx->pinned[slot];
+  if (b.bytes < bytes) {
+    if (b.ptr) {
+      FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      FO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+      FO_CUDA(ctx, cudaFreeHost(b.ptr));
+      b.ptr = nullptr;
+      b.bytes = 0;
+    }
+    size_t want = bytes + 256;
+    cudaError_t e = cudaMallocHost(&b.ptr, want);
+    if (e != cudaSuccess) {
+      b.ptr = nullptr;
+      return fo_fail(ctx, FO_ERR_NOMEM, "cudaMallocHost(%zu bytes) failed: %s", want,
+                     cudaGetErrorString(e));
+    }
+    b.bytes = want;
+  }
+  *out = b.ptr;
+  return FO_OK;
+}
+
+extern "C" int fo_create(int device, fo_ctx** out) {
+  if (!out) return fo_fail(nullptr, FO_ERR_INVALID, "fo_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fo_fail(nullptr, FO_ERR_CUDA,
+                   "fo_create: no usable CUDA device (%s); this library has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev)
+    return fo_fail(nullptr, FO_ERR_INVALID, "fo_create: device %d out of range (0..%d)", device,
+                   ndev - 1);
+  fo_ctx* ctx = new (std::nothrow) fo_ctx();
+  if (!ctx) return fo_fail(nullptr, FO_ERR_NOMEM, "fo_create: out of host memory");
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t err) {
+    int rc = fo_fail(nullptr, FO_ERR_CUDA, "fo_create: %s failed: %s", what, cudaGetErrorString(err));
+    delete ctx;
+    return rc;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess)
+    return bail("cudaGetDeviceProperties", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  for (int i = 0; i < 4; ++i)
+    if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess)
+      return bail("cudaEventCreate", e);
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return FO_OK;
+}
+
+extern "C" void fo_destroy(fo_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  for (auto& b : ctx->scratch)
+    if (b.ptr) cudaFree(b.ptr);
+  for (auto& b : ctx->pinned)
+    if (b.ptr) cudaFreeHost(b.ptr);
+  if (ctx->d_goff) cudaFree(ctx->d_goff);
+  if (ctx->d_gidx) cudaFree(ctx->d_gidx);
+  if (ctx->wig.d_table) cudaFree(ctx->wig.d_table);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+extern "C" const char* fo_last_error(const fo_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int fo_set_stream(fo_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return FO_OK;
+}
+
+extern "C" int fo_sync(fo_ctx* ctx) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FO_OK;
+}
+
+extern "C" int fo_device_info(fo_ctx* ctx, int64_t out[4]) {
+  if (!ctx || !out) return FO_ERR_INVALID;
+  out[0] = ctx->prop.multiProcessorCount;
+  out[1] = ctx->prop.l2CacheSize;
+  out[2] = (int64_t)ctx->prop.sharedMemPerBlockOptin;
+  out[3] = ctx->prop.major * 10 + ctx->prop.minor;
+  return FO_OK;
+}
+
+extern "C" int64_t fo_launch_count(const fo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fo_set_perm(fo_ctx* ctx, const int32_t* group_offsets, int64_t ngroups,
+                           const int32_t* atom_idx, int64_t natoms) {
+  if (!ctx) return FO_ERR_INVALID;
+  if (ngroups < 1 || !group_offsets || !atom_idx || natoms < 1)
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_set_perm: need >=1 group and natoms >= 1");
+  if (group_offsets[0] != 0)
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_set_perm: group_offsets[0] must be 0");
+  for (int64_t g = 0; g < ngroups; ++g)
+    if (group_offsets[g + 1] < group_offsets[g])
+      return fo_fail(ctx, FO_ERR_INVALID, "fo_set_perm: group_offsets must be non-decreasing");
+  int64_t total = group_offsets[ngroups];
+  for (int64_t i = 0; i < total; ++i)
+    if (atom_idx[i] < 0 || atom_idx[i] >= natoms)
+      return fo_fail(ctx, FO_ERR_INVALID, "fo_set_perm: atom index %d out of range [0,%lld)",
+                     atom_idx[i], (long long)natoms);
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_goff) cudaFree(ctx->d_goff);
+  if (ctx->d_gidx) cudaFree(ctx->d_gidx);
+  ctx->d_goff = nullptr;
+  ctx->d_gidx = nullptr;
+  ctx->h_goff.assign(group_offsets, group_offsets + ngroups + 1);
+  ctx->h_gidx.assign(atom_idx, atom_idx + total);
+  FO_CUDA(ctx, cudaMalloc(&ctx->d_goff, sizeof(int32_t) * (ngroups + 1)));
+  FO_CUDA(ctx, cudaMalloc(&ctx->d_gidx, sizeof(int32_t) * (total > 0 ? total : 1)));
+  FO_CUDA(ctx, cudaMemcpy(ctx->d_goff, ctx->h_goff.data(), sizeof(int32_t) * (ngroups + 1),
+                          cudaMemcpyHostToDevice));
+  if (total > 0)
+    FO_CUDA(ctx, cudaMemcpy(ctx->d_gidx, ctx->h_gidx.data(), sizeof(int32_t) * total,
+                            cudaMemcpyHostToDevice));
+  ctx->perm_natoms = natoms;
+  return FO_OK;
+}
+
+int fo_ensure_perm(fo_ctx* ctx, int64_t natoms) {
+  if (ctx->perm_natoms == natoms && ctx->d_goff) return FO_OK;
+  if (ctx->perm_natoms != 0 && ctx->perm_natoms != natoms && ctx->h_goff.size() > 2)
+    return fo_fail(ctx, FO_ERR_INVALID,
+                   "permutation groups were set for %lld atoms but the call has %lld atoms",
+                   (long long)ctx->perm_natoms, (long long)natoms);
+  // default: a single group containing every atom (reference: perm = [arange(N)])
+  std::vector<int32_t> off = {0, (int32_t)natoms};
+  std::vector<int32_t> idx(natoms);
+  for (int64_t i = 0; i < natoms; ++i) idx[i] = (int32_t)i;
+  return fo_set_perm(ctx, off.data(), 1, idx.data(), natoms);
+}
+
+// utils.py:278-313 (_next_fast_len); identical to the FASTLEN table fastutils.f90:78-90.
+extern "C" int64_t fo_next_fast_len(int64_t target) {
+  if (target <= 6) return target;
+  if ((target & (target - 1)) == 0) return target;
+  int64_t best = INT64_MAX;
+  for (int64_t p5 = 1; p5 < 2 * target; p5 *= 5) {
+    for (int64_t p35 = p5; p35 < 2 * target; p35 *= 3) {
+      int64_t v = p35;
+      while (v < target) v *= 2;
+      if (v < best) best = v;
+    }
+  }
+  return best;
+}
+
+extern "C" int fo_per_defaults(int64_t natoms, const double box[3], double* sigma,
+                               int64_t* nwave, int64_t* nfspace) {
+  if (natoms < 1 || !box) return FO_ERR_INVALID;
+  double v = box[0] * box[1] * box[2];
+  int64_t n = (int64_t)ceil(1.3 * pow((double)natoms, 1.0 / 3.0));
+  if (sigma) *sigma = pow(v / (double)natoms, 1.0 / 3.0) / 3.0;
+  if (nwave) *nwave = n;
+  if (nfspace) *nfspace = fo_next_fast_len(2 * (2 * n + 1) + 1);
+  return FO_OK;
+}
+
+// ------------------------------------------------------------------ FP64 peak microbenchmark
+// 8 independent FMA chains per thread, no memory traffic: measures the DFMA issue rate that
+// bounds every kernel of this library.
+__global__ void fo_fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+  double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b);
+      x1 = fma(x1, a, b);
+      x2 = fma(x2, a, b);
+      x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b);
+      x5 = fma(x5, a, b);
+      x6 = fma(x6, a, b);
+      x7 = fma(x7, a, b);
+    }
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+extern "C" int fo_measure_fp64_peak(fo_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return FO_ERR_INVALID;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* d_out = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, 256, &d_out));
+  cudaEvent_t e0, e1;
+  FO_CUDA(ctx, cudaEventCreate(&e0));
+  FO_CUDA(ctx, cudaEventCreate(&e1));
+  const int iters = 4096, threads = 512;
+  const int blocks = ctx->prop.multiProcessorCount * 4;
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 6; ++rep) {
+    FO_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    fo_fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)d_out, iters, 0.999999, 1e-9);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    FO_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    FO_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double flops = 2.0 * 64.0 * (double)iters * threads * (double)blocks;
+  *tflops = flops / (best_ms * 1e-3) / 1e12;
+  return FO_OK;
+}

@@ -1,0 +1,99 @@
+// Internal declarations shared by the translation units of libfastoverlap_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fastoverlap_b200.h"
+
+struct fo_devbuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+// Cached Wigner-d table for one bandwidth (device resident).
+struct fo_wigner_cache {
+  int64_t Jmax = -1;
+  double* d_table = nullptr;  // packed, see fo_spherical.cu
+  size_t bytes = 0;
+};
+
+struct fo_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;  // stream in use (own or external)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaDeviceProp prop;
+  std::string err;
+  int64_t launches = 0;
+
+  // permutation groups (host + device copies)
+  std::vector<int32_t> h_goff;  // [ngroups+1]
+  std::vector<int32_t> h_gidx;  // [natoms_in_groups]
+  int32_t* d_goff = nullptr;
+  int32_t* d_gidx = nullptr;
+  int64_t perm_natoms = 0;  // natoms the perm was declared for (0 = unset -> one group of all)
+
+  // growable device scratch (named slots)
+  fo_devbuf scratch[8];
+  // pinned host staging (named slots)
+  fo_devbuf pinned[6];
+
+  fo_wigner_cache wig;
+};
+
+enum {
+  FO_SCR_POSA = 0,
+  FO_SCR_POSB = 1,
+  FO_SCR_BANK = 2,
+  FO_SCR_OUT = 3,
+  FO_SCR_GRID = 4,
+  FO_SCR_WORK = 5,
+  FO_SCR_COEF = 6,
+  FO_SCR_MISC = 7,
+};
+
+struct fo_bank {
+  int kind = 0;  // 1 = periodic structure factors, 2 = spherical harmonic coefficients
+  int64_t nstruct = 0;
+  int64_t ngroups = 0;
+  int64_t per_struct_elems = 0;  // double2 elements per structure
+  // periodic
+  int64_t nwave = 0;
+  // spherical
+  int64_t nmax = 0, Jmax = 0, natoms = 0;
+  double sigma = 0, harmscale = 0;
+  double* d_data = nullptr;
+};
+
+int fo_fail(fo_ctx* ctx, int code, const char* fmt, ...);
+int fo_scratch(fo_ctx* ctx, int slot, size_t bytes, void** out);
+int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out);
+// make sure a permutation (at least the trivial one) exists for natoms atoms
+int fo_ensure_perm(fo_ctx* ctx, int64_t natoms);
+
+#define FO_CUDA(ctx, call)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return fo_fail((ctx), FO_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__,     \
+                     __LINE__, cudaGetErrorString(_e));                                 \
+  } while (0)
+
+#define FO_CHECK(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != FO_OK) return _rc; \
+  } while (0)
+
+#define FO_LAUNCH_CHECK(ctx)                                                            \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      return fo_fail((ctx), FO_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, \
+                     __LINE__, cudaGetErrorString(_e));                                 \
+  } while (0)

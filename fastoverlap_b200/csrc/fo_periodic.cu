@@ -1,0 +1,971 @@
+// Periodic hot path (replaces reference fastoverlap/f90/fastbulk.f90 ALIGN1/ALIGNCOEFFS up to
+// FINDPEAKS and fastoverlap/periodicAlignment.py:384-456).
+//
+//   K_sf  per_sf_kernel   structure factors S_g(k) = sum_{j in g} exp(-i k.r_j)
+//                         (PERIODICFOURIER fastbulk.f90:599-633, calcFourierCoeff
+//                         periodicAlignment.py:400-406)
+//   K_xf  per_xf_kernel   C(k) = sum_g S^A_g conj(S^B_g) exp(-k^2 sigma^2)      (setPos :437-438,
+//                         DOTFOURIERCOEFFS fastbulk.f90:667-683), zero-padded forward 3-D DFT
+//                         to F^3 (fftn :439, FFT3D fastutils.f90:554-569), modulus, arg-max and
+//                         findMax's parabola (utils.py:319-338) -- fused, the F^3 grid never
+//                         leaves the SM unless the caller asks for it.
+//
+// Data layout in HBM ("bank"): per structure and permutation group the HALF grid
+//   S[ix][iy][l]   ix,iy = 0..2n (k = ix-n, iy-n), l = 0..n (kz >= 0), complex128,
+// because S(-k) = conj(S(k)).  All arithmetic is FP64.
+#include <math.h>
+
+#include "fo_internal.h"
+
+namespace {
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// ------------------------------------------------------------------------------------------
+// K_sf: structure factors.
+//
+// exp(-i k.r) factorises per axis; with c = cos(m theta), s = sin(m theta) for m = 0..n the
+// (2n+1)^3 complex sums reduce to 8 REAL sums over (|kx|,|ky|,|kz|) in [0,n]^3:
+//   S(rho i, sig j, l) = [ccc - rho sig ssc - sig css - rho scs]
+//                      + i[-sig csc - rho scc - ccs + rho sig sss]
+// (names: x,y,z factor each c or s).  A thread owns one (i,j) and TL consecutive l: per atom
+// 4 DMUL + 8*TL DFMA against 2+TL 16-byte shared loads.  This is 4x fewer flops than the
+// complex accumulation over the full grid that the reference performs.
+// ------------------------------------------------------------------------------------------
+constexpr int SF_TA = 64;  // atoms per shared-memory tile
+
+template <int TL>
+__global__ void __launch_bounds__(512)
+per_sf_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
+              const int32_t* __restrict__ gidx, int ngroups, int natoms, int n, double kx,
+              double ky, double kz, double2* __restrict__ bank, int nitems) {
+  extern __shared__ double2 sm_ph[];
+  const int M = n + 1;
+  const int Mp = M | 1;           // odd row pitch: conflict-free 16 B accesses
+  const int LC = (M + TL - 1) / TL;
+  const int Mz = (LC * TL) | 1;   // z rows are zero padded up to LC*TL
+  double2* phx = sm_ph;
+  double2* phy = phx + SF_TA * Mp;
+  double2* phz = phy + SF_TA * Mp;
+
+  const int s = blockIdx.x;
+  const int g = blockIdx.y;
+  const int item = blockIdx.z * blockDim.x + threadIdx.x;
+  const bool active = item < nitems;
+  int lc = 0, j = 0, i = 0;
+  if (active) {
+    lc = item % LC;
+    j = (item / LC) % M;
+    i = item / (LC * M);
+  }
+  const int l0 = lc * TL;
+  const int a_begin = goff[g], a_end = goff[g + 1];
+  const double* spos = pos + (size_t)s * natoms * 3;
+  const double kax[3] = {kx, ky, kz};
+
+  double acc[TL][8];
+#pragma unroll
+  for (int t = 0; t < TL; ++t)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[t][q] = 0.0;
+
+  for (int a0 = a_begin; a0 < a_end; a0 += SF_TA) {
+    const int ta = min(SF_TA, a_end - a0);
+    __syncthreads();
+    // phasor tables: one thread per (atom, axis); powers by complex recurrence
+    for (int t = threadIdx.x; t < 3 * ta; t += blockDim.x) {
+      const int a = t / 3, ax = t - 3 * a;
+      const int atom = gidx[a0 + a];
+      const double th = kax[ax] * spos[atom * 3 + ax];
+      double sn, cs;
+      sincos(th, &sn, &cs);
+      const int pitch = (ax == 2) ? Mz : Mp;
+      double2* row = (ax == 0 ? phx : (ax == 1 ? phy : phz)) + a * pitch;
+      double c = 1.0, sv = 0.0;
+      row[0] = make_double2(1.0, 0.0);
+      for (int m = 1; m <= n; ++m) {
+        const double cn = c * cs - sv * sn;
+        const double snn = sv * cs + c * sn;
+        c = cn;
+        sv = snn;
+        row[m] = make_double2(c, sv);
+      }
+      if (ax == 2)
+        for (int m = M; m < Mz; ++m) row[m] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (active) {
+      const double2* px = phx + i;
+      const double2* py = phy + j;
+      const double2* pz = phz + l0;
+#pragma unroll 2
+      for (int a = 0; a < ta; ++a) {
+        const double2 X = px[a * Mp];
+        const double2 Y = py[a * Mp];
+        const double cc = X.x * Y.x, cs = X.x * Y.y, sc = X.y * Y.x, ss = X.y * Y.y;
+#pragma unroll
+        for (int t = 0; t < TL; ++t) {
+          const double2 Z = pz[a * Mz + t];
+          acc[t][0] = fma(cc, Z.x, acc[t][0]);  // ccc
+          acc[t][1] = fma(cc, Z.y, acc[t][1]);  // ccs
+          acc[t][2] = fma(cs, Z.x, acc[t][2]);  // csc
+          acc[t][3] = fma(cs, Z.y, acc[t][3]);  // css
+          acc[t][4] = fma(sc, Z.x, acc[t][4]);  // scc
+          acc[t][5] = fma(sc, Z.y, acc[t][5]);  // scs
+          acc[t][6] = fma(ss, Z.x, acc[t][6]);  // ssc
+          acc[t][7] = fma(ss, Z.y, acc[t][7]);  // sss
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const int W = 2 * n + 1;
+  double2* out = bank + ((size_t)s * ngroups + g) * ((size_t)W * W * M);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {      // rho = +1, -1
+    if (r == 1 && i == 0) continue;
+    const double rho = r ? -1.0 : 1.0;
+    const int ix = n + (r ? -i : i);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {    // sig = +1, -1
+      if (q == 1 && j == 0) continue;
+      const double sig = q ? -1.0 : 1.0;
+      const int iy = n + (q ? -j : j);
+      double2* o = out + ((size_t)ix * W + iy) * M + l0;
+#pragma unroll
+      for (int t = 0; t < TL; ++t) {
+        if (l0 + t < M) {
+          const double re = acc[t][0] - rho * sig * acc[t][6] - sig * acc[t][3] - rho * acc[t][5];
+          const double im = -sig * acc[t][2] - rho * acc[t][4] - acc[t][1] + rho * sig * acc[t][7];
+          o[t] = make_double2(re, im);
+        }
+      }
+    }
+  }
+}
+
+// Expand the half-grid bank to the reference's full (2n+1)^3 layout (calcFourierCoeff output).
+__global__ void per_expand_kernel(const double2* __restrict__ bank, double2* __restrict__ full,
+                                  int n, size_t nsg) {
+  const int W = 2 * n + 1, M = n + 1;
+  const size_t per = (size_t)W * W * W;
+  const size_t total = nsg * per;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const size_t sg = e / per;
+    int r = (int)(e - sg * per);
+    const int iz = r % W;
+    r /= W;
+    const int iy = r % W;
+    const int ix = r / W;
+    const double2* b = bank + sg * ((size_t)W * W * M);
+    double2 v;
+    if (iz >= n) {
+      v = b[((size_t)ix * W + iy) * M + (iz - n)];
+    } else {
+      v = b[((size_t)(2 * n - ix) * W + (2 * n - iy)) * M + (n - iz)];
+      v.y = -v.y;
+    }
+    full[e] = v;
+  }
+}
+
+// Inverse: take the kz >= 0 half of caller-supplied full-grid coefficients (Cs= hook).
+__global__ void per_compress_kernel(const double2* __restrict__ full, double2* __restrict__ bank,
+                                    int n, size_t nsg) {
+  const int W = 2 * n + 1, M = n + 1;
+  const size_t per = (size_t)W * W * M;
+  const size_t total = nsg * per;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const size_t sg = e / per;
+    int r = (int)(e - sg * per);
+    const int l = r % M;
+    r /= M;
+    const int iy = r % W;
+    const int ix = r / W;
+    bank[e] = full[sg * ((size_t)W * W * W) + ((size_t)ix * W + iy) * W + (n + l)];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K_xf: cross-spectrum + pruned, symmetry-reduced 3-D DFT + |.| + arg-max + parabola.
+//
+//   f[d] = sum_k C[k] exp(-2 pi i (k_idx . d)/F),  k_idx = k + n  (reference: the k=-n corner
+//   sits at index 0)  =>  f[d] = phase(d) * g[d],  g[d] = sum_k C[k] w^(k.d) REAL
+//   because C(-k) = conj(C(k)); the reference only uses |f| = |g|.
+//
+// Stages (all in shared memory; T = trig table of 2 pi t/F):
+//   X  U[dx][iy][l] = sum_mx C[mx][iy][l] w^(mx dx)          (2n+1 -> F, complex)
+//   per slab dx (one group of XF_GT threads each):
+//   Y  V[dy][l]     = sum_my U[dx][my][l] w^(my dy)          (2n+1 -> F, complex)
+//   Z  g[dy][dz]    = V[dy][0] + 2 sum_{l>=1} Re(V[dy][l] w^(l dz))   (n+1 complex -> F real)
+// Each 1-D transform uses the +-m pairing (E = c_m + c_-m with cos, O = c_m - c_-m with sin) so
+// that outputs d and F-d share all products: a quarter of the dense-DFT flops, same order as a
+// radix FFT at these lengths, with no bit reversal and exact handling of any F.
+// ------------------------------------------------------------------------------------------
+constexpr int XF_THREADS = 512;
+constexpr int XF_NG = 4;                       // slab groups
+constexpr int XF_GT = XF_THREADS / XF_NG;      // threads per slab group
+constexpr int XF_DCX = 11;                     // outputs per thread, stage X
+constexpr int XF_DCY = 3;                      // stage Y
+constexpr int XF_DCZ = 7;                      // stage Z
+
+struct XfOut {
+  long long* best_idx;  // [P,3]
+  double* best_val;     // [P]
+  double* frac_idx;     // [P,3]
+  double* grid;         // [P,F,F,F] or null
+  int* status;          // [P] or null
+};
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(XF_GT) : "memory");
+}
+
+__device__ __forceinline__ void better(double& bv, long long& bi, double v, long long i) {
+  if (v > bv || (v == bv && i < bi)) {
+    bv = v;
+    bi = i;
+  }
+}
+
+__global__ void __launch_bounds__(XF_THREADS, 1)
+per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ bankB,
+              const long long* __restrict__ pairs,  // [P,2] or null (then pair p = (p, p))
+              int npairs, int ngroups, int n, int F, double kx, double ky, double kz, double sigma,
+              double2* __restrict__ gscratch,  // null: C and U live in shared memory
+              XfOut out) {
+  extern __shared__ double2 sm[];
+  const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
+  const int WM = W * M;        // lines of stage X
+  const int H = F / 2 + 1;     // outputs d = 0..F/2, partner F-d
+  const size_t c_elems = (size_t)W * WM, u_elems = (size_t)F * WM;
+  // shared layout: tw[F] | damp[3W doubles -> ceil] | V[NG][F*Mp] | red | (C | U)
+  double2* tw = sm;
+  double* damp = (double*)(tw + F);
+  double2* Vall = (double2*)(damp + ((3 * W + 1) & ~1));
+  double* red = (double*)(Vall + (size_t)XF_NG * F * Mp);  // 64 doubles of reduction scratch
+  double2* C;
+  double2* U;
+  if (gscratch) {
+    C = gscratch + (size_t)blockIdx.x * (c_elems + u_elems);
+    U = C + c_elems;
+  } else {
+    C = (double2*)(red + 64);
+    U = C + c_elems;
+  }
+  const int tid = threadIdx.x;
+  const int grp = tid / XF_GT, gtid = tid - grp * XF_GT;
+  double2* V = Vall + (size_t)grp * F * Mp;
+
+  for (int t = tid; t < F; t += XF_THREADS) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+    tw[t] = make_double2(cs, sn);
+  }
+  for (int t = tid; t < 3 * W; t += XF_THREADS) {
+    const int ax = t / W, m = t - ax * W - n;
+    const double k = (ax == 0 ? kx : (ax == 1 ? ky : kz)) * (double)m;
+    damp[t] = exp(-(k * k) * (sigma * sigma));
+  }
+  __syncthreads();
+
+  const size_t bank_stride = (size_t)ngroups * c_elems;
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const long long ia = pairs ? pairs[2 * pair] : pair;
+    const long long ib = pairs ? pairs[2 * pair + 1] : pair;
+    const double2* SA = bankA + (size_t)ia * bank_stride;
+    const double2* SB = bankB + (size_t)ib * bank_stride;
+    // ---- cross spectrum C = sum_g SA conj(SB) * damp
+    for (int e = tid; e < (int)c_elems; e += XF_THREADS) {
+      double re = 0.0, im = 0.0;
+      for (int g = 0; g < ngroups; ++g) {
+        const double2 a = SA[(size_t)g * c_elems + e];
+        const double2 b = SB[(size_t)g * c_elems + e];
+        re += a.x * b.x + a.y * b.y;
+        im += a.y * b.x - a.x * b.y;
+      }
+      const int l = e % M;
+      const int r = e / M;
+      const int iy = r % W, ix = r / W;
+      const double dmp = damp[ix] * damp[W + iy] * damp[2 * W + n + l];
+      C[e] = make_double2(re * dmp, im * dmp);
+    }
+    __syncthreads();
+    // ---- stage X: lines = (iy,l), item = (line, chunk of XF_DCX outputs)
+    {
+      const int nch = (H + XF_DCX - 1) / XF_DCX;
+      for (int item = tid; item < WM * nch; item += XF_THREADS) {
+        const int line = item % WM, ch = item / WM;
+        const int d0 = ch * XF_DCX;
+        const double2* cin = C + line;
+        const double2 c0 = cin[(size_t)n * WM];
+        double2 P[XF_DCX], Q[XF_DCX];
+        int idx[XF_DCX];
+#pragma unroll
+        for (int t = 0; t < XF_DCX; ++t) {
+          P[t] = c0;
+          Q[t] = make_double2(0.0, 0.0);
+          idx[t] = 0;
+        }
+        for (int m = 1; m <= n; ++m) {
+          const double2 a = cin[(size_t)(n + m) * WM], b = cin[(size_t)(n - m) * WM];
+          const double2 E = cadd(a, b), O = csub(a, b);
+#pragma unroll
+          for (int t = 0; t < XF_DCX; ++t) {
+            int k = idx[t] + d0 + t;
+            k -= (k >= F) ? F : 0;
+            idx[t] = k;
+            const double2 w = tw[k];
+            P[t].x = fma(E.x, w.x, P[t].x);
+            P[t].y = fma(E.y, w.x, P[t].y);
+            Q[t].x = fma(O.x, w.y, Q[t].x);
+            Q[t].y = fma(O.y, w.y, Q[t].y);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < XF_DCX; ++t) {
+          const int d = d0 + t;
+          if (d < H) {
+            U[(size_t)d * WM + line] = make_double2(P[t].x + Q[t].y, P[t].y - Q[t].x);
+            if (d != 0 && 2 * d != F)
+              U[(size_t)(F - d) * WM + line] = make_double2(P[t].x - Q[t].y, P[t].y + Q[t].x);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- slabs: group grp takes dx = grp, grp + NG, ...
+    double bv = -1.0;
+    long long bi = 0x7fffffffffffffffLL;
+    const int nslab_iter = (F + XF_NG - 1) / XF_NG;
+    for (int it = 0; it < nslab_iter; ++it) {
+      const int dx = it * XF_NG + grp;
+      if (dx < F) {
+        const double2* Us = U + (size_t)dx * WM;
+        // stage Y: lines l, input over iy (stride M), output V[dy][l]
+        const int nchy = (H + XF_DCY - 1) / XF_DCY;
+        for (int item = gtid; item < M * nchy; item += XF_GT) {
+          const int l = item % M, ch = item / M;
+          const int d0 = ch * XF_DCY;
+          const double2* cin = Us + l;
+          const double2 c0 = cin[(size_t)n * M];
+          double2 P[XF_DCY], Q[XF_DCY];
+          int idx[XF_DCY];
+#pragma unroll
+          for (int t = 0; t < XF_DCY; ++t) {
+            P[t] = c0;
+            Q[t] = make_double2(0.0, 0.0);
+            idx[t] = 0;
+          }
+          for (int m = 1; m <= n; ++m) {
+            const double2 a = cin[(size_t)(n + m) * M], b = cin[(size_t)(n - m) * M];
+            const double2 E = cadd(a, b), O = csub(a, b);
+#pragma unroll
+            for (int t = 0; t < XF_DCY; ++t) {
+              int k = idx[t] + d0 + t;
+              k -= (k >= F) ? F : 0;
+              idx[t] = k;
+              const double2 w = tw[k];
+              P[t].x = fma(E.x, w.x, P[t].x);
+              P[t].y = fma(E.y, w.x, P[t].y);
+              Q[t].x = fma(O.x, w.y, Q[t].x);
+              Q[t].y = fma(O.y, w.y, Q[t].y);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < XF_DCY; ++t) {
+            const int d = d0 + t;
+            if (d < H) {
+              V[(size_t)d * Mp + l] = make_double2(P[t].x + Q[t].y, P[t].y - Q[t].x);
+              if (d != 0 && 2 * d != F)
+                V[(size_t)(F - d) * Mp + l] = make_double2(P[t].x - Q[t].y, P[t].y + Q[t].x);
+            }
+          }
+        }
+      }
+      group_sync(grp);
+      if (dx < F) {
+        // stage Z (complex half-line -> real line), fused with |.| and the running arg-max
+        const int nchz = (H + XF_DCZ - 1) / XF_DCZ;
+        for (int item = gtid; item < F * nchz; item += XF_GT) {
+          const int dy = item % F, ch = item / F;
+          const int d0 = ch * XF_DCZ;
+          const double2* vin = V + (size_t)dy * Mp;
+          const double v0 = vin[0].x;
+          double A[XF_DCZ], B[XF_DCZ];
+          int idx[XF_DCZ];
+#pragma unroll
+          for (int t = 0; t < XF_DCZ; ++t) {
+            A[t] = 0.0;
+            B[t] = 0.0;
+            idx[t] = 0;
+          }
+          for (int l = 1; l <= n; ++l) {
+            const double2 v = vin[l];
+#pragma unroll
+            for (int t = 0; t < XF_DCZ; ++t) {
+              int k = idx[t] + d0 + t;
+              k -= (k >= F) ? F : 0;
+              idx[t] = k;
+              const double2 w = tw[k];
+              A[t] = fma(v.x, w.x, A[t]);
+              B[t] = fma(v.y, w.y, B[t]);
+            }
+          }
+          const long long base = ((long long)dx * F + dy) * F;
+          double* grow = out.grid ? out.grid + ((size_t)pair * F * F * F + (size_t)base) : nullptr;
+#pragma unroll
+          for (int t = 0; t < XF_DCZ; ++t) {
+            const int d = d0 + t;
+            if (d < H) {
+              const double a = v0 + 2.0 * A[t], b = 2.0 * B[t];
+              const double g1 = fabs(a + b);
+              better(bv, bi, g1, base + d);
+              if (grow) grow[d] = g1;
+              if (d != 0 && 2 * d != F) {
+                const double g2 = fabs(a - b);
+                better(bv, bi, g2, base + (F - d));
+                if (grow) grow[F - d] = g2;
+              }
+            }
+          }
+        }
+      }
+      group_sync(grp);
+    }
+    // ---- block arg-max (numpy order: first flat index on exact ties)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+      better(bv, bi, ov, oi);
+    }
+    long long* redi = (long long*)(red + 32);
+    if ((tid & 31) == 0) {
+      red[tid >> 5] = bv;
+      redi[tid >> 5] = bi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      bv = (tid < XF_THREADS / 32) ? red[tid] : -1.0;
+      bi = (tid < XF_THREADS / 32) ? redi[tid] : 0x7fffffffffffffffLL;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+        better(bv, bi, ov, oi);
+      }
+      if (tid == 0) {
+        red[0] = bv;
+        redi[0] = bi;
+      }
+    }
+    __syncthreads();
+    bv = red[0];
+    bi = redi[0];
+    const bool ok = (bi != 0x7fffffffffffffffLL) && isfinite(bv);
+    const int bx = ok ? (int)(bi / ((long long)F * F)) : 0;
+    const int by = ok ? (int)((bi / F) % F) : 0;
+    const int bz = ok ? (int)(bi % F) : 0;
+    __syncthreads();
+    // ---- findMax parabola: the six periodic neighbours, evaluated from U (utils.py:327-337)
+    {
+      const int w = tid >> 5, lane = tid & 31;
+      if (w < 6) {
+        const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;  // w even: +1 neighbour, odd: -1
+        int px = bx, py = by, pz = bz;
+        if (ax == 0) px = (bx + sgn + F) % F;
+        if (ax == 1) py = (by + sgn + F) % F;
+        if (ax == 2) pz = (bz + sgn + F) % F;
+        const double2* Us = U + (size_t)px * WM;
+        double acc = 0.0;
+        for (int e = lane; e < WM; e += 32) {
+          const int l = e % M, iy = e / M;
+          int k = ((iy - n) * py + l * pz) % F;
+          k += (k < 0) ? F : 0;
+          const double2 wv = tw[k];
+          const double2 u = Us[e];
+          const double term = u.x * wv.x + u.y * wv.y;
+          acc += (l == 0) ? term : 2.0 * term;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) red[2 + w] = fabs(acc);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      out.best_idx[3 * (size_t)pair + 0] = bx;
+      out.best_idx[3 * (size_t)pair + 1] = by;
+      out.best_idx[3 * (size_t)pair + 2] = bz;
+      out.best_val[pair] = bv;
+      const int b3[3] = {bx, by, bz};
+      for (int ax = 0; ax < 3; ++ax) {
+        const double y1 = red[2 + 2 * ax], y3 = red[2 + 2 * ax + 1], y2 = bv;
+        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
+      }
+      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
+    }
+    __syncthreads();
+  }
+}
+
+size_t xf_smem_bytes(int n, int F, bool with_grids) {
+  const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
+  size_t b = (size_t)F * 16;                       // tw
+  b += (size_t)((3 * W + 1) & ~1) * 8;             // damp
+  b += (size_t)XF_NG * F * Mp * 16;                // V
+  b += 64 * 8;                                     // red
+  if (with_grids) b += ((size_t)W * W * M + (size_t)F * W * M) * 16;
+  return b;
+}
+
+int check_params(fo_ctx* ctx, const fo_per_params* p) {
+  if (!ctx) return FO_ERR_INVALID;
+  if (!p) return fo_fail(ctx, FO_ERR_INVALID, "params is NULL");
+  if (p->natoms < 1) return fo_fail(ctx, FO_ERR_INVALID, "natoms must be >= 1");
+  if (p->nwave < 1 || p->nwave > 64)
+    return fo_fail(ctx, FO_ERR_UNSUPPORTED, "nwave=%lld outside supported range 1..64",
+                   (long long)p->nwave);
+  if (p->nfspace < 2 * p->nwave + 1 || p->nfspace > 1024)
+    return fo_fail(ctx, FO_ERR_INVALID, "nfspace=%lld must be in [2*nwave+1, 1024]",
+                   (long long)p->nfspace);
+  if (!(p->sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "sigma must be > 0");
+  for (int i = 0; i < 3; ++i)
+    if (!(p->box[i] > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "box lengths must be > 0");
+  return FO_OK;
+}
+
+// Launch K_sf for nstruct structures (device positions) into bank.
+int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t nstruct,
+              double2* d_bank) {
+  if (nstruct == 0) return FO_OK;
+  const int n = (int)p->nwave, M = n + 1;
+  const int ngroups = (int)ctx->h_goff.size() - 1;
+  // TL = 5 gives the best FMA : (mul + load) ratio when it divides n+1 well, else TL = 2.
+  const int waste5 = ((M + 4) / 5) * 5 - M, waste2 = ((M + 1) / 2) * 2 - M;
+  const bool use5 = (waste5 * 2 <= M / 5 + waste2 * 2) || (waste5 == 0);
+  const int TL = use5 ? 5 : 2;
+  const int LC = (M + TL - 1) / TL;
+  const int nitems = M * M * LC;
+  int threads = ((nitems + 31) / 32) * 32;
+  const int max_threads = use5 ? 256 : 512;
+  if (threads > max_threads) threads = max_threads;
+  const int nblk = (nitems + threads - 1) / threads;
+  const int Mp = M | 1, Mz = (LC * TL) | 1;
+  const size_t smem = (size_t)SF_TA * (2 * Mp + Mz) * 16;
+  const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  // gridDim.x carries the structures (up to 2^31-1)
+  dim3 grid((unsigned)nstruct, (unsigned)ngroups, (unsigned)nblk);
+  if (use5) {
+    FO_CUDA(ctx, cudaFuncSetAttribute(per_sf_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    per_sf_kernel<5><<<grid, threads, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
+                                                           (int)p->natoms, n, kx, ky, kz, d_bank,
+                                                           nitems);
+  } else {
+    FO_CUDA(ctx, cudaFuncSetAttribute(per_sf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    per_sf_kernel<2><<<grid, threads, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
+                                                           (int)p->natoms, n, kx, ky, kz, d_bank,
+                                                           nitems);
+  }
+  FO_LAUNCH_CHECK(ctx);
+  return FO_OK;
+}
+
+int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const double2* d_bankB,
+              const long long* d_pairs, int64_t npairs, XfOut out) {
+  if (npairs == 0) return FO_OK;
+  const int n = (int)p->nwave, F = (int)p->nfspace;
+  const int ngroups = (int)ctx->h_goff.size() - 1;
+  const size_t optin = ctx->prop.sharedMemPerBlockOptin;
+  size_t smem = xf_smem_bytes(n, F, true);
+  double2* gscratch = nullptr;
+  int blocks = ctx->prop.multiProcessorCount;
+  if ((int64_t)blocks > npairs) blocks = (int)npairs;
+  if (smem > optin) {
+    smem = xf_smem_bytes(n, F, false);
+    if (smem > optin)
+      return fo_fail(ctx, FO_ERR_UNSUPPORTED,
+                     "nwave=%d nfspace=%d needs %zu bytes of shared memory (> %zu)", n, F, smem,
+                     optin);
+    const int W = 2 * n + 1, M = n + 1;
+    const size_t per_cta = ((size_t)W * W * M + (size_t)F * W * M) * 16;
+    void* ptr = nullptr;
+    FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, per_cta * blocks, &ptr));
+    gscratch = (double2*)ptr;
+  }
+  FO_CUDA(ctx, cudaFuncSetAttribute(per_xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  per_xf_kernel<<<blocks, XF_THREADS, smem, ctx->stream>>>(d_bankA, d_bankB, d_pairs, (int)npairs,
+                                                           ngroups, n, F, kx, ky, kz, p->sigma,
+                                                           gscratch, out);
+  FO_LAUNCH_CHECK(ctx);
+  return FO_OK;
+}
+
+size_t bank_elems_per_struct(fo_ctx* ctx, const fo_per_params* p) {
+  const size_t W = 2 * p->nwave + 1, M = p->nwave + 1;
+  return (ctx->h_goff.size() - 1) * W * W * M;
+}
+
+// pairs per chunk: bounded by a bank budget, a multiple of the SM count where possible
+int64_t chunk_pairs(fo_ctx* ctx, const fo_per_params* p, int64_t npairs, bool want_grid) {
+  const size_t per_pair = 2 * bank_elems_per_struct(ctx, p) * 16;
+  size_t budget = (size_t)768 << 20;
+  int64_t c = (int64_t)(budget / per_pair);
+  if (want_grid) {
+    const size_t g = (size_t)p->nfspace * p->nfspace * p->nfspace * 8;
+    int64_t cg = (int64_t)(((size_t)512 << 20) / g);
+    if (cg < c) c = cg;
+  }
+  const int sms = ctx->prop.multiProcessorCount;
+  if (c > sms) c = (c / sms) * sms;
+  if (c < 1) c = 1;
+  if (c > npairs) c = npairs;
+  return c;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+
+extern "C" int fo_per_align_pairs_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA,
+                                      const double* d_posB, int64_t npairs, int64_t* d_best_idx,
+                                      double* d_best_val, double* d_frac_idx, double* d_grid_out,
+                                      int32_t* d_status) {
+  FO_CHECK(check_params(ctx, p));
+  if (npairs < 0 || (npairs > 0 && (!d_posA || !d_posB || !d_best_idx || !d_best_val || !d_frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs_dev: NULL argument");
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, p->natoms));
+  const size_t per_struct = bank_elems_per_struct(ctx, p);
+  const int64_t chunk = chunk_pairs(ctx, p, npairs, false);
+  void* bank = nullptr;
+  if (npairs > 0) FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
+  double2* bankA = (double2*)bank;
+  double2* bankB = bankA + (size_t)chunk * per_struct;
+  const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    FO_CHECK(launch_sf(ctx, p, d_posA + (size_t)p0 * p->natoms * 3, np, bankA));
+    FO_CHECK(launch_sf(ctx, p, d_posB + (size_t)p0 * p->natoms * 3, np, bankB));
+    XfOut out;
+    out.best_idx = (long long*)d_best_idx + 3 * p0;
+    out.best_val = d_best_val + p0;
+    out.frac_idx = d_frac_idx + 3 * p0;
+    out.grid = d_grid_out ? d_grid_out + (size_t)p0 * F3 : nullptr;
+    out.status = d_status ? d_status + p0 : nullptr;
+    FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+  }
+  return FO_OK;
+}
+
+namespace {
+// Shared host-buffer driver: `stage(p0, np)` must enqueue whatever fills bankA/bankB for pairs
+// [p0, p0+np) and return the (bankA, bankB, d_pairs) to use.
+struct HostOut {
+  int64_t* best_idx;
+  double* best_val;
+  double* frac_idx;
+  double* grid_out;
+  int32_t* status;
+};
+
+int copy_out(fo_ctx* ctx, const fo_per_params* p, int64_t p0, int64_t np, const char* d_out,
+             const double* d_grid, const HostOut& h) {
+  // d_out layout per chunk: best_idx[np*3] i64 | best_val[np] | frac[np*3] | status[np] i32
+  const size_t o_idx = 0, o_val = (size_t)np * 24, o_frac = o_val + (size_t)np * 8,
+               o_st = o_frac + (size_t)np * 24;
+  FO_CUDA(ctx, cudaMemcpyAsync(h.best_idx + 3 * p0, d_out + o_idx, (size_t)np * 24,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  FO_CUDA(ctx, cudaMemcpyAsync(h.best_val + p0, d_out + o_val, (size_t)np * 8,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  FO_CUDA(ctx, cudaMemcpyAsync(h.frac_idx + 3 * p0, d_out + o_frac, (size_t)np * 24,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  if (h.status)
+    FO_CUDA(ctx, cudaMemcpyAsync(h.status + p0, d_out + o_st, (size_t)np * 4,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  if (h.grid_out) {
+    const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
+    FO_CUDA(ctx, cudaMemcpyAsync(h.grid_out + (size_t)p0 * F3, d_grid, (size_t)np * F3 * 8,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return FO_OK;
+}
+
+XfOut make_out(char* d_out, int64_t np, double* d_grid, bool want_status) {
+  XfOut o;
+  o.best_idx = (long long*)d_out;
+  o.best_val = (double*)(d_out + (size_t)np * 24);
+  o.frac_idx = (double*)(d_out + (size_t)np * 32);
+  o.status = want_status ? (int*)(d_out + (size_t)np * 56) : nullptr;
+  o.grid = d_grid;
+  return o;
+}
+}  // namespace
+
+extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const double* posA,
+                                  const double* posB, int64_t npairs, int64_t* best_idx,
+                                  double* best_val, double* frac_idx, double* grid_out,
+                                  int32_t* status) {
+  FO_CHECK(check_params(ctx, p));
+  if (npairs < 0 || (npairs > 0 && (!posA || !posB || !best_idx || !best_val || !frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, p->natoms));
+  const size_t per_struct = bank_elems_per_struct(ctx, p);
+  const int64_t chunk = chunk_pairs(ctx, p, npairs, grid_out != nullptr);
+  const size_t pos_bytes = (size_t)chunk * p->natoms * 3 * 8;
+  const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
+  void *bank, *dA, *dB, *dOut, *dGrid = nullptr, *hA, *hB;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
+  // two position buffers per side so the copy of chunk c+1 overlaps the kernels of chunk c
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, 2 * pos_bytes, &dA));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
+  if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
+  FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
+  FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
+  double2* bankA = (double2*)bank;
+  double2* bankB = bankA + (size_t)chunk * per_struct;
+  HostOut h = {best_idx, best_val, frac_idx, grid_out, status};
+  const int64_t nchunks = (npairs + chunk - 1) / chunk;
+  // pipeline: [host memcpy -> pinned] -> H2D on copy_stream -> kernels + D2H on stream
+  auto stage_in = [&](int64_t c) -> int {
+    const int64_t p0 = c * chunk;
+    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    const int buf = (int)(c & 1);
+    const size_t nb = (size_t)np * p->natoms * 3 * 8;
+    // the pinned buffer `buf` was last read by the H2D of chunk c-2
+    if (c >= 2) FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[buf]));
+    memcpy((char*)hA + buf * pos_bytes, posA + (size_t)p0 * p->natoms * 3, nb);
+    memcpy((char*)hB + buf * pos_bytes, posB + (size_t)p0 * p->natoms * 3, nb);
+    // device buffer `buf` was last read by the kernels of chunk c-2
+    if (c >= 2) FO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2 + buf], 0));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dA + buf * pos_bytes, (char*)hA + buf * pos_bytes, nb,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dB + buf * pos_bytes, (char*)hB + buf * pos_bytes, nb,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
+    return FO_OK;
+  };
+  FO_CHECK(stage_in(0));
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t p0 = c * chunk;
+    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    const int buf = (int)(c & 1);
+    if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
+    FO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[buf], 0));
+    FO_CHECK(launch_sf(ctx, p, (const double*)((char*)dA + buf * pos_bytes), np, bankA));
+    FO_CHECK(launch_sf(ctx, p, (const double*)((char*)dB + buf * pos_bytes), np, bankB));
+    FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+    XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
+    FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+    FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
+  }
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FO_OK;
+}
+
+extern "C" int fo_per_structure_factors(fo_ctx* ctx, const fo_per_params* p, const double* pos,
+                                        int64_t nstruct, double* out) {
+  FO_CHECK(check_params(ctx, p));
+  if (nstruct < 0 || (nstruct > 0 && (!pos || !out)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_structure_factors: NULL argument");
+  if (nstruct == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, p->natoms));
+  const size_t per_struct = bank_elems_per_struct(ctx, p);
+  const size_t ng = ctx->h_goff.size() - 1;
+  const size_t W = 2 * p->nwave + 1;
+  const size_t full_per_struct = ng * W * W * W;
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full_per_struct * 16));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nstruct) chunk = nstruct;
+  void *bank, *dpos, *dfull;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * per_struct * 16, &bank));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * p->natoms * 24, &dpos));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * full_per_struct * 16, &dfull));
+  for (int64_t s0 = 0; s0 < nstruct; s0 += chunk) {
+    const int64_t ns = (nstruct - s0 < chunk) ? nstruct - s0 : chunk;
+    FO_CUDA(ctx, cudaMemcpyAsync(dpos, pos + (size_t)s0 * p->natoms * 3, (size_t)ns * p->natoms * 24,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    FO_CHECK(launch_sf(ctx, p, (const double*)dpos, ns, (double2*)bank));
+    const size_t total = (size_t)ns * full_per_struct;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 65535) blocks = 65535;
+    per_expand_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2*)bank, (double2*)dfull,
+                                                       (int)p->nwave, (size_t)ns * ng);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CUDA(ctx, cudaMemcpyAsync(out + (size_t)s0 * full_per_struct * 2, dfull, total * 16,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_per_align_coeffs(fo_ctx* ctx, const fo_per_params* p, const double* CA,
+                                   const double* CB, int64_t npairs, int64_t* best_idx,
+                                   double* best_val, double* frac_idx, double* grid_out,
+                                   int32_t* status) {
+  FO_CHECK(check_params(ctx, p));
+  if (npairs < 0 || (npairs > 0 && (!CA || !CB || !best_idx || !best_val || !frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_coeffs: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, p->natoms));
+  const size_t per_struct = bank_elems_per_struct(ctx, p);
+  const size_t ng = ctx->h_goff.size() - 1;
+  const size_t W = 2 * p->nwave + 1;
+  const size_t full_per_struct = ng * W * W * W;
+  const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full_per_struct * 32));
+  if (grid_out) {
+    int64_t cg = (int64_t)(((size_t)512 << 20) / (F3 * 8));
+    if (cg < chunk) chunk = cg;
+  }
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *bank, *dfull, *dOut, *dGrid = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, 2 * (size_t)chunk * full_per_struct * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
+  if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
+  double2* bankA = (double2*)bank;
+  double2* bankB = bankA + (size_t)chunk * per_struct;
+  double2* fullA = (double2*)dfull;
+  double2* fullB = fullA + (size_t)chunk * full_per_struct;
+  HostOut h = {best_idx, best_val, frac_idx, grid_out, status};
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    FO_CUDA(ctx, cudaMemcpyAsync(fullA, CA + (size_t)p0 * full_per_struct * 2,
+                                 (size_t)np * full_per_struct * 16, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(fullB, CB + (size_t)p0 * full_per_struct * 2,
+                                 (size_t)np * full_per_struct * 16, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    const size_t total = (size_t)np * per_struct;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 65535) blocks = 65535;
+    per_compress_kernel<<<blocks, 256, 0, ctx->stream>>>(fullA, bankA, (int)p->nwave, (size_t)np * ng);
+    FO_LAUNCH_CHECK(ctx);
+    per_compress_kernel<<<blocks, 256, 0, ctx->stream>>>(fullB, bankB, (int)p->nwave, (size_t)np * ng);
+    FO_LAUNCH_CHECK(ctx);
+    XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
+    FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+    FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_per_bank_create(fo_ctx* ctx, const fo_per_params* p, const double* pos,
+                                  int64_t nstruct, fo_bank** out) {
+  FO_CHECK(check_params(ctx, p));
+  if (!out || nstruct < 1 || !pos)
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_bank_create: bad argument");
+  *out = nullptr;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, p->natoms));
+  fo_bank* b = new (std::nothrow) fo_bank();
+  if (!b) return fo_fail(ctx, FO_ERR_NOMEM, "out of host memory");
+  b->kind = 1;
+  b->nstruct = nstruct;
+  b->ngroups = (int64_t)ctx->h_goff.size() - 1;
+  b->nwave = p->nwave;
+  b->natoms = p->natoms;
+  b->per_struct_elems = (int64_t)bank_elems_per_struct(ctx, p);
+  cudaError_t e = cudaMalloc(&b->d_data, (size_t)nstruct * b->per_struct_elems * 16);
+  if (e != cudaSuccess) {
+    delete b;
+    return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the structure-factor bank failed: %s",
+                   cudaGetErrorString(e));
+  }
+  int64_t chunk = (int64_t)(((size_t)64 << 20) / ((size_t)p->natoms * 24));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nstruct) chunk = nstruct;
+  void* dpos;
+  int rc = fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * p->natoms * 24, &dpos);
+  for (int64_t s0 = 0; rc == FO_OK && s0 < nstruct; s0 += chunk) {
+    const int64_t ns = (nstruct - s0 < chunk) ? nstruct - s0 : chunk;
+    cudaError_t ce = cudaMemcpyAsync(dpos, pos + (size_t)s0 * p->natoms * 3,
+                                     (size_t)ns * p->natoms * 24, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce != cudaSuccess) {
+      rc = fo_fail(ctx, FO_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(ce));
+      break;
+    }
+    rc = launch_sf(ctx, p, (const double*)dpos, ns,
+                   (double2*)b->d_data + (size_t)s0 * b->per_struct_elems);
+    if (rc == FO_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      rc = fo_fail(ctx, FO_ERR_CUDA, "structure-factor kernel failed");
+  }
+  if (rc != FO_OK) {
+    cudaFree(b->d_data);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return FO_OK;
+}
+
+extern "C" int fo_per_align_bank(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank,
+                                 const int64_t* pairs, int64_t npairs, int64_t* best_idx,
+                                 double* best_val, double* frac_idx, double* grid_out,
+                                 int32_t* status) {
+  FO_CHECK(check_params(ctx, p));
+  if (!bank || bank->kind != 1) return fo_fail(ctx, FO_ERR_INVALID, "not a periodic bank");
+  if (bank->nwave != p->nwave || bank->ngroups != (int64_t)ctx->h_goff.size() - 1)
+    return fo_fail(ctx, FO_ERR_INVALID, "bank was built with different nwave / perm groups");
+  if (npairs < 0 || (npairs > 0 && (!pairs || !best_idx || !best_val || !frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_bank: NULL argument");
+  for (int64_t i = 0; i < 2 * npairs; ++i)
+    if (pairs[i] < 0 || pairs[i] >= bank->nstruct)
+      return fo_fail(ctx, FO_ERR_INVALID, "pair index %lld out of range", (long long)pairs[i]);
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
+  int64_t chunk = 1 << 16;
+  if (grid_out) {
+    chunk = (int64_t)(((size_t)512 << 20) / (F3 * 8));
+    if (chunk < 1) chunk = 1;
+  }
+  if (chunk > npairs) chunk = npairs;
+  void *dOut, *dGrid = nullptr, *dPairs;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 16, &dPairs));
+  if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
+  HostOut h = {best_idx, best_val, frac_idx, grid_out, status};
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    FO_CUDA(ctx, cudaMemcpyAsync(dPairs, pairs + 2 * p0, (size_t)np * 16, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
+    FO_CHECK(launch_xf(ctx, p, (const double2*)bank->d_data, (const double2*)bank->d_data,
+                       (const long long*)dPairs, np, out));
+    FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+extern "C" void fo_bank_destroy(fo_ctx* ctx, fo_bank* bank) {
+  if (!bank) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (bank->d_data) cudaFree(bank->d_data);
+  delete bank;
+}

@@ -1,0 +1,217 @@
+/*
+ * fastoverlap_b200 -- C ABI of the B200-native FASTOVERLAP overlap-maximisation hot path.
+ *
+ * This header is the drop-in boundary.  It replaces the f2py
+ * extension modules of the reference (fastoverlap/f90/__init__.py:3-21):
+ *
+ *   fastbulk.bulkfastoverlap.*      (reference fastoverlap/f90/fastbulk.f90)
+ *   fastclusters.clusterfastoverlap.* (reference fastoverlap/f90/fastclusters.f90, DSOFT.f90)
+ *   *.fastoverlaputils.setperm      (reference fastoverlap/f90/fastutils.f90:117-167)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  No torch / numpy types.
+ *   - all reals are double, complex numbers are interleaved (re, im) doubles,
+ *     arrays are row-major (C order) exactly as numpy lays the reference's arrays out.
+ *   - the caller owns every buffer passed in; the library never frees caller memory.
+ *   - every function returns FO_OK (0) or a negative error code; the message is
+ *     available from fo_last_error().  Nothing ever calls exit/abort (the reference
+ *     Fortran STOPs the interpreter, fastclusters.f90:1112-1165).
+ *   - no hidden global state (the reference keeps module-level SAVE state,
+ *     fastutils.f90:70-75, DSOFT.f90:32-34): everything lives in an fo_ctx.
+ *   - one fo_ctx per (host thread, GPU).  Calls on one ctx must not overlap in time.
+ *   - functions whose name ends in _dev take DEVICE pointers, are enqueued on the
+ *     context's stream and return without synchronising (call fo_sync()).
+ *     All other functions take HOST pointers and return with results in place.
+ *   - there is NO CPU fallback: if no CUDA device is usable fo_create fails.
+ */
+#ifndef FASTOVERLAP_B200_H
+#define FASTOVERLAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FO_OK 0
+#define FO_ERR_INVALID -1   /* bad argument */
+#define FO_ERR_CUDA -2      /* CUDA runtime error (message has the detail) */
+#define FO_ERR_NOMEM -3     /* host or device allocation failed */
+#define FO_ERR_UNSUPPORTED -4 /* size outside what the kernels support */
+
+/* per-pair status bits (written to the optional status[] outputs) */
+#define FO_STATUS_OK 0
+#define FO_STATUS_NONFINITE 1   /* a coordinate or result was NaN/Inf */
+#define FO_STATUS_ATOM_AT_ORIGIN 2 /* spherical: r == 0 (the reference yields NaN: utils.py:444) */
+
+typedef struct fo_ctx fo_ctx;
+typedef struct fo_bank fo_bank; /* device-resident coefficient bank (structure factors or C_nlm) */
+
+/* ---------------------------------------------------------------- context */
+
+/* Create a context on CUDA device `device`.  Fails (FO_ERR_CUDA) when no GPU is usable. */
+int fo_create(int device, fo_ctx** out);
+void fo_destroy(fo_ctx* ctx);
+/* Message of the last error on this ctx (or of the last failed fo_create when ctx==NULL). */
+const char* fo_last_error(const fo_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work.
+ * Pass NULL to return to the context's own stream. */
+int fo_set_stream(fo_ctx* ctx, void* cuda_stream);
+int fo_sync(fo_ctx* ctx);
+/* Library / device facts: writes {sm_count, l2_bytes, smem_per_block_optin, cc_major*10+cc_minor}. */
+int fo_device_info(fo_ctx* ctx, int64_t out[4]);
+/* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
+int64_t fo_launch_count(const fo_ctx* ctx);
+
+/* Permutation groups: the atoms of group g are atom_idx[group_offsets[g] .. group_offsets[g+1]).
+ * 0-based.  Replaces fastoverlaputils.setperm(natoms, permgroup(1-based), npermsize)
+ * (reference fastutils.f90:117-167; called from sphericalAlignment.py:483,
+ * periodicAlignment.py:523).  Held per ctx, not globally. */
+int fo_set_perm(fo_ctx* ctx, const int32_t* group_offsets, int64_t ngroups,
+                const int32_t* atom_idx, int64_t natoms);
+
+/* 5-smooth FFT length >= target: utils.py:278-313 (_next_fast_len) == FASTLEN table
+ * fastutils.f90:78-90. */
+int64_t fo_next_fast_len(int64_t target);
+
+/* Measured FP64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA
+ * microbenchmark kernel; used as the roofline denominator because MEASURED_PEAKS.json
+ * has no FP64 figure). */
+int fo_measure_fp64_peak(fo_ctx* ctx, double* tflops);
+
+/* ---------------------------------------------------------------- periodic (fastbulk) */
+
+/* Geometry of a periodic problem.  natoms atoms in an orthorhombic box; k-grid
+ * k = 2*pi/box * (-nwave..nwave)^3 (reference SETWAVEK fastbulk.f90:567-597,
+ * periodicAlignment.py:384-386); displacement grid nfspace^3; Gaussian width sigma
+ * (`scale` / KWIDTH). */
+typedef struct fo_per_params {
+  int64_t natoms;
+  double box[3];
+  int64_t nwave;    /* n  : k index runs -n..n           */
+  int64_t nfspace;  /* F  : FFT length per axis, F >= 2(2n+1)+1 is what the reference uses */
+  double sigma;     /* kernel width                         */
+} fo_per_params;
+
+/* Defaults of the reference for (natoms, box): sigma = (V/N)^(1/3)/3, nwave =
+ * ceil(1.3 N^(1/3)), nfspace = next_fast_len(4 nwave + 3)
+ * (periodicAlignment.py:375-378,391-392; ALIGN fastbulk.f90:296-315). */
+int fo_per_defaults(int64_t natoms, const double box[3], double* sigma, int64_t* nwave,
+                    int64_t* nfspace);
+
+/* Structure factors S[s, g, kx, ky, kz] = sum_{j in group g} exp(-i k.r_j) on the full
+ * (2n+1)^3 grid, index 0 = k=-n, for S structures.  out is [S, ngroups, W, W, W, 2]
+ * doubles, W = 2n+1.  Replaces PeriodicAlign.calcFourierCoeff (periodicAlignment.py:400-406)
+ * / PERIODICFOURIERPERM (fastbulk.f90:635-665).  Uses the ctx permutation groups. */
+int fo_per_structure_factors(fo_ctx* ctx, const fo_per_params* p, const double* pos /*[S,N,3]*/,
+                             int64_t nstruct, double* out);
+
+/* The whole periodic hot path for P independent pairs, host buffers:
+ *   structure factors of posA[i], posB[i]  ->  C = sum_g S_A conj(S_B) exp(-k^2 sigma^2)
+ *   -> zero-padded forward 3-D DFT to F^3 -> modulus -> arg-max (+ parabolic refinement).
+ * Replaces PeriodicAlign.setPos + findDisps(npeaks=1) (periodicAlignment.py:408-456)
+ * / ALIGN1 + ALIGNCOEFFS up to FINDPEAKS (fastbulk.f90:414-531).
+ *   best_idx [P,3] int64 : arg-max index (dx,dy,dz), first in C order on exact ties (numpy argmax)
+ *   best_val [P]         : fabs at the arg-max
+ *   frac_idx [P,3]       : findMax()'s parabolically interpolated index (utils.py:319-338)
+ *   grid_out [P,F,F,F]   : optional (may be NULL) full |f| grid, = PeriodicAlign.fabs
+ *   status   [P] int32   : optional (may be NULL) FO_STATUS_* bits per pair
+ * displacement = frac_idx * box / F (periodicAlignment.py:455). */
+int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const double* posA /*[P,N,3]*/,
+                       const double* posB /*[P,N,3]*/, int64_t npairs, int64_t* best_idx,
+                       double* best_val, double* frac_idx, double* grid_out, int32_t* status);
+
+/* Same, all pointers are DEVICE pointers, enqueued on the ctx stream, no synchronisation.
+ * (bench.py `value`: inputs resident in HBM.) */
+int fo_per_align_pairs_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA,
+                           const double* d_posB, int64_t npairs, int64_t* d_best_idx,
+                           double* d_best_val, double* d_frac_idx, double* d_grid_out,
+                           int32_t* d_status);
+
+/* Same path starting from caller-supplied structure factors (the reference's
+ * `Cs=[c1,c2]` hook, periodicAlignment.py:408-432,458-460): CA, CB are
+ * [P, ngroups, W, W, W, 2] as produced by fo_per_structure_factors.  Only the kz>=0 half
+ * is read (structure factors of real densities are Hermitian). */
+int fo_per_align_coeffs(fo_ctx* ctx, const fo_per_params* p, const double* CA, const double* CB,
+                        int64_t npairs, int64_t* best_idx, double* best_val, double* frac_idx,
+                        double* grid_out, int32_t* status);
+
+/* Device-resident bank of structure factors for S structures (all-vs-all use:
+ * PeriodicAlign.alignGroup periodicAlignment.py:462-479 / ALIGNGROUP fastbulk.f90:336-412
+ * compute coefficients once per structure). */
+int fo_per_bank_create(fo_ctx* ctx, const fo_per_params* p, const double* pos /*[S,N,3]*/,
+                       int64_t nstruct, fo_bank** out);
+/* pairs [P,2] int64 = (index of structure A, index of structure B) into the bank. */
+int fo_per_align_bank(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank,
+                      const int64_t* pairs, int64_t npairs, int64_t* best_idx, double* best_val,
+                      double* frac_idx, double* grid_out, int32_t* status);
+void fo_bank_destroy(fo_ctx* ctx, fo_bank* bank);
+
+/* ---------------------------------------------------------------- spherical (fastclusters) */
+
+/* Inverse SO(3) Fourier transform + arg-max for P coefficient sets, host buffers.
+ * Ilmm is [P, L+1, 2L+1, 2L+1, 2] doubles in the reference's numpy layout (negative m stored
+ * at index m + 2L+1, i.e. python negative-index wrap; soft.py:115-125).
+ *   grid[a,k,g] = sum_l sum_{m1,m2} sqrt((2l+1)/2) d^l_{m1m2}(beta_k) I^l_{m1m2} e^{i(m1 a + m2 g) 2pi/2B}
+ * with B = L+1, beta_k = pi(2k+1)/4B (the weighted grid of the reference).
+ * Replaces SOFT.iSOFT + findMax (soft.py:115-125, utils.py:319-338) / CALCOVERLAP + ISOFT +
+ * FINDROTATIONS arg-max (fastclusters.f90:918-988, DSOFT.f90:265-329).
+ *   invert != 0 : also evaluate the inverted orientation I_inv^l = (-1)^l I^l
+ *                 (fastclusters.f90:351-353; sphericalAlignment.py:370); outputs then have
+ *                 a leading orientation axis of length 2 (0 = normal, 1 = inverted).
+ *   best_idx [P,O,3] int64, best_val [P,O], frac_idx [P,O,3], grid_out [P,O,2B,2B,2B] or NULL.
+ * Euler angles = frac_idx * (2pi/2B, pi/2B, 2pi/2B) + (0, pi/4B, 0)  (soft.py:127-130). */
+int fo_sph_isoft_argmax(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax, int invert,
+                        int64_t* best_idx, double* best_val, double* frac_idx, double* grid_out);
+
+/* Direct (N^2 Bessel) SO(3) coefficients of P pairs of already-centred structures:
+ *   I[l,m1,m2] = 4 pi^2.5 sigma^3 sum_g sum_{j,k in g} i_l(r_j r_k / 2 sigma^2)
+ *                exp(-(r_j^2+r_k^2)/4 sigma^2) Y_lm1(A_j) conj(Y_lm2(B_k))
+ * Replaces SphericalAlign.calcSO3Coeffs summed over perm groups
+ * (sphericalAlignment.py:175,260-273) / FOURIERCOEFFS (fastclusters.f90:868-916) WITHOUT the
+ * Fortran-only 4 sigma pair cut-off.  Ilmm_out [P, L+1, 2L+1, 2L+1, 2]. */
+int fo_sph_coeffs_direct(fo_ctx* ctx, const double* posA /*[P,N,3]*/, const double* posB,
+                         int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
+                         double* Ilmm_out, int32_t* status);
+
+/* The whole spherical hot path (direct coefficients) for P pairs of centred structures:
+ * coefficients -> iSOFT -> arg-max for the normal and (invert!=0) inverted orientation.
+ * Replaces BaseSphericalAlignment.align up to findMax (sphericalAlignment.py:160-194) /
+ * ALIGN up to FINDROTATIONS (fastclusters.f90:129-269).  Outputs as fo_sph_isoft_argmax. */
+int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                       int64_t natoms, int64_t Jmax, double sigma, int invert, int64_t* best_idx,
+                       double* best_val, double* frac_idx, double* grid_out, int32_t* status);
+int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
+                           int64_t npairs, int64_t natoms, int64_t Jmax, double sigma, int invert,
+                           int64_t* d_best_idx, double* d_best_val, double* d_frac_idx,
+                           double* d_grid_out, int32_t* d_status);
+
+/* Harmonic-basis coefficients C[s, g, n, l, m] = sum_{j in g} d_nl(r_j; sigma, r0) conj(Y_lm(r_j))
+ * for S centred structures; out [S, ngroups, nmax+1, L+1, 2L+1, 2] (numpy layout, negative m
+ * wrapped).  Replaces SphericalHarmonicAlign.calcHarmCoeff (sphericalAlignment.py:345-361) /
+ * HARMONICCOEFFSPERM (fastclusters.f90:689-716). */
+int fo_sph_harm_coeffs(fo_ctx* ctx, const double* pos /*[S,N,3]*/, int64_t nstruct, int64_t natoms,
+                       int64_t nmax, int64_t Jmax, double harmscale, double sigma, double* out,
+                       int32_t* status);
+
+/* Device-resident bank of harmonic coefficients + the all-vs-all / pair-list overlap search:
+ *   I[l,m1,m2] = sum_g sum_n conj(C_A[g,n,l,m1]) C_B[g,n,l,m2]   (calcSO3Harm
+ *   sphericalAlignment.py:363-372 / DOTHARMONICCOEFFSPERM fastclusters.f90:765-788)
+ * -> iSOFT -> arg-max, for both orientations when invert != 0.
+ * avg_overlap [P] (may be NULL) = sum |I_lmm'|^2 as CALCSIMILARITY (fastclusters.f90:790-818). */
+int fo_sph_bank_create(fo_ctx* ctx, const double* pos /*[S,N,3]*/, int64_t nstruct,
+                       int64_t natoms, int64_t nmax, int64_t Jmax, double harmscale, double sigma,
+                       fo_bank** out);
+int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs /*[P,2]*/,
+                      int64_t npairs, int invert, int64_t* best_idx, double* best_val,
+                      double* frac_idx, double* avg_overlap, double* grid_out);
+
+/* Wigner-d table of the reference's SOFT object: Ds[l, m1, m2, k] = sqrt((2l+1)/2)
+ * d^l_{m1m2}(beta_k), out [B, 2B-1, 2B-1, 2B] doubles, negative m wrapped modulo 2B-1
+ * (soft.py:73-96, CALCWIGNERD DSOFT.f90:121-195).  Computed on the device. */
+int fo_sph_wigner_table(fo_ctx* ctx, int64_t Jmax, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTOVERLAP_B200_H */

@@ -1,0 +1,182 @@
+"""GPU parity of the periodic hot path: CUDA (through the C ABI) vs golden vectors from the
+unmodified reference and vs the C oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): overlap grids within 1e-10 relative (to the grid max),
+identical best grid index, final distance after the same host permutation step within 1e-8.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden, groups_from
+
+pytestmark = pytest.mark.gpu
+
+GRID_RTOL = 1e-10
+DIST_ATOL = 1e-8
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(b).max()
+
+
+def test_blj256_structure_factors(ctx):
+    from fastoverlap_b200 import PeriodicAlign
+    g = golden("periodic_blj256.npz")
+    al = PeriodicAlign(256, g["box"], [np.arange(204), np.arange(204, 256)], ctx=ctx)
+    assert al.n == int(g["n"]) and al.fshape == (int(g["F"]),) * 3
+    assert abs(al.scale - float(g["scale"])) < 1e-15
+    C1 = al.calcFourierCoeff(g["pos1"])
+    assert C1.shape == g["C1"].shape
+    assert rel(C1, g["C1"]) < 1e-13
+
+
+def test_blj256_grid_argmax_distance(ctx):
+    from fastoverlap_b200 import PeriodicAlign
+    g = golden("periodic_blj256.npz")
+    al = PeriodicAlign(256, g["box"], [np.arange(204), np.arange(204, 256)], ctx=ctx)
+    dist, X1, X2, perm, disp = al(g["pos1"], g["pos2"])
+    assert rel(al.fabs, g["fabs"]) < GRID_RTOL
+    assert tuple(np.unravel_index(al.fabs.argmax(), al.fabs.shape)) == (10, 38, 32)
+    assert tuple(al._best_idx) == (10, 38, 32)
+    assert abs(al._best_val - 55419.12238387397) < 1e-10 * 55419.0
+    assert np.allclose(al._frac_idx, g["findmax"], atol=1e-8)
+    assert abs(dist - 1.5590835031549872) < DIST_ATOL
+    assert abs(dist - float(g["dist"])) < DIST_ATOL
+    assert np.array_equal(np.asarray(perm), g["perm"])
+    assert np.allclose(disp, g["disp"], atol=1e-8)
+    # precomputed-coefficient hook (examples/alignPeriodic.py:35-42 "quickAlign")
+    c1, c2 = al.calcFourierCoeff(g["pos1"]), al.calcFourierCoeff(g["pos2"])
+    d2 = al.align(g["pos1"], g["pos2"], [c1, c2])[0]
+    assert abs(d2 - dist) < 1e-12
+    # and with the reference's own coefficients
+    d3 = al.align(g["pos1"], g["pos2"], [g["C1"], g["C2"]])[0]
+    assert abs(d3 - float(g["dist"])) < DIST_ATOL
+
+
+def test_synthetic_cases_vs_reference_golden(ctx):
+    from fastoverlap_b200 import PeriodicAlign
+    g = golden("periodic_synth.npz")
+    for i in range(int(g["ncases"])):
+        k = "c%d_" % i
+        perm = groups_from(g[k + "groups"], g[k + "gsizes"])
+        N = len(g[k + "pos1"])
+        al = PeriodicAlign(N, g[k + "box"], perm, scale=float(g[k + "scale"]), n=int(g[k + "n"]), ctx=ctx)
+        assert al.fshape[0] == int(g[k + "F"])
+        dist, X1, X2, p, disp = al(g[k + "pos1"], g[k + "pos2"])
+        assert rel(al.fabs, g[k + "fabs"]) < GRID_RTOL, i
+        assert tuple(al._best_idx) == tuple(g[k + "argmax"]), i
+        assert np.allclose(al._frac_idx, g[k + "findmax"], atol=1e-8), i
+        assert abs(dist - float(g[k + "dist"])) < DIST_ATOL, i
+        assert rel(al.calcFourierCoeff(g[k + "pos1"]), g[k + "C1"]) < 1e-13, i
+
+
+def _random_pairs(rng, P, N, box, jitter=0.05):
+    pos1 = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
+    shift = rng.uniform(0, 1, size=(P, 1, 3)) * box
+    pos2 = pos1 + shift + rng.normal(scale=jitter, size=(P, N, 3))
+    return pos1, pos2, shift[:, 0, :]
+
+
+@pytest.mark.parametrize("N,n,groups", [(17, 3, None), (40, 6, [23, 17]), (64, 9, [50, 14]),
+                                         (33, 11, None), (5, 1, None)])
+def test_batch_vs_oracle(ctx, N, n, groups):
+    """Seeded random batches: every pair's grid, arg-max and interpolated maximum vs the oracle."""
+    from fastoverlap_b200 import PeriodicAlign
+    rng = np.random.default_rng(1000 + N)
+    box = np.array([4.0, 4.5, 5.1])
+    perm = None
+    if groups:
+        o = np.cumsum([0] + groups)
+        perm = [np.arange(o[i], o[i + 1]) for i in range(len(groups))]
+    P = 7
+    pos1, pos2, _ = _random_pairs(rng, P, N, box)
+    al = PeriodicAlign(N, box, perm, n=n, ctx=ctx)
+    F = al.fshape[0]
+    p = al._params()
+    bi, bv, fr, grids, st = ctx.per_align_pairs(p, pos1, pos2, want_grid=True)
+    obi, obv, ofr, ogrids, _ = oracle.per_align_pairs(pos1, pos2, box, n, F, al.scale, perm,
+                                                      want_grid=True)
+    assert np.all(st == 0)
+    for i in range(P):
+        assert rel(grids[i], ogrids[i]) < GRID_RTOL
+    assert np.array_equal(bi, obi)
+    assert np.allclose(bv, obv, rtol=1e-12)
+    assert np.allclose(fr, ofr, atol=1e-7)
+    # results without the grid output are identical (the grid is only a side output)
+    bi2, bv2, fr2, _, _ = ctx.per_align_pairs(p, pos1, pos2)
+    assert np.array_equal(bi, bi2) and np.array_equal(bv, bv2) and np.array_equal(fr, fr2)
+
+
+def test_translation_recovery_full_size(ctx):
+    """Size-independent property at BASELINE size (N=256, n=9, F=40): a pure translation plus a
+    permutation within species is recovered; the overlap peak sits at the translation."""
+    from fastoverlap_b200 import PeriodicAlign
+    g = golden("periodic_blj256.npz")
+    rng = np.random.default_rng(256)
+    box = g["box"]
+    perm = [np.arange(204), np.arange(204, 256)]
+    P = 300  # > one chunk of SMs, exercises the persistent loop
+    base = g["pos1"]
+    shift = rng.uniform(0, 1, size=(P, 3)) * box
+    pos2 = np.empty((P, 256, 3))
+    for i in range(P):
+        order = np.concatenate([rng.permutation(204), 204 + rng.permutation(52)])
+        pos2[i] = (base + shift[i])[order]
+    pos1 = np.broadcast_to(base, pos2.shape).copy()
+    al = PeriodicAlign(256, box, perm, ctx=ctx)
+    disps, bi, bv = al.findDisps_batch(pos1, pos2)
+    err = disps - shift
+    err -= np.round(err / box) * box
+    assert np.abs(err).max() < 0.02 * box[0] / 40 * 40 / 10  # well inside one grid cell
+    # self-overlap value: peak equals sum_k |S|^2 damp of the structure (same for every pair)
+    assert np.ptp(bv) / bv.mean() < 1e-3
+    dists, out_disp, perms = al.align_batch(pos1[:5], pos2[:5])
+    assert np.all(dists < 1e-6)
+
+
+def test_all_vs_all_bank_matches_pairs(ctx):
+    from fastoverlap_b200 import PeriodicAlign
+    rng = np.random.default_rng(5)
+    N, box = 24, np.array([3.3, 3.3, 3.3])
+    coords = rng.uniform(-0.5, 0.5, size=(5, N, 3)) * box
+    al = PeriodicAlign(N, box, ctx=ctx)
+    p = al._params()
+    bank = ctx.per_bank_create(p, coords)
+    pairs = np.array([(i, j) for i in range(5) for j in range(5)])
+    bi, bv, fr, _, _ = ctx.per_align_bank(p, bank, pairs)
+    bi2, bv2, fr2, _, _ = ctx.per_align_pairs(p, coords[pairs[:, 0]], coords[pairs[:, 1]])
+    assert np.array_equal(bi, bi2) and np.array_equal(bv, bv2) and np.array_equal(fr, fr2)
+    dists = al.alignGroup(coords)
+    assert np.allclose(np.diag(dists), 0, atol=1e-7)
+    assert np.allclose(dists, dists.T, atol=1e-6)
+
+
+def test_edge_cases(ctx):
+    from fastoverlap_b200 import PeriodicAlign, FastOverlapError
+    box = np.array([3.0, 3.0, 3.0])
+    al = PeriodicAlign(4, box, ctx=ctx)
+    p = al._params()
+    # empty batch
+    bi, bv, fr, _, st = ctx.per_align_pairs(p, np.zeros((0, 4, 3)), np.zeros((0, 4, 3)))
+    assert bi.shape == (0, 3)
+    # NaN coordinate is flagged per pair, the other pair is unaffected
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-1, 1, size=(2, 4, 3))
+    b = a + 0.3
+    a[1, 2, 1] = np.nan
+    bi, bv, fr, _, st = ctx.per_align_pairs(p, a, b)
+    assert st[0] == 0 and st[1] != 0
+    # identical structures: maximum at zero displacement
+    bi, bv, fr, _, st = ctx.per_align_pairs(p, a[:1], a[:1])
+    assert tuple(bi[0]) == (0, 0, 0)
+    # invalid parameters raise, never abort
+    bad = ctx.per_params(4, box, 0, 10, 0.3)
+    with pytest.raises(FastOverlapError):
+        ctx.per_align_pairs(bad, a[:1], a[:1])
+    # a permutation group may be empty
+    al2 = PeriodicAlign(4, box, [np.arange(4), np.array([], int)], ctx=ctx)
+    r = ctx.per_align_pairs(al2._params(), a[:1], b[:1])
+    r0 = ctx.per_align_pairs(p, a[:1], b[:1])
+    ctx.set_perm([np.arange(4)], 4)
+    assert np.array_equal(r[0], r0[0])
