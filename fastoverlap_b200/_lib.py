@@ -37,7 +37,10 @@ SIGNATURES = {
     "fo_destroy": (None, [c_void_p]),
     "fo_last_error": (ctypes.c_char_p, [c_void_p]),
     "fo_set_stream": (ctypes.c_int, [c_void_p, c_void_p]),
+    "fo_reset_stream": (ctypes.c_int, [c_void_p]),
     "fo_sync": (ctypes.c_int, [c_void_p]),
+    "fo_profile_begin": (ctypes.c_int, [c_void_p]),
+    "fo_profile_end": (ctypes.c_int, [c_void_p, c_f64p, c_i64p]),
     "fo_device_info": (ctypes.c_int, [c_void_p, c_i64p]),
     "fo_launch_count": (ctypes.c_int64, [c_void_p]),
     "fo_set_perm": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
@@ -170,7 +173,24 @@ class Context(object):
         self._check(self._lib.fo_sync(self._h), "fo_sync")
 
     def set_stream(self, cuda_stream):
+        """Run on an external cudaStream_t handle (int; 0 = legacy default stream)."""
         self._check(self._lib.fo_set_stream(self._h, c_void_p(cuda_stream or 0)), "fo_set_stream")
+
+    def reset_stream(self):
+        self._check(self._lib.fo_reset_stream(self._h), "fo_reset_stream")
+
+    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "k6", "k7")
+
+    def profile_begin(self):
+        self._check(self._lib.fo_profile_begin(self._h), "fo_profile_begin")
+
+    def profile_end(self):
+        """-> {kernel class: (total ms, launches)} measured with CUDA events on the ctx stream."""
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.int64)
+        self._check(self._lib.fo_profile_end(self._h, ms.ctypes.data_as(c_f64p),
+                                             cnt.ctypes.data_as(c_i64p)), "fo_profile_end")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROF_KINDS) if cnt[i]}
 
     def device_info(self):
         out = np.zeros(4, np.int64)

@@ -129,7 +129,15 @@ extern "C" int fo_set_stream(fo_ctx* ctx, void* cuda_stream) {
   if (!ctx) return FO_ERR_INVALID;
   FO_CUDA(ctx, cudaSetDevice(ctx->device));
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return FO_OK;
+}
+
+extern "C" int fo_reset_stream(fo_ctx* ctx) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = ctx->own_stream;
   return FO_OK;
 }
 
@@ -150,6 +158,41 @@ extern "C" int fo_device_info(fo_ctx* ctx, int64_t out[4]) {
 }
 
 extern "C" int64_t fo_launch_count(const fo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fo_profile_begin(fo_ctx* ctx) {
+  if (!ctx) return FO_ERR_INVALID;
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  ctx->profiling = true;
+  return FO_OK;
+}
+
+extern "C" int fo_profile_end(fo_ctx* ctx, double ms_out[FO_PROF_NKINDS],
+                              int64_t count_out[FO_PROF_NKINDS]) {
+  if (!ctx || !ms_out || !count_out) return FO_ERR_INVALID;
+  ctx->profiling = false;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < FO_PROF_NKINDS; ++k) {
+    ms_out[k] = 0.0;
+    count_out[k] = 0;
+  }
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.kind >= 0 &&
+        r.kind < FO_PROF_NKINDS) {
+      ms_out[r.kind] += ms;
+      count_out[r.kind]++;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  return FO_OK;
+}
 
 extern "C" int fo_set_perm(fo_ctx* ctx, const int32_t* group_offsets, int64_t ngroups,
                            const int32_t* atom_idx, int64_t natoms) {

@@ -20,6 +20,11 @@ struct fo_wigner_cache {
   size_t bytes = 0;
 };
 
+struct fo_prof_rec {
+  int kind;
+  cudaEvent_t e0, e1;
+};
+
 struct fo_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -43,6 +48,10 @@ struct fo_ctx {
   fo_devbuf pinned[6];
 
   fo_wigner_cache wig;
+
+  // per-kernel event timing (fo_profile_begin/end)
+  bool profiling = false;
+  std::vector<fo_prof_rec> prof;
 };
 
 enum {
@@ -74,6 +83,25 @@ int fo_scratch(fo_ctx* ctx, int slot, size_t bytes, void** out);
 int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out);
 // make sure a permutation (at least the trivial one) exists for natoms atoms
 int fo_ensure_perm(fo_ctx* ctx, int64_t natoms);
+
+// RAII bracket: records an event pair around a kernel launch when profiling is on
+struct fo_prof_scope {
+  fo_ctx* ctx;
+  cudaEvent_t e1 = nullptr;
+  fo_prof_scope(fo_ctx* c, int kind) : ctx(c) {
+    if (!c->profiling) return;
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+      e1 = nullptr;
+      return;
+    }
+    cudaEventRecord(e0, c->stream);
+    c->prof.push_back({kind, e0, e1});
+  }
+  ~fo_prof_scope() {
+    if (e1) cudaEventRecord(e1, ctx->stream);
+  }
+};
 
 #define FO_CUDA(ctx, call)                                                              \
   do {                                                                                  \

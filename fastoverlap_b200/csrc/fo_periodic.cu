@@ -563,6 +563,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
   // gridDim.x carries the structures (up to 2^31-1)
   dim3 grid((unsigned)nstruct, (unsigned)ngroups, (unsigned)nblk);
+  fo_prof_scope prof(ctx, FO_PROF_PER_SF);
   if (use5) {
     FO_CUDA(ctx, cudaFuncSetAttribute(per_sf_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
@@ -605,6 +606,7 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   FO_CUDA(ctx, cudaFuncSetAttribute(per_xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  fo_prof_scope prof(ctx, FO_PROF_PER_XF);
   per_xf_kernel<<<blocks, XF_THREADS, smem, ctx->stream>>>(d_bankA, d_bankB, d_pairs, (int)npairs,
                                                            ngroups, n, F, kx, ky, kz, p->sigma,
                                                            gscratch, out);

@@ -54,14 +54,29 @@ int fo_create(int device, fo_ctx** out);
 void fo_destroy(fo_ctx* ctx);
 /* Message of the last error on this ctx (or of the last failed fo_create when ctx==NULL). */
 const char* fo_last_error(const fo_ctx* ctx);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work.
- * Pass NULL to return to the context's own stream. */
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work; NULL is the
+ * legacy default stream.  fo_reset_stream returns to the context's own non-blocking stream. */
 int fo_set_stream(fo_ctx* ctx, void* cuda_stream);
+int fo_reset_stream(fo_ctx* ctx);
 int fo_sync(fo_ctx* ctx);
 /* Library / device facts: writes {sm_count, l2_bytes, smem_per_block_optin, cc_major*10+cc_minor}. */
 int fo_device_info(fo_ctx* ctx, int64_t out[4]);
 /* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
 int64_t fo_launch_count(const fo_ctx* ctx);
+
+/* Per-kernel device timing with CUDA events on the ctx stream (bench.py roofline).  Between
+ * fo_profile_begin and fo_profile_end every launch of a profiled kernel class is bracketed by
+ * an event pair; fo_profile_end synchronises and returns, per class, the summed duration in
+ * milliseconds and the launch count.  Classes: FO_PROF_*. */
+#define FO_PROF_PER_SF 0      /* periodic structure factors            */
+#define FO_PROF_PER_XF 1      /* periodic cross-spectrum + DFT + argmax */
+#define FO_PROF_SPH_COEF 2    /* spherical direct coefficients         */
+#define FO_PROF_SPH_HARM 3    /* spherical harmonic-basis coefficients */
+#define FO_PROF_SPH_DOT 4     /* C_nlm contraction to I_lmm'           */
+#define FO_PROF_SPH_ISOFT 5   /* Wigner-d contraction + 2-D DFT + argmax */
+#define FO_PROF_NKINDS 8
+int fo_profile_begin(fo_ctx* ctx);
+int fo_profile_end(fo_ctx* ctx, double ms_out[FO_PROF_NKINDS], int64_t count_out[FO_PROF_NKINDS]);
 
 /* Permutation groups: the atoms of group g are atom_idx[group_offsets[g] .. group_offsets[g+1]).
  * 0-based.  Replaces fastoverlaputils.setperm(natoms, permgroup(1-based), npermsize)

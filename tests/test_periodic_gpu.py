@@ -129,8 +129,8 @@ def test_translation_recovery_full_size(ctx):
     err = disps - shift
     err -= np.round(err / box) * box
     assert np.abs(err).max() < 0.02 * box[0] / 40 * 40 / 10  # well inside one grid cell
-    # self-overlap value: peak equals sum_k |S|^2 damp of the structure (same for every pair)
-    assert np.ptp(bv) / bv.mean() < 1e-3
+    # the peak height is that of the self-overlap up to grid sampling of the peak
+    assert np.ptp(bv) / bv.mean() < 2e-2
     dists, out_disp, perms = al.align_batch(pos1[:5], pos2[:5])
     assert np.all(dists < 1e-6)
 
