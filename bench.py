@@ -101,7 +101,7 @@ class Blj256:
         fr = res[2]
         d = fr * self.box / self.F - shift
         d -= np.round(d / self.box) * self.box
-        return float(np.abs(d).max()) < self.box[0] / self.F
+        return bool(float(np.abs(d).max()) < self.box[0] / self.F)
 
     # FP64 work of the dominant kernel (per_sf_kernel<5>), per pair, as executed:
     # 2 structures x 256 atoms x 100 (i,j) x [4 DMUL + 2 x 40 DFMA]  (DESIGN.md "K_sf")
@@ -425,7 +425,7 @@ def run_ours(args, wl):
                    "d2h_bytes_per_step": int(wl.d2h_bytes(P)), "steps": e2e_steps,
                    "api": "fo_%s_align_pairs (host buffers)" % ("per" if wl.name == "blj256" else "sph")},
            "roofline": roof, "cpu_baseline": base,
-           "checks": {"positive_control": ok, "device_vs_host_identical": same}}
+           "checks": {"positive_control": bool(ok), "device_vs_host_identical": same}}
     print(json.dumps(res), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -8,5 +8,8 @@ FastOverlapError.
 """
 from ._lib import Context, FastOverlapError, default_context, load_library, library_path
 from .periodic import PeriodicAlign
+from .soft import SOFT
+from .spherical import SphericalAlign, SphericalHarmonicAlign
 
-__all__ = ["PeriodicAlign", "Context", "FastOverlapError", "default_context"]
+__all__ = ["SphericalAlign", "SphericalHarmonicAlign", "PeriodicAlign", "SOFT", "Context",
+           "FastOverlapError", "default_context"]

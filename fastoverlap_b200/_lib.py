@@ -66,6 +66,8 @@ SIGNATURES = {
     "fo_bank_destroy": (None, [c_void_p, c_void_p]),
     "fo_sph_isoft_argmax": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fo_sph_isoft": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                    c_void_p]),
     "fo_sph_coeffs_direct": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
                                             c_void_p, c_void_p]),
@@ -328,6 +330,17 @@ class Context(object):
                                                   _ptr(bi), _ptr(bv), _ptr(fr), _ptr(grid)),
                     "fo_sph_isoft_argmax")
         return bi, bv, fr, grid
+
+    def sph_isoft(self, Ilmm, Jmax, want_imag=True):
+        """Inverse SO(3) transform of arbitrary coefficients -> complex (P, 2B, 2B, 2B) grid."""
+        L = int(Jmax)
+        Ilmm = np.ascontiguousarray(Ilmm, dtype=np.complex128).reshape(-1, L + 1, 2 * L + 1, 2 * L + 1)
+        P = Ilmm.shape[0]
+        n = 2 * (L + 1)
+        re = np.empty((P, n, n, n), np.float64)
+        im = np.empty((P, n, n, n), np.float64) if want_imag else None
+        self._check(self._lib.fo_sph_isoft(self._h, _ptr(Ilmm), P, L, _ptr(re), _ptr(im)), "fo_sph_isoft")
+        return re + 1j * im if want_imag else re
 
     def sph_coeffs_direct(self, posA, posB, Jmax, sigma):
         posA = _f64(posA)

@@ -1,11 +1,1396 @@
-// placeholder replaced by the real kernels
+// Spherical (cluster) hot path.  Replaces reference fastoverlap/f90/fastclusters.f90
+// (RYML, FOURIERCOEFFS, HARMONICNL/HARMONICCOEFFS, DOTHARMONICCOEFFS, CALCOVERLAP), DSOFT.f90
+// (CALCWIGNERD, ISOFT), fastutils.f90 SPHI + the arg-max of FINDPEAKS, and the numpy kernels
+// sphericalAlignment.py:57-65,260-273,288-372, soft.py:73-125, utils.py:319-338.
+//
+// Kernels
+//   sph_prep_kernel     r_j and Y_lm(r_j) (m >= 0) per atom                         [K1]
+//   sph_bessel_kernel   B_l[j,k] = 4 pi^2.5 s^3 i_l(r_j r_k/2s^2) e^{-(r_j^2+r_k^2)/4s^2}  [K2a]
+//   sph_direct_kernel   I^l = Y_A^l B_l Y_B^l^H per (pair, l)                        [K2a]
+//   sph_harm_kernel     C_nlm = sum_j d_nl(r_j) conj(Y_lm(r_j)) per (structure, group) [K2b]
+//   sph_dot_kernel      I^l_{mm'} = sum_g sum_n conj(C^A) C^B per pair               [K3]
+//   sph_wigner_kernel   table sqrt((2l+1)/2) d^l_{m1m2}(beta_k)  (cached per Jmax)   [K4]
+//   sph_isoft_kernel    Wigner contraction + 2-D DFT + arg-max per (pair, beta chunk) [K5-K7]
+//   sph_final_kernel    reduce over beta chunks + findMax parabola                   [K7]
+//
+// Device layouts (complex = double2)
+//   Ypk   [struct][atom][lm]            lm = l(l+1)/2 + m, 0 <= m <= l  (Y_{l,-m} = (-1)^m conj Y_lm)
+//   Bes   [pair][l][j][k]
+//   Ihalf [pair][m2 = 0..L][m1 + L = 0..2L][l = 0..L]     only m2 >= 0 is stored because
+//         I[l,-m1,-m2] = (-1)^{m1+m2} conj(I[l,m1,m2]) for real densities => the grid is real
+//   Dt    [m2 = 0..L][m1 + L][l][k = 0..2B-1]             Wigner table, same (m2,m1,l) order
+//   Cpk   [struct][group][n][lm]        harmonic coefficients, m >= 0
+// All arithmetic is FP64.
+#include <math.h>
+
+#include <string.h>
+
+#include <algorithm>
+
 #include "fo_internal.h"
-#define STUB(name, ...) extern "C" int name(__VA_ARGS__) { return FO_ERR_UNSUPPORTED; }
-STUB(fo_sph_isoft_argmax, fo_ctx*, const double*, int64_t, int64_t, int, int64_t*, double*, double*, double*)
-STUB(fo_sph_coeffs_direct, fo_ctx*, const double*, const double*, int64_t, int64_t, int64_t, double, double*, int32_t*)
-STUB(fo_sph_align_pairs, fo_ctx*, const double*, const double*, int64_t, int64_t, int64_t, double, int, int64_t*, double*, double*, double*, int32_t*)
-STUB(fo_sph_align_pairs_dev, fo_ctx*, const double*, const double*, int64_t, int64_t, int64_t, double, int, int64_t*, double*, double*, double*, int32_t*)
-STUB(fo_sph_harm_coeffs, fo_ctx*, const double*, int64_t, int64_t, int64_t, int64_t, double, double, double*, int32_t*)
-STUB(fo_sph_bank_create, fo_ctx*, const double*, int64_t, int64_t, int64_t, int64_t, double, double, fo_bank**)
-STUB(fo_sph_align_bank, fo_ctx*, const fo_bank*, const int64_t*, int64_t, int, int64_t*, double*, double*, double*, double*)
-STUB(fo_sph_wigner_table, fo_ctx*, int64_t, double*)
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
+  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ int nlm_of(int L) { return (L + 1) * (L + 2) / 2; }
+
+// ------------------------------------------------------------------------------------------
+// K1: r and Y_lm (m >= 0), scipy / Condon-Shortley convention.  One thread per (atom, m): the
+// stable 3-term recurrence in l of the fully normalised associated Legendre functions
+// (what XDNRMP legendre.f90:143-371 returns to RYML fastclusters.f90:602-652).
+// ------------------------------------------------------------------------------------------
+__global__ void sph_prep_kernel(const double* __restrict__ pos, int natoms, int L, size_t nstruct,
+                                double2* __restrict__ Ypk, double* __restrict__ R, int* status) {
+  const int NLM = nlm_of(L);
+  const size_t total = nstruct * (size_t)natoms * (L + 1);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(t % (L + 1));
+    const size_t sa = t / (L + 1);  // struct*natoms + atom
+    const double x = pos[sa * 3 + 0], y = pos[sa * 3 + 1], z = pos[sa * 3 + 2];
+    const double r = sqrt(x * x + y * y + z * z);
+    const bool fin = isfinite(r);
+    double ct = 1.0, st = 0.0, cph = 1.0, sph = 0.0;
+    if (r > 0.0 && fin) {
+      ct = z / r;
+      const double rho = sqrt(x * x + y * y);
+      st = rho / r;
+      if (rho > 0.0) {
+        cph = x / rho;
+        sph = y / rho;
+      }
+    }
+    if (m == 0) {
+      R[sa] = r;
+      if (status) {
+        const size_t s = sa / natoms;
+        if (!fin) atomicOr(&status[s], FO_STATUS_NONFINITE);
+        if (r == 0.0) atomicOr(&status[s], FO_STATUS_ATOM_AT_ORIGIN);
+      }
+    }
+    // exp(i m phi) by repeated squaring-free product (m <= L small): use sincos of m*phi
+    double sm, cm;
+    {
+      const double phi = atan2(sph, cph);
+      sincos((double)m * phi, &sm, &cm);
+    }
+    // P_m^m
+    double pmm = 0.28209479177387814347403972578039;  // sqrt(1/(4 pi))
+    for (int q = 1; q <= m; ++q) pmm *= -sqrt((2.0 * q + 1.0) / (2.0 * q)) * st;
+    double2* out = Ypk + sa * NLM;
+    double pl2 = 0.0, pl1 = pmm;
+    out[m * (m + 1) / 2 + m] = make_double2(pmm * cm, pmm * sm);
+    if (m + 1 <= L) {
+      const double p = sqrt(2.0 * m + 3.0) * ct * pmm;
+      out[(m + 1) * (m + 2) / 2 + m] = make_double2(p * cm, p * sm);
+      pl2 = pmm;
+      pl1 = p;
+    }
+    for (int l = m + 2; l <= L; ++l) {
+      const double a = sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
+      const double b = sqrt((((double)(l - 1) * (l - 1)) - (double)m * m) /
+                            (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
+      const double p = a * (ct * pl1 - b * pl2);
+      out[l * (l + 1) / 2 + m] = make_double2(p * cm, p * sm);
+      pl2 = pl1;
+      pl1 = p;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a part 1: Bessel/Gaussian matrix.  One thread per (pair, j, k): exp(-x) i_l(x) for all l by
+// Miller's backward recurrence (x >= 1; the algorithm of SPHI fastutils.f90:1000-1096) or the
+// ascending series (x < 1), times the Gaussian exp(-(r_j - r_k)^2 / 4 s^2) -- together exactly
+// i_l(x) exp(-(r_j^2 + r_k^2)/4 s^2) of sphericalAlignment.py:268-272 without overflow.
+// Pairs of atoms in different permutation groups get 0 (the reference sums calcSO3Coeffs over
+// groups, sphericalAlignment.py:175).
+// ------------------------------------------------------------------------------------------
+__global__ void sph_bessel_kernel(const double* __restrict__ RA, const double* __restrict__ RB,
+                                  const int* __restrict__ gid, int natoms, int L, double sigma,
+                                  size_t npairs, double* __restrict__ Bes) {
+  const size_t NN = (size_t)natoms * natoms;
+  const size_t total = npairs * NN;
+  const double fact = 4.0 * pow(kPi, 2.5) * sigma * sigma * sigma;
+  const double inv2s2 = 0.5 / (sigma * sigma);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = t / NN;
+    const int jk = (int)(t - p * NN);
+    const int j = jk / natoms, k = jk - j * natoms;
+    double* out = Bes + p * (size_t)(L + 1) * NN + jk;
+    if (gid[j] != gid[k]) {
+      for (int l = 0; l <= L; ++l) out[(size_t)l * NN] = 0.0;
+      continue;
+    }
+    const double ra = RA[p * natoms + j], rb = RB[p * natoms + k];
+    const double x = ra * rb * inv2s2;
+    const double dr = ra - rb;
+    const double g = fact * exp(-0.5 * dr * dr * inv2s2);
+    if (!(x >= 1e-100)) {  // also catches NaN
+      out[0] = (x == x) ? g : x;
+      for (int l = 1; l <= L; ++l) out[(size_t)l * NN] = (x == x) ? 0.0 : x;
+      continue;
+    }
+    if (x < 1.0) {
+      // i_l(x) = x^l/(2l+1)!! sum_q (x^2/2)^q / (q! (2l+3)(2l+5)...(2l+2q+1))
+      const double emx = exp(-x), h = 0.5 * x * x;
+      double pref = emx;  // e^{-x} x^l/(2l+1)!!
+      for (int l = 0; l <= L; ++l) {
+        double term = 1.0, sum = 1.0;
+        for (int q = 1; q <= 14; ++q) {
+          term *= h / ((double)q * (2.0 * l + 2.0 * q + 1.0));
+          sum += term;
+        }
+        out[(size_t)l * NN] = g * pref * sum;
+        pref *= x / (2.0 * l + 3.0);
+      }
+      continue;
+    }
+    const double si0 = -expm1(-2.0 * x) / (2.0 * x);
+    const int mstart = 16 + (int)sqrt(50.0 * x + (double)L * L);
+    const double invx = 1.0 / x;
+    double f0 = 0.0, f1 = 1e-100, f = 0.0;
+    for (int q = mstart; q > L; --q) {
+      f = (2.0 * q + 3.0) * f1 * invx + f0;
+      f0 = f1;
+      f1 = f;
+      if (f > 1e150) {
+        f0 *= 1e-150;
+        f1 *= 1e-150;
+      }
+    }
+    for (int q = L; q >= 0; --q) {
+      f = (2.0 * q + 3.0) * f1 * invx + f0;
+      out[(size_t)q * NN] = f;
+      f0 = f1;
+      f1 = f;
+    }
+    const double cs = g * si0 / f;
+    for (int q = 0; q <= L; ++q) out[(size_t)q * NN] *= cs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a part 2: per (pair, l):  T[m,k] = sum_j Y^A_{lm}(j) B_l[j,k]  (m >= 0; T[-m] = (-1)^m conj T[m])
+//                             I[l,m1,m2] = sum_k T[m1,k] conj(Y^B_{l m2}(k)),  m2 >= 0, all m1.
+// FOURIERCOEFFS fastclusters.f90:868-916 factorised into two small GEMMs.
+// ------------------------------------------------------------------------------------------
+constexpr int DIR_TK = 32;
+
+__global__ void __launch_bounds__(128)
+sph_direct_kernel(const double2* __restrict__ YA, const double2* __restrict__ YB,
+                  const double* __restrict__ Bes, int natoms, int L, double2* __restrict__ Ihalf) {
+  extern __shared__ double2 smd[];
+  const int l = blockIdx.x;
+  const size_t p = blockIdx.y;
+  const int NLM = nlm_of(L), W = 2 * L + 1, L1 = L + 1;
+  const int nm = l + 1;
+  double2* T = smd;                    // [nm][DIR_TK]
+  double2* YBs = T + nm * DIR_TK;      // [DIR_TK][nm]
+  double2* acc = YBs + DIR_TK * nm;    // [(2l+1)][nm]  (m1 = -l..l, m2 = 0..l)
+  const int nout = (2 * l + 1) * nm;
+  const int lbase = l * (l + 1) / 2;
+  const size_t NN = (size_t)natoms * natoms;
+  const double* Bl = Bes + (p * L1 + l) * NN;
+  const double2* ya = YA + p * (size_t)natoms * NLM;
+  const double2* yb = YB + p * (size_t)natoms * NLM;
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) acc[o] = make_double2(0.0, 0.0);
+  for (int k0 = 0; k0 < natoms; k0 += DIR_TK) {
+    const int tk = min(DIR_TK, natoms - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nm * tk; e += blockDim.x) {
+      const int kk = e % tk, m = e / tk;
+      double tr = 0.0, ti = 0.0;
+      for (int j = 0; j < natoms; ++j) {
+        const double b = Bl[(size_t)j * natoms + k0 + kk];
+        const double2 y = ya[(size_t)j * NLM + lbase + m];
+        tr = fma(y.x, b, tr);
+        ti = fma(y.y, b, ti);
+      }
+      T[m * DIR_TK + kk] = make_double2(tr, ti);
+    }
+    for (int e = threadIdx.x; e < nm * tk; e += blockDim.x) {
+      const int m = e % nm, kk = e / nm;
+      YBs[kk * nm + m] = yb[(size_t)(k0 + kk) * NLM + lbase + m];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+      const int m2 = o % nm, m1 = o / nm - l;
+      const int am = m1 < 0 ? -m1 : m1;
+      const double sgn = (m1 < 0 && (am & 1)) ? -1.0 : 1.0;
+      double ar = 0.0, ai = 0.0;
+      for (int kk = 0; kk < tk; ++kk) {
+        double2 t = T[am * DIR_TK + kk];
+        if (m1 < 0) t.y = -t.y;
+        const double2 y = YBs[kk * nm + m2];
+        ar += t.x * y.x + t.y * y.y;
+        ai += t.y * y.x - t.x * y.y;
+      }
+      acc[o].x += sgn * ar;
+      acc[o].y += sgn * ai;
+    }
+  }
+  __syncthreads();
+  double2* out = Ihalf + p * (size_t)L1 * W * L1;
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+    const int m2 = o % nm, m1 = o / nm - l;
+    out[((size_t)m2 * W + (m1 + L)) * L1 + l] = acc[o];
+  }
+}
+
+// zero the (m2, m1, l < max(|m1|, m2)) entries are never read; no need to clear Ihalf.
+
+// Full numpy layout [l][m1 wrap][m2 wrap] -> Ihalf, keeping the part that generates the REAL grid:
+// Ihalf = (I[l,m1,m2] + (-1)^{m1+m2} conj(I[l,-m1,-m2]))/2 (identity for coefficients of real
+// densities).  part = 1 selects the part that generates the IMAGINARY grid instead.
+__global__ void sph_pack_kernel(const double2* __restrict__ full, int L, size_t npairs, int part,
+                                double2* __restrict__ Ihalf) {
+  const int W = 2 * L + 1, L1 = L + 1;
+  const size_t per = (size_t)L1 * W * L1;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < npairs * per;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = t / per;
+    int r = (int)(t - p * per);
+    const int l = r % L1;
+    r /= L1;
+    const int m1 = r % W - L, m2 = r / W;
+    double2 v = make_double2(0.0, 0.0);
+    const int am1 = m1 < 0 ? -m1 : m1;
+    if (l >= am1 && l >= m2) {
+      const double2* f = full + p * (size_t)L1 * W * W + (size_t)l * W * W;
+      const double2 a = f[((m1 + W) % W) * W + m2];
+      double2 b = f[((-m1 + W) % W) * W + ((-m2 + W) % W)];
+      const double sg = ((m1 + m2) & 1) ? -1.0 : 1.0;
+      b = make_double2(sg * b.x, -sg * b.y);  // (-1)^{m1+m2} conj
+      if (part == 0)
+        v = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+      else  // (a - b) / (2i)
+        v = make_double2(0.5 * (a.y - b.y), -0.5 * (a.x - b.x));
+    }
+    Ihalf[t] = v;
+  }
+}
+
+__global__ void sph_unpack_kernel(const double2* __restrict__ Ihalf, int L, size_t npairs,
+                                  double2* __restrict__ full) {
+  const int W = 2 * L + 1, L1 = L + 1;
+  const size_t per = (size_t)L1 * W * W;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < npairs * per;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = t / per;
+    int r = (int)(t - p * per);
+    const int i2 = r % W;
+    r /= W;
+    const int i1 = r % W, l = r / W;
+    const int m1 = i1 <= L ? i1 : i1 - W, m2 = i2 <= L ? i2 : i2 - W;
+    double2 v = make_double2(0.0, 0.0);
+    const int am1 = m1 < 0 ? -m1 : m1, am2 = m2 < 0 ? -m2 : m2;
+    if (l >= am1 && l >= am2) {
+      const double2* h = Ihalf + p * (size_t)L1 * W * L1;
+      if (m2 >= 0) {
+        v = h[((size_t)m2 * W + (m1 + L)) * L1 + l];
+      } else {
+        v = h[((size_t)(-m2) * W + (-m1 + L)) * L1 + l];
+        const double sg = ((m1 + m2) & 1) ? -1.0 : 1.0;
+        v = make_double2(sg * v.x, -sg * v.y);
+      }
+    }
+    full[t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: harmonic-basis coefficients.  d_nl(r) in closed form (Gradshteyn-Ryzhik 7.421.4):
+//   d_nl = 4 pi N_nl sqrt(pi/2) 2^{-l-3/2} beta^{-l-3/2} y^l exp(-r^2/(2(s^2+r0^2))) Q_n,
+//   (n+1) Q_{n+1} = ((2n+l+3/2) delta - kappa) Q_n - (n+l+1/2) delta^2 Q_{n-1}
+// which is what radialIntegralHarmonic + coeffs_harmonicBasis (sphericalAlignment.py:288-360)
+// and HARMONICNL (fastclusters.f90:492-540) evaluate, without their cancellation.
+// One CTA per (structure, group); atoms in tiles; C[n][lm] += d[n][l] conj(Y[lm]).
+// ------------------------------------------------------------------------------------------
+constexpr int HARM_TA = 8;
+
+__global__ void __launch_bounds__(256)
+sph_harm_kernel(const double2* __restrict__ Ypk, const double* __restrict__ R,
+                const int32_t* __restrict__ goff, const int32_t* __restrict__ gidx, int ngroups,
+                int natoms, int nmax, int L, double r0, double sigma, double2* __restrict__ Cpk) {
+  extern __shared__ double smh[];
+  const int s = blockIdx.x, g = blockIdx.y;
+  const int NLM = nlm_of(L), L1 = L + 1, N1 = nmax + 1;
+  double* dnl = smh;                                   // [HARM_TA][N1][L1]
+  double2* ys = (double2*)(dnl + HARM_TA * N1 * L1);   // [HARM_TA][NLM]
+  const int nout = N1 * NLM;
+  // each thread owns outputs o = tid + q*blockDim, o = n*NLM + lm ; keep up to 16 in registers
+  constexpr int MAXQ = 16;
+  double2 acc[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) acc[q] = make_double2(0.0, 0.0);
+  const double s2 = sigma * sigma, r02 = r0 * r0;
+  const double beta = 0.5 * (1.0 / r02 + 1.0 / s2), alpha = 1.0 / r02;
+  const double delta = (beta - alpha) / beta;
+  const int a_begin = goff[g], a_end = goff[g + 1];
+  for (int a0 = a_begin; a0 < a_end; a0 += HARM_TA) {
+    const int ta = min(HARM_TA, a_end - a0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ta * L1; t += blockDim.x) {
+      const int a = t / L1, l = t - a * L1;
+      const int atom = gidx[a0 + a];
+      const double r = R[(size_t)s * natoms + atom];
+      const double y = r / s2;
+      const double kappa = alpha * y * y / (4.0 * beta * beta);
+      const double nu = l + 0.5;
+      double norm = sqrt(2.0 * pow(r0, -2.0 * l - 3.0) / tgamma(l + 1.5));
+      const double pref = 4.0 * kPi * sqrt(kPi / 2.0) * pow(2.0, -nu - 1.0) * pow(beta, -nu - 1.0) *
+                          pow(y, (double)l) * exp(-0.5 * r * r / (s2 + r02));
+      double qm1 = 0.0, q = 1.0;
+      for (int n = 0; n <= nmax; ++n) {
+        dnl[(a * N1 + n) * L1 + l] = pref * norm * q;
+        const double qn = (((2.0 * n + 1.0 + nu) * delta - kappa) * q - (n + nu) * delta * delta * qm1) / (n + 1.0);
+        qm1 = q;
+        q = qn;
+        norm *= sqrt((n + 1.0) / (n + 1.0 + nu));
+      }
+    }
+    for (int t = threadIdx.x; t < ta * NLM; t += blockDim.x) {
+      const int a = t / NLM, lm = t - a * NLM;
+      ys[t] = Ypk[((size_t)s * natoms + gidx[a0 + a]) * NLM + lm];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      const int o = threadIdx.x + q * blockDim.x;
+      if (o < nout) {
+        const int n = o / NLM, lm = o - n * NLM;
+        // l from lm: l = floor((sqrt(8 lm + 1) - 1)/2)
+        int l = (int)((sqrt(8.0 * lm + 1.0) - 1.0) * 0.5);
+        while ((l + 1) * (l + 2) / 2 <= lm) ++l;
+        while (l * (l + 1) / 2 > lm) --l;
+        double ar = acc[q].x, ai = acc[q].y;
+        for (int a = 0; a < ta; ++a) {
+          const double d = dnl[(a * N1 + n) * L1 + l];
+          const double2 yv = ys[a * NLM + lm];
+          ar = fma(d, yv.x, ar);
+          ai = fma(-d, yv.y, ai);
+        }
+        acc[q] = make_double2(ar, ai);
+      }
+    }
+  }
+  double2* out = Cpk + ((size_t)s * ngroups + g) * nout;
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    const int o = threadIdx.x + q * blockDim.x;
+    if (o < nout) out[o] = acc[q];
+  }
+}
+
+// Cpk (m >= 0) -> numpy layout [n][l][m wrap]: C[n,l,-m] = (-1)^m conj(C[n,l,m]).
+__global__ void sph_harm_expand_kernel(const double2* __restrict__ Cpk, int nmax, int L, size_t nsg,
+                                       double2* __restrict__ full) {
+  const int W = 2 * L + 1, L1 = L + 1, N1 = nmax + 1, NLM = nlm_of(L);
+  const size_t per = (size_t)N1 * L1 * W;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < nsg * per;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t sg = t / per;
+    int r = (int)(t - sg * per);
+    const int im = r % W;
+    r /= W;
+    const int l = r % L1, n = r / L1;
+    const int m = im <= L ? im : im - W;
+    const int am = m < 0 ? -m : m;
+    double2 v = make_double2(0.0, 0.0);
+    if (am <= l) {
+      v = Cpk[sg * (size_t)N1 * NLM + (size_t)n * NLM + l * (l + 1) / 2 + am];
+      if (m < 0) {
+        const double sg2 = (am & 1) ? -1.0 : 1.0;
+        v = make_double2(sg2 * v.x, -sg2 * v.y);
+      }
+    }
+    full[t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: I[l,m1,m2] = sum_g sum_n conj(C^A[g,n,l,m1]) C^B[g,n,l,m2] for m2 >= 0, all m1, written in
+// the Ihalf layout; also avg = sum_{l,m1,m2 (all)} |I|^2 (CALCSIMILARITY fastclusters.f90:790-818).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sph_dot_kernel(const double2* __restrict__ bank, const long long* __restrict__ pairs, int ngroups,
+               int nmax, int L, double2* __restrict__ Ihalf, double* __restrict__ avg) {
+  __shared__ double red[8];
+  const size_t p = blockIdx.x;
+  const int W = 2 * L + 1, L1 = L + 1, N1 = nmax + 1, NLM = nlm_of(L);
+  const size_t per_struct = (size_t)ngroups * N1 * NLM;
+  const double2* CA = bank + (size_t)pairs[2 * p] * per_struct;
+  const double2* CB = bank + (size_t)pairs[2 * p + 1] * per_struct;
+  double2* out = Ihalf + p * (size_t)L1 * W * L1;
+  const int nitem = L1 * W * L1;
+  double norm = 0.0;
+  for (int t = threadIdx.x; t < nitem; t += blockDim.x) {
+    const int l = t % L1;
+    int r = t / L1;
+    const int m1 = r % W - L, m2 = r / W;
+    const int am1 = m1 < 0 ? -m1 : m1;
+    if (l < am1 || l < m2) continue;
+    const int lb = l * (l + 1) / 2;
+    double ar = 0.0, ai = 0.0;
+    for (int g = 0; g < ngroups; ++g)
+      for (int n = 0; n < N1; ++n) {
+        double2 a = CA[((size_t)g * N1 + n) * NLM + lb + am1];
+        if (m1 < 0) {  // C[-m] = (-1)^m conj(C[m])
+          const double sg = (am1 & 1) ? -1.0 : 1.0;
+          a = make_double2(sg * a.x, -sg * a.y);
+        }
+        const double2 b = CB[((size_t)g * N1 + n) * NLM + lb + m2];
+        // conj(a) * b
+        ar += a.x * b.x + a.y * b.y;
+        ai += a.x * b.y - a.y * b.x;
+      }
+    out[t] = make_double2(ar, ai);
+    // the (-m1,-m2) partner has the same modulus; m2 = 0 rows are their own partners' mirror
+    norm += (m2 == 0 ? 1.0 : 2.0) * (ar * ar + ai * ai);
+  }
+  if (avg) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) norm += __shfl_down_sync(0xffffffffu, norm, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = norm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+      avg[p] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: Wigner-d table in the Dt layout.  One thread per (m2 >= 0, m1, k): closed-form edge value
+// at l = max(|m1|, m2) then the Kostelec-Rockmore recurrence in l
+// (CALCWIGNERD + RECURRTERMS, DSOFT.f90:81-195).
+// ------------------------------------------------------------------------------------------
+__device__ double wigner_edge(int J, int m1, int m2, double cb2, double sb2) {
+  // d^J_{m1 m2} with max(|m1|,|m2|) = J, times sqrt((2J+1)/2)
+  int m;      // the other index
+  double c, s;  // bases
+  int pc, ps;
+  if (m1 == J) {
+    m = m2; c = cb2; s = -sb2; pc = J + m; ps = J - m;
+  } else if (m1 == -J) {
+    m = m2; c = cb2; s = sb2; pc = J - m; ps = J + m;
+  } else if (m2 == J) {
+    m = m1; c = cb2; s = sb2; pc = J + m; ps = J - m;
+  } else {
+    m = m1; c = cb2; s = -sb2; pc = J - m; ps = J + m;
+  }
+  const int am = m < 0 ? -m : m;
+  double binom = 1.0;  // C(2J, J+m)
+  for (int i = 1; i <= J - am; ++i) binom *= (double)(J + am + i) / (double)i;
+  double v = sqrt((2.0 * J + 1.0) * 0.5 * binom);
+  for (int i = 0; i < pc; ++i) v *= c;
+  for (int i = 0; i < ps; ++i) v *= s;
+  return v;
+}
+
+__global__ void sph_wigner_kernel(int L, double* __restrict__ Dt) {
+  const int B = L + 1, W = 2 * L + 1, L1 = L + 1, NK = 2 * B;
+  const int total = L1 * W * NK;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int k = t % NK;
+    int r = t / NK;
+    const int m1 = r % W - L, m2 = r / W;
+    const int am1 = m1 < 0 ? -m1 : m1;
+    const int J0 = am1 > m2 ? am1 : m2;
+    const double beta = kPi * (2.0 * k + 1.0) / (4.0 * B);
+    double sb2, cb2;
+    sincos(0.5 * beta, &sb2, &cb2);
+    const double cb = cos(beta);
+    double* col = Dt + ((size_t)m2 * W + (m1 + L)) * L1 * NK + k;
+    for (int l = 0; l < J0; ++l) col[(size_t)l * NK] = 0.0;
+    double dm1 = 0.0, d = wigner_edge(J0, m1, m2, cb2, sb2);
+    col[(size_t)J0 * NK] = d;
+    for (int J = J0; J < L; ++J) {
+      const double dj = J, a1 = m1, a2 = m2;
+      const double t1 = sqrt((2.0 * dj + 3.0) / (2.0 * dj + 1.0));
+      const double t3 = (dj + 1.0) * (2.0 * dj + 1.0);
+      const double t5 = 1.0 / sqrt(((dj + 1.0) * (dj + 1.0) - a1 * a1) * ((dj + 1.0) * (dj + 1.0) - a2 * a2));
+      const double Bc = t1 * t3 * t5;
+      double A = 0.0, C = 0.0;
+      if (J > 0) {
+        const double t2 = sqrt((2.0 * dj + 3.0) / (2.0 * dj - 1.0)) * (dj + 1.0) / dj;
+        const double t4 = sqrt((dj * dj - a1 * a1) * (dj * dj - a2 * a2));
+        A = t2 * t4 * t5;
+        C = a1 * a2 / (dj * (dj + 1.0));
+      }
+      const double dn = Bc * (cb - C) * d - A * dm1;
+      dm1 = d;
+      d = dn;
+      col[(size_t)(J + 1) * NK] = d;
+    }
+  }
+}
+
+// Dt -> the reference's Ds[l][m1 wrap][m2 wrap][k] (soft.py:73-96) using
+// d^l_{m1,-m2} = (-1)^{l+m1} d^l_{m1,m2}(pi - beta)  and beta_{2B-1-k} = pi - beta_k.
+__global__ void sph_wigner_export_kernel(const double* __restrict__ Dt, int L, double* __restrict__ Ds) {
+  const int B = L + 1, W = 2 * L + 1, L1 = L + 1, NK = 2 * B;
+  const int total = B * W * W * NK;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int k = t % NK;
+    int r = t / NK;
+    const int i2 = r % W;
+    r /= W;
+    const int i1 = r % W, l = r / W;
+    const int m1 = i1 <= L ? i1 : i1 - W, m2 = i2 <= L ? i2 : i2 - W;
+    const int am1 = m1 < 0 ? -m1 : m1, am2 = m2 < 0 ? -m2 : m2;
+    double v = 0.0;
+    if (l >= am1 && l >= am2) {
+      if (m2 >= 0) {
+        v = Dt[(((size_t)m2 * W + (m1 + L)) * L1 + l) * NK + k];
+      } else {
+        v = Dt[(((size_t)(-m2) * W + (m1 + L)) * L1 + l) * NK + (NK - 1 - k)];
+        if ((l + m1) & 1) v = -v;
+      }
+    }
+    Ds[t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5-K7: inverse SO(3) transform of one (pair, chunk of KC beta planes), both orientations.
+//   S_par[m1][kk][m2] = sum_{l = par mod 2} Dt[m2][m1][l][k] I[m2][m1][l]      par = even / odd l
+//   orientation o: S = S_even + (o ? -1 : +1) S_odd          (I_inv^l = (-1)^l I^l)
+//   A  U[a][kk][m2] = sum_m1 S[m1][kk][m2] e^{+2 pi i m1 a/2B}
+//   B  g[a][k][gam] = U[a][kk][0] + 2 sum_{m2>=1} Re(U[a][kk][m2] e^{+2 pi i m2 gam/2B})
+// with the +-m pairing of the 1-D transforms (see fo_periodic.cu), then the running arg-max.
+// ------------------------------------------------------------------------------------------
+constexpr int IS_THREADS = 256;
+constexpr int IS_DCA = 5;
+constexpr int IS_DCB = 9;
+
+struct IsoOut {
+  double* part_val;      // [P][O][nchunk]
+  long long* part_idx;   // [P][O][nchunk]
+  double* grid;          // [P][O][2B][2B][2B] or null
+};
+
+__device__ __forceinline__ void better_s(double& bv, long long& bi, double v, long long i) {
+  if (v > bv || (v == bv && i < bi)) {
+    bv = v;
+    bi = i;
+  }
+}
+
+template <int KC>
+__global__ void __launch_bounds__(IS_THREADS)
+sph_isoft_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, int L, int norient,
+                 int nchunk, IsoOut out) {
+  extern __shared__ double2 smi[];
+  const int B = L + 1, W = 2 * L + 1, L1 = L + 1, F = 2 * B, H = B + 1;
+  const int M2p = L1 | 1;
+  const int NL = KC * L1;  // lines of stage A: (kk, m2)
+  double2* tw = smi;                          // [F]
+  double2* Se = tw + F;                       // [W][KC][L1]
+  double2* So = Se + (size_t)W * NL;          // [W][KC][L1]
+  double2* U = So + (size_t)W * NL;           // [F][KC][M2p]
+  double* red = (double*)(U + (size_t)F * KC * M2p);  // 32 doubles
+  const int tid = threadIdx.x;
+  const size_t p = blockIdx.x / nchunk;
+  const int chunk = blockIdx.x % nchunk;
+  const int k0 = chunk * KC;
+  for (int t = tid; t < F; t += IS_THREADS) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+    tw[t] = make_double2(cs, sn);
+  }
+  // ---- K5
+  const double2* Ip = Ihalf + p * (size_t)L1 * W * L1;
+  for (int item = tid; item < L1 * W; item += IS_THREADS) {
+    const int m1i = item % W, m2 = item / W;
+    const int m1 = m1i - L;
+    const int am1 = m1 < 0 ? -m1 : m1;
+    const int l0 = am1 > m2 ? am1 : m2;
+    double2 ae[KC], ao[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      ae[kk] = make_double2(0.0, 0.0);
+      ao[kk] = make_double2(0.0, 0.0);
+    }
+    const double2* ip = Ip + (size_t)item * L1;
+    const double* dp = Dt + (size_t)item * L1 * F + k0;
+    for (int l = l0; l <= L; ++l) {
+      const double2 c = ip[l];
+      const double* d = dp + (size_t)l * F;
+      if (l & 1) {
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+          const double dv = d[kk];
+          ao[kk].x = fma(dv, c.x, ao[kk].x);
+          ao[kk].y = fma(dv, c.y, ao[kk].y);
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+          const double dv = d[kk];
+          ae[kk].x = fma(dv, c.x, ae[kk].x);
+          ae[kk].y = fma(dv, c.y, ae[kk].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      Se[(size_t)m1i * NL + kk * L1 + m2] = ae[kk];
+      So[(size_t)m1i * NL + kk * L1 + m2] = ao[kk];
+    }
+  }
+  __syncthreads();
+  for (int o = 0; o < norient; ++o) {
+    const double so = o ? -1.0 : 1.0;
+    // ---- stage A: lines (kk, m2), inputs over m1 = -L..L, outputs a = 0..F-1
+    {
+      const int nch = (H + IS_DCA - 1) / IS_DCA;
+      for (int item = tid; item < NL * nch; item += IS_THREADS) {
+        const int line = item % NL, ch = item / NL;
+        const int kk = line / L1, m2 = line - kk * L1;
+        const int d0 = ch * IS_DCA;
+        const double2* se = Se + line;
+        const double2* sod = So + line;
+        double2 c0 = se[(size_t)L * NL];
+        {
+          const double2 c0o = sod[(size_t)L * NL];
+          c0.x += so * c0o.x;
+          c0.y += so * c0o.y;
+        }
+        double2 P[IS_DCA], Q[IS_DCA];
+        int idx[IS_DCA];
+#pragma unroll
+        for (int t = 0; t < IS_DCA; ++t) {
+          P[t] = c0;
+          Q[t] = make_double2(0.0, 0.0);
+          idx[t] = 0;
+        }
+        for (int m = 1; m <= L; ++m) {
+          double2 a = se[(size_t)(L + m) * NL], b = se[(size_t)(L - m) * NL];
+          const double2 a2 = sod[(size_t)(L + m) * NL], b2 = sod[(size_t)(L - m) * NL];
+          a.x += so * a2.x; a.y += so * a2.y;
+          b.x += so * b2.x; b.y += so * b2.y;
+          const double2 E = make_double2(a.x + b.x, a.y + b.y), O = make_double2(a.x - b.x, a.y - b.y);
+#pragma unroll
+          for (int t = 0; t < IS_DCA; ++t) {
+            int k = idx[t] + d0 + t;
+            k -= (k >= F) ? F : 0;
+            idx[t] = k;
+            const double2 w = tw[k];
+            P[t].x = fma(E.x, w.x, P[t].x);
+            P[t].y = fma(E.y, w.x, P[t].y);
+            Q[t].x = fma(O.x, w.y, Q[t].x);
+            Q[t].y = fma(O.y, w.y, Q[t].y);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < IS_DCA; ++t) {
+          const int d = d0 + t;
+          if (d < H) {
+            // e^{+i}: U[d] = P + iQ, U[F-d] = P - iQ
+            U[((size_t)d * KC + kk) * M2p + m2] = make_double2(P[t].x - Q[t].y, P[t].y + Q[t].x);
+            if (d != 0 && 2 * d != F)
+              U[((size_t)(F - d) * KC + kk) * M2p + m2] = make_double2(P[t].x + Q[t].y, P[t].y - Q[t].x);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- stage B: lines (a, kk), half-complex -> real, arg-max
+    double bv = -1e300;
+    long long bi = 0x7fffffffffffffffLL;
+    {
+      const int nch = (H + IS_DCB - 1) / IS_DCB;
+      for (int item = tid; item < F * KC * nch; item += IS_THREADS) {
+        const int line = item % (F * KC), ch = item / (F * KC);
+        const int a = line / KC, kk = line - a * KC;
+        const int d0 = ch * IS_DCB;
+        const double2* vin = U + (size_t)line * M2p;
+        const double v0 = vin[0].x;
+        double A[IS_DCB], Bq[IS_DCB];
+        int idx[IS_DCB];
+#pragma unroll
+        for (int t = 0; t < IS_DCB; ++t) {
+          A[t] = 0.0;
+          Bq[t] = 0.0;
+          idx[t] = 0;
+        }
+        for (int l = 1; l <= L; ++l) {
+          const double2 v = vin[l];
+#pragma unroll
+          for (int t = 0; t < IS_DCB; ++t) {
+            int k = idx[t] + d0 + t;
+            k -= (k >= F) ? F : 0;
+            idx[t] = k;
+            const double2 w = tw[k];
+            A[t] = fma(v.x, w.x, A[t]);
+            Bq[t] = fma(v.y, w.y, Bq[t]);
+          }
+        }
+        const long long base = ((long long)a * F + (k0 + kk)) * F;
+        double* grow = out.grid ? out.grid + ((p * norient + o) * (size_t)F * F * F + (size_t)base) : nullptr;
+#pragma unroll
+        for (int t = 0; t < IS_DCB; ++t) {
+          const int d = d0 + t;
+          if (d < H) {
+            const double aa = v0 + 2.0 * A[t], bb = 2.0 * Bq[t];
+            const double g1 = aa - bb;  // Re(V e^{+i theta}) = Vr cos - Vi sin
+            better_s(bv, bi, g1, base + d);
+            if (grow) grow[d] = g1;
+            if (d != 0 && 2 * d != F) {
+              const double g2 = aa + bb;
+              better_s(bv, bi, g2, base + (F - d));
+              if (grow) grow[F - d] = g2;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+      better_s(bv, bi, ov, oi);
+    }
+    long long* redi = (long long*)(red + 16);
+    if ((tid & 31) == 0) {
+      red[tid >> 5] = bv;
+      redi[tid >> 5] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < IS_THREADS / 32; ++w) better_s(bv, bi, red[w], redi[w]);
+      out.part_val[(p * norient + o) * nchunk + chunk] = bv;
+      out.part_idx[(p * norient + o) * nchunk + chunk] = bi;
+    }
+    __syncthreads();
+  }
+}
+
+// Grid value at integer point (a, k, g) by the direct Wigner sum (orientation sign so on odd l).
+__device__ double iso_point(const double2* __restrict__ Ip, const double* __restrict__ Dt, int L, int a,
+                            int k, int g, double so, int lane) {
+  const int W = 2 * L + 1, L1 = L + 1, F = 2 * L1;
+  double acc = 0.0;
+  for (int item = lane; item < L1 * W; item += 32) {
+    const int m1i = item % W, m2 = item / W;
+    const int m1 = m1i - L;
+    const int am1 = m1 < 0 ? -m1 : m1;
+    const int l0 = am1 > m2 ? am1 : m2;
+    double sr = 0.0, si = 0.0;
+    const double2* ip = Ip + (size_t)item * L1;
+    const double* dp = Dt + (size_t)item * L1 * F + k;
+    for (int l = l0; l <= L; ++l) {
+      const double dv = ((l & 1) ? so : 1.0) * dp[(size_t)l * F];
+      const double2 c = ip[l];
+      sr = fma(dv, c.x, sr);
+      si = fma(dv, c.y, si);
+    }
+    int e = (m1 * a + m2 * g) % F;
+    e += e < 0 ? F : 0;
+    double sn, cs;
+    sincospi(2.0 * (double)e / (double)F, &sn, &cs);
+    const double term = sr * cs - si * sn;
+    acc += (m2 == 0) ? term : 2.0 * term;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  return acc;
+}
+
+// One CTA (8 warps) per (pair, orientation): reduce the chunk maxima, then the 6 neighbours.
+__global__ void __launch_bounds__(256)
+sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, int L, int norient,
+                 int nchunk, const double* __restrict__ part_val, const long long* __restrict__ part_idx,
+                 long long* __restrict__ best_idx, double* __restrict__ best_val,
+                 double* __restrict__ frac_idx) {
+  __shared__ double nb[6];
+  const size_t po = blockIdx.x;
+  const size_t p = po / norient;
+  const int o = (int)(po % norient);
+  const int F = 2 * (L + 1);
+  double bv = -1e300;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int c = 0; c < nchunk; ++c) better_s(bv, bi, part_val[po * nchunk + c], part_idx[po * nchunk + c]);
+  const bool ok = bi != 0x7fffffffffffffffLL;
+  const int b3[3] = {ok ? (int)(bi / ((long long)F * F)) : 0, ok ? (int)((bi / F) % F) : 0,
+                     ok ? (int)(bi % F) : 0};
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < 6) {
+    const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
+    int q[3] = {b3[0], b3[1], b3[2]};
+    q[ax] = (q[ax] + sgn + F) % F;
+    const double v = iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, L, q[0], q[1], q[2],
+                               o ? -1.0 : 1.0, lane);
+    if (lane == 0) nb[w] = fabs(v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    best_val[po] = bv;
+    for (int ax = 0; ax < 3; ++ax) {
+      best_idx[po * 3 + ax] = b3[ax];
+      const double y1 = nb[2 * ax], y3 = nb[2 * ax + 1], y2 = fabs(bv);
+      frac_idx[po * 3 + ax] = (double)b3[ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+
+int grid_for(size_t total, int threads, int cap = 1 << 16) {
+  size_t b = (total + threads - 1) / threads;
+  if (b > (size_t)cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int ensure_wigner(fo_ctx* ctx, int L) {
+  if (ctx->wig.Jmax == L && ctx->wig.d_table) return FO_OK;
+  if (ctx->wig.d_table) {
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->wig.d_table);
+    ctx->wig.d_table = nullptr;
+    ctx->wig.Jmax = -1;
+  }
+  const size_t n = (size_t)(L + 1) * (2 * L + 1) * (L + 1) * (2 * L + 2);
+  cudaError_t e = cudaMalloc(&ctx->wig.d_table, n * 8);
+  if (e != cudaSuccess)
+    return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the Wigner table (%zu bytes) failed", n * 8);
+  sph_wigner_kernel<<<grid_for((size_t)(L + 1) * (2 * L + 1) * (2 * L + 2), 128), 128, 0, ctx->stream>>>(
+      L, ctx->wig.d_table);
+  FO_LAUNCH_CHECK(ctx);
+  ctx->wig.Jmax = L;
+  ctx->wig.bytes = n * 8;
+  return FO_OK;
+}
+
+int check_L(fo_ctx* ctx, int64_t L) {
+  if (L < 0 || L > 63) return fo_fail(ctx, FO_ERR_UNSUPPORTED, "Jmax=%lld outside 0..63", (long long)L);
+  return FO_OK;
+}
+
+size_t isoft_smem(int L, int KC) {
+  const int B = L + 1, W = 2 * L + 1, L1 = L + 1, F = 2 * B, M2p = L1 | 1;
+  return ((size_t)F + 2 * (size_t)W * KC * L1 + (size_t)F * KC * M2p) * 16 + 32 * 8;
+}
+
+// iSOFT + arg-max for npairs coefficient sets already in the Ihalf layout (device).
+int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int norient,
+              long long* d_best_idx, double* d_best_val, double* d_frac, double* d_grid) {
+  if (npairs == 0) return FO_OK;
+  FO_CHECK(ensure_wigner(ctx, L));
+  const int F = 2 * (L + 1);
+  int KC = 4;
+  while (KC > 1 && (isoft_smem(L, KC) > 100 * 1024 || F % KC)) KC >>= 1;
+  const size_t smem = isoft_smem(L, KC);
+  if (smem > ctx->prop.sharedMemPerBlockOptin)
+    return fo_fail(ctx, FO_ERR_UNSUPPORTED,
+                   "Jmax=%d needs %zu bytes of shared memory per block in the iSOFT kernel (> %zu); "
+                   "large-bandwidth transforms are not supported yet", L, smem,
+                   (size_t)ctx->prop.sharedMemPerBlockOptin);
+  const int nchunk = F / KC;
+  void* part = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * nchunk * 16, &part));
+  IsoOut o;
+  o.part_val = (double*)part;
+  o.part_idx = (long long*)(o.part_val + (size_t)npairs * norient * nchunk);
+  o.grid = d_grid;
+  {
+    fo_prof_scope prof(ctx, FO_PROF_SPH_ISOFT);
+    const unsigned blocks = (unsigned)(npairs * nchunk);
+    if (KC == 4) {
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sph_isoft_kernel<4><<<blocks, IS_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient, nchunk, o);
+    } else if (KC == 2) {
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sph_isoft_kernel<2><<<blocks, IS_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient, nchunk, o);
+    } else {
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sph_isoft_kernel<1><<<blocks, IS_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient, nchunk, o);
+    }
+    FO_LAUNCH_CHECK(ctx);
+    sph_final_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+        d_Ihalf, ctx->wig.d_table, L, norient, nchunk, o.part_val, o.part_idx, d_best_idx, d_best_val, d_frac);
+    FO_LAUNCH_CHECK(ctx);
+  }
+  return FO_OK;
+}
+
+size_t ihalf_elems(int L) { return (size_t)(L + 1) * (2 * L + 1) * (L + 1); }
+
+// group id per atom on the device (from the ctx permutation groups); atoms in no group get -1-i
+int upload_gid(fo_ctx* ctx, int64_t natoms, int** d_gid) {
+  std::vector<int> gid(natoms);
+  for (int64_t i = 0; i < natoms; ++i) gid[i] = -1 - (int)i;
+  const int ng = (int)ctx->h_goff.size() - 1;
+  for (int g = 0; g < ng; ++g)
+    for (int a = ctx->h_goff[g]; a < ctx->h_goff[g + 1]; ++a) gid[ctx->h_gidx[a]] = g;
+  void* p = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)natoms * 4 + 64, &p));
+  FO_CUDA(ctx, cudaMemcpyAsync(p, gid.data(), (size_t)natoms * 4, cudaMemcpyHostToDevice, ctx->stream));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // gid is a stack vector
+  *d_gid = (int*)p;
+  return FO_OK;
+}
+
+// direct coefficients of np pairs (device positions) into d_Ihalf
+int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t np, int64_t natoms, int L,
+               double sigma, const int* d_gid, double2* d_Ihalf, int* d_status, char* work) {
+  if (np == 0) return FO_OK;
+  const int NLM = nlm_of(L);
+  // work: YA | YB | RA | RB | Bes
+  double2* YA = (double2*)work;
+  double2* YB = YA + (size_t)np * natoms * NLM;
+  double* RA = (double*)(YB + (size_t)np * natoms * NLM);
+  double* RB = RA + (size_t)np * natoms;
+  double* Bes = RB + (size_t)np * natoms;
+  fo_prof_scope prof(ctx, FO_PROF_SPH_COEF);
+  const size_t tot = (size_t)np * natoms * (L + 1);
+  sph_prep_kernel<<<grid_for(tot, 128), 128, 0, ctx->stream>>>(d_posA, (int)natoms, L, (size_t)np, YA, RA, d_status);
+  FO_LAUNCH_CHECK(ctx);
+  sph_prep_kernel<<<grid_for(tot, 128), 128, 0, ctx->stream>>>(d_posB, (int)natoms, L, (size_t)np, YB, RB, d_status);
+  FO_LAUNCH_CHECK(ctx);
+  sph_bessel_kernel<<<grid_for((size_t)np * natoms * natoms, 128), 128, 0, ctx->stream>>>(
+      RA, RB, d_gid, (int)natoms, L, sigma, (size_t)np, Bes);
+  FO_LAUNCH_CHECK(ctx);
+  const size_t smem = ((size_t)(L + 1) * DIR_TK * 2 + (size_t)(2 * L + 1) * (L + 1)) * 16;
+  FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(L + 1), (unsigned)np);
+  sph_direct_kernel<<<grid, 128, smem, ctx->stream>>>(YA, YB, Bes, (int)natoms, L, d_Ihalf);
+  FO_LAUNCH_CHECK(ctx);
+  return FO_OK;
+}
+
+size_t direct_work_bytes(int64_t np, int64_t natoms, int L) {
+  const size_t NLM = nlm_of(L);
+  return (size_t)np * natoms * NLM * 32 + (size_t)np * natoms * 16 +
+         (size_t)np * (L + 1) * natoms * natoms * 8 + 256;
+}
+
+int64_t direct_chunk(int64_t npairs, int64_t natoms, int L, bool want_grid) {
+  const size_t per = direct_work_bytes(1, natoms, L) + ihalf_elems(L) * 16;
+  int64_t c = (int64_t)(((size_t)1 << 30) / per);
+  if (want_grid) {
+    const size_t g = (size_t)8 * 2 * (2 * L + 2) * (2 * L + 2) * (2 * L + 2);
+    int64_t cg = (int64_t)(((size_t)512 << 20) / g);
+    if (cg < c) c = cg;
+  }
+  if (c > 65535) c = 65535;  // gridDim.y
+  if (c < 1) c = 1;
+  if (c > npairs) c = npairs;
+  return c;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+
+extern "C" int fo_sph_wigner_table(fo_ctx* ctx, int64_t Jmax, double* out) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (!out) return fo_fail(ctx, FO_ERR_INVALID, "out is NULL");
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax;
+  FO_CHECK(ensure_wigner(ctx, L));
+  const size_t n = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1) * (2 * L + 2);
+  void* d = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, n * 8, &d));
+  sph_wigner_export_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->wig.d_table, L, (double*)d);
+  FO_LAUNCH_CHECK(ctx);
+  FO_CUDA(ctx, cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FO_OK;
+}
+
+extern "C" int fo_sph_isoft_argmax(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax,
+                                   int invert, int64_t* best_idx, double* best_val, double* frac_idx,
+                                   double* grid_out) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (npairs < 0 || (npairs > 0 && (!Ilmm || !best_idx || !best_val || !frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_isoft_argmax: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax, O = invert ? 2 : 1;
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
+  const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + ihalf_elems(L) * 16 + (grid_out ? O * G3 * 8 : 0)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *dfull, *dhalf, *dout, *dgrid = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * O * 64, &dout));
+  if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    FO_CUDA(ctx, cudaMemcpyAsync(dfull, Ilmm + (size_t)p0 * full * 2, (size_t)np * full * 16,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    sph_pack_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
+        (const double2*)dfull, L, (size_t)np, 0, (double2*)dhalf);
+    FO_LAUNCH_CHECK(ctx);
+    long long* d_bi = (long long*)dout;
+    double* d_bv = (double*)((char*)dout + (size_t)np * O * 24);
+    double* d_fr = (double*)((char*)dout + (size_t)np * O * 32);
+    FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, d_bi, d_bv, d_fr, (double*)dgrid));
+    FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (grid_out)
+      FO_CUDA(ctx, cudaMemcpyAsync(grid_out + (size_t)p0 * O * G3, dgrid, (size_t)np * O * G3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_sph_isoft(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax, double* grid_re,
+                            double* grid_im) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (npairs < 0 || (npairs > 0 && (!Ilmm || !grid_re)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_isoft: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax;
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
+  const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + ihalf_elems(L) * 16 + G3 * 8));
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *dfull, *dhalf, *dout, *dgrid;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dout));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * G3 * 8, &dgrid));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    FO_CUDA(ctx, cudaMemcpyAsync(dfull, Ilmm + (size_t)p0 * full * 2, (size_t)np * full * 16,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    for (int part = 0; part < (grid_im ? 2 : 1); ++part) {
+      sph_pack_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
+          (const double2*)dfull, L, (size_t)np, part, (double2*)dhalf);
+      FO_LAUNCH_CHECK(ctx);
+      FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, 1, (long long*)dout,
+                         (double*)((char*)dout + (size_t)np * 24), (double*)((char*)dout + (size_t)np * 32),
+                         (double*)dgrid));
+      FO_CUDA(ctx, cudaMemcpyAsync((part ? grid_im : grid_re) + (size_t)p0 * G3, dgrid, (size_t)np * G3 * 8,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+      FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_sph_coeffs_direct(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                                    int64_t natoms, int64_t Jmax, double sigma, double* Ilmm_out,
+                                    int32_t* status) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (natoms < 1 || !(sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 and sigma > 0 required");
+  if (npairs < 0 || (npairs > 0 && (!posA || !posB || !Ilmm_out)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_coeffs_direct: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, natoms));
+  const int L = (int)Jmax;
+  int* d_gid = nullptr;
+  FO_CHECK(upload_gid(ctx, natoms, &d_gid));
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
+  int64_t chunk = direct_chunk(npairs, natoms, L, false);
+  void *dA, *dB, *work, *dhalf, *dfull, *dst;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * natoms * 24, &dA));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, (size_t)chunk * natoms * 24, &dB));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(chunk, natoms, L), &work));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 4 + 64, &dst));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    FO_CUDA(ctx, cudaMemcpyAsync(dA, posA + (size_t)p0 * natoms * 3, (size_t)np * natoms * 24, cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(dB, posB + (size_t)p0 * natoms * 3, (size_t)np * natoms * 24, cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)np * 4, ctx->stream));
+    FO_CHECK(run_direct(ctx, (const double*)dA, (const double*)dB, np, natoms, L, sigma, d_gid,
+                        (double2*)dhalf, (int*)dst, (char*)work));
+    sph_unpack_kernel<<<grid_for((size_t)np * full, 256), 256, 0, ctx->stream>>>((const double2*)dhalf, L, (size_t)np, (double2*)dfull);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CUDA(ctx, cudaMemcpyAsync(Ilmm_out + (size_t)p0 * full * 2, dfull, (size_t)np * full * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status)
+      FO_CUDA(ctx, cudaMemcpyAsync(status + p0, dst, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
+                                      int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
+                                      int invert, int64_t* d_best_idx, double* d_best_val,
+                                      double* d_frac_idx, double* d_grid_out, int32_t* d_status) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (natoms < 1 || !(sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 and sigma > 0 required");
+  if (npairs < 0 || (npairs > 0 && (!d_posA || !d_posB || !d_best_idx || !d_best_val || !d_frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_pairs_dev: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, natoms));
+  const int L = (int)Jmax, O = invert ? 2 : 1;
+  int* d_gid = nullptr;
+  FO_CHECK(upload_gid(ctx, natoms, &d_gid));
+  const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
+  const int64_t chunk = direct_chunk(npairs, natoms, L, false);
+  void *work, *dhalf;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(chunk, natoms, L), &work));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  if (d_status) FO_CUDA(ctx, cudaMemsetAsync(d_status, 0, (size_t)npairs * 4, ctx->stream));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    FO_CHECK(run_direct(ctx, d_posA + (size_t)p0 * natoms * 3, d_posB + (size_t)p0 * natoms * 3, np, natoms,
+                        L, sigma, d_gid, (double2*)dhalf, d_status ? d_status + p0 : nullptr, (char*)work));
+    FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, (long long*)d_best_idx + (size_t)p0 * O * 3,
+                       d_best_val + (size_t)p0 * O, d_frac_idx + (size_t)p0 * O * 3,
+                       d_grid_out ? d_grid_out + (size_t)p0 * O * G3 : nullptr));
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                                  int64_t natoms, int64_t Jmax, double sigma, int invert,
+                                  int64_t* best_idx, double* best_val, double* frac_idx, double* grid_out,
+                                  int32_t* status) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (natoms < 1 || !(sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 and sigma > 0 required");
+  if (npairs < 0 || (npairs > 0 && (!posA || !posB || !best_idx || !best_val || !frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_pairs: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax, O = invert ? 2 : 1;
+  const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
+  const int64_t chunk = direct_chunk(npairs, natoms, L, grid_out != nullptr);
+  const size_t pos_bytes = (size_t)chunk * natoms * 24;
+  void *dA, *dB, *dout, *dgrid = nullptr, *hA, *hB;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, 2 * pos_bytes, &dA));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * (O * 56 + 8) + 256, &dout));
+  if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
+  FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
+  FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
+  const int64_t nchunks = (npairs + chunk - 1) / chunk;
+  auto stage_in = [&](int64_t c) -> int {
+    const int64_t p0 = c * chunk;
+    const int64_t np = std::min(chunk, npairs - p0);
+    const int buf = (int)(c & 1);
+    const size_t nb = (size_t)np * natoms * 24;
+    if (c >= 2) FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[buf]));
+    memcpy((char*)hA + buf * pos_bytes, posA + (size_t)p0 * natoms * 3, nb);
+    memcpy((char*)hB + buf * pos_bytes, posB + (size_t)p0 * natoms * 3, nb);
+    if (c >= 2) FO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2 + buf], 0));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dA + buf * pos_bytes, (char*)hA + buf * pos_bytes, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dB + buf * pos_bytes, (char*)hB + buf * pos_bytes, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
+    return FO_OK;
+  };
+  FO_CHECK(stage_in(0));
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t p0 = c * chunk;
+    const int64_t np = std::min(chunk, npairs - p0);
+    const int buf = (int)(c & 1);
+    if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
+    FO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[buf], 0));
+    long long* d_bi = (long long*)dout;
+    double* d_bv = (double*)((char*)dout + (size_t)np * O * 24);
+    double* d_fr = (double*)((char*)dout + (size_t)np * O * 32);
+    int* d_st = (int*)((char*)dout + (size_t)np * O * 56);
+    FO_CHECK(fo_sph_align_pairs_dev(ctx, (const double*)((char*)dA + buf * pos_bytes),
+                                    (const double*)((char*)dB + buf * pos_bytes), np, natoms, Jmax, sigma,
+                                    invert, (int64_t*)d_bi, d_bv, d_fr, (double*)dgrid, d_st));
+    FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status)
+      FO_CUDA(ctx, cudaMemcpyAsync(status + p0, d_st, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (grid_out)
+      FO_CUDA(ctx, cudaMemcpyAsync(grid_out + (size_t)p0 * O * G3, dgrid, (size_t)np * O * G3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FO_OK;
+}
+
+namespace {
+// harmonic coefficients of nstruct structures (device positions) into d_Cpk
+int run_harm(fo_ctx* ctx, const double* d_pos, int64_t ns, int64_t natoms, int nmax, int L, double r0,
+             double sigma, double2* d_Cpk, int* d_status, char* work) {
+  if (ns == 0) return FO_OK;
+  const int NLM = nlm_of(L);
+  const int ng = (int)ctx->h_goff.size() - 1;
+  if ((nmax + 1) * NLM > 16 * 256)
+    return fo_fail(ctx, FO_ERR_UNSUPPORTED, "(nmax+1)*(Jmax+1)(Jmax+2)/2 = %d exceeds 4096",
+                   (nmax + 1) * NLM);
+  double2* Y = (double2*)work;
+  double* R = (double*)(Y + (size_t)ns * natoms * NLM);
+  fo_prof_scope prof(ctx, FO_PROF_SPH_HARM);
+  sph_prep_kernel<<<grid_for((size_t)ns * natoms * (L + 1), 128), 128, 0, ctx->stream>>>(
+      d_pos, (int)natoms, L, (size_t)ns, Y, R, d_status);
+  FO_LAUNCH_CHECK(ctx);
+  const size_t smem = (size_t)HARM_TA * (nmax + 1) * (L + 1) * 8 + (size_t)HARM_TA * NLM * 16;
+  FO_CUDA(ctx, cudaFuncSetAttribute(sph_harm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ns, (unsigned)ng);
+  sph_harm_kernel<<<grid, 256, smem, ctx->stream>>>(Y, R, ctx->d_goff, ctx->d_gidx, ng, (int)natoms, nmax, L,
+                                                    r0, sigma, d_Cpk);
+  FO_LAUNCH_CHECK(ctx);
+  return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_sph_harm_coeffs(fo_ctx* ctx, const double* pos, int64_t nstruct, int64_t natoms,
+                                  int64_t nmax, int64_t Jmax, double harmscale, double sigma, double* out,
+                                  int32_t* status) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (natoms < 1 || nmax < 0 || nmax > 255 || !(sigma > 0.0) || !(harmscale > 0.0))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_harm_coeffs: bad size / scale");
+  if (nstruct < 0 || (nstruct > 0 && (!pos || !out))) return fo_fail(ctx, FO_ERR_INVALID, "NULL argument");
+  if (nstruct == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, natoms));
+  const int L = (int)Jmax, NLM = nlm_of(L);
+  const int ng = (int)ctx->h_goff.size() - 1;
+  const size_t cpk = (size_t)ng * (nmax + 1) * NLM, full = (size_t)ng * (nmax + 1) * (L + 1) * (2 * L + 1);
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + cpk * 16 + (size_t)natoms * NLM * 16 + 64));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nstruct) chunk = nstruct;
+  void *dpos, *work, *dc, *dfull, *dst;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * natoms * 24, &dpos));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, (size_t)chunk * natoms * (NLM * 16 + 8) + 256, &work));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * cpk * 16, &dc));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 4 + 64, &dst));
+  for (int64_t s0 = 0; s0 < nstruct; s0 += chunk) {
+    const int64_t ns = std::min(chunk, nstruct - s0);
+    FO_CUDA(ctx, cudaMemcpyAsync(dpos, pos + (size_t)s0 * natoms * 3, (size_t)ns * natoms * 24, cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)ns * 4, ctx->stream));
+    FO_CHECK(run_harm(ctx, (const double*)dpos, ns, natoms, (int)nmax, L, harmscale, sigma, (double2*)dc, (int*)dst, (char*)work));
+    sph_harm_expand_kernel<<<grid_for((size_t)ns * full, 256), 256, 0, ctx->stream>>>(
+        (const double2*)dc, (int)nmax, L, (size_t)ns * ng, (double2*)dfull);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CUDA(ctx, cudaMemcpyAsync(out + (size_t)s0 * full * 2, dfull, (size_t)ns * full * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) FO_CUDA(ctx, cudaMemcpyAsync(status + s0, dst, (size_t)ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_sph_bank_create(fo_ctx* ctx, const double* pos, int64_t nstruct, int64_t natoms,
+                                  int64_t nmax, int64_t Jmax, double harmscale, double sigma, fo_bank** out) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (!out || !pos || nstruct < 1 || natoms < 1 || nmax < 0 || nmax > 255 || !(sigma > 0.0) || !(harmscale > 0.0))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_bank_create: bad argument");
+  *out = nullptr;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, natoms));
+  const int L = (int)Jmax, NLM = nlm_of(L);
+  const int ng = (int)ctx->h_goff.size() - 1;
+  fo_bank* b = new (std::nothrow) fo_bank();
+  if (!b) return fo_fail(ctx, FO_ERR_NOMEM, "out of host memory");
+  b->kind = 2;
+  b->nstruct = nstruct;
+  b->ngroups = ng;
+  b->nmax = nmax;
+  b->Jmax = Jmax;
+  b->natoms = natoms;
+  b->sigma = sigma;
+  b->harmscale = harmscale;
+  b->per_struct_elems = (int64_t)ng * (nmax + 1) * NLM;
+  if (cudaMalloc(&b->d_data, (size_t)nstruct * b->per_struct_elems * 16) != cudaSuccess) {
+    delete b;
+    return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the coefficient bank failed");
+  }
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / ((size_t)natoms * (NLM * 16 + 32)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nstruct) chunk = nstruct;
+  void *dpos = nullptr, *work = nullptr;
+  int rc = fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * natoms * 24, &dpos);
+  if (rc == FO_OK) rc = fo_scratch(ctx, FO_SCR_WORK, (size_t)chunk * natoms * (NLM * 16 + 8) + 256, &work);
+  for (int64_t s0 = 0; rc == FO_OK && s0 < nstruct; s0 += chunk) {
+    const int64_t ns = std::min(chunk, nstruct - s0);
+    if (cudaMemcpyAsync(dpos, pos + (size_t)s0 * natoms * 3, (size_t)ns * natoms * 24, cudaMemcpyHostToDevice,
+                        ctx->stream) != cudaSuccess) {
+      rc = fo_fail(ctx, FO_ERR_CUDA, "H2D copy failed");
+      break;
+    }
+    rc = run_harm(ctx, (const double*)dpos, ns, natoms, (int)nmax, L, harmscale, sigma,
+                  (double2*)b->d_data + (size_t)s0 * b->per_struct_elems, nullptr, (char*)work);
+    if (rc == FO_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      rc = fo_fail(ctx, FO_ERR_CUDA, "harmonic coefficient kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (rc != FO_OK) {
+    cudaFree(b->d_data);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return FO_OK;
+}
+
+extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs, int64_t npairs,
+                                 int invert, int64_t* best_idx, double* best_val, double* frac_idx,
+                                 double* avg_overlap, double* grid_out) {
+  if (!ctx) return FO_ERR_INVALID;
+  if (!bank || bank->kind != 2) return fo_fail(ctx, FO_ERR_INVALID, "not a spherical coefficient bank");
+  if (npairs < 0 || (npairs > 0 && (!pairs || !best_idx || !best_val || !frac_idx)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_bank: NULL argument");
+  for (int64_t i = 0; i < 2 * npairs; ++i)
+    if (pairs[i] < 0 || pairs[i] >= bank->nstruct)
+      return fo_fail(ctx, FO_ERR_INVALID, "pair index %lld out of range", (long long)pairs[i]);
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)bank->Jmax, O = invert ? 2 : 1;
+  const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
+  int64_t chunk = (int64_t)(((size_t)512 << 20) / (ihalf_elems(L) * 16 + (grid_out ? O * G3 * 8 : 0)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *dhalf, *dout, *dpairs, *dgrid = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * (O * 56 + 8) + 256, &dout));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * 16, &dpairs));
+  if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    FO_CUDA(ctx, cudaMemcpyAsync(dpairs, pairs + 2 * p0, (size_t)np * 16, cudaMemcpyHostToDevice, ctx->stream));
+    long long* d_bi = (long long*)dout;
+    double* d_bv = (double*)((char*)dout + (size_t)np * O * 24);
+    double* d_fr = (double*)((char*)dout + (size_t)np * O * 32);
+    double* d_avg = (double*)((char*)dout + (size_t)np * O * 56);
+    {
+      fo_prof_scope prof(ctx, FO_PROF_SPH_DOT);
+      sph_dot_kernel<<<(unsigned)np, 256, 0, ctx->stream>>>((const double2*)bank->d_data, (const long long*)dpairs,
+                                                            (int)bank->ngroups, (int)bank->nmax, L, (double2*)dhalf, d_avg);
+      FO_LAUNCH_CHECK(ctx);
+    }
+    FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, d_bi, d_bv, d_fr, (double*)dgrid));
+    FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (avg_overlap)
+      FO_CUDA(ctx, cudaMemcpyAsync(avg_overlap + p0, d_avg, (size_t)np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (grid_out)
+      FO_CUDA(ctx, cudaMemcpyAsync(grid_out + (size_t)p0 * O * G3, dgrid, (size_t)np * O * G3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}

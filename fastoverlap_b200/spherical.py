@@ -1,0 +1,394 @@
+"""SphericalAlign / SphericalHarmonicAlign -- drop-ins for reference
+fastoverlap/sphericalAlignment.py:29-414 with the hot path (coefficients, inverse SO(3) transform,
+arg-max) on the GPU through the C ABI.  Host side (stays on the CPU, north_star): centring,
+Hungarian permutation, Kearsley rotation, optional continuous refinement of the rotation.
+
+Orientation rule.  The reference's numpy classes choose between the normal and the
+inverted orientation by comparing L-BFGS-refined overlap values; its Fortran path refines both
+and keeps the smaller distance.  Default here: orientation="distance" (Fortran rule; never worse
+than the numpy rule and needs no optimiser).  orientation="overlap" reproduces the numpy rule.
+"""
+import numpy as np
+from numpy import sin, cos, sqrt, exp, pi
+from numpy.linalg import norm
+
+from . import _lib
+from .soft import SOFT
+from .utils import find_best_permutation, EulerM, findMax, findrotation, indtoEuler
+
+
+def isoft_executed_flops(Jmax, invert=True):
+    """FP64 flop executed by sph_isoft_kernel per pair (DFMA = 2): Wigner contraction shared by both
+    orientations + per orientation the two symmetric 1-D transform stages."""
+    L = Jmax
+    B, W, L1, F, H = L + 1, 2 * L + 1, L + 1, 2 * L + 2, L + 2
+    nnz_half = sum((2 * l + 1) * (l + 1) for l in range(L + 1))
+    k5 = 2 * nnz_half * F                       # real x complex DFMA pairs
+    stage_a = F * L1 * H * L * 4                # lines (k, m2) x outputs x m x 4 DFMA
+    stage_b = F * F * H * L * 2                 # lines (a, k) x outputs x m2 x 2 DFMA
+    O = 2 if invert else 1
+    return 2 * (k5 + O * (stage_a + stage_b))
+
+
+class BaseSphericalAlignment(object):
+    calcScale = True
+    orientation = "distance"
+
+    # -- plumbing
+    @property
+    def ctx(self):
+        if getattr(self, "_ctx", None) is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
+
+    def calcSO3Coeffs(self, pos1, pos2):
+        raise NotImplementedError
+
+    def averageSeparation(self, pos):
+        """Mean nearest-neighbour distance (reference :35-41)."""
+        pos = np.asanyarray(pos).reshape(-1, 3)
+        d = norm(pos[:, None, :] - pos[None, :, :], axis=2)
+        np.fill_diagonal(d, np.inf)
+        return d.min(1).sum() / len(pos)
+
+    def setJ(self, Jmax):
+        self.Jmax = Jmax
+        self.J = np.arange(Jmax + 1)
+        self.soft = SOFT(Jmax + 1, ctx=getattr(self, "_ctx", None))
+        self.Js, self.m1s, self.m2s = map(np.array, zip(*[(l, m1, m2) for l in range(Jmax + 1)
+                                                           for m1 in range(-l, l + 1)
+                                                           for m2 in range(-l, l + 1)]))
+
+    def _perm(self, n, perm=None):
+        if perm is None:
+            perm = [np.arange(n)] if self.perm is None else self.perm
+        return perm
+
+    def Hungarian(self, pos1, pos2, perm=None):
+        return find_best_permutation(pos1, pos2, permlist=self._perm(len(pos1), perm))
+
+    def rotate(self, X, R):
+        return X.dot(EulerM(*R))
+
+    def refine(self, X1, X2, R, permlist=None):
+        """Rotate X2 by the Euler angles R, permute (Hungarian), then Kearsley (reference :118-127)."""
+        permlist = self._perm(len(X1), permlist)
+        X2 = np.dot(X2, EulerM(*R))
+        _, perm = self.Hungarian(X1, X2, permlist)
+        dist, MR = findrotation(X1, X2[perm])
+        return dist, X1, X2[perm].dot(MR.T)
+
+    def COM_shift(self, pos1, pos2):
+        X1 = np.array(pos1, float)
+        X2 = np.array(pos2, float)
+        X1 -= X1.mean(axis=0)[None, :]
+        X2 -= X2.mean(axis=0)[None, :]
+        return X1, X2
+
+    # -- continuous refinement of the rotation on the host (reference :67-113), numpy rule only
+    def calcWignerMatrices(self, rot):
+        from scipy.special import eval_jacobi, gammaln
+        a, b, y = rot
+        Js, m1s, m2s = self.Js, self.m1s, self.m2s
+        Jmax = self.Jmax
+        mu, nu = abs(m1s - m2s), abs(m1s + m2s)
+        s = Js - (mu + nu) // 2
+        xi = np.where(m2s < m1s, (-1.0) ** (m1s - m2s), 1.0)
+        factor = np.exp(0.5 * (gammaln(s + 1) + gammaln(s + mu + nu + 1) - gammaln(s + mu + 1) -
+                               gammaln(s + nu + 1))) * xi
+        sb2, cb2, cb, sb = sin(b / 2), cos(b / 2), cos(b), sin(b)
+        jac = eval_jacobi(s, mu, nu, cb)
+        d = factor * jac * sb2 ** mu * cb2 ** nu
+        gfact = 0.5 * (mu + nu + s + 1.0)
+        gjac = np.where(s > 0, eval_jacobi(np.maximum(s - 1, 0), mu + 1, nu + 1, cb), 0.0) * gfact * -sb
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gd = (factor * gjac * sb2 ** mu * cb2 ** nu +
+                  np.where(mu > 0, factor * jac * sb2 ** (mu - 1.0) * cb2 ** (nu + 1.0) * mu / 2, 0.0) -
+                  np.where(nu > 0, factor * jac * sb2 ** (mu + 1.0) * cb2 ** (nu - 1.0) * nu / 2, 0.0))
+        Ds = np.zeros((Jmax + 1, 2 * Jmax + 1, 2 * Jmax + 1), np.complex128)
+        grad = np.zeros((3,) + Ds.shape, np.complex128)
+        ph = exp(-1j * m1s * a) * exp(-1j * m2s * y)
+        Ds[Js, m1s, m2s] = ph * d
+        grad[0, Js, m1s, m2s] = -1j * m1s * Ds[Js, m1s, m2s]
+        grad[1, Js, m1s, m2s] = ph * gd
+        grad[2, Js, m1s, m2s] = -1j * m2s * Ds[Js, m1s, m2s]
+        return Ds, grad
+
+    def getEnergyGradient(self, rot, Ilmm):
+        D, gradD = self.calcWignerMatrices(rot)
+        return -(Ilmm * D).real.sum(), -(Ilmm[None, ...] * gradD).real.sum((1, 2, 3))
+
+    def maxOverlap(self, R, Ilmm):
+        from scipy.optimize import minimize
+        res = minimize(self.getEnergyGradient, R, jac=True, args=(Ilmm,), method='L-BFGS-B')
+        return res.x, res
+
+    # -- hot path wrappers
+    def _grid_search(self, X1, X2, perm, invert, want_grid=False, calcCoeffs=None):
+        """Both orientations: Euler angles of the interpolated grid maximum (GPU)."""
+        raise NotImplementedError
+
+    def findRotation(self, Ilmm):
+        """Grid arg-max -> Euler angles -> host L-BFGS refinement (reference :190-194)."""
+        bi, bv, fr, _ = self.ctx.sph_isoft_argmax(Ilmm, self.Jmax)
+        R = self.soft.indtoEuler(fr[0, 0])
+        R, res = self.maxOverlap(R, np.conj(Ilmm))
+        return R, res.fun
+
+    def findRotations(self, Ilmm, nrot=10, width=2):
+        """Top-nrot rotations by Gaussian fit-and-subtract on the GPU-computed grid (reference :196-204)."""
+        from .peaks import findPeaks
+        overlap = self.ctx.sph_isoft(Ilmm, self.Jmax, want_imag=False)[0]
+        peaks = []
+        while len(peaks) == 0:
+            peaks, amplitude, mean, sigma, f = findPeaks(overlap, npeaks=nrot, width=width)
+            width += 1
+        return np.atleast_2d(self.soft.indtoEuler(peaks)), amplitude, mean, sigma, f
+
+    def _setup(self, pos1, pos2, perm):
+        pos1 = np.asanyarray(pos1, dtype=float).reshape(-1, 3)
+        pos2 = np.asanyarray(pos2, dtype=float).reshape(-1, 3)
+        if self.calcScale:
+            self.scale = (self.averageSeparation(pos1) + self.averageSeparation(pos2)) / 6
+        perm = self._perm(len(pos1), perm)
+        X1, X2 = self.COM_shift(pos1, pos2)
+        return X1, X2, perm
+
+    def align(self, pos1, pos2, perm=None, invert=True, calcCoeffs=None):
+        """(dist, X1, X2) for the best of the normal / inverted orientation (reference :160-188)."""
+        X1, X2, perm = self._setup(pos1, pos2, perm)
+        if self.orientation == "overlap" or calcCoeffs is not None:
+            # numpy rule: compare the L-BFGS-refined overlaps of the two orientations
+            Ilmm = self._coeffs(X1, X2, perm) if calcCoeffs is None else calcCoeffs(False)
+            R, res = self.findRotation(Ilmm)
+            if invert:
+                Ilmm = self._coeffs(X1, -X2, perm) if calcCoeffs is None else calcCoeffs(True)
+                invR, invres = self.findRotation(Ilmm)
+                if invres < res:
+                    R = invR
+                    X2 = -X2
+            return self.refine(X1, X2, R, perm)
+        Rs = self._grid_search(X1, X2, perm, invert)
+        best = self.refine(X1, X2, Rs[0], perm)
+        if invert:
+            inv = self.refine(X1, -X2, Rs[1], perm)
+            if inv[0] < best[0]:
+                best = inv
+        return best
+
+    def malign(self, pos1, pos2, perm=None, invert=True, calcCoeffs=None, nrot=10):
+        """Try the nrot best rotations of each orientation (reference :206-235)."""
+        X1, X2, perm = self._setup(pos1, pos2, perm)
+        Ilmm = self._coeffs(X1, X2, perm) if calcCoeffs is None else calcCoeffs(False)
+        Rs = self.findRotations(Ilmm, nrot)[0]
+        best = min((self.refine(X1, X2, R, perm) for R in Rs), key=lambda x: x[0])
+        if invert:
+            Ilmm = self._coeffs(X1, -X2, perm) if calcCoeffs is None else calcCoeffs(True)
+            Rs = self.findRotations(Ilmm, nrot)[0]
+            inv = min((self.refine(X1, -X2, R, perm) for R in Rs), key=lambda x: x[0])
+            if inv[0] < best[0]:
+                return inv
+        return best
+
+    def __call__(self, pos1, pos2, perm=None, invert=True, calcCoeffs=None, nrot=10, niter=None):
+        dist, X1, X2 = self.align(pos1, pos2, perm, invert, calcCoeffs)
+        if (norm(X1 - X2, axis=1) > self.scale).sum() > len(X1) / 3:
+            try:
+                mdist, mX1, mX2 = self.malign(pos1, pos2, perm, invert, calcCoeffs, nrot)
+                if mdist < dist:
+                    return mdist, mX1, mX2
+            except Exception:
+                pass
+        return dist, X1, X2
+
+    # -- batched, additive API
+    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True):
+        """P independent pairs: one GPU call for the whole batch, host refine per pair.
+        Returns dists (P,) and the Euler angles (P, O, 3)."""
+        pos1 = np.asarray(pos1, float)
+        pos2 = np.asarray(pos2, float)
+        X1 = pos1 - pos1.mean(1, keepdims=True)
+        X2 = pos2 - pos2.mean(1, keepdims=True)
+        perm = self._perm(X1.shape[1], perm)
+        Rs = self._grid_search(X1, X2, perm, invert)
+        Rs = Rs.reshape(len(X1), -1, 3)
+        if not refine:
+            return None, Rs
+        dists = np.empty(len(X1))
+        for i in range(len(X1)):
+            d = self.refine(X1[i], X2[i], Rs[i, 0], perm)[0]
+            if invert:
+                d = min(d, self.refine(X1[i], -X2[i], Rs[i, 1], perm)[0])
+            dists[i] = d
+        return dists, Rs
+
+
+class SphericalAlign(BaseSphericalAlignment):
+    """Direct (N^2 Bessel) overlap coefficients (reference :250-273)."""
+
+    def __init__(self, scale=None, Jmax=15, perm=None, ctx=None, orientation="distance"):
+        self._ctx = ctx
+        if scale is not None:
+            self.scale = scale
+            self.calcScale = False
+        else:
+            self.calcScale = True
+        self.orientation = orientation
+        self.setJ(Jmax)
+        self.perm = perm
+
+    def calcSO3Coeffs(self, pos1, pos2):
+        """I[l, m1, m2] of two (already gathered) atom sets (reference :260-273) -- on the GPU."""
+        pos1 = np.atleast_2d(pos1)
+        pos2 = np.atleast_2d(pos2)
+        assert pos1.shape == pos2.shape
+        self.ctx.set_perm([np.arange(len(pos1))], len(pos1))
+        return self.ctx.sph_coeffs_direct(pos1, pos2, self.Jmax, self.scale)[0][0]
+
+    def _coeffs(self, X1, X2, perm):
+        """sum over permutation groups of calcSO3Coeffs (reference :175) in one call."""
+        self.ctx.set_perm(perm, len(X1))
+        return self.ctx.sph_coeffs_direct(X1, X2, self.Jmax, self.scale)[0][0]
+
+    def _grid_search(self, X1, X2, perm, invert, want_grid=False, calcCoeffs=None):
+        n = X1.shape[-2]
+        self.ctx.set_perm(perm, n)
+        bi, bv, fr, grid, st = self.ctx.sph_align_pairs(X1, X2, self.Jmax, self.scale, invert=invert,
+                                                        want_grid=want_grid)
+        self._best_idx, self._best_val, self._frac_idx, self._grid = bi, bv, fr, grid
+        R = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
+        return R[0] if X1.ndim == 2 else R
+
+
+class SphericalHarmonicAlign(BaseSphericalAlignment):
+    """Harmonic-oscillator radial basis coefficients C_nlm (reference :276-414)."""
+
+    def __init__(self, scale=None, harmscale=1.0, nmax=15, Jmax=15, perm=None, ctx=None,
+                 orientation="distance"):
+        self._ctx = ctx
+        if scale is not None:
+            self.scale = scale
+            self.calcScale = False
+        else:
+            self.calcScale = True
+        self.orientation = orientation
+        self.harmscale = harmscale
+        self.nmax = nmax
+        self.setJ(Jmax)
+        self.perm = perm
+
+    def setCoeffs(self, nmax=None, Jmax=None, harmscale=None):
+        if nmax is not None:
+            self.nmax = nmax
+        if Jmax is not None:
+            self.setJ(Jmax)
+        if harmscale is not None:
+            self.harmscale = harmscale
+
+    def calcHarmCoeff(self, pos):
+        """C[n, l, m] of one atom set (reference :345-361) -- on the GPU."""
+        pos = np.atleast_2d(pos)
+        self.ctx.set_perm([np.arange(len(pos))], len(pos))
+        return self.ctx.sph_harm_coeffs(pos, self.nmax, self.Jmax, self.harmscale, self.scale)[0][0, 0]
+
+    def calcSO3Coeffs(self, pos1, pos2):
+        pos1 = np.atleast_2d(pos1)
+        pos2 = np.atleast_2d(pos2)
+        return self._coeffs(pos1, pos2, [np.arange(len(pos1))])
+
+    def _bank_pair(self, X1, X2, perm, invert, want_grid=False):
+        self.ctx.set_perm(perm, len(X1))
+        bank = self.ctx.sph_bank_create(np.stack([X1, X2]), self.nmax, self.Jmax, self.harmscale, self.scale)
+        try:
+            return self.ctx.sph_align_bank(bank, np.array([[0, 1]]), invert=invert, want_grid=want_grid)
+        finally:
+            bank.close()
+
+    def _coeffs(self, X1, X2, perm):
+        """I[l,m1,m2] = sum_groups sum_n conj(C1) C2 (reference :363-372)."""
+        self.ctx.set_perm(perm, len(X1))
+        C, _ = self.ctx.sph_harm_coeffs(np.stack([X1, X2]), self.nmax, self.Jmax, self.harmscale, self.scale)
+        return self.calcSO3Harm(C[0], C[1])
+
+    def calcSO3Harm(self, c1nlms, c2nlms, invert=False):
+        """Contraction of host-resident coefficient arrays (reference :368-372).  Host einsum: this
+        entry point exists for API compatibility; the alignment path contracts device-resident banks
+        (fo_sph_align_bank)."""
+        c1 = np.asarray(c1nlms)
+        c2 = np.asarray(c2nlms)
+        if c1.ndim == 3:
+            c1, c2 = c1[None], c2[None]
+        if invert:
+            c2 = c2 * (-1.0) ** self.J[None, None, :, None]
+        return np.einsum("gnlm,gnlo->lmo", c1.conj(), c2)
+
+    def _grid_search(self, X1, X2, perm, invert, want_grid=False, calcCoeffs=None):
+        if X1.ndim == 3:
+            P, n = X1.shape[:2]
+            self.ctx.set_perm(perm, n)
+            bank = self.ctx.sph_bank_create(np.concatenate([X1, X2]), self.nmax, self.Jmax, self.harmscale,
+                                            self.scale)
+            try:
+                pairs = np.stack([np.arange(P), P + np.arange(P)], axis=1)
+                bi, bv, fr, avg, grid = self.ctx.sph_align_bank(bank, pairs, invert=invert)
+            finally:
+                bank.close()
+        else:
+            bi, bv, fr, avg, grid = self._bank_pair(X1, X2, perm, invert, want_grid)
+        self._best_idx, self._best_val, self._frac_idx, self._grid = bi, bv, fr, grid
+        R = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
+        return R[0] if X1.ndim == 2 else R
+
+    def compareList(self, poslist, perm=None, invert=False):
+        """All-vs-all average / maximum overlap (reference SphericalHarmonicAlignFortran.compareList
+        :622-663, CALCOVERLAPMATRICES fastclusters.f90:853-866): coefficients once per structure in a
+        device bank, then contraction + inverse SO(3) transform + max per pair."""
+        coords = np.array(poslist, dtype=float)
+        nlist, natoms, dim = coords.shape
+        assert dim == 3
+        coords -= coords.mean(1)[:, None, :]
+        self.ctx.set_perm(self._perm(natoms, perm), natoms)
+        bank = self.ctx.sph_bank_create(coords, self.nmax, self.Jmax, self.harmscale, self.scale)
+        iu = np.triu_indices(nlist)
+        pairs = np.stack(iu, axis=1)
+        try:
+            bi, bv, fr, avg, _ = self.ctx.sph_align_bank(bank, pairs, invert=invert)
+        finally:
+            bank.close()
+        avgoverlap = np.zeros((nlist, nlist))
+        maxoverlap = np.zeros((nlist, nlist))
+        avgoverlap[iu] = avg
+        maxoverlap[iu] = bv.max(1)
+        avgoverlap = np.triu(avgoverlap) + np.triu(avgoverlap, 1).T
+        maxoverlap = np.triu(maxoverlap) + np.triu(maxoverlap, 1).T
+        da, dm = avgoverlap.diagonal(), maxoverlap.diagonal()
+        return (avgoverlap, maxoverlap, avgoverlap / sqrt(da[:, None] * da[None, :]),
+                maxoverlap / sqrt(dm[:, None] * dm[None, :]))
+
+    def alignGroup(self, coords, keepCoords=False):
+        """All-vs-all alignment distances (reference :397-414)."""
+        coords = np.asarray(coords, float)
+        nl, natoms = coords.shape[:2]
+        X = coords - coords.mean(1)[:, None, :]
+        perm = self._perm(natoms)
+        self.ctx.set_perm(perm, natoms)
+        bank = self.ctx.sph_bank_create(X, self.nmax, self.Jmax, self.harmscale, self.scale)
+        ii, jj = np.meshgrid(np.arange(nl), np.arange(nl), indexing="ij")
+        pairs = np.stack([ii.ravel(), jj.ravel()], axis=1)
+        try:
+            bi, bv, fr, avg, _ = self.ctx.sph_align_bank(bank, pairs, invert=True)
+        finally:
+            bank.close()
+        Rs = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
+        dists = np.zeros((nl, nl))
+        if keepCoords:
+            aligned = np.empty((2, nl, nl) + coords[0].shape)
+        for k, (i, j) in enumerate(pairs):
+            best = self.refine(X[i], X[j], Rs[k, 0], perm)
+            inv = self.refine(X[i], -X[j], Rs[k, 1], perm)
+            if inv[0] < best[0]:
+                best = inv
+            dists[i, j] = best[0]
+            if keepCoords:
+                aligned[0, i, j], aligned[1, i, j] = best[1], best[2]
+        return (dists, aligned) if keepCoords else dists

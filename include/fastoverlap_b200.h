@@ -179,6 +179,11 @@ void fo_bank_destroy(fo_ctx* ctx, fo_bank* bank);
 int fo_sph_isoft_argmax(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax, int invert,
                         int64_t* best_idx, double* best_val, double* frac_idx, double* grid_out);
 
+/* Plain inverse SO(3) transform of arbitrary complex coefficients (SOFT.iSOFT, soft.py:115-125):
+ * grid_re / grid_im [P,2B,2B,2B]; grid_im may be NULL.  Two real-output transforms internally. */
+int fo_sph_isoft(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax, double* grid_re,
+                 double* grid_im);
+
 /* Direct (N^2 Bessel) SO(3) coefficients of P pairs of already-centred structures:
  *   I[l,m1,m2] = 4 pi^2.5 sigma^3 sum_g sum_{j,k in g} i_l(r_j r_k / 2 sigma^2)
  *                exp(-(r_j^2+r_k^2)/4 sigma^2) Y_lm1(A_j) conj(Y_lm2(B_k))

@@ -150,6 +150,11 @@ static void fft_rec(int64_t n, const cplx* in, int64_t istride, cplx* out, const
   }
 }
 
+/* transform with a caller-provided twiddle table tw[t] = exp(sign 2 pi i t/n) (plan reuse) */
+void oracle_fft_tw(int64_t n, const cplx* in, int64_t istride, cplx* out, const cplx* tw, cplx* tmp) {
+  fft_rec(n, in, istride, out, tw, n, 1, tmp);
+}
+
 void oracle_fft1d(int64_t n, const cplx* in, int64_t istride, cplx* out, int sign) {
   cplx* tw = (cplx*)malloc(sizeof(cplx) * (size_t)n);
   cplx* tmp = (cplx*)malloc(sizeof(cplx) * (size_t)(n > 16 ? n : 16));

@@ -137,3 +137,115 @@ def per_align_pairs(posA, posB, box, n, F, sigma, perm=None, nthreads=0, want_gr
                                         _p(idx), _p(box), _i64(n), _i64(F), _f64(sigma), _p(bi),
                                         _p(bv), _p(fr), ctypes.c_int(int(nthreads)))
     return bi, bv, fr, None, int(used)
+
+
+# ------------------------------------------------------------------ spherical
+
+def sph_ylm(pos, L):
+    """Y[l, m] (negative m wrapped) of one point -> (L+1, 2L+1) complex, and r."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3)
+    Y = np.empty((L + 1, 2 * L + 1), np.complex128)
+    lib().oracle_sph_ylm.restype = _f64
+    r = lib().oracle_sph_ylm(_p(pos), _i64(L), _p(Y))
+    return Y, float(r)
+
+
+def sphi_scaled(L, x):
+    out = np.empty(L + 1, np.float64)
+    lib().oracle_sphi_scaled(_i64(L), _f64(x), _p(out))
+    return out
+
+
+def sph_coeffs_direct(posA, posB, Jmax, sigma, perm=None):
+    posA = np.ascontiguousarray(posA, dtype=np.float64).reshape(-1, 3)
+    posB = np.ascontiguousarray(posB, dtype=np.float64).reshape(-1, 3)
+    off, idx, ng = _groups(perm, len(posA))
+    L = int(Jmax)
+    I = np.empty((L + 1, 2 * L + 1, 2 * L + 1), np.complex128)
+    lib().oracle_sph_coeffs_direct(_p(posA), _p(posB), _i64(len(posA)), _p(off), _i64(ng), _p(idx),
+                                   _i64(L), _f64(sigma), _p(I))
+    return I
+
+
+def soft_weights(B):
+    w = np.empty(2 * B, np.float64)
+    lib().oracle_soft_weights(_i64(B), _p(w))
+    return w
+
+
+def wigner_table(B):
+    Ds = np.empty((B, 2 * B - 1, 2 * B - 1, 2 * B), np.float64)
+    lib().oracle_wigner_table(_i64(B), _p(Ds))
+    return Ds
+
+
+def isoft(Ilmm, Jmax, want_complex=False):
+    B = int(Jmax) + 1
+    I = np.ascontiguousarray(Ilmm, dtype=np.complex128)
+    assert I.shape == (B, 2 * B - 1, 2 * B - 1)
+    out = np.empty((2 * B,) * 3, np.float64)
+    outc = np.empty((2 * B,) * 3, np.complex128) if want_complex else None
+    lib().oracle_isoft(_p(I), _i64(B), None, _p(out), _p(outc))
+    return outc if want_complex else out
+
+
+def sph_harm_radial(nmax, L, r, sigma, r0, kind="exact"):
+    if kind == "exact":
+        out = np.empty((nmax + 1, L + 1), np.float64)
+        lib().oracle_sph_harm_radial_exact(_i64(nmax), _i64(L), _f64(r), _f64(sigma), _f64(r0), _p(out))
+        return out
+    Lf = L + 2 * nmax
+    out = np.empty((nmax + 1, Lf + 1), np.float64)
+    lib().oracle_sph_harm_radial_fortran(_i64(nmax), _i64(Lf), _f64(r), _f64(sigma), _f64(r0), _p(out))
+    return out[:, :L + 1].copy()
+
+
+def sph_harm_coeffs(pos, nmax, Jmax, harmscale, sigma, idx=None, kind="exact"):
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    idx = np.arange(len(pos), dtype=np.int32) if idx is None else np.asarray(idx, dtype=np.int32)
+    L = int(Jmax)
+    C = np.empty((nmax + 1, L + 1, 2 * L + 1), np.complex128)
+    lib().oracle_sph_harm_coeffs(_p(pos), _i64(len(pos)), _p(idx), _i64(len(idx)), _i64(nmax), _i64(L),
+                                 _f64(harmscale), _f64(sigma), ctypes.c_int(1 if kind == "fortran" else 0),
+                                 _p(C))
+    return C
+
+
+def sph_dot_harm(C1, C2, invert=False):
+    C1 = np.ascontiguousarray(C1, dtype=np.complex128)
+    C2 = np.ascontiguousarray(C2, dtype=np.complex128)
+    if C1.ndim == 3:
+        C1, C2 = C1[None], C2[None]
+    ng, n1, l1, nj = C1.shape
+    I = np.empty((l1, nj, nj), np.complex128)
+    lib().oracle_sph_dot_harm(_p(C1), _p(C2), _i64(ng), _i64(n1 - 1), _i64(l1 - 1),
+                              ctypes.c_int(int(bool(invert))), _p(I))
+    return I
+
+
+def sph_align_pairs(posA, posB, Jmax, sigma, invert=True, perm=None, nthreads=0, want_grid=False):
+    """Whole spherical hot path (direct coefficients) for P pairs of centred structures."""
+    posA = np.ascontiguousarray(posA, dtype=np.float64)
+    posB = np.ascontiguousarray(posB, dtype=np.float64)
+    if posA.ndim == 2:
+        posA, posB = posA[None], posB[None]
+    P, N, _ = posA.shape
+    off, idx, ng = _groups(perm, N)
+    O = 2 if invert else 1
+    L = int(Jmax)
+    nk = 2 * (L + 1)
+    bi = np.empty((P, O, 3), np.int64)
+    bv = np.empty((P, O), np.float64)
+    fr = np.empty((P, O, 3), np.float64)
+    if want_grid:
+        grids = np.empty((P, O, nk, nk, nk), np.float64)
+        for p in range(P):
+            lib().oracle_sph_align_pair(_p(posA[p]), _p(posB[p]), _i64(N), _p(off), _i64(ng), _p(idx),
+                                        _i64(L), _f64(sigma), ctypes.c_int(int(bool(invert))), None,
+                                        _p(bi[p]), _p(bv[p]), _p(fr[p]), _p(grids[p]))
+        return bi, bv, fr, grids, 1
+    lib().oracle_sph_align_pairs.restype = ctypes.c_int
+    used = lib().oracle_sph_align_pairs(_p(posA), _p(posB), _i64(P), _i64(N), _p(off), _i64(ng), _p(idx),
+                                        _i64(L), _f64(sigma), ctypes.c_int(int(bool(invert))), _p(bi),
+                                        _p(bv), _p(fr), ctypes.c_int(int(nthreads)))
+    return bi, bv, fr, None, int(used)

@@ -1,0 +1,133 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fastoverlap_b200.h declares;
+host-side logic (LAP, Kearsley, findMax, peaks, refine) against the reference's golden values.
+No compute call is made on the library (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fastoverlap_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import fastoverlap_b200 as fob
+    from fastoverlap_b200 import _lib
+    path = fob.library_path()
+    if not os.path.exists(path):
+        from fastoverlap_b200 import build
+        build.build()
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+    # the ctypes signature table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_no_gpu_fails_loudly():
+    import fastoverlap_b200 as fob
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(fob.FastOverlapError):
+        fob.Context(0)
+    with pytest.raises(fob.FastOverlapError):
+        fob.PeriodicAlign(4, [1.0, 1.0, 1.0]).calcFourierCoeff(np.zeros((4, 3)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "fastoverlap_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), os.path.join(dp, f)
+                assert "/root/reference" not in txt, os.path.join(dp, f)
+
+
+def test_next_fast_len():
+    from fastoverlap_b200.utils import _next_fast_len
+    tab = golden("next_fast_len.npz")["table"]
+    assert all(_next_fast_len(i) == tab[i] for i in range(len(tab)))
+    lib = ctypes.CDLL(__import__("fastoverlap_b200").library_path())
+    lib.fo_next_fast_len.restype = ctypes.c_int64
+    lib.fo_next_fast_len.argtypes = [ctypes.c_int64]
+    assert all(lib.fo_next_fast_len(i) == tab[i] for i in range(len(tab)))
+    s, n, F = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    box = (ctypes.c_double * 3)(5.975206329, 5.975206329, 5.975206329)
+    lib.fo_per_defaults.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p]
+    assert lib.fo_per_defaults(256, box, ctypes.byref(s), ctypes.byref(n), ctypes.byref(F)) == 0
+    g = golden("periodic_blj256.npz")
+    assert n.value == int(g["n"]) and F.value == int(g["F"]) and abs(s.value - float(g["scale"])) < 1e-15
+
+
+def test_findmax_host():
+    from fastoverlap_b200.utils import findMax
+    g = golden("periodic_blj256.npz")
+    assert np.allclose(findMax(g["fabs"]), g["findmax"], atol=1e-12)
+    s = golden("spherical_lj38.npz")
+    assert np.allclose(findMax(s["J15_grid"]), s["J15_findmax"].real, atol=1e-12)
+
+
+def test_periodic_refine_host_matches_reference():
+    """BasePeriodicAlignment.refine with the reference's displacement reproduces the documented
+    1.559 (periodicAlignment.py:609) -- host LAP uses the pele cost-matrix orientation (Q9)."""
+    from fastoverlap_b200.periodic import PeriodicAlign
+    g = golden("periodic_blj256.npz")
+    al = PeriodicAlign.__new__(PeriodicAlign)
+    al.Natoms, al.boxvec, al.dim = 256, g["box"], 3
+    al.perm = [np.arange(204), np.arange(204, 256)]
+    dist, X1, X2, perm, disp = al.refine(g["pos1"].copy(), g["pos2"].copy(), g["disp0"][None, :])
+    assert abs(dist - 1.5590835031549872) < 1e-10
+    assert np.array_equal(perm, g["perm"])
+    assert np.allclose(disp, g["disp"], atol=1e-10)
+
+
+def test_spherical_refine_host_matches_reference():
+    from fastoverlap_b200.spherical import SphericalAlign
+    from fastoverlap_b200.utils import indtoEuler
+    g = golden("spherical_lj38.npz")
+    sa = SphericalAlign.__new__(SphericalAlign)
+    sa.perm, sa.scale, sa.Jmax = None, 0.3, 15
+    X1, X2 = sa.COM_shift(g["pos1"], g["pos2"])
+    R = indtoEuler(g["J15_findmax_inv"].real, 32)
+    assert abs(sa.refine(X1, -X2, R)[0] - 1.4767670631638872) < 1e-10
+    R = indtoEuler(g["J15_findmax"].real, 32)
+    assert abs(sa.refine(X1, X2, R)[0] - float(g["J15_dist_normal_only"])) < 1e-10
+
+
+def test_kearsley_and_lap():
+    from fastoverlap_b200.utils import findrotation, find_best_permutation, EulerM
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(30, 3))
+    X -= X.mean(0)
+    R = EulerM(0.3, 1.1, -2.0)
+    perm = rng.permutation(30)
+    Y = X.dot(R)[perm]
+    _, p = find_best_permutation(X.dot(R), Y)
+    assert np.array_equal(np.asarray(Y)[p], X.dot(R))
+    d, M = findrotation(X, X.dot(R))
+    assert d < 1e-7 and np.allclose(X.dot(R).dot(M.T), X, atol=1e-7)
+
+
+def test_findpeaks_recovers_planted_gaussians():
+    from fastoverlap_b200.peaks import findPeaks
+    n = 24
+    x = np.indices((n, n, n)).astype(float)
+    f = np.zeros((n, n, n))
+    for c, a in (((5.3, 10.1, 17.6), 3.0), ((15.2, 4.4, 8.9), 2.0)):
+        d2 = sum((np.minimum(abs(x[i] - c[i]), n - abs(x[i] - c[i]))) ** 2 for i in range(3))
+        f += a * np.exp(-d2 / 4.0)
+    peaks, amp, _, _, _ = findPeaks(f, npeaks=2, width=2)
+    assert np.allclose(peaks[0], (5.3, 10.1, 17.6), atol=0.05)
+    assert np.allclose(peaks[1], (15.2, 4.4, 8.9), atol=0.05)
