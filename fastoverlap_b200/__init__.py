@@ -10,6 +10,9 @@ from ._lib import Context, FastOverlapError, default_context, load_library, libr
 from .periodic import PeriodicAlign
 from .soft import SOFT
 from .spherical import SphericalAlign, SphericalHarmonicAlign
+from .fortran_wrappers import (SphericalAlignFortran, SphericalHarmonicAlignFortran,
+                               PeriodicAlignFortran)
 
-__all__ = ["SphericalAlign", "SphericalHarmonicAlign", "PeriodicAlign", "SOFT", "Context",
+__all__ = ["SphericalAlign", "SphericalHarmonicAlign", "PeriodicAlign", "SOFT",
+           "SphericalAlignFortran", "SphericalHarmonicAlignFortran", "PeriodicAlignFortran", "Context",
            "FastOverlapError", "default_context"]

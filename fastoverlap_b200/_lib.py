@@ -223,6 +223,11 @@ class Context(object):
                     "fo_set_perm")
         self._perm_key = key
 
+    def _ensure_perm(self, natoms):
+        """Default permutation (one group of all atoms) unless groups were set for this natoms."""
+        if self._perm_key is None or self._perm_key[0] != int(natoms):
+            self.set_perm([np.arange(int(natoms))], natoms)
+
     # -- periodic
     @staticmethod
     def per_params(natoms, box, nwave, nfspace, sigma):
@@ -236,6 +241,7 @@ class Context(object):
         return p
 
     def per_structure_factors(self, params, pos):
+        self._ensure_perm(params.natoms)
         pos = _f64(pos).reshape(-1, params.natoms, 3)
         S = pos.shape[0]
         W = 2 * params.nwave + 1
@@ -254,6 +260,7 @@ class Context(object):
         return best_idx, best_val, frac, grid, status
 
     def per_align_pairs(self, params, posA, posB, want_grid=False):
+        self._ensure_perm(params.natoms)
         posA = _f64(posA).reshape(-1, params.natoms, 3)
         posB = _f64(posB).reshape(-1, params.natoms, 3)
         if posA.shape != posB.shape:
@@ -288,6 +295,7 @@ class Context(object):
         return bi, bv, fr, grid, st
 
     def per_bank_create(self, params, pos):
+        self._ensure_perm(params.natoms)
         pos = _f64(pos).reshape(-1, params.natoms, 3)
         h = c_void_p()
         self._check(self._lib.fo_per_bank_create(self._h, ctypes.byref(params), _ptr(pos),
@@ -349,6 +357,7 @@ class Context(object):
             posA = posA[None]
             posB = posB[None]
         P, N, _ = posA.shape
+        self._ensure_perm(N)
         L = int(Jmax)
         out = np.empty((P, L + 1, 2 * L + 1, 2 * L + 1), np.complex128)
         st = np.zeros(P, np.int32)
@@ -364,6 +373,7 @@ class Context(object):
             posA = posA[None]
             posB = posB[None]
         P, N, _ = posA.shape
+        self._ensure_perm(N)
         L = int(Jmax)
         bi, bv, fr, grid = self._sph_outputs(P, L, invert, want_grid)
         st = np.zeros(P, np.int32)
@@ -375,6 +385,7 @@ class Context(object):
 
     def sph_align_pairs_dev(self, d_posA, d_posB, P, N, Jmax, sigma, invert, d_best_idx,
                             d_best_val, d_frac, d_grid=0, d_status=0):
+        self._ensure_perm(N)
         self._check(self._lib.fo_sph_align_pairs_dev(
             self._h, c_void_p(d_posA), c_void_p(d_posB), int(P), int(N), int(Jmax), float(sigma),
             int(bool(invert)), c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac),
@@ -385,6 +396,7 @@ class Context(object):
         if pos.ndim == 2:
             pos = pos[None]
         S, N, _ = pos.shape
+        self._ensure_perm(N)
         ng = len(self._perm_key[1]) if self._perm_key and self._perm_key[0] == N else 1
         L = int(Jmax)
         out = np.empty((S, ng, nmax + 1, L + 1, 2 * L + 1), np.complex128)
@@ -399,6 +411,7 @@ class Context(object):
         if pos.ndim == 2:
             pos = pos[None]
         S, N, _ = pos.shape
+        self._ensure_perm(N)
         h = c_void_p()
         self._check(self._lib.fo_sph_bank_create(self._h, _ptr(pos), S, N, int(nmax), int(Jmax),
                                                  float(harmscale), float(sigma), ctypes.byref(h)),

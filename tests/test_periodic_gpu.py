@@ -180,3 +180,24 @@ def test_edge_cases(ctx):
     r0 = ctx.per_align_pairs(p, a[:1], b[:1])
     ctx.set_perm([np.arange(4)], 4)
     assert np.array_equal(r[0], r0[0])
+
+
+def test_multigpu_thread_sharding_identical(ctx):
+    """One Context + one host thread per GPU (here: two contexts on the available device):
+    per-pair results are bit-identical to the single-context run for any shard count."""
+    import torch
+    from fastoverlap_b200 import PeriodicAlign
+    from fastoverlap_b200.batch import MultiGPU
+    rng = np.random.default_rng(8)
+    N, box = 20, np.array([3.0, 3.2, 3.4])
+    pos1, pos2, _ = _random_pairs(rng, 11, N, box)
+    al = PeriodicAlign(N, box, ctx=ctx)
+    ref = ctx.per_align_pairs(al._params(), pos1, pos2)
+    ndev = torch.cuda.device_count()
+    mg = MultiGPU([i % ndev for i in range(3)])
+
+    def fn(c, a, b):
+        c.set_perm([np.arange(N)], N)
+        return c.per_align_pairs(al._params(), a, b)[:3]
+    out = mg.map_pairs(fn, pos1, pos2)
+    assert all(np.array_equal(o, r) for o, r in zip(out, ref[:3]))

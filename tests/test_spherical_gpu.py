@@ -219,3 +219,28 @@ def test_edge_cases(ctx):
         ctx.sph_align_pairs(B, B, 200, 0.5)
     with pytest.raises(FastOverlapError):
         ctx.sph_align_pairs(B, B, 5, -1.0)
+
+
+def test_fortran_wrapper_facade(ctx):
+    """The f2py-module facade (fastoverlap_b200.f90) through the reference's wrapper classes:
+    same call signatures / return tuples as sphericalAlignment.py:441-663, periodicAlignment.py:482-605."""
+    import fastoverlap_b200 as fob
+    g = golden("spherical_lj38.npz")
+    al = fob.SphericalAlignFortran(0.3, 15)
+    dist, X1, X2, rmat = al(g["pos1"], g["pos2"])
+    assert abs(dist - 1.4767670631638872) < DIST_ATOL
+    assert X1.shape == (38, 3) and rmat.shape == (3, 3)
+    assert abs(abs(np.linalg.det(rmat)) - 1) < 1e-9
+    assert abs(np.linalg.norm(X1 - X2) - dist) < 1e-9
+    assert abs(al.align(g["pos1"], g["pos2"])[0] - 1.4767670631638872) < DIST_ATOL
+    ah = fob.SphericalHarmonicAlignFortran(0.3, 15, 1.0, 20)
+    assert abs(ah(g["pos1"], g["pos2"])[0] - 1.4767670631638872) < 1e-6
+    avg, mx, navg, nmx = ah.compareList(np.array([g["pos1"], g["pos2"], g["pos1"]]))
+    assert abs(navg[0, 2] - 1) < 1e-12 and navg[0, 1] < 1
+    p = golden("periodic_blj256.npz")
+    ap = fob.PeriodicAlignFortran(256, p["box"], perm=[np.arange(204), np.arange(204, 256)])
+    dist, Y1, Y2, perm = ap.align(p["pos1"], p["pos2"], ndisps=1)
+    assert abs(dist - 1.5590835031549872) < DIST_ATOL
+    assert np.array_equal(perm - 1, p["perm"])
+    d, aligned = ap.alignGroup(np.array([p["pos1"], p["pos2"]]))
+    assert aligned.shape == (256, 3, 2, 2) and abs(d[0, 1] - 1.5590835031549872) < DIST_ATOL
