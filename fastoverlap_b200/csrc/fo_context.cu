@@ -67,6 +67,29 @@ int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out) {
   return FO_OK;
 }
 
+bool fo_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+void fo_host_copy(void* dst, const void* src, size_t bytes) {
+  const size_t blk = (size_t)1 << 20;
+  const long nblk = (long)((bytes + blk - 1) / blk);
+  if (nblk <= 2) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+#pragma omp parallel for schedule(static) num_threads(8)
+  for (long b = 0; b < nblk; ++b) {
+    const size_t off = (size_t)b * blk;
+    memcpy((char*)dst + off, (const char*)src + off, bytes - off < blk ? bytes - off : blk);
+  }
+}
+
 extern "C" int fo_create(int device, fo_ctx** out) {
   if (!out) return fo_fail(nullptr, FO_ERR_INVALID, "fo_create: out is NULL");
   *out = nullptr;

@@ -49,6 +49,9 @@ struct fo_ctx {
 
   fo_wigner_cache wig;
 
+  // testing hook: force the generic (any-size) kernels instead of the shared-memory fast paths
+  bool force_generic = false;
+
   // per-kernel event timing (fo_profile_begin/end)
   bool profiling = false;
   std::vector<fo_prof_rec> prof;
@@ -81,6 +84,10 @@ struct fo_bank {
 int fo_fail(fo_ctx* ctx, int code, const char* fmt, ...);
 int fo_scratch(fo_ctx* ctx, int slot, size_t bytes, void** out);
 int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out);
+// true when `p` is page-locked (cudaMallocHost / cudaHostRegister): it can be DMA'd directly
+bool fo_is_pinned(const void* p);
+// parallel host memcpy (staging of pageable buffers into the pinned ring)
+void fo_host_copy(void* dst, const void* src, size_t bytes);
 // make sure a permutation (at least the trivial one) exists for natoms atoms
 int fo_ensure_perm(fo_ctx* ctx, int64_t natoms);
 

@@ -226,6 +226,13 @@ __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(XF_GT) : "memory");
 }
 
+__device__ __forceinline__ void better32(double& bv, int& bi, double v, int i) {
+  if (v > bv || (v == bv && i < bi)) {
+    bv = v;
+    bi = i;
+  }
+}
+
 __device__ __forceinline__ void better(double& bv, long long& bi, double v, long long i) {
   if (v > bv || (v == bv && i < bi)) {
     bv = v;
@@ -516,6 +523,352 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K_xf fast path (per_xf3_kernel): the same mathematics as per_xf_kernel, organised so that the
+// FP64 pipe is the limit:
+//   * every 1-D transform is  P[d] = c0 + sum_m E[m] cos(2 pi m d/F),  Q[d] = sum_m O[m] sin(..)
+//     per REAL row (re / im parts are separate rows), E = c_m + c_-m and O = c_m - c_-m being
+//     formed by the previous stage (partner lanes exchange with two shuffles);
+//   * a thread owns one row and walks over all outputs d in chunks of X3_DC, so per (m, chunk) it
+//     loads two doubles from shared memory (k-major layout: conflict-free) for 2 X3_DC DFMA;
+//   * the twiddle matrices live in the kernel-parameter constant bank (__grid_constant__): the
+//     indices are warp-uniform, so they reach the DFMA as uniform-register operands
+//     (LDCU + DFMA R, R, UR, R in SASS) and cost no shared-memory / register-file bandwidth.
+//     (A shared-memory-fed register tile cannot be FP64 bound here: the LSU returns 128 B/clk/SM =
+//     16 doubles against 64 DFMA/clk/SM, ncu profiles/r01.)
+//   phase 1  cross-spectrum  -> XE/XO[m][row],  row = ((j M + l) 2 + s) 2 + part  (j=|ky|, s=sign)
+//   phase 2  stage X: row -> U(+-ky)[dx]; E/O over +-ky by shuffle -> YIN[dx][k][l*2+part]
+//   phase 3  SPI slabs at a time: stage Y rows (slab, l, part) -> ZR/ZI[l][dy];
+//            stage Z rows (slab, dy) -> |g|, running arg-max, optional grid
+//   phase 4  block arg-max + the six parabola neighbours re-evaluated from YIN
+// Used when it fits in shared memory and the constant bank (BLJ256: 190 KB); else per_xf_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int X3_THREADS = 512;
+constexpr int X3_DC = 7;          // outputs per chunk (H = 21 = 3 x 7 for F = 40)
+constexpr int X3_TWMAX = 1024;    // doubles per twiddle table in the parameter bank
+
+struct X3Tw {
+  double c[X3_TWMAX];  // [m-1][HP]
+  double s[X3_TWMAX];
+};
+
+struct X3Layout {
+  int M, W, H, HP, FP, RX, RY, K2, SPI;
+  size_t o_damp, o_red, o_xz, o_yin, total;  // in doubles
+  __host__ __device__ X3Layout(int n, int F) {
+    M = n + 1;
+    W = 2 * n + 1;
+    H = F / 2 + 1;
+    HP = ((H + X3_DC - 1) / X3_DC) * X3_DC;
+    FP = ((F + 3) / 4) * 4 + 2;  // ZR/ZI row pitch == 2 mod 4: spreads the stage-Y stores over banks
+    RX = M * M * 4;
+    RY = 2 * M;
+    K2 = 2 * n + 1;
+    const size_t xin = (size_t)2 * M * RX, zslab = (size_t)2 * M * FP;
+    SPI = 10;
+    while (SPI > 1 && (F + SPI - 1) / SPI == (F + SPI - 2) / (SPI - 1)) --SPI;  // same #iterations
+    size_t xz = xin > zslab * SPI ? xin : zslab * SPI;
+    o_damp = 0;
+    o_red = o_damp + ((3 * W + 1) & ~1);
+    o_xz = o_red + 64;
+    o_yin = o_xz + xz;
+    total = o_yin + (size_t)F * K2 * RY;
+  }
+  __host__ __device__ size_t zin_per_slab() const { return (size_t)2 * M * FP; }
+};
+
+// One real row: for every chunk of X3_DC outputs accumulate P, Q and hand them to epi(d0, P, Q).
+// e / o point at E[1][row] / O[1][row]; consecutive m are kstride apart.  [d_begin, d_end) and all
+// table indices are warp-uniform.
+template <class Epi>
+__device__ __forceinline__ void sym_row(const X3Tw& tw, const double* __restrict__ e,
+                                        const double* __restrict__ o, int kstride, int K, int HP,
+                                        double c0, int d_begin, int d_end, Epi&& epi) {
+  for (int d0 = d_begin; d0 < d_end; d0 += X3_DC) {
+    double P[X3_DC], Q[X3_DC];
+#pragma unroll
+    for (int t = 0; t < X3_DC; ++t) {
+      P[t] = c0;
+      Q[t] = 0.0;
+    }
+    const double* ep = e;
+    const double* op = o;
+    int ti = d0;
+    for (int k = 0; k < K; ++k) {
+      const double ev = *ep, ov = *op;
+#pragma unroll
+      for (int t = 0; t < X3_DC; ++t) {
+        P[t] = fma(ev, tw.c[ti + t], P[t]);
+        Q[t] = fma(ov, tw.s[ti + t], Q[t]);
+      }
+      ep += kstride;
+      op += kstride;
+      ti += HP;
+    }
+    // hand the epilogue an opaque per-thread copy of d0: if it used d0 itself the compiler would keep
+    // the chunk counter (and with it every table index) in vector registers
+    int d0v;
+    asm volatile("mov.s32 %0, %1;" : "=r"(d0v) : "r"(d0));
+    epi(d0v, P, Q);
+  }
+}
+
+// WANT_GRID: the optional F^3 grid output is compiled out of the production instantiation (its
+// per-thread global stores in the stage-Z epilogue make ptxas keep the table indices in vector
+// registers, i.e. LDC + DFMA R,R,R instead of LDCU + DFMA R,R,UR).
+template <bool WANT_GRID>
+__global__ void __launch_bounds__(X3_THREADS, 1)
+per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout L,
+               const double2* __restrict__ bankA, const double2* __restrict__ bankB,
+               const long long* __restrict__ pairs, int npairs, int ngroups, int n, int F, double kx,
+               double ky, double kz, double sigma, XfOut out) {
+  // L is computed on the host and passed through the parameter bank: its members then live in
+  // uniform registers, which is what lets the twiddle indices be proven warp-uniform
+  extern __shared__ double sm3[];
+  const int M = L.M, W = L.W, H = L.H, HP = L.HP, FP = L.FP, RX = L.RX, RY = L.RY, K2 = L.K2;
+  const int SPI = L.SPI;
+  double* damp = sm3 + L.o_damp;
+  double* red = sm3 + L.o_red;
+  double* XE = sm3 + L.o_xz;                 // [M][RX] (index 0: c0)
+  double* XO = XE + (size_t)M * RX;          // [M][RX] (index 0 unused)
+  double* ZIN = XE;                          // aliases the stage-X input: [SPI][2][M][FP]
+  double* YIN = sm3 + L.o_yin;               // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
+  const int tid = threadIdx.x;
+
+  for (int t = tid; t < 3 * W; t += X3_THREADS) {
+    const int ax = t / W, m = t - ax * W - n;
+    const double k = (ax == 0 ? kx : (ax == 1 ? ky : kz)) * (double)m;
+    damp[t] = exp(-(k * k) * (sigma * sigma));
+  }
+  __syncthreads();
+
+  const size_t c_elems = (size_t)W * W * M;
+  const size_t bank_stride = (size_t)ngroups * c_elems;
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const long long ia = pairs ? pairs[2 * pair] : pair;
+    const long long ib = pairs ? pairs[2 * pair + 1] : pair;
+    const double2* SA = bankA + (size_t)ia * bank_stride;
+    const double2* SB = bankB + (size_t)ib * bank_stride;
+    // ---- phase 1: cross spectrum in E/O form
+    for (int item = tid; item < M * W * M; item += X3_THREADS) {
+      const int l = item % M;
+      const int iy = (item / M) % W;
+      const int i = item / (M * W);
+      const size_t ep = ((size_t)(n + i) * W + iy) * M + l, em = ((size_t)(n - i) * W + iy) * M + l;
+      double pr = 0.0, pi = 0.0, mr = 0.0, mi = 0.0;
+      for (int g = 0; g < ngroups; ++g) {
+        const double2 a = SA[(size_t)g * c_elems + ep], b = SB[(size_t)g * c_elems + ep];
+        pr += a.x * b.x + a.y * b.y;
+        pi += a.y * b.x - a.x * b.y;
+        if (i) {
+          const double2 a2 = SA[(size_t)g * c_elems + em], b2 = SB[(size_t)g * c_elems + em];
+          mr += a2.x * b2.x + a2.y * b2.y;
+          mi += a2.y * b2.x - a2.x * b2.y;
+        }
+      }
+      const double dmp = damp[n + i] * damp[W + iy] * damp[2 * W + n + l];
+      pr *= dmp; pi *= dmp; mr *= dmp; mi *= dmp;
+      const int j = iy >= n ? iy - n : n - iy;
+      const int s = iy >= n ? 0 : 1;
+      const int row = ((j * M + l) * 2 + s) * 2;
+      double er, ei, orr, oi;
+      if (i == 0) {
+        er = pr; ei = pi; orr = 0.0; oi = 0.0;
+      } else {
+        er = pr + mr; ei = pi + mi; orr = pr - mr; oi = pi - mi;
+      }
+      *reinterpret_cast<double2*>(XE + (size_t)i * RX + row) = make_double2(er, ei);
+      *reinterpret_cast<double2*>(XO + (size_t)i * RX + row) = make_double2(orr, oi);
+      if (j == 0) {  // ky = 0 has no s = 1 partner: keep those rows finite (their output is unused)
+        *reinterpret_cast<double2*>(XE + (size_t)i * RX + row + 2) = make_double2(er, ei);
+        *reinterpret_cast<double2*>(XO + (size_t)i * RX + row + 2) = make_double2(orr, oi);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: stage X, one thread per row; lanes: bit 0 = part, bit 1 = s
+    for (int rbase = 0; rbase < RX; rbase += X3_THREADS) {
+      const int row = rbase + tid;
+      const bool valid = row < RX;
+      const int r = valid ? row : 0;
+      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
+      const int j = jl / M, l = jl - j * M;
+      const double sgn = part ? -1.0 : 1.0;
+      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
+      const bool store = valid && !(j == 0 && s == 1);
+      sym_row(tw, XE + RX + r, XO + RX + r, RX, n, HP, XE[r], 0, HP,
+              [&](int d0, double (&P)[X3_DC], double (&Q)[X3_DC]) {
+#pragma unroll
+                for (int t = 0; t < X3_DC; ++t) {
+                  const int d = d0 + t;
+                  const double qx = __shfl_xor_sync(0xffffffffu, Q[t], 1);
+                  const double ud = fma(sgn, qx, P[t]);   // U[d]   = P - iQ
+                  const double um = fma(-sgn, qx, P[t]);  // U[F-d] = P + iQ
+                  const double xd = __shfl_xor_sync(0xffffffffu, ud, 2);
+                  const double xm = __shfl_xor_sync(0xffffffffu, um, 2);
+                  // s = 0: E = U(+) + U(-) (or c0 = U for ky = 0); s = 1: O = U(+) - U(-) = x - u
+                  const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
+                  const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
+                  if (store && d < H) {
+                    YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
+                    if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
+                  }
+                }
+              });
+    }
+    __syncthreads();
+    // ---- phase 3: slabs, SPI at a time
+    double bv = -1.0;
+    int bi = 0x7fffffff;  // 32-bit flat index (F <= 1024): 64-bit index math here costs the uniform operands
+    for (int x0 = 0; x0 < F; x0 += SPI) {
+      const int ns = min(SPI, F - x0);
+      // stage Y: rows (slab, l, part); uniform control flow (invalid rows are clamped, stores masked)
+      for (int rbase = 0; rbase < ns * RY; rbase += X3_THREADS) {
+        const int row = rbase + tid;
+        const bool valid = row < ns * RY;
+        const int r = valid ? row : 0;
+        const int sl = r / RY, lp = r - sl * RY;
+        const int l = lp >> 1, part = lp & 1;
+        const double* Y = YIN + (size_t)(x0 + sl) * K2 * RY + lp;
+        double* Zrow = ZIN + (size_t)sl * L.zin_per_slab() + (size_t)part * M * FP + (size_t)l * FP;
+        const double sgn = part ? -1.0 : 1.0;
+        sym_row(tw, Y + RY, Y + (size_t)(n + 1) * RY, RY, n, HP, Y[0], 0, HP,
+                [&](int d0, double (&P)[X3_DC], double (&Q)[X3_DC]) {
+#pragma unroll
+                  for (int t = 0; t < X3_DC; ++t) {
+                    const int d = d0 + t;
+                    // V[d] = P - iQ, V[F-d] = P + iQ: re rows need the partner's Q_im, im rows its Q_re
+                    const double qx = __shfl_xor_sync(0xffffffffu, Q[t], 1);
+                    if (valid && d < H) {
+                      Zrow[d] = fma(sgn, qx, P[t]);
+                      if (d != 0 && 2 * d != F) Zrow[F - d] = fma(-sgn, qx, P[t]);
+                    }
+                  }
+                });
+      }
+      __syncthreads();
+      // stage Z: rows (slab, dy); uniform control flow
+      for (int rbase = 0; rbase < ns * F; rbase += X3_THREADS) {
+        const int row = rbase + tid;
+        const bool valid = row < ns * F;
+        const int r = valid ? row : 0;
+        const int sl = r / F, dy = r - sl * F;
+        const int dx = x0 + sl;
+        const double* ZR = ZIN + (size_t)sl * L.zin_per_slab() + dy;
+        const double* ZI = ZR + (size_t)M * FP;
+        const int base = (dx * F + dy) * F;
+        double* grow = nullptr;
+        if (WANT_GRID) grow = valid ? out.grid + ((size_t)pair * F * F * F + (size_t)base) : nullptr;
+        const double v0 = ZR[0];
+        sym_row(tw, ZR + FP, ZI + FP, FP, n, HP, 0.0, 0, HP,
+                [&](int d0, double (&A)[X3_DC], double (&B)[X3_DC]) {
+                  // convergence point: stops the compiler from unswitching the chunk loop on `valid`,
+                  // which would put the loop under a divergent branch and forbid uniform-register operands
+                  __syncwarp();
+#pragma unroll
+                  for (int t = 0; t < X3_DC; ++t) {
+                    const int d = d0 + t;
+                    if (valid && d < H) {
+                      const double a = fma(2.0, A[t], v0), b = 2.0 * B[t];
+                      const double g1 = fabs(a + b);
+                      better32(bv, bi, g1, base + d);
+                      if (WANT_GRID && grow) grow[d] = g1;
+                      if (d != 0 && 2 * d != F) {
+                        const double g2 = fabs(a - b);
+                        better32(bv, bi, g2, base + (F - d));
+                        if (WANT_GRID && grow) grow[F - d] = g2;
+                      }
+                    }
+                  }
+                });
+      }
+      __syncthreads();
+    }
+    // ---- phase 4: block arg-max (numpy order) and parabola neighbours
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      better32(bv, bi, ov, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red + 32);
+    if ((tid & 31) == 0) {
+      red[tid >> 5] = bv;
+      redi[tid >> 5] = bi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      bv = (tid < X3_THREADS / 32) ? red[tid] : -1.0;
+      bi = (tid < X3_THREADS / 32) ? redi[tid] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        better32(bv, bi, ov, oi);
+      }
+      if (tid == 0) {
+        red[0] = bv;
+        redi[0] = bi;
+      }
+    }
+    __syncthreads();
+    bv = red[0];
+    bi = redi[0];
+    const bool ok = (bi != 0x7fffffff) && isfinite(bv);
+    const int bx = ok ? bi / (F * F) : 0;
+    const int by = ok ? (bi / F) % F : 0;
+    const int bz = ok ? bi % F : 0;
+    __syncthreads();
+    {
+      const int w = tid >> 5, lane = tid & 31;
+      if (w < 6) {
+        const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
+        int px = bx, py = by, pz = bz;
+        if (ax == 0) px = (bx + sgn + F) % F;
+        if (ax == 1) py = (by + sgn + F) % F;
+        if (ax == 2) pz = (bz + sgn + F) % F;
+        const double* Y = YIN + (size_t)px * K2 * RY;
+        double acc = 0.0;
+        for (int e = lane; e < M * M; e += 32) {
+          const int j = e / M, l = e - j * M;
+          double sj, cj, sl_, cl;
+          sincospi(2.0 * (double)((j * py) % F) / (double)F, &sj, &cj);
+          sincospi(2.0 * (double)((l * pz) % F) / (double)F, &sl_, &cl);
+          double vr, vi;
+          if (j == 0) {
+            vr = Y[l * 2];
+            vi = Y[l * 2 + 1];
+          } else {
+            const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
+            const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
+            vr = er * cj + oi * sj;   // Re(E cos - i O sin)
+            vi = ei * cj - orr * sj;  // Im
+          }
+          const double term = vr * cl + vi * sl_;
+          acc += (l == 0) ? term : 2.0 * term;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) red[2 + w] = fabs(acc);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      out.best_idx[3 * (size_t)pair + 0] = bx;
+      out.best_idx[3 * (size_t)pair + 1] = by;
+      out.best_idx[3 * (size_t)pair + 2] = bz;
+      out.best_val[pair] = bv;
+      const int b3[3] = {bx, by, bz};
+      for (int ax = 0; ax < 3; ++ax) {
+        const double y1 = red[2 + 2 * ax], y3 = red[2 + 2 * ax + 1], y2 = bv;
+        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
+      }
+      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
+    }
+    __syncthreads();
+  }
+}
+
 size_t xf_smem_bytes(int n, int F, bool with_grids) {
   const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
   size_t b = (size_t)F * 16;                       // tw
@@ -587,10 +940,43 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   const int n = (int)p->nwave, F = (int)p->nfspace;
   const int ngroups = (int)ctx->h_goff.size() - 1;
   const size_t optin = ctx->prop.sharedMemPerBlockOptin;
-  size_t smem = xf_smem_bytes(n, F, true);
-  double2* gscratch = nullptr;
   int blocks = ctx->prop.multiProcessorCount;
   if ((int64_t)blocks > npairs) blocks = (int)npairs;
+  const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  {  // fast path: everything resident in shared memory, twiddles in the parameter constant bank
+    const X3Layout lay(n, F);
+    const size_t smem3 = lay.total * 8;
+    if (smem3 <= optin && (size_t)n * lay.HP <= (size_t)X3_TWMAX && !ctx->force_generic) {
+      static thread_local X3Tw tw;  // 16 KB: keep it off the stack
+      static thread_local int tw_n = -1, tw_F = -1;
+      if (tw_n != n || tw_F != F) {
+        for (int m = 1; m <= n; ++m)
+          for (int d = 0; d < lay.HP; ++d) {
+            const double ang = kTwoPi * (double)((m * d) % F) / (double)F;
+            tw.c[(m - 1) * lay.HP + d] = d < lay.H ? cos(ang) : 0.0;
+            tw.s[(m - 1) * lay.HP + d] = d < lay.H ? sin(ang) : 0.0;
+          }
+        tw_n = n;
+        tw_F = F;
+      }
+      fo_prof_scope prof(ctx, FO_PROF_PER_XF);
+      if (out.grid) {
+        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem3));
+        per_xf3_kernel<true><<<blocks, X3_THREADS, smem3, ctx->stream>>>(
+            tw, lay, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
+      } else {
+        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem3));
+        per_xf3_kernel<false><<<blocks, X3_THREADS, smem3, ctx->stream>>>(
+            tw, lay, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
+      }
+      FO_LAUNCH_CHECK(ctx);
+      return FO_OK;
+    }
+  }
+  size_t smem = xf_smem_bytes(n, F, true);
+  double2* gscratch = nullptr;
   if (smem > optin) {
     smem = xf_smem_bytes(n, F, false);
     if (smem > optin)
@@ -605,7 +991,6 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   }
   FO_CUDA(ctx, cudaFuncSetAttribute(per_xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-  const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
   fo_prof_scope prof(ctx, FO_PROF_PER_XF);
   per_xf_kernel<<<blocks, XF_THREADS, smem, ctx->stream>>>(d_bankA, d_bankB, d_pairs, (int)npairs,
                                                            ngroups, n, F, kx, ky, kz, p->sigma,
@@ -738,8 +1123,10 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
   FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
-  FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
-  FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
+  const bool pinnedA = fo_is_pinned(posA), pinnedB = fo_is_pinned(posB);
+  hA = hB = nullptr;
+  if (!pinnedA) FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
+  if (!pinnedB) FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
   double2* bankA = (double2*)bank;
   double2* bankB = bankA + (size_t)chunk * per_struct;
   HostOut h = {best_idx, best_val, frac_idx, grid_out, status};
@@ -752,14 +1139,23 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
     const size_t nb = (size_t)np * p->natoms * 3 * 8;
     // the pinned buffer `buf` was last read by the H2D of chunk c-2
     if (c >= 2) FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[buf]));
-    memcpy((char*)hA + buf * pos_bytes, posA + (size_t)p0 * p->natoms * 3, nb);
-    memcpy((char*)hB + buf * pos_bytes, posB + (size_t)p0 * p->natoms * 3, nb);
+    // caller buffers that are already page-locked are DMA'd directly; pageable ones are staged
+    const char* srcA = (const char*)(posA + (size_t)p0 * p->natoms * 3);
+    const char* srcB = (const char*)(posB + (size_t)p0 * p->natoms * 3);
+    if (!pinnedA) {
+      fo_host_copy((char*)hA + buf * pos_bytes, srcA, nb);
+      srcA = (const char*)hA + buf * pos_bytes;
+    }
+    if (!pinnedB) {
+      fo_host_copy((char*)hB + buf * pos_bytes, srcB, nb);
+      srcB = (const char*)hB + buf * pos_bytes;
+    }
     // device buffer `buf` was last read by the kernels of chunk c-2
     if (c >= 2) FO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2 + buf], 0));
-    FO_CUDA(ctx, cudaMemcpyAsync((char*)dA + buf * pos_bytes, (char*)hA + buf * pos_bytes, nb,
-                                 cudaMemcpyHostToDevice, ctx->copy_stream));
-    FO_CUDA(ctx, cudaMemcpyAsync((char*)dB + buf * pos_bytes, (char*)hB + buf * pos_bytes, nb,
-                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dA + buf * pos_bytes, srcA, nb, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dB + buf * pos_bytes, srcB, nb, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
     return FO_OK;
   };

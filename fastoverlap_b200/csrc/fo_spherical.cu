@@ -612,8 +612,10 @@ sph_isoft_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
   }
   // ---- K5
   const double2* Ip = Ihalf + p * (size_t)L1 * W * L1;
-  for (int item = tid; item < L1 * W; item += IS_THREADS) {
-    const int m1i = item % W, m2 = item / W;
+  for (int it = tid; it < L1 * W; it += IS_THREADS) {
+    // m2 fastest across lanes: conflict-free shared stores below
+    const int m2 = it % L1, m1i = it / L1;
+    const int item = m2 * W + m1i;  // index in the Ihalf / Dt layouts
     const int m1 = m1i - L;
     const int am1 = m1 < 0 ? -m1 : m1;
     const int l0 = am1 > m2 ? am1 : m2;
@@ -1186,8 +1188,10 @@ extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double*
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
   FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * (O * 56 + 8) + 256, &dout));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
-  FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
-  FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
+  const bool pinnedA = fo_is_pinned(posA), pinnedB = fo_is_pinned(posB);
+  hA = hB = nullptr;
+  if (!pinnedA) FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
+  if (!pinnedB) FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
   const int64_t nchunks = (npairs + chunk - 1) / chunk;
   auto stage_in = [&](int64_t c) -> int {
     const int64_t p0 = c * chunk;
@@ -1195,11 +1199,19 @@ extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double*
     const int buf = (int)(c & 1);
     const size_t nb = (size_t)np * natoms * 24;
     if (c >= 2) FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[buf]));
-    memcpy((char*)hA + buf * pos_bytes, posA + (size_t)p0 * natoms * 3, nb);
-    memcpy((char*)hB + buf * pos_bytes, posB + (size_t)p0 * natoms * 3, nb);
+    const char* srcA = (const char*)(posA + (size_t)p0 * natoms * 3);
+    const char* srcB = (const char*)(posB + (size_t)p0 * natoms * 3);
+    if (!pinnedA) {
+      fo_host_copy((char*)hA + buf * pos_bytes, srcA, nb);
+      srcA = (const char*)hA + buf * pos_bytes;
+    }
+    if (!pinnedB) {
+      fo_host_copy((char*)hB + buf * pos_bytes, srcB, nb);
+      srcB = (const char*)hB + buf * pos_bytes;
+    }
     if (c >= 2) FO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2 + buf], 0));
-    FO_CUDA(ctx, cudaMemcpyAsync((char*)dA + buf * pos_bytes, (char*)hA + buf * pos_bytes, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
-    FO_CUDA(ctx, cudaMemcpyAsync((char*)dB + buf * pos_bytes, (char*)hB + buf * pos_bytes, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dA + buf * pos_bytes, srcA, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)dB + buf * pos_bytes, srcB, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
     return FO_OK;
   };
