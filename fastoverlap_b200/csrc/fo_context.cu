@@ -137,6 +137,7 @@ extern "C" void fo_destroy(fo_ctx* ctx) {
   if (ctx->d_goff) cudaFree(ctx->d_goff);
   if (ctx->d_gidx) cudaFree(ctx->d_gidx);
   if (ctx->wig.d_table) cudaFree(ctx->wig.d_table);
+  if (ctx->wig.d_packed) cudaFree(ctx->wig.d_packed);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

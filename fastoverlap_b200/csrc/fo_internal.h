@@ -16,7 +16,8 @@ struct fo_devbuf {
 // Cached Wigner-d table for one bandwidth (device resident).
 struct fo_wigner_cache {
   int64_t Jmax = -1;
-  double* d_table = nullptr;  // packed, see fo_spherical.cu
+  double* d_table = nullptr;   // dense Dt[m2][m1][l][k], see fo_spherical.cu
+  double* d_packed = nullptr;  // per-chunk shell-ordered slices for sph_isoft2_kernel
   size_t bytes = 0;
 };
 

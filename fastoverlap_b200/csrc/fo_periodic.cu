@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "fo_internal.h"
+#include "fo_symdft.cuh"
 
 namespace {
 
@@ -142,6 +143,141 @@ per_sf_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
           const double im = -sig * acc[t][2] - rho * acc[t][4] - acc[t][1] + rho * sig * acc[t][7];
           o[t] = make_double2(re, im);
         }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K_sf on the FP64 tensor pipe (per_sf2_kernel).  The 8 real sums are one GEMM per (structure,
+// group):   C[(i,j,c4)][(l,c2)] = sum_a XY[(i,j,c4)][a] Z[a][(l,c2)]
+//   rows r = (i M + j) 4 + c4, c4 = (x: c|s) 2 + (y: c|s);  cols q = 2 l + (z: c|s);  K = atoms.
+// A warp owns MT row tiles (8 rows each) and all NT column tiles: per k-step (4 atoms) it builds MT
+// A elements (two 8-byte shared loads + one DMUL each) and NT B elements (one load each) for
+// MT NT DMMA.8x8x4, i.e. ~1 shared load per DMMA (256 MAC) -- the scalar kernel needs 7 loads per
+// 44 FP64 instructions and is held at ~59 % pipe utilisation by LSU return bandwidth and issue.
+// The C fragment layout puts the two z components of one l in one lane and the four (x,y)
+// combinations of one (i,j) in the 4 lanes {g = 4u..4u+3}: three shuffle rounds gather the 8 sums
+// and each of the 4 lanes writes one of the four sign combinations (rho, sig).
+// ------------------------------------------------------------------------------------------
+template <int MT, int NT>
+__global__ void __launch_bounds__(384)
+per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
+               const int32_t* __restrict__ gidx, int ngroups, int natoms, int n, double kx, double ky,
+               double kz, double2* __restrict__ bank) {
+  extern __shared__ double2 sm_ph2[];
+  const int M = n + 1;
+  const int Mp = M | 1;
+  const int Mz = (4 * NT) | 1;  // z rows zero padded up to 4 NT values of l
+  double2* phx = sm_ph2;
+  double2* phy = phx + SF_TA * Mp;
+  double2* phz = phy + SF_TA * Mp;
+  const int s = blockIdx.x, gq = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int nrows = M * M * 4;
+  const int a_begin = goff[gq], a_end = goff[gq + 1];
+  const double* spos = pos + (size_t)s * natoms * 3;
+  const double kax[3] = {kx, ky, kz};
+
+  // per-lane constants of the MT row tiles: offsets of the x and y components this lane multiplies
+  int offx[MT], offy[MT];
+  bool rvalid[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r = (warp * MT + mt) * 8 + g;
+    rvalid[mt] = r < nrows;
+    const int rr = rvalid[mt] ? r : 0;
+    const int c4 = rr & 3, ij = rr >> 2;
+    const int i = ij / M, j = ij - i * M;
+    offx[mt] = i * 2 + ((c4 >> 1) & 1);  // in doubles within an atom row of phx
+    offy[mt] = j * 2 + (c4 & 1);
+  }
+  int offz[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) offz[nt] = nt * 8 + g;  // = 2 l + c2 (z rows are padded to 4 NT)
+
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  const double* dx_ = reinterpret_cast<const double*>(phx);
+  const double* dy_ = reinterpret_cast<const double*>(phy);
+  const double* dz_ = reinterpret_cast<const double*>(phz);
+  for (int a0 = a_begin; a0 < a_end; a0 += SF_TA) {
+    const int ta = min(SF_TA, a_end - a0);
+    const int ta4 = (ta + 3) & ~3;
+    __syncthreads();
+    for (int t = tid; t < 3 * ta4; t += blockDim.x) {
+      const int a = t / 3, ax = t - 3 * a;
+      const int pitch = (ax == 2) ? Mz : Mp;
+      double2* row = (ax == 0 ? phx : (ax == 1 ? phy : phz)) + a * pitch;
+      if (a < ta) {
+        const int atom = gidx[a0 + a];
+        const double th = kax[ax] * spos[atom * 3 + ax];
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        double c = 1.0, sv = 0.0;
+        row[0] = make_double2(1.0, 0.0);
+        for (int m = 1; m <= n; ++m) {
+          const double cn = c * cs - sv * sn;
+          const double snn = sv * cs + c * sn;
+          c = cn;
+          sv = snn;
+          row[m] = make_double2(c, sv);
+        }
+        if (ax == 2)
+          for (int m = M; m < Mz; ++m) row[m] = make_double2(0.0, 0.0);
+      } else {  // padding atoms of the last k-step contribute nothing
+        for (int m = 0; m < pitch; ++m) row[m] = make_double2(0.0, 0.0);
+      }
+    }
+    __syncthreads();
+    for (int k0 = 0; k0 < ta4; k0 += 4) {
+      const int a = k0 + t4;
+      double bz[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) bz[nt] = dz_[(size_t)a * Mz * 2 + offz[nt]];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const double av = dx_[(size_t)a * Mp * 2 + offx[mt]] * dy_[(size_t)a * Mp * 2 + offy[mt]];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
+      }
+    }
+  }
+  // ---- epilogue: gather the 8 sums of (i, j, l) from the 4 lanes g = 4u + c4 and emit S(rho i, sig j, l)
+  const int W = 2 * n + 1;
+  double2* out = bank + ((size_t)s * ngroups + gq) * ((size_t)W * W * M);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r = (warp * MT + mt) * 8 + g;
+    const int rr = rvalid[mt] ? r : 0;
+    const int c4 = rr & 3, ij = rr >> 2;
+    const int i = ij / M, j = ij - i * M;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      // v[c4'][z]: sums of the row with x,y combination c4' (this lane holds c4' = c4)
+      double v[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // lane holding combination q of the same (i,j): same t4, g' = (g & 4) | q
+        const int src = (((g & 4) | q) << 2) | t4;
+        v[q][0] = __shfl_sync(0xffffffffu, acc[mt][nt][0], src);
+        v[q][1] = __shfl_sync(0xffffffffu, acc[mt][nt][1], src);
+      }
+      const int l = nt * 4 + t4;
+      // this lane writes the sign combination (rho, sig) = (c4 & 2 ? -1 : +1, c4 & 1 ? -1 : +1)
+      const double rho = (c4 & 2) ? -1.0 : 1.0, sig = (c4 & 1) ? -1.0 : 1.0;
+      // names: v[cc=0][c]=ccc v[0][s]=ccs v[cs=1][c]=csc v[1][s]=css v[sc=2][c]=scc v[2][s]=scs v[ss=3][c]=ssc v[3][s]=sss
+      const double re = v[0][0] - rho * sig * v[3][0] - sig * v[1][1] - rho * v[2][1];
+      const double im = -sig * v[1][0] - rho * v[2][0] - v[0][1] + rho * sig * v[3][1];
+      const bool dup = ((c4 & 2) && i == 0) || ((c4 & 1) && j == 0);  // -0 duplicates +0
+      if (rvalid[mt] && l < M && !dup) {
+        const int ix = n + ((c4 & 2) ? -i : i), iy = n + ((c4 & 1) ? -j : j);
+        out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
       }
     }
   }
@@ -545,12 +681,8 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
 // ------------------------------------------------------------------------------------------
 constexpr int X3_THREADS = 512;
 constexpr int X3_DC = 7;          // outputs per chunk (H = 21 = 3 x 7 for F = 40)
-constexpr int X3_TWMAX = 1024;    // doubles per twiddle table in the parameter bank
-
-struct X3Tw {
-  double c[X3_TWMAX];  // [m-1][HP]
-  double s[X3_TWMAX];
-};
+using X3Tw = FoTw;
+constexpr int X3_TWMAX = FO_TWMAX;
 
 struct X3Layout {
   int M, W, H, HP, FP, RX, RY, K2, SPI;
@@ -576,42 +708,6 @@ struct X3Layout {
   }
   __host__ __device__ size_t zin_per_slab() const { return (size_t)2 * M * FP; }
 };
-
-// One real row: for every chunk of X3_DC outputs accumulate P, Q and hand them to epi(d0, P, Q).
-// e / o point at E[1][row] / O[1][row]; consecutive m are kstride apart.  [d_begin, d_end) and all
-// table indices are warp-uniform.
-template <class Epi>
-__device__ __forceinline__ void sym_row(const X3Tw& tw, const double* __restrict__ e,
-                                        const double* __restrict__ o, int kstride, int K, int HP,
-                                        double c0, int d_begin, int d_end, Epi&& epi) {
-  for (int d0 = d_begin; d0 < d_end; d0 += X3_DC) {
-    double P[X3_DC], Q[X3_DC];
-#pragma unroll
-    for (int t = 0; t < X3_DC; ++t) {
-      P[t] = c0;
-      Q[t] = 0.0;
-    }
-    const double* ep = e;
-    const double* op = o;
-    int ti = d0;
-    for (int k = 0; k < K; ++k) {
-      const double ev = *ep, ov = *op;
-#pragma unroll
-      for (int t = 0; t < X3_DC; ++t) {
-        P[t] = fma(ev, tw.c[ti + t], P[t]);
-        Q[t] = fma(ov, tw.s[ti + t], Q[t]);
-      }
-      ep += kstride;
-      op += kstride;
-      ti += HP;
-    }
-    // hand the epilogue an opaque per-thread copy of d0: if it used d0 itself the compiler would keep
-    // the chunk counter (and with it every table index) in vector registers
-    int d0v;
-    asm volatile("mov.s32 %0, %1;" : "=r"(d0v) : "r"(d0));
-    epi(d0v, P, Q);
-  }
-}
 
 // WANT_GRID: the optional F^3 grid output is compiled out of the production instantiation (its
 // per-thread global stores in the stage-Z epilogue make ptxas keep the table indices in vector
@@ -695,7 +791,7 @@ per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout
       const double sgn = part ? -1.0 : 1.0;
       const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
       const bool store = valid && !(j == 0 && s == 1);
-      sym_row(tw, XE + RX + r, XO + RX + r, RX, n, HP, XE[r], 0, HP,
+      sym_row<X3_DC>(tw, XE + RX + r, XO + RX + r, RX, n, HP, XE[r], 0, HP,
               [&](int d0, double (&P)[X3_DC], double (&Q)[X3_DC]) {
 #pragma unroll
                 for (int t = 0; t < X3_DC; ++t) {
@@ -731,7 +827,7 @@ per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout
         const double* Y = YIN + (size_t)(x0 + sl) * K2 * RY + lp;
         double* Zrow = ZIN + (size_t)sl * L.zin_per_slab() + (size_t)part * M * FP + (size_t)l * FP;
         const double sgn = part ? -1.0 : 1.0;
-        sym_row(tw, Y + RY, Y + (size_t)(n + 1) * RY, RY, n, HP, Y[0], 0, HP,
+        sym_row<X3_DC>(tw, Y + RY, Y + (size_t)(n + 1) * RY, RY, n, HP, Y[0], 0, HP,
                 [&](int d0, double (&P)[X3_DC], double (&Q)[X3_DC]) {
 #pragma unroll
                   for (int t = 0; t < X3_DC; ++t) {
@@ -759,7 +855,7 @@ per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout
         double* grow = nullptr;
         if (WANT_GRID) grow = valid ? out.grid + ((size_t)pair * F * F * F + (size_t)base) : nullptr;
         const double v0 = ZR[0];
-        sym_row(tw, ZR + FP, ZI + FP, FP, n, HP, 0.0, 0, HP,
+        sym_row<X3_DC>(tw, ZR + FP, ZI + FP, FP, n, HP, 0.0, 0, HP,
                 [&](int d0, double (&A)[X3_DC], double (&B)[X3_DC]) {
                   // convergence point: stops the compiler from unswitching the chunk loop on `valid`,
                   // which would put the loop under a divergent branch and forbid uniform-register operands
@@ -869,6 +965,305 @@ per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K_xf tensor-core path (per_xf4_kernel): the stages of per_xf3_kernel with every row transform
+// done by SymMma (fo_symdft.cuh): a warp owns 8 consecutive real rows and all outputs, the
+// products run on the FP64 tensor pipe (DMMA.8x8x4), E/O inputs are read once per tile from the
+// k-major shared arrays, the twiddle fragments live in registers.  Layouts as per_xf3_kernel except
+// that the stage-X pitch is padded to RXp == 8 (mod 16) doubles (the four k rows of an A fragment
+// then fall into two disjoint 64-byte bank halves).
+// ------------------------------------------------------------------------------------------
+constexpr int X4_THREADS = 512;
+constexpr int X4_WARPS = X4_THREADS / 32;
+
+struct X4Layout {
+  int M, W, H, FP, RX, RXp, RY, K2, SPI;
+  int o_damp, o_red, o_xz, o_yin, total;  // in doubles
+  X4Layout() {}
+  X4Layout(int n, int F) {
+    M = n + 1;
+    W = 2 * n + 1;
+    H = F / 2 + 1;
+    FP = ((F + 3) / 4) * 4 + 2;
+    RX = M * M * 4;
+    RXp = ((RX + 7) / 16) * 16 + 8;
+    RY = 2 * M;
+    K2 = 2 * n + 1;
+    const int xin = 2 * M * RXp, zslab = 2 * M * FP;
+    SPI = 10;
+    while (SPI > 1 && (F + SPI - 1) / SPI == (F + SPI - 2) / (SPI - 1)) --SPI;
+    const int xz = xin > zslab * SPI ? xin : zslab * SPI;
+    o_damp = 0;
+    o_red = o_damp + ((3 * W + 1) & ~1);
+    o_xz = o_red + 64;
+    o_yin = o_xz + xz;
+    total = o_yin + F * K2 * RY;
+  }
+  __host__ __device__ int zin_per_slab() const { return 2 * M * FP; }
+};
+
+template <int KS, int NT, bool WANT_GRID>
+__global__ void __launch_bounds__(X4_THREADS, 1)
+per_xf4_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ bankA,
+               const double2* __restrict__ bankB, const long long* __restrict__ pairs, int npairs,
+               int ngroups, int n, int F, double kx, double ky, double kz, double sigma, XfOut out) {
+  extern __shared__ double sm4[];
+  const int M = L.M, W = L.W, H = L.H, FP = L.FP, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
+  const int SPI = L.SPI;
+  double* damp = sm4 + L.o_damp;
+  double* red = sm4 + L.o_red;
+  double* XE = sm4 + L.o_xz;            // [M][RXp] (index 0: c0)
+  double* XO = XE + (size_t)M * RXp;    // [M][RXp] (index 0 unused)
+  double* ZIN = XE;                     // aliases the stage-X input: [SPI][2][M][FP]
+  double* YIN = sm4 + L.o_yin;          // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  SymMma<KS, NT> mm;
+  mm.init(n, F, H, lane);
+  for (int t = tid; t < 3 * W; t += X4_THREADS) {
+    const int ax = t / W, m = t - ax * W - n;
+    const double k = (ax == 0 ? kx : (ax == 1 ? ky : kz)) * (double)m;
+    damp[t] = exp(-(k * k) * (sigma * sigma));
+  }
+  __syncthreads();
+
+  const size_t c_elems = (size_t)W * W * M;
+  const size_t bank_stride = (size_t)ngroups * c_elems;
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const long long ia = pairs ? pairs[2 * pair] : pair;
+    const long long ib = pairs ? pairs[2 * pair + 1] : pair;
+    const double2* SA = bankA + (size_t)ia * bank_stride;
+    const double2* SB = bankB + (size_t)ib * bank_stride;
+    // ---- phase 1: cross spectrum in E/O form
+    for (int item = tid; item < M * W * M; item += X4_THREADS) {
+      const int l = item % M;
+      const int iy = (item / M) % W;
+      const int i = item / (M * W);
+      const size_t ep = ((size_t)(n + i) * W + iy) * M + l, em = ((size_t)(n - i) * W + iy) * M + l;
+      double pr = 0.0, pi = 0.0, mr = 0.0, mi = 0.0;
+      for (int gq = 0; gq < ngroups; ++gq) {
+        const double2 a = SA[(size_t)gq * c_elems + ep], b = SB[(size_t)gq * c_elems + ep];
+        pr += a.x * b.x + a.y * b.y;
+        pi += a.y * b.x - a.x * b.y;
+        if (i) {
+          const double2 a2 = SA[(size_t)gq * c_elems + em], b2 = SB[(size_t)gq * c_elems + em];
+          mr += a2.x * b2.x + a2.y * b2.y;
+          mi += a2.y * b2.x - a2.x * b2.y;
+        }
+      }
+      const double dmp = damp[n + i] * damp[W + iy] * damp[2 * W + n + l];
+      pr *= dmp; pi *= dmp; mr *= dmp; mi *= dmp;
+      const int j = iy >= n ? iy - n : n - iy;
+      const int s = iy >= n ? 0 : 1;
+      const int row = ((j * M + l) * 2 + s) * 2;
+      double er, ei, orr, oi;
+      if (i == 0) {
+        er = pr; ei = pi; orr = 0.0; oi = 0.0;
+      } else {
+        er = pr + mr; ei = pi + mi; orr = pr - mr; oi = pi - mi;
+      }
+      *reinterpret_cast<double2*>(XE + (size_t)i * RXp + row) = make_double2(er, ei);
+      *reinterpret_cast<double2*>(XO + (size_t)i * RXp + row) = make_double2(orr, oi);
+      if (j == 0) {  // ky = 0 has no s = 1 partner: keep those rows finite (their output is unused)
+        *reinterpret_cast<double2*>(XE + (size_t)i * RXp + row + 2) = make_double2(er, ei);
+        *reinterpret_cast<double2*>(XO + (size_t)i * RXp + row + 2) = make_double2(orr, oi);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: stage X; tile = 8 rows; row bits: 0 = part, 1 = s  (partners: lane ^ 4, lane ^ 8)
+    for (int tile = warp; tile * 8 < RX; tile += X4_WARPS) {
+      const int row = tile * 8 + g;
+      const bool valid = row < RX;
+      const int r = valid ? row : 0;
+      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
+      const int j = jl / M, l = jl - j * M;
+      const double sgn = part ? -1.0 : 1.0;
+      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
+      const bool store = valid && !(j == 0 && s == 1);
+      double P[NT][2], Q[NT][2];
+      mm.run(XE + RXp + r - g, XO + RXp + r - g, RXp, n, XE[r], lane, P, Q);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = nt * 8 + t4 * 2 + q;
+          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
+          const double ud = fma(sgn, qx, P[nt][q]);   // U[d]   = P - iQ
+          const double um = fma(-sgn, qx, P[nt][q]);  // U[F-d] = P + iQ
+          const double xd = __shfl_xor_sync(0xffffffffu, ud, 8);
+          const double xm = __shfl_xor_sync(0xffffffffu, um, 8);
+          const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
+          const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
+          if (store && d < H) {
+            YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
+            if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
+          }
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: slabs, SPI at a time
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+    for (int x0 = 0; x0 < F; x0 += SPI) {
+      const int ns = min(SPI, F - x0);
+      // stage Y: rows (slab, l, part)
+      for (int tile = warp; tile * 8 < ns * RY; tile += X4_WARPS) {
+        const int row = tile * 8 + g;
+        const bool valid = row < ns * RY;
+        const int r = valid ? row : 0;
+        const int sl = r / RY, lp = r - sl * RY;
+        const int l = lp >> 1, part = lp & 1;
+        const double* Y = YIN + (size_t)(x0 + sl) * K2 * RY + lp;
+        double* Zrow = ZIN + (size_t)sl * L.zin_per_slab() + (size_t)part * M * FP + (size_t)l * FP;
+        const double sgn = part ? -1.0 : 1.0;
+        double P[NT][2], Q[NT][2];
+        mm.run(Y + RY - g, Y + (size_t)(n + 1) * RY - g, RY, n, Y[0], lane, P, Q);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int d = nt * 8 + t4 * 2 + q;
+            // V[d] = P - iQ, V[F-d] = P + iQ: re rows need the partner's Q_im, im rows its Q_re
+            const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
+            if (valid && d < H) {
+              Zrow[d] = fma(sgn, qx, P[nt][q]);
+              if (d != 0 && 2 * d != F) Zrow[F - d] = fma(-sgn, qx, P[nt][q]);
+            }
+          }
+      }
+      __syncthreads();
+      // stage Z: rows (slab, dy)
+      for (int tile = warp; tile * 8 < ns * F; tile += X4_WARPS) {
+        const int row = tile * 8 + g;
+        const bool valid = row < ns * F;
+        const int r = valid ? row : 0;
+        const int sl = r / F, dy = r - sl * F;
+        const int dx = x0 + sl;
+        const double* ZR = ZIN + (size_t)sl * L.zin_per_slab() + dy;
+        const double* ZI = ZR + (size_t)M * FP;
+        const int base = (dx * F + dy) * F;
+        const double v0 = ZR[0];
+        double A[NT][2], B[NT][2];
+        mm.run(ZR + FP - g, ZI + FP - g, FP, n, 0.0, lane, A, B);
+        double g1[NT][2], g2[NT][2];
+        double cmax = -1.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int d = nt * 8 + t4 * 2 + q;
+            const double a = fma(2.0, A[nt][q], v0), b = 2.0 * B[nt][q];
+            g1[nt][q] = (valid && d < H) ? fabs(a + b) : -1.0;
+            g2[nt][q] = (valid && d < H && d != 0 && 2 * d != F) ? fabs(a - b) : -1.0;
+            cmax = fmax(cmax, fmax(g1[nt][q], g2[nt][q]));
+            if (WANT_GRID) {
+              if (valid && d < H) {
+                double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
+                grow[d] = g1[nt][q];
+                if (d != 0 && 2 * d != F) grow[F - d] = g2[nt][q];
+              }
+            }
+          }
+        if (cmax > bv || (cmax == bv && base < bi)) {  // rare once bv has converged
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int d = nt * 8 + t4 * 2 + q;
+              better32(bv, bi, g1[nt][q], base + d);
+              better32(bv, bi, g2[nt][q], base + (F - d));
+            }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase 4: block arg-max (numpy order) and parabola neighbours
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      better32(bv, bi, ov, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red + 32);
+    if ((tid & 31) == 0) {
+      red[tid >> 5] = bv;
+      redi[tid >> 5] = bi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      bv = (tid < X4_THREADS / 32) ? red[tid] : -1.0;
+      bi = (tid < X4_THREADS / 32) ? redi[tid] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        better32(bv, bi, ov, oi);
+      }
+      if (tid == 0) {
+        red[0] = bv;
+        redi[0] = bi;
+      }
+    }
+    __syncthreads();
+    bv = red[0];
+    bi = redi[0];
+    const bool ok = (bi != 0x7fffffff) && isfinite(bv);
+    const int bx = ok ? bi / (F * F) : 0;
+    const int by = ok ? (bi / F) % F : 0;
+    const int bz = ok ? bi % F : 0;
+    __syncthreads();
+    {
+      const int w = tid >> 5, lane = tid & 31;
+      if (w < 6) {
+        const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
+        int px = bx, py = by, pz = bz;
+        if (ax == 0) px = (bx + sgn + F) % F;
+        if (ax == 1) py = (by + sgn + F) % F;
+        if (ax == 2) pz = (bz + sgn + F) % F;
+        const double* Y = YIN + (size_t)px * K2 * RY;
+        double acc = 0.0;
+        for (int e = lane; e < M * M; e += 32) {
+          const int j = e / M, l = e - j * M;
+          double sj, cj, sl_, cl;
+          sincospi(2.0 * (double)((j * py) % F) / (double)F, &sj, &cj);
+          sincospi(2.0 * (double)((l * pz) % F) / (double)F, &sl_, &cl);
+          double vr, vi;
+          if (j == 0) {
+            vr = Y[l * 2];
+            vi = Y[l * 2 + 1];
+          } else {
+            const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
+            const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
+            vr = er * cj + oi * sj;   // Re(E cos - i O sin)
+            vi = ei * cj - orr * sj;  // Im
+          }
+          const double term = vr * cl + vi * sl_;
+          acc += (l == 0) ? term : 2.0 * term;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) red[2 + w] = fabs(acc);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      out.best_idx[3 * (size_t)pair + 0] = bx;
+      out.best_idx[3 * (size_t)pair + 1] = by;
+      out.best_idx[3 * (size_t)pair + 2] = bz;
+      out.best_val[pair] = bv;
+      const int b3[3] = {bx, by, bz};
+      for (int ax = 0; ax < 3; ++ax) {
+        const double y1 = red[2 + 2 * ax], y3 = red[2 + 2 * ax + 1], y2 = bv;
+        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
+      }
+      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
+    }
+    __syncthreads();
+  }
+}
+
 size_t xf_smem_bytes(int n, int F, bool with_grids) {
   const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
   size_t b = (size_t)F * 16;                       // tw
@@ -901,6 +1296,25 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
   if (nstruct == 0) return FO_OK;
   const int n = (int)p->nwave, M = n + 1;
   const int ngroups = (int)ctx->h_goff.size() - 1;
+  {  // tensor-core path: NT column tiles cover 2M columns, MT row tiles per warp, <= 12 warps
+    const int NTq = (2 * M + 7) / 8;
+    const int mtiles = (M * M * 4 + 7) / 8;
+    const int MTq = 5;
+    const int warps = (mtiles + MTq - 1) / MTq;
+    if (NTq == 3 && warps <= 12 && !ctx->force_generic) {
+      const int Mp = M | 1, Mz = (4 * NTq) | 1;
+      const size_t smem = (size_t)SF_TA * (2 * Mp + Mz) * 16;
+      const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+      dim3 grid((unsigned)nstruct, (unsigned)ngroups);
+      fo_prof_scope prof(ctx, FO_PROF_PER_SF);
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_sf2_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+      per_sf2_kernel<5, 3><<<grid, warps * 32, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
+                                                                    (int)p->natoms, n, kx, ky, kz, d_bank);
+      FO_LAUNCH_CHECK(ctx);
+      return FO_OK;
+    }
+  }
   // TL = 5 gives the best FMA : (mul + load) ratio when it divides n+1 well, else TL = 2.
   const int waste5 = ((M + 4) / 5) * 5 - M, waste2 = ((M + 1) / 2) * 2 - M;
   const bool use5 = (waste5 * 2 <= M / 5 + waste2 * 2) || (waste5 == 0);
@@ -943,6 +1357,27 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   int blocks = ctx->prop.multiProcessorCount;
   if ((int64_t)blocks > npairs) blocks = (int)npairs;
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  {  // tensor-core path: everything resident in shared memory, 1-D transforms as DMMA tiles
+    const X4Layout lay4(n, F);
+    const size_t smem4 = (size_t)lay4.total * 8;
+    const int KS = (n + 3) / 4, NT = (lay4.H + 7) / 8;
+    if (smem4 <= optin && !ctx->force_generic && KS == 3 && NT == 3) {
+      fo_prof_scope prof(ctx, FO_PROF_PER_XF);
+      if (out.grid) {
+        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<3, 3, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        per_xf4_kernel<3, 3, true><<<blocks, X4_THREADS, smem4, ctx->stream>>>(
+            lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
+      } else {
+        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<3, 3, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        per_xf4_kernel<3, 3, false><<<blocks, X4_THREADS, smem4, ctx->stream>>>(
+            lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
+      }
+      FO_LAUNCH_CHECK(ctx);
+      return FO_OK;
+    }
+  }
   {  // fast path: everything resident in shared memory, twiddles in the parameter constant bank
     const X3Layout lay(n, F);
     const size_t smem3 = lay.total * 8;
@@ -950,12 +1385,7 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
       static thread_local X3Tw tw;  // 16 KB: keep it off the stack
       static thread_local int tw_n = -1, tw_F = -1;
       if (tw_n != n || tw_F != F) {
-        for (int m = 1; m <= n; ++m)
-          for (int d = 0; d < lay.HP; ++d) {
-            const double ang = kTwoPi * (double)((m * d) % F) / (double)F;
-            tw.c[(m - 1) * lay.HP + d] = d < lay.H ? cos(ang) : 0.0;
-            tw.s[(m - 1) * lay.HP + d] = d < lay.H ? sin(ang) : 0.0;
-          }
+        fo_fill_tw(tw, n, F, lay.H, lay.HP);
         tw_n = n;
         tw_F = F;
       }

@@ -23,11 +23,13 @@
 // All arithmetic is FP64.
 #include <math.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
 #include "fo_internal.h"
+#include "fo_symdft.cuh"
 
 namespace {
 
@@ -848,6 +850,417 @@ sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K5-K7 fast path (sph_isoft2_kernel): same mathematics as sph_isoft_kernel, organised like
+// per_xf3_kernel (fo_symdft.cuh) so that the FP64 pipe, not L2 / shared memory, is the limit:
+//   * persistent CTAs; a CTA owns the four beta planes k = {2c, 2c+1, F-2-2c, F-1-2c} and keeps its
+//     slice of the Wigner table in shared memory for all its pairs (the generic kernel streams
+//     0.7 MB of table per pair from L2).  Only m1 >= 0 entries are stored:
+//         d^l_{-m1,m2}(beta_k) = (-1)^{l+m2} d^l_{m1,m2}(beta_{F-1-k})
+//     so the mirrored plane supplies the -m1 values.  Entries are ordered by shell
+//     lmin = max(m1, m2): level l is the prefix of (l+1)^2 entries, lanes of a warp share lmin.
+//   * K5: a thread owns (|m1|, m2), accumulates S(+m1), S(-m1) for even / odd l separately
+//     (orientation o: I_inv^l = (-1)^l I^l) and writes E = S(+)+S(-), O = S(+)-S(-) for both
+//     orientations as the rows of stage A;
+//   * stage A (m1 -> alpha) and stage B (m2 -> gamma, half-complex -> real) are sym_row passes, one
+//     real row per thread, twiddles as uniform constant-bank operands; both orientations at once;
+//   * arg-max per orientation, and the parabola neighbours that lie inside the CTA's planes.
+// ------------------------------------------------------------------------------------------
+constexpr int I2_THREADS = 512;
+constexpr int I2_DC = 9;
+constexpr int I2_KC = 4;
+
+struct I2Layout {
+  int L, L1, W, F, H, HP, nchunk, NP, RA, RAp, RB, RBp, dts;
+  int o_lvl[65];
+  int o_dts, o_ae, o_ao, o_br, o_bi, o_red, total;  // shared-memory offsets in doubles
+  I2Layout() {}
+  explicit I2Layout(int L_) {
+    L = L_;
+    L1 = L + 1;
+    W = 2 * L + 1;
+    F = 2 * L1;
+    H = F / 2 + 1;
+    HP = ((H + I2_DC - 1) / I2_DC) * I2_DC;
+    nchunk = F / I2_KC;
+    NP = L1 * L1;
+    RA = I2_KC * L1 * 2;
+    RAp = ((RA + 7) / 16) * 16 + 8 + 2;  // == 10 (mod 16): A-fragment k rows spread over the banks and
+                                         // the 16-byte K5 stores of consecutive m1 hit distinct bank groups
+    RB = F * I2_KC;
+    RBp = RB | 1;   // 8-byte stores of consecutive m2 land in distinct banks
+    int off = 0;
+    for (int l = 0; l <= 64; ++l) {
+      o_lvl[l] = off;
+      if (l <= L) off += (l + 1) * (l + 1) * I2_KC;
+    }
+    dts = o_lvl[L] + L1 * L1 * I2_KC;
+    o_dts = 0;
+    o_ae = o_dts + dts;
+    o_ao = o_ae + 2 * L1 * RAp;
+    o_br = o_ao + 2 * L1 * RAp;
+    o_bi = o_br + 2 * L1 * RBp;
+    o_red = o_bi + 2 * L1 * RBp;
+    total = o_red + 96;
+  }
+};
+
+__host__ __device__ __forceinline__ int i2_plane(int F, int chunk, int kk) {
+  return kk < 2 ? 2 * chunk + kk : F - 4 - 2 * chunk + kk;  // kk: 0,1 -> 2c,2c+1 ; 2,3 -> F-2-2c, F-1-2c
+}
+
+// DtP[chunk][level l][pair entry t < (l+1)^2][kk] from the dense table Dt[m2][m1+L][l][k]
+__global__ void sph_wigner_pack_kernel(const double* __restrict__ Dt, const __grid_constant__ I2Layout Y,
+                                       double* __restrict__ DtP) {
+  const int L = Y.L, L1 = Y.L1, W = Y.W, F = Y.F;
+  const int total = Y.nchunk * Y.dts;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e / Y.dts;
+    int r = e - c * Y.dts;
+    int l = 0;
+    while (l < L && r >= Y.o_lvl[l + 1]) ++l;
+    r -= Y.o_lvl[l];
+    const int t = r / I2_KC, kk = r - t * I2_KC;
+    int s = (int)sqrt((double)t);
+    while ((s + 1) * (s + 1) <= t) ++s;
+    while (s * s > t) --s;
+    const int q = t - s * s;
+    const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
+    DtP[e] = Dt[(((size_t)m2 * W + (a + L)) * L1 + l) * F + i2_plane(F, c, kk)];
+  }
+}
+
+struct Iso2Out {
+  double* part_val;   // [P][O][nchunk]
+  int* part_idx;      // [P][O][nchunk]  flat (a F + k) F + g
+  double* part_nb;    // [P][O][nchunk][6]  |neighbour values| (NaN: outside this CTA's planes)
+  double* grid;       // [P][O][F][F][F] or null
+  long long* dbg;     // optional: per-phase cycle counters of CTA 0 (FO_DEBUG_TIMING=1)
+};
+
+#define I2_TICK(slot)                                              \
+  do {                                                             \
+    if (out.dbg && blockIdx.x == 0 && tid == 0) {                  \
+      const long long now_ = clock64();                            \
+      atomicAdd((unsigned long long*)&out.dbg[slot], (unsigned long long)(now_ - tick_)); \
+      tick_ = now_;                                                \
+    }                                                              \
+  } while (0)
+
+// KS = ceil(L/4) k-steps, NT = number of 8-wide output tiles handled by DMMA; NYQ: H = 8 NT + 1, the
+// last output (alpha or gamma = F/2) is the alternating sum c0 + sum (-1)^m E_m, done on the side.
+template <int KS, int NT, bool NYQ, bool WANT_GRID>
+__global__ void __launch_bounds__(I2_THREADS, 1)
+sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict__ Ihalf,
+                  const double* __restrict__ DtP, int npairs, int norient, Iso2Out out) {
+  extern __shared__ double smj[];
+  const int L = Y.L, L1 = Y.L1, W = Y.W, F = Y.F, H = Y.H;
+  const int RA = Y.RA, RAp = Y.RAp, RB = Y.RB, RBp = Y.RBp;
+  double* DtS = smj + Y.o_dts;
+  double* AE = smj + Y.o_ae;   // [o][m1 = 0..L][RAp]   (m1 = 0: c0)
+  double* AO = smj + Y.o_ao;   // [o][m1][RAp]
+  double* BR = smj + Y.o_br;   // [o][m2 = 0..L][RBp]   row = a * KC + kk
+  double* BI = smj + Y.o_bi;
+  double* red = smj + Y.o_red;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int chunk = blockIdx.x % Y.nchunk;
+  const int jstart = blockIdx.x / Y.nchunk, jstride = gridDim.x / Y.nchunk;
+  for (int e = tid; e < Y.dts; e += I2_THREADS) DtS[e] = DtP[(size_t)chunk * Y.dts + e];
+  SymMma<KS, NT> mm;
+  mm.init(L, F, NYQ ? H - 1 : H, lane);
+  __syncthreads();
+
+  long long tick_ = clock64();
+  for (int pair = jstart; pair < npairs; pair += jstride) {
+    const double2* Ip = Ihalf + (size_t)pair * L1 * W * L1;
+    I2_TICK(0);
+    // ---- K5: thread = (pair entry t, half h): planes kk = 2h, 2h+1
+    for (int w = tid; w < 2 * Y.NP; w += I2_THREADS) {
+      const int t = w >> 1, h = w & 1;
+      int s = (int)sqrtf((float)t);
+      while ((s + 1) * (s + 1) <= t) ++s;
+      while (s * s > t) --s;
+      const int q = t - s * s;
+      const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
+      const double2* ipp = Ip + ((size_t)m2 * W + (L + a)) * L1;
+      const double2* ipm = Ip + ((size_t)m2 * W + (L - a)) * L1;
+      double2 pe[2], po[2], me[2], mo[2];
+#pragma unroll
+      for (int kq = 0; kq < 2; ++kq) pe[kq] = po[kq] = me[kq] = mo[kq] = make_double2(0.0, 0.0);
+      double2 cp = ipp[s], cm = ipm[s];
+      for (int l = s; l <= L; ++l) {
+        const double2 cpn = ipp[l < L ? l + 1 : l], cmn = ipm[l < L ? l + 1 : l];  // prefetch next level
+        const double* dp = DtS + Y.o_lvl[l] + t * I2_KC;
+        const double2 dA = *reinterpret_cast<const double2*>(dp + 2 * h);        // planes 2h, 2h+1
+        const double2 dB = *reinterpret_cast<const double2*>(dp + 2 - 2 * h);    // their mirrors 3-2h-1, 3-2h
+        const double dpl[2] = {dA.x, dA.y};
+        const double dmi[2] = {dB.y, dB.x};  // mirror(2h) = 3-2h, mirror(2h+1) = 2-2h
+        if (l & 1) {
+#pragma unroll
+          for (int kq = 0; kq < 2; ++kq) {
+            po[kq].x = fma(dpl[kq], cp.x, po[kq].x);
+            po[kq].y = fma(dpl[kq], cp.y, po[kq].y);
+            mo[kq].x = fma(dmi[kq], cm.x, mo[kq].x);
+            mo[kq].y = fma(dmi[kq], cm.y, mo[kq].y);
+          }
+        } else {
+#pragma unroll
+          for (int kq = 0; kq < 2; ++kq) {
+            pe[kq].x = fma(dpl[kq], cp.x, pe[kq].x);
+            pe[kq].y = fma(dpl[kq], cp.y, pe[kq].y);
+            me[kq].x = fma(dmi[kq], cm.x, me[kq].x);
+            me[kq].y = fma(dmi[kq], cm.y, me[kq].y);
+          }
+        }
+        cp = cpn;
+        cm = cmn;
+      }
+      const double sm2 = (m2 & 1) ? -1.0 : 1.0;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const double so = o ? -1.0 : 1.0;
+#pragma unroll
+        for (int kq = 0; kq < 2; ++kq) {
+          // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
+          const double spx = fma(so, po[kq].x, pe[kq].x), spy = fma(so, po[kq].y, pe[kq].y);
+          const double smx = sm2 * fma(-so, mo[kq].x, me[kq].x), smy = sm2 * fma(-so, mo[kq].y, me[kq].y);
+          const int row = ((2 * h + kq) * L1 + m2) * 2;
+          double2* ae = reinterpret_cast<double2*>(AE + (size_t)(o * L1 + a) * RAp + row);
+          double2* ao = reinterpret_cast<double2*>(AO + (size_t)(o * L1 + a) * RAp + row);
+          if (a == 0) {
+            *ae = make_double2(spx, spy);
+            *ao = make_double2(0.0, 0.0);
+          } else {
+            *ae = make_double2(spx + smx, spy + smy);
+            *ao = make_double2(spx - smx, spy - smy);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    I2_TICK(1);
+    // ---- stage A: tiles of 8 rows (o, kk, m2, part): U[a] = P + iQ, U[F-a] = P - iQ
+    for (int tile = warp; tile * 8 < norient * RA; tile += I2_THREADS / 32) {
+      const int r = tile * 8 + g;  // RA is a multiple of 8: every tile is full
+      const int o = r / RA, row = r - o * RA;
+      const int part = row & 1, line = row >> 1;
+      const int kk = line / L1, m2 = line - kk * L1;
+      const double sgn = part ? 1.0 : -1.0;
+      double* Bout = (part ? BI : BR) + (size_t)(o * L1 + m2) * RBp + kk;
+      const double* e0 = AE + (size_t)(o * L1) * RAp + row;
+      const double* o1 = AO + (size_t)(o * L1 + 1) * RAp + row;
+      double P[NT][2], Q[NT][2];
+      mm.run(e0 + RAp - g, o1 - g, RAp, L, e0[0], lane, P, Q);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = nt * 8 + t4 * 2 + q;
+          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
+          if (d < (NYQ ? H - 1 : H)) {
+            Bout[d * I2_KC] = fma(sgn, qx, P[nt][q]);
+            if (d != 0 && 2 * d != F) Bout[(F - d) * I2_KC] = fma(-sgn, qx, P[nt][q]);
+          }
+        }
+      if (NYQ) {  // a = F/2: U = c0 + sum_m (-1)^m E_m  (sin terms vanish)
+        double acc = (t4 == 0) ? e0[0] : 0.0;
+        for (int m = 1 + t4; m <= L; m += 4) {
+          const double ev = e0[(size_t)m * RAp];
+          acc += (m & 1) ? -ev : ev;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (t4 == 0) Bout[(F / 2) * I2_KC] = acc;
+      }
+    }
+    __syncthreads();
+    I2_TICK(2);
+    // ---- stage B: tiles of 8 rows (o, a, kk): g[gam] = aa - bb, g[F-gam] = aa + bb; arg-max
+    double bv0 = -1e300, bv1 = -1e300;
+    int bi0 = 0x7fffffff, bi1 = 0x7fffffff;
+    for (int tile = warp; tile * 8 < norient * RB; tile += I2_THREADS / 32) {
+      const int r = tile * 8 + g;
+      const int o = r / RB, rowb = r - o * RB;
+      const int a = rowb / I2_KC, kk = rowb - a * I2_KC;
+      const int k = i2_plane(F, chunk, kk);
+      const int base = (a * F + k) * F;
+      const double* br = BR + (size_t)(o * L1) * RBp + rowb;
+      const double* bi1p = BI + (size_t)(o * L1 + 1) * RBp + rowb;
+      const double v0 = br[0];
+      double A[NT][2], Bq[NT][2];
+      mm.run(br + RBp - g, bi1p - g, RBp, L, 0.0, lane, A, Bq);
+      double g1[NT][2], g2[NT][2];
+      double cmax = -1e300;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = nt * 8 + t4 * 2 + q;
+          const double aa = fma(2.0, A[nt][q], v0), bb = 2.0 * Bq[nt][q];
+          const bool in = d < (NYQ ? H - 1 : H);
+          g1[nt][q] = in ? aa - bb : -1e300;
+          g2[nt][q] = (in && d != 0 && 2 * d != F) ? aa + bb : -1e300;
+          cmax = fmax(cmax, fmax(g1[nt][q], g2[nt][q]));
+          if (WANT_GRID) {
+            double* grow = out.grid + (((size_t)pair * norient + o) * F * F * F + (size_t)base);
+            if (in) grow[d] = aa - bb;
+            if (in && d != 0 && 2 * d != F) grow[F - d] = aa + bb;
+          }
+        }
+      double gny = -1e300;
+      if (NYQ) {  // gamma = F/2: g = v0 + 2 sum_m2 (-1)^m2 Vr_m2
+        double acc = 0.0;
+        for (int m = 1 + t4; m <= L; m += 4) {
+          const double ev = br[(size_t)m * RBp];
+          acc += (m & 1) ? -ev : ev;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (t4 == 0) {
+          gny = fma(2.0, acc, v0);
+          cmax = fmax(cmax, gny);
+          if (WANT_GRID) out.grid[((size_t)pair * norient + o) * F * F * F + (size_t)base + F / 2] = gny;
+        }
+      }
+      const double cur = o ? bv1 : bv0;
+      if (cmax >= cur) {
+        double tbv = o ? bv1 : bv0;
+        int tbi = o ? bi1 : bi0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int d = nt * 8 + t4 * 2 + q;
+            if (g1[nt][q] > tbv || (g1[nt][q] == tbv && base + d < tbi)) { tbv = g1[nt][q]; tbi = base + d; }
+            if (g2[nt][q] > tbv || (g2[nt][q] == tbv && base + F - d < tbi)) { tbv = g2[nt][q]; tbi = base + F - d; }
+          }
+        if (NYQ && (gny > tbv || (gny == tbv && base + F / 2 < tbi))) { tbv = gny; tbi = base + F / 2; }
+        if (o) { bv1 = tbv; bi1 = tbi; } else { bv0 = tbv; bi0 = tbi; }
+      }
+    }
+    I2_TICK(3);
+    // block reduction per orientation
+    int* redi = reinterpret_cast<int*>(red + 48);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      double v = o ? bv1 : bv0;
+      int i = o ? bi1 : bi0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, off);
+        const int oi = __shfl_down_sync(0xffffffffu, i, off);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+      }
+      if (lane == 0) {
+        red[o * 16 + warp] = v;
+        redi[o * 16 + warp] = i;
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      double v = red[tid * 16];
+      int i = redi[tid * 16];
+      for (int w = 1; w < I2_THREADS / 32; ++w) {
+        const double ov = red[tid * 16 + w];
+        const int oi = redi[tid * 16 + w];
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+      }
+      red[32 + tid] = v;
+      redi[32 + tid] = i;
+    }
+    __syncthreads();
+    // ---- parabola neighbours inside this CTA's planes: warp w < 6 -> neighbour w, both orientations
+    {
+      if (warp < 6) {
+        for (int o = 0; o < norient; ++o) {
+          const int fi = redi[32 + o];
+          const bool ok = fi != 0x7fffffff;
+          const int a0 = ok ? fi / (F * F) : 0, k0 = ok ? (fi / F) % F : 0, g0 = ok ? fi % F : 0;
+          const int ax = warp >> 1, sg = (warp & 1) ? -1 : 1;
+          int qa = a0, qk = k0, qg = g0;
+          if (ax == 0) qa = (a0 + sg + F) % F;
+          if (ax == 1) qk = (k0 + sg + F) % F;
+          if (ax == 2) qg = (g0 + sg + F) % F;
+          int kk = -1;
+          for (int c = 0; c < I2_KC; ++c)
+            if (i2_plane(F, chunk, c) == qk) kk = c;
+          double acc = 0.0;
+          if (kk >= 0) {
+            const int rowb = qa * I2_KC + kk;
+            for (int m2 = lane; m2 <= L; m2 += 32) {
+              const double vr = BR[(size_t)(o * L1 + m2) * RBp + rowb];
+              if (m2 == 0) {
+                acc += vr;
+              } else {
+                const double vi = BI[(size_t)(o * L1 + m2) * RBp + rowb];
+                double sn, cs;
+                sincospi(2.0 * (double)((m2 * qg) % F) / (double)F, &sn, &cs);
+                acc += 2.0 * (vr * cs - vi * sn);
+              }
+            }
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+          if (lane == 0)
+            out.part_nb[((((size_t)pair * norient + o) * Y.nchunk) + chunk) * 6 + warp] =
+                kk >= 0 ? fabs(acc) : __longlong_as_double(0x7ff8000000000000LL);
+        }
+      }
+      if (tid < norient) {
+        out.part_val[((size_t)pair * norient + tid) * Y.nchunk + chunk] = red[32 + tid];
+        out.part_idx[((size_t)pair * norient + tid) * Y.nchunk + chunk] = redi[32 + tid];
+      }
+    }
+    __syncthreads();
+    I2_TICK(4);
+  }
+}
+
+// One CTA per (pair, orientation): best chunk, then the parabola; neighbours the chunk CTA could not
+// evaluate (NaN) are computed by the direct Wigner sum.
+__global__ void __launch_bounds__(256)
+sph_final2_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, int L, int norient,
+                  int nchunk, const double* __restrict__ part_val, const int* __restrict__ part_idx,
+                  const double* __restrict__ part_nb, long long* __restrict__ best_idx,
+                  double* __restrict__ best_val, double* __restrict__ frac_idx) {
+  __shared__ double nb[6];
+  const size_t po = blockIdx.x;
+  const size_t p = po / norient;
+  const int o = (int)(po % norient);
+  const int F = 2 * (L + 1);
+  double bv = -1e300;
+  int bi = 0x7fffffff, bc = 0;
+  for (int c = 0; c < nchunk; ++c) {
+    const double v = part_val[po * nchunk + c];
+    const int i = part_idx[po * nchunk + c];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; bc = c; }
+  }
+  const bool ok = bi != 0x7fffffff;
+  const int b3[3] = {ok ? bi / (F * F) : 0, ok ? (bi / F) % F : 0, ok ? bi % F : 0};
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < 6) {
+    double v = part_nb[(po * nchunk + bc) * 6 + w];
+    if (v != v) {  // not available from the chunk CTA
+      const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
+      int q[3] = {b3[0], b3[1], b3[2]};
+      q[ax] = (q[ax] + sgn + F) % F;
+      v = fabs(iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, L, q[0], q[1], q[2],
+                         o ? -1.0 : 1.0, lane));
+    }
+    if (lane == 0) nb[w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    best_val[po] = bv;
+    for (int ax = 0; ax < 3; ++ax) {
+      best_idx[po * 3 + ax] = b3[ax];
+      const double y1 = nb[2 * ax], y3 = nb[2 * ax + 1], y2 = fabs(bv);
+      frac_idx[po * 3 + ax] = (double)b3[ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- host side
 
 int grid_for(size_t total, int threads, int cap = 1 << 16) {
@@ -874,6 +1287,19 @@ int ensure_wigner(fo_ctx* ctx, int L) {
   FO_LAUNCH_CHECK(ctx);
   ctx->wig.Jmax = L;
   ctx->wig.bytes = n * 8;
+  // packed per-chunk slices for the fast iSOFT kernel (bandwidths with 2B % 4 == 0)
+  if (ctx->wig.d_packed) {
+    cudaFree(ctx->wig.d_packed);
+    ctx->wig.d_packed = nullptr;
+  }
+  if ((2 * (L + 1)) % I2_KC == 0) {
+    const I2Layout Y(L);
+    if (cudaMalloc(&ctx->wig.d_packed, (size_t)Y.nchunk * Y.dts * 8) != cudaSuccess)
+      return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the packed Wigner table failed");
+    sph_wigner_pack_kernel<<<grid_for((size_t)Y.nchunk * Y.dts, 256), 256, 0, ctx->stream>>>(
+        ctx->wig.d_table, Y, ctx->wig.d_packed);
+    FO_LAUNCH_CHECK(ctx);
+  }
   return FO_OK;
 }
 
@@ -893,6 +1319,69 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
   if (npairs == 0) return FO_OK;
   FO_CHECK(ensure_wigner(ctx, L));
   const int F = 2 * (L + 1);
+  if (ctx->wig.d_packed && !ctx->force_generic) {
+    const I2Layout Y(L);
+    const size_t smem2 = (size_t)Y.total * 8;
+    if (smem2 <= ctx->prop.sharedMemPerBlockOptin && L >= 1) {
+      const int nch = Y.nchunk;
+      void* part = nullptr;
+      FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * nch * (8 + 4 + 48) + 64, &part));
+      Iso2Out o2;
+      o2.part_val = (double*)part;
+      o2.part_nb = o2.part_val + (size_t)npairs * norient * nch;
+      o2.part_idx = (int*)(o2.part_nb + (size_t)npairs * norient * nch * 6);
+      o2.grid = d_grid;
+      o2.dbg = nullptr;
+      if (getenv("FO_DEBUG_TIMING")) {
+        void* dbg = nullptr;
+        FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, 64, &dbg));
+        FO_CUDA(ctx, cudaMemsetAsync(dbg, 0, 64, ctx->stream));
+        o2.dbg = (long long*)dbg;
+      }
+      int per = ctx->prop.multiProcessorCount / nch;
+      if (per < 1) per = 1;
+      if ((int64_t)per > npairs) per = (int)npairs;
+      const unsigned blocks = (unsigned)(per * nch);
+      fo_prof_scope prof(ctx, FO_PROF_SPH_ISOFT);
+#define FO_I2_LAUNCH(KS_, NT_, NYQ_)                                                                      \
+  do {                                                                                                    \
+    if (d_grid) {                                                                                         \
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft2_kernel<KS_, NT_, NYQ_, true>,                          \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));        \
+      sph_isoft2_kernel<KS_, NT_, NYQ_, true><<<blocks, I2_THREADS, smem2, ctx->stream>>>(                \
+          Y, d_Ihalf, ctx->wig.d_packed, (int)npairs, norient, o2);                                       \
+    } else {                                                                                              \
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft2_kernel<KS_, NT_, NYQ_, false>,                         \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));        \
+      sph_isoft2_kernel<KS_, NT_, NYQ_, false><<<blocks, I2_THREADS, smem2, ctx->stream>>>(               \
+          Y, d_Ihalf, ctx->wig.d_packed, (int)npairs, norient, o2);                                       \
+    }                                                                                                     \
+  } while (0)
+      const int KSq = (L + 3) / 4;
+      const bool nyq = (Y.H % 8) == 1;
+      const int NTq = nyq ? (Y.H - 1) / 8 : (Y.H + 7) / 8;
+      if (KSq == 4 && NTq == 2 && nyq) FO_I2_LAUNCH(4, 2, true);        // Jmax 13, 15
+      else if (KSq == 2 && NTq == 1 && nyq) FO_I2_LAUNCH(2, 1, true);   // Jmax 7
+      else if (KSq == 3 && NTq == 2 && !nyq) FO_I2_LAUNCH(3, 2, false); // Jmax 9, 11
+      else if (KSq == 6 && NTq == 3 && !nyq) FO_I2_LAUNCH(6, 3, false); // Jmax 21
+      else goto generic_path;
+#undef FO_I2_LAUNCH
+      FO_LAUNCH_CHECK(ctx);
+      if (o2.dbg) {
+        long long h[8];
+        FO_CUDA(ctx, cudaMemcpyAsync(h, o2.dbg, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[isoft2 CTA0 cycles] wait/load %lld  K5 %lld  stageA %lld  stageB %lld  reduce+nb %lld\n",
+                h[0], h[1], h[2], h[3], h[4]);
+      }
+      sph_final2_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+          d_Ihalf, ctx->wig.d_table, L, norient, nch, o2.part_val, o2.part_idx, o2.part_nb, d_best_idx,
+          d_best_val, d_frac);
+      FO_LAUNCH_CHECK(ctx);
+      return FO_OK;
+    }
+  }
+generic_path:
   int KC = 4;
   while (KC > 1 && (isoft_smem(L, KC) > 100 * 1024 || F % KC)) KC >>= 1;
   const size_t smem = isoft_smem(L, KC);
