@@ -103,9 +103,12 @@ class Blj256:
         d -= np.round(d / self.box) * self.box
         return bool(float(np.abs(d).max()) < self.box[0] / self.F)
 
-    # FP64 work of the dominant kernel (per_sf_kernel<5>), per pair, as executed:
-    # 2 structures x 256 atoms x 100 (i,j) x [4 DMUL + 2 x 40 DFMA]  (DESIGN.md "K_sf")
+    # FP64 work of the dominant kernel (structure factors, per_sf2_kernel), per pair: the 8-real-sum
+    # formulation needs 2 structures x 256 atoms x 100 (i,j) x [4 DMUL + 10 l x 8 FMA]  (DESIGN.md
+    # "K_sf").  The tensor-core kernel executes 24/20 of the FMAs (column padding 20 -> 24); the
+    # padding is NOT counted here.
     dominant = "per_sf"
+    dominant_pipe = "fp64_tensor"
 
     def dominant_flops_per_pair(self):
         return 2 * 256 * 100 * (4 * 1 + 80 * 2)
@@ -185,6 +188,7 @@ class Lj38:
         return bool(np.all(np.isfinite(res[1])))
 
     dominant = "sph_isoft"
+    dominant_pipe = "fp64_tensor"
 
     def dominant_flops_per_pair(self):
         # iSOFT, both orientations (DESIGN.md "K_isoft"): executed real FMA count x 2
@@ -385,18 +389,23 @@ def run_ours(args, wl):
         if dist is not None:
             dist.destroy_process_group()
         return
-    peak = ctx.measure_fp64_peak()
+    peak_vec = ctx.measure_fp64_peak()
+    peak_tensor = ctx.measure_fp64_tensor_peak()
+    peak = peak_tensor if getattr(wl, "dominant_pipe", "") == "fp64_tensor" else peak_vec
     dom_ms, dom_n = prof.get(wl.dominant, (0.0, 0))
     total_prof = sum(v[0] for v in prof.values())
     roof = None
     if dom_n:
         pairs_timed = P * args.steps
         achieved = wl.dominant_flops_per_pair() * pairs_timed / (dom_ms * 1e-3) / 1e12
-        roof = {"bound": "fp64", "kernel": wl.dominant, "achieved": achieved, "peak": peak,
+        roof = {"bound": "fp64", "pipe": getattr(wl, "dominant_pipe", "fp64_vector"), "kernel": wl.dominant, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": "measured in this run (fo_measure_fp64_peak DFMA microbenchmark); "
-                               "MEASURED_PEAKS.json has no FP64 figure",
-                "flops_counted": "executed FP64 (DFMA=2, DMUL=1) of the kernel, symmetry-reduced",
+                "peak_source": "measured in this run: FP64 tensor pipe (mma.sync.m8n8k4.f64 "
+                               "microbenchmark, fo_measure_fp64_tensor_peak); MEASURED_PEAKS.json has no "
+                               "FP64 figure",
+                "peak_fp64_vector_tflops": peak_vec, "peak_fp64_tensor_tflops": peak_tensor,
+                "flops_counted": "useful FP64 of the symmetry-reduced algorithm (FMA=2, MUL=1); "
+                                 "tile padding executed by the kernel is not counted",
                 "algorithmic_unsymmetrised_tflops": wl.algorithmic_flops_per_pair() * pairs_timed /
                 (ms_dev * 1e-3) / 1e12,
                 "kernel_ms_per_launch": dom_ms / dom_n, "kernel_share_of_step": dom_ms / total_prof,
@@ -439,7 +448,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="blj256", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=96)
+    ap.add_argument("--cpu-sample", type=int, default=1536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()

@@ -46,6 +46,8 @@ SIGNATURES = {
     "fo_set_perm": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
     "fo_next_fast_len": (ctypes.c_int64, [ctypes.c_int64]),
     "fo_measure_fp64_peak": (ctypes.c_int, [c_void_p, c_f64p]),
+    "fo_measure_fp64_tensor_peak": (ctypes.c_int, [c_void_p, c_f64p]),
+    "fo_set_option": (ctypes.c_int, [c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "fo_per_defaults": (ctypes.c_int, [ctypes.c_int64, c_f64p, c_f64p, c_i64p, c_i64p]),
     "fo_per_structure_factors": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p,
                                                 ctypes.c_int64, c_void_p]),
@@ -207,6 +209,15 @@ class Context(object):
         v = ctypes.c_double()
         self._check(self._lib.fo_measure_fp64_peak(self._h, ctypes.byref(v)), "fo_measure_fp64_peak")
         return v.value
+
+    def measure_fp64_tensor_peak(self):
+        v = ctypes.c_double()
+        self._check(self._lib.fo_measure_fp64_tensor_peak(self._h, ctypes.byref(v)),
+                    "fo_measure_fp64_tensor_peak")
+        return v.value
+
+    def set_option(self, name, value):
+        self._check(self._lib.fo_set_option(self._h, name.encode(), int(value)), "fo_set_option")
 
     def set_perm(self, perm, natoms):
         """perm: sequence of index arrays (0-based), as the reference's `perm`/`permlist`."""

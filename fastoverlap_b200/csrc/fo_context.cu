@@ -183,6 +183,64 @@ extern "C" int fo_device_info(fo_ctx* ctx, int64_t out[4]) {
 
 extern "C" int64_t fo_launch_count(const fo_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int fo_set_option(fo_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return FO_ERR_INVALID;
+  if (strcmp(name, "force_generic") == 0) {
+    ctx->force_generic = value != 0;
+    return FO_OK;
+  }
+  return fo_fail(ctx, FO_ERR_INVALID, "unknown option '%s'", name);
+}
+
+__global__ void fo_dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i][0] = threadIdx.x;
+    c[i][1] = i;
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+extern "C" int fo_measure_fp64_tensor_peak(fo_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return FO_ERR_INVALID;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* d_out = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, 256, &d_out));
+  cudaEvent_t e0, e1;
+  FO_CUDA(ctx, cudaEventCreate(&e0));
+  FO_CUDA(ctx, cudaEventCreate(&e1));
+  const int iters = 8192, threads = 512;
+  const int blocks = ctx->prop.multiProcessorCount;
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 6; ++rep) {
+    FO_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    fo_dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)d_out, iters, 1.0000001, 0.999999);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    FO_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    FO_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = 2.0 * 256.0 * 8.0 * (double)iters * (threads / 32) * (double)blocks;
+  *tflops = flops / (best_ms * 1e-3) / 1e12;
+  return FO_OK;
+}
+
 extern "C" int fo_profile_begin(fo_ctx* ctx) {
   if (!ctx) return FO_ERR_INVALID;
   for (auto& r : ctx->prof) {

@@ -44,7 +44,7 @@ struct fo_ctx {
   int64_t perm_natoms = 0;  // natoms the perm was declared for (0 = unset -> one group of all)
 
   // growable device scratch (named slots)
-  fo_devbuf scratch[8];
+  fo_devbuf scratch[12];
   // pinned host staging (named slots)
   fo_devbuf pinned[6];
 
@@ -67,6 +67,8 @@ enum {
   FO_SCR_WORK = 5,
   FO_SCR_COEF = 6,
   FO_SCR_MISC = 7,
+  FO_SCR_IPK = 8,
+  FO_SCR_DBG = 9,
 };
 
 struct fo_bank {

@@ -14,6 +14,7 @@
 //   S[ix][iy][l]   ix,iy = 0..2n (k = ix-n, iy-n), l = 0..n (kz >= 0), complex128,
 // because S(-k) = conj(S(k)).  All arithmetic is FP64.
 #include <math.h>
+#include <stdlib.h>
 
 #include "fo_internal.h"
 #include "fo_symdft.cuh"
@@ -161,7 +162,7 @@ per_sf_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
 // and each of the 4 lanes writes one of the four sign combinations (rho, sig).
 // ------------------------------------------------------------------------------------------
 template <int MT, int NT>
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(320, 2)
 per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
                const int32_t* __restrict__ gidx, int ngroups, int natoms, int n, double kx, double ky,
                double kz, double2* __restrict__ bank) {
@@ -1301,7 +1302,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
     const int mtiles = (M * M * 4 + 7) / 8;
     const int MTq = 5;
     const int warps = (mtiles + MTq - 1) / MTq;
-    if (NTq == 3 && warps <= 12 && !ctx->force_generic) {
+    if (NTq == 3 && warps <= 10 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {
       const int Mp = M | 1, Mz = (4 * NTq) | 1;
       const size_t smem = (size_t)SF_TA * (2 * Mp + Mz) * 16;
       const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
@@ -1361,22 +1362,33 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
     const X4Layout lay4(n, F);
     const size_t smem4 = (size_t)lay4.total * 8;
     const int KS = (n + 3) / 4, NT = (lay4.H + 7) / 8;
-    if (smem4 <= optin && !ctx->force_generic && KS == 3 && NT == 3) {
+#define FO_X4_LAUNCH(KS_, NT_)                                                                           \
+  do {                                                                                                   \
+    if (out.grid) {                                                                                      \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<KS_, NT_, true>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));       \
+      per_xf4_kernel<KS_, NT_, true><<<blocks, X4_THREADS, smem4, ctx->stream>>>(                        \
+          lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);       \
+    } else {                                                                                             \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<KS_, NT_, false>,                                 \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));       \
+      per_xf4_kernel<KS_, NT_, false><<<blocks, X4_THREADS, smem4, ctx->stream>>>(                       \
+          lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);       \
+    }                                                                                                    \
+  } while (0)
+    const int code = KS * 10 + NT;
+    if (smem4 <= optin && !ctx->force_generic &&
+        (code == 11 || code == 12 || code == 22 || code == 23 || code == 33)) {
       fo_prof_scope prof(ctx, FO_PROF_PER_XF);
-      if (out.grid) {
-        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<3, 3, true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        per_xf4_kernel<3, 3, true><<<blocks, X4_THREADS, smem4, ctx->stream>>>(
-            lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
-      } else {
-        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<3, 3, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        per_xf4_kernel<3, 3, false><<<blocks, X4_THREADS, smem4, ctx->stream>>>(
-            lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
-      }
+      if (code == 11) FO_X4_LAUNCH(1, 1);
+      else if (code == 12) FO_X4_LAUNCH(1, 2);
+      else if (code == 22) FO_X4_LAUNCH(2, 2);
+      else if (code == 23) FO_X4_LAUNCH(2, 3);
+      else FO_X4_LAUNCH(3, 3);
       FO_LAUNCH_CHECK(ctx);
       return FO_OK;
     }
+#undef FO_X4_LAUNCH
   }
   {  // fast path: everything resident in shared memory, twiddles in the parameter constant bank
     const X3Layout lay(n, F);
@@ -1438,6 +1450,7 @@ size_t bank_elems_per_struct(fo_ctx* ctx, const fo_per_params* p) {
 int64_t chunk_pairs(fo_ctx* ctx, const fo_per_params* p, int64_t npairs, bool want_grid) {
   const size_t per_pair = 2 * bank_elems_per_struct(ctx, p) * 16;
   size_t budget = (size_t)768 << 20;
+  if (const char* e = getenv("FO_PER_BANK_MB")) budget = (size_t)atol(e) << 20;
   int64_t c = (int64_t)(budget / per_pair);
   if (want_grid) {
     const size_t g = (size_t)p->nfspace * p->nfspace * p->nfspace * 8;

@@ -871,7 +871,7 @@ constexpr int I2_DC = 9;
 constexpr int I2_KC = 4;
 
 struct I2Layout {
-  int L, L1, W, F, H, HP, nchunk, NP, RA, RAp, RB, RBp, dts;
+  int L, L1, W, F, H, HP, nchunk, NP, RA, RAp, RB, RBp, dts, ipk;
   int o_lvl[65];
   int o_dts, o_ae, o_ao, o_br, o_bi, o_red, total;  // shared-memory offsets in doubles
   I2Layout() {}
@@ -895,6 +895,7 @@ struct I2Layout {
       if (l <= L) off += (l + 1) * (l + 1) * I2_KC;
     }
     dts = o_lvl[L] + L1 * L1 * I2_KC;
+    ipk = dts / 2;  // double2 elements of the packed coefficients of one pair: [level][entry][+-]
     o_dts = 0;
     o_ae = o_dts + dts;
     o_ao = o_ae + 2 * L1 * RAp;
@@ -930,6 +931,27 @@ __global__ void sph_wigner_pack_kernel(const double* __restrict__ Dt, const __gr
   }
 }
 
+// Ipk[pair][level l][entry t < (l+1)^2][sign +-] from the dense Ihalf[m2][m1+L][l]
+__global__ void sph_ipack_kernel(const double2* __restrict__ Ihalf, const __grid_constant__ I2Layout Y,
+                                 size_t npairs, double2* __restrict__ Ipk) {
+  const int L = Y.L, L1 = Y.L1, W = Y.W;
+  const size_t total = npairs * (size_t)Y.ipk;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = e / Y.ipk;
+    int r = (int)(e - p * Y.ipk);
+    int l = 0;
+    while (l < L && r >= (Y.o_lvl[l + 1] >> 1)) ++l;
+    r -= Y.o_lvl[l] >> 1;
+    const int t = r >> 1, sg = r & 1;
+    int s = (int)sqrtf((float)t);
+    while ((s + 1) * (s + 1) <= t) ++s;
+    while (s * s > t) --s;
+    const int q = t - s * s;
+    const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
+    Ipk[e] = Ihalf[p * (size_t)L1 * W * L1 + ((size_t)m2 * W + (L + (sg ? -a : a))) * L1 + l];
+  }
+}
+
 struct Iso2Out {
   double* part_val;   // [P][O][nchunk]
   int* part_idx;      // [P][O][nchunk]  flat (a F + k) F + g
@@ -951,7 +973,7 @@ struct Iso2Out {
 // last output (alpha or gamma = F/2) is the alternating sum c0 + sum (-1)^m E_m, done on the side.
 template <int KS, int NT, bool NYQ, bool WANT_GRID>
 __global__ void __launch_bounds__(I2_THREADS, 1)
-sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict__ Ihalf,
+sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict__ Ipk,
                   const double* __restrict__ DtP, int npairs, int norient, Iso2Out out) {
   extern __shared__ double smj[];
   const int L = Y.L, L1 = Y.L1, W = Y.W, F = Y.F, H = Y.H;
@@ -973,67 +995,74 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
 
   long long tick_ = clock64();
   for (int pair = jstart; pair < npairs; pair += jstride) {
-    const double2* Ip = Ihalf + (size_t)pair * L1 * W * L1;
     I2_TICK(0);
-    // ---- K5: thread = (pair entry t, half h): planes kk = 2h, 2h+1
-    for (int w = tid; w < 2 * Y.NP; w += I2_THREADS) {
-      const int t = w >> 1, h = w & 1;
-      int s = (int)sqrtf((float)t);
-      while ((s + 1) * (s + 1) <= t) ++s;
-      while (s * s > t) --s;
-      const int q = t - s * s;
-      const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
-      const double2* ipp = Ip + ((size_t)m2 * W + (L + a)) * L1;
-      const double2* ipm = Ip + ((size_t)m2 * W + (L - a)) * L1;
-      double2 pe[2], po[2], me[2], mo[2];
+    // ---- K5: work item = (entry pair {t, NP-1-t}, plane kk).  Pairing a low shell (long l run) with
+    // a high shell (short run) gives every thread ~L+2 levels: no barrier skew.  The coefficients
+    // come from the packed, level-major copy Ipk (coalesced 32-byte reads per lane pair) and are
+    // fetched four levels ahead, so a thread waits for ~(L+2)/4 memory latencies instead of L+1.
+    {
+      const double2* Ik = Ipk + (size_t)pair * Y.ipk;
+      const int nhalf = (Y.NP + 1) >> 1;
+      for (int w = tid; w < nhalf * I2_KC; w += I2_THREADS) {
+        const int kk = w & (I2_KC - 1), qp = w >> 2;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const int t = which ? Y.NP - 1 - qp : qp;
+          if (which && t == qp) break;
+          int s = (int)sqrtf((float)t);
+          while ((s + 1) * (s + 1) <= t) ++s;
+          while (s * s > t) --s;
+          const int q = t - s * s;
+          const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
+          double2 pe = make_double2(0.0, 0.0), po = pe, me = pe, mo = pe;
+          for (int l0 = s; l0 <= L; l0 += 4) {
+            double2 cp[4], cm[4];
+            double dpl[4], dmi[4];
 #pragma unroll
-      for (int kq = 0; kq < 2; ++kq) pe[kq] = po[kq] = me[kq] = mo[kq] = make_double2(0.0, 0.0);
-      double2 cp = ipp[s], cm = ipm[s];
-      for (int l = s; l <= L; ++l) {
-        const double2 cpn = ipp[l < L ? l + 1 : l], cmn = ipm[l < L ? l + 1 : l];  // prefetch next level
-        const double* dp = DtS + Y.o_lvl[l] + t * I2_KC;
-        const double2 dA = *reinterpret_cast<const double2*>(dp + 2 * h);        // planes 2h, 2h+1
-        const double2 dB = *reinterpret_cast<const double2*>(dp + 2 - 2 * h);    // their mirrors 3-2h-1, 3-2h
-        const double dpl[2] = {dA.x, dA.y};
-        const double dmi[2] = {dB.y, dB.x};  // mirror(2h) = 3-2h, mirror(2h+1) = 2-2h
-        if (l & 1) {
+            for (int u = 0; u < 4; ++u) {
+              const int l = min(l0 + u, L);
+              const double2* src = Ik + (Y.o_lvl[l] >> 1) + t * 2;  // o_lvl counts KC = 4 doubles per entry
+              cp[u] = src[0];
+              cm[u] = src[1];
+              const double* dp = DtS + Y.o_lvl[l] + t * I2_KC;
+              dpl[u] = dp[kk];
+              dmi[u] = dp[I2_KC - 1 - kk];
+            }
 #pragma unroll
-          for (int kq = 0; kq < 2; ++kq) {
-            po[kq].x = fma(dpl[kq], cp.x, po[kq].x);
-            po[kq].y = fma(dpl[kq], cp.y, po[kq].y);
-            mo[kq].x = fma(dmi[kq], cm.x, mo[kq].x);
-            mo[kq].y = fma(dmi[kq], cm.y, mo[kq].y);
+            for (int u = 0; u < 4; ++u) {
+              const int l = l0 + u;
+              if (l <= L) {
+                if (l & 1) {
+                  po.x = fma(dpl[u], cp[u].x, po.x);
+                  po.y = fma(dpl[u], cp[u].y, po.y);
+                  mo.x = fma(dmi[u], cm[u].x, mo.x);
+                  mo.y = fma(dmi[u], cm[u].y, mo.y);
+                } else {
+                  pe.x = fma(dpl[u], cp[u].x, pe.x);
+                  pe.y = fma(dpl[u], cp[u].y, pe.y);
+                  me.x = fma(dmi[u], cm[u].x, me.x);
+                  me.y = fma(dmi[u], cm[u].y, me.y);
+                }
+              }
+            }
           }
-        } else {
+          const double sm2 = (m2 & 1) ? -1.0 : 1.0;
+          const int row = (kk * L1 + m2) * 2;
 #pragma unroll
-          for (int kq = 0; kq < 2; ++kq) {
-            pe[kq].x = fma(dpl[kq], cp.x, pe[kq].x);
-            pe[kq].y = fma(dpl[kq], cp.y, pe[kq].y);
-            me[kq].x = fma(dmi[kq], cm.x, me[kq].x);
-            me[kq].y = fma(dmi[kq], cm.y, me[kq].y);
-          }
-        }
-        cp = cpn;
-        cm = cmn;
-      }
-      const double sm2 = (m2 & 1) ? -1.0 : 1.0;
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        const double so = o ? -1.0 : 1.0;
-#pragma unroll
-        for (int kq = 0; kq < 2; ++kq) {
-          // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
-          const double spx = fma(so, po[kq].x, pe[kq].x), spy = fma(so, po[kq].y, pe[kq].y);
-          const double smx = sm2 * fma(-so, mo[kq].x, me[kq].x), smy = sm2 * fma(-so, mo[kq].y, me[kq].y);
-          const int row = ((2 * h + kq) * L1 + m2) * 2;
-          double2* ae = reinterpret_cast<double2*>(AE + (size_t)(o * L1 + a) * RAp + row);
-          double2* ao = reinterpret_cast<double2*>(AO + (size_t)(o * L1 + a) * RAp + row);
-          if (a == 0) {
-            *ae = make_double2(spx, spy);
-            *ao = make_double2(0.0, 0.0);
-          } else {
-            *ae = make_double2(spx + smx, spy + smy);
-            *ao = make_double2(spx - smx, spy - smy);
+          for (int o = 0; o < 2; ++o) {
+            const double so = o ? -1.0 : 1.0;
+            // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
+            const double spx = fma(so, po.x, pe.x), spy = fma(so, po.y, pe.y);
+            const double smx = sm2 * fma(-so, mo.x, me.x), smy = sm2 * fma(-so, mo.y, me.y);
+            double2* ae = reinterpret_cast<double2*>(AE + (size_t)(o * L1 + a) * RAp + row);
+            double2* ao = reinterpret_cast<double2*>(AO + (size_t)(o * L1 + a) * RAp + row);
+            if (a == 0) {
+              *ae = make_double2(spx, spy);
+              *ao = make_double2(0.0, 0.0);
+            } else {
+              *ae = make_double2(spx + smx, spy + smy);
+              *ao = make_double2(spx - smx, spy - smy);
+            }
           }
         }
       }
@@ -1332,9 +1361,12 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       o2.part_idx = (int*)(o2.part_nb + (size_t)npairs * norient * nch * 6);
       o2.grid = d_grid;
       o2.dbg = nullptr;
+      void* ipk = nullptr;
+      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * Y.ipk * 16, &ipk));
+      const double2* d_Ipk = (const double2*)ipk;
       if (getenv("FO_DEBUG_TIMING")) {
         void* dbg = nullptr;
-        FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, 64, &dbg));
+        FO_CHECK(fo_scratch(ctx, FO_SCR_DBG, 64, &dbg));
         FO_CUDA(ctx, cudaMemsetAsync(dbg, 0, 64, ctx->stream));
         o2.dbg = (long long*)dbg;
       }
@@ -1343,18 +1375,21 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       if ((int64_t)per > npairs) per = (int)npairs;
       const unsigned blocks = (unsigned)(per * nch);
       fo_prof_scope prof(ctx, FO_PROF_SPH_ISOFT);
+      sph_ipack_kernel<<<grid_for((size_t)npairs * Y.ipk, 256), 256, 0, ctx->stream>>>(d_Ihalf, Y, (size_t)npairs,
+                                                                                        (double2*)ipk);
+      FO_LAUNCH_CHECK(ctx);
 #define FO_I2_LAUNCH(KS_, NT_, NYQ_)                                                                      \
   do {                                                                                                    \
     if (d_grid) {                                                                                         \
       FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft2_kernel<KS_, NT_, NYQ_, true>,                          \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));        \
       sph_isoft2_kernel<KS_, NT_, NYQ_, true><<<blocks, I2_THREADS, smem2, ctx->stream>>>(                \
-          Y, d_Ihalf, ctx->wig.d_packed, (int)npairs, norient, o2);                                       \
+          Y, d_Ipk, ctx->wig.d_packed, (int)npairs, norient, o2);                                         \
     } else {                                                                                              \
       FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft2_kernel<KS_, NT_, NYQ_, false>,                         \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));        \
       sph_isoft2_kernel<KS_, NT_, NYQ_, false><<<blocks, I2_THREADS, smem2, ctx->stream>>>(               \
-          Y, d_Ihalf, ctx->wig.d_packed, (int)npairs, norient, o2);                                       \
+          Y, d_Ipk, ctx->wig.d_packed, (int)npairs, norient, o2);                                         \
     }                                                                                                     \
   } while (0)
       const int KSq = (L + 3) / 4;

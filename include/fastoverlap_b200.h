@@ -64,6 +64,14 @@ int fo_device_info(fo_ctx* ctx, int64_t out[4]);
 /* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
 int64_t fo_launch_count(const fo_ctx* ctx);
 
+/* Library options.  "force_generic" (0/1): use the any-size kernels instead of the shared-memory
+ * tensor-core fast paths (testing: both families must give the same results). */
+int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
+
+/* Measured throughput of the FP64 tensor pipe (mma.sync.m8n8k4.f64 microbenchmark) in TFLOP/s:
+ * the roofline denominator of the kernels that run their contractions as DMMA. */
+int fo_measure_fp64_tensor_peak(fo_ctx* ctx, double* tflops);
+
 /* Per-kernel device timing with CUDA events on the ctx stream (bench.py roofline).  Between
  * fo_profile_begin and fo_profile_end every launch of a profiled kernel class is bracketed by
  * an event pair; fo_profile_end synchronises and returns, per class, the summed duration in

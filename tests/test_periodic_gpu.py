@@ -201,3 +201,25 @@ def test_multigpu_thread_sharding_identical(ctx):
         return c.per_align_pairs(al._params(), a, b)[:3]
     out = mg.map_pairs(fn, pos1, pos2)
     assert all(np.array_equal(o, r) for o, r in zip(out, ref[:3]))
+
+
+@pytest.mark.parametrize("N,n", [(24, 3), (30, 6), (64, 9), (20, 4)])
+def test_fast_and_generic_kernels_agree(ctx, N, n):
+    """The tensor-core fast paths (per_sf2 / per_xf4) and the any-size kernels (per_sf / per_xf) are
+    two implementations of the same mathematics: same arg-max, values within rounding."""
+    from fastoverlap_b200 import PeriodicAlign
+    rng = np.random.default_rng(N * 100 + n)
+    box = np.array([4.1, 4.4, 4.9])
+    pos1, pos2, _ = _random_pairs(rng, 6, N, box)
+    al = PeriodicAlign(N, box, n=n, ctx=ctx)
+    p = al._params()
+    fast = ctx.per_align_pairs(p, pos1, pos2, want_grid=True)
+    ctx.set_option("force_generic", 1)
+    try:
+        gen = ctx.per_align_pairs(p, pos1, pos2, want_grid=True)
+    finally:
+        ctx.set_option("force_generic", 0)
+    assert np.array_equal(fast[0], gen[0])
+    assert np.allclose(fast[1], gen[1], rtol=1e-12)
+    assert np.allclose(fast[2], gen[2], atol=1e-7)
+    assert rel(fast[3], gen[3]) < 1e-12

@@ -244,3 +244,25 @@ def test_fortran_wrapper_facade(ctx):
     assert np.array_equal(perm - 1, p["perm"])
     d, aligned = ap.alignGroup(np.array([p["pos1"], p["pos2"]]))
     assert aligned.shape == (256, 3, 2, 2) and abs(d[0, 1] - 1.5590835031549872) < DIST_ATOL
+
+
+@pytest.mark.parametrize("N,J", [(20, 7), (38, 15), (25, 9), (18, 21)])
+def test_fast_and_generic_isoft_agree(ctx, N, J):
+    """sph_isoft2_kernel (tensor-core, persistent) vs sph_isoft_kernel (any size)."""
+    rng = np.random.default_rng(N + J)
+    A = rng.normal(size=(4, N, 3))
+    B = rng.normal(size=(4, N, 3))
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    ctx.set_perm([np.arange(N)], N)
+    fast = ctx.sph_align_pairs(A, B, J, 0.5, invert=True, want_grid=True)
+    fast_ng = ctx.sph_align_pairs(A, B, J, 0.5, invert=True)
+    ctx.set_option("force_generic", 1)
+    try:
+        gen = ctx.sph_align_pairs(A, B, J, 0.5, invert=True, want_grid=True)
+    finally:
+        ctx.set_option("force_generic", 0)
+    assert np.array_equal(fast[0], gen[0]) and np.array_equal(fast[0], fast_ng[0])
+    assert np.allclose(fast[1], gen[1], rtol=1e-12) and np.array_equal(fast[1], fast_ng[1])
+    assert np.allclose(fast[2], gen[2], atol=1e-6)
+    assert rel(fast[3], gen[3]) < 1e-12
