@@ -1148,15 +1148,15 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ b
         double A[NT][2], B[NT][2];
         mm.run(ZR + FP - g, ZI + FP - g, FP, n, 0.0, lane, A, B);
         double g1[NT][2], g2[NT][2];
-        double cmax = -1.0;
+        double cmax = -2.0;  // below the bv sentinel (-1): NaN rows never enter the update
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int d = nt * 8 + t4 * 2 + q;
             const double a = fma(2.0, A[nt][q], v0), b = 2.0 * B[nt][q];
-            g1[nt][q] = (valid && d < H) ? fabs(a + b) : -1.0;
-            g2[nt][q] = (valid && d < H && d != 0 && 2 * d != F) ? fabs(a - b) : -1.0;
+            g1[nt][q] = (valid && d < H) ? fabs(a + b) : -2.0;
+            g2[nt][q] = (valid && d < H && d != 0 && 2 * d != F) ? fabs(a - b) : -2.0;
             cmax = fmax(cmax, fmax(g1[nt][q], g2[nt][q]));
             if (WANT_GRID) {
               if (valid && d < H) {
