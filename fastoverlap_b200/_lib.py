@@ -91,6 +91,12 @@ SIGNATURES = {
                                          ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
     "fo_sph_wigner_table": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p]),
+    "fo_host_refine_periodic": (ctypes.c_int, [ctypes.POINTER(PerParams), c_void_p, ctypes.c_int64, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int,
+                                               ctypes.c_int, c_void_p, c_void_p, c_void_p]),
+    "fo_host_refine_spherical": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                                ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
+                                                c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -139,6 +145,59 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def _group_arrays(perm, natoms):
+    groups = [np.asarray(g, dtype=np.int64).ravel() for g in (perm if perm is not None else [np.arange(natoms)])]
+    off = np.zeros(len(groups) + 1, np.int32)
+    off[1:] = np.cumsum([len(g) for g in groups])
+    idx = (np.concatenate(groups) if groups else np.zeros(0, np.int64)).astype(np.int32)
+    if idx.size == 0:
+        idx = np.zeros(1, np.int32)
+    return off, idx, len(groups)
+
+
+def host_refine_periodic(params, perm, posA, posB, frac_idx, niter=10, nthreads=0):
+    """Native host refinement of P periodic pairs (fo_host_refine_periodic; needs no GPU).
+    Returns (dist (P,), perm (P,N), disp (P,3))."""
+    lib = load_library()
+    N = params.natoms
+    posA = _f64(posA).reshape(-1, N, 3)
+    posB = _f64(posB).reshape(-1, N, 3)
+    frac = _f64(frac_idx).reshape(-1, 3)
+    P = posA.shape[0]
+    off, idx, ng = _group_arrays(perm, N)
+    dist = np.empty(P)
+    pm = np.empty((P, N), np.int32)
+    disp = np.empty((P, 3))
+    rc = lib.fo_host_refine_periodic(ctypes.byref(params), _ptr(off), ng, _ptr(idx), _ptr(posA), _ptr(posB),
+                                     _ptr(frac), P, int(niter), int(nthreads), _ptr(dist), _ptr(pm), _ptr(disp))
+    if rc != 0:
+        raise FastOverlapError("fo_host_refine_periodic failed (%d)" % rc)
+    return dist, pm, disp
+
+
+def host_refine_spherical(posA, posB, euler, perm=None, nthreads=0):
+    """Native host refinement of P centred cluster pairs (fo_host_refine_spherical; needs no GPU).
+    euler (P, O, 3).  Returns (dist (P,), orient (P,), perm (P,N), rmat (P,3,3))."""
+    lib = load_library()
+    posA = _f64(posA)
+    posB = _f64(posB)
+    if posA.ndim == 2:
+        posA, posB = posA[None], posB[None]
+    P, N, _ = posA.shape
+    euler = _f64(euler).reshape(P, -1, 3)
+    O = euler.shape[1]
+    off, idx, ng = _group_arrays(perm, N)
+    dist = np.empty(P)
+    orient = np.empty(P, np.int32)
+    pm = np.empty((P, N), np.int32)
+    rmat = np.empty((P, 3, 3))
+    rc = lib.fo_host_refine_spherical(_ptr(posA), _ptr(posB), P, N, _ptr(off), ng, _ptr(idx), _ptr(euler), O,
+                                      int(nthreads), _ptr(dist), _ptr(orient), _ptr(pm), _ptr(rmat))
+    if rc != 0:
+        raise FastOverlapError("fo_host_refine_spherical failed (%d)" % rc)
+    return dist, orient, pm, rmat
 
 
 class Context(object):

@@ -1,0 +1,359 @@
+// Host-side refinement that follows the GPU hot path (BASELINE.json north_star: "The Hungarian /
+// munkres permutation step and the Kabsch refinement stay on the host"), as native C++ on an OpenMP
+// thread pool over independent pairs:
+//   * linear assignment: dense shortest-augmenting-path Jonker-Volgenant (the role of JOVOSAP,
+//     reference fastoverlap/f90/alignutils.f90:989-1259, and of munkres / pele in utils.py:34-60);
+//     same algorithm and tie-breaking as scipy.optimize.linear_sum_assignment, which the Python
+//     classes of this package use, so both host paths return the same permutations;
+//   * periodic: permutation <-> mean-displacement iteration (periodicAlignment.py:27-80,
+//     FINDDISPLACEMENT alignutils.f90:381-419);
+//   * clusters: rotate by the Euler angles of the grid maximum (utils.py:447-460), permute, Kearsley
+//     quaternion fit (utils.py:169-253, FINDROTATION alignutils.f90:304-379), best orientation by
+//     distance (the Fortran rule, fastclusters.f90:243-254).
+// No CUDA in this file; it is compiled into the same shared library.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../../include/fastoverlap_b200.h"
+
+namespace {
+
+// Dense n x n linear assignment (minimise), cost row-major.  col4row[i] = column assigned to row i.
+struct Lap {
+  std::vector<double> u, v, shortest;
+  std::vector<int> path, row4col, remaining;
+  std::vector<char> SR, SC;
+  void solve(int n, const double* cost, int* col4row) {
+    u.assign(n, 0.0);
+    v.assign(n, 0.0);
+    shortest.resize(n);
+    path.resize(n);
+    row4col.assign(n, -1);
+    remaining.resize(n);
+    SR.resize(n);
+    SC.resize(n);
+    for (int i = 0; i < n; ++i) col4row[i] = -1;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int cur = 0; cur < n; ++cur) {
+      std::fill(SR.begin(), SR.end(), 0);
+      std::fill(SC.begin(), SC.end(), 0);
+      std::fill(shortest.begin(), shortest.end(), inf);
+      int nrem = n;
+      for (int it = 0; it < n; ++it) remaining[it] = n - it - 1;
+      int sink = -1, i = cur;
+      double minVal = 0.0;
+      while (sink == -1) {
+        int index = -1;
+        double lowest = inf;
+        SR[i] = 1;
+        const double* ci = cost + (size_t)i * n;
+        for (int it = 0; it < nrem; ++it) {
+          const int j = remaining[it];
+          const double r = minVal + ci[j] - u[i] - v[j];
+          if (r < shortest[j]) {
+            path[j] = i;
+            shortest[j] = r;
+          }
+          if (shortest[j] < lowest || (shortest[j] == lowest && row4col[j] == -1)) {
+            lowest = shortest[j];
+            index = it;
+          }
+        }
+        minVal = lowest;
+        if (index < 0 || minVal == inf) return;  // infeasible (NaN costs): leave -1s
+        const int j = remaining[index];
+        if (row4col[j] == -1)
+          sink = j;
+        else
+          i = row4col[j];
+        SC[j] = 1;
+        remaining[index] = remaining[--nrem];
+      }
+      u[cur] += minVal;
+      for (int r = 0; r < n; ++r)
+        if (SR[r] && r != cur) u[r] += minVal - shortest[col4row[r]];
+      for (int j = 0; j < n; ++j)
+        if (SC[j]) v[j] -= minVal - shortest[j];
+      int j = sink;
+      while (true) {
+        const int r = path[j];
+        row4col[j] = r;
+        std::swap(col4row[r], j);
+        if (r == cur) break;
+      }
+    }
+  }
+};
+
+inline double min_image(double d, double box) { return d - nearbyint(d / box) * box; }
+
+struct Groups {
+  const int32_t* goff;
+  int64_t ngroups;
+  const int32_t* gidx;
+};
+
+// permutation of Y that best matches X group by group; periodic (box != null: cost = min-image
+// distance, periodicAlignment.py:94-102) or free (squared distance, utils.py:48-56)
+void best_perm(const Groups& G, int natoms, const double* X, const double* Y, const double* box, Lap& lap,
+               std::vector<double>& cost, std::vector<int>& c4r, int* perm) {
+  for (int i = 0; i < natoms; ++i) perm[i] = i;
+  for (int64_t g = 0; g < G.ngroups; ++g) {
+    const int n = G.goff[g + 1] - G.goff[g];
+    if (n == 0) continue;
+    const int32_t* idx = G.gidx + G.goff[g];
+    cost.resize((size_t)n * n);
+    c4r.resize(n);
+    for (int i = 0; i < n; ++i) {
+      const double* xi = X + 3 * idx[i];
+      for (int j = 0; j < n; ++j) {
+        const double* yj = Y + 3 * idx[j];
+        double dx = xi[0] - yj[0], dy = xi[1] - yj[1], dz = xi[2] - yj[2];
+        if (box) {
+          dx = min_image(dx, box[0]);
+          dy = min_image(dy, box[1]);
+          dz = min_image(dz, box[2]);
+          cost[(size_t)i * n + j] = sqrt(dx * dx + dy * dy + dz * dz);
+        } else {
+          cost[(size_t)i * n + j] = dx * dx + dy * dy + dz * dz;
+        }
+      }
+    }
+    lap.solve(n, cost.data(), c4r.data());
+    for (int i = 0; i < n; ++i) perm[idx[i]] = c4r[i] >= 0 ? idx[c4r[i]] : idx[i];
+  }
+}
+
+// smallest eigenpair of a symmetric 4x4 matrix by cyclic Jacobi
+void jacobi4(double A[4][4], double& eigmin, double q[4]) {
+  double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < 4; ++p)
+      for (int r = p + 1; r < 4; ++r) off += A[p][r] * A[p][r];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 4; ++p)
+      for (int r = p + 1; r < 4; ++r) {
+        if (fabs(A[p][r]) < 1e-300) continue;
+        const double theta = (A[r][r] - A[p][p]) / (2 * A[p][r]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+        const double c = 1 / sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < 4; ++k) {
+          const double akp = A[k][p], akr = A[k][r];
+          A[k][p] = c * akp - s * akr;
+          A[k][r] = s * akp + c * akr;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double apk = A[p][k], ark = A[r][k];
+          A[p][k] = c * apk - s * ark;
+          A[r][k] = s * apk + c * ark;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = V[k][p], vkr = V[k][r];
+          V[k][p] = c * vkp - s * vkr;
+          V[k][r] = s * vkp + c * vkr;
+        }
+      }
+  }
+  int im = 0;
+  for (int k = 1; k < 4; ++k)
+    if (A[k][k] < A[im][im]) im = k;
+  eigmin = A[im][im];
+  for (int k = 0; k < 4; ++k) q[k] = V[k][im];
+}
+
+// Kearsley: distance after the optimal rotation of x2 onto x1 (both re-centred) and the matrix
+double kearsley(int n, const double* x1, const double* x2, const int* perm, double R[9]) {
+  double c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      c1[k] += x1[3 * i + k];
+      c2[k] += x2[3 * perm[i] + k];
+    }
+  for (int k = 0; k < 3; ++k) {
+    c1[k] /= n;
+    c2[k] /= n;
+  }
+  double Q[4][4] = {};
+  for (int i = 0; i < n; ++i) {
+    const double a[3] = {x1[3 * i] - c1[0], x1[3 * i + 1] - c1[1], x1[3 * i + 2] - c1[2]};
+    const double b[3] = {x2[3 * perm[i]] - c2[0], x2[3 * perm[i] + 1] - c2[1], x2[3 * perm[i] + 2] - c2[2]};
+    const double xm = a[0] - b[0], ym = a[1] - b[1], zm = a[2] - b[2];
+    const double xp = a[0] + b[0], yp = a[1] + b[1], zp = a[2] + b[2];
+    Q[0][0] += xm * xm + ym * ym + zm * zm;
+    Q[0][1] += ym * zp - yp * zm;
+    Q[0][2] += xp * zm - xm * zp;
+    Q[0][3] += xm * yp - xp * ym;
+    Q[1][1] += yp * yp + zp * zp + xm * xm;
+    Q[1][2] += xm * ym - xp * yp;
+    Q[1][3] += xm * zm - xp * zp;
+    Q[2][2] += xp * xp + zp * zp + ym * ym;
+    Q[2][3] += ym * zm - yp * zp;
+    Q[3][3] += xp * xp + yp * yp + zm * zm;
+  }
+  for (int p = 0; p < 4; ++p)
+    for (int r = 0; r < p; ++r) Q[p][r] = Q[r][p];
+  double eig, q[4];
+  jacobi4(Q, eig, q);
+  if (eig < 0) eig = fabs(eig) < 1e-6 ? 0.0 : -eig;
+  if (R) {
+    const double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double q0 = q[0] / nq, q1 = q[1] / nq, q2 = q[2] / nq, q3 = q[3] / nq;
+    R[0] = 2 * (0.5 - q2 * q2 - q3 * q3); R[1] = 2 * (q1 * q2 - q0 * q3); R[2] = 2 * (q1 * q3 + q0 * q2);
+    R[3] = 2 * (q1 * q2 + q0 * q3); R[4] = 2 * (0.5 - q1 * q1 - q3 * q3); R[5] = 2 * (q2 * q3 - q0 * q1);
+    R[6] = 2 * (q1 * q3 - q0 * q2); R[7] = 2 * (q2 * q3 + q0 * q1); R[8] = 2 * (0.5 - q1 * q1 - q2 * q2);
+  }
+  return sqrt(eig);
+}
+
+// EulerM(a, b, y) = My Mb Ma (utils.py:447-460)
+void euler_m(double a, double b, double y, double M[9]) {
+  const double sa = sin(a), ca = cos(a), sb = sin(b), cb = cos(b), sy = sin(y), cy = cos(y);
+  const double Ma[9] = {ca, -sa, 0, sa, ca, 0, 0, 0, 1};
+  const double Mb[9] = {cb, 0, -sb, 0, 1, 0, sb, 0, cb};
+  const double My[9] = {cy, -sy, 0, sy, cy, 0, 0, 0, 1};
+  double T[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += My[3 * i + k] * Mb[3 * k + j];
+      T[3 * i + j] = s;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += T[3 * i + k] * Ma[3 * k + j];
+      M[3 * i + j] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
+                                       const int32_t* atom_idx, const double* posA, const double* posB,
+                                       const double* frac_idx, int64_t npairs, int niter, int nthreads,
+                                       double* dist, int32_t* perm_out, double* disp_out) {
+  if (!p || !group_offsets || !atom_idx || !posA || !posB || !frac_idx || !dist || npairs < 0 || ngroups < 1)
+    return FO_ERR_INVALID;
+  const int N = (int)p->natoms;
+  const Groups G = {group_offsets, ngroups, atom_idx};
+#ifdef _OPENMP
+  const int nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+  const int nt = 1;
+  (void)nthreads;
+#endif
+#pragma omp parallel num_threads(nt)
+  {
+    Lap lap;
+    std::vector<double> cost, ys((size_t)3 * N);
+    std::vector<int> c4r, perm(N), save(N);
+#pragma omp for schedule(dynamic, 4)
+    for (int64_t q = 0; q < npairs; ++q) {
+      const double* x = posA + (size_t)q * N * 3;
+      const double* y = posB + (size_t)q * N * 3;
+      double disp[3];
+      for (int k = 0; k < 3; ++k) disp[k] = frac_idx[3 * q + k] * p->box[k] / (double)p->nfspace;
+      auto shift = [&]() {
+        for (int i = 0; i < N; ++i)
+          for (int k = 0; k < 3; ++k) ys[3 * i + k] = y[3 * i + k] - disp[k];
+      };
+      auto recentre = [&](const int* pm) {
+        double m[3] = {0, 0, 0};
+        for (int i = 0; i < N; ++i)
+          for (int k = 0; k < 3; ++k) m[k] += min_image(x[3 * i + k] - (y[3 * pm[i] + k] - disp[k]), p->box[k]);
+        for (int k = 0; k < 3; ++k) disp[k] -= m[k] / N;
+      };
+      shift();
+      best_perm(G, N, x, ys.data(), p->box, lap, cost, c4r, save.data());
+      perm = save;
+      for (int it = 0; it < niter; ++it) {
+        recentre(save.data());
+        shift();
+        best_perm(G, N, x, ys.data(), p->box, lap, cost, c4r, perm.data());
+        if (perm == save) break;
+        save = perm;
+      }
+      recentre(perm.data());
+      double d2 = 0;
+      for (int i = 0; i < N; ++i)
+        for (int k = 0; k < 3; ++k) {
+          // periodic(x) - periodic(y[perm] - disp), then the minimum image of the difference
+          const double a = min_image(x[3 * i + k], p->box[k]);
+          const double b = min_image(y[3 * perm[i] + k] - disp[k], p->box[k]);
+          const double d = min_image(a - b, p->box[k]);
+          d2 += d * d;
+        }
+      dist[q] = sqrt(d2);
+      if (perm_out)
+        for (int i = 0; i < N; ++i) perm_out[(size_t)q * N + i] = perm[i];
+      if (disp_out)
+        for (int k = 0; k < 3; ++k) disp_out[3 * q + k] = disp[k];
+    }
+  }
+  return FO_OK;
+}
+
+extern "C" int fo_host_refine_spherical(const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                                        const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                                        const double* euler, int norient, int nthreads, double* dist,
+                                        int32_t* orient_out, int32_t* perm_out, double* rmat_out) {
+  if (!posA || !posB || !group_offsets || !atom_idx || !euler || !dist || npairs < 0 || natoms < 1 ||
+      norient < 1 || norient > 2)
+    return FO_ERR_INVALID;
+  const int N = (int)natoms;
+  const Groups G = {group_offsets, ngroups, atom_idx};
+#ifdef _OPENMP
+  const int nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+  const int nt = 1;
+  (void)nthreads;
+#endif
+#pragma omp parallel num_threads(nt)
+  {
+    Lap lap;
+    std::vector<double> cost, xr((size_t)3 * N);
+    std::vector<int> c4r, perm(N), bestperm(N);
+#pragma omp for schedule(dynamic, 8)
+    for (int64_t q = 0; q < npairs; ++q) {
+      const double* x1 = posA + (size_t)q * N * 3;
+      const double* x2 = posB + (size_t)q * N * 3;
+      double best = std::numeric_limits<double>::infinity(), bestR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      int besto = 0;
+      for (int o = 0; o < norient; ++o) {
+        const double* e = euler + ((size_t)q * norient + o) * 3;
+        double M[9], R[9];
+        euler_m(e[0], e[1], e[2], M);
+        const double sg = o ? -1.0 : 1.0;  // orientation 1: inverted structure -X2
+        for (int i = 0; i < N; ++i)
+          for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += sg * x2[3 * i + k] * M[3 * k + j];  // (X2 . M)
+            xr[3 * i + j] = s;
+          }
+        best_perm(G, N, x1, xr.data(), nullptr, lap, cost, c4r, perm.data());
+        const double d = kearsley(N, x1, xr.data(), perm.data(), R);
+        if (d < best) {
+          best = d;
+          besto = o;
+          bestperm = perm;
+          memcpy(bestR, R, sizeof(R));
+        }
+      }
+      dist[q] = best;
+      if (orient_out) orient_out[q] = besto;
+      if (perm_out)
+        for (int i = 0; i < N; ++i) perm_out[(size_t)q * N + i] = bestperm[i];
+      if (rmat_out) memcpy(rmat_out + 9 * q, bestR, sizeof(bestR));
+    }
+  }
+  return FO_OK;
+}

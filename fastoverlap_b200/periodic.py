@@ -178,21 +178,17 @@ class PeriodicAlign(BasePeriodicAlignment):
         bi, bv, fr, _, st = self.ctx.per_align_pairs(self._params(), pos1, pos2)
         return fr * self.boxvec / np.array(self.fshape, float), bi, bv
 
-    def align_batch(self, pos1, pos2, refine=True):
-        """Align P independent pairs.  GPU hot path for the whole batch, host refine per pair.
-        Returns (dists (P,), disps (P,3)[, perms (P,Natoms)])."""
+    def align_batch(self, pos1, pos2, refine=True, nthreads=0):
+        """Align P independent pairs: GPU hot path for the whole batch, then the native host
+        refinement pool (fo_host_refine_periodic).  Returns (dists (P,), disps (P,3), perms (P,Natoms))."""
         pos1 = np.asarray(pos1, float).reshape(-1, self.Natoms, 3)
         pos2 = np.asarray(pos2, float).reshape(-1, self.Natoms, 3)
-        disps, _, _ = self.findDisps_batch(pos1, pos2)
+        p = self._params()
+        bi, bv, fr, _, st = self.ctx.per_align_pairs(p, pos1, pos2)
         if not refine:
-            return None, disps
-        dists = np.empty(len(pos1))
-        perms = np.empty((len(pos1), self.Natoms), int)
-        out_disp = np.empty_like(disps)
-        for i in range(len(pos1)):
-            d, _, _, perm, disp = self.refine(pos1[i], pos2[i], disps[i:i + 1])
-            dists[i], perms[i], out_disp[i] = d, perm, disp
-        return dists, out_disp, perms
+            return None, fr * self.boxvec / np.array(self.fshape, float)
+        dists, perms, disps = _lib.host_refine_periodic(p, self.perm, pos1, pos2, fr, 10, nthreads)
+        return dists, disps, perms
 
     def alignGroup(self, coords, keepCoords=False, npeaks=1, width=2):
         """All-vs-all alignment of a list of structures (reference :462-479): structure factors

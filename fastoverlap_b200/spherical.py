@@ -202,8 +202,9 @@ class BaseSphericalAlignment(object):
         return dist, X1, X2
 
     # -- batched, additive API
-    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True):
-        """P independent pairs: one GPU call for the whole batch, host refine per pair.
+    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True, nthreads=0):
+        """P independent pairs: one GPU call for the whole batch, then the native host refinement
+        pool (fo_host_refine_spherical: rotate, LAP, Kearsley, best orientation by distance).
         Returns dists (P,) and the Euler angles (P, O, 3)."""
         pos1 = np.asarray(pos1, float)
         pos2 = np.asarray(pos2, float)
@@ -214,12 +215,7 @@ class BaseSphericalAlignment(object):
         Rs = Rs.reshape(len(X1), -1, 3)
         if not refine:
             return None, Rs
-        dists = np.empty(len(X1))
-        for i in range(len(X1)):
-            d = self.refine(X1[i], X2[i], Rs[i, 0], perm)[0]
-            if invert:
-                d = min(d, self.refine(X1[i], -X2[i], Rs[i, 1], perm)[0])
-            dists[i] = d
+        dists, orient, perms, rmats = _lib.host_refine_spherical(X1, X2, Rs, perm, nthreads)
         return dists, Rs
 
 

@@ -239,6 +239,30 @@ int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs /*[
  * (soft.py:73-96, CALCWIGNERD DSOFT.f90:121-195).  Computed on the device. */
 int fo_sph_wigner_table(fo_ctx* ctx, int64_t Jmax, double* out);
 
+/* ---------------------------------------------------------------- host refinement (no GPU)
+ * The steps the north star keeps on the host, as native code on an OpenMP pool over pairs
+ * (nthreads <= 0: all cores).  They take the hot-path outputs (frac_idx / Euler angles) directly. */
+
+/* Periodic: permutation (Jonker-Volgenant LAP on the minimum-image distance matrix, per group) <->
+ * mean-displacement iteration, at most niter rounds.  Replaces BasePeriodicAlignment.refine
+ * (periodicAlignment.py:27-80) / ITERATIVEALIGN(bulk) (alignutils.f90:111-286).
+ * frac_idx [P,3] from fo_per_align_pairs; dist [P]; perm [P,N] (nullable): X2 = posB[perm] - disp;
+ * disp [P,3] (nullable). */
+int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
+                            const int32_t* atom_idx, const double* posA, const double* posB,
+                            const double* frac_idx, int64_t npairs, int niter, int nthreads, double* dist,
+                            int32_t* perm, double* disp);
+
+/* Clusters: for each orientation o < norient rotate (o = 1: -posB) by the Euler angles
+ * euler[P,norient,3], permute (LAP on squared distances per group), Kearsley quaternion fit; keep
+ * the orientation with the smaller distance.  Replaces BaseSphericalAlignment.refine
+ * (sphericalAlignment.py:118-127) with the Fortran orientation rule (fastclusters.f90:243-254).
+ * posA / posB centred; dist [P]; orient [P], perm [P,N], rmat [P,9] nullable. */
+int fo_host_refine_spherical(const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                             const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                             const double* euler, int norient, int nthreads, double* dist, int32_t* orient,
+                             int32_t* perm, double* rmat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,3 +131,63 @@ def test_findpeaks_recovers_planted_gaussians():
     peaks, amp, _, _, _ = findPeaks(f, npeaks=2, width=2)
     assert np.allclose(peaks[0], (5.3, 10.1, 17.6), atol=0.05)
     assert np.allclose(peaks[1], (15.2, 4.4, 8.9), atol=0.05)
+
+
+def test_native_periodic_refine_matches_reference_and_python():
+    """fo_host_refine_periodic (C++ JV LAP + mean-displacement loop) on the reference's BLJ256 pair:
+    the documented 1.559, the reference's permutation and displacement, and agreement with the
+    Python refine on random pairs."""
+    from fastoverlap_b200 import _lib
+    from fastoverlap_b200.periodic import PeriodicAlign
+    g = golden("periodic_blj256.npz")
+    perm = [np.arange(204), np.arange(204, 256)]
+    p = _lib.Context.per_params(256, g["box"], int(g["n"]), int(g["F"]), float(g["scale"]))
+    dist, pm, disp = _lib.host_refine_periodic(p, perm, g["pos1"][None], g["pos2"][None], g["findmax"][None])
+    assert abs(dist[0] - 1.5590835031549872) < 1e-9
+    assert np.array_equal(pm[0], g["perm"])
+    assert np.allclose(disp[0], g["disp"], atol=1e-9)
+    rng = np.random.default_rng(4)
+    N, box = 30, np.array([4.0, 4.5, 5.0])
+    al = PeriodicAlign.__new__(PeriodicAlign)
+    al.Natoms, al.boxvec, al.dim = N, box, 3
+    al.perm = [np.arange(18), np.arange(18, 30)]
+    A = rng.uniform(-0.5, 0.5, size=(6, N, 3)) * box
+    shift = rng.uniform(0, 1, size=(6, 1, 3)) * box
+    B = A + shift + rng.normal(scale=0.05, size=A.shape)
+    for i in range(6):
+        B[i] = B[i][np.concatenate([rng.permutation(18), 18 + rng.permutation(12)])]
+    F = 24
+    frac = (shift[:, 0, :] + rng.normal(scale=0.02, size=(6, 3))) / box * F
+    pp = _lib.Context.per_params(N, box, 5, F, 0.3)
+    dist, pm, disp = _lib.host_refine_periodic(pp, al.perm, A, B, frac, nthreads=2)
+    for i in range(6):
+        d, _, _, pyperm, pydisp = al.refine(A[i].copy(), B[i].copy(), (frac[i] * box / F)[None])
+        assert abs(d - dist[i]) < 1e-9 and np.array_equal(pyperm, pm[i]) and np.allclose(pydisp, disp[i], atol=1e-9)
+
+
+def test_native_spherical_refine_matches_reference_and_python():
+    from fastoverlap_b200 import _lib
+    from fastoverlap_b200.spherical import SphericalAlign
+    from fastoverlap_b200.utils import indtoEuler
+    g = golden("spherical_lj38.npz")
+    X1 = g["pos1"] - g["pos1"].mean(0)
+    X2 = g["pos2"] - g["pos2"].mean(0)
+    eul = np.stack([indtoEuler(g["J15_findmax"].real, 32), indtoEuler(g["J15_findmax_inv"].real, 32)])[None]
+    dist, orient, pm, rmat = _lib.host_refine_spherical(X1, X2, eul)
+    assert abs(dist[0] - 1.4767670631638872) < 1e-9 and orient[0] == 1
+    d0 = _lib.host_refine_spherical(X1, X2, eul[:, :1])[0]
+    assert abs(d0[0] - float(g["J15_dist_normal_only"])) < 1e-9
+    assert abs(abs(np.linalg.det(rmat[0])) - 1) < 1e-9
+    sa = SphericalAlign.__new__(SphericalAlign)
+    sa.perm, sa.scale, sa.Jmax = None, 0.5, 9
+    rng = np.random.default_rng(9)
+    A = rng.normal(size=(5, 21, 3))
+    B = rng.normal(size=(5, 21, 3))
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    E = rng.uniform(0, 3, size=(5, 2, 3))
+    groups = [np.arange(9), np.arange(9, 21)]
+    dist, orient, pm, rmat = _lib.host_refine_spherical(A, B, E, groups, nthreads=2)
+    for i in range(5):
+        d = min(sa.refine(A[i], B[i], E[i, 0], groups)[0], sa.refine(A[i], -B[i], E[i, 1], groups)[0])
+        assert abs(d - dist[i]) < 1e-9
