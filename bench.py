@@ -437,9 +437,20 @@ def run_ours(args, wl):
                 "kernel_shares": {k: v[0] / total_prof for k, v in prof.items()},
                 "traffic": None,
                 "hbm_frac_of_measured": None}
+        try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f)[wl.dominant]
+            roof["traffic"] = tr["bytes_per_launch"]
+            roof["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read+write, %d %ss per launch)" % (
+                tr["units_per_launch"], tr["unit"])
+        except Exception:
+            pass
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 roof["hbm_peak_gbs"] = json.load(f).get("hbm_gbs")
+            if roof.get("traffic") and roof.get("hbm_peak_gbs"):
+                roof["hbm_frac_of_measured"] = (roof["traffic"] / (roof["kernel_ms_per_launch"] * 1e-3) / 1e9 /
+                                                roof["hbm_peak_gbs"])
         except Exception:
             pass
     base = None
