@@ -19,6 +19,7 @@ struct fo_wigner_cache {
   double* d_table = nullptr;   // dense Dt[m2][m1][l][k], see fo_spherical.cu
   double* d_packed = nullptr;  // per-chunk shell-ordered slices for sph_isoft2_kernel
   size_t bytes = 0;
+  bool kmajor = false;         // large bandwidths: plane-major layout DtK[k][m2][m1][l]
 };
 
 struct fo_prof_rec {
@@ -52,6 +53,8 @@ struct fo_ctx {
 
   // testing hook: force the generic (any-size) kernels instead of the shared-memory fast paths
   bool force_generic = false;
+  // clusters with at least this many atoms use the tensor-core GEMM form of the direct coefficients
+  int64_t direct_gemm_min = 96;
 
   // per-kernel event timing (fo_profile_begin/end)
   bool profiling = false;

@@ -249,7 +249,162 @@ sph_direct_kernel(const double2* __restrict__ YA, const double2* __restrict__ YB
   }
 }
 
-// zero the (m2, m1, l < max(|m1|, m2)) entries are never read; no need to clear Ihalf.
+// ------------------------------------------------------------------------------------------
+// K2a for large clusters (natoms >= ctx->direct_gemm_min): the two contractions of
+// sph_direct_kernel as FP64 tensor-core GEMMs (DMMA.8x8x4), batched over (pair, l).  Complex
+// quantities are handled as interleaved real rows / columns r = 2 m + (re | im), m = 0..l:
+//   MODE 1   T[r][k]   = sum_j  YA[j][r] B_l[j][k]              (2(l+1) x N x N)
+//   MODE 2   C2[r][r'] = sum_k  T[r][k]  YB[k][r']              (2(l+1) x 2(l+1) x N)
+// and sph_direct_combine_kernel forms I[l,+-m1,m2] from the four real products in C2.
+// CTA tile 64 x 64 x 16, 8 warps as 2 (rows) x 4 (cols), warp tile 32 x 16; k-major shared tiles with
+// pitch 72 (== 8 mod 32: the four k rows of a fragment fall into disjoint bank groups); global loads
+// of the next k tile are in flight while the current one is multiplied.
+// ------------------------------------------------------------------------------------------
+constexpr int DG_TM = 64, DG_TN = 64, DG_TK = 16, DG_LD = 72, DG_THREADS = 256;
+
+__host__ __device__ inline size_t dg_c2_off(int l) { return (size_t)2 * l * (l + 1) * (2 * l + 1) / 3; }
+
+template <int MODE>
+__global__ void __launch_bounds__(DG_THREADS, 2)
+sph_direct_gemm_kernel(const double* __restrict__ Yreal, const double* __restrict__ X, int natoms, int L,
+                       double* __restrict__ Cout) {
+  __shared__ double As[2][DG_TK * DG_LD];
+  __shared__ double Bs[2][DG_TK * DG_LD];
+  const int L1 = L + 1, NLM = nlm_of(L);
+  const int l = blockIdx.z % L1;
+  const size_t p = blockIdx.z / L1;
+  const int M = 2 * (l + 1);
+  const int N = MODE == 1 ? natoms : M;
+  const int K = natoms;
+  const int row0 = blockIdx.y * DG_TM, col0 = blockIdx.x * DG_TN;
+  if (row0 >= M || col0 >= N) return;
+  const int lbase = l * (l + 1) / 2;
+  const double* Ay;  // element (r, kk)
+  const double* Bx;  // element (kk, n)
+  double* C;
+  size_t rsA, csA, rsB, ldc;
+  if (MODE == 1) {
+    Ay = Yreal + (p * (size_t)natoms * NLM + lbase) * 2;
+    rsA = 1;
+    csA = (size_t)2 * NLM;
+    Bx = X + (p * L1 + l) * (size_t)natoms * natoms;
+    rsB = natoms;
+    C = Cout + (p * (size_t)2 * NLM + 2 * lbase) * natoms;
+    ldc = natoms;
+  } else {
+    Ay = X + (p * (size_t)2 * NLM + 2 * lbase) * natoms;
+    rsA = natoms;
+    csA = 1;
+    Bx = Yreal + (p * (size_t)natoms * NLM + lbase) * 2;
+    rsB = (size_t)2 * NLM;
+    C = Cout + p * dg_c2_off(L1) + dg_c2_off(l);
+    ldc = M;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  // loader coordinates
+  const int a_kk = MODE == 1 ? (tid >> 4) : (tid >> 6) * 4;  // MODE 1: one k, 4 rows; MODE 2: one row, 4 k
+  const int a_r = MODE == 1 ? (tid & 15) * 4 : (tid & 63);
+  const int b_kk = tid >> 4, b_n = (tid & 15) * 4;
+  double ra[4], rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + a_r + (MODE == 1 ? i : 0);
+      const int kk = k0 + a_kk + (MODE == 1 ? 0 : i);
+      ra[i] = (r < M && kk < K) ? Ay[(size_t)r * rsA + (size_t)kk * csA] : 0.0;
+      const int n = col0 + b_n + i, kb = k0 + b_kk;
+      rb[i] = (n < N && kb < K) ? Bx[(size_t)kb * rsB + n] : 0.0;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (MODE == 1)
+        As[buf][a_kk * DG_LD + a_r + i] = ra[i];
+      else
+        As[buf][(a_kk + i) * DG_LD + a_r] = ra[i];
+      Bs[buf][b_kk * DG_LD + b_n + i] = rb[i];
+    }
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  bool live[4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) live[mt] = row0 + wm * 32 + mt * 8 < M;
+  const int nkt = (K + DG_TK - 1) / DG_TK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) gload((kt + 1) * DG_TK);
+    const double* as = As[buf] + wm * 32 + g;
+    const double* bs = Bs[buf] + wn * 16 + g;
+#pragma unroll
+    for (int k4 = 0; k4 < DG_TK / 4; ++k4) {
+      const int krow = (k4 * 4 + t4) * DG_LD;
+      const double b0 = bs[krow], b1 = bs[krow + 8];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (live[mt]) {
+          const double a = as[krow + mt * 8];
+          fo_dmma(acc[mt][0], a, b0);
+          fo_dmma(acc[mt][1], a, b1);
+        }
+      }
+    }
+    if (kt + 1 < nkt) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int r = row0 + wm * 32 + mt * 8 + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int n = col0 + wn * 16 + nt * 8 + t4 * 2;
+      if (n < N) C[(size_t)r * ldc + n] = acc[mt][nt][0];
+      if (n + 1 < N) C[(size_t)r * ldc + n + 1] = acc[mt][nt][1];
+    }
+  }
+}
+
+// I[l,m1,m2] (m2 >= 0, all m1) in the Ihalf layout from C2[l][2 m1 + part][2 m2 + part'].
+__global__ void sph_direct_combine_kernel(const double* __restrict__ C2, int L, size_t npairs,
+                                          double2* __restrict__ Ihalf) {
+  const int W = 2 * L + 1, L1 = L + 1;
+  const size_t per = (size_t)L1 * W * L1;
+  const size_t c2per = dg_c2_off(L1);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < npairs * per;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = t / per;
+    int r = (int)(t - p * per);
+    const int l = r % L1;
+    r /= L1;
+    const int m1 = r % W - L, m2 = r / W;
+    const int am = m1 < 0 ? -m1 : m1;
+    if (l < am || l < m2) continue;
+    const int n2 = 2 * (l + 1);
+    const double* c = C2 + p * c2per + dg_c2_off(l);
+    const double rr = c[(size_t)(2 * am) * n2 + 2 * m2], ri = c[(size_t)(2 * am) * n2 + 2 * m2 + 1];
+    const double ir = c[(size_t)(2 * am + 1) * n2 + 2 * m2], ii = c[(size_t)(2 * am + 1) * n2 + 2 * m2 + 1];
+    double2 v;
+    if (m1 >= 0) {
+      v = make_double2(rr + ii, ir - ri);
+    } else {
+      const double sg = (am & 1) ? -1.0 : 1.0;
+      v = make_double2(sg * (rr - ii), sg * (-ir - ri));
+    }
+    Ihalf[t] = v;
+  }
+}
+
+// The (m2, m1, l < max(|m1|, m2)) entries are never read; no need to clear Ihalf.
 
 // Full numpy layout [l][m1 wrap][m2 wrap] -> Ihalf, keeping the part that generates the REAL grid:
 // Ihalf = (I[l,m1,m2] + (-1)^{m1+m2} conj(I[l,-m1,-m2]))/2 (identity for coefficients of real
@@ -501,7 +656,24 @@ __device__ double wigner_edge(int J, int m1, int m2, double cb2, double sb2) {
   return v;
 }
 
-__global__ void sph_wigner_kernel(int L, double* __restrict__ Dt) {
+// Element (item = m2 W + m1 + L, l, k) of the table lives at item sI + l sL + k sK: the standard layout
+// Dt[m2][m1][l][k] has (sI, sL, sK) = (L1 F, F, 1); large bandwidths use the plane-major layout
+// DtK[k][m2][m1][l] = (L1, 1, L1 W L1), whose beta planes are contiguous (sph_isoft_big_kernel).
+struct DtStride {
+  long long sI, sL, sK;
+};
+__host__ __device__ inline DtStride dt_stride(int L, bool kmajor) {
+  const long long L1 = L + 1, W = 2 * L + 1, F = 2 * L + 2;
+  DtStride s;
+  if (kmajor) {
+    s.sI = L1; s.sL = 1; s.sK = L1 * W * L1;
+  } else {
+    s.sI = L1 * F; s.sL = F; s.sK = 1;
+  }
+  return s;
+}
+
+__global__ void sph_wigner_kernel(int L, DtStride ds, double* __restrict__ Dt) {
   const int B = L + 1, W = 2 * L + 1, L1 = L + 1, NK = 2 * B;
   const int total = L1 * W * NK;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -514,10 +686,10 @@ __global__ void sph_wigner_kernel(int L, double* __restrict__ Dt) {
     double sb2, cb2;
     sincos(0.5 * beta, &sb2, &cb2);
     const double cb = cos(beta);
-    double* col = Dt + ((size_t)m2 * W + (m1 + L)) * L1 * NK + k;
-    for (int l = 0; l < J0; ++l) col[(size_t)l * NK] = 0.0;
+    double* col = Dt + ((size_t)m2 * W + (m1 + L)) * ds.sI + (size_t)k * ds.sK;
+    for (int l = 0; l < J0; ++l) col[(size_t)l * ds.sL] = 0.0;
     double dm1 = 0.0, d = wigner_edge(J0, m1, m2, cb2, sb2);
-    col[(size_t)J0 * NK] = d;
+    col[(size_t)J0 * ds.sL] = d;
     for (int J = J0; J < L; ++J) {
       const double dj = J, a1 = m1, a2 = m2;
       const double t1 = sqrt((2.0 * dj + 3.0) / (2.0 * dj + 1.0));
@@ -534,19 +706,20 @@ __global__ void sph_wigner_kernel(int L, double* __restrict__ Dt) {
       const double dn = Bc * (cb - C) * d - A * dm1;
       dm1 = d;
       d = dn;
-      col[(size_t)(J + 1) * NK] = d;
+      col[(size_t)(J + 1) * ds.sL] = d;
     }
   }
 }
 
 // Dt -> the reference's Ds[l][m1 wrap][m2 wrap][k] (soft.py:73-96) using
 // d^l_{m1,-m2} = (-1)^{l+m1} d^l_{m1,m2}(pi - beta)  and beta_{2B-1-k} = pi - beta_k.
-__global__ void sph_wigner_export_kernel(const double* __restrict__ Dt, int L, double* __restrict__ Ds) {
-  const int B = L + 1, W = 2 * L + 1, L1 = L + 1, NK = 2 * B;
-  const int total = B * W * W * NK;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const int k = t % NK;
-    int r = t / NK;
+__global__ void sph_wigner_export_kernel(const double* __restrict__ Dt, DtStride ds, int L,
+                                         double* __restrict__ Ds) {
+  const int B = L + 1, W = 2 * L + 1, NK = 2 * B;
+  const size_t total = (size_t)B * W * W * NK;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t % NK);
+    int r = (int)(t / NK);
     const int i2 = r % W;
     r /= W;
     const int i1 = r % W, l = r / W;
@@ -555,9 +728,9 @@ __global__ void sph_wigner_export_kernel(const double* __restrict__ Dt, int L, d
     double v = 0.0;
     if (l >= am1 && l >= am2) {
       if (m2 >= 0) {
-        v = Dt[(((size_t)m2 * W + (m1 + L)) * L1 + l) * NK + k];
+        v = Dt[((size_t)m2 * W + (m1 + L)) * ds.sI + (size_t)l * ds.sL + (size_t)k * ds.sK];
       } else {
-        v = Dt[(((size_t)(-m2) * W + (m1 + L)) * L1 + l) * NK + (NK - 1 - k)];
+        v = Dt[((size_t)(-m2) * W + (m1 + L)) * ds.sI + (size_t)l * ds.sL + (size_t)(NK - 1 - k) * ds.sK];
         if ((l + m1) & 1) v = -v;
       }
     }
@@ -783,8 +956,8 @@ sph_isoft_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
 }
 
 // Grid value at integer point (a, k, g) by the direct Wigner sum (orientation sign so on odd l).
-__device__ double iso_point(const double2* __restrict__ Ip, const double* __restrict__ Dt, int L, int a,
-                            int k, int g, double so, int lane) {
+__device__ double iso_point(const double2* __restrict__ Ip, const double* __restrict__ Dt, DtStride ds,
+                            int L, int a, int k, int g, double so, int lane) {
   const int W = 2 * L + 1, L1 = L + 1, F = 2 * L1;
   double acc = 0.0;
   for (int item = lane; item < L1 * W; item += 32) {
@@ -794,9 +967,9 @@ __device__ double iso_point(const double2* __restrict__ Ip, const double* __rest
     const int l0 = am1 > m2 ? am1 : m2;
     double sr = 0.0, si = 0.0;
     const double2* ip = Ip + (size_t)item * L1;
-    const double* dp = Dt + (size_t)item * L1 * F + k;
+    const double* dp = Dt + (size_t)item * ds.sI + (size_t)k * ds.sK;
     for (int l = l0; l <= L; ++l) {
-      const double dv = ((l & 1) ? so : 1.0) * dp[(size_t)l * F];
+      const double dv = ((l & 1) ? so : 1.0) * dp[(size_t)l * ds.sL];
       const double2 c = ip[l];
       sr = fma(dv, c.x, sr);
       si = fma(dv, c.y, si);
@@ -815,8 +988,8 @@ __device__ double iso_point(const double2* __restrict__ Ip, const double* __rest
 
 // One CTA (8 warps) per (pair, orientation): reduce the chunk maxima, then the 6 neighbours.
 __global__ void __launch_bounds__(256)
-sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, int L, int norient,
-                 int nchunk, const double* __restrict__ part_val, const long long* __restrict__ part_idx,
+sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, DtStride ds, int L,
+                 int norient, int nchunk, const double* __restrict__ part_val, const long long* __restrict__ part_idx,
                  long long* __restrict__ best_idx, double* __restrict__ best_val,
                  double* __restrict__ frac_idx) {
   __shared__ double nb[6];
@@ -835,8 +1008,8 @@ sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
     const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
     int q[3] = {b3[0], b3[1], b3[2]};
     q[ax] = (q[ax] + sgn + F) % F;
-    const double v = iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, L, q[0], q[1], q[2],
-                               o ? -1.0 : 1.0, lane);
+    const double v = iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, ds, L, q[0], q[1],
+                               q[2], o ? -1.0 : 1.0, lane);
     if (lane == 0) nb[w] = fabs(v);
   }
   __syncthreads();
@@ -1274,8 +1447,8 @@ sph_final2_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ 
       const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
       int q[3] = {b3[0], b3[1], b3[2]};
       q[ax] = (q[ax] + sgn + F) % F;
-      v = fabs(iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, L, q[0], q[1], q[2],
-                         o ? -1.0 : 1.0, lane));
+      v = fabs(iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, dt_stride(L, false), L, q[0],
+                         q[1], q[2], o ? -1.0 : 1.0, lane));
     }
     if (lane == 0) nb[w] = v;
   }
@@ -1288,6 +1461,182 @@ sph_final2_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ 
       frac_idx[po * 3 + ax] = (double)b3[ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5-K7 for large bandwidths (Jmax > IB_LMIN, up to 63: grid up to 128^3).  One CTA per
+// (beta plane k, pair, orientation).  The m2 range is processed in blocks of IB_MB so that only the
+// stage-A output U[a][m2] of the plane (133 KB at Jmax = 63) and one block of S[m1][m2] stay in
+// shared memory; the Wigner table is plane-major (DtK[k][m2][m1][l]: a CTA streams one contiguous
+// plane, and consecutive CTAs share it through L2).  Same mathematics as sph_isoft_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int IB_LMIN = 32;
+constexpr int IB_THREADS = 256;
+constexpr int IB_MB = 16;
+
+__global__ void __launch_bounds__(IB_THREADS)
+sph_isoft_big_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ DtK, int L, int norient,
+                     size_t npairs, IsoOut out) {
+  extern __shared__ double2 smb[];
+  const int W = 2 * L + 1, L1 = L + 1, F = 2 * L1, H = L1 + 1;
+  const int M2p = L1 | 1;
+  double2* tw = smb;                       // [F]
+  double2* S = tw + F;                     // [W][IB_MB]
+  double2* U = S + (size_t)W * IB_MB;      // [F][M2p]
+  double* red = (double*)(U + (size_t)F * M2p);
+  const int tid = threadIdx.x;
+  const int o = (int)(blockIdx.x % norient);
+  const size_t p = (blockIdx.x / norient) % npairs;
+  const int k = (int)(blockIdx.x / ((size_t)norient * npairs));
+  const double so = o ? -1.0 : 1.0;
+  for (int t = tid; t < F; t += IB_THREADS) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+    tw[t] = make_double2(cs, sn);
+  }
+  const double2* Ip = Ihalf + p * (size_t)L1 * W * L1;
+  const double* Dk = DtK + (size_t)k * L1 * W * L1;
+  for (int m2a = 0; m2a < L1; m2a += IB_MB) {
+    const int nb = min(IB_MB, L1 - m2a);
+    __syncthreads();  // S of the previous block is consumed; tw is ready
+    // ---- K5 for m2 in [m2a, m2a + nb)
+    for (int it = tid; it < W * nb; it += IB_THREADS) {
+      const int mm = it % nb, m1i = it / nb;
+      const int m2 = m2a + mm, m1 = m1i - L;
+      const int am1 = m1 < 0 ? -m1 : m1;
+      const int l0 = am1 > m2 ? am1 : m2;
+      const size_t item = (size_t)m2 * W + m1i;
+      const double2* ip = Ip + item * L1;
+      const double* dp = Dk + item * L1;
+      double2 ae = make_double2(0.0, 0.0), ao = ae;
+      for (int l = l0; l <= L; ++l) {
+        const double dv = dp[l];
+        const double2 c = ip[l];
+        if (l & 1) {
+          ao.x = fma(dv, c.x, ao.x);
+          ao.y = fma(dv, c.y, ao.y);
+        } else {
+          ae.x = fma(dv, c.x, ae.x);
+          ae.y = fma(dv, c.y, ae.y);
+        }
+      }
+      S[(size_t)m1i * IB_MB + mm] = make_double2(fma(so, ao.x, ae.x), fma(so, ao.y, ae.y));
+    }
+    __syncthreads();
+    // ---- stage A: lines m2 of the block, inputs m1 = -L..L, outputs a = 0..F-1 into U[a][m2]
+    const int nch = (H + IS_DCA - 1) / IS_DCA;
+    for (int item = tid; item < nb * nch; item += IB_THREADS) {
+      const int mm = item % nb, ch = item / nb;
+      const int m2 = m2a + mm;
+      const int d0 = ch * IS_DCA;
+      const double2* se = S + mm;
+      const double2 c0 = se[(size_t)L * IB_MB];
+      double2 P[IS_DCA], Q[IS_DCA];
+      int idx[IS_DCA];
+#pragma unroll
+      for (int t = 0; t < IS_DCA; ++t) {
+        P[t] = c0;
+        Q[t] = make_double2(0.0, 0.0);
+        idx[t] = 0;
+      }
+      for (int m = 1; m <= L; ++m) {
+        const double2 a = se[(size_t)(L + m) * IB_MB], b = se[(size_t)(L - m) * IB_MB];
+        const double2 E = make_double2(a.x + b.x, a.y + b.y), O = make_double2(a.x - b.x, a.y - b.y);
+#pragma unroll
+        for (int t = 0; t < IS_DCA; ++t) {
+          int kq = idx[t] + d0 + t;
+          kq -= (kq >= F) ? F : 0;
+          idx[t] = kq;
+          const double2 w = tw[kq];
+          P[t].x = fma(E.x, w.x, P[t].x);
+          P[t].y = fma(E.y, w.x, P[t].y);
+          Q[t].x = fma(O.x, w.y, Q[t].x);
+          Q[t].y = fma(O.y, w.y, Q[t].y);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < IS_DCA; ++t) {
+        const int d = d0 + t;
+        if (d < H) {
+          U[(size_t)d * M2p + m2] = make_double2(P[t].x - Q[t].y, P[t].y + Q[t].x);
+          if (d != 0 && 2 * d != F)
+            U[(size_t)(F - d) * M2p + m2] = make_double2(P[t].x + Q[t].y, P[t].y - Q[t].x);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- stage B: lines a, half-complex -> real, arg-max
+  double bv = -1e300;
+  long long bi = 0x7fffffffffffffffLL;
+  {
+    const int nch = (H + IS_DCB - 1) / IS_DCB;
+    for (int item = tid; item < F * nch; item += IB_THREADS) {
+      const int a = item % F, ch = item / F;
+      const int d0 = ch * IS_DCB;
+      const double2* vin = U + (size_t)a * M2p;
+      const double v0 = vin[0].x;
+      double A[IS_DCB], Bq[IS_DCB];
+      int idx[IS_DCB];
+#pragma unroll
+      for (int t = 0; t < IS_DCB; ++t) {
+        A[t] = 0.0;
+        Bq[t] = 0.0;
+        idx[t] = 0;
+      }
+      for (int l = 1; l <= L; ++l) {
+        const double2 v = vin[l];
+#pragma unroll
+        for (int t = 0; t < IS_DCB; ++t) {
+          int kq = idx[t] + d0 + t;
+          kq -= (kq >= F) ? F : 0;
+          idx[t] = kq;
+          const double2 w = tw[kq];
+          A[t] = fma(v.x, w.x, A[t]);
+          Bq[t] = fma(v.y, w.y, Bq[t]);
+        }
+      }
+      const long long base = ((long long)a * F + k) * F;
+      double* grow = out.grid ? out.grid + ((p * norient + o) * (size_t)F * F * F + (size_t)base) : nullptr;
+#pragma unroll
+      for (int t = 0; t < IS_DCB; ++t) {
+        const int d = d0 + t;
+        if (d < H) {
+          const double aa = v0 + 2.0 * A[t], bb = 2.0 * Bq[t];
+          const double g1 = aa - bb;
+          better_s(bv, bi, g1, base + d);
+          if (grow) grow[d] = g1;
+          if (d != 0 && 2 * d != F) {
+            const double g2 = aa + bb;
+            better_s(bv, bi, g2, base + (F - d));
+            if (grow) grow[F - d] = g2;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+    const long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+    better_s(bv, bi, ov, oi);
+  }
+  long long* redi = (long long*)(red + 16);
+  if ((tid & 31) == 0) {
+    red[tid >> 5] = bv;
+    redi[tid >> 5] = bi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < IB_THREADS / 32; ++w) better_s(bv, bi, red[w], redi[w]);
+    out.part_val[(p * norient + o) * (size_t)F + k] = bv;
+    out.part_idx[(p * norient + o) * (size_t)F + k] = bi;
+  }
+}
+
+size_t isoft_big_smem(int L) {
+  const int W = 2 * L + 1, L1 = L + 1, F = 2 * L1, M2p = L1 | 1;
+  return ((size_t)F + (size_t)W * IB_MB + (size_t)F * M2p) * 16 + 32 * 8;
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -1311,8 +1660,9 @@ int ensure_wigner(fo_ctx* ctx, int L) {
   cudaError_t e = cudaMalloc(&ctx->wig.d_table, n * 8);
   if (e != cudaSuccess)
     return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the Wigner table (%zu bytes) failed", n * 8);
+  ctx->wig.kmajor = L > IB_LMIN;
   sph_wigner_kernel<<<grid_for((size_t)(L + 1) * (2 * L + 1) * (2 * L + 2), 128), 128, 0, ctx->stream>>>(
-      L, ctx->wig.d_table);
+      L, dt_stride(L, ctx->wig.kmajor), ctx->wig.d_table);
   FO_LAUNCH_CHECK(ctx);
   ctx->wig.Jmax = L;
   ctx->wig.bytes = n * 8;
@@ -1321,7 +1671,7 @@ int ensure_wigner(fo_ctx* ctx, int L) {
     cudaFree(ctx->wig.d_packed);
     ctx->wig.d_packed = nullptr;
   }
-  if ((2 * (L + 1)) % I2_KC == 0) {
+  if ((2 * (L + 1)) % I2_KC == 0 && !ctx->wig.kmajor) {
     const I2Layout Y(L);
     if (cudaMalloc(&ctx->wig.d_packed, (size_t)Y.nchunk * Y.dts * 8) != cudaSuccess)
       return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the packed Wigner table failed");
@@ -1417,6 +1767,30 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
     }
   }
 generic_path:
+  if (ctx->wig.kmajor) {
+    const size_t smem = isoft_big_smem(L);
+    if (smem > ctx->prop.sharedMemPerBlockOptin)
+      return fo_fail(ctx, FO_ERR_UNSUPPORTED, "Jmax=%d needs %zu bytes of shared memory per block", L, smem);
+    // keep the per-launch partial arrays bounded: at most ~2^20 CTAs per launch
+    void* part = nullptr;
+    FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * F * 16, &part));
+    IsoOut o;
+    o.part_val = (double*)part;
+    o.part_idx = (long long*)(o.part_val + (size_t)npairs * norient * F);
+    o.grid = d_grid;
+    fo_prof_scope prof(ctx, FO_PROF_SPH_ISOFT);
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t blocks = (size_t)F * npairs * norient;
+    if (blocks > 0x7fffffffULL) return fo_fail(ctx, FO_ERR_UNSUPPORTED, "too many pairs in one iSOFT launch");
+    sph_isoft_big_kernel<<<(unsigned)blocks, IB_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient,
+                                                                             (size_t)npairs, o);
+    FO_LAUNCH_CHECK(ctx);
+    sph_final_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+        d_Ihalf, ctx->wig.d_table, dt_stride(L, true), L, norient, F, o.part_val, o.part_idx, d_best_idx,
+        d_best_val, d_frac);
+    FO_LAUNCH_CHECK(ctx);
+    return FO_OK;
+  }
   int KC = 4;
   while (KC > 1 && (isoft_smem(L, KC) > 100 * 1024 || F % KC)) KC >>= 1;
   const size_t smem = isoft_smem(L, KC);
@@ -1447,7 +1821,8 @@ generic_path:
     }
     FO_LAUNCH_CHECK(ctx);
     sph_final_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
-        d_Ihalf, ctx->wig.d_table, L, norient, nchunk, o.part_val, o.part_idx, d_best_idx, d_best_val, d_frac);
+        d_Ihalf, ctx->wig.d_table, dt_stride(L, false), L, norient, nchunk, o.part_val, o.part_idx, d_best_idx,
+        d_best_val, d_frac);
     FO_LAUNCH_CHECK(ctx);
   }
   return FO_OK;
@@ -1490,6 +1865,21 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
   sph_bessel_kernel<<<grid_for((size_t)np * natoms * natoms, 128), 128, 0, ctx->stream>>>(
       RA, RB, d_gid, (int)natoms, L, sigma, (size_t)np, Bes);
   FO_LAUNCH_CHECK(ctx);
+  if (natoms >= ctx->direct_gemm_min) {
+    double* T = Bes + (size_t)np * (L + 1) * natoms * natoms;
+    double* C2 = T + (size_t)np * 2 * NLM * natoms;
+    const unsigned rowt = (unsigned)((2 * (L + 1) + DG_TM - 1) / DG_TM);
+    dim3 g1((unsigned)((natoms + DG_TN - 1) / DG_TN), rowt, (unsigned)(np * (L + 1)));
+    sph_direct_gemm_kernel<1><<<g1, DG_THREADS, 0, ctx->stream>>>((const double*)YA, Bes, (int)natoms, L, T);
+    FO_LAUNCH_CHECK(ctx);
+    dim3 g2(rowt, rowt, (unsigned)(np * (L + 1)));
+    sph_direct_gemm_kernel<2><<<g2, DG_THREADS, 0, ctx->stream>>>((const double*)YB, T, (int)natoms, L, C2);
+    FO_LAUNCH_CHECK(ctx);
+    sph_direct_combine_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
+        C2, L, (size_t)np, d_Ihalf);
+    FO_LAUNCH_CHECK(ctx);
+    return FO_OK;
+  }
   const size_t smem = ((size_t)(L + 1) * DIR_TK * 2 + (size_t)(2 * L + 1) * (L + 1)) * 16;
   FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(L + 1), (unsigned)np);
@@ -1500,19 +1890,24 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
 
 size_t direct_work_bytes(int64_t np, int64_t natoms, int L) {
   const size_t NLM = nlm_of(L);
+  // YA, YB | RA, RB | Bes | T, C2 (tensor-core path for large clusters; reserved unconditionally)
   return (size_t)np * natoms * NLM * 32 + (size_t)np * natoms * 16 +
-         (size_t)np * (L + 1) * natoms * natoms * 8 + 256;
+         (size_t)np * (L + 1) * natoms * natoms * 8 + (size_t)np * 2 * NLM * natoms * 8 +
+         (size_t)np * dg_c2_off(L + 1) * 8 + 256;
 }
 
 int64_t direct_chunk(int64_t npairs, int64_t natoms, int L, bool want_grid) {
   const size_t per = direct_work_bytes(1, natoms, L) + ihalf_elems(L) * 16;
-  int64_t c = (int64_t)(((size_t)1 << 30) / per);
+  // 1 GB of scratch per chunk; large clusters / bandwidths (> 256 MB per pair) get 4 GB
+  const size_t budget = per > ((size_t)256 << 20) ? (size_t)4 << 30 : (size_t)1 << 30;
+  int64_t c = (int64_t)(budget / per);
   if (want_grid) {
     const size_t g = (size_t)8 * 2 * (2 * L + 2) * (2 * L + 2) * (2 * L + 2);
     int64_t cg = (int64_t)(((size_t)512 << 20) / g);
     if (cg < c) c = cg;
   }
   if (c > 65535) c = 65535;  // gridDim.y
+  if (c * (L + 1) > 65535) c = 65535 / (L + 1);  // gridDim.z of the GEMM kernels
   if (c < 1) c = 1;
   if (c > npairs) c = npairs;
   return c;
@@ -1534,7 +1929,8 @@ extern "C" int fo_sph_wigner_table(fo_ctx* ctx, int64_t Jmax, double* out) {
   const size_t n = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1) * (2 * L + 2);
   void* d = nullptr;
   FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, n * 8, &d));
-  sph_wigner_export_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->wig.d_table, L, (double*)d);
+  sph_wigner_export_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+      ctx->wig.d_table, dt_stride(L, ctx->wig.kmajor), L, (double*)d);
   FO_LAUNCH_CHECK(ctx);
   FO_CUDA(ctx, cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -266,3 +266,85 @@ def test_fast_and_generic_isoft_agree(ctx, N, J):
     assert np.allclose(fast[1], gen[1], rtol=1e-12) and np.array_equal(fast[1], fast_ng[1])
     assert np.allclose(fast[2], gen[2], atol=1e-6)
     assert rel(fast[3], gen[3]) < 1e-12
+
+
+@pytest.mark.parametrize("N,J", [(10, 33), (12, 40), (9, 63)])
+def test_large_bandwidth_isoft(ctx, N, J):
+    """Jmax > 32 (grids up to 128^3, BASELINE.json configs[3]): sph_isoft_big_kernel with the
+    plane-major Wigner table vs the oracle (DSOFT.f90:265-329 restatement)."""
+    rng = np.random.default_rng(N * 100 + J)
+    P = 2
+    A = rng.normal(size=(P, N, 3))
+    B = rng.normal(size=(P, N, 3))
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    ctx.set_perm([np.arange(N)], N)
+    bi, bv, fr, grid, st = ctx.sph_align_pairs(A, B, J, 0.45, invert=True, want_grid=True)
+    obi, obv, ofr, ogrid, _ = oracle.sph_align_pairs(A, B, J, 0.45, True, None, want_grid=True)
+    for p in range(P):
+        for o_ in range(2):
+            assert rel(grid[p, o_], ogrid[p, o_]) < GRID_RTOL
+    assert np.array_equal(bi, obi)
+    assert np.allclose(bv, obv, rtol=1e-11)
+    assert np.allclose(fr, ofr, atol=1e-6)
+    bi2, bv2, fr2, _, _ = ctx.sph_align_pairs(A, B, J, 0.45, invert=True)
+    assert np.array_equal(bi, bi2) and np.array_equal(bv, bv2) and np.array_equal(fr, fr2)
+    if J == 40:  # Wigner table export from the plane-major layout
+        assert rel(ctx.sph_wigner_table(J), oracle.wigner_table(J + 1)) < 1e-11
+
+
+@pytest.mark.parametrize("N,J,groups,force", [(24, 9, [14, 10], True), (38, 15, None, True),
+                                              (131, 12, [70, 61], False), (200, 21, None, False)])
+def test_direct_coeffs_tensor_core_gemm(ctx, N, J, groups, force):
+    """Large-cluster form of the direct coefficients (sph_direct_gemm_kernel, DMMA) vs the oracle
+    (fastclusters.f90:868-916 restatement) and vs the small-cluster kernel."""
+    rng = np.random.default_rng(N + 7 * J)
+    P = 3
+    A = rng.normal(size=(P, N, 3)) * 1.5
+    B = rng.normal(size=(P, N, 3)) * 1.5
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    perm = None
+    if groups:
+        o = np.cumsum([0] + groups)
+        perm = [np.arange(o[i], o[i + 1]) for i in range(len(groups))]
+    ctx.set_perm(perm if perm else [np.arange(N)], N)
+    try:
+        ctx.set_option("direct_gemm_min_atoms", 1 if force else 96)
+        I, _ = ctx.sph_coeffs_direct(A, B, J, 0.5)
+        res = ctx.sph_align_pairs(A, B, J, 0.5, invert=True)
+        ctx.set_option("direct_gemm_min_atoms", 1 << 30)
+        I0, _ = ctx.sph_coeffs_direct(A, B, J, 0.5)
+        res0 = ctx.sph_align_pairs(A, B, J, 0.5, invert=True)
+    finally:
+        ctx.set_option("direct_gemm_min_atoms", 96)
+        ctx.set_perm([np.arange(N)], N)
+    for p in range(P):
+        assert rel(I[p], oracle.sph_coeffs_direct(A[p], B[p], J, 0.5, perm)) < 1e-12
+    assert rel(I, I0) < 1e-12
+    assert np.array_equal(res[0], res0[0])
+    assert np.allclose(res[1], res0[1], rtol=1e-11)
+
+
+def test_large_cluster_rotation_recovery(ctx):
+    """configs[3] shape at reduced size: lattice blob of 400 atoms, Jmax = 31, rotated + permuted +
+    jittered partner; the alignment recovers the transformation (distance ~ noise level)."""
+    from fastoverlap_b200 import SphericalAlign
+    rng = np.random.default_rng(1000)
+    g = np.arange(-6, 7) * 1.12
+    pts = np.array(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1).T
+    pts = pts[np.argsort(np.linalg.norm(pts, axis=1), kind="stable")[:400]]
+    A = pts + rng.normal(scale=0.03, size=pts.shape)
+    A -= A.mean(0)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    a, b, c, d = q
+    R = np.array([[a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c)],
+                  [2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)],
+                  [2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d]])
+    noise = rng.normal(scale=0.02, size=A.shape)
+    B = (A + noise).dot(R.T)[rng.permutation(400)]
+    B -= B.mean(0)
+    sa = SphericalAlign(0.37, 31, ctx=ctx)
+    dist = sa(A, B)[0]
+    assert dist < 2.0 * np.linalg.norm(noise), dist
