@@ -54,7 +54,7 @@ struct fo_ctx {
   // testing hook: force the generic (any-size) kernels instead of the shared-memory fast paths
   bool force_generic = false;
   // clusters with at least this many atoms use the tensor-core GEMM form of the direct coefficients
-  int64_t direct_gemm_min = 96;
+  int64_t direct_gemm_min = 64;
 
   // per-kernel event timing (fo_profile_begin/end)
   bool profiling = false;

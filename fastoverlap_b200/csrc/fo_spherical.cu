@@ -404,6 +404,87 @@ __global__ void sph_direct_combine_kernel(const double* __restrict__ C2, int L, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K2a for small clusters on the tensor pipe (sph_direct_mma_kernel): the two contractions of
+// sph_direct_kernel for one (pair, l) per CTA as DMMA.8x8x4 tiles fed from shared memory, complex
+// quantities as interleaved real rows r = 2 m + (re | im) like sph_direct_gemm_kernel:
+//   T[r][k]    = sum_j YA[j][r] B_l[j][k]       (2(l+1) x N x N)
+//   C2[r][r']  = sum_k T[r][k]  YB[k][r']       (2(l+1) x 2(l+1) x N)
+// and I[l,+-m1,m2] is formed in the C fragments (the re / im rows of one m1 sit in lanes g, g^1).
+// All operands are k-major with a pitch == 8 (mod 32) doubles: conflict-free fragment loads.
+// ncu on the scalar kernel: 16 % FP64 pipe, bound by shared / global operand loads (2 loads per 2 FMA).
+// ------------------------------------------------------------------------------------------
+constexpr int DS_THREADS = 128;
+__host__ __device__ inline int fo_ld8(int w) { return w + ((8 - w) % 32 + 32) % 32; }
+
+__global__ void __launch_bounds__(DS_THREADS)
+sph_direct_mma_kernel(const double2* __restrict__ YA, const double2* __restrict__ YB,
+                      const double* __restrict__ Bes, int natoms, int L, double2* __restrict__ Ihalf) {
+  extern __shared__ double smq[];
+  const int l = blockIdx.x;
+  const size_t p = blockIdx.y;
+  const int NLM = nlm_of(L), W = 2 * L + 1, L1 = L + 1;
+  const int R = 2 * (l + 1), R8 = (R + 7) & ~7;
+  const int N4 = (natoms + 3) & ~3, N8 = (natoms + 7) & ~7;
+  const int LDR = fo_ld8((2 * L1 + 7) & ~7), LDN = fo_ld8(N8);
+  double* A1 = smq;                       // [N8][LDR]  YA_l:  A1[j LDR + r]
+  double* B2 = A1 + (size_t)N8 * LDR;     // [N8][LDR]  YB_l
+  double* Ts = B2 + (size_t)N8 * LDR;     // [N8][LDR]  T:     Ts[k LDR + r]
+  double* B1 = Ts + (size_t)N8 * LDR;     // [N8][LDN]  B_l:   B1[j LDN + k]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int lbase = l * (l + 1) / 2;
+  const double* ya = reinterpret_cast<const double*>(YA + p * (size_t)natoms * NLM + lbase);
+  const double* yb = reinterpret_cast<const double*>(YB + p * (size_t)natoms * NLM + lbase);
+  const double* Bl = Bes + (p * L1 + l) * (size_t)natoms * natoms;
+  for (int e = tid; e < N8 * R8; e += DS_THREADS) {
+    const int j = e / R8, r = e - j * R8;
+    const bool in = j < natoms && r < R;
+    A1[j * LDR + r] = in ? ya[(size_t)j * 2 * NLM + r] : 0.0;
+    B2[j * LDR + r] = in ? yb[(size_t)j * 2 * NLM + r] : 0.0;
+  }
+  for (int e = tid; e < N8 * N8; e += DS_THREADS) {
+    const int j = e / N8, k = e - j * N8;
+    B1[j * LDN + k] = (j < natoms && k < natoms) ? Bl[(size_t)j * natoms + k] : 0.0;
+  }
+  __syncthreads();
+  const int nrt = R8 >> 3, nct = N8 >> 3, nks = N4 >> 2;
+  for (int job = warp; job < nrt * nct; job += DS_THREADS / 32) {
+    const int rt = job % nrt, ct = job / nrt;
+    double acc[2] = {0.0, 0.0};
+    const double* a = A1 + t4 * LDR + rt * 8 + g;
+    const double* b = B1 + t4 * LDN + ct * 8 + g;
+    for (int ks = 0; ks < nks; ++ks) fo_dmma(acc, a[ks * 4 * LDR], b[ks * 4 * LDN]);
+    Ts[(ct * 8 + 2 * t4) * LDR + rt * 8 + g] = acc[0];
+    Ts[(ct * 8 + 2 * t4 + 1) * LDR + rt * 8 + g] = acc[1];
+  }
+  __syncthreads();
+  double2* out = Ihalf + p * (size_t)L1 * W * L1;
+  for (int job = warp; job < nrt * nrt; job += DS_THREADS / 32) {
+    const int rt1 = job % nrt, rt2 = job / nrt;
+    double acc[2] = {0.0, 0.0};
+    const double* a = Ts + t4 * LDR + rt1 * 8 + g;
+    const double* b = B2 + t4 * LDR + rt2 * 8 + g;
+    for (int ks = 0; ks < nks; ++ks) fo_dmma(acc, a[ks * 4 * LDR], b[ks * 4 * LDR]);
+    // this lane: row r1 = 8 rt1 + g (m1 = r1 / 2, part g & 1), columns (re, im) of m2 = 4 rt2 + t4
+    const double px0 = __shfl_xor_sync(0xffffffffu, acc[0], 4);
+    const double px1 = __shfl_xor_sync(0xffffffffu, acc[1], 4);
+    const int m1 = (rt1 * 8 + g) >> 1, m2 = rt2 * 4 + t4;
+    if (m1 > l || m2 > l) continue;
+    if ((g & 1) == 0) {  // rr, ri here; ir, ii in the partner: I(+m1, m2)
+      out[((size_t)m2 * W + (L + m1)) * L1 + l] = make_double2(acc[0] + px1, px0 - acc[1]);
+    } else if (m1 > 0) {  // ir, ii here; rr, ri in the partner: I(-m1, m2) = (-1)^m1 (rr - ii, -ir - ri)
+      const double sg = (m1 & 1) ? -1.0 : 1.0;
+      out[((size_t)m2 * W + (L - m1)) * L1 + l] = make_double2(sg * (px0 - acc[1]), sg * (-acc[0] - px1));
+    }
+  }
+}
+
+size_t direct_mma_smem(int64_t natoms, int L) {
+  const int N8 = (int)((natoms + 7) & ~7);
+  return ((size_t)3 * N8 * fo_ld8((2 * (L + 1) + 7) & ~7) + (size_t)N8 * fo_ld8(N8)) * 8;
+}
+
 // The (m2, m1, l < max(|m1|, m2)) entries are never read; no need to clear Ihalf.
 
 // Full numpy layout [l][m1 wrap][m2 wrap] -> Ihalf, keeping the part that generates the REAL grid:
@@ -1128,30 +1209,27 @@ __global__ void sph_ipack_kernel(const double2* __restrict__ Ihalf, const __grid
 struct Iso2Out {
   double* part_val;   // [P][O][nchunk]
   int* part_idx;      // [P][O][nchunk]  flat (a F + k) F + g
-  double* part_nb;    // [P][O][nchunk][6]  |neighbour values| (NaN: outside this CTA's planes)
   double* grid;       // [P][O][F][F][F] or null
-  long long* dbg;     // optional: per-phase cycle counters of CTA 0 (FO_DEBUG_TIMING=1)
 };
-
-#define I2_TICK(slot)                                              \
-  do {                                                             \
-    if (out.dbg && blockIdx.x == 0 && tid == 0) {                  \
-      const long long now_ = clock64();                            \
-      atomicAdd((unsigned long long*)&out.dbg[slot], (unsigned long long)(now_ - tick_)); \
-      tick_ = now_;                                                \
-    }                                                              \
-  } while (0)
 
 // KS = ceil(L/4) k-steps, NT = number of 8-wide output tiles handled by DMMA; NYQ: H = 8 NT + 1, the
 // last output (alpha or gamma = F/2) is the alternating sum c0 + sum (-1)^m E_m, done on the side.
+//
+// The kernel is persistent and every pair has the same geometry, so everything that depends only on
+// (thread, L) -- the K5 entry a thread owns, the rows / output addresses of the (at most two) stage-A
+// and stage-B tiles of a warp -- is decoded once before the pair loop: ncu (profiles/r01_summary.md)
+// showed the first version spending 97 % of its issue slots on that index arithmetic and on the
+// epilogues (DMMA: 2.3 % of the instructions).  The fast path exists for odd L <= 15 (F % 4 == 0 and
+// the shared-memory layout fits), where K5 has one work item per thread.
 template <int KS, int NT, bool NYQ, bool WANT_GRID>
 __global__ void __launch_bounds__(I2_THREADS, 1)
 sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict__ Ipk,
                   const double* __restrict__ DtP, int npairs, int norient, Iso2Out out) {
   extern __shared__ double smj[];
-  const int L = Y.L, L1 = Y.L1, W = Y.W, F = Y.F, H = Y.H;
+  const int L = Y.L, L1 = Y.L1, F = Y.F, H = Y.H;
   const int RA = Y.RA, RAp = Y.RAp, RB = Y.RB, RBp = Y.RBp;
-  double* DtS = smj + Y.o_dts;
+  constexpr int HV = NYQ ? NT * 8 : 0;  // NYQ: all 8 NT DMMA outputs are valid (H - 1 == 8 NT)
+  double2* IkS = reinterpret_cast<double2*>(smj + Y.o_dts);  // packed coefficients of the current pair
   double* AE = smj + Y.o_ae;   // [o][m1 = 0..L][RAp]   (m1 = 0: c0)
   double* AO = smj + Y.o_ao;   // [o][m1][RAp]
   double* BR = smj + Y.o_br;   // [o][m2 = 0..L][RBp]   row = a * KC + kk
@@ -1161,97 +1239,152 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
   const int g = lane >> 2, t4 = lane & 3;
   const int chunk = blockIdx.x % Y.nchunk;
   const int jstart = blockIdx.x / Y.nchunk, jstride = gridDim.x / Y.nchunk;
-  for (int e = tid; e < Y.dts; e += I2_THREADS) DtS[e] = DtP[(size_t)chunk * Y.dts + e];
+  const int nvalid = NYQ ? H - 1 : H;  // outputs produced by the DMMA tiles
+  // The Wigner slice of this chunk (48 KB at L = 15, the same for every pair) is read through L1;
+  // shared memory instead stages the coefficients of the NEXT pair (cp.async issued after K5, landing
+  // during stages A / B), so K5 never waits for L2: ncu showed 45 % of the first version's time in
+  // long-scoreboard stalls on those loads and in the barrier behind them.
+  const double* DtC = DtP + (size_t)chunk * Y.dts;
+  auto stage_coeffs = [&](int pr) {
+    const double2* src = Ipk + (size_t)pr * Y.ipk;
+    for (int e = tid; e < Y.ipk; e += I2_THREADS) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(IkS + e);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (jstart < npairs) stage_coeffs(jstart);
   SymMma<KS, NT> mm;
-  mm.init(L, F, NYQ ? H - 1 : H, lane);
+  mm.init(L, F, nvalid, lane);
+
+  // ---- K5 geometry: work item = (entry pair {t, NP-1-t}, plane kk).  Pairing a low shell (long l
+  // run) with a high shell (short run) gives every thread ~L+2 levels: no barrier skew.
+  const int nhalf = (Y.NP + 1) >> 1;
+  const bool k5_on = tid < nhalf * I2_KC;
+  const int kk5 = tid & (I2_KC - 1);
+  int k5_s[2], k5_src[2], k5_dst[2];
+  bool k5_v[2], k5_a0[2], k5_m2odd[2];
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const int qp = tid >> 2;
+    const int t = which ? Y.NP - 1 - qp : qp;
+    k5_v[which] = k5_on && !(which && t == qp);
+    const int tt = k5_v[which] ? t : 0;
+    int s = (int)sqrtf((float)tt);
+    while ((s + 1) * (s + 1) <= tt) ++s;
+    while (s * s > tt) --s;
+    const int q = tt - s * s;
+    const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
+    k5_s[which] = s;
+    k5_src[which] = (Y.o_lvl[s] >> 1) + tt * 2;   // double2 index into the packed coefficients
+    // (the double index into the packed table slice is 2 k5_src: KC = 4 doubles per entry)
+    k5_dst[which] = a * RAp + (kk5 * L1 + m2) * 2;
+    k5_a0[which] = a == 0;
+    k5_m2odd[which] = m2 & 1;
+  }
+  // ---- stage A / B geometry of this warp's tiles (tile = warp + 16 j, j = 0, 1)
+  constexpr int NW = I2_THREADS / 32;
+  bool ta_v[2], tb_v[2];
+  int ta_in[2], ta_out[2], tb_in[2], tb_base[2];
+  bool ta_part[2], tb_o[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int tile = warp + NW * j;
+    {
+      ta_v[j] = tile * 8 < norient * RA;
+      const int r = ta_v[j] ? tile * 8 + g : g;  // RA is a multiple of 8: every tile is full
+      const int o = r / RA, row = r - o * RA;
+      const int part = row & 1, line = row >> 1;
+      const int kk = line / L1, m2 = line - kk * L1;
+      ta_in[j] = o * L1 * RAp + row;
+      ta_out[j] = (part ? Y.o_bi : Y.o_br) + (o * L1 + m2) * RBp + kk;
+      ta_part[j] = part;
+    }
+    {
+      tb_v[j] = tile * 8 < norient * RB;
+      const int r = tb_v[j] ? tile * 8 + g : g;
+      const int o = r / RB, rowb = r - o * RB;
+      const int a = rowb / I2_KC, kk = rowb - a * I2_KC;
+      tb_in[j] = o * L1 * RBp + rowb;
+      tb_base[j] = (a * F + i2_plane(F, chunk, kk)) * F;
+      tb_o[j] = o != 0;
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  long long tick_ = clock64();
   for (int pair = jstart; pair < npairs; pair += jstride) {
-    I2_TICK(0);
-    // ---- K5: work item = (entry pair {t, NP-1-t}, plane kk).  Pairing a low shell (long l run) with
-    // a high shell (short run) gives every thread ~L+2 levels: no barrier skew.  The coefficients
-    // come from the packed, level-major copy Ipk (coalesced 32-byte reads per lane pair) and are
-    // fetched four levels ahead, so a thread waits for ~(L+2)/4 memory latencies instead of L+1.
-    {
-      const double2* Ik = Ipk + (size_t)pair * Y.ipk;
-      const int nhalf = (Y.NP + 1) >> 1;
-      for (int w = tid; w < nhalf * I2_KC; w += I2_THREADS) {
-        const int kk = w & (I2_KC - 1), qp = w >> 2;
-#pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
-          const int t = which ? Y.NP - 1 - qp : qp;
-          if (which && t == qp) break;
-          int s = (int)sqrtf((float)t);
-          while ((s + 1) * (s + 1) <= t) ++s;
-          while (s * s > t) --s;
-          const int q = t - s * s;
-          const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
-          double2 pe = make_double2(0.0, 0.0), po = pe, me = pe, mo = pe;
-          for (int l0 = s; l0 <= L; l0 += 4) {
-            double2 cp[4], cm[4];
-            double dpl[4], dmi[4];
+    // ---- K5.  The coefficients come from the packed, level-major copy Ipk (coalesced 32-byte reads
+    // per lane pair) and are fetched four levels ahead.  Consecutive levels alternate parity, so the
+    // four accumulators (x: entry +a, y: entry -a; index: parity relative to the first level s) need
+    // no branch; orientation o uses I_inv^l = (-1)^l I^l.
+    if (k5_on) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int l = min(l0 + u, L);
-              const double2* src = Ik + (Y.o_lvl[l] >> 1) + t * 2;  // o_lvl counts KC = 4 doubles per entry
-              cp[u] = src[0];
-              cm[u] = src[1];
-              const double* dp = DtS + Y.o_lvl[l] + t * I2_KC;
-              dpl[u] = dp[kk];
-              dmi[u] = dp[I2_KC - 1 - kk];
-            }
+      for (int which = 0; which < 2; ++which) {
+        if (!k5_v[which]) continue;
+        const int s = k5_s[which];
+        const double2* src = IkS + k5_src[which];
+        const double* dp = DtC + 2 * k5_src[which];
+        int inc = (s + 1) * (s + 1);  // entries of level l
+        double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
+        for (int l0 = s; l0 <= L; l0 += 4) {
+          double2 cp[4], cm[4];
+          double dpl[4], dmi[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int l = l0 + u;
-              if (l <= L) {
-                if (l & 1) {
-                  po.x = fma(dpl[u], cp[u].x, po.x);
-                  po.y = fma(dpl[u], cp[u].y, po.y);
-                  mo.x = fma(dmi[u], cm[u].x, mo.x);
-                  mo.y = fma(dmi[u], cm[u].y, mo.y);
-                } else {
-                  pe.x = fma(dpl[u], cp[u].x, pe.x);
-                  pe.y = fma(dpl[u], cp[u].y, pe.y);
-                  me.x = fma(dmi[u], cm[u].x, me.x);
-                  me.y = fma(dmi[u], cm[u].y, me.y);
-                }
-              }
+          for (int u = 0; u < 4; ++u) {
+            const int l = l0 + u;
+            const bool in = l <= L;
+            cp[u] = src[0];
+            cm[u] = src[1];
+            dpl[u] = in ? __ldg(dp + kk5) : 0.0;
+            dmi[u] = in ? __ldg(dp + (I2_KC - 1 - kk5)) : 0.0;
+            if (l < L) {  // clamp at the last level: the masked table value makes the term vanish
+              src += 2 * inc;
+              dp += I2_KC * inc;
+              inc += 2 * l + 3;
             }
           }
-          const double sm2 = (m2 & 1) ? -1.0 : 1.0;
-          const int row = (kk * L1 + m2) * 2;
+          x0.x = fma(dpl[0], cp[0].x, x0.x); x0.y = fma(dpl[0], cp[0].y, x0.y);
+          y0.x = fma(dmi[0], cm[0].x, y0.x); y0.y = fma(dmi[0], cm[0].y, y0.y);
+          x1.x = fma(dpl[1], cp[1].x, x1.x); x1.y = fma(dpl[1], cp[1].y, x1.y);
+          y1.x = fma(dmi[1], cm[1].x, y1.x); y1.y = fma(dmi[1], cm[1].y, y1.y);
+          x0.x = fma(dpl[2], cp[2].x, x0.x); x0.y = fma(dpl[2], cp[2].y, x0.y);
+          y0.x = fma(dmi[2], cm[2].x, y0.x); y0.y = fma(dmi[2], cm[2].y, y0.y);
+          x1.x = fma(dpl[3], cp[3].x, x1.x); x1.y = fma(dpl[3], cp[3].y, x1.y);
+          y1.x = fma(dmi[3], cm[3].x, y1.x); y1.y = fma(dmi[3], cm[3].y, y1.y);
+        }
+        const bool sodd = s & 1;
+        const double2 pe = sodd ? x1 : x0, po = sodd ? x0 : x1;
+        const double2 me = sodd ? y1 : y0, mo = sodd ? y0 : y1;
+        const double sm2 = k5_m2odd[which] ? -1.0 : 1.0;
 #pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            const double so = o ? -1.0 : 1.0;
-            // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
-            const double spx = fma(so, po.x, pe.x), spy = fma(so, po.y, pe.y);
-            const double smx = sm2 * fma(-so, mo.x, me.x), smy = sm2 * fma(-so, mo.y, me.y);
-            double2* ae = reinterpret_cast<double2*>(AE + (size_t)(o * L1 + a) * RAp + row);
-            double2* ao = reinterpret_cast<double2*>(AO + (size_t)(o * L1 + a) * RAp + row);
-            if (a == 0) {
-              *ae = make_double2(spx, spy);
-              *ao = make_double2(0.0, 0.0);
-            } else {
-              *ae = make_double2(spx + smx, spy + smy);
-              *ao = make_double2(spx - smx, spy - smy);
-            }
+        for (int o = 0; o < 2; ++o) {
+          const double so = o ? -1.0 : 1.0;
+          // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
+          const double spx = fma(so, po.x, pe.x), spy = fma(so, po.y, pe.y);
+          const double smx = sm2 * fma(-so, mo.x, me.x), smy = sm2 * fma(-so, mo.y, me.y);
+          double2* ae = reinterpret_cast<double2*>(AE + (size_t)o * L1 * RAp + k5_dst[which]);
+          double2* ao = reinterpret_cast<double2*>(AO + (size_t)o * L1 * RAp + k5_dst[which]);
+          if (k5_a0[which]) {
+            *ae = make_double2(spx, spy);
+            *ao = make_double2(0.0, 0.0);
+          } else {
+            *ae = make_double2(spx + smx, spy + smy);
+            *ao = make_double2(spx - smx, spy - smy);
           }
         }
       }
     }
     __syncthreads();
-    I2_TICK(1);
+    if (pair + jstride < npairs) stage_coeffs(pair + jstride);
     // ---- stage A: tiles of 8 rows (o, kk, m2, part): U[a] = P + iQ, U[F-a] = P - iQ
-    for (int tile = warp; tile * 8 < norient * RA; tile += I2_THREADS / 32) {
-      const int r = tile * 8 + g;  // RA is a multiple of 8: every tile is full
-      const int o = r / RA, row = r - o * RA;
-      const int part = row & 1, line = row >> 1;
-      const int kk = line / L1, m2 = line - kk * L1;
-      const double sgn = part ? 1.0 : -1.0;
-      double* Bout = (part ? BI : BR) + (size_t)(o * L1 + m2) * RBp + kk;
-      const double* e0 = AE + (size_t)(o * L1) * RAp + row;
-      const double* o1 = AO + (size_t)(o * L1 + 1) * RAp + row;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (!ta_v[j]) continue;
+      const double* e0 = AE + ta_in[j];
+      const double* o1 = AO + ta_in[j] + RAp;
+      double* Bout = smj + ta_out[j];
+      const double sgn = ta_part[j] ? 1.0 : -1.0;
       double P[NT][2], Q[NT][2];
       mm.run(e0 + RAp - g, o1 - g, RAp, L, e0[0], lane, P, Q);
 #pragma unroll
@@ -1260,9 +1393,9 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
         for (int q = 0; q < 2; ++q) {
           const int d = nt * 8 + t4 * 2 + q;
           const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
-          if (d < (NYQ ? H - 1 : H)) {
+          if (NYQ || d < nvalid) {
             Bout[d * I2_KC] = fma(sgn, qx, P[nt][q]);
-            if (d != 0 && 2 * d != F) Bout[(F - d) * I2_KC] = fma(-sgn, qx, P[nt][q]);
+            if (d != 0 && (NYQ || 2 * d != F)) Bout[(F - d) * I2_KC] = fma(-sgn, qx, P[nt][q]);
           }
         }
       if (NYQ) {  // a = F/2: U = c0 + sum_m (-1)^m E_m  (sin terms vanish)
@@ -1277,37 +1410,36 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
       }
     }
     __syncthreads();
-    I2_TICK(2);
-    // ---- stage B: tiles of 8 rows (o, a, kk): g[gam] = aa - bb, g[F-gam] = aa + bb; arg-max
-    double bv0 = -1e300, bv1 = -1e300;
-    int bi0 = 0x7fffffff, bi1 = 0x7fffffff;
-    for (int tile = warp; tile * 8 < norient * RB; tile += I2_THREADS / 32) {
-      const int r = tile * 8 + g;
-      const int o = r / RB, rowb = r - o * RB;
-      const int a = rowb / I2_KC, kk = rowb - a * I2_KC;
-      const int k = i2_plane(F, chunk, kk);
-      const int base = (a * F + k) * F;
-      const double* br = BR + (size_t)(o * L1) * RBp + rowb;
-      const double* bi1p = BI + (size_t)(o * L1 + 1) * RBp + rowb;
-      const double v0 = br[0];
+    // ---- stage B: tiles of 8 rows (o, a, kk): g[gam] = aa - bb, g[F-gam] = aa + bb; arg-max.
+    // Everything is kept at half scale (accumulators start at v0/2, the grid value is 2 (A -+ B)):
+    // the larger of the two outputs of a column is A + |B|, one DADD + one max per column instead
+    // of forming both values; only a tile that beats the running maximum is looked at in detail.
+    double bvh[2] = {-1e300, -1e300};
+    int bix[2] = {0x7fffffff, 0x7fffffff};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (!tb_v[j]) continue;
+      const double* br = BR + tb_in[j];
+      const double* bi1p = BI + tb_in[j] + RBp;
+      const int base = tb_base[j];
+      const int o = tb_o[j] ? 1 : 0;
+      const double v0h = 0.5 * br[0];
       double A[NT][2], Bq[NT][2];
-      mm.run(br + RBp - g, bi1p - g, RBp, L, 0.0, lane, A, Bq);
-      double g1[NT][2], g2[NT][2];
+      mm.run(br + RBp - g, bi1p - g, RBp, L, v0h, lane, A, Bq);
       double cmax = -1e300;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int d = nt * 8 + t4 * 2 + q;
-          const double aa = fma(2.0, A[nt][q], v0), bb = 2.0 * Bq[nt][q];
-          const bool in = d < (NYQ ? H - 1 : H);
-          g1[nt][q] = in ? aa - bb : -1e300;
-          g2[nt][q] = (in && d != 0 && 2 * d != F) ? aa + bb : -1e300;
-          cmax = fmax(cmax, fmax(g1[nt][q], g2[nt][q]));
+          const double c = A[nt][q] + fabs(Bq[nt][q]);
+          if (NYQ || nt * 8 + 7 < HV || d < nvalid) cmax = fmax(cmax, c);
           if (WANT_GRID) {
             double* grow = out.grid + (((size_t)pair * norient + o) * F * F * F + (size_t)base);
-            if (in) grow[d] = aa - bb;
-            if (in && d != 0 && 2 * d != F) grow[F - d] = aa + bb;
+            if (NYQ || d < nvalid) {
+              grow[d] = 2.0 * (A[nt][q] - Bq[nt][q]);
+              if (d != 0 && (NYQ || 2 * d != F)) grow[F - d] = 2.0 * (A[nt][q] + Bq[nt][q]);
+            }
           }
         }
       double gny = -1e300;
@@ -1320,144 +1452,149 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         if (t4 == 0) {
-          gny = fma(2.0, acc, v0);
+          gny = v0h + acc;
           cmax = fmax(cmax, gny);
-          if (WANT_GRID) out.grid[((size_t)pair * norient + o) * F * F * F + (size_t)base + F / 2] = gny;
+          if (WANT_GRID) out.grid[((size_t)pair * norient + o) * F * F * F + (size_t)base + F / 2] = 2.0 * gny;
         }
       }
-      const double cur = o ? bv1 : bv0;
+      const double cur = o ? bvh[1] : bvh[0];
       if (cmax >= cur) {
-        double tbv = o ? bv1 : bv0;
-        int tbi = o ? bi1 : bi0;
+        double tbv = cur;
+        int tbi = o ? bix[1] : bix[0];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int d = nt * 8 + t4 * 2 + q;
-            if (g1[nt][q] > tbv || (g1[nt][q] == tbv && base + d < tbi)) { tbv = g1[nt][q]; tbi = base + d; }
-            if (g2[nt][q] > tbv || (g2[nt][q] == tbv && base + F - d < tbi)) { tbv = g2[nt][q]; tbi = base + F - d; }
+            const bool in = NYQ || d < nvalid;
+            const double g1 = in ? A[nt][q] - Bq[nt][q] : -1e300;
+            const double g2 = (in && d != 0 && (NYQ || 2 * d != F)) ? A[nt][q] + Bq[nt][q] : -1e300;
+            if (g1 > tbv || (g1 == tbv && base + d < tbi)) { tbv = g1; tbi = base + d; }
+            if (g2 > tbv || (g2 == tbv && base + F - d < tbi)) { tbv = g2; tbi = base + F - d; }
           }
         if (NYQ && (gny > tbv || (gny == tbv && base + F / 2 < tbi))) { tbv = gny; tbi = base + F / 2; }
-        if (o) { bv1 = tbv; bi1 = tbi; } else { bv0 = tbv; bi0 = tbi; }
+        if (o) { bvh[1] = tbv; bix[1] = tbi; } else { bvh[0] = tbv; bix[0] = tbi; }
       }
     }
-    I2_TICK(3);
-    // block reduction per orientation
+    // ---- block arg-max per orientation: warp max of the value, then the smallest index among the
+    // lanes that hold it (REDUX), then 16 warps through shared memory
     int* redi = reinterpret_cast<int*>(red + 48);
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
-      double v = o ? bv1 : bv0;
-      int i = o ? bi1 : bi0;
+      double m = bvh[o];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, v, off);
-        const int oi = __shfl_down_sync(0xffffffffu, i, off);
-        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-      }
+      for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+      const int cand = (bvh[o] == m) ? bix[o] : 0x7fffffff;
+      const int imin = __reduce_min_sync(0xffffffffu, cand);
       if (lane == 0) {
-        red[o * 16 + warp] = v;
-        redi[o * 16 + warp] = i;
+        red[o * 16 + warp] = m;
+        redi[o * 16 + warp] = imin;
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // next pair's coefficients: visible after the barrier
     __syncthreads();
-    if (tid < 2) {
+    if (tid < norient) {
       double v = red[tid * 16];
       int i = redi[tid * 16];
-      for (int w = 1; w < I2_THREADS / 32; ++w) {
+      for (int w = 1; w < NW; ++w) {
         const double ov = red[tid * 16 + w];
         const int oi = redi[tid * 16 + w];
         if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
       }
-      red[32 + tid] = v;
-      redi[32 + tid] = i;
+      out.part_val[((size_t)pair * norient + tid) * Y.nchunk + chunk] = 2.0 * v;
+      out.part_idx[((size_t)pair * norient + tid) * Y.nchunk + chunk] = i;
     }
-    __syncthreads();
-    // ---- parabola neighbours inside this CTA's planes: warp w < 6 -> neighbour w, both orientations
-    {
-      if (warp < 6) {
-        for (int o = 0; o < norient; ++o) {
-          const int fi = redi[32 + o];
-          const bool ok = fi != 0x7fffffff;
-          const int a0 = ok ? fi / (F * F) : 0, k0 = ok ? (fi / F) % F : 0, g0 = ok ? fi % F : 0;
-          const int ax = warp >> 1, sg = (warp & 1) ? -1 : 1;
-          int qa = a0, qk = k0, qg = g0;
-          if (ax == 0) qa = (a0 + sg + F) % F;
-          if (ax == 1) qk = (k0 + sg + F) % F;
-          if (ax == 2) qg = (g0 + sg + F) % F;
-          int kk = -1;
-          for (int c = 0; c < I2_KC; ++c)
-            if (i2_plane(F, chunk, c) == qk) kk = c;
-          double acc = 0.0;
-          if (kk >= 0) {
-            const int rowb = qa * I2_KC + kk;
-            for (int m2 = lane; m2 <= L; m2 += 32) {
-              const double vr = BR[(size_t)(o * L1 + m2) * RBp + rowb];
-              if (m2 == 0) {
-                acc += vr;
-              } else {
-                const double vi = BI[(size_t)(o * L1 + m2) * RBp + rowb];
-                double sn, cs;
-                sincospi(2.0 * (double)((m2 * qg) % F) / (double)F, &sn, &cs);
-                acc += 2.0 * (vr * cs - vi * sn);
-              }
-            }
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-          if (lane == 0)
-            out.part_nb[((((size_t)pair * norient + o) * Y.nchunk) + chunk) * 6 + warp] =
-                kk >= 0 ? fabs(acc) : __longlong_as_double(0x7ff8000000000000LL);
-        }
-      }
-      if (tid < norient) {
-        out.part_val[((size_t)pair * norient + tid) * Y.nchunk + chunk] = red[32 + tid];
-        out.part_idx[((size_t)pair * norient + tid) * Y.nchunk + chunk] = redi[32 + tid];
-      }
-    }
-    __syncthreads();
-    I2_TICK(4);
+    // no barrier here: the next writes to red / BR / BI come after the next pair's K5 barrier
   }
 }
 
-// One CTA per (pair, orientation): best chunk, then the parabola; neighbours the chunk CTA could not
-// evaluate (NaN) are computed by the direct Wigner sum.
+// One CTA per (pair, orientation): best chunk, then findMax's parabola (utils.py:319-338).  The six
+// neighbours are evaluated from the coefficients: one pass over the (m1, m2 >= 0) entries forms
+// S_k(m1, m2) for the three planes k0-1, k0, k0+1 (adjacent table columns) and accumulates the four
+// in-plane neighbours and the two out-of-plane ones; all 256 threads share the pass.
 __global__ void __launch_bounds__(256)
 sph_final2_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, int L, int norient,
                   int nchunk, const double* __restrict__ part_val, const int* __restrict__ part_idx,
-                  const double* __restrict__ part_nb, long long* __restrict__ best_idx,
-                  double* __restrict__ best_val, double* __restrict__ frac_idx) {
-  __shared__ double nb[6];
+                  long long* __restrict__ best_idx, double* __restrict__ best_val,
+                  double* __restrict__ frac_idx) {
+  __shared__ double2 tw[128];
+  __shared__ double nbs[8][6];
   const size_t po = blockIdx.x;
   const size_t p = po / norient;
   const int o = (int)(po % norient);
-  const int F = 2 * (L + 1);
+  const int L1 = L + 1, W = 2 * L + 1, F = 2 * L1;
+  const double so = o ? -1.0 : 1.0;
+  for (int t = threadIdx.x; t < F; t += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+    tw[t] = make_double2(cs, sn);
+  }
   double bv = -1e300;
-  int bi = 0x7fffffff, bc = 0;
+  int bi = 0x7fffffff;
   for (int c = 0; c < nchunk; ++c) {
     const double v = part_val[po * nchunk + c];
     const int i = part_idx[po * nchunk + c];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; bc = c; }
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
   const bool ok = bi != 0x7fffffff;
-  const int b3[3] = {ok ? bi / (F * F) : 0, ok ? (bi / F) % F : 0, ok ? bi % F : 0};
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (w < 6) {
-    double v = part_nb[(po * nchunk + bc) * 6 + w];
-    if (v != v) {  // not available from the chunk CTA
-      const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
-      int q[3] = {b3[0], b3[1], b3[2]};
-      q[ax] = (q[ax] + sgn + F) % F;
-      v = fabs(iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, dt_stride(L, false), L, q[0],
-                         q[1], q[2], o ? -1.0 : 1.0, lane));
+  const int a0 = ok ? bi / (F * F) : 0, k0 = ok ? (bi / F) % F : 0, g0 = ok ? bi % F : 0;
+  const int km = (k0 + F - 1) % F, kp = (k0 + 1) % F;
+  __syncthreads();
+  // accumulators: 0,1 = a0 -+ 1; 2,3 = k0 -+ 1; 4,5 = g0 -+ 1   (order of the parabola below)
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const double2* Ip = Ihalf + p * (size_t)L1 * W * L1;
+  for (int item = threadIdx.x; item < L1 * W; item += blockDim.x) {
+    const int m1i = item % W, m2 = item / W;
+    const int m1 = m1i - L;
+    const int am1 = m1 < 0 ? -m1 : m1;
+    const int l0 = am1 > m2 ? am1 : m2;
+    double sr[3] = {0.0, 0.0, 0.0}, si[3] = {0.0, 0.0, 0.0};
+    const double2* ip = Ip + (size_t)item * L1;
+    const double* dp = Dt + (size_t)item * L1 * F;
+    for (int l = l0; l <= L; ++l) {
+      const double sg = (l & 1) ? so : 1.0;
+      const double2 c = ip[l];
+      const double* d = dp + (size_t)l * F;
+      const double cx = sg * c.x, cy = sg * c.y;
+      const double d0 = d[km], d1 = d[k0], d2 = d[kp];
+      sr[0] = fma(d0, cx, sr[0]); si[0] = fma(d0, cy, si[0]);
+      sr[1] = fma(d1, cx, sr[1]); si[1] = fma(d1, cy, si[1]);
+      sr[2] = fma(d2, cx, sr[2]); si[2] = fma(d2, cy, si[2]);
     }
-    if (lane == 0) nb[w] = v;
+    const double wgt = (m2 == 0) ? 1.0 : 2.0;
+    const int e0 = ((m1 * a0 + m2 * g0) % F + F) % F;
+    // term(plane j, phase e) = S_r cos - S_i sin
+    auto term = [&](int j, int e) {
+      const double2 w = tw[e];
+      return wgt * (sr[j] * w.x - si[j] * w.y);
+    };
+    acc[0] += term(1, ((e0 - m1) % F + F) % F);
+    acc[1] += term(1, ((e0 + m1) % F + F) % F);
+    acc[2] += term(0, e0);
+    acc[3] += term(2, e0);
+    acc[4] += term(1, ((e0 - m2) % F + F) % F);
+    acc[5] += term(1, (e0 + m2) % F);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], off);
+    if (lane == 0) nbs[w][q] = acc[q];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    double nb[6];
+    for (int q = 0; q < 6; ++q) {
+      double s = 0.0;
+      for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) s += nbs[ww][q];
+      nb[q] = fabs(s);
+    }
     best_val[po] = bv;
+    const int b3[3] = {a0, k0, g0};
     for (int ax = 0; ax < 3; ++ax) {
       best_idx[po * 3 + ax] = b3[ax];
-      const double y1 = nb[2 * ax], y3 = nb[2 * ax + 1], y2 = fabs(bv);
+      const double y1 = nb[2 * ax + 1], y3 = nb[2 * ax], y2 = fabs(bv);
       frac_idx[po * 3 + ax] = (double)b3[ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
     }
   }
@@ -1704,22 +1841,14 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
     if (smem2 <= ctx->prop.sharedMemPerBlockOptin && L >= 1) {
       const int nch = Y.nchunk;
       void* part = nullptr;
-      FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * nch * (8 + 4 + 48) + 64, &part));
+      FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * nch * (8 + 4) + 64, &part));
       Iso2Out o2;
       o2.part_val = (double*)part;
-      o2.part_nb = o2.part_val + (size_t)npairs * norient * nch;
-      o2.part_idx = (int*)(o2.part_nb + (size_t)npairs * norient * nch * 6);
+      o2.part_idx = (int*)(o2.part_val + (size_t)npairs * norient * nch);
       o2.grid = d_grid;
-      o2.dbg = nullptr;
       void* ipk = nullptr;
       FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * Y.ipk * 16, &ipk));
       const double2* d_Ipk = (const double2*)ipk;
-      if (getenv("FO_DEBUG_TIMING")) {
-        void* dbg = nullptr;
-        FO_CHECK(fo_scratch(ctx, FO_SCR_DBG, 64, &dbg));
-        FO_CUDA(ctx, cudaMemsetAsync(dbg, 0, 64, ctx->stream));
-        o2.dbg = (long long*)dbg;
-      }
       int per = ctx->prop.multiProcessorCount / nch;
       if (per < 1) per = 1;
       if ((int64_t)per > npairs) per = (int)npairs;
@@ -1748,19 +1877,11 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       if (KSq == 4 && NTq == 2 && nyq) FO_I2_LAUNCH(4, 2, true);        // Jmax 13, 15
       else if (KSq == 2 && NTq == 1 && nyq) FO_I2_LAUNCH(2, 1, true);   // Jmax 7
       else if (KSq == 3 && NTq == 2 && !nyq) FO_I2_LAUNCH(3, 2, false); // Jmax 9, 11
-      else if (KSq == 6 && NTq == 3 && !nyq) FO_I2_LAUNCH(6, 3, false); // Jmax 21
       else goto generic_path;
 #undef FO_I2_LAUNCH
       FO_LAUNCH_CHECK(ctx);
-      if (o2.dbg) {
-        long long h[8];
-        FO_CUDA(ctx, cudaMemcpyAsync(h, o2.dbg, 64, cudaMemcpyDeviceToHost, ctx->stream));
-        FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "[isoft2 CTA0 cycles] wait/load %lld  K5 %lld  stageA %lld  stageB %lld  reduce+nb %lld\n",
-                h[0], h[1], h[2], h[3], h[4]);
-      }
       sph_final2_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
-          d_Ihalf, ctx->wig.d_table, L, norient, nch, o2.part_val, o2.part_idx, o2.part_nb, d_best_idx,
+          d_Ihalf, ctx->wig.d_table, L, norient, nch, o2.part_val, o2.part_idx, d_best_idx,
           d_best_val, d_frac);
       FO_LAUNCH_CHECK(ctx);
       return FO_OK;
@@ -1880,24 +2001,33 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
     FO_LAUNCH_CHECK(ctx);
     return FO_OK;
   }
+  dim3 grid((unsigned)(L + 1), (unsigned)np);
+  const size_t smem_mma = direct_mma_smem(natoms, L);
+  if (!ctx->force_generic && smem_mma <= 110 * 1024) {
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+    sph_direct_mma_kernel<<<grid, DS_THREADS, smem_mma, ctx->stream>>>(YA, YB, Bes, (int)natoms, L, d_Ihalf);
+    FO_LAUNCH_CHECK(ctx);
+    return FO_OK;
+  }
   const size_t smem = ((size_t)(L + 1) * DIR_TK * 2 + (size_t)(2 * L + 1) * (L + 1)) * 16;
   FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)(L + 1), (unsigned)np);
   sph_direct_kernel<<<grid, 128, smem, ctx->stream>>>(YA, YB, Bes, (int)natoms, L, d_Ihalf);
   FO_LAUNCH_CHECK(ctx);
   return FO_OK;
 }
 
-size_t direct_work_bytes(int64_t np, int64_t natoms, int L) {
+size_t direct_work_bytes(const fo_ctx* ctx, int64_t np, int64_t natoms, int L) {
   const size_t NLM = nlm_of(L);
-  // YA, YB | RA, RB | Bes | T, C2 (tensor-core path for large clusters; reserved unconditionally)
-  return (size_t)np * natoms * NLM * 32 + (size_t)np * natoms * 16 +
-         (size_t)np * (L + 1) * natoms * natoms * 8 + (size_t)np * 2 * NLM * natoms * 8 +
-         (size_t)np * dg_c2_off(L + 1) * 8 + 256;
+  // YA, YB | RA, RB | Bes | T, C2 (GEMM path for large clusters only)
+  size_t b = (size_t)np * natoms * NLM * 32 + (size_t)np * natoms * 16 +
+             (size_t)np * (L + 1) * natoms * natoms * 8 + 256;
+  if (natoms >= ctx->direct_gemm_min)
+    b += (size_t)np * 2 * NLM * natoms * 8 + (size_t)np * dg_c2_off(L + 1) * 8;
+  return b;
 }
 
-int64_t direct_chunk(int64_t npairs, int64_t natoms, int L, bool want_grid) {
-  const size_t per = direct_work_bytes(1, natoms, L) + ihalf_elems(L) * 16;
+int64_t direct_chunk(const fo_ctx* ctx, int64_t npairs, int64_t natoms, int L, bool want_grid) {
+  const size_t per = direct_work_bytes(ctx, 1, natoms, L) + ihalf_elems(L) * 16;
   // 1 GB of scratch per chunk; large clusters / bandwidths (> 256 MB per pair) get 4 GB
   const size_t budget = per > ((size_t)256 << 20) ? (size_t)4 << 30 : (size_t)1 << 30;
   int64_t c = (int64_t)(budget / per);
@@ -2031,11 +2161,11 @@ extern "C" int fo_sph_coeffs_direct(fo_ctx* ctx, const double* posA, const doubl
   int* d_gid = nullptr;
   FO_CHECK(upload_gid(ctx, natoms, &d_gid));
   const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
-  int64_t chunk = direct_chunk(npairs, natoms, L, false);
+  int64_t chunk = direct_chunk(ctx, npairs, natoms, L, false);
   void *dA, *dB, *work, *dhalf, *dfull, *dst;
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * natoms * 24, &dA));
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, (size_t)chunk * natoms * 24, &dB));
-  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(chunk, natoms, L), &work));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(ctx, chunk, natoms, L), &work));
   FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
   FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
   FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 4 + 64, &dst));
@@ -2072,9 +2202,9 @@ extern "C" int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const d
   int* d_gid = nullptr;
   FO_CHECK(upload_gid(ctx, natoms, &d_gid));
   const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
-  const int64_t chunk = direct_chunk(npairs, natoms, L, false);
+  const int64_t chunk = direct_chunk(ctx, npairs, natoms, L, false);
   void *work, *dhalf;
-  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(chunk, natoms, L), &work));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(ctx, chunk, natoms, L), &work));
   FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
   if (d_status) FO_CUDA(ctx, cudaMemsetAsync(d_status, 0, (size_t)npairs * 4, ctx->stream));
   for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
@@ -2101,7 +2231,7 @@ extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double*
   FO_CUDA(ctx, cudaSetDevice(ctx->device));
   const int L = (int)Jmax, O = invert ? 2 : 1;
   const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
-  const int64_t chunk = direct_chunk(npairs, natoms, L, grid_out != nullptr);
+  const int64_t chunk = direct_chunk(ctx, npairs, natoms, L, grid_out != nullptr);
   const size_t pos_bytes = (size_t)chunk * natoms * 24;
   void *dA, *dB, *dout, *dgrid = nullptr, *hA, *hB;
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, 2 * pos_bytes, &dA));

@@ -66,7 +66,7 @@ int64_t fo_launch_count(const fo_ctx* ctx);
 
 /* Library options.  "force_generic" (0/1): use the any-size kernels instead of the shared-memory
  * tensor-core fast paths (testing: both families must give the same results).
- * "direct_gemm_min_atoms" (default 96): clusters with at least this many atoms compute the direct
+ * "direct_gemm_min_atoms" (default 64): clusters with at least this many atoms compute the direct
  * coefficients (fo_sph_coeffs_direct / fo_sph_align_pairs) with the tensor-core GEMM kernels. */
 int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
 

@@ -310,14 +310,14 @@ def test_direct_coeffs_tensor_core_gemm(ctx, N, J, groups, force):
         perm = [np.arange(o[i], o[i + 1]) for i in range(len(groups))]
     ctx.set_perm(perm if perm else [np.arange(N)], N)
     try:
-        ctx.set_option("direct_gemm_min_atoms", 1 if force else 96)
+        ctx.set_option("direct_gemm_min_atoms", 1 if force else 64)
         I, _ = ctx.sph_coeffs_direct(A, B, J, 0.5)
         res = ctx.sph_align_pairs(A, B, J, 0.5, invert=True)
         ctx.set_option("direct_gemm_min_atoms", 1 << 30)
         I0, _ = ctx.sph_coeffs_direct(A, B, J, 0.5)
         res0 = ctx.sph_align_pairs(A, B, J, 0.5, invert=True)
     finally:
-        ctx.set_option("direct_gemm_min_atoms", 96)
+        ctx.set_option("direct_gemm_min_atoms", 64)
         ctx.set_perm([np.arange(N)], N)
     for p in range(P):
         assert rel(I[p], oracle.sph_coeffs_direct(A[p], B[p], J, 0.5, perm)) < 1e-12
