@@ -976,12 +976,13 @@ per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout
 // ------------------------------------------------------------------------------------------
 constexpr int X4_THREADS = 512;
 constexpr int X4_WARPS = X4_THREADS / 32;
+constexpr int X4_YS = 3, X4_ZS = 4;  // tiles per warp and slab group in stages Y / Z (upper bounds)
 
 struct X4Layout {
   int M, W, H, FP, RX, RXp, RY, K2, SPI;
-  int o_damp, o_red, o_xz, o_yin, total;  // in doubles
+  int o_red, o_x, o_yin, o_z, total;  // in doubles
   X4Layout() {}
-  X4Layout(int n, int F) {
+  X4Layout(int n, int F, size_t smem_limit_bytes) {
     M = n + 1;
     W = 2 * n + 1;
     H = F / 2 + 1;
@@ -990,87 +991,143 @@ struct X4Layout {
     RXp = ((RX + 7) / 16) * 16 + 8;
     RY = 2 * M;
     K2 = 2 * n + 1;
-    const int xin = 2 * M * RXp, zslab = 2 * M * FP;
+    o_red = 0;
+    o_x = 64;
+    o_yin = o_x + 2 * M * RXp;
+    o_z = o_yin + F * K2 * RY;
+    // slabs per iteration: as many as fit (at most 10), without a short last iteration
     SPI = 10;
-    while (SPI > 1 && (F + SPI - 1) / SPI == (F + SPI - 2) / (SPI - 1)) --SPI;
-    const int xz = xin > zslab * SPI ? xin : zslab * SPI;
-    o_damp = 0;
-    o_red = o_damp + ((3 * W + 1) & ~1);
-    o_xz = o_red + 64;
-    o_yin = o_xz + xz;
-    total = o_yin + F * K2 * RY;
+    while (SPI > 1 && (size_t)(o_z + zin_per_slab() * SPI) * 8 > smem_limit_bytes) --SPI;
+    SPI &= ~1;  // two half-CTA pipelines of SPI / 2 slabs each
+    if (SPI < 2) SPI = 2;
+    while (SPI > 2 && (F + SPI / 2 - 1) / (SPI / 2) == (F + SPI / 2 - 2) / (SPI / 2 - 1)) SPI -= 2;  // same #groups
+    // tiles per warp (8 warps per half) must fit the unrolled slots: X4_YS = 3, X4_ZS = 4
+    while (SPI > 2 && ((SPI / 2) * RY > 3 * 64 || (SPI / 2) * F > 4 * 64)) SPI -= 2;
+    total = o_z + zin_per_slab() * SPI;
+    if ((SPI / 2) * RY > 3 * 64 || (SPI / 2) * F > 4 * 64) total = 1 << 30;  // does not fit: other kernels
   }
   __host__ __device__ int zin_per_slab() const { return 2 * M * FP; }
+  __host__ __device__ int ximg_doubles() const { return 2 * M * RXp; }
 };
 
-template <int KS, int NT, bool WANT_GRID>
-__global__ void __launch_bounds__(X4_THREADS, 1)
-per_xf4_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ bankA,
-               const double2* __restrict__ bankB, const long long* __restrict__ pairs, int npairs,
-               int ngroups, int n, int F, double kx, double ky, double kz, double sigma, XfOut out) {
-  extern __shared__ double sm4[];
-  const int M = L.M, W = L.W, H = L.H, FP = L.FP, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
-  const int SPI = L.SPI;
-  double* damp = sm4 + L.o_damp;
-  double* red = sm4 + L.o_red;
-  double* XE = sm4 + L.o_xz;            // [M][RXp] (index 0: c0)
-  double* XO = XE + (size_t)M * RXp;    // [M][RXp] (index 0 unused)
-  double* ZIN = XE;                     // aliases the stage-X input: [SPI][2][M][FP]
-  double* YIN = sm4 + L.o_yin;          // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t4 = lane & 3;
-
-  SymMma<KS, NT> mm;
-  mm.init(n, F, H, lane);
-  for (int t = tid; t < 3 * W; t += X4_THREADS) {
+// Cross-spectrum of one pair in the E/O form stage X consumes (a10, periodicAlignment.py:433-438 /
+// fastbulk.f90:441-454,667-683): C[k] = sum_g SA_g[k] conj(SB_g[k]) exp(-|k|^2 sigma^2), then for
+// +-kx: E = C(+) + C(-), O = C(+) - C(-), written as the shared-memory image [E | O][kx = 0..n][RXp]
+// of per_xf4_kernel.  This is the only phase that reads the structure-factor bank (231 KB per
+// BLJ256 pair from HBM); it used to be phase 1 of the transform kernel, where ncu showed its load
+// latency exposed (one CTA per SM) -- as a separate kernel it runs at full occupancy and the
+// transform kernel prefetches the 65 KB image of its next pair with cp.async.
+__global__ void __launch_bounds__(256, 4)
+per_cross_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ bankA,
+                 const double2* __restrict__ bankB, const long long* __restrict__ pairs, int ngroups, int n,
+                 double kx, double ky, double kz, double sigma, double* __restrict__ ximg) {
+  __shared__ double damp[3 * 129];
+  const int M = L.M, W = L.W, RXp = L.RXp;
+  const int tid = threadIdx.x;
+  const size_t pair = blockIdx.x;
+  for (int t = tid; t < 3 * W; t += blockDim.x) {
     const int ax = t / W, m = t - ax * W - n;
     const double k = (ax == 0 ? kx : (ax == 1 ? ky : kz)) * (double)m;
     damp[t] = exp(-(k * k) * (sigma * sigma));
   }
   __syncthreads();
-
   const size_t c_elems = (size_t)W * W * M;
   const size_t bank_stride = (size_t)ngroups * c_elems;
-  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-    const long long ia = pairs ? pairs[2 * pair] : pair;
-    const long long ib = pairs ? pairs[2 * pair + 1] : pair;
-    const double2* SA = bankA + (size_t)ia * bank_stride;
-    const double2* SB = bankB + (size_t)ib * bank_stride;
-    // ---- phase 1: cross spectrum in E/O form
-    for (int item = tid; item < M * W * M; item += X4_THREADS) {
-      const int l = item % M;
-      const int iy = (item / M) % W;
-      const int i = item / (M * W);
-      const size_t ep = ((size_t)(n + i) * W + iy) * M + l, em = ((size_t)(n - i) * W + iy) * M + l;
-      double pr = 0.0, pi = 0.0, mr = 0.0, mi = 0.0;
-      for (int gq = 0; gq < ngroups; ++gq) {
-        const double2 a = SA[(size_t)gq * c_elems + ep], b = SB[(size_t)gq * c_elems + ep];
-        pr += a.x * b.x + a.y * b.y;
-        pi += a.y * b.x - a.x * b.y;
-        if (i) {
-          const double2 a2 = SA[(size_t)gq * c_elems + em], b2 = SB[(size_t)gq * c_elems + em];
-          mr += a2.x * b2.x + a2.y * b2.y;
-          mi += a2.y * b2.x - a2.x * b2.y;
-        }
-      }
-      const double dmp = damp[n + i] * damp[W + iy] * damp[2 * W + n + l];
-      pr *= dmp; pi *= dmp; mr *= dmp; mi *= dmp;
-      const int j = iy >= n ? iy - n : n - iy;
-      const int s = iy >= n ? 0 : 1;
-      const int row = ((j * M + l) * 2 + s) * 2;
-      double er, ei, orr, oi;
-      if (i == 0) {
-        er = pr; ei = pi; orr = 0.0; oi = 0.0;
-      } else {
-        er = pr + mr; ei = pi + mi; orr = pr - mr; oi = pi - mi;
-      }
-      *reinterpret_cast<double2*>(XE + (size_t)i * RXp + row) = make_double2(er, ei);
-      *reinterpret_cast<double2*>(XO + (size_t)i * RXp + row) = make_double2(orr, oi);
-      if (j == 0) {  // ky = 0 has no s = 1 partner: keep those rows finite (their output is unused)
-        *reinterpret_cast<double2*>(XE + (size_t)i * RXp + row + 2) = make_double2(er, ei);
-        *reinterpret_cast<double2*>(XO + (size_t)i * RXp + row + 2) = make_double2(orr, oi);
+  const long long ia = pairs ? pairs[2 * pair] : (long long)pair;
+  const long long ib = pairs ? pairs[2 * pair + 1] : (long long)pair;
+  const double2* SA = bankA + (size_t)ia * bank_stride;
+  const double2* SB = bankB + (size_t)ib * bank_stride;
+  double* XE = ximg + pair * (size_t)L.ximg_doubles();
+  double* XO = XE + (size_t)M * RXp;
+  for (int item = tid; item < M * W * M; item += blockDim.x) {
+    const int l = item % M;
+    const int iy = (item / M) % W;
+    const int i = item / (M * W);
+    const size_t ep = ((size_t)(n + i) * W + iy) * M + l, em = ((size_t)(n - i) * W + iy) * M + l;
+    double pr = 0.0, pi = 0.0, mr = 0.0, mi = 0.0;
+    for (int gq = 0; gq < ngroups; ++gq) {
+      const double2 a = SA[(size_t)gq * c_elems + ep], b = SB[(size_t)gq * c_elems + ep];
+      pr += a.x * b.x + a.y * b.y;
+      pi += a.y * b.x - a.x * b.y;
+      if (i) {
+        const double2 a2 = SA[(size_t)gq * c_elems + em], b2 = SB[(size_t)gq * c_elems + em];
+        mr += a2.x * b2.x + a2.y * b2.y;
+        mi += a2.y * b2.x - a2.x * b2.y;
       }
     }
+    const double dmp = damp[n + i] * damp[W + iy] * damp[2 * W + n + l];
+    pr *= dmp; pi *= dmp; mr *= dmp; mi *= dmp;
+    const int j = iy >= n ? iy - n : n - iy;
+    const int s = iy >= n ? 0 : 1;
+    const int row = ((j * M + l) * 2 + s) * 2;
+    double er, ei, orr, oi;
+    if (i == 0) {
+      er = pr; ei = pi; orr = 0.0; oi = 0.0;
+    } else {
+      er = pr + mr; ei = pi + mi; orr = pr - mr; oi = pi - mi;
+    }
+    *reinterpret_cast<double2*>(XE + (size_t)i * RXp + row) = make_double2(er, ei);
+    *reinterpret_cast<double2*>(XO + (size_t)i * RXp + row) = make_double2(orr, oi);
+    if (j == 0) {  // ky = 0 has no s = 1 partner: keep those rows finite (their output is unused)
+      *reinterpret_cast<double2*>(XE + (size_t)i * RXp + row + 2) = make_double2(er, ei);
+      *reinterpret_cast<double2*>(XO + (size_t)i * RXp + row + 2) = make_double2(orr, oi);
+    }
+  }
+}
+
+template <int KS, int NT, bool WANT_GRID>
+__global__ void __launch_bounds__(X4_THREADS, 1)
+per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ ximg, int npairs, int n, int F,
+               XfOut out) {
+  extern __shared__ double sm4[];
+  const int M = L.M, H = L.H, FP = L.FP, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
+  const int SPI = L.SPI;
+  double* red = sm4 + L.o_red;
+  double* XE = sm4 + L.o_x;             // [M][RXp] (index 0: c0)
+  double* XO = XE + (size_t)M * RXp;    // [M][RXp] (index 0 unused)
+  double* YIN = sm4 + L.o_yin;          // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
+  double* ZIN = sm4 + L.o_z;            // [SPI][2][M][FP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  // stage-X input image of a pair (per_cross_kernel) -> shared memory, asynchronously
+  auto stage_x = [&](int pr) {
+    const double2* src = reinterpret_cast<const double2*>(ximg + (size_t)pr * L.ximg_doubles());
+    double2* dst = reinterpret_cast<double2*>(XE);
+    for (int e = tid; e < M * RXp; e += X4_THREADS) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + e);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < npairs) stage_x(blockIdx.x);
+  SymMma<KS, NT> mm;
+  mm.init(n, F, H, lane);
+  // phase-3 geometry of this warp's tiles (the same for every slab group and pair)
+  const int half = warp >> 3, wq = warp & 7;
+  const int SPH = SPI >> 1;  // slabs per group of one half (the layout keeps SPI even)
+  double* Zh = ZIN + (size_t)half * SPH * L.zin_per_slab();
+  unsigned long long* sbest = reinterpret_cast<unsigned long long*>(red + 48);
+  int y_off[X4_YS], zrow_off[X4_YS], z_off[X4_ZS];
+#pragma unroll
+  for (int sI = 0; sI < X4_YS; ++sI) {
+    int r = (wq + 8 * sI) * 8 + g;
+    if (r >= SPH * RY) r = 0;
+    const int sl = r / RY, lp = r - sl * RY;
+    y_off[sI] = sl * K2 * RY + lp;
+    zrow_off[sI] = sl * L.zin_per_slab() + (lp & 1) * M * FP + (lp >> 1) * FP;
+  }
+#pragma unroll
+  for (int sI = 0; sI < X4_ZS; ++sI) {
+    int r = (wq + 8 * sI) * 8 + g;
+    if (r >= SPH * F) r = (wq + 8 * sI) * 8 < SPH * F ? (wq + 8 * sI) * 8 : 0;
+    const int sl = r / F, dy = r - sl * F;
+    z_off[sI] = sl * L.zin_per_slab() + dy;
+  }
+
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    if (tid == 0) *sbest = 0ull;  // +0.0: |f| >= 0, and only strictly smaller tiles are filtered
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // ---- phase 2: stage X; tile = 8 rows; row bits: 0 = part, 1 = s  (partners: lane ^ 4, lane ^ 8)
     for (int tile = warp; tile * 8 < RX; tile += X4_WARPS) {
@@ -1103,20 +1160,28 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ b
         }
     }
     __syncthreads();
-    // ---- phase 3: slabs, SPI at a time
-    double bv = -1.0;
+    if (pair + (int)gridDim.x < npairs) stage_x(pair + gridDim.x);  // lands during phase 3
+    // ---- phase 3: slabs.  The two halves of the CTA (8 warps each, named barriers 1 and 2) run their
+    // own Y -> Z pipelines on alternating groups of SPH slabs, each in its own half of ZIN: a half
+    // waiting at its barrier leaves the tensor pipe to the other one (ncu on the single-pipeline
+    // version: 20 % of the samples at CTA-wide barriers).
+    // Arg-max at half scale: accumulators start at v0/2, the two outputs of a column are
+    // 2 |A + B| and 2 |A - B|, their maximum is 2 (|A| + |B|): one DADD + one max per column.  Only a
+    // tile that beats both the thread's and the CTA's running maximum (sbest: shared, monotone,
+    // read early as a filter) is examined column by column.
+    double bvh = -1.0;
     int bi = 0x7fffffff;
-    for (int x0 = 0; x0 < F; x0 += SPI) {
-      const int ns = min(SPI, F - x0);
+    for (int x0 = half * SPH; x0 < F; x0 += 2 * SPH) {
+      const int ns = min(SPH, F - x0);
       // stage Y: rows (slab, l, part)
-      for (int tile = warp; tile * 8 < ns * RY; tile += X4_WARPS) {
-        const int row = tile * 8 + g;
+#pragma unroll
+      for (int sI = 0; sI < X4_YS; ++sI) {
+        const int row = (wq + 8 * sI) * 8 + g;
+        if ((wq + 8 * sI) * 8 >= ns * RY) break;
         const bool valid = row < ns * RY;
-        const int r = valid ? row : 0;
-        const int sl = r / RY, lp = r - sl * RY;
-        const int l = lp >> 1, part = lp & 1;
-        const double* Y = YIN + (size_t)(x0 + sl) * K2 * RY + lp;
-        double* Zrow = ZIN + (size_t)sl * L.zin_per_slab() + (size_t)part * M * FP + (size_t)l * FP;
+        const int part = y_off[sI] & 1;
+        const double* Y = YIN + (size_t)x0 * K2 * RY + y_off[sI];
+        double* Zrow = Zh + zrow_off[sI];
         const double sgn = part ? -1.0 : 1.0;
         double P[NT][2], Q[NT][2];
         mm.run(Y + RY - g, Y + (size_t)(n + 1) * RY - g, RY, n, Y[0], lane, P, Q);
@@ -1133,52 +1198,55 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ b
             }
           }
       }
-      __syncthreads();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(X4_THREADS / 2) : "memory");
       // stage Z: rows (slab, dy)
-      for (int tile = warp; tile * 8 < ns * F; tile += X4_WARPS) {
-        const int row = tile * 8 + g;
-        const bool valid = row < ns * F;
-        const int r = valid ? row : 0;
-        const int sl = r / F, dy = r - sl * F;
-        const int dx = x0 + sl;
-        const double* ZR = ZIN + (size_t)sl * L.zin_per_slab() + dy;
+#pragma unroll
+      for (int sI = 0; sI < X4_ZS; ++sI) {
+        const int r0 = (wq + 8 * sI) * 8;
+        if (r0 >= ns * F) break;
+        const bool valid = r0 + g < ns * F;
+        const int r = valid ? r0 + g : r0;
+        const double sb = __longlong_as_double(*sbest);
+        const double* ZR = Zh + z_off[sI];
         const double* ZI = ZR + (size_t)M * FP;
-        const int base = (dx * F + dy) * F;
-        const double v0 = ZR[0];
+        const int base = (x0 * F + r) * F;
+        const double v0h = 0.5 * ZR[0];
         double A[NT][2], B[NT][2];
-        mm.run(ZR + FP - g, ZI + FP - g, FP, n, 0.0, lane, A, B);
-        double g1[NT][2], g2[NT][2];
-        double cmax = -2.0;  // below the bv sentinel (-1): NaN rows never enter the update
+        mm.run(ZR + FP - g, ZI + FP - g, FP, n, v0h, lane, A, B);
+        double cmax = -2.0;  // below the bvh sentinel (-1): NaN rows never enter the update
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int d = nt * 8 + t4 * 2 + q;
-            const double a = fma(2.0, A[nt][q], v0), b = 2.0 * B[nt][q];
-            g1[nt][q] = (valid && d < H) ? fabs(a + b) : -2.0;
-            g2[nt][q] = (valid && d < H && d != 0 && 2 * d != F) ? fabs(a - b) : -2.0;
-            cmax = fmax(cmax, fmax(g1[nt][q], g2[nt][q]));
+            const double c = fabs(A[nt][q]) + fabs(B[nt][q]);
+            if ((nt + 1) * 8 <= H || d < H) cmax = fmax(cmax, c);
             if (WANT_GRID) {
               if (valid && d < H) {
                 double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
-                grow[d] = g1[nt][q];
-                if (d != 0 && 2 * d != F) grow[F - d] = g2[nt][q];
+                grow[d] = 2.0 * fabs(A[nt][q] + B[nt][q]);
+                if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * fabs(A[nt][q] - B[nt][q]);
               }
             }
           }
-        if (cmax > bv || (cmax == bv && base < bi)) {  // rare once bv has converged
+        if (valid && cmax >= sb && (cmax > bvh || (cmax == bvh && base < bi))) {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int d = nt * 8 + t4 * 2 + q;
-              better32(bv, bi, g1[nt][q], base + d);
-              better32(bv, bi, g2[nt][q], base + (F - d));
+              const double g1 = d < H ? fabs(A[nt][q] + B[nt][q]) : -2.0;
+              const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[nt][q] - B[nt][q]) : -2.0;
+              better32(bvh, bi, g1, base + d);
+              better32(bvh, bi, g2, base + (F - d));
             }
+          if (bvh > sb) atomicMax(sbest, (unsigned long long)__double_as_longlong(bvh));
         }
       }
-      __syncthreads();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(X4_THREADS / 2) : "memory");
     }
+    double bv = 2.0 * bvh;
+    if (bvh < 0.0) bv = -1.0;
     // ---- phase 4: block arg-max (numpy order) and parabola neighbours
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -1261,7 +1329,7 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ b
       }
       if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
     }
-    __syncthreads();
+    // no barrier here: the barrier at the top of the loop orders the reuse of red / YIN
   }
 }
 
@@ -1359,7 +1427,7 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   if ((int64_t)blocks > npairs) blocks = (int)npairs;
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
   {  // tensor-core path: everything resident in shared memory, 1-D transforms as DMMA tiles
-    const X4Layout lay4(n, F);
+    const X4Layout lay4(n, F, optin);
     const size_t smem4 = (size_t)lay4.total * 8;
     const int KS = (n + 3) / 4, NT = (lay4.H + 7) / 8;
 #define FO_X4_LAUNCH(KS_, NT_)                                                                           \
@@ -1368,18 +1436,23 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
       FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<KS_, NT_, true>,                                  \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));       \
       per_xf4_kernel<KS_, NT_, true><<<blocks, X4_THREADS, smem4, ctx->stream>>>(                        \
-          lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);       \
+          lay4, (const double*)ximg, (int)npairs, n, F, out);                                            \
     } else {                                                                                             \
       FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<KS_, NT_, false>,                                 \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));       \
       per_xf4_kernel<KS_, NT_, false><<<blocks, X4_THREADS, smem4, ctx->stream>>>(                       \
-          lay4, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);       \
+          lay4, (const double*)ximg, (int)npairs, n, F, out);                                            \
     }                                                                                                    \
   } while (0)
     const int code = KS * 10 + NT;
-    if (smem4 <= optin && !ctx->force_generic &&
+    if (smem4 <= optin && !ctx->force_generic && 2 * n + 1 <= 129 &&
         (code == 11 || code == 12 || code == 22 || code == 23 || code == 33)) {
+      void* ximg = nullptr;
+      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay4.ximg_doubles() * 8, &ximg));
       fo_prof_scope prof(ctx, FO_PROF_PER_XF);
+      per_cross_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay4, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
+                                                                ky, kz, p->sigma, (double*)ximg);
+      FO_LAUNCH_CHECK(ctx);
       if (code == 11) FO_X4_LAUNCH(1, 1);
       else if (code == 12) FO_X4_LAUNCH(1, 2);
       else if (code == 22) FO_X4_LAUNCH(2, 2);
