@@ -91,6 +91,16 @@ SIGNATURES = {
                                          ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
     "fo_sph_wigner_table": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p]),
+    "fo_grid_find_peaks": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_i64p, ctypes.c_int64,
+                                          ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    "fo_grid_find_peaks_dev": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_i64p, ctypes.c_int64,
+                                              ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fo_sph_isoft_peaks": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fo_per_align_pairs_peaks": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
+                                                ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "fo_host_refine_periodic": (ctypes.c_int, [ctypes.POINTER(PerParams), c_void_p, ctypes.c_int64, c_void_p,
                                                c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int,
                                                ctypes.c_int, c_void_p, c_void_p, c_void_p]),
@@ -242,7 +252,7 @@ class Context(object):
     def reset_stream(self):
         self._check(self._lib.fo_reset_stream(self._h), "fo_reset_stream")
 
-    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "k6", "k7")
+    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "peaks", "k7")
 
     def profile_begin(self):
         self._check(self._lib.fo_profile_begin(self._h), "fo_profile_begin")
@@ -419,6 +429,51 @@ class Context(object):
         im = np.empty((P, n, n, n), np.float64) if want_imag else None
         self._check(self._lib.fo_sph_isoft(self._h, _ptr(Ilmm), P, L, _ptr(re), _ptr(im)), "fo_sph_isoft")
         return re + 1j * im if want_imag else re
+
+    # -- top-k peaks (a8), on the device
+    @staticmethod
+    def _peak_outputs(P, npeaks):
+        return (np.empty((P, npeaks, 3), np.float64), np.empty((P, npeaks), np.float64),
+                np.empty((P, npeaks), np.float64), np.empty((P, npeaks, 6), np.float64),
+                np.zeros(P, np.int32))
+
+    def grid_find_peaks(self, grids, npeaks=10, width=2, want_residual=False):
+        """findPeaks (utils.py:366-396) of P grids (P, n0, n1, n2) on the device ->
+        (peaks (P,k,3), amplitude (P,k), mean (P,k), alpha (P,k,6), nfound (P,), residual|None)."""
+        grids = np.ascontiguousarray(grids, dtype=np.float64)
+        if grids.ndim == 3:
+            grids = grids[None]
+        P = grids.shape[0]
+        shape = np.array(grids.shape[1:], np.int64)
+        pk, amp, mean, alpha, nf = self._peak_outputs(P, npeaks)
+        res = np.empty_like(grids) if want_residual else None
+        self._check(self._lib.fo_grid_find_peaks(self._h, _ptr(grids), P, shape.ctypes.data_as(c_i64p),
+                                                 int(npeaks), int(width), _ptr(pk), _ptr(amp), _ptr(mean),
+                                                 _ptr(alpha), _ptr(nf), _ptr(res)), "fo_grid_find_peaks")
+        return pk, amp, mean, alpha, nf, res
+
+    def sph_isoft_peaks(self, Ilmm, Jmax, npeaks=10, width=2):
+        """Coefficients -> overlap grid -> top-npeaks peaks, all on the device (findRotations)."""
+        L = int(Jmax)
+        Ilmm = np.ascontiguousarray(Ilmm, dtype=np.complex128).reshape(-1, L + 1, 2 * L + 1, 2 * L + 1)
+        P = Ilmm.shape[0]
+        pk, amp, mean, alpha, nf = self._peak_outputs(P, npeaks)
+        self._check(self._lib.fo_sph_isoft_peaks(self._h, _ptr(Ilmm), P, L, int(npeaks), int(width), _ptr(pk),
+                                                 _ptr(amp), _ptr(mean), _ptr(alpha), _ptr(nf)),
+                    "fo_sph_isoft_peaks")
+        return pk, amp, mean, alpha, nf
+
+    def per_align_pairs_peaks(self, params, posA, posB, npeaks=10, width=2):
+        """Positions -> |f| grid -> top-npeaks displacements (fractional grid indices), on the device."""
+        self._ensure_perm(params.natoms)
+        posA = _f64(posA).reshape(-1, params.natoms, 3)
+        posB = _f64(posB).reshape(-1, params.natoms, 3)
+        P = posA.shape[0]
+        pk, amp, mean, alpha, nf = self._peak_outputs(P, npeaks)
+        self._check(self._lib.fo_per_align_pairs_peaks(self._h, ctypes.byref(params), _ptr(posA), _ptr(posB), P,
+                                                       int(npeaks), int(width), _ptr(pk), _ptr(amp), _ptr(mean),
+                                                       _ptr(alpha), _ptr(nf)), "fo_per_align_pairs_peaks")
+        return pk, amp, mean, alpha, nf
 
     def sph_coeffs_direct(self, posA, posB, Jmax, sigma):
         posA = _f64(posA)

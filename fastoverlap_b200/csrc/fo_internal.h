@@ -72,6 +72,7 @@ enum {
   FO_SCR_MISC = 7,
   FO_SCR_IPK = 8,
   FO_SCR_DBG = 9,
+  FO_SCR_PEAKS = 10,
 };
 
 struct fo_bank {
@@ -96,6 +97,16 @@ bool fo_is_pinned(const void* p);
 void fo_host_copy(void* dst, const void* src, size_t bytes);
 // make sure a permutation (at least the trivial one) exists for natoms atoms
 int fo_ensure_perm(fo_ctx* ctx, int64_t natoms);
+
+// top-k peak extraction on device grids (fo_peaks.cu); grids are updated in place
+int fo_peaks_run_dev(fo_ctx* ctx, double* d_grids, int64_t P, const int64_t shape[3], int64_t npeaks,
+                     int64_t width, double* d_peaks, double* d_amp, double* d_mean, double* d_alpha,
+                     int32_t* d_nfound);
+int fo_peaks_outputs(fo_ctx* ctx, int64_t np, int64_t npeaks, double** pk, double** amp, double** mean,
+                     double** alpha, int32_t** nf);
+int fo_peaks_copy_out(fo_ctx* ctx, int64_t p0, int64_t np, int64_t npeaks, const double* pk, const double* amp,
+                      const double* mean, const double* alpha, const int32_t* nf, double* peaks,
+                      double* amplitude, double* meanv, double* alphav, int32_t* nfound);
 
 // RAII bracket: records an event pair around a kernel launch when profiling is on
 struct fo_prof_scope {

@@ -1693,6 +1693,52 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
   return FO_OK;
 }
 
+// a8 fused: positions -> F^3 |f| grid on the device -> top-npeaks displacements; the grid never
+// leaves HBM (findDisps with npeaks > 1, periodicAlignment.py:442-451).
+extern "C" int fo_per_align_pairs_peaks(fo_ctx* ctx, const fo_per_params* p, const double* posA,
+                                        const double* posB, int64_t npairs, int64_t npeaks, int64_t width,
+                                        double* peaks, double* amplitude, double* mean, double* alpha,
+                                        int32_t* nfound) {
+  FO_CHECK(check_params(ctx, p));
+  if (npairs < 0 || (npairs > 0 && (!posA || !posB || !peaks || !amplitude || !nfound)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs_peaks: NULL argument");
+  if (npeaks < 1 || npeaks > 64 || width < 1 || width > 4)
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs_peaks: npeaks in 1..64, width in 1..4");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  FO_CHECK(fo_ensure_perm(ctx, p->natoms));
+  const size_t per_struct = bank_elems_per_struct(ctx, p);
+  const int64_t chunk = chunk_pairs(ctx, p, npairs, true);
+  const size_t pos_bytes = (size_t)chunk * p->natoms * 3 * 8;
+  const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
+  const int64_t shape[3] = {p->nfspace, p->nfspace, p->nfspace};
+  void *bank, *dA, *dB, *dOut, *dGrid;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, pos_bytes, &dA));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, pos_bytes, &dB));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
+  double *pk, *amp, *mn, *al;
+  int32_t* nf;
+  FO_CHECK(fo_peaks_outputs(ctx, chunk, npeaks, &pk, &amp, &mn, &al, &nf));
+  double2* bankA = (double2*)bank;
+  double2* bankB = bankA + (size_t)chunk * per_struct;
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    const size_t nb = (size_t)np * p->natoms * 3 * 8;
+    FO_CUDA(ctx, cudaMemcpyAsync(dA, posA + (size_t)p0 * p->natoms * 3, nb, cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(dB, posB + (size_t)p0 * p->natoms * 3, nb, cudaMemcpyHostToDevice, ctx->stream));
+    FO_CHECK(launch_sf(ctx, p, (const double*)dA, np, bankA));
+    FO_CHECK(launch_sf(ctx, p, (const double*)dB, np, bankB));
+    XfOut out = make_out((char*)dOut, np, (double*)dGrid, false);
+    FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+    FO_CHECK(fo_peaks_run_dev(ctx, (double*)dGrid, np, shape, npeaks, width, pk, amp, mn, al, nf));
+    FO_CHECK(fo_peaks_copy_out(ctx, p0, np, npeaks, pk, amp, mn, al, nf, peaks, amplitude, mean, alpha, nfound));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
 extern "C" int fo_per_structure_factors(fo_ctx* ctx, const fo_per_params* p, const double* pos,
                                         int64_t nstruct, double* out) {
   FO_CHECK(check_params(ctx, p));

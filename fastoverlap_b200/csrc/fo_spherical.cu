@@ -2146,6 +2146,51 @@ extern "C" int fo_sph_isoft(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int
   return FO_OK;
 }
 
+// a8 fused: coefficients -> (2L+2)^3 overlap grid on the device -> top-npeaks rotations (fractional
+// grid indices; indtoEuler on the host).  findRotations, sphericalAlignment.py:196-204.
+extern "C" int fo_sph_isoft_peaks(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax, int64_t npeaks,
+                                  int64_t width, double* peaks, double* amplitude, double* mean, double* alpha,
+                                  int32_t* nfound) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (npairs < 0 || (npairs > 0 && (!Ilmm || !peaks || !amplitude || !nfound)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_isoft_peaks: NULL argument");
+  if (npeaks < 1 || npeaks > 64 || width < 1 || width > 4)
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_isoft_peaks: npeaks in 1..64, width in 1..4");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax;
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
+  const int64_t shape[3] = {2 * L + 2, 2 * L + 2, 2 * L + 2};
+  const size_t G3 = (size_t)shape[0] * shape[1] * shape[2];
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + ihalf_elems(L) * 16 + G3 * 8));
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *dfull, *dhalf, *dout, *dgrid;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dout));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * G3 * 8, &dgrid));
+  double *pk, *amp, *mn, *al;
+  int32_t* nf;
+  FO_CHECK(fo_peaks_outputs(ctx, chunk, npeaks, &pk, &amp, &mn, &al, &nf));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    FO_CUDA(ctx, cudaMemcpyAsync(dfull, Ilmm + (size_t)p0 * full * 2, (size_t)np * full * 16,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    sph_pack_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
+        (const double2*)dfull, L, (size_t)np, 0, (double2*)dhalf);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, 1, (long long*)dout,
+                       (double*)((char*)dout + (size_t)np * 24), (double*)((char*)dout + (size_t)np * 32),
+                       (double*)dgrid));
+    FO_CHECK(fo_peaks_run_dev(ctx, (double*)dgrid, np, shape, npeaks, width, pk, amp, mn, al, nf));
+    FO_CHECK(fo_peaks_copy_out(ctx, p0, np, npeaks, pk, amp, mn, al, nf, peaks, amplitude, mean, alpha, nfound));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
 extern "C" int fo_sph_coeffs_direct(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
                                     int64_t natoms, int64_t Jmax, double sigma, double* Ilmm_out,
                                     int32_t* status) {

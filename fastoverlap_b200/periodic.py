@@ -158,8 +158,9 @@ class PeriodicAlign(BasePeriodicAlignment):
     def findDisps(self, pos1, pos2, Cs=None, npeaks=1, width=2):
         self.setPos(pos1, pos2, Cs)
         if npeaks > 1:
-            from .peaks import findPeaks
-            disps = findPeaks(self.fabs, npeaks, width)[0]
+            # top-k by fit-and-subtract on the device (fo_grid_find_peaks; reference :444-451)
+            pk, _, _, _, nf, _ = self.ctx.grid_find_peaks(self.fabs, npeaks, width)
+            disps = pk[0, :int(nf[0])]
             if len(disps):
                 disps = disps * self.boxvec / self.fabs.shape
             else:

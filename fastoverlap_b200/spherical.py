@@ -136,14 +136,24 @@ class BaseSphericalAlignment(object):
         return R, res.fun
 
     def findRotations(self, Ilmm, nrot=10, width=2):
-        """Top-nrot rotations by Gaussian fit-and-subtract on the GPU-computed grid (reference :196-204)."""
-        from .peaks import findPeaks
-        overlap = self.ctx.sph_isoft(Ilmm, self.Jmax, want_imag=False)[0]
-        peaks = []
-        while len(peaks) == 0:
-            peaks, amplitude, mean, sigma, f = findPeaks(overlap, npeaks=nrot, width=width)
+        """Top-nrot rotations by Gaussian fit-and-subtract (reference :196-204): iSOFT and the peak
+        search both run on the device (fo_sph_isoft_peaks); the grid is not copied to the host.
+        Returns (Euler angles (k,3), amplitude, mean, sigma, None) -- the reference's last element, the
+        residual grid, is available from ctx.grid_find_peaks(..., want_residual=True)."""
+        from .utils import findMax
+        while True:
+            if width > 4:  # no fit converged: the reference falls back to the interpolated maximum
+                overlap = self.ctx.sph_isoft(Ilmm, self.Jmax, want_imag=False)[0]
+                return (np.atleast_2d(self.soft.indtoEuler(findMax(overlap)[None, :])), [overlap.max()], [0],
+                        [np.nan], None)
+            pk, amp, mean, alpha, nf = self.ctx.sph_isoft_peaks(Ilmm, self.Jmax, npeaks=nrot, width=width)
+            k = int(nf[0])
+            if k > 0:
+                break
             width += 1
-        return np.atleast_2d(self.soft.indtoEuler(peaks)), amplitude, mean, sigma, f
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sigma = [(2 * a) ** -0.5 for a in alpha[0, :k]]
+        return np.atleast_2d(self.soft.indtoEuler(pk[0, :k])), list(amp[0, :k]), list(mean[0, :k]), sigma, None
 
     def _setup(self, pos1, pos2, perm):
         pos1 = np.asanyarray(pos1, dtype=float).reshape(-1, 3)

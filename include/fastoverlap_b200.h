@@ -84,6 +84,7 @@ int fo_measure_fp64_tensor_peak(fo_ctx* ctx, double* tflops);
 #define FO_PROF_SPH_HARM 3    /* spherical harmonic-basis coefficients */
 #define FO_PROF_SPH_DOT 4     /* C_nlm contraction to I_lmm'           */
 #define FO_PROF_SPH_ISOFT 5   /* Wigner-d contraction + 2-D DFT + argmax */
+#define FO_PROF_PEAKS 6       /* top-k peak extraction (fit-and-subtract) */
 #define FO_PROF_NKINDS 8
 int fo_profile_begin(fo_ctx* ctx);
 int fo_profile_end(fo_ctx* ctx, double ms_out[FO_PROF_NKINDS], int64_t count_out[FO_PROF_NKINDS]);
@@ -240,6 +241,36 @@ int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs /*[
  * d^l_{m1m2}(beta_k), out [B, 2B-1, 2B-1, 2B] doubles, negative m wrapped modulo 2B-1
  * (soft.py:73-96, CALCWIGNERD DSOFT.f90:121-195).  Computed on the device. */
 int fo_sph_wigner_table(fo_ctx* ctx, int64_t Jmax, double* out);
+
+/* ---------------------------------------------------------------- top-k peaks (a8)
+ * Top-npeaks peaks of P overlap grids [P][n0][n1][n2] by the reference's Gaussian fit-and-subtract,
+ * entirely on the device: findPeaks / fitPeak / _gaussian (utils.py:347-396), FINDPEAKS / FINDPEAK /
+ * FIT / GAUSSIAN (fastutils.f90:231-548).  Per grid: f = a - min(a); repeat {arg-max; fit
+ * A exp(-(x-x0)^T S (x-x0)) + mu to the (2 width + 1)^3 periodic window (Levenberg-Marquardt from
+ * (f[ind], 0, identity, 0)); record; subtract the fitted function from the whole grid}.
+ * Outputs per grid: peaks [npeaks][3] fractional grid indices (x0 + ind), amplitude [npeaks] (A),
+ * mean [npeaks] (mu, nullable), alpha [npeaks][6] (upper triangle of S: s00 s01 s02 s11 s12 s22,
+ * nullable; the reference's sigma is (2 alpha)^-1/2), nfound (a failed fit ends the search, as the
+ * reference's `except RuntimeError: break`; entries beyond nfound are NaN), residual (nullable): the
+ * grid after the subtractions (the reference's returned `f`).  width <= 4, npeaks <= 64. */
+int fo_grid_find_peaks(fo_ctx* ctx, const double* grids, int64_t P, const int64_t shape[3], int64_t npeaks,
+                       int64_t width, double* peaks, double* amplitude, double* mean, double* alpha,
+                       int32_t* nfound, double* residual);
+/* Device-resident variant: d_grids is updated in place (becomes the residual). */
+int fo_grid_find_peaks_dev(fo_ctx* ctx, double* d_grids, int64_t P, const int64_t shape[3], int64_t npeaks,
+                           int64_t width, double* d_peaks, double* d_amplitude, double* d_mean,
+                           double* d_alpha, int32_t* d_nfound);
+/* Fused forms: the overlap grid is produced and searched on the device and never copied to the host.
+ * fo_sph_isoft_peaks: coefficients Ilmm [P][L+1][2L+1][2L+1] complex -> (2L+2)^3 grid -> peaks
+ * (findRotations, sphericalAlignment.py:196-204; ALIGN with nrotations > 1, fastclusters.f90:129).
+ * fo_per_align_pairs_peaks: positions -> F^3 |f| grid -> peaks (findDisps with npeaks > 1,
+ * periodicAlignment.py:442-451; ALIGN with ndisplacements > 1, fastbulk.f90:279). */
+int fo_sph_isoft_peaks(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax, int64_t npeaks,
+                       int64_t width, double* peaks, double* amplitude, double* mean, double* alpha,
+                       int32_t* nfound);
+int fo_per_align_pairs_peaks(fo_ctx* ctx, const fo_per_params* p, const double* posA, const double* posB,
+                             int64_t npairs, int64_t npeaks, int64_t width, double* peaks, double* amplitude,
+                             double* mean, double* alpha, int32_t* nfound);
 
 /* ---------------------------------------------------------------- host refinement (no GPU)
  * The steps the north star keeps on the host, as native code on an OpenMP pool over pairs
