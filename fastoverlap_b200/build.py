@@ -15,13 +15,14 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libfastoverlap_b200.so"
 SOURCES = ["fo_context.cu", "fo_periodic.cu", "fo_spherical.cu", "fo_peaks.cu", "fo_host.cu"]
+HOST_ONLY = {"fo_host.cu"}
 HEADERS = [os.path.join(CSRC, "fo_internal.h"), os.path.join(CSRC, "fo_symdft.cuh"),
            os.path.join(HERE, "..", "include", "fastoverlap_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-fopenmp",
+    "-Xcompiler", "-fPIC,-O3,-fopenmp,-msse4.1",
     "-fmad=true",
     "-prec-div=true", "-prec-sqrt=true",
 ]
@@ -55,9 +56,15 @@ def build(force=False, verbose=False):
         obj = os.path.join(LIBDIR, os.path.basename(src).replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + HEADERS):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            if os.path.basename(src) in HOST_ONLY:
+                # no device code: compiled by g++ directly (function multiversioning, OpenMP SIMD)
+                cmd = [shutil.which("g++") or "g++", "-x", "c++", "-std=c++17", "-O3", "-fPIC", "-fopenmp",
+                       "-msse4.1", "-I", os.path.join(os.path.dirname(nvcc), "..", "include"), "-c", src, "-o", obj]
+            else:
+                cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
             if verbose:
-                cmd.insert(1, "-Xptxas=-v")
+                if os.path.basename(src) not in HOST_ONLY:
+                    cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
     out = lib_path()

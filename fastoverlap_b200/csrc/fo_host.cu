@@ -29,7 +29,7 @@ namespace {
 // Dense n x n linear assignment (minimise), cost row-major.  col4row[i] = column assigned to row i.
 struct Lap {
   std::vector<double> u, v, shortest;
-  std::vector<int> path, row4col, remaining;
+  std::vector<int> path, row4col, remaining, colmin;
   std::vector<char> SR, SC;
   void solve(int n, const double* cost, int* col4row) {
     u.assign(n, 0.0);
@@ -42,7 +42,31 @@ struct Lap {
     SC.resize(n);
     for (int i = 0; i < n; ++i) col4row[i] = -1;
     const double inf = std::numeric_limits<double>::infinity();
+    // Column reduction (the initialisation phase of Jonker-Volgenant, JOVOSAP alignutils.f90:1041-1075):
+    // v[j] = min_i c[i][j], and column j is given to its minimising row when that row is still free.
+    // With u = 0 this is dual feasible and tight on the assigned pairs, so the augmentation below only
+    // has to run for the rows left free -- after a good alignment that is almost none of them.
+    {
+      colmin.assign(n, 0);
+      for (int j = 0; j < n; ++j) v[j] = cost[j];
+      for (int i = 1; i < n; ++i) {
+        const double* ci = cost + (size_t)i * n;
+        for (int j = 0; j < n; ++j)
+          if (ci[j] < v[j]) {
+            v[j] = ci[j];
+            colmin[j] = i;
+          }
+      }
+      for (int j = n - 1; j >= 0; --j) {
+        const int i = colmin[j];
+        if (v[j] == v[j] && col4row[i] == -1) {
+          col4row[i] = j;
+          row4col[j] = i;
+        }
+      }
+    }
     for (int cur = 0; cur < n; ++cur) {
+      if (col4row[cur] != -1) continue;
       std::fill(SR.begin(), SR.end(), 0);
       std::fill(SC.begin(), SC.end(), 0);
       std::fill(shortest.begin(), shortest.end(), inf);
@@ -93,7 +117,8 @@ struct Lap {
   }
 };
 
-inline double min_image(double d, double box) { return d - nearbyint(d / box) * box; }
+// rint == nearbyint in the default rounding mode; it inlines to one roundsd (-msse4.1)
+inline double min_image(double d, double box) { return d - __builtin_rint(d / box) * box; }
 
 struct Groups {
   const int32_t* goff;
@@ -101,10 +126,52 @@ struct Groups {
   const int32_t* gidx;
 };
 
+// Cost matrices of one permutation group from structure-of-arrays coordinates; the inner loops are
+// branch-free so that gcc vectorises them (function multiversioning picks the AVX2 clone at run time).
+// d * (1/box) instead of d / box can move the rounding only at exact half-box separations, where both
+// images give the same distance.
+#if defined(__GNUC__) && !defined(__CUDACC__)
+#define FO_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define FO_CLONES
+#endif
+
+FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const double* box, double* cost) {
+  const double b0 = box[0], b1 = box[1], b2 = box[2];
+  const double i0 = 1.0 / b0, i1 = 1.0 / b1, i2 = 1.0 / b2;
+  const double *y0 = ys, *y1 = ys + n, *y2 = ys + 2 * n;
+  for (int i = 0; i < n; ++i) {
+    const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i];
+    double* c = cost + (size_t)i * n;
+#pragma omp simd
+    for (int j = 0; j < n; ++j) {
+      double dx = x0 - y0[j], dy = x1 - y1[j], dz = x2 - y2[j];
+      dx -= __builtin_rint(dx * i0) * b0;
+      dy -= __builtin_rint(dy * i1) * b1;
+      dz -= __builtin_rint(dz * i2) * b2;
+      c[j] = __builtin_sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  }
+}
+
+FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost) {
+  const double *y0 = ys, *y1 = ys + n, *y2 = ys + 2 * n;
+  for (int i = 0; i < n; ++i) {
+    const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i];
+    double* c = cost + (size_t)i * n;
+#pragma omp simd
+    for (int j = 0; j < n; ++j) {
+      const double dx = x0 - y0[j], dy = x1 - y1[j], dz = x2 - y2[j];
+      c[j] = dx * dx + dy * dy + dz * dz;
+    }
+  }
+}
+
 // permutation of Y that best matches X group by group; periodic (box != null: cost = min-image
 // distance, periodicAlignment.py:94-102) or free (squared distance, utils.py:48-56)
 void best_perm(const Groups& G, int natoms, const double* X, const double* Y, const double* box, Lap& lap,
                std::vector<double>& cost, std::vector<int>& c4r, int* perm) {
+  static thread_local std::vector<double> soa;
   for (int i = 0; i < natoms; ++i) perm[i] = i;
   for (int64_t g = 0; g < G.ngroups; ++g) {
     const int n = G.goff[g + 1] - G.goff[g];
@@ -112,21 +179,18 @@ void best_perm(const Groups& G, int natoms, const double* X, const double* Y, co
     const int32_t* idx = G.gidx + G.goff[g];
     cost.resize((size_t)n * n);
     c4r.resize(n);
-    for (int i = 0; i < n; ++i) {
-      const double* xi = X + 3 * idx[i];
-      for (int j = 0; j < n; ++j) {
-        const double* yj = Y + 3 * idx[j];
-        double dx = xi[0] - yj[0], dy = xi[1] - yj[1], dz = xi[2] - yj[2];
-        if (box) {
-          dx = min_image(dx, box[0]);
-          dy = min_image(dy, box[1]);
-          dz = min_image(dz, box[2]);
-          cost[(size_t)i * n + j] = sqrt(dx * dx + dy * dy + dz * dz);
-        } else {
-          cost[(size_t)i * n + j] = dx * dx + dy * dy + dz * dz;
-        }
+    soa.resize((size_t)6 * n);
+    double* xs = soa.data();
+    double* ys = xs + 3 * n;
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        xs[k * n + i] = X[3 * idx[i] + k];
+        ys[k * n + i] = Y[3 * idx[i] + k];
       }
-    }
+    if (box)
+      cost_periodic(n, xs, ys, box, cost.data());
+    else
+      cost_free(n, xs, ys, cost.data());
     lap.solve(n, cost.data(), c4r.data());
     for (int i = 0; i < n; ++i) perm[idx[i]] = c4r[i] >= 0 ? idx[c4r[i]] : idx[i];
   }
