@@ -359,8 +359,8 @@ struct XfOut {
   int* status;          // [P] or null
 };
 
-__device__ __forceinline__ void group_sync(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(XF_GT) : "memory");
+__device__ __forceinline__ void group_sync(int grp, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ void better32(double& bv, int& bi, double v, int i) {
@@ -382,6 +382,7 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
               const long long* __restrict__ pairs,  // [P,2] or null (then pair p = (p, p))
               int npairs, int ngroups, int n, int F, double kx, double ky, double kz, double sigma,
               double2* __restrict__ gscratch,  // null: C and U live in shared memory
+              int xf_ng,                       // slab groups (4, 2 or 1: fewer when F (n+1) is large)
               XfOut out) {
   extern __shared__ double2 sm[];
   const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
@@ -392,7 +393,7 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
   double2* tw = sm;
   double* damp = (double*)(tw + F);
   double2* Vall = (double2*)(damp + ((3 * W + 1) & ~1));
-  double* red = (double*)(Vall + (size_t)XF_NG * F * Mp);  // 64 doubles of reduction scratch
+  double* red = (double*)(Vall + (size_t)xf_ng * F * Mp);  // 64 doubles of reduction scratch
   double2* C;
   double2* U;
   if (gscratch) {
@@ -403,7 +404,8 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
     U = C + c_elems;
   }
   const int tid = threadIdx.x;
-  const int grp = tid / XF_GT, gtid = tid - grp * XF_GT;
+  const int xf_gt = XF_THREADS / xf_ng;  // threads per slab group
+  const int grp = tid / xf_gt, gtid = tid - grp * xf_gt;
   double2* V = Vall + (size_t)grp * F * Mp;
 
   for (int t = tid; t < F; t += XF_THREADS) {
@@ -486,14 +488,14 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
     // ---- slabs: group grp takes dx = grp, grp + NG, ...
     double bv = -1.0;
     long long bi = 0x7fffffffffffffffLL;
-    const int nslab_iter = (F + XF_NG - 1) / XF_NG;
+    const int nslab_iter = (F + xf_ng - 1) / xf_ng;
     for (int it = 0; it < nslab_iter; ++it) {
-      const int dx = it * XF_NG + grp;
+      const int dx = it * xf_ng + grp;
       if (dx < F) {
         const double2* Us = U + (size_t)dx * WM;
         // stage Y: lines l, input over iy (stride M), output V[dy][l]
         const int nchy = (H + XF_DCY - 1) / XF_DCY;
-        for (int item = gtid; item < M * nchy; item += XF_GT) {
+        for (int item = gtid; item < M * nchy; item += xf_gt) {
           const int l = item % M, ch = item / M;
           const int d0 = ch * XF_DCY;
           const double2* cin = Us + l;
@@ -532,11 +534,11 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
           }
         }
       }
-      group_sync(grp);
+      group_sync(grp, xf_gt);
       if (dx < F) {
         // stage Z (complex half-line -> real line), fused with |.| and the running arg-max
         const int nchz = (H + XF_DCZ - 1) / XF_DCZ;
-        for (int item = gtid; item < F * nchz; item += XF_GT) {
+        for (int item = gtid; item < F * nchz; item += xf_gt) {
           const int dy = item % F, ch = item / F;
           const int d0 = ch * XF_DCZ;
           const double2* vin = V + (size_t)dy * Mp;
@@ -580,7 +582,7 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
           }
         }
       }
-      group_sync(grp);
+      group_sync(grp, xf_gt);
     }
     // ---- block arg-max (numpy order: first flat index on exact ties)
 #pragma unroll
@@ -1333,11 +1335,11 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
   }
 }
 
-size_t xf_smem_bytes(int n, int F, bool with_grids) {
+size_t xf_smem_bytes(int n, int F, bool with_grids, int xf_ng = XF_NG) {
   const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
   size_t b = (size_t)F * 16;                       // tw
   b += (size_t)((3 * W + 1) & ~1) * 8;             // damp
-  b += (size_t)XF_NG * F * Mp * 16;                // V
+  b += (size_t)xf_ng * F * Mp * 16;                // V
   b += 64 * 8;                                     // red
   if (with_grids) b += ((size_t)W * W * M + (size_t)F * W * M) * 16;
   return b;
@@ -1492,8 +1494,13 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   }
   size_t smem = xf_smem_bytes(n, F, true);
   double2* gscratch = nullptr;
+  int xf_ng = XF_NG;
   if (smem > optin) {
     smem = xf_smem_bytes(n, F, false);
+    while (smem > optin && xf_ng > 1) {  // fine k-grids: fewer, larger slab groups
+      xf_ng >>= 1;
+      smem = xf_smem_bytes(n, F, false, xf_ng);
+    }
     if (smem > optin)
       return fo_fail(ctx, FO_ERR_UNSUPPORTED,
                      "nwave=%d nfspace=%d needs %zu bytes of shared memory (> %zu)", n, F, smem,
@@ -1509,7 +1516,7 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   fo_prof_scope prof(ctx, FO_PROF_PER_XF);
   per_xf_kernel<<<blocks, XF_THREADS, smem, ctx->stream>>>(d_bankA, d_bankB, d_pairs, (int)npairs,
                                                            ngroups, n, F, kx, ky, kz, p->sigma,
-                                                           gscratch, out);
+                                                           gscratch, xf_ng, out);
   FO_LAUNCH_CHECK(ctx);
   return FO_OK;
 }
