@@ -204,17 +204,21 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-  const double* dx_ = reinterpret_cast<const double*>(phx);
-  const double* dy_ = reinterpret_cast<const double*>(phy);
-  const double* dz_ = reinterpret_cast<const double*>(phz);
-  for (int a0 = a_begin; a0 < a_end; a0 += SF_TA) {
+  // Phasor tables are double buffered: the table of atom tile t+1 is built (by whichever threads get
+  // there first) before a thread starts its DMMA share of tile t, so one barrier per tile suffices and
+  // the sincos / recurrence work overlaps the tensor-pipe work of the other warps (ncu on the
+  // single-buffered version: 15 % of the samples at the two barriers around the phasor phase).
+  const size_t buf_elems = (size_t)SF_TA * (2 * Mp + Mz);  // double2 elements per buffer
+  auto build_phasors = [&](int a0, int buf) {
     const int ta = min(SF_TA, a_end - a0);
     const int ta4 = (ta + 3) & ~3;
-    __syncthreads();
+    double2* bx = phx + buf * buf_elems;
+    double2* by = phy + buf * buf_elems;
+    double2* bz = phz + buf * buf_elems;
     for (int t = tid; t < 3 * ta4; t += blockDim.x) {
       const int a = t / 3, ax = t - 3 * a;
       const int pitch = (ax == 2) ? Mz : Mp;
-      double2* row = (ax == 0 ? phx : (ax == 1 ? phy : phz)) + a * pitch;
+      double2* row = (ax == 0 ? bx : (ax == 1 ? by : bz)) + a * pitch;
       if (a < ta) {
         const int atom = gidx[a0 + a];
         const double th = kax[ax] * spos[atom * 3 + ax];
@@ -235,7 +239,17 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
         for (int m = 0; m < pitch; ++m) row[m] = make_double2(0.0, 0.0);
       }
     }
-    __syncthreads();
+  };
+  if (a_begin < a_end) build_phasors(a_begin, 0);
+  __syncthreads();
+  int buf = 0;
+  for (int a0 = a_begin; a0 < a_end; a0 += SF_TA, buf ^= 1) {
+    const int ta = min(SF_TA, a_end - a0);
+    const int ta4 = (ta + 3) & ~3;
+    if (a0 + SF_TA < a_end) build_phasors(a0 + SF_TA, buf ^ 1);
+    const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
+    const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
+    const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
     for (int k0 = 0; k0 < ta4; k0 += 4) {
       const int a = k0 + t4;
       double bz[NT];
@@ -248,6 +262,7 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
         for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
       }
     }
+    __syncthreads();
   }
   // ---- epilogue: gather the 8 sums of (i, j, l) from the 4 lanes g = 4u + c4 and emit S(rho i, sig j, l)
   const int W = 2 * n + 1;
@@ -1374,7 +1389,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
     const int warps = (mtiles + MTq - 1) / MTq;
     if (NTq == 3 && warps <= 10 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {
       const int Mp = M | 1, Mz = (4 * NTq) | 1;
-      const size_t smem = (size_t)SF_TA * (2 * Mp + Mz) * 16;
+      const size_t smem = (size_t)2 * SF_TA * (2 * Mp + Mz) * 16;  // double-buffered phasor tables
       const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
       dim3 grid((unsigned)nstruct, (unsigned)ngroups);
       fo_prof_scope prof(ctx, FO_PROF_PER_SF);

@@ -437,15 +437,35 @@ sph_direct_mma_kernel(const double2* __restrict__ YA, const double2* __restrict_
   const double* ya = reinterpret_cast<const double*>(YA + p * (size_t)natoms * NLM + lbase);
   const double* yb = reinterpret_cast<const double*>(YB + p * (size_t)natoms * NLM + lbase);
   const double* Bl = Bes + (p * L1 + l) * (size_t)natoms * natoms;
-  for (int e = tid; e < N8 * R8; e += DS_THREADS) {
-    const int j = e / R8, r = e - j * R8;
-    const bool in = j < natoms && r < R;
-    A1[j * LDR + r] = in ? ya[(size_t)j * 2 * NLM + r] : 0.0;
-    B2[j * LDR + r] = in ? yb[(size_t)j * 2 * NLM + r] : 0.0;
-  }
-  for (int e = tid; e < N8 * N8; e += DS_THREADS) {
-    const int j = e / N8, k = e - j * N8;
-    B1[j * LDN + k] = (j < natoms && k < natoms) ? Bl[(size_t)j * natoms + k] : 0.0;
+  // Operands go global -> shared with cp.async (all copies of the CTA in flight at once: ncu showed
+  // the register-staged loads of the first version as 46 % long-scoreboard stalls); the zero padding
+  // (rows r >= R, atoms >= natoms) is written with ordinary stores to disjoint addresses.
+  {
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 8 threads
+    const int nm = l + 1;
+    for (int j = ty; j < N8; j += DS_THREADS / 16) {
+      if (j < natoms) {
+        for (int m = tx; m < nm; m += 16) {
+          const unsigned da = (unsigned)__cvta_generic_to_shared(A1 + j * LDR + 2 * m);
+          const unsigned db = (unsigned)__cvta_generic_to_shared(B2 + j * LDR + 2 * m);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(ya + (size_t)j * 2 * NLM + 2 * m)
+                       : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db), "l"(yb + (size_t)j * 2 * NLM + 2 * m)
+                       : "memory");
+        }
+        for (int r = R + tx; r < R8; r += 16) A1[j * LDR + r] = B2[j * LDR + r] = 0.0;
+        for (int k = tx; k < natoms; k += 16) {
+          const unsigned d1 = (unsigned)__cvta_generic_to_shared(B1 + j * LDN + k);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(Bl + (size_t)j * natoms + k)
+                       : "memory");
+        }
+        for (int k = natoms + tx; k < N8; k += 16) B1[j * LDN + k] = 0.0;
+      } else {
+        for (int r = tx; r < R8; r += 16) A1[j * LDR + r] = B2[j * LDR + r] = 0.0;
+        for (int k = tx; k < N8; k += 16) B1[j * LDN + k] = 0.0;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
   const int nrt = R8 >> 3, nct = N8 >> 3, nks = N4 >> 2;
