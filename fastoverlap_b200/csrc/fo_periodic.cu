@@ -174,7 +174,9 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   double2* phy = phx + SF_TA * Mp;
   double2* phz = phy + SF_TA * Mp;
   const int s = blockIdx.x, gq = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // blockIdx.z splits the row tiles of fine k-grids over several CTAs (each rebuilds the phasors)
+  const int warp = blockIdx.z * (blockDim.x >> 5) + (tid >> 5);
   const int g = lane >> 2, t4 = lane & 3;
   const int nrows = M * M * 4;
   const int a_begin = goff[gq], a_end = goff[gq + 1];
@@ -1382,23 +1384,44 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
   if (nstruct == 0) return FO_OK;
   const int n = (int)p->nwave, M = n + 1;
   const int ngroups = (int)ctx->h_goff.size() - 1;
-  {  // tensor-core path: NT column tiles cover 2M columns, MT row tiles per warp, <= 12 warps
+  {  // tensor-core path: NT column tiles cover the 2M columns, MT row tiles per warp, <= 10 warps per
+     // CTA; more row tiles than 10 MT (fine k-grids) are split over blockIdx.z
     const int NTq = (2 * M + 7) / 8;
     const int mtiles = (M * M * 4 + 7) / 8;
-    const int MTq = 5;
-    const int warps = (mtiles + MTq - 1) / MTq;
-    if (NTq == 3 && warps <= 10 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {
+    static const int mt_for_nt[9] = {0, 5, 5, 5, 4, 3, 2, 2, 2};
+    if (NTq <= 8 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {  // n <= 31; beyond, the scalar kernel wins
+      const int MTq = mt_for_nt[NTq];
+      int warps = (mtiles + MTq - 1) / MTq;
+      if (warps > 10) warps = 10;
+      const int nz = (mtiles + MTq * warps - 1) / (MTq * warps);
       const int Mp = M | 1, Mz = (4 * NTq) | 1;
       const size_t smem = (size_t)2 * SF_TA * (2 * Mp + Mz) * 16;  // double-buffered phasor tables
-      const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
-      dim3 grid((unsigned)nstruct, (unsigned)ngroups);
-      fo_prof_scope prof(ctx, FO_PROF_PER_SF);
-      FO_CUDA(ctx, cudaFuncSetAttribute(per_sf2_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-      per_sf2_kernel<5, 3><<<grid, warps * 32, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
-                                                                    (int)p->natoms, n, kx, ky, kz, d_bank);
-      FO_LAUNCH_CHECK(ctx);
-      return FO_OK;
+      if (smem <= ctx->prop.sharedMemPerBlockOptin) {
+        const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+        dim3 grid((unsigned)nstruct, (unsigned)ngroups, (unsigned)nz);
+        fo_prof_scope prof(ctx, FO_PROF_PER_SF);
+#define FO_SF2_LAUNCH(MT_, NT_)                                                                              \
+  do {                                                                                                       \
+    FO_CUDA(ctx, cudaFuncSetAttribute(per_sf2_kernel<MT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                           \
+    per_sf2_kernel<MT_, NT_><<<grid, warps * 32, smem, ctx->stream>>>(                                       \
+        d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, kx, ky, kz, d_bank);                    \
+  } while (0)
+        switch (NTq) {
+          case 1: FO_SF2_LAUNCH(5, 1); break;
+          case 2: FO_SF2_LAUNCH(5, 2); break;
+          case 3: FO_SF2_LAUNCH(5, 3); break;
+          case 4: FO_SF2_LAUNCH(4, 4); break;
+          case 5: FO_SF2_LAUNCH(3, 5); break;
+          case 6: FO_SF2_LAUNCH(2, 6); break;
+          case 7: FO_SF2_LAUNCH(2, 7); break;
+          case 8: FO_SF2_LAUNCH(2, 8); break;
+          default: FO_SF2_LAUNCH(2, 8); break;
+        }
+#undef FO_SF2_LAUNCH
+        FO_LAUNCH_CHECK(ctx);
+        return FO_OK;
+      }
     }
   }
   // TL = 5 gives the best FMA : (mul + load) ratio when it divides n+1 well, else TL = 2.
