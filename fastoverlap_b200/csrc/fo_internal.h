@@ -17,7 +17,8 @@ struct fo_devbuf {
 struct fo_wigner_cache {
   int64_t Jmax = -1;
   double* d_table = nullptr;   // dense Dt[m2][m1][l][k], see fo_spherical.cu
-  double* d_packed = nullptr;  // per-chunk shell-ordered slices for sph_isoft2_kernel
+  double* d_packed = nullptr;  // per-chunk shell-ordered slices for sph_isoft3_kernel
+  int packed_kc = 0;           // beta planes per chunk of d_packed (0: none)
   size_t bytes = 0;
   bool kmajor = false;         // large bandwidths: plane-major layout DtK[k][m2][m1][l]
 };

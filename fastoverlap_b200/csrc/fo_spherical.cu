@@ -1125,63 +1125,63 @@ sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
 }
 
 // ------------------------------------------------------------------------------------------
-// K5-K7 fast path (sph_isoft2_kernel): same mathematics as sph_isoft_kernel, organised like
-// per_xf3_kernel (fo_symdft.cuh) so that the FP64 pipe, not L2 / shared memory, is the limit:
-//   * persistent CTAs; a CTA owns the four beta planes k = {2c, 2c+1, F-2-2c, F-1-2c} and keeps its
-//     slice of the Wigner table in shared memory for all its pairs (the generic kernel streams
-//     0.7 MB of table per pair from L2).  Only m1 >= 0 entries are stored:
-//         d^l_{-m1,m2}(beta_k) = (-1)^{l+m2} d^l_{m1,m2}(beta_{F-1-k})
+// K5-K7 fast path (sph_isoft3_kernel): same mathematics as sph_isoft_kernel, organised so that the
+// FP64 tensor pipe, not L2 / shared memory / index arithmetic, is the limit:
+//   * persistent CTAs; a CTA owns KC beta planes in mirror pairs {k, F-1-k} (KC = 2: {c, F-1-c};
+//     KC = 4: {2c, 2c+1, F-2-2c, F-1-2c}) and keeps its slice of the Wigner table in shared memory for
+//     all its pairs (the generic kernel streams 0.7 MB of table per pair from L2).  Only m1 >= 0
+//     entries are stored:   d^l_{-m1,m2}(beta_k) = (-1)^{l+m2} d^l_{m1,m2}(beta_{F-1-k})
 //     so the mirrored plane supplies the -m1 values.  Entries are ordered by shell
-//     lmin = max(m1, m2): level l is the prefix of (l+1)^2 entries, lanes of a warp share lmin.
-//   * K5: a thread owns (|m1|, m2), accumulates S(+m1), S(-m1) for even / odd l separately
-//     (orientation o: I_inv^l = (-1)^l I^l) and writes E = S(+)+S(-), O = S(+)-S(-) for both
-//     orientations as the rows of stage A;
-//   * stage A (m1 -> alpha) and stage B (m2 -> gamma, half-complex -> real) are sym_row passes, one
-//     real row per thread, twiddles as uniform constant-bank operands; both orientations at once;
-//   * arg-max per orientation, and the parabola neighbours that lie inside the CTA's planes.
+//     lmin = max(m1, m2): level l is the prefix of (l+1)^2 entries.
+//   * the packed coefficients of the next pair are staged into shared memory with cp.async while the
+//     current pair is transformed;
+//   * K5 (Wigner contraction) in registers in the A-fragment layout, stage A (m1 -> alpha) and stage
+//     B (m2 -> gamma, half-complex -> real) as DMMA tiles (SymMma), arg-max per orientation.
 // ------------------------------------------------------------------------------------------
-constexpr int I2_THREADS = 512;
-constexpr int I2_DC = 9;
-constexpr int I2_KC = 4;
+#ifndef FO_I3_KC
+#define FO_I3_KC 2  // beta planes per CTA of sph_isoft3_kernel (2: two CTAs per SM; 4: one)
+#endif
 
 struct I2Layout {
-  int L, L1, W, F, H, HP, nchunk, NP, RA, RAp, RB, RBp, dts, ipk;
-  int o_lvl[65];
-  int o_dts, o_ae, o_ao, o_br, o_bi, o_red, total;  // shared-memory offsets in doubles
+  int L, L1, W, F, H, KC, nchunk, NP, RA, RB, RBp, nent, dts, ipk;
+  int o_ent[65];                                   // entries below level l: sum_{l' < l} (l'+1)^2
+  int o_dts, o3_iks, o3_br, o3_bi, o3_red, total3;  // shared-memory offsets in doubles
   I2Layout() {}
-  explicit I2Layout(int L_) {
+  I2Layout(int L_, int KC_) {
     L = L_;
+    KC = KC_;
     L1 = L + 1;
     W = 2 * L + 1;
     F = 2 * L1;
     H = F / 2 + 1;
-    HP = ((H + I2_DC - 1) / I2_DC) * I2_DC;
-    nchunk = F / I2_KC;
+    nchunk = F / KC;
     NP = L1 * L1;
-    RA = I2_KC * L1 * 2;
-    RAp = ((RA + 7) / 16) * 16 + 8 + 2;  // == 10 (mod 16): A-fragment k rows spread over the banks and
-                                         // the 16-byte K5 stores of consecutive m1 hit distinct bank groups
-    RB = F * I2_KC;
+    RA = KC * L1 * 2;
+    RB = F * KC;
     RBp = RB | 1;   // 8-byte stores of consecutive m2 land in distinct banks
     int off = 0;
     for (int l = 0; l <= 64; ++l) {
-      o_lvl[l] = off;
-      if (l <= L) off += (l + 1) * (l + 1) * I2_KC;
+      o_ent[l] = off;
+      if (l <= L) off += (l + 1) * (l + 1);
     }
-    dts = o_lvl[L] + L1 * L1 * I2_KC;
-    ipk = dts / 2;  // double2 elements of the packed coefficients of one pair: [level][entry][+-]
+    nent = off;
+    dts = nent * KC;  // doubles of one chunk's table slice: [level][entry][kk]
+    ipk = nent * 2;   // double2 elements of the packed coefficients of one pair: [level][entry][+-]
     o_dts = 0;
-    o_ae = o_dts + dts;
-    o_ao = o_ae + 2 * L1 * RAp;
-    o_br = o_ao + 2 * L1 * RAp;
-    o_bi = o_br + 2 * L1 * RBp;
-    o_red = o_bi + 2 * L1 * RBp;
-    total = o_red + 96;
+    o3_iks = o_dts + ((dts + 1) & ~1);
+    o3_br = o3_iks + 2 * ipk;
+    o3_bi = o3_br + 2 * L1 * RBp;
+    o3_red = o3_bi + 2 * L1 * RBp;
+    o3_red = (o3_red + 1) & ~1;
+    total3 = o3_red + 96;
   }
 };
 
-__host__ __device__ __forceinline__ int i2_plane(int F, int chunk, int kk) {
-  return kk < 2 ? 2 * chunk + kk : F - 4 - 2 * chunk + kk;  // kk: 0,1 -> 2c,2c+1 ; 2,3 -> F-2-2c, F-1-2c
+__host__ __device__ __forceinline__ int i2_plane(int F, int KC, int chunk, int kk) {
+  // first half of the kk range: planes c KC/2 + kk; second half: their mirrors in reverse order, so that
+  // the mirror of kk is KC - 1 - kk
+  const int h = KC >> 1;
+  return kk < h ? h * chunk + kk : F - KC + kk - h * chunk;
 }
 
 // DtP[chunk][level l][pair entry t < (l+1)^2][kk] from the dense table Dt[m2][m1+L][l][k]
@@ -1193,15 +1193,15 @@ __global__ void sph_wigner_pack_kernel(const double* __restrict__ Dt, const __gr
     const int c = e / Y.dts;
     int r = e - c * Y.dts;
     int l = 0;
-    while (l < L && r >= Y.o_lvl[l + 1]) ++l;
-    r -= Y.o_lvl[l];
-    const int t = r / I2_KC, kk = r - t * I2_KC;
+    while (l < L && r >= Y.o_ent[l + 1] * Y.KC) ++l;
+    r -= Y.o_ent[l] * Y.KC;
+    const int t = r / Y.KC, kk = r - t * Y.KC;
     int s = (int)sqrt((double)t);
     while ((s + 1) * (s + 1) <= t) ++s;
     while (s * s > t) --s;
     const int q = t - s * s;
     const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
-    DtP[e] = Dt[(((size_t)m2 * W + (a + L)) * L1 + l) * F + i2_plane(F, c, kk)];
+    DtP[e] = Dt[(((size_t)m2 * W + (a + L)) * L1 + l) * F + i2_plane(F, Y.KC, c, kk)];
   }
 }
 
@@ -1214,8 +1214,8 @@ __global__ void sph_ipack_kernel(const double2* __restrict__ Ihalf, const __grid
     const size_t p = e / Y.ipk;
     int r = (int)(e - p * Y.ipk);
     int l = 0;
-    while (l < L && r >= (Y.o_lvl[l + 1] >> 1)) ++l;
-    r -= Y.o_lvl[l] >> 1;
+    while (l < L && r >= Y.o_ent[l + 1] * 2) ++l;
+    r -= Y.o_ent[l] * 2;
     const int t = r >> 1, sg = r & 1;
     int s = (int)sqrtf((float)t);
     while ((s + 1) * (s + 1) <= t) ++s;
@@ -1232,42 +1232,44 @@ struct Iso2Out {
   double* grid;       // [P][O][F][F][F] or null
 };
 
-// KS = ceil(L/4) k-steps, NT = number of 8-wide output tiles handled by DMMA; NYQ: H = 8 NT + 1, the
-// last output (alpha or gamma = F/2) is the alternating sum c0 + sum (-1)^m E_m, done on the side.
-//
-// The kernel is persistent and every pair has the same geometry, so everything that depends only on
-// (thread, L) -- the K5 entry a thread owns, the rows / output addresses of the (at most two) stage-A
-// and stage-B tiles of a warp -- is decoded once before the pair loop: ncu (profiles/r01_summary.md)
-// showed the first version spending 97 % of its issue slots on that index arithmetic and on the
-// epilogues (DMMA: 2.3 % of the instructions).  The fast path exists for odd L <= 15 (F % 4 == 0 and
-// the shared-memory layout fits), where K5 has one work item per thread.
-template <int KS, int NT, bool NYQ, bool WANT_GRID>
-__global__ void __launch_bounds__(I2_THREADS, 1)
-sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict__ Ipk,
+// ------------------------------------------------------------------------------------------
+// sph_isoft3_kernel<KC, KS, NT, NYQ, WANT_GRID>.  KC = beta planes per CTA (the planes k and F-1-k
+// come in mirror pairs), KS = ceil(L/4) k-steps, NT = number of 8-wide output tiles handled by DMMA;
+// NYQ: H = 8 NT + 1, the last output (alpha or gamma = F/2) is the alternating sum
+// c0 + sum (-1)^m E_m, done on the side.  4 KC warps per CTA.
+// The Wigner contraction (K5) is done in registers, directly in the A-fragment layout of stage A
+// (the first fast kernel kept E / O arrays in shared memory between K5 and stage A: 70 KB, one more
+// barrier, and 97 % of its issue slots were index arithmetic -- profiles/r01_summary.md).
+// A warp owns stage-A tile w of both orientations: its 8 rows
+// are 4 consecutive (kk, m2) lines x (re | im); lane (g, t) holds A[row g][m1 = 4 ks + t + 1].  The
+// lane evaluates S(+-m1) for exactly those entries, the two lanes of one line (g, g ^ 1) splitting the
+// l sum by parity -- the even-l / odd-l partial sums are what the two orientations need
+// (I_inv^l = (-1)^l I^l) and the re / im component each lane lacks comes from its partner by one
+// shuffle.  No AE / AO arrays (70 KB), no barrier between K5 and stage A; the freed shared memory
+// holds the Wigner slice again (no L1 misses) next to the cp.async-staged coefficients.
+// ------------------------------------------------------------------------------------------
+template <int KC, int KS, int NT, bool NYQ, bool WANT_GRID>
+__global__ void __launch_bounds__(KC * 128, 4 / KC)
+sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict__ Ipk,
                   const double* __restrict__ DtP, int npairs, int norient, Iso2Out out) {
   extern __shared__ double smj[];
+  constexpr int NTHREADS = KC * 128;
   const int L = Y.L, L1 = Y.L1, F = Y.F, H = Y.H;
-  const int RA = Y.RA, RAp = Y.RAp, RB = Y.RB, RBp = Y.RBp;
-  constexpr int HV = NYQ ? NT * 8 : 0;  // NYQ: all 8 NT DMMA outputs are valid (H - 1 == 8 NT)
-  double2* IkS = reinterpret_cast<double2*>(smj + Y.o_dts);  // packed coefficients of the current pair
-  double* AE = smj + Y.o_ae;   // [o][m1 = 0..L][RAp]   (m1 = 0: c0)
-  double* AO = smj + Y.o_ao;   // [o][m1][RAp]
-  double* BR = smj + Y.o_br;   // [o][m2 = 0..L][RBp]   row = a * KC + kk
-  double* BI = smj + Y.o_bi;
-  double* red = smj + Y.o_red;
+  const int RA = Y.RA, RB = Y.RB, RBp = Y.RBp;
+  double* DtS = smj + Y.o_dts;
+  double2* IkS = reinterpret_cast<double2*>(smj + Y.o3_iks);
+  double* BR = smj + Y.o3_br;   // [o][m2 = 0..L][RBp]   row = a * KC + kk
+  double* BI = smj + Y.o3_bi;
+  double* red = smj + Y.o3_red;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int chunk = blockIdx.x % Y.nchunk;
   const int jstart = blockIdx.x / Y.nchunk, jstride = gridDim.x / Y.nchunk;
   const int nvalid = NYQ ? H - 1 : H;  // outputs produced by the DMMA tiles
-  // The Wigner slice of this chunk (48 KB at L = 15, the same for every pair) is read through L1;
-  // shared memory instead stages the coefficients of the NEXT pair (cp.async issued after K5, landing
-  // during stages A / B), so K5 never waits for L2: ncu showed 45 % of the first version's time in
-  // long-scoreboard stalls on those loads and in the barrier behind them.
-  const double* DtC = DtP + (size_t)chunk * Y.dts;
+  for (int e = tid; e < Y.dts; e += NTHREADS) DtS[e] = DtP[(size_t)chunk * Y.dts + e];
   auto stage_coeffs = [&](int pr) {
     const double2* src = Ipk + (size_t)pr * Y.ipk;
-    for (int e = tid; e < Y.ipk; e += I2_THREADS) {
+    for (int e = tid; e < Y.ipk; e += NTHREADS) {
       const unsigned dst = (unsigned)__cvta_generic_to_shared(IkS + e);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + e) : "memory");
     }
@@ -1277,163 +1279,138 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
   SymMma<KS, NT> mm;
   mm.init(L, F, nvalid, lane);
 
-  // ---- K5 geometry: work item = (entry pair {t, NP-1-t}, plane kk).  Pairing a low shell (long l
-  // run) with a high shell (short run) gives every thread ~L+2 levels: no barrier skew.
-  const int nhalf = (Y.NP + 1) >> 1;
-  const bool k5_on = tid < nhalf * I2_KC;
-  const int kk5 = tid & (I2_KC - 1);
-  int k5_s[2], k5_src[2], k5_dst[2];
-  bool k5_v[2], k5_a0[2], k5_m2odd[2];
+  // ---- geometry of this warp's stage-A tile (the same tile index in both orientations)
+  constexpr int NW = NTHREADS / 32;
+  const bool ta_on = warp * 8 < RA;  // ceil(RA / 8) <= 4 KC tiles: one per warp (L1 <= 16)
+  const int part = g & 1;
+  // KC L1 lines; with KC = 2 and an even Jmax the last tile is only half full: lane_on masks its rows
+  const bool lane_on = ta_on && warp * 4 + (g >> 1) < KC * L1;
+  const int line = lane_on ? warp * 4 + (g >> 1) : 0;
+  const int kkA = line / L1, m2A = line - kkA * L1;
+  const double sm2 = (m2A & 1) ? -1.0 : 1.0;
+  // entry ks: a = 4 ks + t4 + 1; entry KS: a = 0 (the row constant c0, evaluated by the t4 == 0 lanes).
+  // e_tt: shell-ordered entry index; e_l0: first level >= max(a, m2) with this lane's parity
+  int e_tt[KS + 1], e_l0[KS + 1];
 #pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const int qp = tid >> 2;
-    const int t = which ? Y.NP - 1 - qp : qp;
-    k5_v[which] = k5_on && !(which && t == qp);
-    const int tt = k5_v[which] ? t : 0;
-    int s = (int)sqrtf((float)tt);
-    while ((s + 1) * (s + 1) <= tt) ++s;
-    while (s * s > tt) --s;
-    const int q = tt - s * s;
-    const int a = q <= s ? q : s, m2 = q <= s ? s : q - s - 1;
-    k5_s[which] = s;
-    k5_src[which] = (Y.o_lvl[s] >> 1) + tt * 2;   // double2 index into the packed coefficients
-    // (the double index into the packed table slice is 2 k5_src: KC = 4 doubles per entry)
-    k5_dst[which] = a * RAp + (kk5 * L1 + m2) * 2;
-    k5_a0[which] = a == 0;
-    k5_m2odd[which] = m2 & 1;
+  for (int ks = 0; ks <= KS; ++ks) {
+    const int a = ks < KS ? 4 * ks + t4 + 1 : 0;
+    const bool on = lane_on && a <= L && (ks < KS || t4 == 0);
+    const int sh = a > m2A ? a : m2A;
+    e_tt[ks] = m2A >= a ? m2A * m2A + a : a * a + a + 1 + m2A;
+    e_l0[ks] = on ? sh + ((sh ^ part) & 1) : L + 1;  // L + 1: empty level loop
   }
-  // ---- stage A / B geometry of this warp's tiles (tile = warp + 16 j, j = 0, 1)
-  constexpr int NW = I2_THREADS / 32;
-  bool ta_v[2], tb_v[2];
-  int ta_in[2], ta_out[2], tb_in[2], tb_base[2];
-  bool ta_part[2], tb_o[2];
+  const int outA = (m2A)*RBp + kkA;  // + (part ? o3_bi : o3_br) + o L1 RBp
+  // ---- stage-B geometry (tile = warp + 16 j)
+  bool tb_v[2], tb_o[2], tb_lane[2];
+  int tb_in[2], tb_base[2];
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int tile = warp + NW * j;
-    {
-      ta_v[j] = tile * 8 < norient * RA;
-      const int r = ta_v[j] ? tile * 8 + g : g;  // RA is a multiple of 8: every tile is full
-      const int o = r / RA, row = r - o * RA;
-      const int part = row & 1, line = row >> 1;
-      const int kk = line / L1, m2 = line - kk * L1;
-      ta_in[j] = o * L1 * RAp + row;
-      ta_out[j] = (part ? Y.o_bi : Y.o_br) + (o * L1 + m2) * RBp + kk;
-      ta_part[j] = part;
-    }
-    {
-      tb_v[j] = tile * 8 < norient * RB;
-      const int r = tb_v[j] ? tile * 8 + g : g;
-      const int o = r / RB, rowb = r - o * RB;
-      const int a = rowb / I2_KC, kk = rowb - a * I2_KC;
-      tb_in[j] = o * L1 * RBp + rowb;
-      tb_base[j] = (a * F + i2_plane(F, chunk, kk)) * F;
-      tb_o[j] = o != 0;
-    }
+    tb_v[j] = tile * 8 < norient * RB;
+    tb_lane[j] = tile * 8 + g < norient * RB;  // the last tile can be partial (RB = F KC, F = 2 mod 4)
+    const int r = tb_lane[j] ? tile * 8 + g : 0;
+    const int o = r / RB, rowb = r - o * RB;
+    const int a = rowb / KC, kk = rowb - a * KC;
+    tb_in[j] = o * L1 * RBp + rowb;
+    tb_base[j] = (a * F + i2_plane(F, KC, chunk, kk)) * F;
+    tb_o[j] = o != 0;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   for (int pair = jstart; pair < npairs; pair += jstride) {
-    // ---- K5.  The coefficients come from the packed, level-major copy Ipk (coalesced 32-byte reads
-    // per lane pair) and are fetched four levels ahead.  Consecutive levels alternate parity, so the
-    // four accumulators (x: entry +a, y: entry -a; index: parity relative to the first level s) need
-    // no branch; orientation o uses I_inv^l = (-1)^l I^l.
-    if (k5_on) {
+    // ---- K5 in registers + stage A
+    if (ta_on) {
+      double fe[2][KS], fo[2][KS], c0o[2];  // A fragments E / O per orientation, row constants
+      // partial sums over the levels of this lane's parity, all KS + 1 entries advanced together (one
+      // running level offset, 4 (KS + 1) independent loads in flight per step):
+      // P = sum d(+a) I(+a), Mn = sum d(-a) I(-a)
+      double2 Ps[KS + 1], Ms[KS + 1];
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        if (!k5_v[which]) continue;
-        const int s = k5_s[which];
-        const double2* src = IkS + k5_src[which];
-        const double* dp = DtC + 2 * k5_src[which];
-        int inc = (s + 1) * (s + 1);  // entries of level l
-        double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
-        for (int l0 = s; l0 <= L; l0 += 4) {
-          double2 cp[4], cm[4];
-          double dpl[4], dmi[4];
+      for (int ks = 0; ks <= KS; ++ks) Ps[ks] = Ms[ks] = make_double2(0.0, 0.0);
+      {
+        int base = Y.o_ent[part];  // entries below level lv
+        for (int lv = part; lv <= L; lv += 2) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int l = l0 + u;
-            const bool in = l <= L;
-            cp[u] = src[0];
-            cm[u] = src[1];
-            dpl[u] = in ? __ldg(dp + kk5) : 0.0;
-            dmi[u] = in ? __ldg(dp + (I2_KC - 1 - kk5)) : 0.0;
-            if (l < L) {  // clamp at the last level: the masked table value makes the term vanish
-              src += 2 * inc;
-              dp += I2_KC * inc;
-              inc += 2 * l + 3;
+          for (int ks = 0; ks <= KS; ++ks) {
+            if (lv >= e_l0[ks]) {
+              const int idx = base + e_tt[ks];
+              const double dp = DtS[idx * KC + kkA], dm = DtS[idx * KC + (KC - 1 - kkA)];
+              const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
+              Ps[ks].x = fma(dp, cp.x, Ps[ks].x);
+              Ps[ks].y = fma(dp, cp.y, Ps[ks].y);
+              Ms[ks].x = fma(dm, cm.x, Ms[ks].x);
+              Ms[ks].y = fma(dm, cm.y, Ms[ks].y);
             }
           }
-          x0.x = fma(dpl[0], cp[0].x, x0.x); x0.y = fma(dpl[0], cp[0].y, x0.y);
-          y0.x = fma(dmi[0], cm[0].x, y0.x); y0.y = fma(dmi[0], cm[0].y, y0.y);
-          x1.x = fma(dpl[1], cp[1].x, x1.x); x1.y = fma(dpl[1], cp[1].y, x1.y);
-          y1.x = fma(dmi[1], cm[1].x, y1.x); y1.y = fma(dmi[1], cm[1].y, y1.y);
-          x0.x = fma(dpl[2], cp[2].x, x0.x); x0.y = fma(dpl[2], cp[2].y, x0.y);
-          y0.x = fma(dmi[2], cm[2].x, y0.x); y0.y = fma(dmi[2], cm[2].y, y0.y);
-          x1.x = fma(dpl[3], cp[3].x, x1.x); x1.y = fma(dpl[3], cp[3].y, x1.y);
-          y1.x = fma(dmi[3], cm[3].x, y1.x); y1.y = fma(dmi[3], cm[3].y, y1.y);
+          base += (lv + 1) * (lv + 1) + (lv + 2) * (lv + 2);
         }
-        const bool sodd = s & 1;
-        const double2 pe = sodd ? x1 : x0, po = sodd ? x0 : x1;
-        const double2 me = sodd ? y1 : y0, mo = sodd ? y0 : y1;
-        const double sm2 = k5_m2odd[which] ? -1.0 : 1.0;
+      }
+#pragma unroll
+      for (int ks = 0; ks <= KS; ++ks) {
+        const double2 P = Ps[ks], Mn = Ms[ks];
+        // component c = part of the even / odd sums: own one, partner (lane ^ 4) supplies the other
+        const double sendP = part ? P.x : P.y, sendM = part ? Mn.x : Mn.y;
+        const double recvP = __shfl_xor_sync(0xffffffffu, sendP, 4);
+        const double recvM = __shfl_xor_sync(0xffffffffu, sendM, 4);
+        const double pe = part ? recvP : P.x, po = part ? P.y : recvP;
+        const double me = part ? recvM : Mn.x, mo = part ? Mn.y : recvM;
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           const double so = o ? -1.0 : 1.0;
           // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
-          const double spx = fma(so, po.x, pe.x), spy = fma(so, po.y, pe.y);
-          const double smx = sm2 * fma(-so, mo.x, me.x), smy = sm2 * fma(-so, mo.y, me.y);
-          double2* ae = reinterpret_cast<double2*>(AE + (size_t)o * L1 * RAp + k5_dst[which]);
-          double2* ao = reinterpret_cast<double2*>(AO + (size_t)o * L1 * RAp + k5_dst[which]);
-          if (k5_a0[which]) {
-            *ae = make_double2(spx, spy);
-            *ao = make_double2(0.0, 0.0);
+          const double sp = fma(so, po, pe), sn = sm2 * fma(-so, mo, me);
+          if (ks < KS) {
+            fe[o][ks] = sp + sn;
+            fo[o][ks] = sp - sn;
           } else {
-            *ae = make_double2(spx + smx, spy + smy);
-            *ao = make_double2(spx - smx, spy - smy);
+            c0o[o] = __shfl_sync(0xffffffffu, sp, lane & ~3);  // from the t4 == 0 lane of this row
           }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        if (o >= norient) break;
+        double Pq[NT][2], Qq[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          Pq[nt][0] = Pq[nt][1] = c0o[o];
+          Qq[nt][0] = Qq[nt][1] = 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            fo_dmma(Pq[nt], fe[o][ks], mm.bc[ks][nt]);
+            fo_dmma(Qq[nt], fo[o][ks], mm.bs[ks][nt]);
+          }
+        double* Bout = smj + (part ? Y.o3_bi : Y.o3_br) + o * L1 * RBp + outA;
+        const double sgn = part ? 1.0 : -1.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int d = nt * 8 + t4 * 2 + q;
+            const double qx = __shfl_xor_sync(0xffffffffu, Qq[nt][q], 4);
+            if (lane_on && (NYQ || d < nvalid)) {
+              Bout[d * KC] = fma(sgn, qx, Pq[nt][q]);
+              if (d != 0 && (NYQ || 2 * d != F)) Bout[(F - d) * KC] = fma(-sgn, qx, Pq[nt][q]);
+            }
+          }
+        if (NYQ) {  // a = F/2: U = c0 + sum_m (-1)^m E_m  (sin terms vanish); m = 4 ks + t4 + 1
+          double acc = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) acc += (t4 & 1) ? fe[o][ks] : -fe[o][ks];
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          if (t4 == 0 && lane_on) Bout[(F / 2) * KC] = c0o[o] + acc;
         }
       }
     }
     __syncthreads();
-    if (pair + jstride < npairs) stage_coeffs(pair + jstride);
-    // ---- stage A: tiles of 8 rows (o, kk, m2, part): U[a] = P + iQ, U[F-a] = P - iQ
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (!ta_v[j]) continue;
-      const double* e0 = AE + ta_in[j];
-      const double* o1 = AO + ta_in[j] + RAp;
-      double* Bout = smj + ta_out[j];
-      const double sgn = ta_part[j] ? 1.0 : -1.0;
-      double P[NT][2], Q[NT][2];
-      mm.run(e0 + RAp - g, o1 - g, RAp, L, e0[0], lane, P, Q);
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int d = nt * 8 + t4 * 2 + q;
-          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
-          if (NYQ || d < nvalid) {
-            Bout[d * I2_KC] = fma(sgn, qx, P[nt][q]);
-            if (d != 0 && (NYQ || 2 * d != F)) Bout[(F - d) * I2_KC] = fma(-sgn, qx, P[nt][q]);
-          }
-        }
-      if (NYQ) {  // a = F/2: U = c0 + sum_m (-1)^m E_m  (sin terms vanish)
-        double acc = (t4 == 0) ? e0[0] : 0.0;
-        for (int m = 1 + t4; m <= L; m += 4) {
-          const double ev = e0[(size_t)m * RAp];
-          acc += (m & 1) ? -ev : ev;
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (t4 == 0) Bout[(F / 2) * I2_KC] = acc;
-      }
-    }
-    __syncthreads();
-    // ---- stage B: tiles of 8 rows (o, a, kk): g[gam] = aa - bb, g[F-gam] = aa + bb; arg-max.
-    // Everything is kept at half scale (accumulators start at v0/2, the grid value is 2 (A -+ B)):
-    // the larger of the two outputs of a column is A + |B|, one DADD + one max per column instead
-    // of forming both values; only a tile that beats the running maximum is looked at in detail.
+    if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during stage B
+    // ---- stage B: tiles of 8 rows (o, a, kk): g[gam] = aa - bb, g[F-gam] = aa + bb; arg-max at half
+    // scale (see sph_isoft2_kernel)
     double bvh[2] = {-1e300, -1e300};
     int bix[2] = {0x7fffffff, 0x7fffffff};
 #pragma unroll
@@ -1453,8 +1430,8 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
         for (int q = 0; q < 2; ++q) {
           const int d = nt * 8 + t4 * 2 + q;
           const double c = A[nt][q] + fabs(Bq[nt][q]);
-          if (NYQ || nt * 8 + 7 < HV || d < nvalid) cmax = fmax(cmax, c);
-          if (WANT_GRID) {
+          if (NYQ || d < nvalid) cmax = fmax(cmax, c);
+          if (WANT_GRID && tb_lane[j]) {
             double* grow = out.grid + (((size_t)pair * norient + o) * F * F * F + (size_t)base);
             if (NYQ || d < nvalid) {
               grow[d] = 2.0 * (A[nt][q] - Bq[nt][q]);
@@ -1474,11 +1451,12 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
         if (t4 == 0) {
           gny = v0h + acc;
           cmax = fmax(cmax, gny);
-          if (WANT_GRID) out.grid[((size_t)pair * norient + o) * F * F * F + (size_t)base + F / 2] = 2.0 * gny;
+          if (WANT_GRID && tb_lane[j])
+            out.grid[((size_t)pair * norient + o) * F * F * F + (size_t)base + F / 2] = 2.0 * gny;
         }
       }
       const double cur = o ? bvh[1] : bvh[0];
-      if (cmax >= cur) {
+      if (tb_lane[j] && cmax >= cur) {
         double tbv = cur;
         int tbi = o ? bix[1] : bix[0];
 #pragma unroll
@@ -1496,8 +1474,6 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
         if (o) { bvh[1] = tbv; bix[1] = tbi; } else { bvh[0] = tbv; bix[0] = tbi; }
       }
     }
-    // ---- block arg-max per orientation: warp max of the value, then the smallest index among the
-    // lanes that hold it (REDUX), then 16 warps through shared memory
     int* redi = reinterpret_cast<int*>(red + 48);
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
@@ -1524,7 +1500,7 @@ sph_isoft2_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
       out.part_val[((size_t)pair * norient + tid) * Y.nchunk + chunk] = 2.0 * v;
       out.part_idx[((size_t)pair * norient + tid) * Y.nchunk + chunk] = i;
     }
-    // no barrier here: the next writes to red / BR / BI come after the next pair's K5 barrier
+    // no barrier: red is rewritten only after the next pair's stage-A barrier
   }
 }
 
@@ -1828,8 +1804,10 @@ int ensure_wigner(fo_ctx* ctx, int L) {
     cudaFree(ctx->wig.d_packed);
     ctx->wig.d_packed = nullptr;
   }
-  if ((2 * (L + 1)) % I2_KC == 0 && !ctx->wig.kmajor) {
-    const I2Layout Y(L);
+  ctx->wig.packed_kc = 0;
+  if (L <= 15 && !ctx->wig.kmajor) {  // bandwidths of the fast iSOFT kernel (one stage-A tile per warp)
+    ctx->wig.packed_kc = FO_I3_KC;
+    const I2Layout Y(L, FO_I3_KC);
     if (cudaMalloc(&ctx->wig.d_packed, (size_t)Y.nchunk * Y.dts * 8) != cudaSuccess)
       return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the packed Wigner table failed");
     sph_wigner_pack_kernel<<<grid_for((size_t)Y.nchunk * Y.dts, 256), 256, 0, ctx->stream>>>(
@@ -1855,10 +1833,17 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
   if (npairs == 0) return FO_OK;
   FO_CHECK(ensure_wigner(ctx, L));
   const int F = 2 * (L + 1);
-  if (ctx->wig.d_packed && !ctx->force_generic) {
-    const I2Layout Y(L);
-    const size_t smem2 = (size_t)Y.total * 8;
-    if (smem2 <= ctx->prop.sharedMemPerBlockOptin && L >= 1) {
+  if (ctx->wig.d_packed && !ctx->force_generic && L >= 1) {
+    const int KC = ctx->wig.packed_kc;
+    const I2Layout Y(L, KC);
+    const size_t smem3 = (size_t)Y.total3 * 8;
+    const int KSq = (L + 3) / 4;
+    const bool nyq = (Y.H % 8) == 1;
+    const int NTq = nyq ? (Y.H - 1) / 8 : (Y.H + 7) / 8;
+    const int code = KSq * 100 + NTq * 10 + (nyq ? 1 : 0);
+    const bool have = code == 421 || code == 420 || code == 320 || code == 220 || code == 211 || code == 210 ||
+                      code == 110;
+    if (have && smem3 <= ctx->prop.sharedMemPerBlockOptin) {
       const int nch = Y.nchunk;
       void* part = nullptr;
       FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * nch * (8 + 4) + 64, &part));
@@ -1869,7 +1854,8 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       void* ipk = nullptr;
       FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * Y.ipk * 16, &ipk));
       const double2* d_Ipk = (const double2*)ipk;
-      int per = ctx->prop.multiProcessorCount / nch;
+      // persistent grid: (CTAs per SM) x SMs, a multiple of the chunk count
+      int per = ctx->prop.multiProcessorCount * (4 / KC) / nch;
       if (per < 1) per = 1;
       if ((int64_t)per > npairs) per = (int)npairs;
       const unsigned blocks = (unsigned)(per * nch);
@@ -1877,28 +1863,29 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       sph_ipack_kernel<<<grid_for((size_t)npairs * Y.ipk, 256), 256, 0, ctx->stream>>>(d_Ihalf, Y, (size_t)npairs,
                                                                                         (double2*)ipk);
       FO_LAUNCH_CHECK(ctx);
-#define FO_I2_LAUNCH(KS_, NT_, NYQ_)                                                                      \
-  do {                                                                                                    \
-    if (d_grid) {                                                                                         \
-      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft2_kernel<KS_, NT_, NYQ_, true>,                          \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));        \
-      sph_isoft2_kernel<KS_, NT_, NYQ_, true><<<blocks, I2_THREADS, smem2, ctx->stream>>>(                \
-          Y, d_Ipk, ctx->wig.d_packed, (int)npairs, norient, o2);                                         \
-    } else {                                                                                              \
-      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft2_kernel<KS_, NT_, NYQ_, false>,                         \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));        \
-      sph_isoft2_kernel<KS_, NT_, NYQ_, false><<<blocks, I2_THREADS, smem2, ctx->stream>>>(               \
-          Y, d_Ipk, ctx->wig.d_packed, (int)npairs, norient, o2);                                         \
-    }                                                                                                     \
+#define FO_I3_GO(KC_, KS_, NT_, NYQ_, G_)                                                                    \
+  do {                                                                                                       \
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft3_kernel<KC_, KS_, NT_, NYQ_, G_>,                            \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));             \
+    sph_isoft3_kernel<KC_, KS_, NT_, NYQ_, G_><<<blocks, KC_ * 128, smem3, ctx->stream>>>(                   \
+        Y, d_Ipk, ctx->wig.d_packed, (int)npairs, norient, o2);                                              \
   } while (0)
-      const int KSq = (L + 3) / 4;
-      const bool nyq = (Y.H % 8) == 1;
-      const int NTq = nyq ? (Y.H - 1) / 8 : (Y.H + 7) / 8;
-      if (KSq == 4 && NTq == 2 && nyq) FO_I2_LAUNCH(4, 2, true);        // Jmax 13, 15
-      else if (KSq == 2 && NTq == 1 && nyq) FO_I2_LAUNCH(2, 1, true);   // Jmax 7
-      else if (KSq == 3 && NTq == 2 && !nyq) FO_I2_LAUNCH(3, 2, false); // Jmax 9, 11
-      else goto generic_path;
-#undef FO_I2_LAUNCH
+#define FO_I3_LAUNCH(KS_, NT_, NYQ_)                         \
+  do {                                                       \
+    if (d_grid) FO_I3_GO(FO_I3_KC, KS_, NT_, NYQ_, true);    \
+    else FO_I3_GO(FO_I3_KC, KS_, NT_, NYQ_, false);          \
+  } while (0)
+      switch (code) {
+        case 421: FO_I3_LAUNCH(4, 2, true); break;    // Jmax 15
+        case 420: FO_I3_LAUNCH(4, 2, false); break;   // Jmax 13, 14
+        case 320: FO_I3_LAUNCH(3, 2, false); break;   // Jmax 9 .. 12
+        case 220: FO_I3_LAUNCH(2, 2, false); break;   // Jmax 8
+        case 211: FO_I3_LAUNCH(2, 1, true); break;    // Jmax 7
+        case 210: FO_I3_LAUNCH(2, 1, false); break;   // Jmax 5, 6
+        default: FO_I3_LAUNCH(1, 1, false); break;    // Jmax 1 .. 4
+      }
+#undef FO_I3_LAUNCH
+#undef FO_I3_GO
       FO_LAUNCH_CHECK(ctx);
       sph_final2_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
           d_Ihalf, ctx->wig.d_table, L, norient, nch, o2.part_val, o2.part_idx, d_best_idx,

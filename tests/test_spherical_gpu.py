@@ -246,7 +246,8 @@ def test_fortran_wrapper_facade(ctx):
     assert aligned.shape == (256, 3, 2, 2) and abs(d[0, 1] - 1.5590835031549872) < DIST_ATOL
 
 
-@pytest.mark.parametrize("N,J", [(20, 7), (38, 15), (25, 9), (18, 21)])
+@pytest.mark.parametrize("N,J", [(20, 7), (38, 15), (25, 9), (18, 21), (20, 14), (16, 13), (15, 8),
+                                 (14, 6), (12, 4), (10, 2), (9, 1), (22, 11), (21, 12)])
 def test_fast_and_generic_isoft_agree(ctx, N, J):
     """sph_isoft2_kernel (tensor-core, persistent) vs sph_isoft_kernel (any size)."""
     rng = np.random.default_rng(N + J)
