@@ -49,9 +49,39 @@ __host__ __device__ __forceinline__ int nlm_of(int L) { return (L + 1) * (L + 2)
 // stable 3-term recurrence in l of the fully normalised associated Legendre functions
 // (what XDNRMP legendre.f90:143-371 returns to RYML fastclusters.f90:602-652).
 // ------------------------------------------------------------------------------------------
-__global__ void sph_prep_kernel(const double* __restrict__ pos, int natoms, int L, size_t nstruct,
-                                double2* __restrict__ Ypk, double* __restrict__ R, int* status) {
+__global__ void __launch_bounds__(128)
+sph_prep_kernel(const double* __restrict__ pos, int natoms, int L, size_t nstruct,
+                double2* __restrict__ Ypk, double* __restrict__ R, int* status) {
+  // Recurrence coefficients once per CTA (they cost two square roots and two divisions per (l, m),
+  // which used to be paid by every thread at every step):
+  //   P_m^m = cmm[m] sin^m(theta),  P_l^m = ca[lm] (cos(theta) P_{l-1}^m - cb[lm] P_{l-2}^m)
+  extern __shared__ double sm_prep[];
   const int NLM = nlm_of(L);
+  double* ca = sm_prep;        // [NLM]
+  double* cb = ca + NLM;       // [NLM]
+  double* cmm = cb + NLM;      // [L + 1]
+  for (int e = threadIdx.x; e < NLM; e += blockDim.x) {
+    int l = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while ((l + 1) * (l + 2) / 2 <= e) ++l;
+    while (l * (l + 1) / 2 > e) --l;
+    const int m = e - l * (l + 1) / 2;
+    double a = 0.0, b = 0.0;
+    if (l >= m + 2) {
+      a = sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
+      b = sqrt((((double)(l - 1) * (l - 1)) - (double)m * m) / (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
+    }
+    ca[e] = a;
+    cb[e] = b;
+  }
+  if (threadIdx.x == 0) {
+    double c = 0.28209479177387814347403972578039;  // sqrt(1/(4 pi))
+    cmm[0] = c;
+    for (int q = 1; q <= L; ++q) {
+      c *= -sqrt((2.0 * q + 1.0) / (2.0 * q));
+      cmm[q] = c;
+    }
+  }
+  __syncthreads();
   const size_t total = nstruct * (size_t)natoms * (L + 1);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
@@ -78,15 +108,15 @@ __global__ void sph_prep_kernel(const double* __restrict__ pos, int natoms, int 
         if (r == 0.0) atomicOr(&status[s], FO_STATUS_ATOM_AT_ORIGIN);
       }
     }
-    // exp(i m phi) by repeated squaring-free product (m <= L small): use sincos of m*phi
-    double sm, cm;
-    {
-      const double phi = atan2(sph, cph);
-      sincos((double)m * phi, &sm, &cm);
+    // exp(i m phi) = (cos phi + i sin phi)^m and sin^m(theta) by m multiplications
+    double cm = 1.0, sm = 0.0, stm = 1.0;
+    for (int q = 0; q < m; ++q) {
+      const double c2 = cm * cph - sm * sph;
+      sm = sm * cph + cm * sph;
+      cm = c2;
+      stm *= st;
     }
-    // P_m^m
-    double pmm = 0.28209479177387814347403972578039;  // sqrt(1/(4 pi))
-    for (int q = 1; q <= m; ++q) pmm *= -sqrt((2.0 * q + 1.0) / (2.0 * q)) * st;
+    const double pmm = cmm[m] * stm;
     double2* out = Ypk + sa * NLM;
     double pl2 = 0.0, pl1 = pmm;
     out[m * (m + 1) / 2 + m] = make_double2(pmm * cm, pmm * sm);
@@ -97,11 +127,9 @@ __global__ void sph_prep_kernel(const double* __restrict__ pos, int natoms, int 
       pl1 = p;
     }
     for (int l = m + 2; l <= L; ++l) {
-      const double a = sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
-      const double b = sqrt((((double)(l - 1) * (l - 1)) - (double)m * m) /
-                            (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
-      const double p = a * (ct * pl1 - b * pl2);
-      out[l * (l + 1) / 2 + m] = make_double2(p * cm, p * sm);
+      const int lm = l * (l + 1) / 2 + m;
+      const double p = ca[lm] * (ct * pl1 - cb[lm] * pl2);
+      out[lm] = make_double2(p * cm, p * sm);
       pl2 = pl1;
       pl1 = p;
     }
@@ -1986,9 +2014,12 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
   double* Bes = RB + (size_t)np * natoms;
   fo_prof_scope prof(ctx, FO_PROF_SPH_COEF);
   const size_t tot = (size_t)np * natoms * (L + 1);
-  sph_prep_kernel<<<grid_for(tot, 128), 128, 0, ctx->stream>>>(d_posA, (int)natoms, L, (size_t)np, YA, RA, d_status);
+  const size_t smem_prep = ((size_t)2 * NLM + L + 1) * 8;
+  FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+  // YA and YB are adjacent in the work buffer and posA / posB need not be: two launches
+  sph_prep_kernel<<<grid_for(tot, 128, 148 * 16), 128, smem_prep, ctx->stream>>>(d_posA, (int)natoms, L, (size_t)np, YA, RA, d_status);
   FO_LAUNCH_CHECK(ctx);
-  sph_prep_kernel<<<grid_for(tot, 128), 128, 0, ctx->stream>>>(d_posB, (int)natoms, L, (size_t)np, YB, RB, d_status);
+  sph_prep_kernel<<<grid_for(tot, 128, 148 * 16), 128, smem_prep, ctx->stream>>>(d_posB, (int)natoms, L, (size_t)np, YB, RB, d_status);
   FO_LAUNCH_CHECK(ctx);
   sph_bessel_kernel<<<grid_for((size_t)np * natoms * natoms, 128), 128, 0, ctx->stream>>>(
       RA, RB, d_gid, (int)natoms, L, sigma, (size_t)np, Bes);
@@ -2357,7 +2388,9 @@ int run_harm(fo_ctx* ctx, const double* d_pos, int64_t ns, int64_t natoms, int n
   double2* Y = (double2*)work;
   double* R = (double*)(Y + (size_t)ns * natoms * NLM);
   fo_prof_scope prof(ctx, FO_PROF_SPH_HARM);
-  sph_prep_kernel<<<grid_for((size_t)ns * natoms * (L + 1), 128), 128, 0, ctx->stream>>>(
+  const size_t smem_prep = ((size_t)2 * NLM + L + 1) * 8;
+  FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+  sph_prep_kernel<<<grid_for((size_t)ns * natoms * (L + 1), 128, 148 * 16), 128, smem_prep, ctx->stream>>>(
       d_pos, (int)natoms, L, (size_t)ns, Y, R, d_status);
   FO_LAUNCH_CHECK(ctx);
   const size_t smem = (size_t)HARM_TA * (nmax + 1) * (L + 1) * 8 + (size_t)HARM_TA * NLM * 16;
