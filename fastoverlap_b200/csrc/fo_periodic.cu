@@ -1232,14 +1232,17 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
         const double v0h = 0.5 * ZR[0];
         double A[NT][2], B[NT][2];
         mm.run(ZR + FP - g, ZI + FP - g, FP, n, v0h, lane, A, B);
-        double cmax = -2.0;  // below the bvh sentinel (-1): NaN rows never enter the update
+        // Filter on the high word of |A| + |B| (non-negative doubles order like their bit patterns): one
+        // DADD + one integer max per column, off the FP64 pipe; a tile within 2^-20 of the running
+        // maximum (or holding a NaN) falls through to the exact column-by-column comparison.
+        int chi = 0;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int d = nt * 8 + t4 * 2 + q;
             const double c = fabs(A[nt][q]) + fabs(B[nt][q]);
-            if ((nt + 1) * 8 <= H || d < H) cmax = fmax(cmax, c);
+            if ((nt + 1) * 8 <= H || d < H) chi = max(chi, __double2hiint(c));
             if (WANT_GRID) {
               if (valid && d < H) {
                 double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
@@ -1248,7 +1251,7 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
               }
             }
           }
-        if (valid && cmax >= sb && (cmax > bvh || (cmax == bvh && base < bi))) {
+        if (valid && chi >= __double2hiint(fmax(sb, bvh))) {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
