@@ -114,7 +114,8 @@ _lib_lock = threading.Lock()
 
 
 def library_path():
-    return _build.lib_path()
+    """In-tree build, or the library named by FASTOVERLAP_B200_LIB (A/B runs of two builds)."""
+    return os.environ.get("FASTOVERLAP_B200_LIB") or _build.lib_path()
 
 
 def load_library():
