@@ -1438,7 +1438,9 @@ sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
     __syncthreads();
     if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during stage B
     // ---- stage B: tiles of 8 rows (o, a, kk): g[gam] = aa - bb, g[F-gam] = aa + bb; arg-max at half
-    // scale (see sph_isoft2_kernel)
+    // scale: accumulators start at v0/2, the grid value is 2 (A -+ B), and the larger of the two outputs
+    // of a column is A + |B| -- one DADD + one max per column; only a tile that beats the running
+    // maximum is looked at in detail
     double bvh[2] = {-1e300, -1e300};
     int bix[2] = {0x7fffffff, 0x7fffffff};
 #pragma unroll
