@@ -758,6 +758,100 @@ sph_dot_kernel(const double2* __restrict__ bank, const long long* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------
+// K3 on the tensor pipe (sph_dot_mma_kernel): one CTA per pair.  Both structures' packed coefficients
+// [k = (group, n)][lm] are copied to shared memory once (cp.async, k-major, pitch == 24 mod 32 doubles);
+// for every l the four real products of  I = sum_k conj(C^A[k, l, a]) C^B[k, l, m2]  are one small GEMM
+// on interleaved re / im rows and columns (as in sph_direct_mma_kernel), and
+//   I(+a, m2) = (RR + II, RI - IR),   I(-a, m2) = (-1)^a (RR - II, RI + IR)
+// because C[n, l, -a] = (-1)^a conj(C[n, l, a]).  avg = sum |I|^2 is reduced in a fixed order.
+// ------------------------------------------------------------------------------------------
+constexpr int DOT_THREADS = 256;
+
+__global__ void __launch_bounds__(DOT_THREADS)
+sph_dot_mma_kernel(const double2* __restrict__ bank, const long long* __restrict__ pairs, int ngroups,
+                   int nmax, int L, double2* __restrict__ Ihalf, double* __restrict__ avg) {
+  extern __shared__ double smd2[];
+  const size_t p = blockIdx.x;
+  const int W = 2 * L + 1, L1 = L + 1, N1 = nmax + 1, NLM = nlm_of(L);
+  const int K = ngroups * N1, K4 = (K + 3) & ~3;
+  const int LDC = fo_ld8(2 * NLM) + 16;  // == 24 (mod 32): the four k rows of a fragment in distinct bank groups
+  double* As = smd2;                      // [K4][LDC]
+  double* Bs = As + (size_t)K4 * LDC;     // [K4][LDC]
+  double* red = Bs + (size_t)K4 * LDC;    // [8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const size_t per_struct = (size_t)K * NLM;
+  const double2* CA = bank + (size_t)pairs[2 * p] * per_struct;
+  const double2* CB = bank + (size_t)pairs[2 * p + 1] * per_struct;
+  for (int e = tid; e < K4 * NLM; e += DOT_THREADS) {
+    const int k = e / NLM, c = e - k * NLM;
+    double* da = As + (size_t)k * LDC + 2 * c;
+    double* db = Bs + (size_t)k * LDC + 2 * c;
+    if (k < K) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(da), sb = (unsigned)__cvta_generic_to_shared(db);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(CA + (size_t)k * NLM + c) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb), "l"(CB + (size_t)k * NLM + c) : "memory");
+    } else {
+      da[0] = da[1] = db[0] = db[1] = 0.0;
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  double2* out = Ihalf + p * (size_t)L1 * W * L1;
+  double norm = 0.0;
+  // jobs: (l, row tile, column tile), enumerated l-major; nrt(l) = ceil(2 (l+1) / 8)
+  int job = warp;
+  for (int l = 0, j0 = 0; l <= L; ++l) {
+    const int nrt = (2 * (l + 1) + 7) >> 3;
+    const int lb2 = l * (l + 1);  // 2 * lbase: first double of this l in a row
+    for (; job < j0 + nrt * nrt; job += DOT_THREADS / 32) {
+      const int q = job - j0;
+      const int rt1 = q % nrt, rt2 = q / nrt;
+      double acc[2] = {0.0, 0.0};
+      // rows / columns beyond 2 (l+1) read the next l's coefficients (finite, results discarded)
+      const double* a = As + t4 * LDC + lb2 + rt1 * 8 + g;
+      const double* b = Bs + t4 * LDC + lb2 + rt2 * 8 + g;
+      for (int ks = 0; ks < (K4 >> 2); ++ks) fo_dmma(acc, a[ks * 4 * LDC], b[ks * 4 * LDC]);
+      // this lane: row r1 = 8 rt1 + g (a = r1 / 2, part g & 1), columns (re, im) of m2 = 4 rt2 + t4
+      const double px0 = __shfl_xor_sync(0xffffffffu, acc[0], 4);
+      const double px1 = __shfl_xor_sync(0xffffffffu, acc[1], 4);
+      const int am = (rt1 * 8 + g) >> 1, m2 = rt2 * 4 + t4;
+      if (am > l || m2 > l) continue;
+      double2 v;
+      if ((g & 1) == 0) {  // RR, RI here; IR, II in the partner: I(+a, m2)
+        v = make_double2(acc[0] + px1, acc[1] - px0);
+        out[((size_t)m2 * W + (L + am)) * L1 + l] = v;
+      } else if (am > 0) {  // IR, II here; RR, RI in the partner: I(-a, m2)
+        const double sg = (am & 1) ? -1.0 : 1.0;
+        v = make_double2(sg * (px0 - acc[1]), sg * (px1 + acc[0]));
+        out[((size_t)m2 * W + (L - am)) * L1 + l] = v;
+      } else {
+        continue;
+      }
+      // the (-m1, -m2) partner has the same modulus
+      norm += (m2 == 0 ? 1.0 : 2.0) * (v.x * v.x + v.y * v.y);
+    }
+    j0 += nrt * nrt;
+  }
+  if (avg) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) norm += __shfl_down_sync(0xffffffffu, norm, off);
+    if (lane == 0) red[warp] = norm;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < DOT_THREADS / 32; ++w) t += red[w];
+      avg[p] = t;
+    }
+  }
+}
+
+size_t dot_mma_smem(int ngroups, int nmax, int L) {
+  const int K4 = (ngroups * (nmax + 1) + 3) & ~3;
+  return ((size_t)2 * K4 * (fo_ld8(2 * nlm_of(L)) + 16) + 8) * 8;
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: Wigner-d table in the Dt layout.  One thread per (m2 >= 0, m1, k): closed-form edge value
 // at l = max(|m1|, m2) then the Kostelec-Rockmore recurrence in l
 // (CALCWIGNERD + RECURRTERMS, DSOFT.f90:81-195).
@@ -1363,7 +1457,15 @@ sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
           for (int ks = 0; ks <= KS; ++ks) {
             if (lv >= e_l0[ks]) {
               const int idx = base + e_tt[ks];
-              const double dp = DtS[idx * KC + kkA], dm = DtS[idx * KC + (KC - 1 - kkA)];
+              double dp, dm;
+              if (KC == 2) {  // the plane and its mirror are one 16-byte entry
+                const double2 dd = *reinterpret_cast<const double2*>(DtS + idx * 2);
+                dp = kkA ? dd.y : dd.x;
+                dm = kkA ? dd.x : dd.y;
+              } else {
+                dp = DtS[idx * KC + kkA];
+                dm = DtS[idx * KC + (KC - 1 - kkA)];
+              }
               const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
               Ps[ks].x = fma(dp, cp.x, Ps[ks].x);
               Ps[ks].y = fma(dp, cp.y, Ps[ks].y);
@@ -2527,8 +2629,16 @@ extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t
     double* d_avg = (double*)((char*)dout + (size_t)np * O * 56);
     {
       fo_prof_scope prof(ctx, FO_PROF_SPH_DOT);
-      sph_dot_kernel<<<(unsigned)np, 256, 0, ctx->stream>>>((const double2*)bank->d_data, (const long long*)dpairs,
-                                                            (int)bank->ngroups, (int)bank->nmax, L, (double2*)dhalf, d_avg);
+      const size_t smem_dot = dot_mma_smem((int)bank->ngroups, (int)bank->nmax, L);
+      if (!ctx->force_generic && smem_dot <= ctx->prop.sharedMemPerBlockOptin) {
+        FO_CUDA(ctx, cudaFuncSetAttribute(sph_dot_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dot));
+        sph_dot_mma_kernel<<<(unsigned)np, DOT_THREADS, smem_dot, ctx->stream>>>(
+            (const double2*)bank->d_data, (const long long*)dpairs, (int)bank->ngroups, (int)bank->nmax, L,
+            (double2*)dhalf, d_avg);
+      } else {
+        sph_dot_kernel<<<(unsigned)np, 256, 0, ctx->stream>>>((const double2*)bank->d_data, (const long long*)dpairs,
+                                                              (int)bank->ngroups, (int)bank->nmax, L, (double2*)dhalf, d_avg);
+      }
       FO_LAUNCH_CHECK(ctx);
     }
     FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, d_bi, d_bv, d_fr, (double*)dgrid));
