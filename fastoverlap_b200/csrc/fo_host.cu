@@ -31,7 +31,9 @@ struct Lap {
   std::vector<double> u, v, shortest;
   std::vector<int> path, row4col, remaining, colmin;
   std::vector<char> SR, SC;
-  void solve(int n, const double* cost, int* col4row) {
+  // colmin_in / vmin_in (optional): per-column minimum and its row, when the caller already has them
+  void solve(int n, const double* cost, int* col4row, const int* colmin_in = nullptr,
+             const double* vmin_in = nullptr) {
     u.assign(n, 0.0);
     v.assign(n, 0.0);
     shortest.resize(n);
@@ -47,18 +49,24 @@ struct Lap {
     // With u = 0 this is dual feasible and tight on the assigned pairs, so the augmentation below only
     // has to run for the rows left free -- after a good alignment that is almost none of them.
     {
-      colmin.assign(n, 0);
-      for (int j = 0; j < n; ++j) v[j] = cost[j];
-      for (int i = 1; i < n; ++i) {
-        const double* ci = cost + (size_t)i * n;
-        for (int j = 0; j < n; ++j)
-          if (ci[j] < v[j]) {
-            v[j] = ci[j];
-            colmin[j] = i;
-          }
+      const int* cm = colmin_in;
+      if (cm) {
+        for (int j = 0; j < n; ++j) v[j] = vmin_in[j];
+      } else {
+        colmin.assign(n, 0);
+        for (int j = 0; j < n; ++j) v[j] = cost[j];
+        for (int i = 1; i < n; ++i) {
+          const double* ci = cost + (size_t)i * n;
+          for (int j = 0; j < n; ++j)
+            if (ci[j] < v[j]) {
+              v[j] = ci[j];
+              colmin[j] = i;
+            }
+        }
+        cm = colmin.data();
       }
       for (int j = n - 1; j >= 0; --j) {
-        const int i = colmin[j];
+        const int i = cm[j];
         if (v[j] == v[j] && col4row[i] == -1) {
           col4row[i] = j;
           row4col[j] = i;
@@ -136,10 +144,17 @@ struct Groups {
 #define FO_CLONES
 #endif
 
-FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const double* box, double* cost) {
+// vmin / imin: running minimum of every column and its row (the column reduction of the LAP), kept in
+// the same pass that writes the matrix.
+FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const double* box, double* cost,
+                             double* vmin, int* imin) {
   const double b0 = box[0], b1 = box[1], b2 = box[2];
   const double i0 = 1.0 / b0, i1 = 1.0 / b1, i2 = 1.0 / b2;
   const double *y0 = ys, *y1 = ys + n, *y2 = ys + 2 * n;
+  for (int j = 0; j < n; ++j) {
+    vmin[j] = std::numeric_limits<double>::infinity();
+    imin[j] = 0;
+  }
   for (int i = 0; i < n; ++i) {
     const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i];
     double* c = cost + (size_t)i * n;
@@ -149,20 +164,32 @@ FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const do
       dx -= __builtin_rint(dx * i0) * b0;
       dy -= __builtin_rint(dy * i1) * b1;
       dz -= __builtin_rint(dz * i2) * b2;
-      c[j] = __builtin_sqrt(dx * dx + dy * dy + dz * dz);
+      const double d = __builtin_sqrt(dx * dx + dy * dy + dz * dz);
+      c[j] = d;
+      const bool lt = d < vmin[j];
+      vmin[j] = lt ? d : vmin[j];
+      imin[j] = lt ? i : imin[j];
     }
   }
 }
 
-FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost) {
+FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost, double* vmin, int* imin) {
   const double *y0 = ys, *y1 = ys + n, *y2 = ys + 2 * n;
+  for (int j = 0; j < n; ++j) {
+    vmin[j] = std::numeric_limits<double>::infinity();
+    imin[j] = 0;
+  }
   for (int i = 0; i < n; ++i) {
     const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i];
     double* c = cost + (size_t)i * n;
 #pragma omp simd
     for (int j = 0; j < n; ++j) {
       const double dx = x0 - y0[j], dy = x1 - y1[j], dz = x2 - y2[j];
-      c[j] = dx * dx + dy * dy + dz * dz;
+      const double d = dx * dx + dy * dy + dz * dz;
+      c[j] = d;
+      const bool lt = d < vmin[j];
+      vmin[j] = lt ? d : vmin[j];
+      imin[j] = lt ? i : imin[j];
     }
   }
 }
@@ -171,7 +198,8 @@ FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost
 // distance, periodicAlignment.py:94-102) or free (squared distance, utils.py:48-56)
 void best_perm(const Groups& G, int natoms, const double* X, const double* Y, const double* box, Lap& lap,
                std::vector<double>& cost, std::vector<int>& c4r, int* perm) {
-  static thread_local std::vector<double> soa;
+  static thread_local std::vector<double> soa, vmin;
+  static thread_local std::vector<int> imin;
   for (int i = 0; i < natoms; ++i) perm[i] = i;
   for (int64_t g = 0; g < G.ngroups; ++g) {
     const int n = G.goff[g + 1] - G.goff[g];
@@ -187,11 +215,13 @@ void best_perm(const Groups& G, int natoms, const double* X, const double* Y, co
         xs[k * n + i] = X[3 * idx[i] + k];
         ys[k * n + i] = Y[3 * idx[i] + k];
       }
+    vmin.resize(n);
+    imin.resize(n);
     if (box)
-      cost_periodic(n, xs, ys, box, cost.data());
+      cost_periodic(n, xs, ys, box, cost.data(), vmin.data(), imin.data());
     else
-      cost_free(n, xs, ys, cost.data());
-    lap.solve(n, cost.data(), c4r.data());
+      cost_free(n, xs, ys, cost.data(), vmin.data(), imin.data());
+    lap.solve(n, cost.data(), c4r.data(), imin.data(), vmin.data());
     for (int i = 0; i < n; ++i) perm[idx[i]] = c4r[i] >= 0 ? idx[c4r[i]] : idx[i];
   }
 }

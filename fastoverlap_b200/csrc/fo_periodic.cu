@@ -354,7 +354,7 @@ __global__ void per_compress_kernel(const double2* __restrict__ full, double2* _
 //
 // Stages (all in shared memory; T = trig table of 2 pi t/F):
 //   X  U[dx][iy][l] = sum_mx C[mx][iy][l] w^(mx dx)          (2n+1 -> F, complex)
-//   per slab dx (one group of XF_GT threads each):
+//   per slab dx (one group of XF_THREADS / xf_ng threads each):
 //   Y  V[dy][l]     = sum_my U[dx][my][l] w^(my dy)          (2n+1 -> F, complex)
 //   Z  g[dy][dz]    = V[dy][0] + 2 sum_{l>=1} Re(V[dy][l] w^(l dz))   (n+1 complex -> F real)
 // Each 1-D transform uses the +-m pairing (E = c_m + c_-m with cos, O = c_m - c_-m with sin) so
@@ -362,8 +362,7 @@ __global__ void per_compress_kernel(const double2* __restrict__ full, double2* _
 // radix FFT at these lengths, with no bit reversal and exact handling of any F.
 // ------------------------------------------------------------------------------------------
 constexpr int XF_THREADS = 512;
-constexpr int XF_NG = 4;                       // slab groups
-constexpr int XF_GT = XF_THREADS / XF_NG;      // threads per slab group
+constexpr int XF_NG = 4;                       // slab groups (upper bound; fewer for large F (n+1))
 constexpr int XF_DCX = 11;                     // outputs per thread, stage X
 constexpr int XF_DCY = 3;                      // stage Y
 constexpr int XF_DCZ = 7;                      // stage Z

@@ -35,13 +35,6 @@ namespace {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-// a * conj(b)
-__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
-  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
 __host__ __device__ __forceinline__ int nlm_of(int L) { return (L + 1) * (L + 2) / 2; }
 
 // ------------------------------------------------------------------------------------------
@@ -2026,7 +2019,6 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       return FO_OK;
     }
   }
-generic_path:
   if (ctx->wig.kmajor) {
     const size_t smem = isoft_big_smem(L);
     if (smem > ctx->prop.sharedMemPerBlockOptin)
