@@ -1281,6 +1281,14 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
       redi[tid >> 5] = bi;
     }
     __syncthreads();
+    // twiddle table for the parabola neighbours in the (now dead) ZIN region, built by warps 1.. while
+    // warp 0 finishes the arg-max
+    double2* twz = reinterpret_cast<double2*>(ZIN);
+    for (int t = tid - 32; t >= 0 && t < F; t += X4_THREADS - 32) {
+      double sn, cs;
+      sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+      twz[t] = make_double2(cs, sn);
+    }
     if (tid < 32) {
       bv = (tid < X4_THREADS / 32) ? red[tid] : -1.0;
       bi = (tid < X4_THREADS / 32) ? redi[tid] : 0x7fffffff;
@@ -1315,9 +1323,8 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
         double acc = 0.0;
         for (int e = lane; e < M * M; e += 32) {
           const int j = e / M, l = e - j * M;
-          double sj, cj, sl_, cl;
-          sincospi(2.0 * (double)((j * py) % F) / (double)F, &sj, &cj);
-          sincospi(2.0 * (double)((l * pz) % F) / (double)F, &sl_, &cl);
+          const double2 wj = twz[(j * py) % F], wl = twz[(l * pz) % F];
+          const double sj = wj.y, cj = wj.x, sl_ = wl.y, cl = wl.x;
           double vr, vi;
           if (j == 0) {
             vr = Y[l * 2];
