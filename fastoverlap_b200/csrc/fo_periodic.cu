@@ -1361,6 +1361,318 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K_xf for fine k-grids (per_xf5_kernel<NT>): the stages of per_xf4_kernel when neither the stage-X
+// image nor YIN (646 KB per pair at n = 16, 4.6 MB at n = 32) fit in shared memory.
+//   * stage X reads its E / O fragments straight from the image per_cross_kernel wrote (L2) and writes
+//     YIN[dx][ky][l] to a per-CTA global scratch;
+//   * slabs: YIN[dx] (K2 RY doubles) is staged into shared memory with cp.async, double buffered, SPI
+//     slabs at a time; stages Y and Z as in per_xf4_kernel; arg-max with the high-word filter;
+//   * the twiddle matrices live in shared memory (B fragments: one 8-byte load per DMMA) -- with up to
+//     8 x 9 fragment pairs they do not fit the register file.
+// One persistent 512-thread CTA per SM.  NT = ceil((F/2+1)/8) column tiles (template), any n.
+// ------------------------------------------------------------------------------------------
+constexpr int X5_THREADS = 512;
+constexpr int X5_WARPS = X5_THREADS / 32;
+
+struct X5Layout {
+  int M, W, H, KS, FP, RX, RXp, RY, K2, SPI, LDT;
+  int o_red, o_tc, o_ts, o_yb, o_z, total;  // shared-memory offsets in doubles
+  X5Layout() {}
+  X5Layout(int n, int F, int NT, size_t smem_limit_bytes) {
+    M = n + 1;
+    W = 2 * n + 1;
+    H = F / 2 + 1;
+    KS = (n + 3) / 4;
+    FP = ((F + 3) / 4) * 4 + 2;
+    RX = M * M * 4;
+    RXp = ((RX + 7) / 16) * 16 + 8;
+    RY = 2 * M;
+    K2 = 2 * n + 1;
+    LDT = 8 * NT;
+    LDT += ((8 - LDT) % 32 + 32) % 32;  // == 8 (mod 32)
+    o_red = 0;
+    o_tc = 64;
+    o_ts = o_tc + 4 * KS * LDT;
+    o_yb = o_ts + 4 * KS * LDT;
+    SPI = 8;
+    while (SPI > 1 && (size_t)(o_yb + SPI * (2 * K2 * RY + 2 * M * FP)) * 8 > smem_limit_bytes) --SPI;
+    o_z = o_yb + 2 * SPI * K2 * RY;
+    total = o_z + SPI * 2 * M * FP;
+  }
+  __host__ __device__ int zin_per_slab() const { return 2 * M * FP; }
+  __host__ __device__ int ximg_doubles() const { return 2 * M * RXp; }
+  __host__ __device__ size_t yin_doubles(int F) const { return (size_t)F * K2 * RY; }
+};
+
+// P[8 x 8NT] = c0 + E[8 x K] COS[K x 8NT], Q = O SIN with the twiddles in shared memory (TC / TS:
+// [4 KS][LDT], zero beyond K harmonics / H outputs).  e1 / o1: E[m = 1][first row of the tile].
+template <int NT>
+__device__ __forceinline__ void sym_run_smem(const double* __restrict__ e1, const double* __restrict__ o1,
+                                             size_t kstride, int K, int KS, const double* __restrict__ TC,
+                                             const double* __restrict__ TS, int LDT, double c0, int lane,
+                                             double (&P)[NT][2], double (&Q)[NT][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    P[nt][0] = P[nt][1] = c0;
+    Q[nt][0] = Q[nt][1] = 0.0;
+  }
+  for (int ks = 0; ks < KS; ++ks) {
+    int m = ks * 4 + t;
+    const int mc = m < K ? m : K - 1;  // rows beyond K: twiddles are zero
+    const double ae = e1[(size_t)mc * kstride + g];
+    const double ao = o1[(size_t)mc * kstride + g];
+    const double* tc = TC + m * LDT + g;
+    const double* ts = TS + m * LDT + g;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      fo_dmma(P[nt], ae, tc[nt * 8]);
+      fo_dmma(Q[nt], ao, ts[nt * 8]);
+    }
+  }
+}
+
+template <int NT, bool WANT_GRID>
+__global__ void __launch_bounds__(X5_THREADS, 1)
+per_xf5_kernel(const __grid_constant__ X5Layout L, const double* __restrict__ ximg, double* __restrict__ yin_all,
+               int npairs, int n, int F, XfOut out) {
+  extern __shared__ double sm5[];
+  const int M = L.M, H = L.H, KS = L.KS, FP = L.FP, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
+  const int SPI = L.SPI, LDT = L.LDT;
+  double* red = sm5 + L.o_red;
+  double* TC = sm5 + L.o_tc;
+  double* TS = sm5 + L.o_ts;
+  double* YB = sm5 + L.o_yb;            // [2][SPI][K2][RY]
+  double* ZIN = sm5 + L.o_z;            // [SPI][2][M][FP]
+  double* YIN = yin_all + (size_t)blockIdx.x * L.yin_doubles(F);  // [F][K2][RY]: k = j (c0 / E), n + j (O)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  unsigned long long* sbest = reinterpret_cast<unsigned long long*>(red + 48);
+  for (int e = tid; e < 4 * KS * LDT; e += X5_THREADS) {
+    const int m = e / LDT + 1, d = e - (m - 1) * LDT;
+    double sn = 0.0, cs = 0.0;
+    if (m <= n && d < H) sincospi(2.0 * (double)((m * d) % F) / (double)F, &sn, &cs);
+    TC[e] = cs;
+    TS[e] = sn;
+  }
+  const int slab_d = K2 * RY;  // doubles of one YIN slab
+  auto stage_slabs = [&](int x0, int buf) {
+    const int ns = min(SPI, F - x0);
+    const double2* src = reinterpret_cast<const double2*>(YIN + (size_t)x0 * slab_d);
+    double2* dst = reinterpret_cast<double2*>(YB + (size_t)buf * SPI * slab_d);
+    for (int e = tid; e < ns * (slab_d >> 1); e += X5_THREADS) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + e);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  __syncthreads();
+
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    if (tid == 0) *sbest = 0ull;
+    const double* XE = ximg + (size_t)pair * L.ximg_doubles();  // [M][RXp] (index 0: c0)
+    const double* XO = XE + (size_t)M * RXp;
+    // ---- stage X; tile = 8 rows; row bits: 0 = part, 1 = s  (partners: lane ^ 4, lane ^ 8)
+    for (int tile = warp; tile * 8 < RX; tile += X5_WARPS) {
+      const int row = tile * 8 + g;
+      const bool valid = row < RX;
+      const int r = valid ? row : 0;
+      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
+      const int j = jl / M, l = jl - j * M;
+      const double sgn = part ? -1.0 : 1.0;
+      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
+      const bool store = valid && !(j == 0 && s == 1);
+      double P[NT][2], Q[NT][2];
+      // rows of a partial last tile read the (finite) padding of the image; their outputs are not stored
+      sym_run_smem<NT>(XE + RXp + tile * 8, XO + RXp + tile * 8, RXp, n, KS, TC, TS, LDT, XE[r], lane, P, Q);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = nt * 8 + t4 * 2 + q;
+          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
+          const double ud = fma(sgn, qx, P[nt][q]);   // U[d]   = P - iQ
+          const double um = fma(-sgn, qx, P[nt][q]);  // U[F-d] = P + iQ
+          const double xd = __shfl_xor_sync(0xffffffffu, ud, 8);
+          const double xm = __shfl_xor_sync(0xffffffffu, um, 8);
+          const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
+          const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
+          if (store && d < H) {
+            YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
+            if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
+          }
+        }
+    }
+    __syncthreads();  // YIN complete (global writes of this CTA are visible to it after the barrier)
+    stage_slabs(0, 0);
+    // ---- slabs, SPI at a time
+    double bvh = -1.0;
+    int bi = 0x7fffffff;
+    int buf = 0;
+    for (int x0 = 0; x0 < F; x0 += SPI, buf ^= 1) {
+      const int ns = min(SPI, F - x0);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();  // slabs of this iteration staged; ZIN and the other buffer free
+      if (x0 + SPI < F) stage_slabs(x0 + SPI, buf ^ 1);
+      const double* Yb = YB + (size_t)buf * SPI * slab_d;
+      // stage Y: rows (slab, l, part)
+      for (int tile = warp; tile * 8 < ns * RY; tile += X5_WARPS) {
+        const int row = tile * 8 + g;
+        const bool valid = row < ns * RY;
+        const int r = valid ? row : 0;
+        const int sl = r / RY, lp = r - sl * RY;
+        const int l = lp >> 1, part = lp & 1;
+        const double* Y = Yb + (size_t)sl * slab_d + lp;
+        double* Zrow = ZIN + (size_t)sl * L.zin_per_slab() + (size_t)part * M * FP + (size_t)l * FP;
+        const double sgn = part ? -1.0 : 1.0;
+        double P[NT][2], Q[NT][2];
+        // per-lane rows (a tile can straddle two slabs): e1 / o1 are given per lane, g offset removed
+        sym_run_smem<NT>(Y + RY - g, Y + (size_t)(n + 1) * RY - g, RY, n, KS, TC, TS, LDT, Y[0], lane, P, Q);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int d = nt * 8 + t4 * 2 + q;
+            const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
+            if (valid && d < H) {
+              Zrow[d] = fma(sgn, qx, P[nt][q]);
+              if (d != 0 && 2 * d != F) Zrow[F - d] = fma(-sgn, qx, P[nt][q]);
+            }
+          }
+      }
+      __syncthreads();
+      // stage Z: rows (slab, dy)
+      for (int tile = warp; tile * 8 < ns * F; tile += X5_WARPS) {
+        const int row = tile * 8 + g;
+        const bool valid = row < ns * F;
+        const int r = valid ? row : 0;
+        const int sl = r / F, dy = r - sl * F;
+        const double sb = __longlong_as_double(*sbest);
+        const double* ZR = ZIN + (size_t)sl * L.zin_per_slab() + dy;
+        const double* ZI = ZR + (size_t)M * FP;
+        const int base = ((x0 + sl) * F + dy) * F;
+        const double v0h = 0.5 * ZR[0];
+        double A[NT][2], B[NT][2];
+        sym_run_smem<NT>(ZR + FP - g, ZI + FP - g, FP, n, KS, TC, TS, LDT, v0h, lane, A, B);
+        int chi = 0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int d = nt * 8 + t4 * 2 + q;
+            const double c = fabs(A[nt][q]) + fabs(B[nt][q]);
+            if (d < H) chi = max(chi, __double2hiint(c));
+            if (WANT_GRID) {
+              if (valid && d < H) {
+                double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
+                grow[d] = 2.0 * fabs(A[nt][q] + B[nt][q]);
+                if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * fabs(A[nt][q] - B[nt][q]);
+              }
+            }
+          }
+        if (valid && chi >= __double2hiint(fmax(sb, bvh))) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int d = nt * 8 + t4 * 2 + q;
+              const double g1 = d < H ? fabs(A[nt][q] + B[nt][q]) : -2.0;
+              const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[nt][q] - B[nt][q]) : -2.0;
+              better32(bvh, bi, g1, base + d);
+              better32(bvh, bi, g2, base + (F - d));
+            }
+          if (bvh > sb) atomicMax(sbest, (unsigned long long)__double_as_longlong(bvh));
+        }
+      }
+    }
+    double bv = 2.0 * bvh;
+    if (bvh < 0.0) bv = -1.0;
+    // ---- block arg-max (numpy order) and parabola neighbours
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      better32(bv, bi, ov, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red + 32);
+    if ((tid & 31) == 0) {
+      red[tid >> 5] = bv;
+      redi[tid >> 5] = bi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      bv = (tid < X5_WARPS) ? red[tid] : -1.0;
+      bi = (tid < X5_WARPS) ? redi[tid] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        better32(bv, bi, ov, oi);
+      }
+      if (tid == 0) {
+        red[0] = bv;
+        redi[0] = bi;
+      }
+    }
+    __syncthreads();
+    bv = red[0];
+    bi = redi[0];
+    const bool ok = (bi != 0x7fffffff) && isfinite(bv);
+    const int bx = ok ? bi / (F * F) : 0;
+    const int by = ok ? (bi / F) % F : 0;
+    const int bz = ok ? bi % F : 0;
+    __syncthreads();
+    {
+      if (warp < 6) {
+        const int ax = warp >> 1, sgn = (warp & 1) ? -1 : 1;
+        int px = bx, py = by, pz = bz;
+        if (ax == 0) px = (bx + sgn + F) % F;
+        if (ax == 1) py = (by + sgn + F) % F;
+        if (ax == 2) pz = (bz + sgn + F) % F;
+        const double* Y = YIN + (size_t)px * slab_d;
+        double acc = 0.0;
+        for (int e = lane; e < M * M; e += 32) {
+          const int j = e / M, l = e - j * M;
+          double sj, cj, sl_, cl;
+          sincospi(2.0 * (double)((j * py) % F) / (double)F, &sj, &cj);
+          sincospi(2.0 * (double)((l * pz) % F) / (double)F, &sl_, &cl);
+          double vr, vi;
+          if (j == 0) {
+            vr = Y[l * 2];
+            vi = Y[l * 2 + 1];
+          } else {
+            const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
+            const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
+            vr = er * cj + oi * sj;   // Re(E cos - i O sin)
+            vi = ei * cj - orr * sj;  // Im
+          }
+          const double term = vr * cl + vi * sl_;
+          acc += (l == 0) ? term : 2.0 * term;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) red[2 + warp] = fabs(acc);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      out.best_idx[3 * (size_t)pair + 0] = bx;
+      out.best_idx[3 * (size_t)pair + 1] = by;
+      out.best_idx[3 * (size_t)pair + 2] = bz;
+      out.best_val[pair] = bv;
+      const int b3[3] = {bx, by, bz};
+      for (int ax = 0; ax < 3; ++ax) {
+        const double y1 = red[2 + 2 * ax], y3 = red[2 + 2 * ax + 1], y2 = bv;
+        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
+      }
+      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
+    }
+    __syncthreads();  // red / YIN are reused by the next pair
+  }
+}
+
 size_t xf_smem_bytes(int n, int F, bool with_grids, int xf_ng = XF_NG) {
   const int W = 2 * n + 1, M = n + 1, Mp = M | 1;
   size_t b = (size_t)F * 16;                       // tw
@@ -1511,6 +1823,51 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
       return FO_OK;
     }
 #undef FO_X4_LAUNCH
+  }
+  {  // tensor-core path for fine k-grids: stage-X image and YIN in global memory (L2), slabs staged
+    const int NT5 = (F / 2 + 1 + 7) / 8;
+    const X5Layout lay5(n, F, NT5, optin);
+    const size_t smem5 = (size_t)lay5.total * 8;
+    if (NT5 >= 3 && NT5 <= 9 && smem5 <= optin && !ctx->force_generic && 2 * n + 1 <= 129 && !getenv("FO_XF_GENERIC")) {
+      void *ximg = nullptr, *yin = nullptr;
+      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay5.ximg_doubles() * 8, &ximg));
+      FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, (size_t)blocks * lay5.yin_doubles(F) * 8, &yin));
+      // per_cross_kernel only needs M, W, RXp of the layout: build the X4 form of it
+      X4Layout lx;
+      lx.M = lay5.M;
+      lx.W = lay5.W;
+      lx.RXp = lay5.RXp;
+      fo_prof_scope prof(ctx, FO_PROF_PER_XF);
+      per_cross_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lx, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
+                                                                ky, kz, p->sigma, (double*)ximg);
+      FO_LAUNCH_CHECK(ctx);
+#define FO_X5_LAUNCH(NT_)                                                                                  \
+  do {                                                                                                     \
+    if (out.grid) {                                                                                        \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf5_kernel<NT_, true>,                                         \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));         \
+      per_xf5_kernel<NT_, true><<<blocks, X5_THREADS, smem5, ctx->stream>>>(                               \
+          lay5, (const double*)ximg, (double*)yin, (int)npairs, n, F, out);                                \
+    } else {                                                                                               \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf5_kernel<NT_, false>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));         \
+      per_xf5_kernel<NT_, false><<<blocks, X5_THREADS, smem5, ctx->stream>>>(                              \
+          lay5, (const double*)ximg, (double*)yin, (int)npairs, n, F, out);                                \
+    }                                                                                                      \
+  } while (0)
+      switch (NT5) {
+        case 3: FO_X5_LAUNCH(3); break;
+        case 4: FO_X5_LAUNCH(4); break;
+        case 5: FO_X5_LAUNCH(5); break;
+        case 6: FO_X5_LAUNCH(6); break;
+        case 7: FO_X5_LAUNCH(7); break;
+        case 8: FO_X5_LAUNCH(8); break;
+        default: FO_X5_LAUNCH(9); break;
+      }
+#undef FO_X5_LAUNCH
+      FO_LAUNCH_CHECK(ctx);
+      return FO_OK;
+    }
   }
   {  // fast path: everything resident in shared memory, twiddles in the parameter constant bank
     const X3Layout lay(n, F);
