@@ -679,318 +679,14 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
 }
 
 // ------------------------------------------------------------------------------------------
-// K_xf fast path (per_xf3_kernel): the same mathematics as per_xf_kernel, organised so that the
-// FP64 pipe is the limit:
-//   * every 1-D transform is  P[d] = c0 + sum_m E[m] cos(2 pi m d/F),  Q[d] = sum_m O[m] sin(..)
-//     per REAL row (re / im parts are separate rows), E = c_m + c_-m and O = c_m - c_-m being
-//     formed by the previous stage (partner lanes exchange with two shuffles);
-//   * a thread owns one row and walks over all outputs d in chunks of X3_DC, so per (m, chunk) it
-//     loads two doubles from shared memory (k-major layout: conflict-free) for 2 X3_DC DFMA;
-//   * the twiddle matrices live in the kernel-parameter constant bank (__grid_constant__): the
-//     indices are warp-uniform, so they reach the DFMA as uniform-register operands
-//     (LDCU + DFMA R, R, UR, R in SASS) and cost no shared-memory / register-file bandwidth.
-//     (A shared-memory-fed register tile cannot be FP64 bound here: the LSU returns 128 B/clk/SM =
-//     16 doubles against 64 DFMA/clk/SM, ncu profiles/r01.)
-//   phase 1  cross-spectrum  -> XE/XO[m][row],  row = ((j M + l) 2 + s) 2 + part  (j=|ky|, s=sign)
-//   phase 2  stage X: row -> U(+-ky)[dx]; E/O over +-ky by shuffle -> YIN[dx][k][l*2+part]
-//   phase 3  SPI slabs at a time: stage Y rows (slab, l, part) -> ZR/ZI[l][dy];
-//            stage Z rows (slab, dy) -> |g|, running arg-max, optional grid
-//   phase 4  block arg-max + the six parabola neighbours re-evaluated from YIN
-// Used when it fits in shared memory and the constant bank (BLJ256: 190 KB); else per_xf_kernel.
-// ------------------------------------------------------------------------------------------
-constexpr int X3_THREADS = 512;
-constexpr int X3_DC = 7;          // outputs per chunk (H = 21 = 3 x 7 for F = 40)
-using X3Tw = FoTw;
-constexpr int X3_TWMAX = FO_TWMAX;
-
-struct X3Layout {
-  int M, W, H, HP, FP, RX, RY, K2, SPI;
-  size_t o_damp, o_red, o_xz, o_yin, total;  // in doubles
-  __host__ __device__ X3Layout(int n, int F) {
-    M = n + 1;
-    W = 2 * n + 1;
-    H = F / 2 + 1;
-    HP = ((H + X3_DC - 1) / X3_DC) * X3_DC;
-    FP = ((F + 3) / 4) * 4 + 2;  // ZR/ZI row pitch == 2 mod 4: spreads the stage-Y stores over banks
-    RX = M * M * 4;
-    RY = 2 * M;
-    K2 = 2 * n + 1;
-    const size_t xin = (size_t)2 * M * RX, zslab = (size_t)2 * M * FP;
-    SPI = 10;
-    while (SPI > 1 && (F + SPI - 1) / SPI == (F + SPI - 2) / (SPI - 1)) --SPI;  // same #iterations
-    size_t xz = xin > zslab * SPI ? xin : zslab * SPI;
-    o_damp = 0;
-    o_red = o_damp + ((3 * W + 1) & ~1);
-    o_xz = o_red + 64;
-    o_yin = o_xz + xz;
-    total = o_yin + (size_t)F * K2 * RY;
-  }
-  __host__ __device__ size_t zin_per_slab() const { return (size_t)2 * M * FP; }
-};
-
-// WANT_GRID: the optional F^3 grid output is compiled out of the production instantiation (its
-// per-thread global stores in the stage-Z epilogue make ptxas keep the table indices in vector
-// registers, i.e. LDC + DFMA R,R,R instead of LDCU + DFMA R,R,UR).
-template <bool WANT_GRID>
-__global__ void __launch_bounds__(X3_THREADS, 1)
-per_xf3_kernel(const __grid_constant__ X3Tw tw, const __grid_constant__ X3Layout L,
-               const double2* __restrict__ bankA, const double2* __restrict__ bankB,
-               const long long* __restrict__ pairs, int npairs, int ngroups, int n, int F, double kx,
-               double ky, double kz, double sigma, XfOut out) {
-  // L is computed on the host and passed through the parameter bank: its members then live in
-  // uniform registers, which is what lets the twiddle indices be proven warp-uniform
-  extern __shared__ double sm3[];
-  const int M = L.M, W = L.W, H = L.H, HP = L.HP, FP = L.FP, RX = L.RX, RY = L.RY, K2 = L.K2;
-  const int SPI = L.SPI;
-  double* damp = sm3 + L.o_damp;
-  double* red = sm3 + L.o_red;
-  double* XE = sm3 + L.o_xz;                 // [M][RX] (index 0: c0)
-  double* XO = XE + (size_t)M * RX;          // [M][RX] (index 0 unused)
-  double* ZIN = XE;                          // aliases the stage-X input: [SPI][2][M][FP]
-  double* YIN = sm3 + L.o_yin;               // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
-  const int tid = threadIdx.x;
-
-  for (int t = tid; t < 3 * W; t += X3_THREADS) {
-    const int ax = t / W, m = t - ax * W - n;
-    const double k = (ax == 0 ? kx : (ax == 1 ? ky : kz)) * (double)m;
-    damp[t] = exp(-(k * k) * (sigma * sigma));
-  }
-  __syncthreads();
-
-  const size_t c_elems = (size_t)W * W * M;
-  const size_t bank_stride = (size_t)ngroups * c_elems;
-  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-    const long long ia = pairs ? pairs[2 * pair] : pair;
-    const long long ib = pairs ? pairs[2 * pair + 1] : pair;
-    const double2* SA = bankA + (size_t)ia * bank_stride;
-    const double2* SB = bankB + (size_t)ib * bank_stride;
-    // ---- phase 1: cross spectrum in E/O form
-    for (int item = tid; item < M * W * M; item += X3_THREADS) {
-      const int l = item % M;
-      const int iy = (item / M) % W;
-      const int i = item / (M * W);
-      const size_t ep = ((size_t)(n + i) * W + iy) * M + l, em = ((size_t)(n - i) * W + iy) * M + l;
-      double pr = 0.0, pi = 0.0, mr = 0.0, mi = 0.0;
-      for (int g = 0; g < ngroups; ++g) {
-        const double2 a = SA[(size_t)g * c_elems + ep], b = SB[(size_t)g * c_elems + ep];
-        pr += a.x * b.x + a.y * b.y;
-        pi += a.y * b.x - a.x * b.y;
-        if (i) {
-          const double2 a2 = SA[(size_t)g * c_elems + em], b2 = SB[(size_t)g * c_elems + em];
-          mr += a2.x * b2.x + a2.y * b2.y;
-          mi += a2.y * b2.x - a2.x * b2.y;
-        }
-      }
-      const double dmp = damp[n + i] * damp[W + iy] * damp[2 * W + n + l];
-      pr *= dmp; pi *= dmp; mr *= dmp; mi *= dmp;
-      const int j = iy >= n ? iy - n : n - iy;
-      const int s = iy >= n ? 0 : 1;
-      const int row = ((j * M + l) * 2 + s) * 2;
-      double er, ei, orr, oi;
-      if (i == 0) {
-        er = pr; ei = pi; orr = 0.0; oi = 0.0;
-      } else {
-        er = pr + mr; ei = pi + mi; orr = pr - mr; oi = pi - mi;
-      }
-      *reinterpret_cast<double2*>(XE + (size_t)i * RX + row) = make_double2(er, ei);
-      *reinterpret_cast<double2*>(XO + (size_t)i * RX + row) = make_double2(orr, oi);
-      if (j == 0) {  // ky = 0 has no s = 1 partner: keep those rows finite (their output is unused)
-        *reinterpret_cast<double2*>(XE + (size_t)i * RX + row + 2) = make_double2(er, ei);
-        *reinterpret_cast<double2*>(XO + (size_t)i * RX + row + 2) = make_double2(orr, oi);
-      }
-    }
-    __syncthreads();
-    // ---- phase 2: stage X, one thread per row; lanes: bit 0 = part, bit 1 = s
-    for (int rbase = 0; rbase < RX; rbase += X3_THREADS) {
-      const int row = rbase + tid;
-      const bool valid = row < RX;
-      const int r = valid ? row : 0;
-      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
-      const int j = jl / M, l = jl - j * M;
-      const double sgn = part ? -1.0 : 1.0;
-      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
-      const bool store = valid && !(j == 0 && s == 1);
-      sym_row<X3_DC>(tw, XE + RX + r, XO + RX + r, RX, n, HP, XE[r], 0, HP,
-              [&](int d0, double (&P)[X3_DC], double (&Q)[X3_DC]) {
-#pragma unroll
-                for (int t = 0; t < X3_DC; ++t) {
-                  const int d = d0 + t;
-                  const double qx = __shfl_xor_sync(0xffffffffu, Q[t], 1);
-                  const double ud = fma(sgn, qx, P[t]);   // U[d]   = P - iQ
-                  const double um = fma(-sgn, qx, P[t]);  // U[F-d] = P + iQ
-                  const double xd = __shfl_xor_sync(0xffffffffu, ud, 2);
-                  const double xm = __shfl_xor_sync(0xffffffffu, um, 2);
-                  // s = 0: E = U(+) + U(-) (or c0 = U for ky = 0); s = 1: O = U(+) - U(-) = x - u
-                  const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
-                  const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
-                  if (store && d < H) {
-                    YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
-                    if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
-                  }
-                }
-              });
-    }
-    __syncthreads();
-    // ---- phase 3: slabs, SPI at a time
-    double bv = -1.0;
-    int bi = 0x7fffffff;  // 32-bit flat index (F <= 1024): 64-bit index math here costs the uniform operands
-    for (int x0 = 0; x0 < F; x0 += SPI) {
-      const int ns = min(SPI, F - x0);
-      // stage Y: rows (slab, l, part); uniform control flow (invalid rows are clamped, stores masked)
-      for (int rbase = 0; rbase < ns * RY; rbase += X3_THREADS) {
-        const int row = rbase + tid;
-        const bool valid = row < ns * RY;
-        const int r = valid ? row : 0;
-        const int sl = r / RY, lp = r - sl * RY;
-        const int l = lp >> 1, part = lp & 1;
-        const double* Y = YIN + (size_t)(x0 + sl) * K2 * RY + lp;
-        double* Zrow = ZIN + (size_t)sl * L.zin_per_slab() + (size_t)part * M * FP + (size_t)l * FP;
-        const double sgn = part ? -1.0 : 1.0;
-        sym_row<X3_DC>(tw, Y + RY, Y + (size_t)(n + 1) * RY, RY, n, HP, Y[0], 0, HP,
-                [&](int d0, double (&P)[X3_DC], double (&Q)[X3_DC]) {
-#pragma unroll
-                  for (int t = 0; t < X3_DC; ++t) {
-                    const int d = d0 + t;
-                    // V[d] = P - iQ, V[F-d] = P + iQ: re rows need the partner's Q_im, im rows its Q_re
-                    const double qx = __shfl_xor_sync(0xffffffffu, Q[t], 1);
-                    if (valid && d < H) {
-                      Zrow[d] = fma(sgn, qx, P[t]);
-                      if (d != 0 && 2 * d != F) Zrow[F - d] = fma(-sgn, qx, P[t]);
-                    }
-                  }
-                });
-      }
-      __syncthreads();
-      // stage Z: rows (slab, dy); uniform control flow
-      for (int rbase = 0; rbase < ns * F; rbase += X3_THREADS) {
-        const int row = rbase + tid;
-        const bool valid = row < ns * F;
-        const int r = valid ? row : 0;
-        const int sl = r / F, dy = r - sl * F;
-        const int dx = x0 + sl;
-        const double* ZR = ZIN + (size_t)sl * L.zin_per_slab() + dy;
-        const double* ZI = ZR + (size_t)M * FP;
-        const int base = (dx * F + dy) * F;
-        double* grow = nullptr;
-        if (WANT_GRID) grow = valid ? out.grid + ((size_t)pair * F * F * F + (size_t)base) : nullptr;
-        const double v0 = ZR[0];
-        sym_row<X3_DC>(tw, ZR + FP, ZI + FP, FP, n, HP, 0.0, 0, HP,
-                [&](int d0, double (&A)[X3_DC], double (&B)[X3_DC]) {
-                  // convergence point: stops the compiler from unswitching the chunk loop on `valid`,
-                  // which would put the loop under a divergent branch and forbid uniform-register operands
-                  __syncwarp();
-#pragma unroll
-                  for (int t = 0; t < X3_DC; ++t) {
-                    const int d = d0 + t;
-                    if (valid && d < H) {
-                      const double a = fma(2.0, A[t], v0), b = 2.0 * B[t];
-                      const double g1 = fabs(a + b);
-                      better32(bv, bi, g1, base + d);
-                      if (WANT_GRID && grow) grow[d] = g1;
-                      if (d != 0 && 2 * d != F) {
-                        const double g2 = fabs(a - b);
-                        better32(bv, bi, g2, base + (F - d));
-                        if (WANT_GRID && grow) grow[F - d] = g2;
-                      }
-                    }
-                  }
-                });
-      }
-      __syncthreads();
-    }
-    // ---- phase 4: block arg-max (numpy order) and parabola neighbours
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
-      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-      better32(bv, bi, ov, oi);
-    }
-    int* redi = reinterpret_cast<int*>(red + 32);
-    if ((tid & 31) == 0) {
-      red[tid >> 5] = bv;
-      redi[tid >> 5] = bi;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      bv = (tid < X3_THREADS / 32) ? red[tid] : -1.0;
-      bi = (tid < X3_THREADS / 32) ? redi[tid] : 0x7fffffff;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-        better32(bv, bi, ov, oi);
-      }
-      if (tid == 0) {
-        red[0] = bv;
-        redi[0] = bi;
-      }
-    }
-    __syncthreads();
-    bv = red[0];
-    bi = redi[0];
-    const bool ok = (bi != 0x7fffffff) && isfinite(bv);
-    const int bx = ok ? bi / (F * F) : 0;
-    const int by = ok ? (bi / F) % F : 0;
-    const int bz = ok ? bi % F : 0;
-    __syncthreads();
-    {
-      const int w = tid >> 5, lane = tid & 31;
-      if (w < 6) {
-        const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
-        int px = bx, py = by, pz = bz;
-        if (ax == 0) px = (bx + sgn + F) % F;
-        if (ax == 1) py = (by + sgn + F) % F;
-        if (ax == 2) pz = (bz + sgn + F) % F;
-        const double* Y = YIN + (size_t)px * K2 * RY;
-        double acc = 0.0;
-        for (int e = lane; e < M * M; e += 32) {
-          const int j = e / M, l = e - j * M;
-          double sj, cj, sl_, cl;
-          sincospi(2.0 * (double)((j * py) % F) / (double)F, &sj, &cj);
-          sincospi(2.0 * (double)((l * pz) % F) / (double)F, &sl_, &cl);
-          double vr, vi;
-          if (j == 0) {
-            vr = Y[l * 2];
-            vi = Y[l * 2 + 1];
-          } else {
-            const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
-            const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
-            vr = er * cj + oi * sj;   // Re(E cos - i O sin)
-            vi = ei * cj - orr * sj;  // Im
-          }
-          const double term = vr * cl + vi * sl_;
-          acc += (l == 0) ? term : 2.0 * term;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-        if (lane == 0) red[2 + w] = fabs(acc);
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      out.best_idx[3 * (size_t)pair + 0] = bx;
-      out.best_idx[3 * (size_t)pair + 1] = by;
-      out.best_idx[3 * (size_t)pair + 2] = bz;
-      out.best_val[pair] = bv;
-      const int b3[3] = {bx, by, bz};
-      for (int ax = 0; ax < 3; ++ax) {
-        const double y1 = red[2 + 2 * ax], y3 = red[2 + 2 * ax + 1], y2 = bv;
-        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
-        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
-      }
-      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
-    }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K_xf tensor-core path (per_xf4_kernel): the stages of per_xf3_kernel with every row transform
-// done by SymMma (fo_symdft.cuh): a warp owns 8 consecutive real rows and all outputs, the
-// products run on the FP64 tensor pipe (DMMA.8x8x4), E/O inputs are read once per tile from the
-// k-major shared arrays, the twiddle fragments live in registers.  Layouts as per_xf3_kernel except
-// that the stage-X pitch is padded to RXp == 8 (mod 16) doubles (the four k rows of an A fragment
-// then fall into two disjoint 64-byte bank halves).
+// K_xf tensor-core path (per_xf4_kernel): the stages of per_xf_kernel with every 1-D transform done
+// per REAL row (re / im parts are separate rows, inputs in E / O form) by SymMma (fo_symdft.cuh): a
+// warp owns 8 consecutive rows and all outputs, the products run on the FP64 tensor pipe
+// (DMMA.8x8x4), E/O inputs are read once per tile from k-major shared arrays, the twiddle fragments
+// live in registers.  The stage-X pitch is padded to RXp == 8 (mod 16) doubles (the four k rows of an
+// A fragment then fall into two disjoint 64-byte bank halves).  Earlier forms of this kernel (scalar
+// register tiles fed from shared memory; twiddles as uniform constant-bank operands) were limited by
+// operand delivery and issue slots, not by the FP64 pipe: profiles/r01_summary.md.
 // ------------------------------------------------------------------------------------------
 constexpr int X4_THREADS = 512;
 constexpr int X4_WARPS = X4_THREADS / 32;
@@ -1865,33 +1561,6 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
         default: FO_X5_LAUNCH(9); break;
       }
 #undef FO_X5_LAUNCH
-      FO_LAUNCH_CHECK(ctx);
-      return FO_OK;
-    }
-  }
-  {  // fast path: everything resident in shared memory, twiddles in the parameter constant bank
-    const X3Layout lay(n, F);
-    const size_t smem3 = lay.total * 8;
-    if (smem3 <= optin && (size_t)n * lay.HP <= (size_t)X3_TWMAX && !ctx->force_generic) {
-      static thread_local X3Tw tw;  // 16 KB: keep it off the stack
-      static thread_local int tw_n = -1, tw_F = -1;
-      if (tw_n != n || tw_F != F) {
-        fo_fill_tw(tw, n, F, lay.H, lay.HP);
-        tw_n = n;
-        tw_F = F;
-      }
-      fo_prof_scope prof(ctx, FO_PROF_PER_XF);
-      if (out.grid) {
-        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem3));
-        per_xf3_kernel<true><<<blocks, X3_THREADS, smem3, ctx->stream>>>(
-            tw, lay, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
-      } else {
-        FO_CUDA(ctx, cudaFuncSetAttribute(per_xf3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem3));
-        per_xf3_kernel<false><<<blocks, X3_THREADS, smem3, ctx->stream>>>(
-            tw, lay, d_bankA, d_bankB, d_pairs, (int)npairs, ngroups, n, F, kx, ky, kz, p->sigma, out);
-      }
       FO_LAUNCH_CHECK(ctx);
       return FO_OK;
     }

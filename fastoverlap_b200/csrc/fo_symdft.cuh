@@ -5,78 +5,14 @@
 // (re / im parts are separate rows) as
 //     P[d] = c0 + sum_{m=1..K} E[m] cos(2 pi m d/F),    Q[d] = sum_{m=1..K} O[m] sin(2 pi m d/F)
 // with E = c_m + c_-m, O = c_m - c_-m formed by the previous stage; outputs d and F-d then follow
-// from P -+ iQ.  A thread owns one row and walks over the outputs in chunks of DC: per (m, chunk)
-// it loads two doubles from shared memory for 2 DC DFMA.  The twiddle matrices live in the
-// kernel-parameter constant bank (__grid_constant__ FoTw): their indices are warp-uniform, so they
-// reach the DFMA as uniform-register operands (SASS: LDCU.64 + DFMA R, R, UR, R) and cost no
-// shared-memory or register-file bandwidth.  Why not a shared-memory-fed register tile: the LSU
-// returns 128 B/clk/SM = 16 doubles against 64 DFMA/clk/SM, so every loaded double has to feed
-// >= 4 DFMA (measured: profiles/r01_summary.md).
-//
-// Rules that keep ptxas on the uniform path (found the hard way):
-//   * all layout integers must come from the parameter bank (no integer division in the kernel);
-//   * control flow around sym_row must be warp-uniform (clamp invalid rows, mask the stores);
-//   * no per-thread global stores and no 64-bit index arithmetic in the epilogue.
+// from P -+ iQ: a quarter of the dense-DFT flops, exact for any F.
 #pragma once
 
-constexpr int FO_TWMAX = 1024;  // doubles per twiddle table in the parameter bank
-
-struct FoTw {
-  double c[FO_TWMAX];  // [m-1][HP]  cos(2 pi m d / F), zero for d >= H
-  double s[FO_TWMAX];  // [m-1][HP]  sin
-};
-
-// e / o point at E[1][row] / O[1][row]; consecutive m are kstride doubles apart.
-template <int DC, class Epi>
-__device__ __forceinline__ void sym_row(const FoTw& tw, const double* __restrict__ e,
-                                        const double* __restrict__ o, int kstride, int K, int HP,
-                                        double c0, int d_begin, int d_end, Epi&& epi) {
-  // The epilogue gets its own per-thread output counter dv, started from an opaque copy of d_begin:
-  // the compiler cannot merge it with the loop counter d0, so d0 (and with it every table index)
-  // stays in uniform registers even when the epilogue uses dv for per-thread addressing.
-  int dv;
-  asm volatile("mov.s32 %0, %1;" : "=r"(dv) : "r"(d_begin));
-  for (int d0 = d_begin; d0 < d_end; d0 += DC, dv += DC) {
-    double P[DC], Q[DC];
-#pragma unroll
-    for (int t = 0; t < DC; ++t) {
-      P[t] = c0;
-      Q[t] = 0.0;
-    }
-    const double* ep = e;
-    const double* op = o;
-    int ti = d0;
-    for (int k = 0; k < K; ++k) {
-      const double ev = *ep, ov = *op;
-#pragma unroll
-      for (int t = 0; t < DC; ++t) {
-        P[t] = fma(ev, tw.c[ti + t], P[t]);
-        Q[t] = fma(ov, tw.s[ti + t], Q[t]);
-      }
-      ep += kstride;
-      op += kstride;
-      ti += HP;
-    }
-    epi(dv, P, Q);
-  }
-}
-
-// host: fill the tables for transform length F, K harmonics, H = F/2+1 outputs padded to HP
-inline void fo_fill_tw(FoTw& tw, int K, int F, int H, int HP) {
-  const double twopi = 6.283185307179586476925286766559;
-  for (int m = 1; m <= K; ++m)
-    for (int d = 0; d < HP; ++d) {
-      const double ang = twopi * (double)((m * d) % F) / (double)F;
-      tw.c[(m - 1) * HP + d] = d < H ? cos(ang) : 0.0;
-      tw.s[(m - 1) * HP + d] = d < H ? sin(ang) : 0.0;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// FP64 tensor-core form of the same stage.  ncu (profiles/r01_summary.md) shows the scalar forms
-// are bound by operand delivery / issue slots, not by the FP64 pipe: a shared-memory-fed register
-// tile is capped by the 128 B/clk LSU return path, the uniform-operand form by one LDCU per DFMA
-// and by latency at 8-16 warps per SM.  mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) runs at the same
+// FP64 tensor-core form.  ncu (profiles/r01_summary.md) showed the scalar forms of this stage bound
+// by operand delivery / issue slots, not by the FP64 pipe: a shared-memory-fed register tile is
+// capped by the 128 B/clk LSU return path (16 doubles against 64 DFMA per clock and SM), a
+// uniform-constant-operand form by one LDCU per DFMA and by latency at 8-16 warps per SM.  mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) runs at the same
 // 37 TFLOP/s as DFMA on B200 (scripts/dmma_peak.cu: 37.2 vs 33.9 TFLOP/s measured) while one
 // instruction carries 256 MACs and the operands are spread over the warp, so the contraction-bound
 // stages go to the tensor pipe (BASELINE.json north_star: "... placed on the FP64 tensor-core pipe
