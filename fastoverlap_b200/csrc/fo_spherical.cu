@@ -277,11 +277,12 @@ sph_direct_kernel(const double2* __restrict__ YA, const double2* __restrict__ YB
 //   MODE 1   T[r][k]   = sum_j  YA[j][r] B_l[j][k]              (2(l+1) x N x N)
 //   MODE 2   C2[r][r'] = sum_k  T[r][k]  YB[k][r']              (2(l+1) x 2(l+1) x N)
 // and sph_direct_combine_kernel forms I[l,+-m1,m2] from the four real products in C2.
-// CTA tile 64 x 64 x 16, 8 warps as 2 (rows) x 4 (cols), warp tile 32 x 16; k-major shared tiles with
-// pitch 72 (== 8 mod 32: the four k rows of a fragment fall into disjoint bank groups); global loads
-// of the next k tile are in flight while the current one is multiplied.
+// CTA tile 64 x 64 x 32, 8 warps as 2 (rows) x 4 (cols), warp tile 32 x 16; k-major shared tiles with
+// pitch 72 (== 8 mod 32: the four k rows of a fragment fall into disjoint bank groups); a three-stage
+// cp.async pipeline keeps two k tiles in flight while the current one is multiplied.
 // ------------------------------------------------------------------------------------------
-constexpr int DG_TM = 64, DG_TN = 64, DG_TK = 16, DG_LD = 72, DG_THREADS = 256;
+constexpr int DG_TM = 64, DG_TN = 64, DG_TK = 32, DG_LD = 72, DG_THREADS = 256, DG_STAGES = 3;
+constexpr size_t DG_SMEM = (size_t)DG_STAGES * 2 * DG_TK * DG_LD * 8;
 
 __host__ __device__ inline size_t dg_c2_off(int l) { return (size_t)2 * l * (l + 1) * (2 * l + 1) / 3; }
 
@@ -289,8 +290,7 @@ template <int MODE>
 __global__ void __launch_bounds__(DG_THREADS, 2)
 sph_direct_gemm_kernel(const double* __restrict__ Yreal, const double* __restrict__ X, int natoms, int L,
                        double* __restrict__ Cout) {
-  __shared__ double As[2][DG_TK * DG_LD];
-  __shared__ double Bs[2][DG_TK * DG_LD];
+  extern __shared__ double smg[];  // [DG_STAGES][A | B][DG_TK][DG_LD]
   const int L1 = L + 1, NLM = nlm_of(L);
   const int l = blockIdx.z % L1;
   const size_t p = blockIdx.z / L1;
@@ -324,30 +324,60 @@ sph_direct_gemm_kernel(const double* __restrict__ Yreal, const double* __restric
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
-  // loader coordinates
-  const int a_kk = MODE == 1 ? (tid >> 4) : (tid >> 6) * 4;  // MODE 1: one k, 4 rows; MODE 2: one row, 4 k
-  const int a_r = MODE == 1 ? (tid & 15) * 4 : (tid & 63);
-  const int b_kk = tid >> 4, b_n = (tid & 15) * 4;
-  double ra[4], rb[4];
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = row0 + a_r + (MODE == 1 ? i : 0);
-      const int kk = k0 + a_kk + (MODE == 1 ? 0 : i);
-      ra[i] = (r < M && kk < K) ? Ay[(size_t)r * rsA + (size_t)kk * csA] : 0.0;
-      const int n = col0 + b_n + i, kb = k0 + b_kk;
-      rb[i] = (n < N && kb < K) ? Bx[(size_t)kb * rsB + n] : 0.0;
-    }
+  // Operand tiles go global -> shared with cp.async (zero fill outside the matrices), three stages of
+  // 32 k each: one barrier per 512 DMMA of the CTA, no register staging.
+  auto As = [&](int st) { return smg + (size_t)st * 2 * DG_TK * DG_LD; };
+  auto Bs = [&](int st) { return smg + (size_t)st * 2 * DG_TK * DG_LD + DG_TK * DG_LD; };
+  auto cp16 = [](double* dst, const double* src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
   };
-  auto sstore = [&](int buf) {
+  auto cp8 = [](double* dst, const double* src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+  };
+  auto issue = [&](int kt) {
+    const int k0 = kt * DG_TK;
+    double* as = As(kt % DG_STAGES);
+    double* bs = Bs(kt % DG_STAGES);
+    if (MODE == 1) {
+      // A(r, kk): rows contiguous and 16-byte aligned (interleaved re / im); 64 x 32 doubles = 1024 chunks
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (MODE == 1)
-        As[buf][a_kk * DG_LD + a_r + i] = ra[i];
-      else
-        As[buf][(a_kk + i) * DG_LD + a_r] = ra[i];
-      Bs[buf][b_kk * DG_LD + b_n + i] = rb[i];
+      for (int i = 0; i < 4; ++i) {
+        const int c = tid + i * DG_THREADS;      // chunk: kk = c / 32, rows 2 (c % 32) ..
+        const int kk = c >> 5, r = (c & 31) * 2;
+        const bool ok = row0 + r < M && k0 + kk < K;  // M is even: a chunk is all in or all out
+        cp16(as + kk * DG_LD + r, ok ? Ay + (size_t)(k0 + kk) * csA + row0 + r : Ay, ok);
+      }
+      // B(kk, n): 8-byte aligned only (natoms may be odd); 32 x 64 doubles
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = tid + i * DG_THREADS;
+        const int kk = c >> 6, n = c & 63;
+        const bool ok = col0 + n < N && k0 + kk < K;
+        cp8(bs + kk * DG_LD + n, ok ? Bx + (size_t)(k0 + kk) * rsB + col0 + n : Bx, ok);
+      }
+    } else {
+      // A(r, kk): contiguous along kk in memory, k-major in shared memory: element-wise
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = tid + i * DG_THREADS;
+        const int r = c >> 5, kk = c & 31;
+        const bool ok = row0 + r < M && k0 + kk < K;
+        cp8(as + kk * DG_LD + r, ok ? Ay + (size_t)(row0 + r) * rsA + k0 + kk : Ay, ok);
+      }
+      // B(kk, n): interleaved re / im columns, 16-byte aligned
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = tid + i * DG_THREADS;
+        const int kk = c >> 5, n = (c & 31) * 2;
+        const bool ok = col0 + n < N && k0 + kk < K;
+        cp16(bs + kk * DG_LD + n, ok ? Bx + (size_t)(k0 + kk) * rsB + col0 + n : Bx, ok);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   double acc[4][2][2];
 #pragma unroll
@@ -358,14 +388,17 @@ sph_direct_gemm_kernel(const double* __restrict__ Yreal, const double* __restric
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) live[mt] = row0 + wm * 32 + mt * 8 < M;
   const int nkt = (K + DG_TK - 1) / DG_TK;
-  gload(0);
-  sstore(0);
-  __syncthreads();
+  issue(0);
+  if (nkt > 1) issue(1);
   for (int kt = 0; kt < nkt; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nkt) gload((kt + 1) * DG_TK);
-    const double* as = As[buf] + wm * 32 + g;
-    const double* bs = Bs[buf] + wn * 16 + g;
+    if (kt + 1 < nkt)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile kt visible to all; everyone is done with tile kt-1 (its stage is reused next)
+    if (kt + 2 < nkt) issue(kt + 2);
+    const double* as = As(kt % DG_STAGES) + wm * 32 + g;
+    const double* bs = Bs(kt % DG_STAGES) + wn * 16 + g;
 #pragma unroll
     for (int k4 = 0; k4 < DG_TK / 4; ++k4) {
       const int krow = (k4 * 4 + t4) * DG_LD;
@@ -379,8 +412,6 @@ sph_direct_gemm_kernel(const double* __restrict__ Yreal, const double* __restric
         }
       }
     }
-    if (kt + 1 < nkt) sstore(buf ^ 1);
-    __syncthreads();
   }
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
@@ -1171,12 +1202,13 @@ sph_isoft_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
   }
 }
 
-// Grid value at integer point (a, k, g) by the direct Wigner sum (orientation sign so on odd l).
-__device__ double iso_point(const double2* __restrict__ Ip, const double* __restrict__ Dt, DtStride ds,
-                            int L, int a, int k, int g, double so, int lane) {
+// Grid value at integer point (a, k, g) by the direct Wigner sum (orientation sign so on odd l):
+// partial sum over the items tid, tid + nthreads, ... of one thread.
+__device__ double iso_point_partial(const double2* __restrict__ Ip, const double* __restrict__ Dt, DtStride ds,
+                                    int L, int a, int k, int g, double so, int tid, int nthreads) {
   const int W = 2 * L + 1, L1 = L + 1, F = 2 * L1;
   double acc = 0.0;
-  for (int item = lane; item < L1 * W; item += 32) {
+  for (int item = tid; item < L1 * W; item += nthreads) {
     const int m1i = item % W, m2 = item / W;
     const int m1 = m1i - L;
     const int am1 = m1 < 0 ? -m1 : m1;
@@ -1197,19 +1229,21 @@ __device__ double iso_point(const double2* __restrict__ Ip, const double* __rest
     const double term = sr * cs - si * sn;
     acc += (m2 == 0) ? term : 2.0 * term;
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
   return acc;
 }
 
-// One CTA (8 warps) per (pair, orientation): reduce the chunk maxima, then the 6 neighbours.
+// findMax (utils.py:319-338) of the generic / large-bandwidth paths.  One CTA per ((pair,
+// orientation), neighbour w): every CTA reduces the chunk maxima (cheap), then all 256 threads share
+// the Wigner sum of neighbour w (axis w >> 1, step +1 / -1) -- at Jmax = 63 that is 8128 (m1, m2)
+// items of up to 64 levels, which a single warp per neighbour took 2.2 ms for (profiles/r01_summary.md).
 __global__ void __launch_bounds__(256)
 sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, DtStride ds, int L,
-                 int norient, int nchunk, const double* __restrict__ part_val, const long long* __restrict__ part_idx,
-                 long long* __restrict__ best_idx, double* __restrict__ best_val,
-                 double* __restrict__ frac_idx) {
-  __shared__ double nb[6];
+                 int norient, int nchunk, const double* __restrict__ part_val,
+                 const long long* __restrict__ part_idx, long long* __restrict__ best_idx,
+                 double* __restrict__ best_val, double* __restrict__ nbv) {
+  __shared__ double red[8];
   const size_t po = blockIdx.x;
+  const int w = blockIdx.y;
   const size_t p = po / norient;
   const int o = (int)(po % norient);
   const int F = 2 * (L + 1);
@@ -1219,23 +1253,35 @@ sph_final_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ D
   const bool ok = bi != 0x7fffffffffffffffLL;
   const int b3[3] = {ok ? (int)(bi / ((long long)F * F)) : 0, ok ? (int)((bi / F) % F) : 0,
                      ok ? (int)(bi % F) : 0};
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (w < 6) {
-    const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
-    int q[3] = {b3[0], b3[1], b3[2]};
-    q[ax] = (q[ax] + sgn + F) % F;
-    const double v = iso_point(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, ds, L, q[0], q[1],
-                               q[2], o ? -1.0 : 1.0, lane);
-    if (lane == 0) nb[w] = fabs(v);
-  }
+  const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
+  int q[3] = {b3[0], b3[1], b3[2]};
+  q[ax] = (q[ax] + sgn + F) % F;
+  double v = iso_point_partial(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), Dt, ds, L, q[0], q[1], q[2],
+                               o ? -1.0 : 1.0, threadIdx.x, blockDim.x);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x == 0) {
-    best_val[po] = bv;
-    for (int ax = 0; ax < 3; ++ax) {
-      best_idx[po * 3 + ax] = b3[ax];
-      const double y1 = nb[2 * ax], y3 = nb[2 * ax + 1], y2 = fabs(bv);
-      frac_idx[po * 3 + ax] = (double)b3[ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    nbv[po * 6 + w] = fabs(t);
+    if (w == 0) {
+      best_val[po] = bv;
+      for (int a3 = 0; a3 < 3; ++a3) best_idx[po * 3 + a3] = b3[a3];
     }
+  }
+}
+
+// parabola through the maximum and its two neighbours per axis -> fractional index
+__global__ void sph_parabola_kernel(size_t npo, const long long* __restrict__ best_idx,
+                                    const double* __restrict__ best_val, const double* __restrict__ nbv,
+                                    double* __restrict__ frac_idx) {
+  const size_t po = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (po >= npo) return;
+  for (int ax = 0; ax < 3; ++ax) {
+    const double y1 = nbv[po * 6 + 2 * ax], y3 = nbv[po * 6 + 2 * ax + 1], y2 = fabs(best_val[po]);
+    frac_idx[po * 3 + ax] = (double)best_idx[po * 3 + ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
   }
 }
 
@@ -2037,9 +2083,14 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
     sph_isoft_big_kernel<<<(unsigned)blocks, IB_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient,
                                                                              (size_t)npairs, o);
     FO_LAUNCH_CHECK(ctx);
-    sph_final_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+    void* nbv = nullptr;
+    FO_CHECK(fo_scratch(ctx, FO_SCR_DBG, (size_t)npairs * norient * 48 + 64, &nbv));
+    sph_final_kernel<<<dim3((unsigned)(npairs * norient), 6), 256, 0, ctx->stream>>>(
         d_Ihalf, ctx->wig.d_table, dt_stride(L, true), L, norient, F, o.part_val, o.part_idx, d_best_idx,
-        d_best_val, d_frac);
+        d_best_val, (double*)nbv);
+    FO_LAUNCH_CHECK(ctx);
+    sph_parabola_kernel<<<grid_for((size_t)npairs * norient, 128), 128, 0, ctx->stream>>>(
+        (size_t)npairs * norient, d_best_idx, d_best_val, (const double*)nbv, d_frac);
     FO_LAUNCH_CHECK(ctx);
     return FO_OK;
   }
@@ -2072,9 +2123,14 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       sph_isoft_kernel<1><<<blocks, IS_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient, nchunk, o);
     }
     FO_LAUNCH_CHECK(ctx);
-    sph_final_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+    void* nbv = nullptr;
+    FO_CHECK(fo_scratch(ctx, FO_SCR_DBG, (size_t)npairs * norient * 48 + 64, &nbv));
+    sph_final_kernel<<<dim3((unsigned)(npairs * norient), 6), 256, 0, ctx->stream>>>(
         d_Ihalf, ctx->wig.d_table, dt_stride(L, false), L, norient, nchunk, o.part_val, o.part_idx, d_best_idx,
-        d_best_val, d_frac);
+        d_best_val, (double*)nbv);
+    FO_LAUNCH_CHECK(ctx);
+    sph_parabola_kernel<<<grid_for((size_t)npairs * norient, 128), 128, 0, ctx->stream>>>(
+        (size_t)npairs * norient, d_best_idx, d_best_val, (const double*)nbv, d_frac);
     FO_LAUNCH_CHECK(ctx);
   }
   return FO_OK;
@@ -2125,10 +2181,12 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
     double* C2 = T + (size_t)np * 2 * NLM * natoms;
     const unsigned rowt = (unsigned)((2 * (L + 1) + DG_TM - 1) / DG_TM);
     dim3 g1((unsigned)((natoms + DG_TN - 1) / DG_TN), rowt, (unsigned)(np * (L + 1)));
-    sph_direct_gemm_kernel<1><<<g1, DG_THREADS, 0, ctx->stream>>>((const double*)YA, Bes, (int)natoms, L, T);
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+    sph_direct_gemm_kernel<1><<<g1, DG_THREADS, DG_SMEM, ctx->stream>>>((const double*)YA, Bes, (int)natoms, L, T);
     FO_LAUNCH_CHECK(ctx);
     dim3 g2(rowt, rowt, (unsigned)(np * (L + 1)));
-    sph_direct_gemm_kernel<2><<<g2, DG_THREADS, 0, ctx->stream>>>((const double*)YB, T, (int)natoms, L, C2);
+    sph_direct_gemm_kernel<2><<<g2, DG_THREADS, DG_SMEM, ctx->stream>>>((const double*)YB, T, (int)natoms, L, C2);
     FO_LAUNCH_CHECK(ctx);
     sph_direct_combine_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
         C2, L, (size_t)np, d_Ihalf);
