@@ -1938,6 +1938,228 @@ sph_isoft_big_kernel(const double2* __restrict__ Ihalf, const double* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// sph_isoft_big2_kernel: the large-bandwidth transform with stages A and B on the FP64 tensor pipe.
+// Same decomposition as sph_isoft_big_kernel (CTA per (beta plane, pair, orientation), K5 per block of
+// IB2_MB values of m2), but
+//   * stage A reads its E / O fragments straight from the S block (E = S(+m1) + S(-m1), O = S(+) - S(-),
+//     pitch 2 IB2_MB + 8 doubles: conflict-free) and writes U re / im k-major (BR / BI [m2][a]);
+//   * stage B: rows a, half-complex -> real, as in sph_isoft3_kernel;
+//   * a work unit is (8-row tile, group of 3 column tiles): no template parameter depends on Jmax; the
+//     twiddles come from a one-period table TW[F] through the running index (m d) mod F.
+// ------------------------------------------------------------------------------------------
+constexpr int IB2_THREADS = 512;
+constexpr int IB2_MB = 16;
+constexpr int IB2_SP = 2 * IB2_MB + 8;  // doubles per m1 row of the S block (== 8 mod 32 for MB = 16)
+constexpr int IB2_NS = 3;               // column tiles per unit
+
+struct Ib2Layout {
+  int L, L1, W, F, H, NT, NG, KS, FBp;
+  int o_tw, o_s, o_br, o_bi, o_red, total;  // doubles
+  Ib2Layout() {}
+  explicit Ib2Layout(int L_) {
+    L = L_;
+    L1 = L + 1;
+    W = 2 * L + 1;
+    F = 2 * L1;
+    H = L1 + 1;
+    NT = (H + 7) / 8;
+    NG = (NT + IB2_NS - 1) / IB2_NS;
+    KS = (L + 3) / 4;
+    FBp = F + ((8 - F) % 32 + 32) % 32;  // == 8 (mod 32)
+    o_tw = 0;
+    o_s = o_tw + 2 * F;
+    o_br = o_s + W * IB2_SP;
+    o_bi = o_br + L1 * FBp;
+    o_red = o_bi + L1 * FBp;
+    total = o_red + 48;
+  }
+};
+
+__global__ void __launch_bounds__(IB2_THREADS, 1)
+sph_isoft_big2_kernel(const __grid_constant__ Ib2Layout Y, const double2* __restrict__ Ihalf,
+                      const double* __restrict__ DtK, int norient, size_t npairs, IsoOut out) {
+  extern __shared__ double smb2[];
+  const int L = Y.L, L1 = Y.L1, W = Y.W, F = Y.F, H = Y.H, NT = Y.NT, NG = Y.NG, KS = Y.KS, FBp = Y.FBp;
+  double2* TW = reinterpret_cast<double2*>(smb2 + Y.o_tw);  // [F] (cos, sin)(2 pi t / F)
+  double* Sd = smb2 + Y.o_s;    // S block as doubles: [m1 + L][IB2_SP], (mm, part) -> 2 mm + part
+  double* BR = smb2 + Y.o_br;   // [m2][FBp]  Re U[a][m2]
+  double* BI = smb2 + Y.o_bi;
+  double* red = smb2 + Y.o_red;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  constexpr int NWARP = IB2_THREADS / 32;
+  const int o = (int)(blockIdx.x % norient);
+  const size_t p = (blockIdx.x / norient) % npairs;
+  const int k = (int)(blockIdx.x / ((size_t)norient * npairs));
+  const double so = o ? -1.0 : 1.0;
+  for (int t = tid; t < F; t += IB2_THREADS) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+    TW[t] = make_double2(cs, sn);
+  }
+  const double2* Ip = Ihalf + p * (size_t)L1 * W * L1;
+  const double* Dk = DtK + (size_t)k * L1 * W * L1;
+  for (int m2a = 0; m2a < L1; m2a += IB2_MB) {
+    const int nb = min(IB2_MB, L1 - m2a);
+    __syncthreads();  // S of the previous block is consumed; TW is ready
+    // ---- K5 for m2 in [m2a, m2a + nb): S[m1][mm] = sum_l so^l d I
+    for (int it = tid; it < W * nb; it += IB2_THREADS) {
+      const int mm = it % nb, m1i = it / nb;
+      const int m2 = m2a + mm, m1 = m1i - L;
+      const int am1 = m1 < 0 ? -m1 : m1;
+      const int l0 = am1 > m2 ? am1 : m2;
+      const size_t item = (size_t)m2 * W + m1i;
+      const double2* ip = Ip + item * L1;
+      const double* dp = Dk + item * L1;
+      double2 ae = make_double2(0.0, 0.0), ao = ae;
+      for (int l = l0; l <= L; ++l) {
+        const double dv = dp[l];
+        const double2 c = ip[l];
+        if (l & 1) {
+          ao.x = fma(dv, c.x, ao.x);
+          ao.y = fma(dv, c.y, ao.y);
+        } else {
+          ae.x = fma(dv, c.x, ae.x);
+          ae.y = fma(dv, c.y, ae.y);
+        }
+      }
+      *reinterpret_cast<double2*>(Sd + (size_t)m1i * IB2_SP + 2 * mm) =
+          make_double2(fma(so, ao.x, ae.x), fma(so, ao.y, ae.y));
+    }
+    // rows of a partial last block: keep them finite
+    for (int it = tid; it < W * (IB2_MB - nb); it += IB2_THREADS) {
+      const int mm = nb + it % (IB2_MB - nb), m1i = it / (IB2_MB - nb);
+      *reinterpret_cast<double2*>(Sd + (size_t)m1i * IB2_SP + 2 * mm) = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    // ---- stage A: rows (mm, part) of the block, k = m1 = 1..L, outputs a; units (row tile, column group)
+    const int ntile = (2 * nb + 7) >> 3;
+    for (int unit = warp; unit < ntile * NG; unit += NWARP) {
+      const int tile = unit % ntile, cg = unit / ntile;
+      const int row = tile * 8 + g;                 // 2 mm + part
+      const int part = row & 1, mm = row >> 1;
+      const bool rvalid = mm < nb;
+      const double c0 = Sd[(size_t)L * IB2_SP + row];
+      double P[IB2_NS][2], Q[IB2_NS][2];
+      int idx[IB2_NS], dstep[IB2_NS];
+      bool dval[IB2_NS];
+#pragma unroll
+      for (int u = 0; u < IB2_NS; ++u) {
+        const int d = (cg * IB2_NS + u) * 8 + g;    // output of this lane's B-fragment column
+        dval[u] = cg * IB2_NS + u < NT && d < H;
+        idx[u] = ((t4 + 1) * d) % F;
+        dstep[u] = (4 * d) % F;
+        P[u][0] = P[u][1] = c0;
+        Q[u][0] = Q[u][1] = 0.0;
+      }
+      for (int ks = 0; ks < KS; ++ks) {
+        const int m = 4 * ks + t4 + 1;
+        const int mc = m <= L ? m : L;
+        const double sp = Sd[(size_t)(L + mc) * IB2_SP + row], sm = Sd[(size_t)(L - mc) * IB2_SP + row];
+        const double fe = sp + sm, fo = sp - sm;
+#pragma unroll
+        for (int u = 0; u < IB2_NS; ++u) {
+          const double2 w = TW[idx[u]];
+          const bool on = dval[u] && m <= L;
+          fo_dmma(P[u], fe, on ? w.x : 0.0);
+          fo_dmma(Q[u], fo, on ? w.y : 0.0);
+          idx[u] += dstep[u];
+          idx[u] -= idx[u] >= F ? F : 0;
+        }
+      }
+      double* Bout = (part ? BI : BR) + (size_t)(m2a + mm) * FBp;
+      const double sgn = part ? 1.0 : -1.0;
+#pragma unroll
+      for (int u = 0; u < IB2_NS; ++u)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = (cg * IB2_NS + u) * 8 + t4 * 2 + q;  // output of this lane's C-fragment column
+          const double qx = __shfl_xor_sync(0xffffffffu, Q[u][q], 4);
+          if (rvalid && cg * IB2_NS + u < NT && d < H) {
+            Bout[d] = fma(sgn, qx, P[u][q]);
+            if (d != 0 && 2 * d != F) Bout[F - d] = fma(-sgn, qx, P[u][q]);
+          }
+        }
+    }
+  }
+  __syncthreads();
+  // ---- stage B: rows a, k = m2 = 1..L (re with cos, im with sin), outputs gamma; arg-max
+  double bv = -1e300;
+  long long bi = 0x7fffffffffffffffLL;
+  {
+    const int ntile = (F + 7) >> 3;  // F = 2 (L + 1) is a multiple of 8 only when L + 1 is a multiple of 4
+    for (int unit = warp; unit < ntile * NG; unit += NWARP) {
+      const int tile = unit % ntile, cg = unit / ntile;
+      const int a = tile * 8 + g;
+      const bool avalid = a < F;
+      const int ac = avalid ? a : 0;
+      const double v0h = 0.5 * BR[ac];
+      double A[IB2_NS][2], Bq[IB2_NS][2];
+      int idx[IB2_NS], dstep[IB2_NS];
+      bool dval[IB2_NS];
+#pragma unroll
+      for (int u = 0; u < IB2_NS; ++u) {
+        const int d = (cg * IB2_NS + u) * 8 + g;
+        dval[u] = cg * IB2_NS + u < NT && d < H;
+        idx[u] = ((t4 + 1) * d) % F;
+        dstep[u] = (4 * d) % F;
+        A[u][0] = A[u][1] = v0h;
+        Bq[u][0] = Bq[u][1] = 0.0;
+      }
+      for (int ks = 0; ks < KS; ++ks) {
+        const int m = 4 * ks + t4 + 1;
+        const int mc = m <= L ? m : L;
+        const double vr = BR[(size_t)mc * FBp + ac], vi = BI[(size_t)mc * FBp + ac];
+#pragma unroll
+        for (int u = 0; u < IB2_NS; ++u) {
+          const double2 w = TW[idx[u]];
+          const bool on = dval[u] && m <= L;
+          fo_dmma(A[u], vr, on ? w.x : 0.0);
+          fo_dmma(Bq[u], vi, on ? w.y : 0.0);
+          idx[u] += dstep[u];
+          idx[u] -= idx[u] >= F ? F : 0;
+        }
+      }
+      const long long base = ((long long)ac * F + k) * F;
+      double* grow = out.grid ? out.grid + ((p * norient + o) * (size_t)F * F * F + (size_t)base) : nullptr;
+#pragma unroll
+      for (int u = 0; u < IB2_NS; ++u)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = (cg * IB2_NS + u) * 8 + t4 * 2 + q;
+          if (avalid && cg * IB2_NS + u < NT && d < H) {
+            const double g1 = 2.0 * (A[u][q] - Bq[u][q]);  // Re(V e^{+i theta})
+            better_s(bv, bi, g1, base + d);
+            if (grow) grow[d] = g1;
+            if (d != 0 && 2 * d != F) {
+              const double g2 = 2.0 * (A[u][q] + Bq[u][q]);
+              better_s(bv, bi, g2, base + (F - d));
+              if (grow) grow[F - d] = g2;
+            }
+          }
+        }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+    const long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+    better_s(bv, bi, ov, oi);
+  }
+  long long* redi = (long long*)(red + 16);
+  if (lane == 0) {
+    red[warp] = bv;
+    redi[warp] = bi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NWARP; ++w) better_s(bv, bi, red[w], redi[w]);
+    out.part_val[(p * norient + o) * (size_t)F + k] = bv;
+    out.part_idx[(p * norient + o) * (size_t)F + k] = bi;
+  }
+}
+
 size_t isoft_big_smem(int L) {
   const int W = 2 * L + 1, L1 = L + 1, F = 2 * L1, M2p = L1 | 1;
   return ((size_t)F + (size_t)W * IB_MB + (size_t)F * M2p) * 16 + 32 * 8;
@@ -2077,11 +2299,19 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
     o.part_idx = (long long*)(o.part_val + (size_t)npairs * norient * F);
     o.grid = d_grid;
     fo_prof_scope prof(ctx, FO_PROF_SPH_ISOFT);
-    FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t blocks = (size_t)F * npairs * norient;
     if (blocks > 0x7fffffffULL) return fo_fail(ctx, FO_ERR_UNSUPPORTED, "too many pairs in one iSOFT launch");
-    sph_isoft_big_kernel<<<(unsigned)blocks, IB_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient,
-                                                                             (size_t)npairs, o);
+    const Ib2Layout Y2(L);
+    const size_t smem2 = (size_t)Y2.total * 8;
+    if (!ctx->force_generic && smem2 <= ctx->prop.sharedMemPerBlockOptin) {  // stages A / B on the tensor pipe
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_big2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      sph_isoft_big2_kernel<<<(unsigned)blocks, IB2_THREADS, smem2, ctx->stream>>>(Y2, d_Ihalf, ctx->wig.d_table,
+                                                                                  norient, (size_t)npairs, o);
+    } else {
+      FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sph_isoft_big_kernel<<<(unsigned)blocks, IB_THREADS, smem, ctx->stream>>>(d_Ihalf, ctx->wig.d_table, L, norient,
+                                                                               (size_t)npairs, o);
+    }
     FO_LAUNCH_CHECK(ctx);
     void* nbv = nullptr;
     FO_CHECK(fo_scratch(ctx, FO_SCR_DBG, (size_t)npairs * norient * 48 + 64, &nbv));
