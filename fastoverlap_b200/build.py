@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    objs = []
+    objs, cmds = [], []
     for src in srcs:
         obj = os.path.join(LIBDIR, os.path.basename(src).replace(".cu", ".o"))
         objs.append(obj)
@@ -66,7 +66,14 @@ def build(force=False, verbose=False):
                 if os.path.basename(src) not in HOST_ONLY:
                     cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
+            cmds.append(cmd)
+    if verbose:  # keep the ptxas reports of the translation units apart
+        for cmd in cmds:
             subprocess.run(cmd, check=True)
+    elif cmds:   # the translation units are independent: compile them concurrently
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(cmds)) as pool:
+            list(pool.map(lambda c: subprocess.run(c, check=True), cmds))
     out = lib_path()
     if force or _stale(out, objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + \
