@@ -327,14 +327,16 @@ def test_direct_coeffs_tensor_core_gemm(ctx, N, J, groups, force):
     assert np.allclose(res[1], res0[1], rtol=1e-11)
 
 
-def test_large_cluster_rotation_recovery(ctx):
-    """configs[3] shape at reduced size: lattice blob of 400 atoms, Jmax = 31, rotated + permuted +
-    jittered partner; the alignment recovers the transformation (distance ~ noise level)."""
+@pytest.mark.parametrize("N,J", [(400, 31), (1000, 63)])
+def test_large_cluster_rotation_recovery(ctx, N, J):
+    """BASELINE.json configs[3] (LJ1000-size clusters at high Jmax; also at reduced size): lattice blob,
+    rotated + permuted + jittered partner; the alignment recovers the transformation (distance ~ noise
+    level).  Size-independent property at the full configuration size."""
     from fastoverlap_b200 import SphericalAlign
     rng = np.random.default_rng(1000)
-    g = np.arange(-6, 7) * 1.12
+    g = np.arange(-8, 9) * 1.12
     pts = np.array(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1).T
-    pts = pts[np.argsort(np.linalg.norm(pts, axis=1), kind="stable")[:400]]
+    pts = pts[np.argsort(np.linalg.norm(pts, axis=1), kind="stable")[:N]]
     A = pts + rng.normal(scale=0.03, size=pts.shape)
     A -= A.mean(0)
     q = rng.normal(size=4)
@@ -344,8 +346,8 @@ def test_large_cluster_rotation_recovery(ctx):
                   [2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)],
                   [2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d]])
     noise = rng.normal(scale=0.02, size=A.shape)
-    B = (A + noise).dot(R.T)[rng.permutation(400)]
+    B = (A + noise).dot(R.T)[rng.permutation(N)]
     B -= B.mean(0)
-    sa = SphericalAlign(0.37, 31, ctx=ctx)
+    sa = SphericalAlign(0.37, J, ctx=ctx)
     dist = sa(A, B)[0]
     assert dist < 2.0 * np.linalg.norm(noise), dist
