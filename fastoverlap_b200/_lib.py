@@ -90,6 +90,21 @@ SIGNATURES = {
     "fo_sph_align_bank": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
                                          ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
+    "fo_sph_refine_rotations": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                               c_void_p, c_void_p, c_void_p]),
+    "fo_sph_overlap_gradient": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                               c_void_p, c_void_p, c_void_p]),
+    "fo_sph_align_pairs_refined": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                                  ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                                  ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p]),
+    "fo_sph_align_pairs_refined_dev": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                                      ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                      c_void_p, c_void_p]),
+    "fo_sph_align_bank_refined": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                                 ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p]),
     "fo_sph_wigner_table": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p]),
     "fo_grid_find_peaks": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_i64p, ctypes.c_int64,
                                           ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -509,6 +524,59 @@ class Context(object):
                     "fo_sph_align_pairs")
         return bi, bv, fr, grid, st
 
+    def sph_refine_rotations(self, Ilmm, Jmax, euler):
+        """maxOverlap on the device: (euler_out (P,3), overlap (P,), nevals (P,))."""
+        L = int(Jmax)
+        Ilmm = np.ascontiguousarray(Ilmm, dtype=np.complex128).reshape(-1, L + 1, 2 * L + 1, 2 * L + 1)
+        P = Ilmm.shape[0]
+        euler = _f64(euler).reshape(P, 3)
+        out = np.empty((P, 3), np.float64)
+        ov = np.empty(P, np.float64)
+        ne = np.zeros(P, np.int32)
+        self._check(self._lib.fo_sph_refine_rotations(self._h, _ptr(Ilmm), P, L, _ptr(euler), _ptr(out), _ptr(ov),
+                                                      _ptr(ne)), "fo_sph_refine_rotations")
+        return out, ov, ne
+
+    def sph_overlap_gradient(self, Ilmm, Jmax, euler):
+        """(value (P,), grad (P,3), hess (P,6)) of the un-weighted overlap at the Euler angles."""
+        L = int(Jmax)
+        Ilmm = np.ascontiguousarray(Ilmm, dtype=np.complex128).reshape(-1, L + 1, 2 * L + 1, 2 * L + 1)
+        P = Ilmm.shape[0]
+        euler = _f64(euler).reshape(P, 3)
+        val = np.empty(P, np.float64)
+        grad = np.empty((P, 3), np.float64)
+        hess = np.empty((P, 6), np.float64)
+        self._check(self._lib.fo_sph_overlap_gradient(self._h, _ptr(Ilmm), P, L, _ptr(euler), _ptr(val), _ptr(grad),
+                                                      _ptr(hess)), "fo_sph_overlap_gradient")
+        return val, grad, hess
+
+    def sph_align_pairs_refined(self, posA, posB, Jmax, sigma, invert=True):
+        """Hot path + continuous refinement: (best_idx, best_val, frac_idx, euler (P,O,3), overlap (P,O), status)."""
+        posA = _f64(posA)
+        posB = _f64(posB)
+        if posA.ndim == 2:
+            posA = posA[None]
+            posB = posB[None]
+        P, N, _ = posA.shape
+        self._ensure_perm(N)
+        L = int(Jmax)
+        bi, bv, fr, _ = self._sph_outputs(P, L, invert, False)
+        eu = np.empty_like(fr)
+        ov = np.empty_like(bv)
+        st = np.zeros(P, np.int32)
+        self._check(self._lib.fo_sph_align_pairs_refined(self._h, _ptr(posA), _ptr(posB), P, N, L, float(sigma),
+                                                         int(bool(invert)), _ptr(bi), _ptr(bv), _ptr(fr), _ptr(eu),
+                                                         _ptr(ov), _ptr(st)), "fo_sph_align_pairs_refined")
+        return bi, bv, fr, eu, ov, st
+
+    def sph_align_pairs_refined_dev(self, d_posA, d_posB, P, N, Jmax, sigma, invert, d_best_idx, d_best_val,
+                                    d_frac, d_euler, d_overlap, d_status=0):
+        self._ensure_perm(N)
+        self._check(self._lib.fo_sph_align_pairs_refined_dev(
+            self._h, c_void_p(d_posA), c_void_p(d_posB), int(P), int(N), int(Jmax), float(sigma),
+            int(bool(invert)), c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac),
+            c_void_p(d_euler), c_void_p(d_overlap), c_void_p(d_status or 0)), "fo_sph_align_pairs_refined_dev")
+
     def sph_align_pairs_dev(self, d_posA, d_posB, P, N, Jmax, sigma, invert, d_best_idx,
                             d_best_val, d_frac, d_grid=0, d_status=0):
         self._ensure_perm(N)
@@ -555,6 +623,19 @@ class Context(object):
                                                 int(bool(invert)), _ptr(bi), _ptr(bv), _ptr(fr),
                                                 _ptr(avg), _ptr(grid)), "fo_sph_align_bank")
         return bi, bv, fr, avg, grid
+
+
+    def sph_align_bank_refined(self, bank, pairs, invert=True, want_avg=True):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        P = pairs.shape[0]
+        bi, bv, fr, _ = self._sph_outputs(P, bank.Jmax, invert, False)
+        eu = np.empty_like(fr)
+        ov = np.empty_like(bv)
+        avg = np.empty(P, np.float64) if want_avg else None
+        self._check(self._lib.fo_sph_align_bank_refined(self._h, bank._h, _ptr(pairs), P, int(bool(invert)),
+                                                        _ptr(bi), _ptr(bv), _ptr(fr), _ptr(avg), _ptr(eu),
+                                                        _ptr(ov)), "fo_sph_align_bank_refined")
+        return bi, bv, fr, avg, eu, ov
 
 
 class Bank(object):

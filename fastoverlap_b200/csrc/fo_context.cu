@@ -138,6 +138,7 @@ extern "C" void fo_destroy(fo_ctx* ctx) {
   if (ctx->d_gidx) cudaFree(ctx->d_gidx);
   if (ctx->wig.d_table) cudaFree(ctx->wig.d_table);
   if (ctx->wig.d_packed) cudaFree(ctx->wig.d_packed);
+  if (ctx->refine_tab.ptr) cudaFree(ctx->refine_tab.ptr);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

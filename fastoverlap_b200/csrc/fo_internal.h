@@ -51,6 +51,9 @@ struct fo_ctx {
   fo_devbuf pinned[6];
 
   fo_wigner_cache wig;
+  // recurrence table of the continuous rotation refinement (fo_refine.cu), cached per bandwidth
+  fo_devbuf refine_tab;
+  int refine_L = -1;
 
   // testing hook: force the generic (any-size) kernels instead of the shared-memory fast paths
   bool force_generic = false;
@@ -108,6 +111,14 @@ int fo_peaks_outputs(fo_ctx* ctx, int64_t np, int64_t npeaks, double** pk, doubl
 int fo_peaks_copy_out(fo_ctx* ctx, int64_t p0, int64_t np, int64_t npeaks, const double* pk, const double* amp,
                       const double* mean, const double* alpha, const int32_t* nf, double* peaks,
                       double* amplitude, double* meanv, double* alphav, int32_t* nfound);
+
+// continuous rotation refinement (fo_refine.cu): one CTA per (pair, orientation) on the Ihalf layout;
+// d_start is [np*norient][3] fractional grid indices (from_frac) or Euler angles
+int fo_refine_run_dev(fo_ctx* ctx, const void* d_Ihalf, int64_t np, int L, int norient, const double* d_start,
+                      int from_frac, double* d_euler, double* d_overlap, int* d_iters);
+
+int fo_refine_eval_dev(fo_ctx* ctx, const void* d_Ihalf, int64_t np, int L, const double* d_euler, double* d_value,
+                       double* d_grad, double* d_hess);
 
 // RAII bracket: records an event pair around a kernel launch when profiling is on
 struct fo_prof_scope {

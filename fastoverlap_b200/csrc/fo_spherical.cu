@@ -2653,10 +2653,12 @@ extern "C" int fo_sph_coeffs_direct(fo_ctx* ctx, const double* posA, const doubl
   return FO_OK;
 }
 
-extern "C" int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
-                                      int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
-                                      int invert, int64_t* d_best_idx, double* d_best_val,
-                                      double* d_frac_idx, double* d_grid_out, int32_t* d_status) {
+namespace {
+// d_euler [P,O,3] / d_overlap [P,O] non-null: continuous refinement of both orientations (fo_refine.cu)
+int align_pairs_dev_impl(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t npairs, int64_t natoms,
+                         int64_t Jmax, double sigma, int invert, int64_t* d_best_idx, double* d_best_val,
+                         double* d_frac_idx, double* d_grid_out, int32_t* d_status, double* d_euler,
+                         double* d_overlap) {
   if (!ctx) return FO_ERR_INVALID;
   FO_CHECK(check_L(ctx, Jmax));
   if (natoms < 1 || !(sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 and sigma > 0 required");
@@ -2681,14 +2683,37 @@ extern "C" int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const d
     FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, (long long*)d_best_idx + (size_t)p0 * O * 3,
                        d_best_val + (size_t)p0 * O, d_frac_idx + (size_t)p0 * O * 3,
                        d_grid_out ? d_grid_out + (size_t)p0 * O * G3 : nullptr));
+    if (d_euler)
+      FO_CHECK(fo_refine_run_dev(ctx, dhalf, np, L, O, d_frac_idx + (size_t)p0 * O * 3, 1,
+                                 d_euler + (size_t)p0 * O * 3, d_overlap + (size_t)p0 * O, nullptr));
   }
   return FO_OK;
 }
+}  // namespace
 
-extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
-                                  int64_t natoms, int64_t Jmax, double sigma, int invert,
-                                  int64_t* best_idx, double* best_val, double* frac_idx, double* grid_out,
-                                  int32_t* status) {
+extern "C" int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
+                                      int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
+                                      int invert, int64_t* d_best_idx, double* d_best_val,
+                                      double* d_frac_idx, double* d_grid_out, int32_t* d_status) {
+  return align_pairs_dev_impl(ctx, d_posA, d_posB, npairs, natoms, Jmax, sigma, invert, d_best_idx, d_best_val,
+                              d_frac_idx, d_grid_out, d_status, nullptr, nullptr);
+}
+
+extern "C" int fo_sph_align_pairs_refined_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
+                                              int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
+                                              int invert, int64_t* d_best_idx, double* d_best_val,
+                                              double* d_frac_idx, double* d_euler, double* d_overlap,
+                                              int32_t* d_status) {
+  if (ctx && npairs > 0 && (!d_euler || !d_overlap))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_pairs_refined_dev: NULL argument");
+  return align_pairs_dev_impl(ctx, d_posA, d_posB, npairs, natoms, Jmax, sigma, invert, d_best_idx, d_best_val,
+                              d_frac_idx, nullptr, d_status, d_euler, d_overlap);
+}
+
+namespace {
+int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                     int64_t Jmax, double sigma, int invert, int64_t* best_idx, double* best_val,
+                     double* frac_idx, double* grid_out, int32_t* status, double* euler, double* overlap) {
   if (!ctx) return FO_ERR_INVALID;
   FO_CHECK(check_L(ctx, Jmax));
   if (natoms < 1 || !(sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 and sigma > 0 required");
@@ -2703,7 +2728,7 @@ extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double*
   void *dA, *dB, *dout, *dgrid = nullptr, *hA, *hB;
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, 2 * pos_bytes, &dA));
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
-  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * (O * 56 + 8) + 256, &dout));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * (O * 88 + 8) + 256, &dout));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
   const bool pinnedA = fo_is_pinned(posA), pinnedB = fo_is_pinned(posB);
   hA = hB = nullptr;
@@ -2742,11 +2767,18 @@ extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double*
     long long* d_bi = (long long*)dout;
     double* d_bv = (double*)((char*)dout + (size_t)np * O * 24);
     double* d_fr = (double*)((char*)dout + (size_t)np * O * 32);
-    int* d_st = (int*)((char*)dout + (size_t)np * O * 56);
-    FO_CHECK(fo_sph_align_pairs_dev(ctx, (const double*)((char*)dA + buf * pos_bytes),
-                                    (const double*)((char*)dB + buf * pos_bytes), np, natoms, Jmax, sigma,
-                                    invert, (int64_t*)d_bi, d_bv, d_fr, (double*)dgrid, d_st));
+    double* d_eu = (double*)((char*)dout + (size_t)np * O * 56);
+    double* d_ov = (double*)((char*)dout + (size_t)np * O * 80);
+    int* d_st = (int*)((char*)dout + (size_t)np * O * 88);
+    FO_CHECK(align_pairs_dev_impl(ctx, (const double*)((char*)dA + buf * pos_bytes),
+                                  (const double*)((char*)dB + buf * pos_bytes), np, natoms, Jmax, sigma,
+                                  invert, (int64_t*)d_bi, d_bv, d_fr, (double*)dgrid, d_st,
+                                  euler ? d_eu : nullptr, euler ? d_ov : nullptr));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+    if (euler) {
+      FO_CUDA(ctx, cudaMemcpyAsync(euler + (size_t)p0 * O * 3, d_eu, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+      FO_CUDA(ctx, cudaMemcpyAsync(overlap + (size_t)p0 * O, d_ov, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
     FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
     FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2756,6 +2788,108 @@ extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double*
       FO_CUDA(ctx, cudaMemcpyAsync(grid_out + (size_t)p0 * O * G3, dgrid, (size_t)np * O * G3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                                  int64_t natoms, int64_t Jmax, double sigma, int invert,
+                                  int64_t* best_idx, double* best_val, double* frac_idx, double* grid_out,
+                                  int32_t* status) {
+  return align_pairs_impl(ctx, posA, posB, npairs, natoms, Jmax, sigma, invert, best_idx, best_val, frac_idx,
+                          grid_out, status, nullptr, nullptr);
+}
+
+extern "C" int fo_sph_align_pairs_refined(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                                          int64_t natoms, int64_t Jmax, double sigma, int invert,
+                                          int64_t* best_idx, double* best_val, double* frac_idx, double* euler,
+                                          double* overlap, int32_t* status) {
+  if (ctx && npairs > 0 && (!euler || !overlap))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_pairs_refined: NULL argument");
+  return align_pairs_impl(ctx, posA, posB, npairs, natoms, Jmax, sigma, invert, best_idx, best_val, frac_idx,
+                          nullptr, status, euler, overlap);
+}
+
+// Continuous refinement of P rotations from caller-supplied coefficients (maxOverlap,
+// sphericalAlignment.py:98-103): Ilmm as fo_sph_isoft_argmax, euler_in [P,3] the starting angles.
+extern "C" int fo_sph_refine_rotations(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax,
+                                       const double* euler_in, double* euler_out, double* overlap_out,
+                                       int32_t* nevals_out) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (npairs < 0 || (npairs > 0 && (!Ilmm || !euler_in || !euler_out || !overlap_out)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_refine_rotations: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax;
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + ihalf_elems(L) * 16));
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *dfull, *dhalf, *dout;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dout));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    double* d_in = (double*)dout;
+    double* d_eu = d_in + (size_t)np * 3;
+    double* d_ov = d_eu + (size_t)np * 3;
+    int* d_ne = (int*)(d_ov + np);
+    FO_CUDA(ctx, cudaMemcpyAsync(dfull, Ilmm + (size_t)p0 * full * 2, (size_t)np * full * 16,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(d_in, euler_in + (size_t)p0 * 3, (size_t)np * 24, cudaMemcpyHostToDevice, ctx->stream));
+    sph_pack_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
+        (const double2*)dfull, L, (size_t)np, 0, (double2*)dhalf);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CHECK(fo_refine_run_dev(ctx, dhalf, np, L, 1, d_in, 0, d_eu, d_ov, d_ne));
+    FO_CUDA(ctx, cudaMemcpyAsync(euler_out + (size_t)p0 * 3, d_eu, (size_t)np * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(overlap_out + p0, d_ov, (size_t)np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nevals_out)
+      FO_CUDA(ctx, cudaMemcpyAsync(nevals_out + p0, d_ne, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FO_OK;
+}
+
+// One evaluation of the refinement objective and its derivatives (getEnergyGradient,
+// sphericalAlignment.py:93-96, with the sign of the overlap: value = -E, grad = -dE).
+extern "C" int fo_sph_overlap_gradient(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax,
+                                       const double* euler, double* value, double* grad, double* hess) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (npairs < 0 || (npairs > 0 && (!Ilmm || !euler || !value || !grad)))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_overlap_gradient: NULL argument");
+  if (npairs == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax;
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * (2 * L + 1);
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + ihalf_elems(L) * 16));
+  if (chunk < 1) chunk = 1;
+  if (chunk > npairs) chunk = npairs;
+  void *dfull, *dhalf, *dout;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 104, &dout));
+  for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, npairs - p0);
+    double* d_in = (double*)dout;
+    double* d_v = d_in + (size_t)np * 3;
+    double* d_g = d_v + np;
+    double* d_h = d_g + (size_t)np * 3;
+    FO_CUDA(ctx, cudaMemcpyAsync(dfull, Ilmm + (size_t)p0 * full * 2, (size_t)np * full * 16,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(d_in, euler + (size_t)p0 * 3, (size_t)np * 24, cudaMemcpyHostToDevice, ctx->stream));
+    sph_pack_kernel<<<grid_for((size_t)np * ihalf_elems(L), 256), 256, 0, ctx->stream>>>(
+        (const double2*)dfull, L, (size_t)np, 0, (double2*)dhalf);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CHECK(fo_refine_eval_dev(ctx, dhalf, np, L, d_in, d_v, d_g, d_h));
+    FO_CUDA(ctx, cudaMemcpyAsync(value + p0, d_v, (size_t)np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaMemcpyAsync(grad + (size_t)p0 * 3, d_g, (size_t)np * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hess)
+      FO_CUDA(ctx, cudaMemcpyAsync(hess + (size_t)p0 * 6, d_h, (size_t)np * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return FO_OK;
 }
 
@@ -2878,9 +3012,10 @@ extern "C" int fo_sph_bank_create(fo_ctx* ctx, const double* pos, int64_t nstruc
   return FO_OK;
 }
 
-extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs, int64_t npairs,
-                                 int invert, int64_t* best_idx, double* best_val, double* frac_idx,
-                                 double* avg_overlap, double* grid_out) {
+namespace {
+int align_bank_impl(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs, int64_t npairs, int invert,
+                    int64_t* best_idx, double* best_val, double* frac_idx, double* avg_overlap, double* grid_out,
+                    double* euler, double* overlap) {
   if (!ctx) return FO_ERR_INVALID;
   if (!bank || bank->kind != 2) return fo_fail(ctx, FO_ERR_INVALID, "not a spherical coefficient bank");
   if (npairs < 0 || (npairs > 0 && (!pairs || !best_idx || !best_val || !frac_idx)))
@@ -2897,7 +3032,7 @@ extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t
   if (chunk > npairs) chunk = npairs;
   void *dhalf, *dout, *dpairs, *dgrid = nullptr;
   FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
-  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * (O * 56 + 8) + 256, &dout));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * (O * 88 + 8) + 256, &dout));
   FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * 16, &dpairs));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
   for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
@@ -2906,7 +3041,9 @@ extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t
     long long* d_bi = (long long*)dout;
     double* d_bv = (double*)((char*)dout + (size_t)np * O * 24);
     double* d_fr = (double*)((char*)dout + (size_t)np * O * 32);
-    double* d_avg = (double*)((char*)dout + (size_t)np * O * 56);
+    double* d_eu = (double*)((char*)dout + (size_t)np * O * 56);
+    double* d_ov = (double*)((char*)dout + (size_t)np * O * 80);
+    double* d_avg = (double*)((char*)dout + (size_t)np * O * 88);
     {
       fo_prof_scope prof(ctx, FO_PROF_SPH_DOT);
       const size_t smem_dot = dot_mma_smem((int)bank->ngroups, (int)bank->nmax, L);
@@ -2922,6 +3059,11 @@ extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t
       FO_LAUNCH_CHECK(ctx);
     }
     FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, d_bi, d_bv, d_fr, (double*)dgrid));
+    if (euler) {
+      FO_CHECK(fo_refine_run_dev(ctx, dhalf, np, L, O, d_fr, 1, d_eu, d_ov, nullptr));
+      FO_CUDA(ctx, cudaMemcpyAsync(euler + (size_t)p0 * O * 3, d_eu, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+      FO_CUDA(ctx, cudaMemcpyAsync(overlap + (size_t)p0 * O, d_ov, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
     FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
     FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2932,4 +3074,21 @@ extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t
     FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs, int64_t npairs,
+                                 int invert, int64_t* best_idx, double* best_val, double* frac_idx,
+                                 double* avg_overlap, double* grid_out) {
+  return align_bank_impl(ctx, bank, pairs, npairs, invert, best_idx, best_val, frac_idx, avg_overlap, grid_out,
+                         nullptr, nullptr);
+}
+
+extern "C" int fo_sph_align_bank_refined(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs, int64_t npairs,
+                                         int invert, int64_t* best_idx, double* best_val, double* frac_idx,
+                                         double* avg_overlap, double* euler, double* overlap) {
+  if (ctx && npairs > 0 && (!euler || !overlap))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_bank_refined: NULL argument");
+  return align_bank_impl(ctx, bank, pairs, npairs, invert, best_idx, best_val, frac_idx, avg_overlap, nullptr,
+                         euler, overlap);
 }

@@ -85,8 +85,10 @@ class BaseSphericalAlignment(object):
         X2 -= X2.mean(axis=0)[None, :]
         return X1, X2
 
-    # -- continuous refinement of the rotation on the host (reference :67-113), numpy rule only
+    # -- continuous refinement of the rotation (reference :67-113) on the device (fo_refine.cu)
     def calcWignerMatrices(self, rot):
+        """D^l_{m1m2}(rot) and its gradient as host arrays (reference :67-91).  API compatibility only:
+        the refinement itself (maxOverlap / getEnergyGradient) runs on the device."""
         from scipy.special import eval_jacobi, gammaln
         a, b, y = rot
         Js, m1s, m2s = self.Js, self.m1s, self.m2s
@@ -115,13 +117,22 @@ class BaseSphericalAlignment(object):
         return Ds, grad
 
     def getEnergyGradient(self, rot, Ilmm):
-        D, gradD = self.calcWignerMatrices(rot)
-        return -(Ilmm * D).real.sum(), -(Ilmm[None, ...] * gradD).real.sum((1, 2, 3))
+        """(E, dE/d(a,b,g)) of the reference's objective (:93-96), evaluated on the device
+        (fo_sph_overlap_gradient).  Ilmm is the CONJUGATED coefficient array, as the reference passes it."""
+        val, grad, _ = self.ctx.sph_overlap_gradient(np.conj(Ilmm), self.Jmax, np.asarray(rot, float))
+        return -float(val[0]), -grad[0]
 
     def maxOverlap(self, R, Ilmm):
-        from scipy.optimize import minimize
-        res = minimize(self.getEnergyGradient, R, jac=True, args=(Ilmm,), method='L-BFGS-B')
-        return res.x, res
+        """Refine the Euler angles R by maximising the un-weighted overlap (reference :98-103).
+        Ilmm is the CONJUGATED coefficient array, as the reference passes it (:193).  Returns
+        (R, res) with res.x, res.fun = -overlap, res.nfev like scipy's OptimizeResult."""
+        eu, ov, ne = self.ctx.sph_refine_rotations(np.conj(Ilmm), self.Jmax, np.asarray(R, float))
+
+        class _Res(object):
+            pass
+        res = _Res()
+        res.x, res.fun, res.nfev, res.success = eu[0], -float(ov[0]), int(ne[0]), True
+        return eu[0], res
 
     # -- hot path wrappers
     def _grid_search(self, X1, X2, perm, invert, want_grid=False, calcCoeffs=None):
@@ -129,7 +140,7 @@ class BaseSphericalAlignment(object):
         raise NotImplementedError
 
     def findRotation(self, Ilmm):
-        """Grid arg-max -> Euler angles -> host L-BFGS refinement (reference :190-194)."""
+        """Grid arg-max -> Euler angles -> continuous refinement, all on the device (reference :190-194)."""
         bi, bv, fr, _ = self.ctx.sph_isoft_argmax(Ilmm, self.Jmax)
         R = self.soft.indtoEuler(fr[0, 0])
         R, res = self.maxOverlap(R, np.conj(Ilmm))
@@ -167,8 +178,14 @@ class BaseSphericalAlignment(object):
     def align(self, pos1, pos2, perm=None, invert=True, calcCoeffs=None):
         """(dist, X1, X2) for the best of the normal / inverted orientation (reference :160-188)."""
         X1, X2, perm = self._setup(pos1, pos2, perm)
+        if self.orientation == "overlap" and calcCoeffs is None:
+            # numpy rule, fused: coefficients -> iSOFT -> arg-max -> refinement of both orientations
+            Rs, ov = self._grid_search_refined(X1, X2, perm, invert)
+            if invert and ov[1] > ov[0]:
+                return self.refine(X1, -X2, Rs[1], perm)
+            return self.refine(X1, X2, Rs[0], perm)
         if self.orientation == "overlap" or calcCoeffs is not None:
-            # numpy rule: compare the L-BFGS-refined overlaps of the two orientations
+            # numpy rule: compare the refined overlaps of the two orientations
             Ilmm = self._coeffs(X1, X2, perm) if calcCoeffs is None else calcCoeffs(False)
             R, res = self.findRotation(Ilmm)
             if invert:
@@ -221,6 +238,18 @@ class BaseSphericalAlignment(object):
         X1 = pos1 - pos1.mean(1, keepdims=True)
         X2 = pos2 - pos2.mean(1, keepdims=True)
         perm = self._perm(X1.shape[1], perm)
+        if self.orientation == "overlap":
+            # numpy rule (:178-187): the orientation with the larger refined overlap is the only one
+            # that goes through the host LAP + Kearsley refinement
+            Rs, ov = self._grid_search_refined(X1, X2, perm, invert)
+            Rs = Rs.reshape(len(X1), -1, 3)
+            if not refine:
+                return None, Rs
+            pick = ov.reshape(len(X1), -1).argmax(1)
+            sign = np.where(pick == 1, -1.0, 1.0)[:, None, None]
+            Rp = Rs[np.arange(len(X1)), pick][:, None, :]
+            dists, orient, perms, rmats = _lib.host_refine_spherical(X1, sign * X2, Rp, perm, nthreads)
+            return dists, Rs
         Rs = self._grid_search(X1, X2, perm, invert)
         Rs = Rs.reshape(len(X1), -1, 3)
         if not refine:
@@ -264,6 +293,13 @@ class SphericalAlign(BaseSphericalAlignment):
         self._best_idx, self._best_val, self._frac_idx, self._grid = bi, bv, fr, grid
         R = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
         return R[0] if X1.ndim == 2 else R
+
+
+    def _grid_search_refined(self, X1, X2, perm, invert):
+        self.ctx.set_perm(perm, X1.shape[-2])
+        bi, bv, fr, eu, ov, st = self.ctx.sph_align_pairs_refined(X1, X2, self.Jmax, self.scale, invert=invert)
+        self._best_idx, self._best_val, self._frac_idx, self._grid = bi, bv, fr, None
+        return (eu[0], ov[0]) if X1.ndim == 2 else (eu, ov)
 
 
 class SphericalHarmonicAlign(BaseSphericalAlignment):
@@ -344,6 +380,21 @@ class SphericalHarmonicAlign(BaseSphericalAlignment):
         self._best_idx, self._best_val, self._frac_idx, self._grid = bi, bv, fr, grid
         R = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
         return R[0] if X1.ndim == 2 else R
+
+    def _grid_search_refined(self, X1, X2, perm, invert):
+        single = X1.ndim == 2
+        A = X1[None] if single else X1
+        B = X2[None] if single else X2
+        P, n = A.shape[:2]
+        self.ctx.set_perm(perm, n)
+        bank = self.ctx.sph_bank_create(np.concatenate([A, B]), self.nmax, self.Jmax, self.harmscale, self.scale)
+        try:
+            pairs = np.stack([np.arange(P), P + np.arange(P)], axis=1)
+            bi, bv, fr, avg, eu, ov = self.ctx.sph_align_bank_refined(bank, pairs, invert=invert)
+        finally:
+            bank.close()
+        self._best_idx, self._best_val, self._frac_idx, self._grid = bi, bv, fr, None
+        return (eu[0], ov[0]) if single else (eu, ov)
 
     def compareList(self, poslist, perm=None, invert=False):
         """All-vs-all average / maximum overlap (reference SphericalHarmonicAlignFortran.compareList

@@ -85,6 +85,7 @@ int fo_measure_fp64_tensor_peak(fo_ctx* ctx, double* tflops);
 #define FO_PROF_SPH_DOT 4     /* C_nlm contraction to I_lmm'           */
 #define FO_PROF_SPH_ISOFT 5   /* Wigner-d contraction + 2-D DFT + argmax */
 #define FO_PROF_PEAKS 6       /* top-k peak extraction (fit-and-subtract) */
+#define FO_PROF_SPH_REFINE 7  /* continuous rotation refinement (damped Newton) */
 #define FO_PROF_NKINDS 8
 int fo_profile_begin(fo_ctx* ctx);
 int fo_profile_end(fo_ctx* ctx, double ms_out[FO_PROF_NKINDS], int64_t count_out[FO_PROF_NKINDS]);
@@ -236,6 +237,41 @@ int fo_sph_bank_create(fo_ctx* ctx, const double* pos /*[S,N,3]*/, int64_t nstru
 int fo_sph_align_bank(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs /*[P,2]*/,
                       int64_t npairs, int invert, int64_t* best_idx, double* best_val,
                       double* frac_idx, double* avg_overlap, double* grid_out);
+
+/* Continuous refinement of the rotation: maximise the un-weighted overlap
+ *   f(a,b,g) = Re sum_{l m1 m2} conj(I^l_{m1m2}) e^{-i m1 a} d^l_{m1m2}(b) e^{-i m2 g}
+ * from euler_in [P,3] by a damped Newton iteration on the device, one CTA per rotation (analytic
+ * gradient and Hessian from the Wigner-d recurrence).  Replaces BaseSphericalAlignment.maxOverlap /
+ * getEnergyGradient / calcWignerMatrices (sphericalAlignment.py:67-113; scipy L-BFGS-B on E = -f):
+ * euler_out [P,3] = res.x, overlap_out [P] = -res.fun, nevals_out [P] (nullable) = evaluations used.
+ * Ilmm as in fo_sph_isoft_argmax (what findRotation receives; it is conjugated internally as
+ * findRotation does, sphericalAlignment.py:190-194). */
+int fo_sph_refine_rotations(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax,
+                            const double* euler_in, double* euler_out, double* overlap_out,
+                            int32_t* nevals_out);
+
+/* One evaluation of that objective: value [P] = f, grad [P,3] = df/d(a,b,g), hess [P,6] (nullable)
+ * = second derivatives (aa ab ag bb bg gg).  getEnergyGradient (sphericalAlignment.py:93-96) returns
+ * (-value, -grad). */
+int fo_sph_overlap_gradient(fo_ctx* ctx, const double* Ilmm, int64_t npairs, int64_t Jmax,
+                            const double* euler, double* value, double* grad, double* hess);
+
+/* fo_sph_align_pairs / fo_sph_align_bank followed, on the device, by that refinement of the
+ * interpolated grid maximum of every (pair, orientation): the numpy classes' findRotation
+ * (sphericalAlignment.py:190-194) for whole batches.  euler [P,O,3] are the refined Euler angles,
+ * overlap [P,O] the refined un-weighted overlap (= -res.fun): the numpy orientation rule keeps the
+ * orientation with the larger overlap (sphericalAlignment.py:178-187). */
+int fo_sph_align_pairs_refined(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                               int64_t natoms, int64_t Jmax, double sigma, int invert, int64_t* best_idx,
+                               double* best_val, double* frac_idx, double* euler, double* overlap,
+                               int32_t* status);
+int fo_sph_align_pairs_refined_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
+                                   int64_t npairs, int64_t natoms, int64_t Jmax, double sigma, int invert,
+                                   int64_t* d_best_idx, double* d_best_val, double* d_frac_idx,
+                                   double* d_euler, double* d_overlap, int32_t* d_status);
+int fo_sph_align_bank_refined(fo_ctx* ctx, const fo_bank* bank, const int64_t* pairs /*[P,2]*/,
+                              int64_t npairs, int invert, int64_t* best_idx, double* best_val,
+                              double* frac_idx, double* avg_overlap, double* euler, double* overlap);
 
 /* Wigner-d table of the reference's SOFT object: Ds[l, m1, m2, k] = sqrt((2l+1)/2)
  * d^l_{m1m2}(beta_k), out [B, 2B-1, 2B-1, 2B] doubles, negative m wrapped modulo 2B-1

@@ -249,3 +249,50 @@ def sph_align_pairs(posA, posB, Jmax, sigma, invert=True, perm=None, nthreads=0,
                                         _i64(L), _f64(sigma), ctypes.c_int(int(bool(invert))), _p(bi),
                                         _p(bv), _p(fr), ctypes.c_int(int(nthreads)))
     return bi, bv, fr, None, int(used)
+
+
+# -- continuous rotation refinement (numpy restatement; small, per-rotation) ---------------------
+def sph_wigner_at(rot, Jmax):
+    """Un-weighted Wigner D^l_{m1 m2}(a, b, g) and its gradient on the reference's
+    [l][m1 wrap][m2 wrap] layout: BaseSphericalAlignment.calcWignerMatrices(rot)
+    (sphericalAlignment.py:67-91; d^l by Jacobi polynomials, eval_grad_jacobi utils.py)."""
+    from scipy.special import eval_jacobi, gammaln
+    a, b, y = rot
+    Js, m1s, m2s = map(np.array, zip(*[(l, m1, m2) for l in range(Jmax + 1) for m1 in range(-l, l + 1)
+                                       for m2 in range(-l, l + 1)]))
+    mu, nu = abs(m1s - m2s), abs(m1s + m2s)
+    s = Js - (mu + nu) // 2
+    xi = np.where(m2s < m1s, (-1.0) ** (m1s - m2s), 1.0)
+    factor = np.exp(0.5 * (gammaln(s + 1) + gammaln(s + mu + nu + 1) - gammaln(s + mu + 1) -
+                           gammaln(s + nu + 1))) * xi
+    sb2, cb2, cb, sb = np.sin(b / 2), np.cos(b / 2), np.cos(b), np.sin(b)
+    jac = eval_jacobi(s, mu, nu, cb)
+    d = factor * jac * sb2 ** mu * cb2 ** nu
+    gjac = np.where(s > 0, eval_jacobi(np.maximum(s - 1, 0), mu + 1, nu + 1, cb), 0.0) * 0.5 * (mu + nu + s + 1.0) * -sb
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gd = (factor * gjac * sb2 ** mu * cb2 ** nu +
+              np.where(mu > 0, factor * jac * sb2 ** (mu - 1.0) * cb2 ** (nu + 1.0) * mu / 2, 0.0) -
+              np.where(nu > 0, factor * jac * sb2 ** (mu + 1.0) * cb2 ** (nu - 1.0) * nu / 2, 0.0))
+    Ds = np.zeros((Jmax + 1, 2 * Jmax + 1, 2 * Jmax + 1), np.complex128)
+    grad = np.zeros((3,) + Ds.shape, np.complex128)
+    ph = np.exp(-1j * m1s * a) * np.exp(-1j * m2s * y)
+    Ds[Js, m1s, m2s] = ph * d
+    grad[0, Js, m1s, m2s] = -1j * m1s * Ds[Js, m1s, m2s]
+    grad[1, Js, m1s, m2s] = ph * gd
+    grad[2, Js, m1s, m2s] = -1j * m2s * Ds[Js, m1s, m2s]
+    return Ds, grad
+
+
+def sph_energy_gradient(rot, Ilmm_conj, Jmax):
+    """getEnergyGradient (sphericalAlignment.py:93-96): E = -Re sum(Ilmm * D), dE/d(a,b,g)."""
+    D, gD = sph_wigner_at(rot, Jmax)
+    return -(Ilmm_conj * D).real.sum(), -(Ilmm_conj[None] * gD).real.sum((1, 2, 3))
+
+
+def sph_max_overlap(rot0, Ilmm, Jmax):
+    """findRotation's refinement (sphericalAlignment.py:98-103,190-194): scipy L-BFGS-B on
+    getEnergyGradient with conj(Ilmm).  Returns (R, -res.fun)."""
+    from scipy.optimize import minimize
+    res = minimize(sph_energy_gradient, np.asarray(rot0, float), jac=True, args=(np.conj(Ilmm), Jmax),
+                   method="L-BFGS-B")
+    return res.x, -res.fun

@@ -115,3 +115,23 @@ def test_synthetic_cases():
             C = oracle.sph_harm_coeffs(X1, 12, J, 1.0, sc, idx=idx)
             assert rel(C, g[k + "H_c1"][gi]) < 1e-9
         assert rel(oracle.sph_dot_harm(g[k + "H_c1"], g[k + "H_c2"]), g[k + "H_Ilmm"]) < 1e-13
+
+
+def test_oracle_rotation_refinement_vs_reference_golden():
+    """oracle.sph_energy_gradient / sph_max_overlap (numpy restatement of sphericalAlignment.py:67-103)
+    against the reference's own getEnergyGradient / maxOverlap outputs (tests/golden/refine.npz)."""
+    G = golden("refine.npz")
+    lj = golden("spherical_lj38.npz")
+    sy = golden("spherical_synth.npz")
+    src = {"J14": lj["J14_Ilmm"], "J15inv": lj["J15_Ilmm_inv"], "H": lj["H_Ilmm"], "c0": sy["c0_Ilmm"],
+           "c1": sy["c1_Ilmm"], "c2": sy["c2_Ilmm"]}
+    Ls = dict(zip([str(k) for k in G["keys"]], [int(j) for j in G["Jmax"]]))
+    for k, I in src.items():
+        L = Ls[k]
+        for tag in ("p", "0"):
+            E, g = oracle.sph_energy_gradient(G[k + "_R" + tag], I.conj(), L)
+            assert abs(E - float(G[k + "_E" + tag])) <= 1e-13 * abs(E), k
+            assert np.abs(g - G[k + "_G" + tag]).max() <= 1e-12 * max(1.0, abs(E)), k
+        R, f = oracle.sph_max_overlap(G[k + "_R0"], I, L)
+        assert abs(f + float(G[k + "_E"])) <= 1e-12 * abs(f), k
+        assert np.abs(R - G[k + "_R"]).max() < 1e-9, k
