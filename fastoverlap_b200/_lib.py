@@ -268,7 +268,7 @@ class Context(object):
     def reset_stream(self):
         self._check(self._lib.fo_reset_stream(self._h), "fo_reset_stream")
 
-    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "peaks", "k7")
+    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "peaks", "sph_refine")
 
     def profile_begin(self):
         self._check(self._lib.fo_profile_begin(self._h), "fo_profile_begin")

@@ -117,7 +117,7 @@ extern "C" int fo_create(int device, fo_ctx** out) {
     return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if ((e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming)) != cudaSuccess)
       return bail("cudaEventCreate", e);
   ctx->stream = ctx->own_stream;
@@ -139,7 +139,7 @@ extern "C" void fo_destroy(fo_ctx* ctx) {
   if (ctx->wig.d_table) cudaFree(ctx->wig.d_table);
   if (ctx->wig.d_packed) cudaFree(ctx->wig.d_packed);
   if (ctx->refine_tab.ptr) cudaFree(ctx->refine_tab.ptr);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

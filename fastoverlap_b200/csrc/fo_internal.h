@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -33,7 +34,7 @@ struct fo_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // stream in use (own or external)
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0,1 H2D done; 2,3 inputs consumed; 4,5 D2H done
   cudaDeviceProp prop;
   std::string err;
   int64_t launches = 0;
@@ -99,6 +100,20 @@ int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out);
 bool fo_is_pinned(const void* p);
 // parallel host memcpy (staging of pageable buffers into the pinned ring)
 void fo_host_copy(void* dst, const void* src, size_t bytes);
+// Chunk boundaries of the double-buffered host-buffer pipelines: [0, s1, s2, ..., npairs], every
+// chunk <= chunk pairs; with more than one chunk the first is chunk / 8 (its H2D copy is the only one
+// that no kernel overlaps).
+inline std::vector<int64_t> fo_chunk_starts(int64_t npairs, int64_t chunk) {
+  std::vector<int64_t> s(1, 0);
+  int64_t first = chunk;
+  if (npairs > chunk && chunk >= 64) first = chunk / 8;
+  for (int64_t p0 = std::min(first, npairs); ; p0 = std::min(p0 + chunk, npairs)) {
+    s.push_back(p0);
+    if (p0 >= npairs) break;
+  }
+  return s;
+}
+
 // make sure a permutation (at least the trivial one) exists for natoms atoms
 int fo_ensure_perm(fo_ctx* ctx, int64_t natoms);
 

@@ -16,6 +16,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include "fo_internal.h"
 #include "fo_symdft.cuh"
 
@@ -1687,6 +1689,16 @@ int copy_out(fo_ctx* ctx, const fo_per_params* p, int64_t p0, int64_t np, const 
   return FO_OK;
 }
 
+// Deferred delivery of the per-pair results: one D2H of the whole chunk block into a pinned ring
+// (never blocks the host, unlike a D2H into the caller's pageable arrays), unpacked into the caller's
+// arrays one chunk later while the GPU already works on the next chunk.
+void deliver_out(const HostOut& h, int64_t p0, int64_t np, const char* src) {
+  memcpy(h.best_idx + 3 * p0, src, (size_t)np * 24);
+  memcpy(h.best_val + p0, src + (size_t)np * 24, (size_t)np * 8);
+  memcpy(h.frac_idx + 3 * p0, src + (size_t)np * 32, (size_t)np * 24);
+  if (h.status) memcpy(h.status + p0, src + (size_t)np * 56, (size_t)np * 4);
+}
+
 XfOut make_out(char* d_out, int64_t np, double* d_grid, bool want_status) {
   XfOut o;
   o.best_idx = (long long*)d_out;
@@ -1726,11 +1738,13 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
   double2* bankA = (double2*)bank;
   double2* bankB = bankA + (size_t)chunk * per_struct;
   HostOut h = {best_idx, best_val, frac_idx, grid_out, status};
-  const int64_t nchunks = (npairs + chunk - 1) / chunk;
+  // chunk boundaries: a short first chunk, so that the only H2D copy nothing can hide is small
+  const std::vector<int64_t> starts = fo_chunk_starts(npairs, chunk);
+  const int64_t nchunks = (int64_t)starts.size() - 1;
   // pipeline: [host memcpy -> pinned] -> H2D on copy_stream -> kernels + D2H on stream
   auto stage_in = [&](int64_t c) -> int {
-    const int64_t p0 = c * chunk;
-    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    const int64_t p0 = starts[c];
+    const int64_t np = starts[c + 1] - p0;
     const int buf = (int)(c & 1);
     const size_t nb = (size_t)np * p->natoms * 3 * 8;
     // the pinned buffer `buf` was last read by the H2D of chunk c-2
@@ -1755,21 +1769,40 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
     return FO_OK;
   };
+  void* hOut = nullptr;
+  const size_t out_bytes = (size_t)chunk * 64;
+  if (!grid_out) FO_CHECK(fo_pinned(ctx, 2, 2 * out_bytes, &hOut));
   FO_CHECK(stage_in(0));
   for (int64_t c = 0; c < nchunks; ++c) {
-    const int64_t p0 = c * chunk;
-    const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
+    const int64_t p0 = starts[c];
+    const int64_t np = starts[c + 1] - p0;
     const int buf = (int)(c & 1);
-    if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
     FO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[buf], 0));
     FO_CHECK(launch_sf(ctx, p, (const double*)((char*)dA + buf * pos_bytes), np, bankA));
     FO_CHECK(launch_sf(ctx, p, (const double*)((char*)dB + buf * pos_bytes), np, bankB));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
     XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
     FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
-    FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
+    if (grid_out) {  // test / single-pair path: large grids straight into the caller's array
+      FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
+      if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
+      continue;
+    }
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)hOut + buf * out_bytes, dOut, (size_t)np * 60, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    FO_CUDA(ctx, cudaEventRecord(ctx->ev[4 + buf], ctx->stream));
+    // host work of this iteration runs while the GPU is busy with chunk c
+    if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
+    if (c >= 1) {
+      FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[4 + (buf ^ 1)]));
+      deliver_out(h, starts[c - 1], starts[c] - starts[c - 1], (const char*)hOut + (buf ^ 1) * out_bytes);
+    }
   }
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!grid_out) {
+    const int64_t c = nchunks - 1;
+    deliver_out(h, starts[c], starts[c + 1] - starts[c], (const char*)hOut + (c & 1) * out_bytes);
+  }
   return FO_OK;
 }
 

@@ -2734,10 +2734,11 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
   hA = hB = nullptr;
   if (!pinnedA) FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
   if (!pinnedB) FO_CHECK(fo_pinned(ctx, 1, 2 * pos_bytes, &hB));
-  const int64_t nchunks = (npairs + chunk - 1) / chunk;
+  const std::vector<int64_t> starts = fo_chunk_starts(npairs, chunk);  // short first chunk
+  const int64_t nchunks = (int64_t)starts.size() - 1;
   auto stage_in = [&](int64_t c) -> int {
-    const int64_t p0 = c * chunk;
-    const int64_t np = std::min(chunk, npairs - p0);
+    const int64_t p0 = starts[c];
+    const int64_t np = starts[c + 1] - p0;
     const int buf = (int)(c & 1);
     const size_t nb = (size_t)np * natoms * 24;
     if (c >= 2) FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[buf]));
@@ -2757,12 +2758,28 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
     return FO_OK;
   };
+  // results: one D2H of the chunk's output block into a pinned ring, unpacked into the caller's arrays
+  // one chunk later (a D2H into pageable arrays would block the host and idle the GPU between chunks)
+  void* hOut = nullptr;
+  const size_t out_bytes = (size_t)chunk * (O * 88 + 8);
+  if (!grid_out) FO_CHECK(fo_pinned(ctx, 2, 2 * out_bytes, &hOut));
+  auto deliver = [&](int64_t c) {
+    const int64_t p0 = starts[c], np = starts[c + 1] - p0;
+    const char* src = (const char*)hOut + (c & 1) * out_bytes;
+    memcpy(best_idx + (size_t)p0 * O * 3, src, (size_t)np * O * 24);
+    memcpy(best_val + (size_t)p0 * O, src + (size_t)np * O * 24, (size_t)np * O * 8);
+    memcpy(frac_idx + (size_t)p0 * O * 3, src + (size_t)np * O * 32, (size_t)np * O * 24);
+    if (euler) {
+      memcpy(euler + (size_t)p0 * O * 3, src + (size_t)np * O * 56, (size_t)np * O * 24);
+      memcpy(overlap + (size_t)p0 * O, src + (size_t)np * O * 80, (size_t)np * O * 8);
+    }
+    if (status) memcpy(status + p0, src + (size_t)np * O * 88, (size_t)np * 4);
+  };
   FO_CHECK(stage_in(0));
   for (int64_t c = 0; c < nchunks; ++c) {
-    const int64_t p0 = c * chunk;
-    const int64_t np = std::min(chunk, npairs - p0);
+    const int64_t p0 = starts[c];
+    const int64_t np = starts[c + 1] - p0;
     const int buf = (int)(c & 1);
-    if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
     FO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[buf], 0));
     long long* d_bi = (long long*)dout;
     double* d_bv = (double*)((char*)dout + (size_t)np * O * 24);
@@ -2775,19 +2792,31 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
                                   invert, (int64_t*)d_bi, d_bv, d_fr, (double*)dgrid, d_st,
                                   euler ? d_eu : nullptr, euler ? d_ov : nullptr));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
-    if (euler) {
-      FO_CUDA(ctx, cudaMemcpyAsync(euler + (size_t)p0 * O * 3, d_eu, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
-      FO_CUDA(ctx, cudaMemcpyAsync(overlap + (size_t)p0 * O, d_ov, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
-    FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status)
-      FO_CUDA(ctx, cudaMemcpyAsync(status + p0, d_st, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (grid_out)
+    if (grid_out) {  // test / single-pair path: straight into the caller's arrays
+      if (euler) {
+        FO_CUDA(ctx, cudaMemcpyAsync(euler + (size_t)p0 * O * 3, d_eu, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        FO_CUDA(ctx, cudaMemcpyAsync(overlap + (size_t)p0 * O, d_ov, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      FO_CUDA(ctx, cudaMemcpyAsync(best_idx + (size_t)p0 * O * 3, d_bi, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+      FO_CUDA(ctx, cudaMemcpyAsync(best_val + (size_t)p0 * O, d_bv, (size_t)np * O * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      FO_CUDA(ctx, cudaMemcpyAsync(frac_idx + (size_t)p0 * O * 3, d_fr, (size_t)np * O * 24, cudaMemcpyDeviceToHost, ctx->stream));
+      if (status)
+        FO_CUDA(ctx, cudaMemcpyAsync(status + p0, d_st, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
       FO_CUDA(ctx, cudaMemcpyAsync(grid_out + (size_t)p0 * O * G3, dgrid, (size_t)np * O * G3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
+      continue;
+    }
+    FO_CUDA(ctx, cudaMemcpyAsync((char*)hOut + buf * out_bytes, dout, (size_t)np * (O * 88 + 4), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    FO_CUDA(ctx, cudaEventRecord(ctx->ev[4 + buf], ctx->stream));
+    if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));  // host staging runs while the GPU works on chunk c
+    if (c >= 1) {
+      FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[4 + (buf ^ 1)]));
+      deliver(c - 1);
+    }
   }
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!grid_out) deliver(nchunks - 1);
   return FO_OK;
 }
 }  // namespace
