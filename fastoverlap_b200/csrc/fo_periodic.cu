@@ -166,15 +166,15 @@ per_sf_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
 template <int MT, int NT>
 __global__ void __launch_bounds__(320, 2)
 per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
-               const int32_t* __restrict__ gidx, int ngroups, int natoms, int n, double kx, double ky,
+               const int32_t* __restrict__ gidx, int ngroups, int natoms, int n, int TA, double kx, double ky,
                double kz, double2* __restrict__ bank) {
   extern __shared__ double2 sm_ph2[];
   const int M = n + 1;
   const int Mp = M | 1;
   const int Mz = (4 * NT) | 1;  // z rows zero padded up to 4 NT values of l
   double2* phx = sm_ph2;
-  double2* phy = phx + SF_TA * Mp;
-  double2* phz = phy + SF_TA * Mp;
+  double2* phy = phx + TA * Mp;
+  double2* phz = phy + TA * Mp;
   const int s = blockIdx.x, gq = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31;
   // blockIdx.z splits the row tiles of fine k-grids over several CTAs (each rebuilds the phasors)
@@ -212,9 +212,9 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   // there first) before a thread starts its DMMA share of tile t, so one barrier per tile suffices and
   // the sincos / recurrence work overlaps the tensor-pipe work of the other warps (ncu on the
   // single-buffered version: 15 % of the samples at the two barriers around the phasor phase).
-  const size_t buf_elems = (size_t)SF_TA * (2 * Mp + Mz);  // double2 elements per buffer
+  const size_t buf_elems = (size_t)TA * (2 * Mp + Mz);  // double2 elements per buffer
   auto build_phasors = [&](int a0, int buf) {
-    const int ta = min(SF_TA, a_end - a0);
+    const int ta = min(TA, a_end - a0);
     const int ta4 = (ta + 3) & ~3;
     double2* bx = phx + buf * buf_elems;
     double2* by = phy + buf * buf_elems;
@@ -247,10 +247,10 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   if (a_begin < a_end) build_phasors(a_begin, 0);
   __syncthreads();
   int buf = 0;
-  for (int a0 = a_begin; a0 < a_end; a0 += SF_TA, buf ^= 1) {
-    const int ta = min(SF_TA, a_end - a0);
+  for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1) {
+    const int ta = min(TA, a_end - a0);
     const int ta4 = (ta + 3) & ~3;
-    if (a0 + SF_TA < a_end) build_phasors(a0 + SF_TA, buf ^ 1);
+    if (a0 + TA < a_end) build_phasors(a0 + TA, buf ^ 1);
     const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
     const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
     const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
@@ -1407,14 +1407,17 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
      // CTA; more row tiles than 10 MT (fine k-grids) are split over blockIdx.z
     const int NTq = (2 * M + 7) / 8;
     const int mtiles = (M * M * 4 + 7) / 8;
-    static const int mt_for_nt[9] = {0, 5, 5, 5, 4, 3, 2, 2, 2};
-    if (NTq <= 8 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {  // n <= 31; beyond, the scalar kernel wins
+    static const int mt_for_nt[10] = {0, 5, 5, 5, 4, 3, 2, 2, 2, 2};
+    if (NTq <= 9 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {  // n <= 35; beyond, the scalar kernel
       const int MTq = mt_for_nt[NTq];
       int warps = (mtiles + MTq - 1) / MTq;
       if (warps > 10) warps = 10;
       const int nz = (mtiles + MTq * warps - 1) / (MTq * warps);
       const int Mp = M | 1, Mz = (4 * NTq) | 1;
-      const size_t smem = (size_t)2 * SF_TA * (2 * Mp + Mz) * 16;  // double-buffered phasor tables
+      // double-buffered phasor tables of TA atoms; TA shrinks on fine k-grids so that two CTAs share an SM
+      int TA = SF_TA;
+      while (TA > 16 && (size_t)2 * TA * (2 * Mp + Mz) * 16 > (size_t)113 * 1024) TA >>= 1;
+      const size_t smem = (size_t)2 * TA * (2 * Mp + Mz) * 16;
       if (smem <= ctx->prop.sharedMemPerBlockOptin) {
         const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
         dim3 grid((unsigned)nstruct, (unsigned)ngroups, (unsigned)nz);
@@ -1424,7 +1427,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
     FO_CUDA(ctx, cudaFuncSetAttribute(per_sf2_kernel<MT_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)smem));                                                           \
     per_sf2_kernel<MT_, NT_><<<grid, warps * 32, smem, ctx->stream>>>(                                       \
-        d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, kx, ky, kz, d_bank);                    \
+        d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, TA, kx, ky, kz, d_bank);                \
   } while (0)
         switch (NTq) {
           case 1: FO_SF2_LAUNCH(5, 1); break;
@@ -1435,7 +1438,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
           case 6: FO_SF2_LAUNCH(2, 6); break;
           case 7: FO_SF2_LAUNCH(2, 7); break;
           case 8: FO_SF2_LAUNCH(2, 8); break;
-          default: FO_SF2_LAUNCH(2, 8); break;
+          default: FO_SF2_LAUNCH(2, 9); break;
         }
 #undef FO_SF2_LAUNCH
         FO_LAUNCH_CHECK(ctx);
