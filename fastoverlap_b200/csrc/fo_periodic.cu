@@ -303,6 +303,175 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// per_sf3_kernel: per_sf2 for n = 9 (M = 10, the default k-grid of a 256-atom cell) without the
+// 20 -> 24 column padding.  The 2M = 20 columns split into 16 (l = 0..7: two full column tiles, as in
+// per_sf2) and 4 left over (l = 8, 9).  The left-over block X(20) x Y(20) x Z(4) is matricised the
+// other way round:   C'[(i, cx, zl)][(j, cy)] = sum_a (X[a][(i,cx)] Z[a][zl]) Y[a][(j,cy)]
+// 80 rows = one 8-row tile per i (= per warp: 10 warps), 20 -> 24 columns (3 tiles): 30 DMMA per
+// k-step instead of the 50 of a third column tile; 130 instead of 150 DMMA per k-step in total.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(320, 2)
+per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
+               const int32_t* __restrict__ gidx, int ngroups, int natoms, int TA, double kx, double ky,
+               double kz, double2* __restrict__ bank) {
+  extern __shared__ double2 sm_ph3[];
+  constexpr int n = 9, M = 10, MT = 5, NT = 2, NTL = 3;
+  constexpr int Mp = M | 1;          // x rows
+  constexpr int My = (4 * NTL) | 1;  // y rows zero padded to 4 NTL values of j
+  constexpr int Mz = M | 1;
+  const int s = blockIdx.x, gq = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int a_begin = goff[gq], a_end = goff[gq + 1];
+  const double* spos = pos + (size_t)s * natoms * 3;
+  const double kax[3] = {kx, ky, kz};
+
+  int offx[MT], offy[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r = (warp * MT + mt) * 8 + g;
+    const int c4 = r & 3, ij = r >> 2;
+    const int i = ij / M, j = ij - i * M;
+    offx[mt] = i * 2 + ((c4 >> 1) & 1);
+    offy[mt] = j * 2 + (c4 & 1);
+  }
+  // left-over tile of this warp: i = warp, row g = cx 4 + zl, zl = (l - 8) 2 + cz
+  const int offxl = warp * 2 + (g >> 2), offzl = 16 + (g & 3);
+
+  double acc[MT][NT][2], accl[NTL][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt) accl[nt][0] = accl[nt][1] = 0.0;
+
+  const size_t buf_elems = (size_t)TA * (Mp + My + Mz);  // double2 elements per buffer
+  double2* phx = sm_ph3;
+  double2* phy = phx + (size_t)TA * Mp;
+  double2* phz = phy + (size_t)TA * My;
+  auto build_phasors = [&](int a0, int buf) {
+    const int ta = min(TA, a_end - a0);
+    const int ta4 = (ta + 3) & ~3;
+    double2* bx = phx + buf * buf_elems;
+    double2* by = phy + buf * buf_elems;
+    double2* bz = phz + buf * buf_elems;
+    for (int t = tid; t < 3 * ta4; t += blockDim.x) {
+      const int a = t / 3, ax = t - 3 * a;
+      const int pitch = ax == 0 ? Mp : (ax == 1 ? My : Mz);
+      double2* row = (ax == 0 ? bx : (ax == 1 ? by : bz)) + a * pitch;
+      if (a < ta) {
+        const int atom = gidx[a0 + a];
+        const double th = kax[ax] * spos[atom * 3 + ax];
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        double c = 1.0, sv = 0.0;
+        row[0] = make_double2(1.0, 0.0);
+        for (int m = 1; m <= n; ++m) {
+          const double cn = c * cs - sv * sn;
+          const double snn = sv * cs + c * sn;
+          c = cn;
+          sv = snn;
+          row[m] = make_double2(c, sv);
+        }
+        for (int m = M; m < pitch; ++m) row[m] = make_double2(0.0, 0.0);
+      } else {  // padding atoms of the last k-step contribute nothing
+        for (int m = 0; m < pitch; ++m) row[m] = make_double2(0.0, 0.0);
+      }
+    }
+  };
+  if (a_begin < a_end) build_phasors(a_begin, 0);
+  __syncthreads();
+  int buf = 0;
+  for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1) {
+    const int ta = min(TA, a_end - a0);
+    const int ta4 = (ta + 3) & ~3;
+    if (a0 + TA < a_end) build_phasors(a0 + TA, buf ^ 1);
+    const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
+    const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
+    const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
+    for (int k0 = 0; k0 < ta4; k0 += 4) {
+      const int a = k0 + t4;
+      const double* xr = dx_ + (size_t)a * Mp * 2;
+      const double* yr = dy_ + (size_t)a * My * 2;
+      const double* zr = dz_ + (size_t)a * Mz * 2;
+      double bz[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const double av = xr[offx[mt]] * yr[offy[mt]];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
+      }
+      const double avl = xr[offxl] * zr[offzl];
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) fo_dmma(accl[nt], avl, yr[nt * 8 + g]);
+    }
+    __syncthreads();
+  }
+  // ---- epilogue
+  constexpr int W = 2 * n + 1;
+  double2* out = bank + ((size_t)s * ngroups + gq) * ((size_t)W * W * M);
+  // main block: as per_sf2 (lanes g = 4u + c4 of one (i, j); this lane writes the signs of its own c4)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r = (warp * MT + mt) * 8 + g;
+    const int c4 = r & 3, ij = r >> 2;
+    const int i = ij / M, j = ij - i * M;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      double v[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int src = (((g & 4) | q) << 2) | t4;
+        v[q][0] = __shfl_sync(0xffffffffu, acc[mt][nt][0], src);
+        v[q][1] = __shfl_sync(0xffffffffu, acc[mt][nt][1], src);
+      }
+      const int l = nt * 4 + t4;
+      const double rho = (c4 & 2) ? -1.0 : 1.0, sig = (c4 & 1) ? -1.0 : 1.0;
+      const double re = v[0][0] - rho * sig * v[3][0] - sig * v[1][1] - rho * v[2][1];
+      const double im = -sig * v[1][0] - rho * v[2][0] - v[0][1] + rho * sig * v[3][1];
+      const bool dup = ((c4 & 2) && i == 0) || ((c4 & 1) && j == 0);
+      if (!dup) {
+        const int ix = n + ((c4 & 2) ? -i : i), iy = n + ((c4 & 1) ? -j : j);
+        out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
+      }
+    }
+  }
+  // left-over block: i = warp; lane (g, t4) of column tile nt holds (j = 4 nt + t4; cy = 0, 1) of row
+  // (cx = g >> 2, l = 8 + ((g >> 1) & 1), cz = g & 1).  The four lanes (cx, cz) of one (j, l) gather all
+  // eight sums v[cx][cy][cz] and write the sign combination rho = (cx ? - : +), sig = (cz ? - : +).
+  {
+    const int i = warp;
+    const int cxw = g >> 2, lb = (g >> 1) & 1, czw = g & 1;
+    const int l = 8 + lb;
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      double v[2][2][2];  // [cx][cy][cz]
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+        for (int cz = 0; cz < 2; ++cz) {
+          const int src = ((cx * 4 + lb * 2 + cz) << 2) | t4;
+          v[cx][0][cz] = __shfl_sync(0xffffffffu, accl[nt][0], src);
+          v[cx][1][cz] = __shfl_sync(0xffffffffu, accl[nt][1], src);
+        }
+      const int j = nt * 4 + t4;
+      const double rho = cxw ? -1.0 : 1.0, sig = czw ? -1.0 : 1.0;
+      // re = ccc - rho sig ssc - sig css - rho scs ; im = -sig csc - rho scc - ccs + rho sig sss   (x y z)
+      const double re = v[0][0][0] - rho * sig * v[1][1][0] - sig * v[0][1][1] - rho * v[1][0][1];
+      const double im = -sig * v[0][1][0] - rho * v[1][0][0] - v[0][0][1] + rho * sig * v[1][1][1];
+      const bool dup = (cxw && i == 0) || (czw && j == 0);
+      if (j < M && !dup) {
+        const int ix = n + (cxw ? -i : i), iy = n + (czw ? -j : j);
+        out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
+      }
+    }
+  }
+}
+
 // Expand the half-grid bank to the reference's full (2n+1)^3 layout (calcFourierCoeff output).
 __global__ void per_expand_kernel(const double2* __restrict__ bank, double2* __restrict__ full,
                                   int n, size_t nsg) {
@@ -1429,6 +1598,14 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
     per_sf2_kernel<MT_, NT_><<<grid, warps * 32, smem, ctx->stream>>>(                                       \
         d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, TA, kx, ky, kz, d_bank);                \
   } while (0)
+        if (M == 10 && warps == 10 && !getenv("FO_SF_PADDED")) {  // default k-grid of 256 atoms: no column padding
+          const size_t smem3 = (size_t)2 * TA * (11 + 13 + 11) * 16;
+          FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+          per_sf3_kernel<<<grid, 320, smem3, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
+                                                           (int)p->natoms, TA, kx, ky, kz, d_bank);
+          FO_LAUNCH_CHECK(ctx);
+          return FO_OK;
+        }
         switch (NTq) {
           case 1: FO_SF2_LAUNCH(5, 1); break;
           case 2: FO_SF2_LAUNCH(5, 2); break;
