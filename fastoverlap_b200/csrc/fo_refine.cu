@@ -27,6 +27,7 @@ namespace {
 constexpr double kPi = 3.14159265358979323846;
 constexpr int RF_THREADS = 256;
 constexpr int RF_MAXIT = 60;
+constexpr int RF_PW = 132;  // 2 Jmax + 1 <= 127 powers, padded
 
 __device__ __forceinline__ double powi_dev(double x, int n) {
   if (n < 0) return 0.0;  // only ever multiplied by a zero coefficient
@@ -92,11 +93,20 @@ __global__ void sph_refine_tab_kernel(int L, RfEdge* __restrict__ edge, double4*
 // part, the ten sums land in res[0..9] (shared).  so = -1 for the inverted orientation (odd l flip).
 __device__ void rf_eval(const double2* __restrict__ Ip, const RfEdge* __restrict__ edge,
                         const double4* __restrict__ coef, int L, double so, const double x[3],
-                        double* red /*[RF_THREADS/32][10]*/, double* res /*[10]*/) {
+                        double* red /*[RF_THREADS/32][10]*/, double* res /*[10]*/,
+                        double* pw /*[2][RF_PW]: cos(b/2)^t, sin(b/2)^t*/) {
   const int W = 2 * L + 1, L1 = L + 1;
   double sb2, cb2, sb, cb;
   sincos(0.5 * x[1], &sb2, &cb2);
   sincos(x[1], &sb, &cb);
+  // powers 0 .. 2L of cos(b/2) and sin(b/2) for the edge values (one short product per thread)
+  for (int t = threadIdx.x; t < 2 * (2 * L + 1); t += RF_THREADS) {
+    const int e = t >> 1;
+    pw[(t & 1) * RF_PW + e] = powi_dev((t & 1) ? sb2 : cb2, e);
+  }
+  __syncthreads();
+  const double* pc = pw;
+  const double* ps = pw + RF_PW;
   double acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.0;
@@ -107,9 +117,10 @@ __device__ void rf_eval(const double2* __restrict__ Ip, const RfEdge* __restrict
     const RfEdge e = edge[item];
     const int p = e.p, q = e.q;
     // C^a S^b and the two derivatives of the edge value (d/db C^a S^b = -a/2 C^{a-1} S^{b+1} + b/2 C^{a+1} S^{b-1})
-    const double Cp2 = powi_dev(cb2, p - 2), Sq2 = powi_dev(sb2, q - 2);
-    const double Cp1 = p >= 2 ? Cp2 * cb2 : powi_dev(cb2, p - 1), Sq1 = q >= 2 ? Sq2 * sb2 : powi_dev(sb2, q - 1);
-    const double Cp = p >= 1 ? Cp1 * cb2 : 1.0, Sq = q >= 1 ? Sq1 * sb2 : 1.0;
+    // (negative exponents only ever meet a zero coefficient)
+    const double Cp2 = p >= 2 ? pc[p - 2] : 0.0, Sq2 = q >= 2 ? ps[q - 2] : 0.0;
+    const double Cp1 = p >= 1 ? pc[p - 1] : 0.0, Sq1 = q >= 1 ? ps[q - 1] : 0.0;
+    const double Cp = pc[p], Sq = ps[q];
     double d = e.K * Cp * Sq;
     double d1 = e.K * (-0.5 * p * Cp1 * (Sq * sb2) + 0.5 * q * (Cp * cb2) * Sq1);
     double d2 = e.K * (0.25 * p * (p - 1) * Cp2 * (Sq * sb2 * sb2) - 0.25 * (p * (q + 1) + q * (p + 1)) * Cp * Sq +
@@ -118,7 +129,8 @@ __device__ void rf_eval(const double2* __restrict__ Ip, const RfEdge* __restrict
     double s0r = 0.0, s0i = 0.0, s1r = 0.0, s1i = 0.0, s2r = 0.0, s2i = 0.0;
     const double2* ip = Ip + (size_t)item * L1;
     const double4* cp = coef + (size_t)item * L1;
-    for (int l = l0; l <= L; ++l) {
+#pragma unroll 4
+    for (int l = l0; l <= L; ++l) {  // the loads do not depend on the recurrence: unrolled, they overlap
       const double4 c = cp[l];
       const double2 v = ip[l];
       const double w = (l & 1) ? so * c.w : c.w;
@@ -196,6 +208,7 @@ sph_refine_kernel(const double2* __restrict__ Ihalf, const RfEdge* __restrict__ 
                   int* __restrict__ iters_out) {
   __shared__ double red[(RF_THREADS / 32) * 10];
   __shared__ double cur[10], tri[10];
+  __shared__ double pw[2 * RF_PW];
   __shared__ double xs[3], xt[3];
   __shared__ int flag;  // 0: evaluate xt, 1: finished
   const size_t po = blockIdx.x;
@@ -213,7 +226,7 @@ sph_refine_kernel(const double2* __restrict__ Ihalf, const RfEdge* __restrict__ 
     }
   }
   __syncthreads();
-  rf_eval(Ip, edge, coef, L, so, xs, red, cur);
+  rf_eval(Ip, edge, coef, L, so, xs, red, cur, pw);
   double lam = 0.0, hs = 0.0;
   int it = 0, nev = 1;
   if (threadIdx.x == 0) hs = fmax(fmax(fabs(cur[4]), fabs(cur[7])), fmax(fabs(cur[9]), 1e-300));
@@ -238,7 +251,7 @@ sph_refine_kernel(const double2* __restrict__ Ihalf, const RfEdge* __restrict__ 
     }
     __syncthreads();
     if (flag) break;
-    rf_eval(Ip, edge, coef, L, so, xt, red, tri);
+    rf_eval(Ip, edge, coef, L, so, xt, red, tri, pw);
     ++nev;
     if (threadIdx.x == 0) {
       if (isfinite(tri[0]) && tri[0] >= cur[0] - 1e-15 * fabs(cur[0])) {
@@ -265,9 +278,10 @@ sph_refine_eval_kernel(const double2* __restrict__ Ihalf, const RfEdge* __restri
                        double* __restrict__ value, double* __restrict__ grad, double* __restrict__ hess) {
   __shared__ double red[(RF_THREADS / 32) * 10];
   __shared__ double cur[10];
+  __shared__ double pw[2 * RF_PW];
   const size_t p = blockIdx.x;
   const double x[3] = {euler[p * 3], euler[p * 3 + 1], euler[p * 3 + 2]};
-  rf_eval(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), edge, coef, L, 1.0, x, red, cur);
+  rf_eval(Ihalf + p * (size_t)(L + 1) * (2 * L + 1) * (L + 1), edge, coef, L, 1.0, x, red, cur, pw);
   if (threadIdx.x == 0) value[p] = cur[0];
   if (threadIdx.x < 3) grad[p * 3 + threadIdx.x] = cur[1 + threadIdx.x];
   if (hess && threadIdx.x < 6) hess[p * 6 + threadIdx.x] = cur[4 + threadIdx.x];

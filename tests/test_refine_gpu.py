@@ -153,3 +153,31 @@ def test_refined_batch_split_identical_and_recovers_rotation(ctx):
     d_di, _ = sa2.align_batch(A, B)
     assert np.all(d_ov < 0.01 * np.sqrt(3 * N) * 3)           # the rotation is recovered (noise level)
     assert np.all(d_di <= d_ov + 1e-9)                         # the distance rule is never worse
+
+
+def test_refine_edge_cases(ctx):
+    """Empty batches, NaN coefficients (must terminate, NaN out, other pairs untouched), general complex
+    coefficients (only the part that generates the real grid enters, as the reference's .real)."""
+    L = 5
+    shape = (L + 1, 2 * L + 1, 2 * L + 1)
+    eu, ov, ne = ctx.sph_refine_rotations(np.zeros((0,) + shape, complex), L, np.zeros((0, 3)))
+    assert eu.shape == (0, 3) and ov.shape == (0,)
+    rng = np.random.default_rng(3)
+    I = np.zeros((3,) + shape, complex)
+    for l in range(L + 1):
+        for m1 in range(-l, l + 1):
+            for m2 in range(-l, l + 1):
+                I[:, l, m1, m2] = rng.normal(size=3) + 1j * rng.normal(size=3)
+    R0 = np.array([[0.3, 1.1, 2.0]] * 3)
+    ref = ctx.sph_refine_rotations(I, L, R0)
+    bad = I.copy()
+    bad[1, 2, 1, 1] = np.nan
+    out = ctx.sph_refine_rotations(bad, L, R0)
+    assert np.isnan(out[1][1])
+    for k in (0, 2):
+        assert np.array_equal(out[0][k], ref[0][k]) and out[1][k] == ref[1][k]
+    # oracle on the general complex set: same value / gradient of Re sum conj(I) D
+    v, g, _ = ctx.sph_overlap_gradient(I[0], L, R0[0])
+    E, gE = oracle.sph_energy_gradient(R0[0], I[0].conj(), L)
+    assert abs(v[0] + E) <= 1e-12 * max(1.0, abs(E)) and np.abs(g[0] + gE).max() <= 1e-11 * max(1.0, abs(E))
+    assert ref[1][0] >= v[0]  # the refinement never ends below its starting value
