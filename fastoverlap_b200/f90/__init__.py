@@ -87,11 +87,13 @@ class _BulkFastOverlap(object):
 
     def align(self, coordsb, coordsa, debug, boxlx, boxly, boxlz, kernelwidth, ndisplacements):
         """(distance, dist2); coordsa is overwritten with the aligned, permuted structure."""
-        if self._m.commons.ohcellt:
-            raise NotImplementedError("O_h cell symmetries are out of scope (broken in the reference, "
-                                      "fastbulk.f90:464-466)")
         natoms = coordsb.size // 3
         al = self._aligner(natoms, [boxlx, boxly, boxlz], kernelwidth)
+        if self._m.commons.ohcellt:  # 48 octahedral operations of a cubic cell (ALIGN1, fastbulk.f90:458-480)
+            dist, X1, X2, perm, disp, R = al.align_oh(coordsb.reshape(natoms, 3), coordsa.reshape(natoms, 3))
+            coordsa[:] = X2.ravel()
+            self._m.commons.bestperm = np.asarray(perm, dtype=int) + 1
+            return dist, dist ** 2
         nd = 10 if ndisplacements == 0 else int(ndisplacements)
         dist, X1, X2, perm, disp = al.align(coordsb.reshape(natoms, 3), coordsa.reshape(natoms, 3),
                                             npeaks=nd)

@@ -173,6 +173,27 @@ class PeriodicAlign(BasePeriodicAlignment):
         disps = self.findDisps(pos1, pos2, Cs, npeaks, width)
         return self.refine(self.pos1, self.pos2, disps)
 
+    def align_oh(self, pos1, pos2, nthreads=0):
+        """Alignment of a CUBIC cell over the 48 octahedral symmetry operations (the reference's
+        OHCELLT branch, ALIGN1 fastbulk.f90:458-480, whose own implementation multiplies the
+        untransformed coefficients): pos2 is transformed by every operation, the 48
+        (pos1, R pos2) pairs go through the GPU hot path in one batch and through the host
+        refinement pool, and the operation with the smallest distance is kept.
+        Returns (dist, X1, X2, perm, disp, R) -- the reference's tuple plus the winning operation."""
+        from .utils import oh_operations
+        if np.ptp(self.boxvec) > 1e-12 * self.boxvec.max():
+            raise ValueError("O_h cell symmetries need a cubic box, got %s" % (self.boxvec,))
+        pos1 = np.asarray(pos1, float).reshape(self.Natoms, 3)
+        pos2 = np.asarray(pos2, float).reshape(self.Natoms, 3)
+        ops = oh_operations()
+        X2s = np.einsum("oij,aj->oai", ops, pos2)
+        X1s = np.broadcast_to(pos1, X2s.shape).copy()
+        dists, disps, perms = self.align_batch(X1s, X2s, nthreads=nthreads)
+        best = int(np.argmin(dists))
+        bi, bv, fr, _, st = self.ctx.per_align_pairs(self._params(), pos1, X2s[best])
+        res = self.refine(pos1, X2s[best], (fr[0] * self.boxvec / np.array(self.fshape, float))[None, :])
+        return tuple(res) + (ops[best],)
+
     # -- batched, additive API
     def findDisps_batch(self, pos1, pos2):
         """pos1, pos2: (P, Natoms, 3).  Returns (disps (P,3), best_idx (P,3), best_val (P,))."""

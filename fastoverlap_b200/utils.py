@@ -160,3 +160,20 @@ def BruteOverlap(pos1, pos2, scale):
     pos2 = np.atleast_2d(pos2)
     rs2 = cdist(pos1, pos2, 'sqeuclidean')
     return np.exp(-rs2 / 4 / scale ** 2).sum() * (pi * scale ** 2) ** 1.5
+
+
+def oh_operations():
+    """The 48 operations of the octahedral group O_h as (48, 3, 3) signed permutation matrices,
+    identity first, the 24 proper rotations before the 24 improper ones.  The reference holds the
+    same set as a data table (OHOPS, alignutils.f90:830-987; OHOPSMAT, fastbulk.f90:102-248); the
+    order only decides which of several exactly equal distances is reported."""
+    import itertools
+    ops = []
+    for perm in itertools.permutations(range(3)):
+        for signs in itertools.product((1.0, -1.0), repeat=3):
+            R = np.zeros((3, 3))
+            for r in range(3):
+                R[r, perm[r]] = signs[r]
+            ops.append(R)
+    ops.sort(key=lambda R: (np.linalg.det(R) < 0, not np.array_equal(R, np.eye(3))))
+    return np.array(ops)

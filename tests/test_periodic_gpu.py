@@ -224,3 +224,39 @@ def test_fast_and_generic_kernels_agree(ctx, N, n):
     assert np.allclose(fast[1], gen[1], rtol=1e-12)
     assert np.allclose(fast[2], gen[2], atol=1e-7)
     assert rel(fast[3], gen[3]) < 1e-12
+
+
+def test_oh_cell_symmetries(ctx):
+    """O_h branch (ALIGN1 with OHCELLT, fastbulk.f90:458-480; broken in the reference): a cubic
+    cell, the partner is an octahedral image + translation + noise + permutation of the first structure.
+    The plain alignment cannot match it, the 48-operation search recovers the noise-level distance and
+    the operation."""
+    from fastoverlap_b200 import PeriodicAlign, PeriodicAlignFortran
+    from fastoverlap_b200.utils import oh_operations
+    rng = np.random.default_rng(48)
+    N, box = 40, np.array([5.0, 5.0, 5.0])
+    groups = [np.arange(30), np.arange(30, 40)]
+    ops = oh_operations()
+    assert ops.shape == (48, 3, 3) and len({o.tobytes() for o in ops}) == 48
+    al = PeriodicAlign(N, box, groups, ctx=ctx)
+    pos1 = rng.uniform(-0.5, 0.5, size=(N, 3)) * box
+    noise = 0.01
+    for k in (7, 19, 41):  # two proper rotations / one improper operation (none the identity)
+        R0 = ops[k]
+        pos2 = pos1.dot(R0.T) + rng.uniform(0, 1, size=3) * box + rng.normal(scale=noise, size=(N, 3))
+        order = np.arange(N)
+        for g in groups:
+            order[g] = rng.permutation(g)
+        pos2 = pos2[order]
+        plain = al(pos1, pos2)[0]
+        dist, X1, X2, perm, disp, R = al.align_oh(pos1, pos2)
+        assert dist < 3 * noise * np.sqrt(3 * N), (k, dist)
+        assert plain > 10 * dist, (k, plain, dist)
+        assert np.array_equal(R, R0.T), k
+        d = X1 - X2
+        d -= np.round(d / box) * box
+        assert abs(np.linalg.norm(d) - dist) < 1e-9
+        fw = PeriodicAlignFortran(N, box, perm=groups)
+        assert abs(fw.align(pos1, pos2, ohcell=True)[0] - dist) < 1e-9
+    with pytest.raises(ValueError):
+        PeriodicAlign(N, [5.0, 5.0, 6.0], groups, ctx=ctx).align_oh(pos1, pos1)
