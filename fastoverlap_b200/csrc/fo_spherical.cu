@@ -1447,7 +1447,9 @@ sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
   // KC L1 lines; with KC = 2 and an even Jmax the last tile is only half full: lane_on masks its rows
   const bool lane_on = ta_on && warp * 4 + (g >> 1) < KC * L1;
   const int line = lane_on ? warp * 4 + (g >> 1) : 0;
-  const int kkA = line / L1, m2A = line - kkA * L1;
+  // lines are ordered (m2, kk), kk fastest: the KC lanes of one m2 read the same coefficient / table
+  // entries in the K5 loop, so those shared-memory loads are broadcasts (half the wavefronts at KC = 2)
+  const int kkA = line % KC, m2A = line / KC;
   const double sm2 = (m2A & 1) ? -1.0 : 1.0;
   // entry ks: a = 4 ks + t4 + 1; entry KS: a = 0 (the row constant c0, evaluated by the t4 == 0 lanes).
   // e_tt: shell-ordered entry index; e_l0: first level >= max(a, m2) with this lane's parity
