@@ -66,6 +66,8 @@ SIGNATURES = {
                                          ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
     "fo_bank_destroy": (None, [c_void_p, c_void_p]),
+    "fo_sph_ylm": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                  c_void_p, c_void_p]),
     "fo_sph_isoft_argmax": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fo_sph_isoft": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
@@ -415,6 +417,19 @@ class Context(object):
         self._check(self._lib.fo_sph_wigner_table(self._h, int(Jmax), _ptr(out)),
                     "fo_sph_wigner_table")
         return out
+
+    def sph_ylm(self, pos, Jmax):
+        """Y[s, l, m (wrapped), atom] and r[s, atom] of S structures (sphHarm layout)."""
+        pos = _f64(pos)
+        if pos.ndim == 2:
+            pos = pos[None]
+        S, N, _ = pos.shape
+        L = int(Jmax)
+        Y = np.empty((S, L + 1, 2 * L + 1, N), np.complex128)
+        r = np.empty((S, N), np.float64)
+        st = np.zeros(S, np.int32)
+        self._check(self._lib.fo_sph_ylm(self._h, _ptr(pos), S, N, L, _ptr(Y), _ptr(r), _ptr(st)), "fo_sph_ylm")
+        return Y, r, st
 
     def _sph_outputs(self, P, Jmax, invert, want_grid):
         O = 2 if invert else 1

@@ -618,6 +618,33 @@ __global__ void sph_unpack_kernel(const double2* __restrict__ Ihalf, int L, size
   }
 }
 
+// Ypk[struct][atom][lm] (m >= 0) -> the reference's sphHarm layout Y[l][m wrap][atom]
+// (sphericalAlignment.py:57-65), Y_{l,-m} = (-1)^m conj(Y_lm); entries with |m| > l are 0.
+__global__ void sph_ylm_expand_kernel(const double2* __restrict__ Ypk, int natoms, int L, size_t nstruct,
+                                      double2* __restrict__ out) {
+  const int W = 2 * L + 1, L1 = L + 1, NLM = nlm_of(L);
+  const size_t per = (size_t)L1 * W * natoms;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < nstruct * per;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t sidx = t / per;
+    size_t r = t - sidx * per;
+    const int a = (int)(r % natoms);
+    r /= natoms;
+    const int mi = (int)(r % W), l = (int)(r / W);
+    const int m = mi <= L ? mi : mi - W;
+    const int am = m < 0 ? -m : m;
+    double2 v = make_double2(0.0, 0.0);
+    if (am <= l) {
+      v = Ypk[(sidx * natoms + a) * NLM + l * (l + 1) / 2 + am];
+      if (m < 0) {
+        const double sg = (am & 1) ? -1.0 : 1.0;
+        v = make_double2(sg * v.x, -sg * v.y);
+      }
+    }
+    out[t] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2b: harmonic-basis coefficients.  d_nl(r) in closed form (Gradshteyn-Ryzhik 7.421.4):
 //   d_nl = 4 pi N_nl sqrt(pi/2) 2^{-l-3/2} beta^{-l-3/2} y^l exp(-r^2/(2(s^2+r0^2))) Q_n,
@@ -2488,6 +2515,47 @@ extern "C" int fo_sph_wigner_table(fo_ctx* ctx, int64_t Jmax, double* out) {
   FO_LAUNCH_CHECK(ctx);
   FO_CUDA(ctx, cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FO_OK;
+}
+
+extern "C" int fo_sph_ylm(fo_ctx* ctx, const double* pos, int64_t nstruct, int64_t natoms, int64_t Jmax,
+                          double* Y_out, double* r_out, int32_t* status) {
+  if (!ctx) return FO_ERR_INVALID;
+  FO_CHECK(check_L(ctx, Jmax));
+  if (natoms < 1) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 required");
+  if (nstruct < 0 || (nstruct > 0 && (!pos || !Y_out))) return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_ylm: NULL argument");
+  if (nstruct == 0) return FO_OK;
+  FO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = (int)Jmax, NLM = nlm_of(L);
+  const size_t full = (size_t)(L + 1) * (2 * L + 1) * natoms;
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / (full * 16 + (size_t)natoms * (NLM * 16 + 40)));
+  if (chunk < 1) chunk = 1;
+  if (chunk > nstruct) chunk = nstruct;
+  void *dpos, *work, *dfull, *dst;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, (size_t)chunk * natoms * 24, &dpos));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, (size_t)chunk * natoms * (NLM * 16 + 8) + 256, &work));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * full * 16, &dfull));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 4 + 64, &dst));
+  const size_t smem_prep = ((size_t)2 * NLM + L + 1) * 8;
+  FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+  for (int64_t s0 = 0; s0 < nstruct; s0 += chunk) {
+    const int64_t ns = std::min(chunk, nstruct - s0);
+    double2* Y = (double2*)work;
+    double* R = (double*)(Y + (size_t)ns * natoms * NLM);
+    FO_CUDA(ctx, cudaMemcpyAsync(dpos, pos + (size_t)s0 * natoms * 3, (size_t)ns * natoms * 24, cudaMemcpyHostToDevice, ctx->stream));
+    FO_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)ns * 4, ctx->stream));
+    sph_prep_kernel<<<grid_for((size_t)ns * natoms * (L + 1), 128, 148 * 16), 128, smem_prep, ctx->stream>>>(
+        (const double*)dpos, (int)natoms, L, (size_t)ns, Y, R, (int*)dst);
+    FO_LAUNCH_CHECK(ctx);
+    sph_ylm_expand_kernel<<<grid_for((size_t)ns * full, 256), 256, 0, ctx->stream>>>(Y, (int)natoms, L, (size_t)ns,
+                                                                                   (double2*)dfull);
+    FO_LAUNCH_CHECK(ctx);
+    FO_CUDA(ctx, cudaMemcpyAsync(Y_out + (size_t)s0 * full * 2, dfull, (size_t)ns * full * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (r_out)
+      FO_CUDA(ctx, cudaMemcpyAsync(r_out + (size_t)s0 * natoms, R, (size_t)ns * natoms * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) FO_CUDA(ctx, cudaMemcpyAsync(status + s0, dst, (size_t)ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return FO_OK;
 }
 

@@ -36,6 +36,10 @@ class SOFT(object):
             self._Ds = self.ctx.sph_wigner_table(self.Jmax)
         return self._Ds
 
+    def calcWignerMatrices(self):
+        """The table Ds (soft.py:73-96), computed on the device (fo_sph_wigner_table)."""
+        return self.ctx.sph_wigner_table(self.Jmax)
+
     @classmethod
     def makeweights(cls, bw):
         """Quadrature weights (soft.py:64-71)."""

@@ -78,6 +78,15 @@ class BaseSphericalAlignment(object):
         dist, MR = findrotation(X1, X2[perm])
         return dist, X1, X2[perm].dot(MR.T)
 
+    def sphHarm(self, theta, phi):
+        """Y[l, m, j] = Y_lm(theta_j, phi_j) for l <= Jmax (reference :57-65: theta polar, phi azimuth,
+        negative m at index m + 2 Jmax + 1) -- evaluated on the GPU (fo_sph_ylm) from the unit vectors."""
+        theta = np.asarray(theta, float).ravel()
+        phi = np.asarray(phi, float).ravel()
+        assert theta.shape == phi.shape
+        u = np.stack([sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta)], axis=1)
+        return self.ctx.sph_ylm(u, self.Jmax)[0][0]
+
     def COM_shift(self, pos1, pos2):
         X1 = np.array(pos1, float)
         X2 = np.array(pos2, float)
@@ -203,6 +212,10 @@ class BaseSphericalAlignment(object):
                 best = inv
         return best
 
+    def _align(self, pos1, pos2, perm=None, invert=True):
+        """The reference's older entry point (:139-158): align without the calcCoeffs hook."""
+        return self.align(pos1, pos2, perm, invert)
+
     def malign(self, pos1, pos2, perm=None, invert=True, calcCoeffs=None, nrot=10):
         """Try the nrot best rotations of each orientation (reference :206-235)."""
         X1, X2, perm = self._setup(pos1, pos2, perm)
@@ -318,6 +331,43 @@ class SphericalHarmonicAlign(BaseSphericalAlignment):
         self.nmax = nmax
         self.setJ(Jmax)
         self.perm = perm
+
+    # -- the reference's radial helper functions (:287-329).  API compatibility only: the coefficient
+    # kernel evaluates d_nl(r) in closed form and uses none of these.
+    @classmethod
+    def radialIntegralHarmonic(cls, n, l, rj, sigma, r0):
+        """int_0^inf exp(-(r^2+rj^2)/2s^2) exp(-r^2/2r0^2) i_l(r rj/s^2) r^(n+2) dr (reference :288-299)."""
+        from scipy.special import hyp1f1, gamma
+        a = 0.5 * (3 + n + l)
+        return (sqrt(2.0 ** (3 + n - l) * pi ** 3) * rj ** l * (sigma ** -2 + r0 ** -2) ** (-a) * sigma ** (-2 * l) *
+                hyp1f1(a, 1.5 + l, 0.5 * rj ** 2 * r0 ** 2 / (r0 ** 2 * sigma ** 2 + sigma ** 4)) *
+                gamma(a) / gamma(1.5 + l) * exp(-0.5 * rj ** 2 / sigma ** 2))
+
+    @classmethod
+    def HarmCoeffs(cls, nmax, lmax, r0):
+        """coeffs[n, l, s]: power-series coefficients in r of N_nl r^l L_n^{l+1/2}(r^2/r0^2) (reference :313-319)."""
+        from .utils import coeffs_harmonicBasis
+        coeffs = np.zeros((nmax + 1, lmax + 1, 2 * nmax + lmax + 1))
+        for n in range(nmax + 1):
+            for l in range(lmax + 1):
+                coeffs[n, l, :2 * n + l + 1] = coeffs_harmonicBasis(n, l, r0)
+        return coeffs
+
+    @classmethod
+    def _radial_moments(cls, smax, r0):
+        from scipy.special import gamma
+        ns = np.arange(smax)
+        return gamma(0.5 * (ns + 3)) * 2 ** (0.5 * (ns + 1)) * r0 ** (3 + ns)
+
+    @classmethod
+    def HarmInt(cls, n, l, r0):
+        """int_0^inf N_nl r^l exp(-r^2/2r0^2) L_n^{l+1/2}(r^2/r0^2) r^2 dr (reference :301-311)."""
+        from .utils import coeffs_harmonicBasis
+        return coeffs_harmonicBasis(n, l, r0).dot(cls._radial_moments(2 * n + l + 1, r0))
+
+    @classmethod
+    def HarmInts(cls, nmax, lmax, r0):
+        return cls.HarmCoeffs(nmax, lmax, r0).dot(cls._radial_moments(2 * nmax + lmax + 1, r0))
 
     def setCoeffs(self, nmax=None, Jmax=None, harmscale=None):
         if nmax is not None:

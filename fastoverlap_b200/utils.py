@@ -177,3 +177,21 @@ def oh_operations():
             ops.append(R)
     ops.sort(key=lambda R: (np.linalg.det(R) < 0, not np.array_equal(R, np.eye(3))))
     return np.array(ops)
+
+
+def norm_harmonicBasis(n, l, r0):
+    """Normalisation N_nl of the harmonic-oscillator radial basis function (reference utils.py:408-412)."""
+    from scipy.special import factorial, gamma
+    return np.sqrt(2 * factorial(n) * r0 ** (-2 * l - 3) / gamma(1.5 + n + l))
+
+
+def coeffs_harmonicBasis(n, l, r0):
+    """Coefficients g_s, s = 0 .. 2n+l, of  N_nl r^l L_n^{l+1/2}(r^2) = sum_s g_s r^s  (reference
+    utils.py:414-427).  As in the reference the Laguerre argument is not scaled by r0 (exact for the
+    default harmscale r0 = 1); the device kernel does not use this expansion.
+    L_n^a(x) = sum_k (-1)^k binom(n + a, n - k) x^k / k!."""
+    from scipy.special import binom, factorial
+    k = np.arange(n + 1)
+    out = np.zeros(2 * n + l + 1)
+    out[l::2] = (-1.0) ** k * binom(n + l + 0.5, n - k) / factorial(k)
+    return out * norm_harmonicBasis(n, l, r0)

@@ -176,6 +176,14 @@ void fo_bank_destroy(fo_ctx* ctx, fo_bank* bank);
 
 /* ---------------------------------------------------------------- spherical (fastclusters) */
 
+/* Spherical harmonics of the atoms of S structures (row a1): Y_out [S, L+1, 2L+1, N] complex in the
+ * layout of BaseSphericalAlignment.sphHarm (sphericalAlignment.py:57-65: scipy / Condon-Shortley
+ * convention, negative m at index m + 2L+1, zeros for |m| > l) / RYML (fastclusters.f90:602-652);
+ * r_out [S, N] (nullable) = |pos| (calcThetaPhiR, utils.py:439-445).  An atom at the origin sets
+ * FO_STATUS_ATOM_AT_ORIGIN (the reference yields NaN). */
+int fo_sph_ylm(fo_ctx* ctx, const double* pos /*[S,N,3]*/, int64_t nstruct, int64_t natoms, int64_t Jmax,
+               double* Y_out, double* r_out, int32_t* status);
+
 /* Inverse SO(3) Fourier transform + arg-max for P coefficient sets, host buffers.
  * Ilmm is [P, L+1, 2L+1, 2L+1, 2] doubles in the reference's numpy layout (negative m stored
  * at index m + 2L+1, i.e. python negative-index wrap; soft.py:115-125).

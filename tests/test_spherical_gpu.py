@@ -351,3 +351,30 @@ def test_large_cluster_rotation_recovery(ctx, N, J):
     sa = SphericalAlign(0.37, J, ctx=ctx)
     dist = sa(A, B)[0]
     assert dist < 2.0 * np.linalg.norm(noise), dist
+
+
+def test_sphharm_stage_method(ctx):
+    """a1 as a stage method: sphHarm(theta, phi) (sphericalAlignment.py:57-65) on the device vs scipy, in the
+    reference's [l, m wrapped, atom] layout; r from fo_sph_ylm; SOFT.calcWignerMatrices; _align alias."""
+    from scipy.special import sph_harm_y
+    from fastoverlap_b200 import SphericalAlign, SOFT
+    rng = np.random.default_rng(57)
+    for L in (4, 15, 31):
+        sa = SphericalAlign(0.3, L, ctx=ctx)
+        pos = rng.normal(size=(23, 3))
+        r = np.linalg.norm(pos, axis=1)
+        theta, phi = np.arccos(pos[:, 2] / r), np.arctan2(pos[:, 1], pos[:, 0])
+        Y = sa.sphHarm(theta, phi)
+        assert Y.shape == (L + 1, 2 * L + 1, 23)
+        ref = np.zeros_like(Y)
+        for l in range(L + 1):
+            for m in range(-l, l + 1):
+                ref[l, m] = sph_harm_y(l, m, theta, phi)
+        assert np.abs(Y - ref).max() < 2e-13, L
+        Y2, r2, st = ctx.sph_ylm(pos, L)
+        assert np.abs(Y2[0] - ref).max() < 2e-13 and np.abs(r2[0] - r).max() < 1e-15 and st[0] == 0
+    s = golden("soft_tables.npz")
+    assert np.abs(SOFT(8, ctx=ctx).calcWignerMatrices() - s["Ds_8"]).max() < 1e-12
+    g = golden("spherical_lj38.npz")
+    sa = SphericalAlign(0.3, 15, ctx=ctx)
+    assert abs(sa._align(g["pos1"], g["pos2"])[0] - float(g["J15_dist"])) < DIST_ATOL
