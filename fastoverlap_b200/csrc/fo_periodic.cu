@@ -327,15 +327,12 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   const double* spos = pos + (size_t)s * natoms * 3;
   const double kax[3] = {kx, ky, kz};
 
-  int offx[MT], offy[MT];
+  // rows r = (warp MT + mt) 8 + g: (i M + j) = warp 10 + 2 mt + (g >> 2), i.e. i = warp for every tile of
+  // the warp (MT = 5, M = 10) -- one x operand per k-step serves all five A elements
+  const int offx0 = warp * 2 + ((g >> 1) & 1);
+  int offy[MT];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    const int r = (warp * MT + mt) * 8 + g;
-    const int c4 = r & 3, ij = r >> 2;
-    const int i = ij / M, j = ij - i * M;
-    offx[mt] = i * 2 + ((c4 >> 1) & 1);
-    offy[mt] = j * 2 + (c4 & 1);
-  }
+  for (int mt = 0; mt < MT; ++mt) offy[mt] = (2 * mt + (g >> 2)) * 2 + (g & 1);
   // left-over tile of this warp: i = warp, row g = cx 4 + zl, zl = (l - 8) 2 + cz
   const int offxl = warp * 2 + (g >> 2), offzl = 16 + (g & 3);
 
@@ -400,8 +397,10 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
 #pragma unroll
+      const double xv = xr[offx0];
+#pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const double av = xr[offx[mt]] * yr[offy[mt]];
+        const double av = xv * yr[offy[mt]];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
       }
