@@ -40,6 +40,8 @@ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_doub
 // complex accumulation over the full grid that the reference performs.
 // ------------------------------------------------------------------------------------------
 constexpr int SF_TA = 64;  // atoms per shared-memory tile
+// smallest row pitch >= m with pitch = 2 (mod 4), in double2 elements (DMMA structure-factor kernels)
+__host__ __device__ constexpr int sf_pitch(int m) { return m + ((6 - (m & 3)) & 3); }
 
 template <int TL>
 __global__ void __launch_bounds__(512)
@@ -170,8 +172,10 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
                double kz, double2* __restrict__ bank) {
   extern __shared__ double2 sm_ph2[];
   const int M = n + 1;
-  const int Mp = M | 1;
-  const int Mz = (4 * NT) | 1;  // z rows zero padded up to 4 NT values of l
+  // row pitches = 2 mod 4 (in double2): the four atoms (t4) of a k-step start 8 banks apart, so the
+  // 8-byte operand loads of a warp are free of bank conflicts (odd pitches cost ~1.6 wavefronts per load)
+  const int Mp = sf_pitch(M);
+  const int Mz = sf_pitch(4 * NT);  // z rows zero padded up to 4 NT values of l
   double2* phx = sm_ph2;
   double2* phy = phx + TA * Mp;
   double2* phz = phy + TA * Mp;
@@ -219,6 +223,8 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
     double2* bx = phx + buf * buf_elems;
     double2* by = phy + buf * buf_elems;
     double2* bz = phz + buf * buf_elems;
+    // (items packed into the first warps: spreading them over all warps costs more FP64 issue slots --
+    // a partly filled warp occupies the pipe like a full one -- and measured 2.6 % slower)
     for (int t = tid; t < 3 * ta4; t += blockDim.x) {
       const int a = t / 3, ax = t - 3 * a;
       const int pitch = (ax == 2) ? Mz : Mp;
@@ -317,9 +323,9 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
                double kz, double2* __restrict__ bank) {
   extern __shared__ double2 sm_ph3[];
   constexpr int n = 9, M = 10, MT = 5, NT = 2, NTL = 3;
-  constexpr int Mp = M | 1;          // x rows
-  constexpr int My = (4 * NTL) | 1;  // y rows zero padded to 4 NTL values of j
-  constexpr int Mz = M | 1;
+  constexpr int Mp = sf_pitch(M);        // x rows (pitches = 2 mod 4: conflict-free operand loads)
+  constexpr int My = sf_pitch(4 * NTL);  // y rows zero padded to 4 NTL values of j
+  constexpr int Mz = sf_pitch(M);
   const int s = blockIdx.x, gq = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
@@ -354,6 +360,8 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
     double2* bx = phx + buf * buf_elems;
     double2* by = phy + buf * buf_elems;
     double2* bz = phz + buf * buf_elems;
+    // (items packed into the first warps: spreading them over all warps costs more FP64 issue slots --
+    // a partly filled warp occupies the pipe like a full one -- and measured 2.6 % slower)
     for (int t = tid; t < 3 * ta4; t += blockDim.x) {
       const int a = t / 3, ax = t - 3 * a;
       const int pitch = ax == 0 ? Mp : (ax == 1 ? My : Mz);
@@ -396,7 +404,6 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
       double bz[NT];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
-#pragma unroll
       const double xv = xr[offx0];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -1581,11 +1588,23 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
       int warps = (mtiles + MTq - 1) / MTq;
       if (warps > 10) warps = 10;
       const int nz = (mtiles + MTq * warps - 1) / (MTq * warps);
-      const int Mp = M | 1, Mz = (4 * NTq) | 1;
-      // double-buffered phasor tables of TA atoms; TA shrinks on fine k-grids so that two CTAs share an SM
-      int TA = SF_TA;
-      while (TA > 16 && (size_t)2 * TA * (2 * Mp + Mz) * 16 > (size_t)113 * 1024) TA >>= 1;
-      const size_t smem = (size_t)2 * TA * (2 * Mp + Mz) * 16;
+      const int Mp = sf_pitch(M), Mz = sf_pitch(4 * NTq);
+      // double-buffered phasor tables of TA atoms.  Every tile costs one CTA barrier (measured ~2.5 % of the
+      // kernel each at n = 9), so TA is the largest tile that still lets two CTAs share an SM (113 KB each),
+      // then evened out over the tiles of the largest group: 204 atoms -> 2 tiles of 104 (64-atom tiles: 4)
+      const bool sf3 = M == 10 && warps == 10 && !getenv("FO_SF_PADDED");  // per_sf3_kernel: no column padding
+      const size_t row_bytes = (sf3 ? sf_pitch(10) + sf_pitch(12) + sf_pitch(10) : 2 * Mp + Mz) * (size_t)16;
+      int TA = (int)((size_t)113 * 1024 / (2 * row_bytes)) & ~3;
+      TA = TA < 16 ? 16 : (TA > 128 ? 128 : TA);
+      int gmax = 1;
+      for (int q = 0; q < ngroups; ++q) gmax = std::max(gmax, (int)(ctx->h_goff[q + 1] - ctx->h_goff[q]));
+      const int ntile = (gmax + TA - 1) / TA;
+      TA = std::min(TA, (((gmax + ntile - 1) / ntile) + 3) & ~3);
+      if (const char* e = getenv("FO_SF_TA")) {  // tuning override (multiple of 4)
+        const int v = atoi(e);
+        if (v >= 4 && v <= 256 && v % 4 == 0) TA = v;
+      }
+      const size_t smem = (size_t)2 * TA * row_bytes;
       if (smem <= ctx->prop.sharedMemPerBlockOptin) {
         const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
         dim3 grid((unsigned)nstruct, (unsigned)ngroups, (unsigned)nz);
@@ -1597,10 +1616,9 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
     per_sf2_kernel<MT_, NT_><<<grid, warps * 32, smem, ctx->stream>>>(                                       \
         d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, TA, kx, ky, kz, d_bank);                \
   } while (0)
-        if (M == 10 && warps == 10 && !getenv("FO_SF_PADDED")) {  // default k-grid of 256 atoms: no column padding
-          const size_t smem3 = (size_t)2 * TA * (11 + 13 + 11) * 16;
-          FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-          per_sf3_kernel<<<grid, 320, smem3, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
+        if (sf3) {  // default k-grid of 256 atoms
+          FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          per_sf3_kernel<<<grid, 320, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
                                                            (int)p->natoms, TA, kx, ky, kz, d_bank);
           FO_LAUNCH_CHECK(ctx);
           return FO_OK;
