@@ -326,10 +326,9 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   constexpr int Mp = sf_pitch(M);        // x rows (pitches = 2 mod 4: conflict-free operand loads)
   constexpr int My = sf_pitch(4 * NTL);  // y rows zero padded to 4 NTL values of j
   constexpr int Mz = sf_pitch(M);
-  const int s = blockIdx.x, gq = blockIdx.y;
+  const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int a_begin = goff[gq], a_end = goff[gq + 1];
   const double* spos = pos + (size_t)s * natoms * 3;
   const double kax[3] = {kx, ky, kz};
 
@@ -342,26 +341,18 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   // left-over tile of this warp: i = warp, row g = cx 4 + zl, zl = (l - 8) 2 + cz
   const int offxl = warp * 2 + (g >> 2), offzl = 16 + (g & 3);
 
-  double acc[MT][NT][2], accl[NTL][2];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-#pragma unroll
-  for (int nt = 0; nt < NTL; ++nt) accl[nt][0] = accl[nt][1] = 0.0;
-
   const size_t buf_elems = (size_t)TA * (Mp + My + Mz);  // double2 elements per buffer
   double2* phx = sm_ph3;
   double2* phy = phx + (size_t)TA * Mp;
   double2* phz = phy + (size_t)TA * My;
-  auto build_phasors = [&](int a0, int buf) {
+  // (items packed into the first warps: spreading them over all warps costs more FP64 issue slots --
+  // a partly filled warp occupies the pipe like a full one -- and measured 2.6 % slower)
+  auto build_phasors = [&](int a0, int a_end, int buf) {
     const int ta = min(TA, a_end - a0);
     const int ta4 = (ta + 3) & ~3;
     double2* bx = phx + buf * buf_elems;
     double2* by = phy + buf * buf_elems;
     double2* bz = phz + buf * buf_elems;
-    // (items packed into the first warps: spreading them over all warps costs more FP64 issue slots --
-    // a partly filled warp occupies the pipe like a full one -- and measured 2.6 % slower)
     for (int t = tid; t < 3 * ta4; t += blockDim.x) {
       const int a = t / 3, ax = t - 3 * a;
       const int pitch = ax == 0 ? Mp : (ax == 1 ? My : Mz);
@@ -386,93 +377,122 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
       }
     }
   };
-  if (a_begin < a_end) build_phasors(a_begin, 0);
+  // One CTA per structure runs through the permutation groups in turn: the table of the next tile -- of
+  // the same group or the first tile of the next non-empty one -- is built while the current tile is on the
+  // tensor pipe, so only the first tile of the structure has an exposed build, and a warp's epilogue of one
+  // group overlaps the other warps' DMMA of the next.  (One CTA per (structure, group) left the short
+  // groups -- 52 of 256 atoms in BLJ256 -- with a build and an epilogue as long as their DMMA phase.)
+  auto next_group = [&](int q) {  // first non-empty group >= q, or ngroups
+    while (q < ngroups && goff[q + 1] == goff[q]) ++q;
+    return q;
+  };
+  {
+    const int q0 = next_group(0);
+    if (q0 < ngroups) build_phasors(goff[q0], goff[q0 + 1], 0);
+  }
   __syncthreads();
   int buf = 0;
-  for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1) {
-    const int ta = min(TA, a_end - a0);
-    const int ta4 = (ta + 3) & ~3;
-    if (a0 + TA < a_end) build_phasors(a0 + TA, buf ^ 1);
-    const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
-    const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
-    const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
-    for (int k0 = 0; k0 < ta4; k0 += 4) {
-      const int a = k0 + t4;
-      const double* xr = dx_ + (size_t)a * Mp * 2;
-      const double* yr = dy_ + (size_t)a * My * 2;
-      const double* zr = dz_ + (size_t)a * Mz * 2;
-      double bz[NT];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
-      const double xv = xr[offx0];
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const double av = xv * yr[offy[mt]];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
-      }
-      const double avl = xr[offxl] * zr[offzl];
-#pragma unroll
-      for (int nt = 0; nt < NTL; ++nt) fo_dmma(accl[nt], avl, yr[nt * 8 + g]);
-    }
-    __syncthreads();
-  }
-  // ---- epilogue
   constexpr int W = 2 * n + 1;
-  double2* out = bank + ((size_t)s * ngroups + gq) * ((size_t)W * W * M);
-  // main block: as per_sf2 (lanes g = 4u + c4 of one (i, j); this lane writes the signs of its own c4)
+  for (int gq = 0; gq < ngroups; ++gq) {
+    const int a_begin = goff[gq], a_end = goff[gq + 1];
+    double acc[MT][NT][2], accl[NTL][2];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    const int r = (warp * MT + mt) * 8 + g;
-    const int c4 = r & 3, ij = r >> 2;
-    const int i = ij / M, j = ij - i * M;
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      double v[4][2];
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int src = (((g & 4) | q) << 2) | t4;
-        v[q][0] = __shfl_sync(0xffffffffu, acc[mt][nt][0], src);
-        v[q][1] = __shfl_sync(0xffffffffu, acc[mt][nt][1], src);
+    for (int nt = 0; nt < NTL; ++nt) accl[nt][0] = accl[nt][1] = 0.0;
+    for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1) {
+      const int ta = min(TA, a_end - a0);
+      const int ta4 = (ta + 3) & ~3;
+      bool more = true;  // CTA-uniform: is there a tile after this one?
+      if (a0 + TA < a_end) {
+        build_phasors(a0 + TA, a_end, buf ^ 1);
+      } else {
+        const int q = next_group(gq + 1);
+        more = q < ngroups;
+        if (more) build_phasors(goff[q], goff[q + 1], buf ^ 1);
       }
-      const int l = nt * 4 + t4;
-      const double rho = (c4 & 2) ? -1.0 : 1.0, sig = (c4 & 1) ? -1.0 : 1.0;
-      const double re = v[0][0] - rho * sig * v[3][0] - sig * v[1][1] - rho * v[2][1];
-      const double im = -sig * v[1][0] - rho * v[2][0] - v[0][1] + rho * sig * v[3][1];
-      const bool dup = ((c4 & 2) && i == 0) || ((c4 & 1) && j == 0);
-      if (!dup) {
-        const int ix = n + ((c4 & 2) ? -i : i), iy = n + ((c4 & 1) ? -j : j);
-        out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
+      const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
+      const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
+      const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
+      for (int k0 = 0; k0 < ta4; k0 += 4) {
+        const int a = k0 + t4;
+        const double* xr = dx_ + (size_t)a * Mp * 2;
+        const double* yr = dy_ + (size_t)a * My * 2;
+        const double* zr = dz_ + (size_t)a * Mz * 2;
+        double bz[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
+        const double xv = xr[offx0];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const double av = xv * yr[offy[mt]];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
+        }
+        const double avl = xr[offxl] * zr[offzl];
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) fo_dmma(accl[nt], avl, yr[nt * 8 + g]);
+      }
+      if (more) __syncthreads();  // the last tile of the structure needs no barrier behind it
+    }
+    // ---- epilogue of group gq (zeros for an empty group)
+    double2* out = bank + ((size_t)s * ngroups + gq) * ((size_t)W * W * M);
+    // main block: as per_sf2 (lanes g = 4u + c4 of one (i, j); this lane writes the signs of its own c4)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r = (warp * MT + mt) * 8 + g;
+      const int c4 = r & 3, ij = r >> 2;
+      const int i = ij / M, j = ij - i * M;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        double v[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int src = (((g & 4) | q) << 2) | t4;
+          v[q][0] = __shfl_sync(0xffffffffu, acc[mt][nt][0], src);
+          v[q][1] = __shfl_sync(0xffffffffu, acc[mt][nt][1], src);
+        }
+        const int l = nt * 4 + t4;
+        const double rho = (c4 & 2) ? -1.0 : 1.0, sig = (c4 & 1) ? -1.0 : 1.0;
+        const double re = v[0][0] - rho * sig * v[3][0] - sig * v[1][1] - rho * v[2][1];
+        const double im = -sig * v[1][0] - rho * v[2][0] - v[0][1] + rho * sig * v[3][1];
+        const bool dup = ((c4 & 2) && i == 0) || ((c4 & 1) && j == 0);
+        if (!dup) {
+          const int ix = n + ((c4 & 2) ? -i : i), iy = n + ((c4 & 1) ? -j : j);
+          out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
+        }
       }
     }
-  }
-  // left-over block: i = warp; lane (g, t4) of column tile nt holds (j = 4 nt + t4; cy = 0, 1) of row
-  // (cx = g >> 2, l = 8 + ((g >> 1) & 1), cz = g & 1).  The four lanes (cx, cz) of one (j, l) gather all
-  // eight sums v[cx][cy][cz] and write the sign combination rho = (cx ? - : +), sig = (cz ? - : +).
-  {
-    const int i = warp;
-    const int cxw = g >> 2, lb = (g >> 1) & 1, czw = g & 1;
-    const int l = 8 + lb;
+    // left-over block: i = warp; lane (g, t4) of column tile nt holds (j = 4 nt + t4; cy = 0, 1) of row
+    // (cx = g >> 2, l = 8 + ((g >> 1) & 1), cz = g & 1).  The four lanes (cx, cz) of one (j, l) gather all
+    // eight sums v[cx][cy][cz] and write the sign combination rho = (cx ? - : +), sig = (cz ? - : +).
+    {
+      const int i = warp;
+      const int cxw = g >> 2, lb = (g >> 1) & 1, czw = g & 1;
+      const int l = 8 + lb;
 #pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) {
-      double v[2][2][2];  // [cx][cy][cz]
+      for (int nt = 0; nt < NTL; ++nt) {
+        double v[2][2][2];  // [cx][cy][cz]
 #pragma unroll
-      for (int cx = 0; cx < 2; ++cx)
+        for (int cx = 0; cx < 2; ++cx)
 #pragma unroll
-        for (int cz = 0; cz < 2; ++cz) {
-          const int src = ((cx * 4 + lb * 2 + cz) << 2) | t4;
-          v[cx][0][cz] = __shfl_sync(0xffffffffu, accl[nt][0], src);
-          v[cx][1][cz] = __shfl_sync(0xffffffffu, accl[nt][1], src);
+          for (int cz = 0; cz < 2; ++cz) {
+            const int src = ((cx * 4 + lb * 2 + cz) << 2) | t4;
+            v[cx][0][cz] = __shfl_sync(0xffffffffu, accl[nt][0], src);
+            v[cx][1][cz] = __shfl_sync(0xffffffffu, accl[nt][1], src);
+          }
+        const int j = nt * 4 + t4;
+        const double rho = cxw ? -1.0 : 1.0, sig = czw ? -1.0 : 1.0;
+        // re = ccc - rho sig ssc - sig css - rho scs ; im = -sig csc - rho scc - ccs + rho sig sss   (x y z)
+        const double re = v[0][0][0] - rho * sig * v[1][1][0] - sig * v[0][1][1] - rho * v[1][0][1];
+        const double im = -sig * v[0][1][0] - rho * v[1][0][0] - v[0][0][1] + rho * sig * v[1][1][1];
+        const bool dup = (cxw && i == 0) || (czw && j == 0);
+        if (j < M && !dup) {
+          const int ix = n + (cxw ? -i : i), iy = n + (czw ? -j : j);
+          out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
         }
-      const int j = nt * 4 + t4;
-      const double rho = cxw ? -1.0 : 1.0, sig = czw ? -1.0 : 1.0;
-      // re = ccc - rho sig ssc - sig css - rho scs ; im = -sig csc - rho scc - ccs + rho sig sss   (x y z)
-      const double re = v[0][0][0] - rho * sig * v[1][1][0] - sig * v[0][1][1] - rho * v[1][0][1];
-      const double im = -sig * v[0][1][0] - rho * v[1][0][0] - v[0][0][1] + rho * sig * v[1][1][1];
-      const bool dup = (cxw && i == 0) || (czw && j == 0);
-      if (j < M && !dup) {
-        const int ix = n + (cxw ? -i : i), iy = n + (czw ? -j : j);
-        out[((size_t)ix * W + iy) * M + l] = make_double2(re, im);
       }
     }
   }
@@ -1618,7 +1638,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
   } while (0)
         if (sf3) {  // default k-grid of 256 atoms
           FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          per_sf3_kernel<<<grid, 320, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
+          per_sf3_kernel<<<(unsigned)nstruct, 320, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
                                                            (int)p->natoms, TA, kx, ky, kz, d_bank);
           FO_LAUNCH_CHECK(ctx);
           return FO_OK;

@@ -38,12 +38,21 @@ else:
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(reps):
-    run()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
+import subprocess
+def timed():
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader", "-lms", "100"],
+                       stdout=subprocess.PIPE, text=True)
+blocks = [timed() for _ in range(4)]
+smi.terminate()
+lines = [l.strip() for l in smi.stdout.read().splitlines() if l.strip()]
+print("blocks ms/step:", [round(b, 3) for b in blocks], "| smi:", lines[:: max(1, len(lines) // 6)][:8])
+ms = min(blocks)
 ctx.profile_begin()
 for _ in range(4):
     run()
