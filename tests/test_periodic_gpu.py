@@ -80,6 +80,8 @@ def _random_pairs(rng, P, N, box, jitter=0.05):
 
 @pytest.mark.parametrize("N,n,groups", [(17, 3, None), (40, 6, [23, 17]), (64, 9, [50, 14]),
                                          (33, 11, None), (5, 1, None),
+                                         # per_sf3: several atom tiles per group, an empty and a tiny group
+                                         (230, 9, [120, 0, 3, 107]),
                                          (36, 16, [20, 16]), (24, 32, None)])  # fine k-grids: F = 72, 135
 def test_batch_vs_oracle(ctx, N, n, groups):
     """Seeded random batches: every pair's grid, arg-max and interpolated maximum vs the oracle."""
