@@ -309,6 +309,28 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   }
 }
 
+// mbarrier primitives (shared::cta): init / arrive by every participating thread / wait on a phase parity
+__device__ __forceinline__ void fo_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void fo_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fo_mbar_wait(uint64_t* bar, int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "FO_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra FO_MBAR_DONE;\n"
+      "bra FO_MBAR_WAIT;\n"
+      "FO_MBAR_DONE:\n"
+      "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // per_sf3_kernel: per_sf2 for n = 9 (M = 10, the default k-grid of a 256-atom cell) without the
 // 20 -> 24 column padding.  The 2M = 20 columns split into 16 (l = 0..7: two full column tiles, as in
@@ -317,6 +339,7 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
 // 80 rows = one 8-row tile per i (= per warp: 10 warps), 20 -> 24 columns (3 tiles): 30 DMMA per
 // k-step instead of the 50 of a third column tile; 130 instead of 150 DMMA per k-step in total.
 // ------------------------------------------------------------------------------------------
+template <bool MB>
 __global__ void __launch_bounds__(320, 2)
 per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
                const int32_t* __restrict__ gidx, int ngroups, int natoms, int TA, double kx, double ky,
@@ -386,12 +409,24 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
     while (q < ngroups && goff[q + 1] == goff[q]) ++q;
     return q;
   };
+  // Tile hand-over.  MB: mbarriers instead of a CTA barrier per tile -- full[b] (every thread arrives after
+  // its share of the table of buffer b is written) and empty[b] (every thread arrives when it has finished
+  // reading buffer b).  A thread waits for full[b] before the tile, and builds the next tile in the MIDDLE
+  // of the current one, after waiting for empty of the buffer it overwrites -- by then a formality: all
+  // warps left that buffer half a tile ago.  So warps never meet; they can drift by up to half a tile
+  // (a __syncthreads per tile cost ~2.5 % of the kernel each: profiles/r01_summary.md).
+  __shared__ uint64_t mbar[4];  // full[0], full[1], empty[0], empty[1]
+  if (MB) {
+    if (tid == 0)
+      for (int i = 0; i < 4; ++i) fo_mbar_init(&mbar[i], blockDim.x);
+    __syncthreads();
+  }
   {
     const int q0 = next_group(0);
     if (q0 < ngroups) build_phasors(goff[q0], goff[q0 + 1], 0);
   }
-  __syncthreads();
-  int buf = 0;
+  if (MB) fo_mbar_arrive(&mbar[0]); else __syncthreads();
+  int buf = 0, tile = 0;
   constexpr int W = 2 * n + 1;
   for (int gq = 0; gq < ngroups; ++gq) {
     const int a_begin = goff[gq], a_end = goff[gq + 1];
@@ -402,40 +437,62 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 #pragma unroll
     for (int nt = 0; nt < NTL; ++nt) accl[nt][0] = accl[nt][1] = 0.0;
-    for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1) {
+    for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1, ++tile) {
       const int ta = min(TA, a_end - a0);
       const int ta4 = (ta + 3) & ~3;
-      bool more = true;  // CTA-uniform: is there a tile after this one?
+      // next tile (CTA-uniform): same group, or the first tile of the next non-empty group
+      int nb = -1, ne = 0;
       if (a0 + TA < a_end) {
-        build_phasors(a0 + TA, a_end, buf ^ 1);
+        nb = a0 + TA;
+        ne = a_end;
       } else {
         const int q = next_group(gq + 1);
-        more = q < ngroups;
-        if (more) build_phasors(goff[q], goff[q + 1], buf ^ 1);
+        if (q < ngroups) {
+          nb = goff[q];
+          ne = goff[q + 1];
+        }
       }
+      const bool more = nb >= 0;
+      if (!MB && more) build_phasors(nb, ne, buf ^ 1);
+      if (MB) fo_mbar_wait(&mbar[buf], (tile >> 1) & 1);
       const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
       const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
       const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
-      for (int k0 = 0; k0 < ta4; k0 += 4) {
-        const int a = k0 + t4;
-        const double* xr = dx_ + (size_t)a * Mp * 2;
-        const double* yr = dy_ + (size_t)a * My * 2;
-        const double* zr = dz_ + (size_t)a * Mz * 2;
-        double bz[NT];
+      auto mma_ksteps = [&](int kb, int ke) {
+        for (int k0 = kb; k0 < ke; k0 += 4) {
+          const int a = k0 + t4;
+          const double* xr = dx_ + (size_t)a * Mp * 2;
+          const double* yr = dy_ + (size_t)a * My * 2;
+          const double* zr = dz_ + (size_t)a * Mz * 2;
+          double bz[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
-        const double xv = xr[offx0];
+          for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
+          const double xv = xr[offx0];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const double av = xv * yr[offy[mt]];
+          for (int mt = 0; mt < MT; ++mt) {
+            const double av = xv * yr[offy[mt]];
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
+            for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
+          }
+          const double avl = xr[offxl] * zr[offzl];
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt) fo_dmma(accl[nt], avl, yr[nt * 8 + g]);
         }
-        const double avl = xr[offxl] * zr[offzl];
-#pragma unroll
-        for (int nt = 0; nt < NTL; ++nt) fo_dmma(accl[nt], avl, yr[nt * 8 + g]);
+      };
+      if (MB) {
+        const int kh = ((ta4 >> 2) >> 1) << 2;  // first half of the k-steps
+        mma_ksteps(0, kh);
+        if (more) {
+          if (tile >= 1) fo_mbar_wait(&mbar[2 + (buf ^ 1)], ((tile - 1) >> 1) & 1);
+          build_phasors(nb, ne, buf ^ 1);
+          fo_mbar_arrive(&mbar[buf ^ 1]);
+        }
+        mma_ksteps(kh, ta4);
+        fo_mbar_arrive(&mbar[2 + buf]);
+      } else {
+        mma_ksteps(0, ta4);
+        if (more) __syncthreads();  // the last tile of the structure needs no barrier behind it
       }
-      if (more) __syncthreads();  // the last tile of the structure needs no barrier behind it
     }
     // ---- epilogue of group gq (zeros for an empty group)
     double2* out = bank + ((size_t)s * ngroups + gq) * ((size_t)W * W * M);
@@ -1637,9 +1694,17 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
         d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, TA, kx, ky, kz, d_bank);                \
   } while (0)
         if (sf3) {  // default k-grid of 256 atoms
-          FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          per_sf3_kernel<<<(unsigned)nstruct, 320, smem, ctx->stream>>>(d_pos, ctx->d_goff, ctx->d_gidx, ngroups,
-                                                           (int)p->natoms, TA, kx, ky, kz, d_bank);
+          if (!getenv("FO_SF_SYNCTHREADS")) {  // tile hand-over through mbarriers (default)
+            FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            per_sf3_kernel<true><<<(unsigned)nstruct, 320, smem, ctx->stream>>>(
+                d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, TA, kx, ky, kz, d_bank);
+          } else {
+            FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            per_sf3_kernel<false><<<(unsigned)nstruct, 320, smem, ctx->stream>>>(
+                d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, TA, kx, ky, kz, d_bank);
+          }
           FO_LAUNCH_CHECK(ctx);
           return FO_OK;
         }
