@@ -63,7 +63,8 @@ class Blj256:
                             "configs[4] batching)", "natoms": 256, "species": [204, 52],
                 "nwave": self.n, "nfspace": self.F, "pairs_per_step_per_gpu": pairs,
                 "seed": 256, "l2_policy": "inputs + intermediates per step exceed L2 "
-                "(coords %.0f MB, structure-factor bank %.0f MB per chunk)" % (
+                "(coords %.0f MB, structure-factor bank %.0f MB per chunk of 3256 pairs through host buffers, up "
+                "to three times that device-resident)" % (
                     2 * pairs * 256 * 24 / 1e6, 3256 * 2 * 2 * 3610 * 16 / 1e6)}
 
     def make(self, pairs, rank):
@@ -491,9 +492,15 @@ def run_ours(args, wl):
         try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 tr = json.load(f)[wl.dominant]
-            roof["traffic"] = tr["bytes_per_launch"]
-            roof["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read+write, %d %ss per launch)" % (
-                tr["units_per_launch"], tr["unit"])
+            # the capture holds the bytes of one launch of tr["units_per_launch"] units; the launches of this run
+            # may be larger (chunk size), so scale by the units an average launch of the timed region processed
+            units_timed = pairs_timed * (2 if tr["unit"] == "structure" else 1)
+            units_per_launch = units_timed / dom_n
+            roof["traffic"] = tr["bytes_per_launch"] * units_per_launch / tr["units_per_launch"]
+            roof["traffic_source"] = ("profiles/r01_traffic.json (ncu dram__bytes_read+write: %.0f bytes per %s, "
+                                      "captured on a launch of %d; x %.0f %ss per launch here)" % (
+                                          tr["bytes_per_launch"] / tr["units_per_launch"], tr["unit"],
+                                          tr["units_per_launch"], units_per_launch, tr["unit"]))
         except Exception:
             pass
         try:
