@@ -30,10 +30,24 @@ namespace {
 struct Lap {
   std::vector<double> u, v, shortest;
   std::vector<int> path, row4col, remaining, colmin;
-  std::vector<char> SR, SC;
-  // colmin_in / vmin_in (optional): per-column minimum and its row, when the caller already has them
-  void solve(int n, const double* cost, int* col4row, const int* colmin_in = nullptr,
-             const double* vmin_in = nullptr) {
+  std::vector<char> SR, SC, rowdone;
+  // colmin_in / vmin_in (optional): per-column minimum and its row, when the caller already has them.
+  // lazy_sqrt: cost (and vmin_in) hold SQUARED costs; the LAP runs on their square roots, taken row by row
+  // only for the rows an augmentation actually scans.  The column reduction needs no roots but those of
+  // the column minima (sqrt is monotone), and after a good alignment it already assigns almost every row,
+  // so a 204 x 204 periodic cost matrix costs ~200 square roots instead of 41616 (the vector sqrt was
+  // 2/3 of the whole host refinement of a BLJ256 pair).
+  void solve(int n, double* cost, int* col4row, const int* colmin_in = nullptr,
+             const double* vmin_in = nullptr, bool lazy_sqrt = false) {
+    if (lazy_sqrt) rowdone.assign(n, 0);
+    auto row_of = [&](int i) -> const double* {
+      double* ci = cost + (size_t)i * n;
+      if (lazy_sqrt && !rowdone[i]) {
+        for (int j = 0; j < n; ++j) ci[j] = __builtin_sqrt(ci[j]);
+        rowdone[i] = 1;
+      }
+      return ci;
+    };
     u.assign(n, 0.0);
     v.assign(n, 0.0);
     shortest.resize(n);
@@ -51,12 +65,12 @@ struct Lap {
     {
       const int* cm = colmin_in;
       if (cm) {
-        for (int j = 0; j < n; ++j) v[j] = vmin_in[j];
+        for (int j = 0; j < n; ++j) v[j] = lazy_sqrt ? __builtin_sqrt(vmin_in[j]) : vmin_in[j];
       } else {
         colmin.assign(n, 0);
-        for (int j = 0; j < n; ++j) v[j] = cost[j];
+        for (int j = 0; j < n; ++j) v[j] = row_of(0)[j];
         for (int i = 1; i < n; ++i) {
-          const double* ci = cost + (size_t)i * n;
+          const double* ci = row_of(i);
           for (int j = 0; j < n; ++j)
             if (ci[j] < v[j]) {
               v[j] = ci[j];
@@ -86,7 +100,7 @@ struct Lap {
         int index = -1;
         double lowest = inf;
         SR[i] = 1;
-        const double* ci = cost + (size_t)i * n;
+        const double* ci = row_of(i);
         for (int it = 0; it < nrem; ++it) {
           const int j = remaining[it];
           const double r = minVal + ci[j] - u[i] - v[j];
@@ -139,57 +153,121 @@ struct Groups {
 // d * (1/box) instead of d / box can move the rounding only at exact half-box separations, where both
 // images give the same distance.
 #if defined(__GNUC__) && !defined(__CUDACC__)
-#define FO_CLONES __attribute__((target_clones("avx2", "default")))
+#define FO_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
 #else
 #define FO_CLONES
 #endif
 
 // vmin / imin: running minimum of every column and its row (the column reduction of the LAP), kept in
-// the same pass that writes the matrix.
+// the same pass that writes the matrix.  Both kernels write SQUARED distances; the periodic LAP is on the
+// distances themselves (periodicAlignment.py:94-102) and takes the square roots lazily.
+// Columns are processed in blocks of CB: the block's y coordinates, running minima and their rows stay in
+// registers over the whole sweep down the rows (the row-by-row form reloaded and stored vmin / imin for
+// every element and ran at ~18 cycles per 4-wide vector); the row index is carried as a double so that all
+// lanes have one type.
+constexpr int CB = 8;
+
 FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const double* box, double* cost,
                              double* vmin, int* imin) {
   const double b0 = box[0], b1 = box[1], b2 = box[2];
   const double i0 = 1.0 / b0, i1 = 1.0 / b1, i2 = 1.0 / b2;
-  const double *y0 = ys, *y1 = ys + n, *y2 = ys + 2 * n;
-  for (int j = 0; j < n; ++j) {
-    vmin[j] = std::numeric_limits<double>::infinity();
-    imin[j] = 0;
-  }
-  for (int i = 0; i < n; ++i) {
-    const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i];
-    double* c = cost + (size_t)i * n;
+  const double inf = std::numeric_limits<double>::infinity();
+  for (int jb = 0; jb < n; jb += CB) {
+    const int w = n - jb < CB ? n - jb : CB;
+    double y0[CB], y1[CB], y2[CB], vm[CB], im[CB];
+    for (int jj = 0; jj < CB; ++jj) {
+      const int j = jb + (jj < w ? jj : w - 1);  // the tail block repeats its last column
+      y0[jj] = ys[j];
+      y1[jj] = ys[n + j];
+      y2[jj] = ys[2 * n + j];
+      vm[jj] = inf;
+      im[jj] = 0.0;
+    }
+    if (w == CB) {
+      for (int i = 0; i < n; ++i) {
+        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
+        double* c = cost + (size_t)i * n + jb;
 #pragma omp simd
-    for (int j = 0; j < n; ++j) {
-      double dx = x0 - y0[j], dy = x1 - y1[j], dz = x2 - y2[j];
-      dx -= __builtin_rint(dx * i0) * b0;
-      dy -= __builtin_rint(dy * i1) * b1;
-      dz -= __builtin_rint(dz * i2) * b2;
-      const double d = __builtin_sqrt(dx * dx + dy * dy + dz * dz);
-      c[j] = d;
-      const bool lt = d < vmin[j];
-      vmin[j] = lt ? d : vmin[j];
-      imin[j] = lt ? i : imin[j];
+        for (int jj = 0; jj < CB; ++jj) {
+          double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
+          dx -= __builtin_rint(dx * i0) * b0;
+          dy -= __builtin_rint(dy * i1) * b1;
+          dz -= __builtin_rint(dz * i2) * b2;
+          const double d = dx * dx + dy * dy + dz * dz;  // squared: Lap::solve(lazy_sqrt) takes the roots it needs
+          c[jj] = d;
+          const bool lt = d < vm[jj];
+          vm[jj] = lt ? d : vm[jj];
+          im[jj] = lt ? di : im[jj];
+        }
+      }
+    } else {
+      for (int i = 0; i < n; ++i) {
+        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
+        double* c = cost + (size_t)i * n + jb;
+        for (int jj = 0; jj < w; ++jj) {
+          double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
+          dx -= __builtin_rint(dx * i0) * b0;
+          dy -= __builtin_rint(dy * i1) * b1;
+          dz -= __builtin_rint(dz * i2) * b2;
+          const double d = dx * dx + dy * dy + dz * dz;
+          c[jj] = d;
+          const bool lt = d < vm[jj];
+          vm[jj] = lt ? d : vm[jj];
+          im[jj] = lt ? di : im[jj];
+        }
+      }
+    }
+    for (int jj = 0; jj < w; ++jj) {
+      vmin[jb + jj] = vm[jj];
+      imin[jb + jj] = (int)im[jj];
     }
   }
 }
 
 FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost, double* vmin, int* imin) {
-  const double *y0 = ys, *y1 = ys + n, *y2 = ys + 2 * n;
-  for (int j = 0; j < n; ++j) {
-    vmin[j] = std::numeric_limits<double>::infinity();
-    imin[j] = 0;
-  }
-  for (int i = 0; i < n; ++i) {
-    const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i];
-    double* c = cost + (size_t)i * n;
+  const double inf = std::numeric_limits<double>::infinity();
+  for (int jb = 0; jb < n; jb += CB) {
+    const int w = n - jb < CB ? n - jb : CB;
+    double y0[CB], y1[CB], y2[CB], vm[CB], im[CB];
+    for (int jj = 0; jj < CB; ++jj) {
+      const int j = jb + (jj < w ? jj : w - 1);
+      y0[jj] = ys[j];
+      y1[jj] = ys[n + j];
+      y2[jj] = ys[2 * n + j];
+      vm[jj] = inf;
+      im[jj] = 0.0;
+    }
+    if (w == CB) {
+      for (int i = 0; i < n; ++i) {
+        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
+        double* c = cost + (size_t)i * n + jb;
 #pragma omp simd
-    for (int j = 0; j < n; ++j) {
-      const double dx = x0 - y0[j], dy = x1 - y1[j], dz = x2 - y2[j];
-      const double d = dx * dx + dy * dy + dz * dz;
-      c[j] = d;
-      const bool lt = d < vmin[j];
-      vmin[j] = lt ? d : vmin[j];
-      imin[j] = lt ? i : imin[j];
+        for (int jj = 0; jj < CB; ++jj) {
+          const double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
+          const double d = dx * dx + dy * dy + dz * dz;
+          c[jj] = d;
+          const bool lt = d < vm[jj];
+          vm[jj] = lt ? d : vm[jj];
+          im[jj] = lt ? di : im[jj];
+        }
+      }
+    } else {
+      for (int i = 0; i < n; ++i) {
+        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
+        double* c = cost + (size_t)i * n + jb;
+        for (int jj = 0; jj < w; ++jj) {
+          const double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
+          const double d = dx * dx + dy * dy + dz * dz;
+          c[jj] = d;
+          const bool lt = d < vm[jj];
+          vm[jj] = lt ? d : vm[jj];
+          im[jj] = lt ? di : im[jj];
+        }
+      }
+    }
+    for (int jj = 0; jj < w; ++jj) {
+      vmin[jb + jj] = vm[jj];
+      imin[jb + jj] = (int)im[jj];
     }
   }
 }
@@ -221,7 +299,7 @@ void best_perm(const Groups& G, int natoms, const double* X, const double* Y, co
       cost_periodic(n, xs, ys, box, cost.data(), vmin.data(), imin.data());
     else
       cost_free(n, xs, ys, cost.data(), vmin.data(), imin.data());
-    lap.solve(n, cost.data(), c4r.data(), imin.data(), vmin.data());
+    lap.solve(n, cost.data(), c4r.data(), imin.data(), vmin.data(), /*lazy_sqrt=*/box != nullptr);
     for (int i = 0; i < n; ++i) perm[idx[i]] = c4r[i] >= 0 ? idx[c4r[i]] : idx[i];
   }
 }

@@ -165,6 +165,53 @@ def test_native_periodic_refine_matches_reference_and_python():
         assert abs(d - dist[i]) < 1e-9 and np.array_equal(pyperm, pm[i]) and np.allclose(pydisp, disp[i], atol=1e-9)
 
 
+def test_native_periodic_refine_hard_assignments():
+    """Large jitter (many rows left free by the column reduction, so the augmentation scans rows whose
+    square roots are taken lazily) and group sizes that are not multiples of the 8-column blocks of the
+    cost kernel: permutations identical to scipy's linear_sum_assignment on the min-image distance matrix,
+    distances to 1e-12."""
+    from scipy.optimize import linear_sum_assignment
+    from fastoverlap_b200 import _lib
+    rng = np.random.default_rng(11)
+    N, box, F = 61, np.array([4.0, 4.5, 5.0]), 24
+    groups = [np.arange(37), np.arange(37, 50), np.arange(50, 61)]
+    P = 12
+    A = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
+    shift = rng.uniform(0, 1, size=(P, 1, 3)) * box
+    B = A + shift + rng.normal(scale=0.35, size=A.shape)
+    for i in range(P):
+        B[i] = B[i][np.concatenate([g[0] + rng.permutation(len(g)) for g in groups])]
+    frac = shift[:, 0, :] / box * F
+    pp = _lib.Context.per_params(N, box, 5, F, 0.3)
+    dist, pm, disp = _lib.host_refine_periodic(pp, groups, A, B, frac, nthreads=2)
+
+    def mi(d):
+        return d - np.rint(d / box) * box
+
+    def bestperm(x, y):
+        perm = np.arange(N)
+        for g in groups:
+            c = np.linalg.norm(mi(x[g][:, None, :] - y[g][None, :, :]), axis=2)
+            r, cc = linear_sum_assignment(c)
+            perm[g[r]] = g[cc]
+        return perm
+
+    for q in range(P):
+        x, y, d = A[q], B[q], frac[q] * box / F
+        save = bestperm(x, y - d)
+        perm = save
+        for _ in range(10):
+            d = d - mi(x - (y[save] - d)).mean(0)
+            perm = bestperm(x, y - d)
+            if np.array_equal(perm, save):
+                break
+            save = perm
+        d = d - mi(x - (y[perm] - d)).mean(0)
+        ref = np.sqrt((mi(mi(x) - mi(y[perm] - d)) ** 2).sum())
+        assert np.array_equal(perm, pm[q])
+        assert abs(ref - dist[q]) < 1e-12
+
+
 def test_native_spherical_refine_matches_reference_and_python():
     from fastoverlap_b200 import _lib
     from fastoverlap_b200.spherical import SphericalAlign
