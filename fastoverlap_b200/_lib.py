@@ -121,6 +121,7 @@ SIGNATURES = {
     "fo_host_refine_periodic": (ctypes.c_int, [ctypes.POINTER(PerParams), c_void_p, ctypes.c_int64, c_void_p,
                                                c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int,
                                                ctypes.c_int, c_void_p, c_void_p, c_void_p]),
+    "fo_host_refine_counters": (None, [c_void_p, ctypes.c_int]),
     "fo_host_refine_spherical": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
                                                 ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
                                                 c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -203,6 +204,14 @@ def host_refine_periodic(params, perm, posA, posB, frac_idx, niter=10, nthreads=
     if rc != 0:
         raise FastOverlapError("fo_host_refine_periodic failed (%d)" % rc)
     return dist, pm, disp
+
+
+def host_refine_counters(reset=False):
+    """(LAP solves, screened assignments, skipped repeat solves) of host_refine_periodic since load / the
+    last reset (fo_host_refine_counters)."""
+    out = np.zeros(3, np.int64)
+    load_library().fo_host_refine_counters(_ptr(out), int(bool(reset)))
+    return tuple(int(v) for v in out)
 
 
 def host_refine_spherical(posA, posB, euler, perm=None, nthreads=0):

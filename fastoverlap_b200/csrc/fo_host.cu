@@ -26,6 +26,10 @@
 
 namespace {
 
+// fo_host_refine_counters: [0] LAP solves, [1] screened assignments, [2] skipped repeat solves
+long long g_counters[3] = {0, 0, 0};
+inline void count(int k) { __atomic_fetch_add(&g_counters[k], 1LL, __ATOMIC_RELAXED); }
+
 // Dense n x n linear assignment (minimise), cost row-major.  col4row[i] = column assigned to row i.
 struct Lap {
   std::vector<double> u, v, shortest;
@@ -161,6 +165,7 @@ struct Groups {
 // vmin / imin: running minimum of every column and its row (the column reduction of the LAP), kept in
 // the same pass that writes the matrix.  Both kernels write SQUARED distances; the periodic LAP is on the
 // distances themselves (periodicAlignment.py:94-102) and takes the square roots lazily.
+// vmin2: the second smallest entry of every column (squared), for the gap test of best_perm.
 // Columns are processed in blocks of CB: the block's y coordinates, running minima and their rows stay in
 // registers over the whole sweep down the rows (the row-by-row form reloaded and stored vmin / imin for
 // every element and ran at ~18 cycles per 4-wide vector); the row index is carried as a double so that all
@@ -168,19 +173,20 @@ struct Groups {
 constexpr int CB = 8;
 
 FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const double* box, double* cost,
-                             double* vmin, int* imin) {
+                             double* vmin, int* imin, double* vmin2) {
   const double b0 = box[0], b1 = box[1], b2 = box[2];
   const double i0 = 1.0 / b0, i1 = 1.0 / b1, i2 = 1.0 / b2;
   const double inf = std::numeric_limits<double>::infinity();
   for (int jb = 0; jb < n; jb += CB) {
     const int w = n - jb < CB ? n - jb : CB;
-    double y0[CB], y1[CB], y2[CB], vm[CB], im[CB];
+    double y0[CB], y1[CB], y2[CB], vm[CB], v2[CB], im[CB];
     for (int jj = 0; jj < CB; ++jj) {
       const int j = jb + (jj < w ? jj : w - 1);  // the tail block repeats its last column
       y0[jj] = ys[j];
       y1[jj] = ys[n + j];
       y2[jj] = ys[2 * n + j];
       vm[jj] = inf;
+      v2[jj] = inf;
       im[jj] = 0.0;
     }
     if (w == CB) {
@@ -196,6 +202,8 @@ FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const do
           const double d = dx * dx + dy * dy + dz * dz;  // squared: Lap::solve(lazy_sqrt) takes the roots it needs
           c[jj] = d;
           const bool lt = d < vm[jj];
+          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
+          v2[jj] = hi < v2[jj] ? hi : v2[jj];
           vm[jj] = lt ? d : vm[jj];
           im[jj] = lt ? di : im[jj];
         }
@@ -212,6 +220,8 @@ FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const do
           const double d = dx * dx + dy * dy + dz * dz;
           c[jj] = d;
           const bool lt = d < vm[jj];
+          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
+          v2[jj] = hi < v2[jj] ? hi : v2[jj];
           vm[jj] = lt ? d : vm[jj];
           im[jj] = lt ? di : im[jj];
         }
@@ -219,22 +229,25 @@ FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const do
     }
     for (int jj = 0; jj < w; ++jj) {
       vmin[jb + jj] = vm[jj];
+      vmin2[jb + jj] = v2[jj];
       imin[jb + jj] = (int)im[jj];
     }
   }
 }
 
-FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost, double* vmin, int* imin) {
+FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost, double* vmin, int* imin,
+                         double* vmin2) {
   const double inf = std::numeric_limits<double>::infinity();
   for (int jb = 0; jb < n; jb += CB) {
     const int w = n - jb < CB ? n - jb : CB;
-    double y0[CB], y1[CB], y2[CB], vm[CB], im[CB];
+    double y0[CB], y1[CB], y2[CB], vm[CB], v2[CB], im[CB];
     for (int jj = 0; jj < CB; ++jj) {
       const int j = jb + (jj < w ? jj : w - 1);
       y0[jj] = ys[j];
       y1[jj] = ys[n + j];
       y2[jj] = ys[2 * n + j];
       vm[jj] = inf;
+      v2[jj] = inf;
       im[jj] = 0.0;
     }
     if (w == CB) {
@@ -247,6 +260,8 @@ FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost
           const double d = dx * dx + dy * dy + dz * dz;
           c[jj] = d;
           const bool lt = d < vm[jj];
+          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
+          v2[jj] = hi < v2[jj] ? hi : v2[jj];
           vm[jj] = lt ? d : vm[jj];
           im[jj] = lt ? di : im[jj];
         }
@@ -260,6 +275,8 @@ FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost
           const double d = dx * dx + dy * dy + dz * dz;
           c[jj] = d;
           const bool lt = d < vm[jj];
+          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
+          v2[jj] = hi < v2[jj] ? hi : v2[jj];
           vm[jj] = lt ? d : vm[jj];
           im[jj] = lt ? di : im[jj];
         }
@@ -267,25 +284,131 @@ FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost
     }
     for (int jj = 0; jj < w; ++jj) {
       vmin[jb + jj] = vm[jj];
+      vmin2[jb + jj] = v2[jj];
       imin[jb + jj] = (int)im[jj];
     }
   }
 }
 
+// Single-precision screening pass of the periodic assignment: smallest and second smallest min-image
+// distance (squared) of every column and the row of the smallest, 16 columns at a time, nothing stored.
+// After a good alignment every atom's partner is far closer than anything else, the column minima form a
+// permutation, and that permutation is the unique optimum of the assignment -- proven by best_perm from
+// these three arrays with the rounding error of this pass as a tolerance, so that neither the double-
+// precision matrix nor the LAP is needed.  Coordinates must be wrapped into [-box/2, box/2] (error analysis
+// in best_perm).
+// Written with GCC vector extensions (one 16-float vector per statement; the AVX2 / default clones split
+// it): the scalar form of this update was compiled into mask tests and branches with the running minima
+// spilled to the stack.  rint(t) = (t + 1.5 * 2^23) - 1.5 * 2^23 for |t| < 2^22 in round-to-nearest.
+// ys is padded to a multiple of CBF columns per component (pitch npad), the padding repeating a real column.
+constexpr int CBF = 16;
+typedef float vf16 __attribute__((vector_size(64)));
+typedef int vi16 __attribute__((vector_size(64)));
+
+FO_CLONES void colmin_periodic_f32(int n, int npad, const float* xs, const float* ys, const float* box, float* vmin,
+                                   int* imin, float* vmin2) {
+  const float b0 = box[0], b1 = box[1], b2 = box[2];
+  const float i0 = 1.0f / b0, i1 = 1.0f / b1, i2 = 1.0f / b2;
+  const float inf = std::numeric_limits<float>::infinity(), M = 12582912.0f;
+  for (int jb = 0; jb < npad; jb += CBF) {
+    vf16 y0, y1, y2;
+    memcpy(&y0, ys + jb, sizeof(vf16));
+    memcpy(&y1, ys + npad + jb, sizeof(vf16));
+    memcpy(&y2, ys + 2 * npad + jb, sizeof(vf16));
+    vf16 vm = y0 * 0.0f + inf, v2 = vm;
+    vi16 im = {0};
+    for (int i = 0; i < n; ++i) {
+      vf16 dx = xs[i] - y0, dy = xs[n + i] - y1, dz = xs[2 * n + i] - y2;
+      dx -= ((dx * i0 + M) - M) * b0;
+      dy -= ((dy * i1 + M) - M) * b1;
+      dz -= ((dz * i2 + M) - M) * b2;
+      const vf16 d = dx * dx + dy * dy + dz * dz;
+      const vi16 lt = d < vm;
+      const vf16 hi = lt ? vm : d;  // the larger of the entry and the running minimum
+      v2 = hi < v2 ? hi : v2;
+      vm = lt ? d : vm;
+      im = lt ? (vi16){0} + i : im;
+    }
+    memcpy(vmin + jb, &vm, sizeof(vf16));
+    memcpy(vmin2 + jb, &v2, sizeof(vf16));
+    memcpy(imin + jb, &im, sizeof(vi16));
+  }
+}
+
+// Screening of one periodic group in single precision (colmin_periodic_f32).  Returns true, the assignment
+// (c4r[row] = column) and the updated stability margin when the column minima provably form the unique
+// optimal assignment; false when the double-precision matrix + LAP has to decide.
+// Rounding: wrapped coordinates |x| <= b / 2 (b = largest box length) are cast with an error <= 3e-8 b; the
+// difference, the image shift and the rounding of the box lengths add <= 7e-7 b per component in the worst
+// case (a difference within rounding of half a box may take the other image, which moves it by twice its
+// distance to the half box), so a distance is off by less than 2e-6 b.  tol = 1e-5 b is used: row i_j is
+// certainly the strict minimum of column j when sqrt(second) - sqrt(first) > 2 tol in single precision, and
+// the true gap is at least that difference - 2 tol.
+bool screen_periodic(int n, const double* xs, const double* ys, const double* box, int* imin, int* c4r,
+                     double* margin) {
+  static thread_local std::vector<float> f;
+  static thread_local std::vector<int> im;
+  static thread_local std::vector<char> seen;
+  const int npad = (n + CBF - 1) / CBF * CBF;
+  if (f.size() < (size_t)3 * n + 5 * npad) {
+    f.resize((size_t)3 * n + 5 * npad);
+    im.resize(npad);
+  }
+  float* xf = f.data();
+  float* yf = xf + 3 * n;
+  float* v1 = yf + 3 * npad;
+  float* v2 = v1 + npad;
+  const float boxf[3] = {(float)box[0], (float)box[1], (float)box[2]};
+  for (int k = 0; k < 3; ++k) {
+    const double b = box[k], ib = 1.0 / b;
+    for (int i = 0; i < n; ++i) {
+      const double x = xs[k * n + i], y = ys[k * n + i];
+      xf[k * n + i] = (float)(x - __builtin_rint(x * ib) * b);
+      yf[k * npad + i] = (float)(y - __builtin_rint(y * ib) * b);
+    }
+    for (int i = n; i < npad; ++i) yf[k * npad + i] = yf[k * npad + n - 1];
+  }
+  colmin_periodic_f32(n, npad, xf, yf, boxf, v1, im.data(), v2);
+  for (int j = 0; j < n; ++j) imin[j] = im[j];
+  const double tol2 = 2e-5 * std::max(box[0], std::max(box[1], box[2]));
+  seen.assign(n, 0);
+  double gap = std::numeric_limits<double>::infinity();
+  for (int j = 0; j < n; ++j) {
+    const double g = __builtin_sqrt((double)v2[j]) - __builtin_sqrt((double)v1[j]) - tol2;
+    if (!(g > 0) || seen[imin[j]]) return false;  // also catches NaN coordinates
+    seen[imin[j]] = 1;
+    gap = std::min(gap, g);
+    c4r[imin[j]] = j;
+  }
+  *margin = std::min(*margin, gap);
+  return true;
+}
+
 // permutation of Y that best matches X group by group; periodic (box != null: cost = min-image
-// distance, periodicAlignment.py:94-102) or free (squared distance, utils.py:48-56)
-void best_perm(const Groups& G, int natoms, const double* X, const double* Y, const double* box, Lap& lap,
-               std::vector<double>& cost, std::vector<int>& c4r, int* perm) {
-  static thread_local std::vector<double> soa, vmin;
+// distance, periodicAlignment.py:94-102) or free (squared distance, utils.py:48-56).
+// Returns the stability margin of the periodic result: when in every group every column's smallest entry
+// sits in a different row, that assignment is the unique optimum (it attains the lower bound sum_j min_i
+// c_ij), and it stays the unique optimum for as long as no column minimum changes rows.  The min-image
+// distance is a metric on the torus, so moving all of Y by delta changes every entry by at most |delta|:
+// the permutation provably survives any |delta| < margin / 2, margin = min_j (second smallest - smallest
+// entry of column j).  -1 when the column minima do not form a permutation (or for free costs).
+// screen (optional, one flag per group, in / out): whether the single-precision screening is worth trying;
+// cleared for a group once it fails, so that the later solves of a badly aligned pair go straight to the LAP.
+double best_perm(const Groups& G, int natoms, const double* X, const double* Y, const double* box, Lap& lap,
+                 std::vector<double>& cost, std::vector<int>& c4r, int* perm, char* screen = nullptr) {
+  static thread_local std::vector<double> soa, vmin, vmin2;
   static thread_local std::vector<int> imin;
+  static thread_local std::vector<char> seen;
+  double margin = box ? std::numeric_limits<double>::infinity() : -1.0;
   for (int i = 0; i < natoms; ++i) perm[i] = i;
   for (int64_t g = 0; g < G.ngroups; ++g) {
     const int n = G.goff[g + 1] - G.goff[g];
     if (n == 0) continue;
     const int32_t* idx = G.gidx + G.goff[g];
-    cost.resize((size_t)n * n);
-    c4r.resize(n);
-    soa.resize((size_t)6 * n);
+    // grow only: shrinking for a small group and growing again would zero-fill the matrix every time
+    if (cost.size() < (size_t)n * n) cost.resize((size_t)n * n);
+    if (c4r.size() < (size_t)n) c4r.resize(n);
+    if (soa.size() < (size_t)6 * n) soa.resize((size_t)6 * n);
     double* xs = soa.data();
     double* ys = xs + 3 * n;
     for (int i = 0; i < n; ++i)
@@ -293,15 +416,39 @@ void best_perm(const Groups& G, int natoms, const double* X, const double* Y, co
         xs[k * n + i] = X[3 * idx[i] + k];
         ys[k * n + i] = Y[3 * idx[i] + k];
       }
-    vmin.resize(n);
-    imin.resize(n);
+    if (vmin.size() < (size_t)n) {
+      vmin.resize(n);
+      vmin2.resize(n);
+      imin.resize(n);
+    }
+    if (box && screen && screen[g] && n >= 2 && n < (1 << 24)) {
+      if (screen_periodic(n, xs, ys, box, imin.data(), c4r.data(), &margin)) {
+        for (int i = 0; i < n; ++i) perm[idx[i]] = idx[c4r[i]];
+        count(1);
+        continue;
+      }
+      screen[g] = 0;
+    }
+    if (box) count(0);
     if (box)
-      cost_periodic(n, xs, ys, box, cost.data(), vmin.data(), imin.data());
+      cost_periodic(n, xs, ys, box, cost.data(), vmin.data(), imin.data(), vmin2.data());
     else
-      cost_free(n, xs, ys, cost.data(), vmin.data(), imin.data());
+      cost_free(n, xs, ys, cost.data(), vmin.data(), imin.data(), vmin2.data());
     lap.solve(n, cost.data(), c4r.data(), imin.data(), vmin.data(), /*lazy_sqrt=*/box != nullptr);
     for (int i = 0; i < n; ++i) perm[idx[i]] = c4r[i] >= 0 ? idx[c4r[i]] : idx[i];
+    if (margin >= 0) {
+      seen.assign(n, 0);
+      double gap = std::numeric_limits<double>::infinity();
+      bool ok = true;
+      for (int j = 0; j < n; ++j) {
+        ok = ok && !seen[imin[j]] && vmin[j] == vmin[j];
+        seen[imin[j]] = 1;
+        gap = std::min(gap, __builtin_sqrt(vmin2[j]) - __builtin_sqrt(vmin[j]));  // entries are squared
+      }
+      margin = ok ? std::min(margin, gap) : -1.0;
+    }
   }
+  return margin;
 }
 
 // smallest eigenpair of a symmetric 4x4 matrix by cyclic Jacobi
@@ -409,6 +556,13 @@ void euler_m(double a, double b, double y, double M[9]) {
 
 }  // namespace
 
+extern "C" void fo_host_refine_counters(int64_t out[3], int reset) {
+  for (int k = 0; k < 3; ++k) {
+    out[k] = (int64_t)__atomic_load_n(&g_counters[k], __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_counters[k], 0LL, __ATOMIC_RELAXED);
+  }
+}
+
 extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
                                        const int32_t* atom_idx, const double* posA, const double* posB,
                                        const double* frac_idx, int64_t npairs, int niter, int nthreads,
@@ -428,6 +582,7 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
     Lap lap;
     std::vector<double> cost, ys((size_t)3 * N);
     std::vector<int> c4r, perm(N), save(N);
+    std::vector<char> screen(ngroups);
 #pragma omp for schedule(dynamic, 4)
     for (int64_t q = 0; q < npairs; ++q) {
       const double* x = posA + (size_t)q * N * 3;
@@ -445,12 +600,23 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
         for (int k = 0; k < 3; ++k) disp[k] -= m[k] / N;
       };
       shift();
-      best_perm(G, N, x, ys.data(), p->box, lap, cost, c4r, save.data());
+      std::fill(screen.begin(), screen.end(), 1);
+      double margin = best_perm(G, N, x, ys.data(), p->box, lap, cost, c4r, save.data(), screen.data());
+      double dref[3] = {disp[0], disp[1], disp[2]};  // displacement the margin belongs to
       perm = save;
       for (int it = 0; it < niter; ++it) {
         recentre(save.data());
+        // The reference solves the assignment again and stops when it comes back unchanged
+        // (periodicAlignment.py:66-75).  When the move since the last solve is provably too small to change
+        // it (best_perm), the solve is skipped: same permutation, same displacement, bit for bit.
+        const double dx = disp[0] - dref[0], dy = disp[1] - dref[1], dz = disp[2] - dref[2];
+        if (margin > 0 && 2.0 * sqrt(dx * dx + dy * dy + dz * dz) + 1e-9 < margin) {
+          count(2);
+          break;
+        }
         shift();
-        best_perm(G, N, x, ys.data(), p->box, lap, cost, c4r, perm.data());
+        margin = best_perm(G, N, x, ys.data(), p->box, lap, cost, c4r, perm.data(), screen.data());
+        for (int k = 0; k < 3; ++k) dref[k] = disp[k];
         if (perm == save) break;
         save = perm;
       }

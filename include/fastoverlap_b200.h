@@ -321,7 +321,9 @@ int fo_per_align_pairs_peaks(fo_ctx* ctx, const fo_per_params* p, const double* 
  * (nthreads <= 0: all cores).  They take the hot-path outputs (frac_idx / Euler angles) directly. */
 
 /* Periodic: permutation (Jonker-Volgenant LAP on the minimum-image distance matrix, per group) <->
- * mean-displacement iteration, at most niter rounds.  Replaces BasePeriodicAlignment.refine
+ * mean-displacement iteration, at most niter rounds.  Well-aligned pairs never build the matrix: a
+ * single-precision pass proves the nearest-partner assignment optimal, and the loop's confirming second
+ * solve is skipped when the displacement update is too small to change it (results bit-identical).  Replaces BasePeriodicAlignment.refine
  * (periodicAlignment.py:27-80) / ITERATIVEALIGN(bulk) (alignutils.f90:111-286).
  * frac_idx [P,3] from fo_per_align_pairs; dist [P]; perm [P,N] (nullable): X2 = posB[perm] - disp;
  * disp [P,3] (nullable). */
@@ -329,6 +331,13 @@ int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets
                             const int32_t* atom_idx, const double* posA, const double* posB,
                             const double* frac_idx, int64_t npairs, int niter, int nthreads, double* dist,
                             int32_t* perm, double* disp);
+
+/* Work counters of fo_host_refine_periodic since load (summed over calls and threads), for tests and
+ * profiling: out[0] assignments solved by the double-precision matrix + LAP (per group), out[1] assignments
+ * settled by the single-precision screening (column minima proven to be the unique optimum), out[2] repeat
+ * solves of the permutation <-> displacement loop skipped because the displacement moved by less than half
+ * the stability margin of the last assignment.  reset != 0 zeroes them after reading. */
+void fo_host_refine_counters(int64_t out[3], int reset);
 
 /* Clusters: for each orientation o < norient rotate (o = 1: -posB) by the Euler angles
  * euler[P,norient,3], permute (LAP on squared distances per group), Kearsley quaternion fit; keep

@@ -165,11 +165,16 @@ def test_native_periodic_refine_matches_reference_and_python():
         assert abs(d - dist[i]) < 1e-9 and np.array_equal(pyperm, pm[i]) and np.allclose(pydisp, disp[i], atol=1e-9)
 
 
-def test_native_periodic_refine_hard_assignments():
-    """Large jitter (many rows left free by the column reduction, so the augmentation scans rows whose
-    square roots are taken lazily) and group sizes that are not multiples of the 8-column blocks of the
-    cost kernel: permutations identical to scipy's linear_sum_assignment on the min-image distance matrix,
-    distances to 1e-12."""
+@pytest.mark.parametrize("jitter", [0.35, 0.12, 0.04, 0.0])
+def test_native_periodic_refine_hard_assignments(jitter):
+    """Group sizes that are not multiples of the 8- / 16-column blocks of the cost kernels, at four noise
+    levels: large jitter (many rows left free by the column reduction, so the augmentation scans rows whose
+    square roots are taken lazily; the single-precision screening fails and the double-precision matrix +
+    LAP decides), intermediate (screening passes for some groups and solves, fails for others), small and
+    none (screening proves the column minima optimal and the second solve of the loop is skipped by the
+    stability margin; coordinates far outside the box).  Permutations identical to scipy's
+    linear_sum_assignment on the min-image distance matrix through the reference's full loop
+    (periodicAlignment.py:27-80), distances to 1e-12."""
     from scipy.optimize import linear_sum_assignment
     from fastoverlap_b200 import _lib
     rng = np.random.default_rng(11)
@@ -177,13 +182,25 @@ def test_native_periodic_refine_hard_assignments():
     groups = [np.arange(37), np.arange(37, 50), np.arange(50, 61)]
     P = 12
     A = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
+    if jitter < 0.1:
+        # spread lattice-like points so that partners are unambiguous, then push them out of the cell
+        A = (np.stack(np.unravel_index(rng.permutation(64)[:N], (4, 4, 4)), 1)[None] + 0.5 +
+             rng.uniform(-0.15, 0.15, size=(P, N, 3))) / 4 * box + rng.integers(-3, 4, size=(P, N, 3)) * box
     shift = rng.uniform(0, 1, size=(P, 1, 3)) * box
-    B = A + shift + rng.normal(scale=0.35, size=A.shape)
+    B = A + shift + rng.normal(scale=jitter, size=A.shape)
     for i in range(P):
         B[i] = B[i][np.concatenate([g[0] + rng.permutation(len(g)) for g in groups])]
     frac = shift[:, 0, :] / box * F
     pp = _lib.Context.per_params(N, box, 5, F, 0.3)
+    _lib.host_refine_counters(reset=True)
     dist, pm, disp = _lib.host_refine_periodic(pp, groups, A, B, frac, nthreads=2)
+    solved, screened, skipped = _lib.host_refine_counters()
+    if jitter >= 0.3:
+        assert screened < solved and skipped < P   # the LAP decides
+    elif jitter >= 0.1:
+        assert solved > 0 and screened > 0         # both paths
+    else:
+        assert (solved, screened, skipped) == (0, 3 * P, P)   # one screened pass per group, no second solve
 
     def mi(d):
         return d - np.rint(d / box) * box
