@@ -297,43 +297,61 @@ FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost
 // these three arrays with the rounding error of this pass as a tolerance, so that neither the double-
 // precision matrix nor the LAP is needed.  Coordinates must be wrapped into [-box/2, box/2] (error analysis
 // in best_perm).
-// Written with GCC vector extensions (one 16-float vector per statement; the AVX2 / default clones split
-// it): the scalar form of this update was compiled into mask tests and branches with the running minima
-// spilled to the stack.  rint(t) = (t + 1.5 * 2^23) - 1.5 * 2^23 for |t| < 2^22 in round-to-nearest.
-// ys is padded to a multiple of CBF columns per component (pitch npad), the padding repeating a real column.
+// Written with GCC vector extensions, one vector of the widest native type per statement (the scalar form of
+// this update was compiled into mask tests and branches with the running minima spilled to the stack; a
+// 64-byte vector type on a narrower ISA is scalarised), stamped out per ISA and picked once at run time.
+// rint(t) = (t + 1.5 * 2^23) - 1.5 * 2^23 for |t| < 2^22 in round-to-nearest.  ys is padded to a multiple
+// of CBF columns per component (pitch npad), the padding repeating a real column.
 constexpr int CBF = 16;
-typedef float vf16 __attribute__((vector_size(64)));
-typedef int vi16 __attribute__((vector_size(64)));
 
-FO_CLONES void colmin_periodic_f32(int n, int npad, const float* xs, const float* ys, const float* box, float* vmin,
-                                   int* imin, float* vmin2) {
-  const float b0 = box[0], b1 = box[1], b2 = box[2];
-  const float i0 = 1.0f / b0, i1 = 1.0f / b1, i2 = 1.0f / b2;
-  const float inf = std::numeric_limits<float>::infinity(), M = 12582912.0f;
-  for (int jb = 0; jb < npad; jb += CBF) {
-    vf16 y0, y1, y2;
-    memcpy(&y0, ys + jb, sizeof(vf16));
-    memcpy(&y1, ys + npad + jb, sizeof(vf16));
-    memcpy(&y2, ys + 2 * npad + jb, sizeof(vf16));
-    vf16 vm = y0 * 0.0f + inf, v2 = vm;
-    vi16 im = {0};
-    for (int i = 0; i < n; ++i) {
-      vf16 dx = xs[i] - y0, dy = xs[n + i] - y1, dz = xs[2 * n + i] - y2;
-      dx -= ((dx * i0 + M) - M) * b0;
-      dy -= ((dy * i1 + M) - M) * b1;
-      dz -= ((dz * i2 + M) - M) * b2;
-      const vf16 d = dx * dx + dy * dy + dz * dz;
-      const vi16 lt = d < vm;
-      const vf16 hi = lt ? vm : d;  // the larger of the entry and the running minimum
-      v2 = hi < v2 ? hi : v2;
-      vm = lt ? d : vm;
-      im = lt ? (vi16){0} + i : im;
-    }
-    memcpy(vmin + jb, &vm, sizeof(vf16));
-    memcpy(vmin2 + jb, &v2, sizeof(vf16));
-    memcpy(imin + jb, &im, sizeof(vi16));
+#define FO_COLMIN_F32(NAME, W, ATTR)                                                                          \
+  ATTR void NAME(int n, int npad, const float* xs, const float* ys, const float* box, float* vmin, int* imin,  \
+                 float* vmin2) {                                                                               \
+    typedef float vf __attribute__((vector_size(4 * W)));                                                      \
+    typedef int vi __attribute__((vector_size(4 * W)));                                                        \
+    const float b0 = box[0], b1 = box[1], b2 = box[2];                                                         \
+    const float i0 = 1.0f / b0, i1 = 1.0f / b1, i2 = 1.0f / b2;                                                \
+    const float inf = std::numeric_limits<float>::infinity(), M = 12582912.0f;                                 \
+    for (int jb = 0; jb < npad; jb += W) {                                                                     \
+      vf y0, y1, y2;                                                                                           \
+      memcpy(&y0, ys + jb, sizeof(vf));                                                                        \
+      memcpy(&y1, ys + npad + jb, sizeof(vf));                                                                 \
+      memcpy(&y2, ys + 2 * npad + jb, sizeof(vf));                                                             \
+      vf vm = y0 * 0.0f + inf, v2 = vm;                                                                        \
+      vi im = {0};                                                                                             \
+      for (int i = 0; i < n; ++i) {                                                                            \
+        vf dx = xs[i] - y0, dy = xs[n + i] - y1, dz = xs[2 * n + i] - y2;                                      \
+        dx -= ((dx * i0 + M) - M) * b0;                                                                        \
+        dy -= ((dy * i1 + M) - M) * b1;                                                                        \
+        dz -= ((dz * i2 + M) - M) * b2;                                                                        \
+        const vf d = dx * dx + dy * dy + dz * dz;                                                              \
+        const vi lt = d < vm;                                                                                  \
+        const vf hi = lt ? vm : d; /* the larger of the entry and the running minimum */                       \
+        v2 = hi < v2 ? hi : v2;                                                                                \
+        vm = lt ? d : vm;                                                                                      \
+        im = lt ? (vi){0} + i : im;                                                                            \
+      }                                                                                                        \
+      memcpy(vmin + jb, &vm, sizeof(vf));                                                                      \
+      memcpy(vmin2 + jb, &v2, sizeof(vf));                                                                     \
+      memcpy(imin + jb, &im, sizeof(vi));                                                                      \
+    }                                                                                                          \
   }
+
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(__CUDACC__)
+FO_COLMIN_F32(colmin_f32_avx512, 16, __attribute__((target("avx512f"))))
+FO_COLMIN_F32(colmin_f32_avx2, 8, __attribute__((target("avx2,fma"))))
+FO_COLMIN_F32(colmin_f32_base, 4, )
+typedef void (*colmin_f32_fn)(int, int, const float*, const float*, const float*, float*, int*, float*);
+colmin_f32_fn pick_colmin_f32() {
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f")) return colmin_f32_avx512;
+  if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma")) return colmin_f32_avx2;
+  return colmin_f32_base;
 }
+const colmin_f32_fn colmin_periodic_f32 = pick_colmin_f32();
+#else
+FO_COLMIN_F32(colmin_periodic_f32, 4, )
+#endif
 
 // Screening of one periodic group in single precision (colmin_periodic_f32).  Returns true, the assignment
 // (c4r[row] = column) and the updated stability margin when the column minima provably form the unique
