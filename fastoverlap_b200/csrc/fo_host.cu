@@ -143,8 +143,10 @@ struct Lap {
   }
 };
 
-// rint == nearbyint in the default rounding mode; it inlines to one roundsd (-msse4.1)
-inline double min_image(double d, double box) { return d - __builtin_rint(d / box) * box; }
+// rint == nearbyint in the default rounding mode; it inlines to one roundsd (-msse4.1).  d * (1 / box)
+// instead of d / box (a division costs ~4 cycles of throughput and the pair loop takes ~3800 minimum images)
+// can pick the other image only within rounding of exactly half a box, where both are equally near.
+inline double min_image(double d, double box, double ibox) { return d - __builtin_rint(d * ibox) * box; }
 
 struct Groups {
   const int32_t* goff;
@@ -606,6 +608,7 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
       const double* x = posA + (size_t)q * N * 3;
       const double* y = posB + (size_t)q * N * 3;
       double disp[3];
+      const double ibox[3] = {1.0 / p->box[0], 1.0 / p->box[1], 1.0 / p->box[2]};
       for (int k = 0; k < 3; ++k) disp[k] = frac_idx[3 * q + k] * p->box[k] / (double)p->nfspace;
       auto shift = [&]() {
         for (int i = 0; i < N; ++i)
@@ -614,7 +617,8 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
       auto recentre = [&](const int* pm) {
         double m[3] = {0, 0, 0};
         for (int i = 0; i < N; ++i)
-          for (int k = 0; k < 3; ++k) m[k] += min_image(x[3 * i + k] - (y[3 * pm[i] + k] - disp[k]), p->box[k]);
+          for (int k = 0; k < 3; ++k)
+            m[k] += min_image(x[3 * i + k] - (y[3 * pm[i] + k] - disp[k]), p->box[k], ibox[k]);
         for (int k = 0; k < 3; ++k) disp[k] -= m[k] / N;
       };
       shift();
@@ -643,9 +647,9 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
       for (int i = 0; i < N; ++i)
         for (int k = 0; k < 3; ++k) {
           // periodic(x) - periodic(y[perm] - disp), then the minimum image of the difference
-          const double a = min_image(x[3 * i + k], p->box[k]);
-          const double b = min_image(y[3 * perm[i] + k] - disp[k], p->box[k]);
-          const double d = min_image(a - b, p->box[k]);
+          const double a = min_image(x[3 * i + k], p->box[k], ibox[k]);
+          const double b = min_image(y[3 * perm[i] + k] - disp[k], p->box[k], ibox[k]);
+          const double d = min_image(a - b, p->box[k], ibox[k]);
           d2 += d * d;
         }
       dist[q] = sqrt(d2);
