@@ -30,9 +30,33 @@ namespace {
 long long g_counters[3] = {0, 0, 0};
 inline void count(int k) { __atomic_fetch_add(&g_counters[k], 1LL, __ATOMIC_RELAXED); }
 
+#if defined(__GNUC__) && !defined(__CUDACC__)
+#define FO_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define FO_CLONES
+#endif
+
+// One row scan of the shortest-augmenting-path search (Lap::solve): relaxes every column through row i and
+// returns the smallest tentative distance.  cd: tentative distances (+inf for closed columns), cl: 0 / +inf
+// for open / closed columns, pd: predecessor row (as a double, one lane type).
+FO_CLONES double lap_scan(int n, const double* ci, const double* v, const double* cl, double* cd, double* pd,
+                          double minVal, double ui, double di) {
+  double lowest = std::numeric_limits<double>::infinity();
+#pragma omp simd reduction(min : lowest)
+  for (int j = 0; j < n; ++j) {
+    const double r = minVal + ci[j] - ui - v[j] + cl[j];
+    const bool lt = r < cd[j];
+    const double c = lt ? r : cd[j];
+    cd[j] = c;
+    pd[j] = lt ? di : pd[j];
+    lowest = c < lowest ? c : lowest;
+  }
+  return lowest;
+}
+
 // Dense n x n linear assignment (minimise), cost row-major.  col4row[i] = column assigned to row i.
 struct Lap {
-  std::vector<double> u, v, shortest;
+  std::vector<double> u, v, shortest, cand, closed, pathd;
   std::vector<int> path, row4col, remaining, colmin;
   std::vector<char> SR, SC, rowdone;
   // colmin_in / vmin_in (optional): per-column minimum and its row, when the caller already has them.
@@ -91,41 +115,54 @@ struct Lap {
         }
       }
     }
+    // Shortest augmenting path per free row.  The scan of a row runs over ALL columns without branches or
+    // index indirection so that it vectorises: cand[j] is the tentative distance of an open column and +inf
+    // once the column is closed (then shortest[j] keeps its final distance for the dual update), closed[j] =
+    // +inf keeps a closed column from being reopened; the arithmetic of r is scipy's, term by term.
+    cand.resize(n);
+    closed.resize(n);
+    pathd.resize(n);
     for (int cur = 0; cur < n; ++cur) {
       if (col4row[cur] != -1) continue;
       std::fill(SR.begin(), SR.end(), 0);
       std::fill(SC.begin(), SC.end(), 0);
-      std::fill(shortest.begin(), shortest.end(), inf);
-      int nrem = n;
-      for (int it = 0; it < n; ++it) remaining[it] = n - it - 1;
+      double* cd = cand.data();
+      double* cl = closed.data();
+      double* pd = pathd.data();
+      const double* vv = v.data();
+      for (int j = 0; j < n; ++j) {
+        cd[j] = inf;
+        cl[j] = 0.0;
+      }
       int sink = -1, i = cur;
       double minVal = 0.0;
       while (sink == -1) {
-        int index = -1;
-        double lowest = inf;
         SR[i] = 1;
         const double* ci = row_of(i);
-        for (int it = 0; it < nrem; ++it) {
-          const int j = remaining[it];
-          const double r = minVal + ci[j] - u[i] - v[j];
-          if (r < shortest[j]) {
-            path[j] = i;
-            shortest[j] = r;
+        const double ui = u[i], di = (double)i;
+        const double lowest = lap_scan(n, ci, vv, cl, cd, pd, minVal, ui, di);
+        if (lowest == inf) return;  // infeasible (NaN costs): leave -1s
+        int index = -1;
+        for (int j = 0; j < n; ++j)
+          if (cd[j] == lowest) {  // ties: an unassigned column first
+            if (row4col[j] == -1) {
+              index = j;
+              break;
+            }
+            if (index < 0) index = j;
           }
-          if (shortest[j] < lowest || (shortest[j] == lowest && row4col[j] == -1)) {
-            lowest = shortest[j];
-            index = it;
-          }
-        }
+        if (index < 0) return;  // NaN
         minVal = lowest;
-        if (index < 0 || minVal == inf) return;  // infeasible (NaN costs): leave -1s
-        const int j = remaining[index];
+        const int j = index;
+        shortest[j] = lowest;
+        path[j] = (int)pd[j];
+        cd[j] = inf;
+        cl[j] = inf;
+        SC[j] = 1;
         if (row4col[j] == -1)
           sink = j;
         else
           i = row4col[j];
-        SC[j] = 1;
-        remaining[index] = remaining[--nrem];
       }
       u[cur] += minVal;
       for (int r = 0; r < n; ++r)
@@ -158,11 +195,6 @@ struct Groups {
 // branch-free so that gcc vectorises them (function multiversioning picks the AVX2 clone at run time).
 // d * (1/box) instead of d / box can move the rounding only at exact half-box separations, where both
 // images give the same distance.
-#if defined(__GNUC__) && !defined(__CUDACC__)
-#define FO_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
-#else
-#define FO_CLONES
-#endif
 
 // vmin / imin: running minimum of every column and its row (the column reduction of the LAP), kept in
 // the same pass that writes the matrix.  Both kernels write SQUARED distances; the periodic LAP is on the
