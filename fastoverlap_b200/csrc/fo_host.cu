@@ -507,10 +507,14 @@ double best_perm(const Groups& G, int natoms, const double* X, const double* Y, 
 void jacobi4(double A[4][4], double& eigmin, double q[4]) {
   double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
   for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0;
-    for (int p = 0; p < 4; ++p)
+    double off = 0, diag = 0;
+    for (int p = 0; p < 4; ++p) {
+      diag += A[p][p] * A[p][p];
       for (int r = p + 1; r < 4; ++r) off += A[p][r] * A[p][r];
-    if (off < 1e-300) break;
+    }
+    // off-diagonal norm below 1e-18 of the diagonal's: a further sweep cannot change a double (the former
+    // absolute 1e-300 ran four more sweeps after that point, the last ones on denormals)
+    if (off <= 1e-36 * diag) break;
     for (int p = 0; p < 4; ++p)
       for (int r = p + 1; r < 4; ++r) {
         if (fabs(A[p][r]) < 1e-300) continue;
