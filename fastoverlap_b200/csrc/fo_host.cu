@@ -335,12 +335,13 @@ FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost
 // this update was compiled into mask tests and branches with the running minima spilled to the stack; a
 // 64-byte vector type on a narrower ISA is scalarised), stamped out per ISA and picked once at run time.
 // rint(t) = (t + 1.5 * 2^23) - 1.5 * 2^23 for |t| < 2^22 in round-to-nearest.  ys is padded to a multiple
-// of CBF columns per component (pitch npad), the padding repeating a real column.
+// of CBF columns per component (pitch npad), the padding repeating a real column.  Every block of CBF columns
+// visits two runs of rows only (runs: 4 ints per block), see screen_periodic.
 constexpr int CBF = 16;
 
 #define FO_COLMIN_F32(NAME, W, ATTR)                                                                          \
-  ATTR void NAME(int n, int npad, const float* xs, const float* ys, const float* box, float* vmin, int* imin,  \
-                 float* vmin2) {                                                                               \
+  ATTR void NAME(int n, int npad, const float* xs, const float* ys, const float* box, const int* runs,         \
+                 float* vmin, int* imin, float* vmin2) {                                                       \
     typedef float vf __attribute__((vector_size(4 * W)));                                                      \
     typedef int vi __attribute__((vector_size(4 * W)));                                                        \
     const float b0 = box[0], b1 = box[1], b2 = box[2];                                                         \
@@ -353,7 +354,12 @@ constexpr int CBF = 16;
       memcpy(&y2, ys + 2 * npad + jb, sizeof(vf));                                                             \
       vf vm = y0 * 0.0f + inf, v2 = vm;                                                                        \
       vi im = {0};                                                                                             \
-      for (int i = 0; i < n; ++i) {                                                                            \
+      const int* rn = runs + 4 * (jb / CBF); /* rows [rn[0], rn[1]) and [rn[2], rn[3]) */                      \
+      for (int i = rn[0]; i < rn[3]; ++i) {                                                                    \
+        if (i == rn[1]) {                                                                                      \
+          i = rn[2];                                                                                           \
+          if (i >= rn[3]) break;                                                                               \
+        }                                                                                                      \
         vf dx = xs[i] - y0, dy = xs[n + i] - y1, dz = xs[2 * n + i] - y2;                                      \
         dx -= ((dx * i0 + M) - M) * b0;                                                                        \
         dy -= ((dy * i1 + M) - M) * b1;                                                                        \
@@ -375,7 +381,8 @@ constexpr int CBF = 16;
 FO_COLMIN_F32(colmin_f32_avx512, 16, __attribute__((target("avx512f"))))
 FO_COLMIN_F32(colmin_f32_avx2, 8, __attribute__((target("avx2,fma"))))
 FO_COLMIN_F32(colmin_f32_base, 4, )
-typedef void (*colmin_f32_fn)(int, int, const float*, const float*, const float*, float*, int*, float*);
+typedef void (*colmin_f32_fn)(int, int, const float*, const float*, const float*, const int*, float*, int*,
+                              float*);
 colmin_f32_fn pick_colmin_f32() {
   __builtin_cpu_init();
   if (__builtin_cpu_supports("avx512f")) return colmin_f32_avx512;
@@ -399,38 +406,125 @@ FO_COLMIN_F32(colmin_periodic_f32, 4, )
 bool screen_periodic(int n, const double* xs, const double* ys, const double* box, int* imin, int* c4r,
                      double* margin) {
   static thread_local std::vector<float> f;
-  static thread_local std::vector<int> im;
+  static thread_local std::vector<int> iw;
   static thread_local std::vector<char> seen;
-  const int npad = (n + CBF - 1) / CBF * CBF;
-  if (f.size() < (size_t)3 * n + 5 * npad) {
-    f.resize((size_t)3 * n + 5 * npad);
-    im.resize(npad);
+  const int npad = (n + CBF - 1) / CBF * CBF, nblk = npad / CBF;
+  constexpr int SMAX = 64;
+  if (f.size() < (size_t)3 * n + 5 * npad + 2 * n) {
+    f.resize((size_t)3 * n + 5 * npad + 2 * n);
+    iw.resize((size_t)npad + 4 * n + 4 * nblk + 2 * (SMAX + 1));
   }
   float* xf = f.data();
   float* yf = xf + 3 * n;
   float* v1 = yf + 3 * npad;
   float* v2 = v1 + npad;
+  float* wx = v2 + npad;  // wrapped coordinate along the slab axis, rows / columns
+  float* wy = wx + n;
+  int* im = iw.data();
+  int* xord = im + npad;  // sorted position -> row / column of the group
+  int* yord = xord + n;
+  int* sx = yord + n;     // slab of every row / column
+  int* sy = sx + n;
+  int* runs = sy + n;
+  int* xstart = runs + 4 * nblk;  // first sorted row of every slab
+  int* ystart = xstart + SMAX + 1;
   const float boxf[3] = {(float)box[0], (float)box[1], (float)box[2]};
+  const double bmax = std::max(box[0], std::max(box[1], box[2]));
+  const double tol = 1e-5 * bmax;
+  // Slabs along the longest axis.  A column only needs the rows within c = half the mean spacing of the group:
+  // a partner further away than that is not an unambiguous nearest neighbour anyway.  Rows and columns are
+  // bucket-sorted by slab; the 16 columns of a block span slabs sa..sb, and rows outside sa-k..sb+k (cyclic)
+  // are at least ceff = k w - tol away from all of them (w: slab width), so they are skipped and the second
+  // minimum is capped at ceff: the gap test below stays a proof.
+  const int ax = box[0] >= box[1] ? (box[0] >= box[2] ? 0 : 2) : (box[1] >= box[2] ? 1 : 2);
+  const double c = 0.5 * cbrt(box[0] * box[1] * box[2] / n);
+  int S = (int)(box[ax] / (c / 3.0));
+  S = S > SMAX ? SMAX : S;
+  int kk = 0;
+  double ceff2 = std::numeric_limits<double>::infinity();
+  if (S >= 8) {
+    const double w = box[ax] / S;
+    kk = (int)ceil((c + tol) / w);
+    const double ceff = kk * w - tol;
+    ceff2 = ceff * ceff;
+  }
+  const bool slabs = S >= 8 && 2 * kk + 2 < S;
+  {
+    const double b = box[ax], ib = 1.0 / b;
+    for (int i = 0; i < n; ++i) {
+      const double x = xs[ax * n + i], y = ys[ax * n + i];
+      wx[i] = (float)(x - __builtin_rint(x * ib) * b);
+      wy[i] = (float)(y - __builtin_rint(y * ib) * b);
+    }
+  }
+  if (slabs) {
+    const float fs = (float)S, ibf = 1.0f / boxf[ax];
+    for (int s = 0; s <= S; ++s) xstart[s] = ystart[s] = 0;
+    for (int i = 0; i < n; ++i) {
+      int a = (int)((wx[i] * ibf + 0.5f) * fs), b = (int)((wy[i] * ibf + 0.5f) * fs);
+      a = a < 0 ? 0 : (a >= S ? S - 1 : a);
+      b = b < 0 ? 0 : (b >= S ? S - 1 : b);
+      sx[i] = a;
+      sy[i] = b;
+      ++xstart[a + 1];
+      ++ystart[b + 1];
+    }
+    for (int s = 0; s < S; ++s) {
+      xstart[s + 1] += xstart[s];
+      ystart[s + 1] += ystart[s];
+    }
+    // counting sort; xstart / ystart are advanced while placing and restored afterwards
+    for (int i = 0; i < n; ++i) {
+      xord[xstart[sx[i]]++] = i;
+      yord[ystart[sy[i]]++] = i;
+    }
+    for (int s = S; s > 0; --s) xstart[s] = xstart[s - 1];
+    xstart[0] = 0;
+    for (int b = 0; b < nblk; ++b) {
+      const int jl = std::min(b * CBF + CBF - 1, n - 1);
+      const int sa = sy[yord[b * CBF]], sb = sy[yord[jl]];
+      int* rn = runs + 4 * b;
+      const int lo = sa - kk, hi = sb + kk;
+      if (hi - lo + 1 >= S) {
+        rn[0] = 0; rn[1] = n; rn[2] = n; rn[3] = n;
+      } else if (lo < 0) {
+        rn[0] = 0; rn[1] = xstart[hi + 1]; rn[2] = xstart[lo + S]; rn[3] = n;
+      } else if (hi >= S) {
+        rn[0] = 0; rn[1] = xstart[hi - S + 1]; rn[2] = xstart[lo]; rn[3] = n;
+      } else {
+        rn[0] = xstart[lo]; rn[1] = xstart[hi + 1]; rn[2] = n; rn[3] = n;
+      }
+    }
+  } else {
+    for (int i = 0; i < n; ++i) xord[i] = yord[i] = i;
+    for (int b = 0; b < nblk; ++b) {
+      int* rn = runs + 4 * b;
+      rn[0] = 0; rn[1] = n; rn[2] = n; rn[3] = n;
+    }
+    ceff2 = std::numeric_limits<double>::infinity();
+  }
   for (int k = 0; k < 3; ++k) {
     const double b = box[k], ib = 1.0 / b;
     for (int i = 0; i < n; ++i) {
-      const double x = xs[k * n + i], y = ys[k * n + i];
+      const double x = xs[k * n + xord[i]], y = ys[k * n + yord[i]];
       xf[k * n + i] = (float)(x - __builtin_rint(x * ib) * b);
       yf[k * npad + i] = (float)(y - __builtin_rint(y * ib) * b);
     }
     for (int i = n; i < npad; ++i) yf[k * npad + i] = yf[k * npad + n - 1];
   }
-  colmin_periodic_f32(n, npad, xf, yf, boxf, v1, im.data(), v2);
-  for (int j = 0; j < n; ++j) imin[j] = im[j];
-  const double tol2 = 2e-5 * std::max(box[0], std::max(box[1], box[2]));
+  colmin_periodic_f32(n, npad, xf, yf, boxf, runs, v1, im, v2);
+  const double tol2 = 2.0 * tol;
   seen.assign(n, 0);
   double gap = std::numeric_limits<double>::infinity();
   for (int j = 0; j < n; ++j) {
-    const double g = __builtin_sqrt((double)v2[j]) - __builtin_sqrt((double)v1[j]) - tol2;
-    if (!(g > 0) || seen[imin[j]]) return false;  // also catches NaN coordinates
-    seen[imin[j]] = 1;
+    const double second = std::min((double)v2[j], ceff2);
+    const double g = __builtin_sqrt(second) - __builtin_sqrt((double)v1[j]) - tol2;
+    const int row = im[j];
+    if (!(g > 0) || row < 0 || row >= n || seen[row]) return false;  // also catches NaN coordinates, empty runs
+    seen[row] = 1;
     gap = std::min(gap, g);
-    c4r[imin[j]] = j;
+    imin[yord[j]] = xord[row];
+    c4r[xord[row]] = yord[j];
   }
   *margin = std::min(*margin, gap);
   return true;

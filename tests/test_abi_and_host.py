@@ -229,6 +229,73 @@ def test_native_periodic_refine_hard_assignments(jitter):
         assert abs(ref - dist[q]) < 1e-12
 
 
+def test_native_periodic_refine_randomized():
+    """Random sizes, boxes (cubic and not), 1-3 groups, four kinds of structures (uniform, a blob far outside
+    the cell, lattice-like, a thin sheet across the slab axis of the screening) and five noise levels, so that
+    every path of fo_host_refine_periodic (slab-pruned single-precision screening, skipped confirming solve,
+    double-precision LAP) meets awkward inputs: permutations identical to scipy's through the reference's
+    loop (periodicAlignment.py:27-80)."""
+    from scipy.optimize import linear_sum_assignment
+    from fastoverlap_b200 import _lib
+    rng = np.random.default_rng(5)
+    tot = np.zeros(3, int)
+    for trial in range(40):
+        N = int(rng.integers(8, 260))
+        box = rng.uniform(3.0, 9.0, 3) if trial % 3 else np.full(3, rng.uniform(3, 9))
+        ng = int(rng.integers(1, 4))
+        cuts = np.sort(rng.choice(np.arange(1, N), ng - 1, replace=False)) if ng > 1 else []
+        groups = np.split(np.arange(N), cuts)
+        P, F, mode = 3, 24, trial % 4
+        if mode == 0:
+            A = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
+        elif mode == 1:
+            A = rng.normal(scale=0.15, size=(P, N, 3)) * box + 7 * box
+        elif mode == 2:
+            m = int(np.ceil(N ** (1 / 3)))
+            A = (np.stack(np.unravel_index(rng.permutation(m ** 3)[:N], (m, m, m)), 1)[None] + 0.5 +
+                 rng.uniform(-0.2, 0.2, size=(P, N, 3))) / m * box
+        else:
+            A = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
+            A[:, :, np.argmax(box)] *= 0.05
+        jitter = [0.0, 0.01, 0.05, 0.1, 0.2][trial % 5] * (np.prod(box) / N) ** (1 / 3)
+        shift = rng.uniform(0, 1, size=(P, 1, 3)) * box
+        B = A + shift + rng.normal(scale=jitter, size=A.shape)
+        for i in range(P):
+            B[i] = B[i][np.concatenate([g[0] + rng.permutation(len(g)) for g in groups])]
+        frac = shift[:, 0, :] / box * F + rng.normal(scale=0.02, size=(P, 3))
+        pp = _lib.Context.per_params(N, box, 5, F, 0.3)
+        _lib.host_refine_counters(reset=True)
+        dist, pm, disp = _lib.host_refine_periodic(pp, groups, A, B, frac, nthreads=2)
+        tot += np.array(_lib.host_refine_counters())
+
+        def mi(d):
+            return d - np.rint(d / box) * box
+
+        def bestperm(x, y):
+            perm = np.arange(N)
+            for g in groups:
+                c = np.linalg.norm(mi(x[g][:, None, :] - y[g][None, :, :]), axis=2)
+                r, cc = linear_sum_assignment(c)
+                perm[g[r]] = g[cc]
+            return perm
+
+        for q in range(P):
+            x, y, d = A[q], B[q], frac[q] * box / F
+            save = bestperm(x, y - d)
+            perm = save
+            for _ in range(10):
+                d = d - mi(x - (y[save] - d)).mean(0)
+                perm = bestperm(x, y - d)
+                if np.array_equal(perm, save):
+                    break
+                save = perm
+            d = d - mi(x - (y[perm] - d)).mean(0)
+            ref = np.sqrt((mi(mi(x) - mi(y[perm] - d)) ** 2).sum())
+            assert np.array_equal(perm, pm[q]), (trial, q, N, mode, jitter)
+            assert abs(ref - dist[q]) < 1e-10 * max(1.0, ref)
+    assert (tot > 20).all(), tot   # all three paths took part
+
+
 def test_native_spherical_refine_matches_reference_and_python():
     from fastoverlap_b200 import _lib
     from fastoverlap_b200.spherical import SphericalAlign
