@@ -296,6 +296,57 @@ def test_native_periodic_refine_randomized():
     assert (tot > 20).all(), tot   # all three paths took part
 
 
+class _StubCtx(object):
+    """Stands in for the GPU context in the pipeline test: the displacement of a translated, permuted copy is
+    the difference of the centroids."""
+
+    def __init__(self, box, F, fail_at=None):
+        self.box, self.F, self.fail_at, self.calls, self.active = box, F, fail_at, [], 0
+
+    def set_perm(self, perm, natoms):
+        pass
+
+    def per_align_pairs(self, p, pos1, pos2):
+        import threading
+        import time
+        self.active += 1
+        assert self.active == 1   # a context is not re-entrant
+        time.sleep(0.002)
+        self.calls.append((threading.current_thread().name, len(pos1)))
+        if self.fail_at is not None and len(self.calls) > self.fail_at:
+            self.active -= 1
+            raise RuntimeError("device stage failed")
+        fr = (pos2.mean(1) - pos1.mean(1)) / self.box * self.F
+        self.active -= 1
+        return None, None, fr, None, None
+
+
+def test_align_batch_overlaps_device_and_host_stages():
+    """PeriodicAlign.align_batch in chunks (batch.overlap_chunks: device stage on a worker thread, host pool
+    on the caller's): same results as in one piece, ragged last chunk, device-stage errors re-raised."""
+    from fastoverlap_b200.periodic import PeriodicAlign
+    rng = np.random.default_rng(3)
+    N, box, P = 40, np.array([4.0, 4.4, 4.8]), 300
+    groups = [np.arange(25), np.arange(25, 40)]
+    A = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
+    B = A + rng.uniform(0, 1, size=(P, 1, 3)) * box + rng.normal(scale=0.03, size=A.shape)
+    for i in range(P):
+        B[i] = B[i][np.concatenate([g[0] + rng.permutation(len(g)) for g in groups])]
+    al = PeriodicAlign(N, box, groups, n=4, ctx=_StubCtx(box, 24))
+    al.fshape = (24, 24, 24)
+    d0, s0, p0 = al.align_batch(A, B, chunk=0, nthreads=2)
+    assert al.ctx.calls == [("MainThread", P)]
+    al._ctx = _StubCtx(box, 24)
+    d1, s1, p1 = al.align_batch(A, B, chunk=64, nthreads=2)
+    assert [c[1] for c in al.ctx.calls] == [64, 64, 64, 64, 44]
+    assert all(c[0] == "fastoverlap-device-stage" for c in al.ctx.calls)
+    assert np.array_equal(d0, d1) and np.array_equal(s0, s1) and np.array_equal(p0, p1)
+    assert np.median(d0) < 0.03 * np.sqrt(3 * N) * 1.5
+    al._ctx = _StubCtx(box, 24, fail_at=2)
+    with pytest.raises(RuntimeError, match="device stage failed"):
+        al.align_batch(A, B, chunk=64, nthreads=2)
+
+
 def test_native_spherical_refine_matches_reference_and_python():
     from fastoverlap_b200 import _lib
     from fastoverlap_b200.spherical import SphericalAlign
