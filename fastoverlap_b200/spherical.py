@@ -242,15 +242,37 @@ class BaseSphericalAlignment(object):
         return dist, X1, X2
 
     # -- batched, additive API
-    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True, nthreads=0):
-        """P independent pairs: one GPU call for the whole batch, then the native host refinement
+    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True, nthreads=0, chunk=None):
+        """P independent pairs: GPU hot path for the batch, then the native host refinement
         pool (fo_host_refine_spherical: rotate, LAP, Kearsley, best orientation by distance).
+        With the distance rule, batches of at least 2048 pairs go through in chunks (default 1024 pairs;
+        chunk=0: one piece), the host pool refining one chunk while the GPU works on the next
+        (batch.overlap_chunks); per-pair results do not depend on the chunking.
         Returns dists (P,) and the Euler angles (P, O, 3)."""
         pos1 = np.asarray(pos1, float)
         pos2 = np.asarray(pos2, float)
         X1 = pos1 - pos1.mean(1, keepdims=True)
         X2 = pos2 - pos2.mean(1, keepdims=True)
         perm = self._perm(X1.shape[1], perm)
+        P = len(X1)
+        if chunk is None:
+            chunk = 1024 if P >= 2048 else 0
+        if refine and self.orientation != "overlap" and 0 < chunk < P:
+            from .batch import overlap_chunks
+            dists = np.empty(P)
+            out = {}
+
+            def device_step(a, b):
+                return self._grid_search(X1[a:b], X2[a:b], perm, invert).reshape(b - a, -1, 3)
+
+            def host_step(a, b, Rs):
+                if "Rs" not in out:
+                    out["Rs"] = np.empty((P,) + Rs.shape[1:])
+                out["Rs"][a:b] = Rs
+                dists[a:b] = _lib.host_refine_spherical(X1[a:b], X2[a:b], Rs, perm, nthreads)[0]
+
+            overlap_chunks([(a, min(a + chunk, P)) for a in range(0, P, chunk)], device_step, host_step)
+            return dists, out["Rs"]
         if self.orientation == "overlap":
             # numpy rule (:178-187): the orientation with the larger refined overlap is the only one
             # that goes through the host LAP + Kearsley refinement

@@ -347,6 +347,40 @@ def test_align_batch_overlaps_device_and_host_stages():
         al.align_batch(A, B, chunk=64, nthreads=2)
 
 
+def test_spherical_align_batch_chunks_match_one_piece():
+    """SphericalAlign.align_batch through batch.overlap_chunks (device stage stubbed with the known Euler
+    angles): distances and angles identical to the one-piece call, ragged last chunk."""
+    from fastoverlap_b200.spherical import SphericalAlign
+    from fastoverlap_b200.utils import EulerM
+    g = golden("spherical_lj38.npz")
+    X = g["pos1"] - g["pos1"].mean(0)
+    N, P = len(X), 200
+    rng = np.random.default_rng(3)
+    A = np.repeat(X[None], P, 0) + rng.normal(scale=0.05, size=(P, N, 3))
+    A -= A.mean(1, keepdims=True)
+    eul, B = np.zeros((P, 2, 3)), np.empty_like(A)
+    for q in range(P):
+        a, b, c = rng.uniform(0, 6), rng.uniform(0.2, 2.9), rng.uniform(0, 6)
+        B[q] = (X @ EulerM(a, b, c).T)[rng.permutation(N)]
+        eul[q, 0] = (a, b, c)
+        eul[q, 1] = rng.uniform(0, 3, 3)
+    sa = SphericalAlign.__new__(SphericalAlign)
+    sa.orientation, sa.perm, sa.Jmax, sa.scale = "distance", None, 15, 0.3
+    calls = []
+
+    def grid_search(X1, X2, perm, invert, want_grid=False, calcCoeffs=None):
+        i = int(np.argmin(np.abs(A - X1[0]).sum((1, 2))))
+        calls.append((i, len(X1)))
+        return eul[i:i + len(X1)]
+
+    sa._grid_search = grid_search
+    d0, R0 = sa.align_batch(A, B, chunk=0, nthreads=2)
+    d1, R1 = sa.align_batch(A, B, chunk=64, nthreads=2)
+    assert calls == [(0, 200), (0, 64), (64, 64), (128, 64), (192, 8)]
+    assert np.array_equal(d0, d1) and np.array_equal(R0, R1)
+    assert abs(np.median(d0) - 0.05 * np.sqrt(3 * N)) < 0.05
+
+
 def test_native_spherical_refine_matches_reference_and_python():
     from fastoverlap_b200 import _lib
     from fastoverlap_b200.spherical import SphericalAlign
