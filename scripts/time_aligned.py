@@ -27,3 +27,13 @@ for name in ("lj38", "blj256"):
         t2 = time.perf_counter()
         print(name, "rep", rep, "gpu+wrapper %.1f ms  host refine %.1f ms  -> %.0f pairs/s (threads %d)" % (
             (t1 - t0) * 1e3, (t2 - t1) * 1e3, 4096 / (t2 - t0), nthr), flush=True)
+    # the public batched call, in one piece and with the chunk pipeline (batch.overlap_chunks)
+    al = wl.sa if name == "lj38" else wl.al
+    for chunk in (0, 512, 1024, 2048):
+        best = 1e9
+        for rep in range(4):
+            t0 = time.perf_counter()
+            d = al.align_batch(A, B, nthreads=nthr, chunk=chunk)[0]
+            best = min(best, time.perf_counter() - t0)
+        print(name, "align_batch chunk %4d: %.1f ms -> %.0f pairs/s (median distance %.4f)" % (
+            chunk, best * 1e3, 4096 / best, float(np.median(d))), flush=True)
