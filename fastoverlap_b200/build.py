@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
             if os.path.basename(src) in HOST_ONLY:
                 # no device code: compiled by g++ directly (function multiversioning, OpenMP SIMD)
                 cmd = [shutil.which("g++") or "g++", "-x", "c++", "-std=c++17", "-O3", "-fPIC", "-fopenmp",
-                       "-msse4.1", "-Wno-psabi", "-I", os.path.join(os.path.dirname(nvcc), "..", "include"), "-c", src, "-o", obj]
+                       "-msse4.1", "-fno-math-errno", "-Wno-psabi", "-I", os.path.join(os.path.dirname(nvcc), "..", "include"), "-c", src, "-o", obj]
             else:
                 cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
             if verbose:
