@@ -121,6 +121,26 @@ SIGNATURES = {
     "fo_host_refine_periodic": (ctypes.c_int, [ctypes.POINTER(PerParams), c_void_p, ctypes.c_int64, c_void_p,
                                                c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int,
                                                ctypes.c_int, c_void_p, c_void_p, c_void_p]),
+    "fo_host_refine_periodic_subset": (ctypes.c_int, [ctypes.POINTER(PerParams), c_void_p, ctypes.c_int64, c_void_p,
+                                                      c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64,
+                                                      ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
+    "fo_host_refine_spherical_hint": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                                     ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int, c_void_p,
+                                                     c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p,
+                                                     c_void_p]),
+    "fo_per_align_pairs_full": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
+                                               ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_i64p]),
+    "fo_sph_align_pairs_full": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                               ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_i64p]),
+    "fo_per_align_pairs_full_dev": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
+                                                   ctypes.c_int64, ctypes.c_int, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fo_sph_align_pairs_screen_dev": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                     ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_void_p,
+                                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fo_host_refine_counters": (None, [c_void_p, ctypes.c_int]),
     "fo_host_refine_spherical": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
                                                 ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
@@ -279,15 +299,16 @@ class Context(object):
     def reset_stream(self):
         self._check(self._lib.fo_reset_stream(self._h), "fo_reset_stream")
 
-    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "peaks", "sph_refine")
+    PROF_KINDS = ("per_sf", "per_xf", "sph_coef", "sph_harm", "sph_dot", "sph_isoft", "peaks", "sph_refine",
+                  "assign")
 
     def profile_begin(self):
         self._check(self._lib.fo_profile_begin(self._h), "fo_profile_begin")
 
     def profile_end(self):
         """-> {kernel class: (total ms, launches)} measured with CUDA events on the ctx stream."""
-        ms = np.zeros(8, np.float64)
-        cnt = np.zeros(8, np.int64)
+        ms = np.zeros(len(self.PROF_KINDS), np.float64)
+        cnt = np.zeros(len(self.PROF_KINDS), np.int64)
         self._check(self._lib.fo_profile_end(self._h, ms.ctypes.data_as(c_f64p),
                                              cnt.ctypes.data_as(c_i64p)), "fo_profile_end")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROF_KINDS) if cnt[i]}
@@ -382,12 +403,45 @@ class Context(object):
     def per_align_pairs_dev(self, params, d_posA, d_posB, P, d_best_idx, d_best_val, d_frac,
                             d_grid=0, d_status=0):
         """All arguments are raw device addresses (ints); asynchronous on the ctx stream."""
+        self._ensure_perm(params.natoms)
         self._check(self._lib.fo_per_align_pairs_dev(
             self._h, ctypes.byref(params), c_void_p(d_posA), c_void_p(d_posB), int(P),
             c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac), c_void_p(d_grid or 0),
             c_void_p(d_status or 0)), "fo_per_align_pairs_dev")
 
+    def per_align_pairs_full_dev(self, params, d_posA, d_posB, P, d_dist, d_perm, d_disp, d_flag, d_best_idx,
+                                 d_best_val, d_frac, niter=10, d_status=0):
+        """Raw device addresses; hot path + screening / displacement loop on the device, asynchronous."""
+        self._ensure_perm(params.natoms)
+        self._check(self._lib.fo_per_align_pairs_full_dev(
+            self._h, ctypes.byref(params), c_void_p(d_posA), c_void_p(d_posB), int(P), int(niter), c_void_p(d_dist),
+            c_void_p(d_perm or 0), c_void_p(d_disp), c_void_p(d_flag), c_void_p(d_best_idx), c_void_p(d_best_val),
+            c_void_p(d_frac), c_void_p(d_status or 0)), "fo_per_align_pairs_full_dev")
+
+    def per_align_pairs_full(self, params, posA, posB, niter=10, nthreads=0, want_perm=True):
+        """Hot path + device screening of the assignment + host LAP pool for the flagged pairs
+        (fo_per_align_pairs_full).  Returns (dist (P,), perm (P,N)|None, disp (P,3), frac_idx (P,3),
+        status (P,), nhost)."""
+        self._ensure_perm(params.natoms)
+        posA = _f64(posA).reshape(-1, params.natoms, 3)
+        posB = _f64(posB).reshape(-1, params.natoms, 3)
+        if posA.shape != posB.shape:
+            raise ValueError("posA and posB must have the same shape")
+        P = posA.shape[0]
+        dist = np.empty(P)
+        perm = np.empty((P, params.natoms), np.int32) if want_perm else None
+        disp = np.empty((P, 3))
+        frac = np.empty((P, 3))
+        st = np.zeros(P, np.int32)
+        nhost = ctypes.c_int64(0)
+        self._check(self._lib.fo_per_align_pairs_full(self._h, ctypes.byref(params), _ptr(posA), _ptr(posB), P,
+                                                      int(niter), int(nthreads), _ptr(dist), _ptr(perm),
+                                                      _ptr(disp), _ptr(frac), _ptr(st), ctypes.byref(nhost)),
+                    "fo_per_align_pairs_full")
+        return dist, perm, disp, frac, st, int(nhost.value)
+
     def per_align_coeffs(self, params, CA, CB, want_grid=False):
+        self._ensure_perm(params.natoms)
         W = 2 * params.nwave + 1
         CA = np.ascontiguousarray(CA, dtype=np.complex128)
         CB = np.ascontiguousarray(CB, dtype=np.complex128)
@@ -547,6 +601,39 @@ class Context(object):
                                                  _ptr(fr), _ptr(grid), _ptr(st)),
                     "fo_sph_align_pairs")
         return bi, bv, fr, grid, st
+
+    def sph_align_pairs_screen_dev(self, d_posA, d_posB, P, N, Jmax, sigma, invert, d_best_idx, d_best_val,
+                                   d_frac, d_perm, d_ok, d_status=0):
+        self._ensure_perm(N)
+        self._check(self._lib.fo_sph_align_pairs_screen_dev(
+            self._h, c_void_p(d_posA), c_void_p(d_posB), int(P), int(N), int(Jmax), float(sigma),
+            int(bool(invert)), c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac), c_void_p(d_perm),
+            c_void_p(d_ok), c_void_p(d_status or 0)), "fo_sph_align_pairs_screen_dev")
+
+    def sph_align_pairs_full(self, posA, posB, Jmax, sigma, invert=True, nthreads=0, want_perm=True):
+        """Hot path + device screening of the assignment + host pool (LAP where needed, Kearsley)
+        (fo_sph_align_pairs_full).  Structures must be centred.  Returns (dist (P,), orient (P,),
+        perm (P,N)|None, rmat (P,3,3), euler (P,O,3), status (P,), nhost)."""
+        posA = _f64(posA)
+        posB = _f64(posB)
+        if posA.ndim == 2:
+            posA = posA[None]
+            posB = posB[None]
+        P, N, _ = posA.shape
+        self._ensure_perm(N)
+        O = 2 if invert else 1
+        dist = np.empty(P)
+        orient = np.empty(P, np.int32)
+        perm = np.empty((P, N), np.int32) if want_perm else None
+        rmat = np.empty((P, 3, 3))
+        euler = np.empty((P, O, 3))
+        st = np.zeros(P, np.int32)
+        nhost = ctypes.c_int64(0)
+        self._check(self._lib.fo_sph_align_pairs_full(self._h, _ptr(posA), _ptr(posB), P, N, int(Jmax), float(sigma),
+                                                      int(bool(invert)), int(nthreads), _ptr(dist), _ptr(orient),
+                                                      _ptr(perm), _ptr(rmat), _ptr(euler), _ptr(st),
+                                                      ctypes.byref(nhost)), "fo_sph_align_pairs_full")
+        return dist, orient, perm, rmat, euler, st, int(nhost.value)
 
     def sph_refine_rotations(self, Ilmm, Jmax, euler):
         """maxOverlap on the device: (euler_out (P,3), overlap (P,), nevals (P,))."""

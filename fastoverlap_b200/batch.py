@@ -63,36 +63,3 @@ class MultiGPU(object):
         if err:
             raise err[0]
         return tuple(np.concatenate([o[i] for o in out]) for i in range(len(out[0])))
-
-
-def overlap_chunks(bounds, device_step, host_step):
-    """Two-stage pipeline over chunks of a batch: device_step(a, b) -- the GPU hot path of pairs a..b, a
-    ctypes call that releases the GIL -- runs on a worker thread, ahead of host_step(a, b, result) -- the
-    native host refinement pool -- on the caller's thread, so that the host refines chunk k while the GPU
-    works on chunk k + 1.  Only the worker touches the context while the pipeline runs (a context is not
-    re-entrant).  Exceptions of either stage are re-raised on the caller's thread."""
-    import queue
-    q = queue.Queue()
-    stop = threading.Event()
-
-    def work():
-        try:
-            for a, b in bounds:
-                if stop.is_set():
-                    break
-                q.put((a, b, device_step(a, b), None))
-        except BaseException as e:  # noqa: B902 -- handed to the caller
-            q.put((None, None, None, e))
-
-    t = threading.Thread(target=work, name="fastoverlap-device-stage")
-    t.start()
-    try:
-        for _ in bounds:
-            a, b, res, err = q.get()
-            if err is not None:
-                raise err
-            host_step(a, b, res)
-    finally:
-        stop.set()
-        t.join()
-

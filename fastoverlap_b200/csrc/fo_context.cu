@@ -312,6 +312,7 @@ extern "C" int fo_set_perm(fo_ctx* ctx, const int32_t* group_offsets, int64_t ng
     FO_CUDA(ctx, cudaMemcpy(ctx->d_gidx, ctx->h_gidx.data(), sizeof(int32_t) * total,
                             cudaMemcpyHostToDevice));
   ctx->perm_natoms = natoms;
+  ctx->gid_natoms = -1;  // the per-atom group-id table of the spherical path is rebuilt on next use
   return FO_OK;
 }
 

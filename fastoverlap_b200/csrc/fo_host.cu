@@ -257,6 +257,35 @@ struct Lap {
 // can pick the other image only within rounding of exactly half a box, where both are equally near.
 inline double min_image(double d, double box, double ibox) { return d - __builtin_rint(d * ibox) * box; }
 
+// Canonical summation order shared with the device path (fo_assign.cu: canon_sum): 32 strided partial sums,
+// each accumulated in index order, combined pairwise by an xor butterfly.  The displacement update and the final
+// distance use it so that pairs settled by the device screening and pairs settled here agree bit for bit
+// (this translation unit is compiled without FMA contraction targets for these loops: plain mul / add).
+inline double canon_sum(const double* t, int n) {
+  double p[32], q[32];
+  for (int l = 0; l < 32; ++l) {
+    double s = 0.0;
+    for (int i = l; i < n; i += 32) s += t[i];
+    p[l] = s;
+  }
+  for (int off = 16; off; off >>= 1) {
+    for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ off];
+    for (int l = 0; l < 32; ++l) p[l] = q[l];
+  }
+  return p[0];
+}
+
+// permutation groups as the C ABI passes them; validated like fo_set_perm does for the device path
+inline bool groups_valid(const int32_t* goff, int64_t ngroups, const int32_t* gidx, int64_t natoms) {
+  if (ngroups < 1 || !goff || !gidx || natoms < 1 || goff[0] != 0) return false;
+  for (int64_t g = 0; g < ngroups; ++g)
+    if (goff[g + 1] < goff[g]) return false;
+  if (goff[ngroups] > natoms) return false;
+  for (int64_t i = 0; i < goff[ngroups]; ++i)
+    if (gidx[i] < 0 || gidx[i] >= natoms) return false;
+  return true;
+}
+
 struct Groups {
   const int32_t* goff;
   int64_t ngroups;
@@ -785,16 +814,19 @@ extern "C" void fo_host_refine_counters(int64_t out[3], int reset) {
   }
 }
 
-extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
-                                       const int32_t* atom_idx, const double* posA, const double* posB,
-                                       const double* frac_idx, int64_t npairs, int niter, int nthreads,
-                                       double* dist, int32_t* perm_out, double* disp_out) {
-  if (!p || !group_offsets || !atom_idx || !posA || !posB || !frac_idx || !dist || npairs < 0 || ngroups < 1)
-    return FO_ERR_INVALID;
+namespace {
+// pair_idx (nullable): the pairs to refine, results written at those indices; null = all of 0..npairs-1
+int host_refine_periodic_impl(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
+                              const int32_t* atom_idx, const double* posA, const double* posB,
+                              const double* frac_idx, const int64_t* pair_idx, int64_t npairs, int niter,
+                              int nthreads, double* dist, int32_t* perm_out, double* disp_out) {
+  if (!p || !posA || !posB || !frac_idx || !dist || npairs < 0) return FO_ERR_INVALID;
+  if (!groups_valid(group_offsets, ngroups, atom_idx, p->natoms)) return FO_ERR_INVALID;
   const int N = (int)p->natoms;
   const Groups G = {group_offsets, ngroups, atom_idx};
 #ifdef _OPENMP
-  const int nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+  int nt = nthreads > 0 ? nthreads : omp_get_num_procs();
+  if ((int64_t)nt > npairs) nt = (int)std::max<int64_t>(npairs, 1);
 #else
   const int nt = 1;
   (void)nthreads;
@@ -802,11 +834,12 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
 #pragma omp parallel num_threads(nt)
   {
     Lap lap;
-    std::vector<double> cost, ys((size_t)3 * N);
+    std::vector<double> cost, ys((size_t)3 * N), term((size_t)3 * N);
     std::vector<int> c4r, perm(N), save(N);
     std::vector<char> screen(ngroups);
 #pragma omp for schedule(dynamic, 4)
-    for (int64_t q = 0; q < npairs; ++q) {
+    for (int64_t qq = 0; qq < npairs; ++qq) {
+      const int64_t q = pair_idx ? pair_idx[qq] : qq;
       const double* x = posA + (size_t)q * N * 3;
       const double* y = posB + (size_t)q * N * 3;
       double disp[3];
@@ -817,11 +850,11 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
           for (int k = 0; k < 3; ++k) ys[3 * i + k] = y[3 * i + k] - disp[k];
       };
       auto recentre = [&](const int* pm) {
-        double m[3] = {0, 0, 0};
+        double* t = term.data();
         for (int i = 0; i < N; ++i)
           for (int k = 0; k < 3; ++k)
-            m[k] += min_image(x[3 * i + k] - (y[3 * pm[i] + k] - disp[k]), p->box[k], ibox[k]);
-        for (int k = 0; k < 3; ++k) disp[k] -= m[k] / N;
+            t[k * N + i] = min_image(x[3 * i + k] - (y[3 * pm[i] + k] - disp[k]), p->box[k], ibox[k]);
+        for (int k = 0; k < 3; ++k) disp[k] -= canon_sum(t + k * N, N) / N;
       };
       shift();
       std::fill(screen.begin(), screen.end(), 1);
@@ -845,16 +878,19 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
         save = perm;
       }
       recentre(perm.data());
-      double d2 = 0;
-      for (int i = 0; i < N; ++i)
+      double* t = term.data();
+      for (int i = 0; i < N; ++i) {
+        double s = 0.0;
         for (int k = 0; k < 3; ++k) {
           // periodic(x) - periodic(y[perm] - disp), then the minimum image of the difference
           const double a = min_image(x[3 * i + k], p->box[k], ibox[k]);
           const double b = min_image(y[3 * perm[i] + k] - disp[k], p->box[k], ibox[k]);
           const double d = min_image(a - b, p->box[k], ibox[k]);
-          d2 += d * d;
+          s = k == 0 ? d * d : s + d * d;
         }
-      dist[q] = sqrt(d2);
+        t[i] = s;
+      }
+      dist[q] = sqrt(canon_sum(t, N));
       if (perm_out)
         for (int i = 0; i < N; ++i) perm_out[(size_t)q * N + i] = perm[i];
       if (disp_out)
@@ -863,18 +899,43 @@ extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* gr
   }
   return FO_OK;
 }
+}  // namespace
 
-extern "C" int fo_host_refine_spherical(const double* posA, const double* posB, int64_t npairs, int64_t natoms,
-                                        const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
-                                        const double* euler, int norient, int nthreads, double* dist,
-                                        int32_t* orient_out, int32_t* perm_out, double* rmat_out) {
-  if (!posA || !posB || !group_offsets || !atom_idx || !euler || !dist || npairs < 0 || natoms < 1 ||
-      norient < 1 || norient > 2)
+extern "C" int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
+                                       const int32_t* atom_idx, const double* posA, const double* posB,
+                                       const double* frac_idx, int64_t npairs, int niter, int nthreads,
+                                       double* dist, int32_t* perm_out, double* disp_out) {
+  return host_refine_periodic_impl(p, group_offsets, ngroups, atom_idx, posA, posB, frac_idx, nullptr, npairs,
+                                   niter, nthreads, dist, perm_out, disp_out);
+}
+
+extern "C" int fo_host_refine_periodic_subset(const fo_per_params* p, const int32_t* group_offsets,
+                                              int64_t ngroups, const int32_t* atom_idx, const double* posA,
+                                              const double* posB, const double* frac_idx,
+                                              const int64_t* pair_idx, int64_t nidx, int niter, int nthreads,
+                                              double* dist, int32_t* perm_out, double* disp_out) {
+  if (nidx > 0 && !pair_idx) return FO_ERR_INVALID;
+  return host_refine_periodic_impl(p, group_offsets, ngroups, atom_idx, posA, posB, frac_idx, pair_idx, nidx,
+                                   niter, nthreads, dist, perm_out, disp_out);
+}
+
+namespace {
+// perm_hint [P, norient, N] / hint_ok [P, norient] (nullable): permutations the device screening proved optimal
+// (fo_assign.cu: sph_assign_kernel); where hint_ok is set the LAP is skipped.
+int host_refine_spherical_impl(const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                               const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                               const double* euler, int norient, const int32_t* perm_hint,
+                               const int32_t* hint_ok, int nthreads, double* dist, int32_t* orient_out,
+                               int32_t* perm_out, double* rmat_out) {
+  if (!posA || !posB || !euler || !dist || npairs < 0 || natoms < 1 || norient < 1 || norient > 2)
     return FO_ERR_INVALID;
+  if (!groups_valid(group_offsets, ngroups, atom_idx, natoms)) return FO_ERR_INVALID;
+  if ((perm_hint == nullptr) != (hint_ok == nullptr)) return FO_ERR_INVALID;
   const int N = (int)natoms;
   const Groups G = {group_offsets, ngroups, atom_idx};
 #ifdef _OPENMP
-  const int nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+  int nt = nthreads > 0 ? nthreads : omp_get_num_procs();
+  if ((int64_t)nt > npairs) nt = (int)std::max<int64_t>(npairs, 1);
 #else
   const int nt = 1;
   (void)nthreads;
@@ -901,7 +962,13 @@ extern "C" int fo_host_refine_spherical(const double* posA, const double* posB, 
             for (int k = 0; k < 3; ++k) s += sg * x2[3 * i + k] * M[3 * k + j];  // (X2 . M)
             xr[3 * i + j] = s;
           }
-        best_perm(G, N, x1, xr.data(), nullptr, lap, cost, c4r, perm.data());
+        if (hint_ok && hint_ok[q * norient + o]) {
+          const int32_t* h = perm_hint + ((size_t)q * norient + o) * N;
+          for (int i = 0; i < N; ++i) perm[i] = h[i];
+          count(1);
+        } else {
+          best_perm(G, N, x1, xr.data(), nullptr, lap, cost, c4r, perm.data());
+        }
         const double d = kearsley(N, x1, xr.data(), perm.data(), R);
         if (d < best) {
           best = d;
@@ -918,4 +985,23 @@ extern "C" int fo_host_refine_spherical(const double* posA, const double* posB, 
     }
   }
   return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_host_refine_spherical(const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                                        const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                                        const double* euler, int norient, int nthreads, double* dist,
+                                        int32_t* orient_out, int32_t* perm_out, double* rmat_out) {
+  return host_refine_spherical_impl(posA, posB, npairs, natoms, group_offsets, ngroups, atom_idx, euler, norient,
+                                    nullptr, nullptr, nthreads, dist, orient_out, perm_out, rmat_out);
+}
+
+extern "C" int fo_host_refine_spherical_hint(const double* posA, const double* posB, int64_t npairs,
+                                             int64_t natoms, const int32_t* group_offsets, int64_t ngroups,
+                                             const int32_t* atom_idx, const double* euler, int norient,
+                                             const int32_t* perm_hint, const int32_t* hint_ok, int nthreads,
+                                             double* dist, int32_t* orient_out, int32_t* perm_out,
+                                             double* rmat_out) {
+  return host_refine_spherical_impl(posA, posB, npairs, natoms, group_offsets, ngroups, atom_idx, euler, norient,
+                                    perm_hint, hint_ok, nthreads, dist, orient_out, perm_out, rmat_out);
 }

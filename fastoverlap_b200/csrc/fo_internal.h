@@ -45,11 +45,12 @@ struct fo_ctx {
   int32_t* d_goff = nullptr;
   int32_t* d_gidx = nullptr;
   int64_t perm_natoms = 0;  // natoms the perm was declared for (0 = unset -> one group of all)
+  int64_t gid_natoms = -1;  // natoms the cached per-atom group-id table (FO_SCR_GID) was built for; -1 = stale
 
   // growable device scratch (named slots)
-  fo_devbuf scratch[12];
+  fo_devbuf scratch[14];
   // pinned host staging (named slots)
-  fo_devbuf pinned[6];
+  fo_devbuf pinned[8];
 
   fo_wigner_cache wig;
   // recurrence table of the continuous rotation refinement (fo_refine.cu), cached per bandwidth
@@ -78,6 +79,8 @@ enum {
   FO_SCR_IPK = 8,
   FO_SCR_DBG = 9,
   FO_SCR_PEAKS = 10,
+  FO_SCR_FULL = 11,
+  FO_SCR_GID = 12,
 };
 
 struct fo_bank {
@@ -134,6 +137,15 @@ int fo_peaks_copy_out(fo_ctx* ctx, int64_t p0, int64_t np, int64_t npeaks, const
 // d_start is [np*norient][3] fractional grid indices (from_frac) or Euler angles
 int fo_refine_run_dev(fo_ctx* ctx, const void* d_Ihalf, int64_t np, int L, int norient, const double* d_start,
                       int from_frac, double* d_euler, double* d_overlap, int* d_iters);
+
+// device-side screening of the permutational assignment (fo_assign.cu).  Periodic: d_flag [np] = 0 when the pair
+// was settled on the device (dist / disp / perm written), non-zero when the host LAP pool must take it.
+// Clusters: d_perm [np, norient, natoms], d_ok [np, norient] = 1 where the permutation is the proven optimum.
+int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA, const double* d_posB,
+                          const double* d_frac, int64_t np, int niter, double* d_dist, double* d_disp,
+                          int32_t* d_perm, int32_t* d_flag);
+int fo_sph_assign_run_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB, const double* d_frac,
+                          int64_t np, int64_t natoms, int L, int norient, int32_t* d_perm, int32_t* d_ok);
 
 int fo_refine_eval_dev(fo_ctx* ctx, const void* d_Ihalf, int64_t np, int L, const double* d_euler, double* d_value,
                        double* d_grad, double* d_hess);

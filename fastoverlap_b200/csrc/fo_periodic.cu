@@ -1941,6 +1941,17 @@ extern "C" int fo_per_align_pairs_dev(fo_ctx* ctx, const fo_per_params* p, const
   return FO_OK;
 }
 
+extern "C" int fo_per_align_pairs_full_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA,
+                                           const double* d_posB, int64_t npairs, int niter, double* d_dist,
+                                           int32_t* d_perm, double* d_disp, int32_t* d_flag, int64_t* d_best_idx,
+                                           double* d_best_val, double* d_frac_idx, int32_t* d_status) {
+  if (ctx && npairs > 0 && (!d_dist || !d_disp || !d_flag))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs_full_dev: NULL argument");
+  FO_CHECK(fo_per_align_pairs_dev(ctx, p, d_posA, d_posB, npairs, d_best_idx, d_best_val, d_frac_idx, nullptr,
+                                  d_status));
+  return fo_per_assign_run_dev(ctx, p, d_posA, d_posB, d_frac_idx, npairs, niter, d_dist, d_disp, d_perm, d_flag);
+}
+
 namespace {
 // Shared host-buffer driver: `stage(p0, np)` must enqueue whatever fills bankA/bankB for pairs
 // [p0, p0+np) and return the (bankA, bankB, d_pairs) to use.
@@ -1995,10 +2006,20 @@ XfOut make_out(char* d_out, int64_t np, double* d_grid, bool want_status) {
 }
 }  // namespace
 
-extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const double* posA,
-                                  const double* posB, int64_t npairs, int64_t* best_idx,
-                                  double* best_val, double* frac_idx, double* grid_out,
-                                  int32_t* status) {
+namespace {
+// Outputs of the full alignment (fo_per_align_pairs_full): the device screening settles a pair (dist, disp,
+// perm written by per_assign_kernel) or flags it for the host LAP pool.
+struct FullOut {
+  int niter, nthreads;
+  double* dist;      // [P]
+  int32_t* perm;     // [P,N] or null
+  double* disp;      // [P,3] or null
+  int64_t nhost = 0; // pairs that went through the host pool
+};
+
+int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA, const double* posB,
+                         int64_t npairs, int64_t* best_idx, double* best_val, double* frac_idx, double* grid_out,
+                         int32_t* status, FullOut* full) {
   FO_CHECK(check_params(ctx, p));
   if (npairs < 0 || (npairs > 0 && (!posA || !posB || !best_idx || !best_val || !frac_idx)))
     return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs: NULL argument");
@@ -2007,15 +2028,20 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
   FO_CHECK(fo_ensure_perm(ctx, p->natoms));
   const size_t per_struct = bank_elems_per_struct(ctx, p);
   const int64_t chunk = chunk_pairs(ctx, p, npairs, grid_out != nullptr);
-  const size_t pos_bytes = (size_t)chunk * p->natoms * 3 * 8;
+  const int64_t N = p->natoms;
+  const size_t pos_bytes = (size_t)chunk * N * 3 * 8;
   const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
-  void *bank, *dA, *dB, *dOut, *dGrid = nullptr, *hA, *hB;
+  void *bank, *dA, *dB, *dOut, *dGrid = nullptr, *hA, *hB, *dFull = nullptr;
   FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
   // two position buffers per side so the copy of chunk c+1 overlaps the kernels of chunk c
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, 2 * pos_bytes, &dA));
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
   FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
+  // full alignment: dist[np] | disp[3 np] | flag[np] i32 (padded to 8 np) | perm[np N] i32, per chunk
+  const bool want_perm = full && full->perm;
+  const size_t full_stride = 40 + (want_perm ? (size_t)N * 4 : 0);
+  if (full) FO_CHECK(fo_scratch(ctx, FO_SCR_FULL, (size_t)chunk * full_stride, &dFull));
   const bool pinnedA = fo_is_pinned(posA), pinnedB = fo_is_pinned(posB);
   hA = hB = nullptr;
   if (!pinnedA) FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
@@ -2031,12 +2057,12 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
     const int64_t p0 = starts[c];
     const int64_t np = starts[c + 1] - p0;
     const int buf = (int)(c & 1);
-    const size_t nb = (size_t)np * p->natoms * 3 * 8;
+    const size_t nb = (size_t)np * N * 3 * 8;
     // the pinned buffer `buf` was last read by the H2D of chunk c-2
     if (c >= 2) FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[buf]));
     // caller buffers that are already page-locked are DMA'd directly; pageable ones are staged
-    const char* srcA = (const char*)(posA + (size_t)p0 * p->natoms * 3);
-    const char* srcB = (const char*)(posB + (size_t)p0 * p->natoms * 3);
+    const char* srcA = (const char*)(posA + (size_t)p0 * N * 3);
+    const char* srcB = (const char*)(posB + (size_t)p0 * N * 3);
     if (!pinnedA) {
       fo_host_copy((char*)hA + buf * pos_bytes, srcA, nb);
       srcA = (const char*)hA + buf * pos_bytes;
@@ -2054,20 +2080,55 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[buf], ctx->copy_stream));
     return FO_OK;
   };
-  void* hOut = nullptr;
-  const size_t out_bytes = (size_t)chunk * 64;
+  void *hOut = nullptr, *hFull = nullptr;
+  const size_t out_bytes = (size_t)chunk * 64, full_bytes = (size_t)chunk * full_stride;
   if (!grid_out) FO_CHECK(fo_pinned(ctx, 2, 2 * out_bytes, &hOut));
+  if (full) FO_CHECK(fo_pinned(ctx, 3, 2 * full_bytes, &hFull));
+  std::vector<int64_t> hard;
+  // unpack chunk c from the pinned ring into the caller's arrays; full alignment: the flagged pairs go through
+  // the host pool here, while the GPU works on the next chunk
+  auto deliver = [&](int64_t c) -> int {
+    const int64_t p0 = starts[c], np = starts[c + 1] - p0;
+    deliver_out(h, p0, np, (const char*)hOut + (c & 1) * out_bytes);
+    if (!full) return FO_OK;
+    const char* src = (const char*)hFull + (c & 1) * full_bytes;
+    const int32_t* flag = (const int32_t*)(src + (size_t)np * 32);
+    memcpy(full->dist + p0, src, (size_t)np * 8);
+    if (full->disp) memcpy(full->disp + 3 * p0, src + (size_t)np * 8, (size_t)np * 24);
+    if (want_perm) fo_host_copy(full->perm + (size_t)p0 * N, src + (size_t)np * 40, (size_t)np * N * 4);
+    hard.clear();
+    for (int64_t q = 0; q < np; ++q)
+      if (flag[q]) hard.push_back(p0 + q);
+    if (!hard.empty()) {
+      full->nhost += (int64_t)hard.size();
+      const int rc = fo_host_refine_periodic_subset(p, ctx->h_goff.data(), (int64_t)ctx->h_goff.size() - 1,
+                                                    ctx->h_gidx.data(), posA, posB, frac_idx, hard.data(),
+                                                    (int64_t)hard.size(), full->niter, full->nthreads, full->dist,
+                                                    full->perm, full->disp);
+      if (rc != FO_OK) return fo_fail(ctx, rc, "host refinement of %zu flagged pairs failed", hard.size());
+    }
+    return FO_OK;
+  };
   FO_CHECK(stage_in(0));
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t p0 = starts[c];
     const int64_t np = starts[c + 1] - p0;
     const int buf = (int)(c & 1);
+    const double* cA = (const double*)((char*)dA + buf * pos_bytes);
+    const double* cB = (const double*)((char*)dB + buf * pos_bytes);
     FO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[buf], 0));
-    FO_CHECK(launch_sf(ctx, p, (const double*)((char*)dA + buf * pos_bytes), np, bankA));
-    FO_CHECK(launch_sf(ctx, p, (const double*)((char*)dB + buf * pos_bytes), np, bankB));
-    FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+    FO_CHECK(launch_sf(ctx, p, cA, np, bankA));
+    FO_CHECK(launch_sf(ctx, p, cB, np, bankB));
+    if (!full) FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
     XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
     FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+    if (full) {  // screening + permutation <-> displacement loop on the device (reads the positions again)
+      char* f = (char*)dFull;
+      FO_CHECK(fo_per_assign_run_dev(ctx, p, cA, cB, out.frac_idx, np, full->niter, (double*)f,
+                                     (double*)(f + (size_t)np * 8), want_perm ? (int32_t*)(f + (size_t)np * 40) : nullptr,
+                                     (int32_t*)(f + (size_t)np * 32)));
+      FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+    }
     if (grid_out) {  // test / single-pair path: large grids straight into the caller's array
       FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
       if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
@@ -2075,20 +2136,56 @@ extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const dou
     }
     FO_CUDA(ctx, cudaMemcpyAsync((char*)hOut + buf * out_bytes, dOut, (size_t)np * 60, cudaMemcpyDeviceToHost,
                                  ctx->stream));
+    if (full)
+      FO_CUDA(ctx, cudaMemcpyAsync((char*)hFull + buf * full_bytes, dFull, (size_t)np * full_stride,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[4 + buf], ctx->stream));
     // host work of this iteration runs while the GPU is busy with chunk c
     if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));
     if (c >= 1) {
       FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[4 + (buf ^ 1)]));
-      deliver_out(h, starts[c - 1], starts[c] - starts[c - 1], (const char*)hOut + (buf ^ 1) * out_bytes);
+      FO_CHECK(deliver(c - 1));
     }
   }
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (!grid_out) {
-    const int64_t c = nchunks - 1;
-    deliver_out(h, starts[c], starts[c + 1] - starts[c], (const char*)hOut + (c & 1) * out_bytes);
-  }
+  if (!grid_out) FO_CHECK(deliver(nchunks - 1));
   return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_per_align_pairs(fo_ctx* ctx, const fo_per_params* p, const double* posA,
+                                  const double* posB, int64_t npairs, int64_t* best_idx,
+                                  double* best_val, double* frac_idx, double* grid_out,
+                                  int32_t* status) {
+  return per_align_pairs_impl(ctx, p, posA, posB, npairs, best_idx, best_val, frac_idx, grid_out, status, nullptr);
+}
+
+extern "C" int fo_per_align_pairs_full(fo_ctx* ctx, const fo_per_params* p, const double* posA, const double* posB,
+                                       int64_t npairs, int niter, int nthreads, double* dist, int32_t* perm,
+                                       double* disp, double* frac_idx, int32_t* status, int64_t* nhost) {
+  if (!ctx) return FO_ERR_INVALID;
+  if (npairs > 0 && !dist) return fo_fail(ctx, FO_ERR_INVALID, "fo_per_align_pairs_full: dist is NULL");
+  if (npairs <= 0) {
+    if (nhost) *nhost = 0;
+    return npairs < 0 ? fo_fail(ctx, FO_ERR_INVALID, "npairs < 0") : FO_OK;
+  }
+  // best_idx / best_val (and frac_idx when the caller does not want it) live in library-owned host memory
+  std::vector<int64_t> bi((size_t)npairs * 3);
+  std::vector<double> bv((size_t)npairs), fr;
+  if (!frac_idx) {
+    fr.resize((size_t)npairs * 3);
+    frac_idx = fr.data();
+  }
+  FullOut full;
+  full.niter = niter;
+  full.nthreads = nthreads;
+  full.dist = dist;
+  full.perm = perm;
+  full.disp = disp;
+  const int rc = per_align_pairs_impl(ctx, p, posA, posB, npairs, bi.data(), bv.data(), frac_idx, nullptr, status,
+                                      &full);
+  if (nhost) *nhost = full.nhost;
+  return rc;
 }
 
 // a8 fused: positions -> F^3 |f| grid on the device -> top-npeaks displacements; the grid never

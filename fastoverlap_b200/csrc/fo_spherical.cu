@@ -2397,17 +2397,24 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
 
 size_t ihalf_elems(int L) { return (size_t)(L + 1) * (2 * L + 1) * (L + 1); }
 
-// group id per atom on the device (from the ctx permutation groups); atoms in no group get -1-i
+// group id per atom on the device (from the ctx permutation groups); atoms in no group get -1-i.  Cached in
+// the ctx until fo_set_perm changes the groups: the per-chunk calls of the host-buffer pipeline must not
+// synchronise the stream (that would serialise the double-buffered copies against the kernels).
 int upload_gid(fo_ctx* ctx, int64_t natoms, int** d_gid) {
+  if (ctx->gid_natoms == natoms && ctx->scratch[FO_SCR_GID].ptr) {
+    *d_gid = (int*)ctx->scratch[FO_SCR_GID].ptr;
+    return FO_OK;
+  }
   std::vector<int> gid(natoms);
   for (int64_t i = 0; i < natoms; ++i) gid[i] = -1 - (int)i;
   const int ng = (int)ctx->h_goff.size() - 1;
   for (int g = 0; g < ng; ++g)
     for (int a = ctx->h_goff[g]; a < ctx->h_goff[g + 1]; ++a) gid[ctx->h_gidx[a]] = g;
   void* p = nullptr;
-  FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)natoms * 4 + 64, &p));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_GID, (size_t)natoms * 4 + 64, &p));
   FO_CUDA(ctx, cudaMemcpyAsync(p, gid.data(), (size_t)natoms * 4, cudaMemcpyHostToDevice, ctx->stream));
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // gid is a stack vector
+  ctx->gid_natoms = natoms;
   *d_gid = (int*)p;
   return FO_OK;
 }
@@ -2769,6 +2776,19 @@ extern "C" int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const d
                               d_frac_idx, d_grid_out, d_status, nullptr, nullptr);
 }
 
+extern "C" int fo_sph_align_pairs_screen_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
+                                             int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
+                                             int invert, int64_t* d_best_idx, double* d_best_val,
+                                             double* d_frac_idx, int32_t* d_perm, int32_t* d_ok,
+                                             int32_t* d_status) {
+  if (ctx && npairs > 0 && (!d_perm || !d_ok))
+    return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_pairs_screen_dev: NULL argument");
+  FO_CHECK(align_pairs_dev_impl(ctx, d_posA, d_posB, npairs, natoms, Jmax, sigma, invert, d_best_idx, d_best_val,
+                                d_frac_idx, nullptr, d_status, nullptr, nullptr));
+  return fo_sph_assign_run_dev(ctx, d_posA, d_posB, d_frac_idx, npairs, natoms, (int)Jmax, invert ? 2 : 1, d_perm,
+                               d_ok);
+}
+
 extern "C" int fo_sph_align_pairs_refined_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB,
                                               int64_t npairs, int64_t natoms, int64_t Jmax, double sigma,
                                               int invert, int64_t* d_best_idx, double* d_best_val,
@@ -2781,9 +2801,22 @@ extern "C" int fo_sph_align_pairs_refined_dev(fo_ctx* ctx, const double* d_posA,
 }
 
 namespace {
+// Outputs of the full alignment (fo_sph_align_pairs_full): the device screening proposes a permutation per
+// (pair, orientation); the host pool runs the Kearsley fit (and the LAP where the screening failed).
+struct SphFull {
+  int nthreads;
+  double* dist;        // [P]
+  int32_t* orient;     // [P] or null
+  int32_t* perm;       // [P,N] or null
+  double* rmat;        // [P,9] or null
+  double* euler_grid;  // [P,O,3] or null: Euler angles of the interpolated grid maxima
+  int64_t nhost = 0;   // (pair, orientation) assignments the host LAP solved
+};
+
 int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs, int64_t natoms,
                      int64_t Jmax, double sigma, int invert, int64_t* best_idx, double* best_val,
-                     double* frac_idx, double* grid_out, int32_t* status, double* euler, double* overlap) {
+                     double* frac_idx, double* grid_out, int32_t* status, double* euler, double* overlap,
+                     SphFull* full = nullptr) {
   if (!ctx) return FO_ERR_INVALID;
   FO_CHECK(check_L(ctx, Jmax));
   if (natoms < 1 || !(sigma > 0.0)) return fo_fail(ctx, FO_ERR_INVALID, "natoms >= 1 and sigma > 0 required");
@@ -2800,6 +2833,15 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
   FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * (O * 88 + 8) + 256, &dout));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
+  // full alignment: ok[np O] i32 | perm[np O N] i32 per chunk
+  void *dfull = nullptr, *hFull = nullptr;
+  const size_t full_stride = (size_t)O * 4 * (1 + natoms);
+  if (full) {
+    FO_CHECK(fo_ensure_perm(ctx, natoms));
+    FO_CHECK(fo_scratch(ctx, FO_SCR_FULL, (size_t)chunk * full_stride, &dfull));
+    FO_CHECK(fo_pinned(ctx, 3, 2 * (size_t)chunk * full_stride, &hFull));
+  }
+  std::vector<double> eul;
   const bool pinnedA = fo_is_pinned(posA), pinnedB = fo_is_pinned(posB);
   hA = hB = nullptr;
   if (!pinnedA) FO_CHECK(fo_pinned(ctx, 0, 2 * pos_bytes, &hA));
@@ -2833,7 +2875,7 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
   void* hOut = nullptr;
   const size_t out_bytes = (size_t)chunk * (O * 88 + 8);
   if (!grid_out) FO_CHECK(fo_pinned(ctx, 2, 2 * out_bytes, &hOut));
-  auto deliver = [&](int64_t c) {
+  auto deliver = [&](int64_t c) -> int {
     const int64_t p0 = starts[c], np = starts[c + 1] - p0;
     const char* src = (const char*)hOut + (c & 1) * out_bytes;
     memcpy(best_idx + (size_t)p0 * O * 3, src, (size_t)np * O * 24);
@@ -2844,6 +2886,28 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
       memcpy(overlap + (size_t)p0 * O, src + (size_t)np * O * 80, (size_t)np * O * 8);
     }
     if (status) memcpy(status + p0, src + (size_t)np * O * 88, (size_t)np * 4);
+    if (!full) return FO_OK;
+    // host stage of the full alignment, while the GPU works on the next chunk: Euler angles of the grid
+    // maxima (indtoEuler, utils.py:340-345), then rotate + permutation (device hint or LAP) + Kearsley
+    const double kPi = 3.14159265358979323846, n2 = (double)(2 * (L + 1));
+    eul.resize((size_t)np * O * 3);
+    const double* fr = frac_idx + (size_t)p0 * O * 3;
+    for (int64_t i = 0; i < np * O; ++i) {
+      eul[3 * i] = (2 * kPi / n2) * fr[3 * i];
+      eul[3 * i + 1] = (kPi / n2) * fr[3 * i + 1] + 0.5 * kPi / n2;
+      eul[3 * i + 2] = (2 * kPi / n2) * fr[3 * i + 2];
+    }
+    if (full->euler_grid) memcpy(full->euler_grid + (size_t)p0 * O * 3, eul.data(), (size_t)np * O * 24);
+    const int32_t* ok = (const int32_t*)((const char*)hFull + (c & 1) * (size_t)chunk * full_stride);
+    const int32_t* hint = ok + (size_t)np * O;
+    for (int64_t i = 0; i < np * O; ++i) full->nhost += ok[i] ? 0 : 1;
+    const int rc = fo_host_refine_spherical_hint(
+        posA + (size_t)p0 * natoms * 3, posB + (size_t)p0 * natoms * 3, np, natoms, ctx->h_goff.data(),
+        (int64_t)ctx->h_goff.size() - 1, ctx->h_gidx.data(), eul.data(), O, hint, ok, full->nthreads,
+        full->dist + p0, full->orient ? full->orient + p0 : nullptr,
+        full->perm ? full->perm + (size_t)p0 * natoms : nullptr, full->rmat ? full->rmat + 9 * p0 : nullptr);
+    if (rc != FO_OK) return fo_fail(ctx, rc, "host refinement of chunk %lld failed", (long long)c);
+    return FO_OK;
   };
   FO_CHECK(stage_in(0));
   for (int64_t c = 0; c < nchunks; ++c) {
@@ -2861,6 +2925,10 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
                                   (const double*)((char*)dB + buf * pos_bytes), np, natoms, Jmax, sigma,
                                   invert, (int64_t*)d_bi, d_bv, d_fr, (double*)dgrid, d_st,
                                   euler ? d_eu : nullptr, euler ? d_ov : nullptr));
+    if (full)  // nearest-partner screening of both orientations on the device (reads the positions again)
+      FO_CHECK(fo_sph_assign_run_dev(ctx, (const double*)((char*)dA + buf * pos_bytes),
+                                     (const double*)((char*)dB + buf * pos_bytes), d_fr, np, natoms, L, O,
+                                     (int32_t*)dfull + (size_t)np * O, (int32_t*)dfull));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
     if (grid_out) {  // test / single-pair path: straight into the caller's arrays
       if (euler) {
@@ -2878,18 +2946,47 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
     }
     FO_CUDA(ctx, cudaMemcpyAsync((char*)hOut + buf * out_bytes, dout, (size_t)np * (O * 88 + 4), cudaMemcpyDeviceToHost,
                                  ctx->stream));
+    if (full)
+      FO_CUDA(ctx, cudaMemcpyAsync((char*)hFull + buf * (size_t)chunk * full_stride, dfull, (size_t)np * full_stride,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[4 + buf], ctx->stream));
     if (c + 1 < nchunks) FO_CHECK(stage_in(c + 1));  // host staging runs while the GPU works on chunk c
     if (c >= 1) {
       FO_CUDA(ctx, cudaEventSynchronize(ctx->ev[4 + (buf ^ 1)]));
-      deliver(c - 1);
+      FO_CHECK(deliver(c - 1));
     }
   }
   FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (!grid_out) deliver(nchunks - 1);
+  if (!grid_out) FO_CHECK(deliver(nchunks - 1));
   return FO_OK;
 }
 }  // namespace
+
+extern "C" int fo_sph_align_pairs_full(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
+                                       int64_t natoms, int64_t Jmax, double sigma, int invert, int nthreads,
+                                       double* dist, int32_t* orient, int32_t* perm, double* rmat, double* euler,
+                                       int32_t* status, int64_t* nhost) {
+  if (!ctx) return FO_ERR_INVALID;
+  if (npairs > 0 && !dist) return fo_fail(ctx, FO_ERR_INVALID, "fo_sph_align_pairs_full: dist is NULL");
+  if (npairs <= 0) {
+    if (nhost) *nhost = 0;
+    return npairs < 0 ? fo_fail(ctx, FO_ERR_INVALID, "npairs < 0") : FO_OK;
+  }
+  const int O = invert ? 2 : 1;
+  std::vector<int64_t> bi((size_t)npairs * O * 3);
+  std::vector<double> bv((size_t)npairs * O), fr((size_t)npairs * O * 3);
+  SphFull full;
+  full.nthreads = nthreads;
+  full.dist = dist;
+  full.orient = orient;
+  full.perm = perm;
+  full.rmat = rmat;
+  full.euler_grid = euler;
+  const int rc = align_pairs_impl(ctx, posA, posB, npairs, natoms, Jmax, sigma, invert, bi.data(), bv.data(),
+                                  fr.data(), nullptr, status, nullptr, nullptr, &full);
+  if (nhost) *nhost = full.nhost;
+  return rc;
+}
 
 extern "C" int fo_sph_align_pairs(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs,
                                   int64_t natoms, int64_t Jmax, double sigma, int invert,

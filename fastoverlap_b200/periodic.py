@@ -200,38 +200,20 @@ class PeriodicAlign(BasePeriodicAlignment):
         bi, bv, fr, _, st = self.ctx.per_align_pairs(self._params(), pos1, pos2)
         return fr * self.boxvec / np.array(self.fshape, float), bi, bv
 
-    def align_batch(self, pos1, pos2, refine=True, nthreads=0, chunk=None):
-        """Align P independent pairs: GPU hot path, then the native host refinement pool
-        (fo_host_refine_periodic).  Batches of at least 2048 pairs go through in chunks (default 1024 pairs;
-        chunk=0: one piece), the host pool refining one chunk while the GPU works on the next
-        (batch.overlap_chunks); per-pair results do not depend on the chunking.
-        Returns (dists (P,), disps (P,3), perms (P,Natoms))."""
+    def align_batch(self, pos1, pos2, refine=True, nthreads=0, want_perm=True):
+        """Align P independent pairs in one native call (fo_per_align_pairs_full): GPU hot path, on the device
+        the nearest-partner screening of the assignment with the permutation <-> mean-displacement loop, and
+        the host LAP pool (nthreads; 0 = all cores) only for the pairs whose screening fails, overlapped with
+        the GPU's next chunk.  Returns (dists (P,), disps (P,3), perms (P,Natoms) or None); with refine=False
+        (None, grid displacements (P,3), None).  self.last_nhost = pairs the host pool took."""
         pos1 = np.asarray(pos1, float).reshape(-1, self.Natoms, 3)
         pos2 = np.asarray(pos2, float).reshape(-1, self.Natoms, 3)
         p = self._params()
-        P = len(pos1)
-        if chunk is None:
-            chunk = 1024 if P >= 2048 else 0
-        if not refine or chunk <= 0 or P <= chunk:
-            bi, bv, fr, _, st = self.ctx.per_align_pairs(p, pos1, pos2)
-            if not refine:
-                return None, fr * self.boxvec / np.array(self.fshape, float)
-            dists, perms, disps = _lib.host_refine_periodic(p, self.perm, pos1, pos2, fr, 10, nthreads)
-            return dists, disps, perms
-        from .batch import overlap_chunks
-        dists = np.empty(P)
-        disps = np.empty((P, 3))
-        perms = np.empty((P, self.Natoms), np.int32)
-        ctx = self.ctx
-
-        def device_step(a, b):
-            return ctx.per_align_pairs(p, pos1[a:b], pos2[a:b])[2]
-
-        def host_step(a, b, fr):
-            dists[a:b], perms[a:b], disps[a:b] = _lib.host_refine_periodic(p, self.perm, pos1[a:b], pos2[a:b],
-                                                                          fr, 10, nthreads)
-
-        overlap_chunks([(a, min(a + chunk, P)) for a in range(0, P, chunk)], device_step, host_step)
+        if not refine:
+            fr = self.ctx.per_align_pairs(p, pos1, pos2)[2]
+            return None, fr * self.boxvec / np.array(self.fshape, float), None
+        dists, perms, disps, fr, st, self.last_nhost = self.ctx.per_align_pairs_full(
+            p, pos1, pos2, niter=10, nthreads=nthreads, want_perm=want_perm)
         return dists, disps, perms
 
     def alignGroup(self, coords, keepCoords=False, npeaks=1, width=2):

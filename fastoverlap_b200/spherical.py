@@ -242,37 +242,31 @@ class BaseSphericalAlignment(object):
         return dist, X1, X2
 
     # -- batched, additive API
-    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True, nthreads=0, chunk=None):
-        """P independent pairs: GPU hot path for the batch, then the native host refinement
-        pool (fo_host_refine_spherical: rotate, LAP, Kearsley, best orientation by distance).
-        With the distance rule, batches of at least 2048 pairs go through in chunks (default 1024 pairs;
-        chunk=0: one piece), the host pool refining one chunk while the GPU works on the next
-        (batch.overlap_chunks); per-pair results do not depend on the chunking.
-        Returns dists (P,) and the Euler angles (P, O, 3)."""
+    def _batch_scale(self, X1, X2):
+        """Kernel width of a batch when the constructor left it to be computed (calcScale): the reference's
+        rule (:165-166, a third of the mean nearest-neighbour separation of the two structures) averaged
+        over the batch, so that one width serves every pair of the call."""
+        if not self.calcScale:
+            return self.scale
+        n = min(len(X1), 64)  # a sample of the batch is enough for a mean
+        sep = [self.averageSeparation(X1[i]) + self.averageSeparation(X2[i]) for i in range(n)]
+        self.scale = float(np.mean(sep)) / 6
+        return self.scale
+
+    def align_batch(self, pos1, pos2, perm=None, invert=True, refine=True, nthreads=0):
+        """P independent pairs.  Distance rule (default): one native call (fo_sph_align_pairs_full) -- GPU hot
+        path, on the device the rotation by the grid-maximum Euler angles and the nearest-partner screening of
+        the assignment for both orientations, on the host pool (nthreads; 0 = all cores, overlapped with the
+        GPU's next chunk) the LAP where the screening failed and the Kearsley fit.  orientation="overlap": the
+        numpy rule, continuous refinement on the device, then one host LAP + Kearsley per pair.
+        Returns dists (P,) and the Euler angles (P, O, 3); self.last_perms / last_orient / last_rmats hold the
+        rest of the result."""
         pos1 = np.asarray(pos1, float)
         pos2 = np.asarray(pos2, float)
         X1 = pos1 - pos1.mean(1, keepdims=True)
         X2 = pos2 - pos2.mean(1, keepdims=True)
         perm = self._perm(X1.shape[1], perm)
-        P = len(X1)
-        if chunk is None:
-            chunk = 1024 if P >= 2048 else 0
-        if refine and self.orientation != "overlap" and 0 < chunk < P:
-            from .batch import overlap_chunks
-            dists = np.empty(P)
-            out = {}
-
-            def device_step(a, b):
-                return self._grid_search(X1[a:b], X2[a:b], perm, invert).reshape(b - a, -1, 3)
-
-            def host_step(a, b, Rs):
-                if "Rs" not in out:
-                    out["Rs"] = np.empty((P,) + Rs.shape[1:])
-                out["Rs"][a:b] = Rs
-                dists[a:b] = _lib.host_refine_spherical(X1[a:b], X2[a:b], Rs, perm, nthreads)[0]
-
-            overlap_chunks([(a, min(a + chunk, P)) for a in range(0, P, chunk)], device_step, host_step)
-            return dists, out["Rs"]
+        self._batch_scale(X1, X2)
         if self.orientation == "overlap":
             # numpy rule (:178-187): the orientation with the larger refined overlap is the only one
             # that goes through the host LAP + Kearsley refinement
@@ -284,13 +278,17 @@ class BaseSphericalAlignment(object):
             sign = np.where(pick == 1, -1.0, 1.0)[:, None, None]
             Rp = Rs[np.arange(len(X1)), pick][:, None, :]
             dists, orient, perms, rmats = _lib.host_refine_spherical(X1, sign * X2, Rp, perm, nthreads)
+            self.last_orient, self.last_perms, self.last_rmats = pick, perms, rmats
             return dists, Rs
-        Rs = self._grid_search(X1, X2, perm, invert)
-        Rs = Rs.reshape(len(X1), -1, 3)
-        if not refine:
-            return None, Rs
-        dists, orient, perms, rmats = _lib.host_refine_spherical(X1, X2, Rs, perm, nthreads)
-        return dists, Rs
+        if not refine or not hasattr(self, "_full_batch"):
+            Rs = self._grid_search(X1, X2, perm, invert)
+            Rs = Rs.reshape(len(X1), -1, 3)
+            if not refine:
+                return None, Rs
+            dists, self.last_orient, self.last_perms, self.last_rmats = _lib.host_refine_spherical(
+                X1, X2, Rs, perm, nthreads)
+            return dists, Rs
+        return self._full_batch(X1, X2, perm, invert, nthreads)
 
 
 class SphericalAlign(BaseSphericalAlignment):
@@ -329,6 +327,12 @@ class SphericalAlign(BaseSphericalAlignment):
         R = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
         return R[0] if X1.ndim == 2 else R
 
+
+    def _full_batch(self, X1, X2, perm, invert, nthreads):
+        self.ctx.set_perm(perm, X1.shape[-2])
+        dists, self.last_orient, self.last_perms, self.last_rmats, Rs, st, self.last_nhost = \
+            self.ctx.sph_align_pairs_full(X1, X2, self.Jmax, self.scale, invert=invert, nthreads=nthreads)
+        return dists, Rs
 
     def _grid_search_refined(self, X1, X2, perm, invert):
         self.ctx.set_perm(perm, X1.shape[-2])

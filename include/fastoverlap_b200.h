@@ -86,7 +86,8 @@ int fo_measure_fp64_tensor_peak(fo_ctx* ctx, double* tflops);
 #define FO_PROF_SPH_ISOFT 5   /* Wigner-d contraction + 2-D DFT + argmax */
 #define FO_PROF_PEAKS 6       /* top-k peak extraction (fit-and-subtract) */
 #define FO_PROF_SPH_REFINE 7  /* continuous rotation refinement (damped Newton) */
-#define FO_PROF_NKINDS 8
+#define FO_PROF_ASSIGN 8      /* nearest-partner screening of the assignment (full alignment) */
+#define FO_PROF_NKINDS 9
 int fo_profile_begin(fo_ctx* ctx);
 int fo_profile_end(fo_ctx* ctx, double ms_out[FO_PROF_NKINDS], int64_t count_out[FO_PROF_NKINDS]);
 
@@ -154,6 +155,32 @@ int fo_per_align_pairs_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_
                            const double* d_posB, int64_t npairs, int64_t* d_best_idx,
                            double* d_best_val, double* d_frac_idx, double* d_grid_out,
                            int32_t* d_status);
+
+/* The whole periodic alignment for P independent pairs, host buffers: the hot path of fo_per_align_pairs,
+ * then BasePeriodicAlignment.refine (periodicAlignment.py:27-80) / ITERATIVEALIGN(bulk) (alignutils.f90:111-286).
+ * The Hungarian step stays on the host; what runs on the device is the screening that makes it unnecessary for
+ * well-aligned pairs: with the arg-max displacement applied every atom of B looks for its nearest same-group
+ * atom of A (minimum image); when those nearest partners form a permutation and every runner-up is further away
+ * by a clear gap, that permutation is the unique optimum of the assignment problem, and the permutation <->
+ * mean-displacement loop and the final distance are finished on the device with the host path's operations in
+ * the host path's order (bit-identical results).  Every other pair goes through fo_host_refine_periodic on
+ * `nthreads` host threads (<= 0: all cores) while the GPU works on the next chunk.
+ *   dist [P]; perm [P,N] int32 (nullable): X2 = posB[perm] - disp; disp [P,3] (nullable);
+ *   frac_idx [P,3] (nullable): the hot path's interpolated arg-max; status [P] (nullable);
+ *   nhost (nullable): number of pairs the host pool had to take. */
+int fo_per_align_pairs_full(fo_ctx* ctx, const fo_per_params* p, const double* posA /*[P,N,3]*/,
+                            const double* posB /*[P,N,3]*/, int64_t npairs, int niter, int nthreads,
+                            double* dist, int32_t* perm, double* disp, double* frac_idx, int32_t* status,
+                            int64_t* nhost);
+
+/* Device-resident form (all pointers are DEVICE pointers, enqueued on the ctx stream, no synchronisation, no
+ * host pool): d_flag [P] int32 = 0 where the pair was settled on the device (d_dist / d_disp / d_perm valid),
+ * non-zero where the host LAP is needed (the caller then runs fo_host_refine_periodic_subset on those).
+ * d_perm [P,N] nullable. */
+int fo_per_align_pairs_full_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA, const double* d_posB,
+                                int64_t npairs, int niter, double* d_dist, int32_t* d_perm, double* d_disp,
+                                int32_t* d_flag, int64_t* d_best_idx, double* d_best_val, double* d_frac_idx,
+                                int32_t* d_status);
 
 /* Same path starting from caller-supplied structure factors (the reference's
  * `Cs=[c1,c2]` hook, periodicAlignment.py:408-432,458-460): CA, CB are
@@ -225,6 +252,27 @@ int fo_sph_align_pairs_dev(fo_ctx* ctx, const double* d_posA, const double* d_po
                            int64_t npairs, int64_t natoms, int64_t Jmax, double sigma, int invert,
                            int64_t* d_best_idx, double* d_best_val, double* d_frac_idx,
                            double* d_grid_out, int32_t* d_status);
+
+/* The whole cluster alignment for P pairs of centred structures, host buffers: the hot path of
+ * fo_sph_align_pairs, then BaseSphericalAlignment.refine (sphericalAlignment.py:118-127) for every orientation
+ * with the Fortran orientation rule (smaller distance, fastclusters.f90:243-254).  On the device: rotation by the
+ * Euler angles of the grid maximum and the nearest-partner screening of the assignment (see
+ * fo_per_align_pairs_full); on the host pool (`nthreads`, <= 0: all cores), overlapped with the GPU's next
+ * chunk: the LAP where the screening failed and the Kearsley fit for every (pair, orientation).
+ *   dist [P]; orient [P], perm [P,N], rmat [P,9], euler [P,O,3] (grid-maximum angles), status [P] nullable;
+ *   nhost (nullable): number of (pair, orientation) assignments the host LAP solved. */
+int fo_sph_align_pairs_full(fo_ctx* ctx, const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                            int64_t Jmax, double sigma, int invert, int nthreads, double* dist, int32_t* orient,
+                            int32_t* perm, double* rmat, double* euler, int32_t* status, int64_t* nhost);
+
+/* Device-resident form of the GPU stage of fo_sph_align_pairs_full: fo_sph_align_pairs_dev followed by the
+ * screening kernel.  d_perm [P,O,N] int32 = nearest-partner permutation of every (pair, orientation) after the
+ * rotation by the grid-maximum Euler angles, d_ok [P,O] int32 = 1 where it is the proven optimum of the
+ * assignment (fo_host_refine_spherical_hint takes both as they are). */
+int fo_sph_align_pairs_screen_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t npairs,
+                                  int64_t natoms, int64_t Jmax, double sigma, int invert, int64_t* d_best_idx,
+                                  double* d_best_val, double* d_frac_idx, int32_t* d_perm, int32_t* d_ok,
+                                  int32_t* d_status);
 
 /* Harmonic-basis coefficients C[s, g, n, l, m] = sum_{j in g} d_nl(r_j; sigma, r0) conj(Y_lm(r_j))
  * for S centred structures; out [S, ngroups, nmax+1, L+1, 2L+1, 2] (numpy layout, negative m
@@ -332,6 +380,13 @@ int fo_host_refine_periodic(const fo_per_params* p, const int32_t* group_offsets
                             const double* frac_idx, int64_t npairs, int niter, int nthreads, double* dist,
                             int32_t* perm, double* disp);
 
+/* Same for the pairs pair_idx[0..nidx) only (indices into posA / posB / frac_idx / the outputs): the host stage
+ * of fo_per_align_pairs_full for the pairs its device screening flags. */
+int fo_host_refine_periodic_subset(const fo_per_params* p, const int32_t* group_offsets, int64_t ngroups,
+                                   const int32_t* atom_idx, const double* posA, const double* posB,
+                                   const double* frac_idx, const int64_t* pair_idx, int64_t nidx, int niter,
+                                   int nthreads, double* dist, int32_t* perm, double* disp);
+
 /* Work counters of fo_host_refine_periodic since load (summed over calls and threads), for tests and
  * profiling: out[0] assignments solved by the double-precision matrix + LAP (per group), out[1] assignments
  * settled by the single-precision screening (column minima proven to be the unique optimum), out[2] repeat
@@ -348,6 +403,14 @@ int fo_host_refine_spherical(const double* posA, const double* posB, int64_t npa
                              const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
                              const double* euler, int norient, int nthreads, double* dist, int32_t* orient,
                              int32_t* perm, double* rmat);
+
+/* Same with permutation hints: perm_hint [P,norient,N] and hint_ok [P,norient]; where hint_ok is non-zero the
+ * LAP is skipped and perm_hint used (the device screening of fo_sph_align_pairs_full proved it optimal). */
+int fo_host_refine_spherical_hint(const double* posA, const double* posB, int64_t npairs, int64_t natoms,
+                                  const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                                  const double* euler, int norient, const int32_t* perm_hint,
+                                  const int32_t* hint_ok, int nthreads, double* dist, int32_t* orient,
+                                  int32_t* perm, double* rmat);
 
 #ifdef __cplusplus
 }

@@ -1,39 +1,62 @@
-"""Full-alignment rate (GPU hot path + native host refinement pool), repeated, per workload."""
+"""End-to-end ALIGNED pairs/s (fo_*_align_pairs_full: hot path + device screening + host pool), per workload,
+against the two-step path (hot path, then the host pool on every pair).
+    python scripts/time_aligned.py [pairs] [threads]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
+import torch
 import fastoverlap_b200 as fob
 from fastoverlap_b200 import _lib
 
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+nthr = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
 ctx = fob.Context(0)
-for name in ("lj38", "blj256"):
+for name in ("blj256", "lj38"):
     wl = bench.WORKLOADS[name]()
     wl.setup(ctx)
-    A, B, _ = wl.make(4096, 0)
-    nthr = os.cpu_count()
-    for rep in range(4):
-        t0 = time.perf_counter()
-        if name == "lj38":
-            X1 = A - A.mean(1, keepdims=True); X2 = B - B.mean(1, keepdims=True)
-            Rs = wl.sa._grid_search(X1, X2, [np.arange(38)], True).reshape(len(X1), -1, 3)
-            t1 = time.perf_counter()
-            r = _lib.host_refine_spherical(X1, X2, Rs, [np.arange(38)], nthr)
-        else:
-            bi, bv, fr, _, st = ctx.per_align_pairs(wl.params, A, B)
-            t1 = time.perf_counter()
-            r = _lib.host_refine_periodic(wl.params, wl.perm, A, B, fr, 10, nthr)
-        t2 = time.perf_counter()
-        print(name, "rep", rep, "gpu+wrapper %.1f ms  host refine %.1f ms  -> %.0f pairs/s (threads %d)" % (
-            (t1 - t0) * 1e3, (t2 - t1) * 1e3, 4096 / (t2 - t0), nthr), flush=True)
-    # the public batched call, in one piece and with the chunk pipeline (batch.overlap_chunks)
-    al = wl.sa if name == "lj38" else wl.al
-    for chunk in (0, 512, 1024, 2048):
-        best = 1e9
-        for rep in range(4):
-            t0 = time.perf_counter()
-            d = al.align_batch(A, B, nthreads=nthr, chunk=chunk)[0]
-            best = min(best, time.perf_counter() - t0)
-        print(name, "align_batch chunk %4d: %.1f ms -> %.0f pairs/s (median distance %.4f)" % (
-            chunk, best * 1e3, 4096 / best, float(np.median(d))), flush=True)
+    A, B, _ = wl.make(P, 0)
+    if name == "lj38":
+        A -= A.mean(1, keepdims=True)
+        B -= B.mean(1, keepdims=True)
+    hA = torch.from_numpy(A).pin_memory()
+    hB = torch.from_numpy(B).pin_memory()
+    for pinned in (True, False):
+        a, b = (hA.numpy(), hB.numpy()) if pinned else (A, B)
+        for want_perm in (True, False):
+            best, nh = 1e9, -1
+            for rep in range(4):
+                t0 = time.perf_counter()
+                if name == "lj38":
+                    r = ctx.sph_align_pairs_full(a, b, 15, 0.3, invert=True, nthreads=nthr, want_perm=want_perm)
+                    d, nh = r[0], r[-1]
+                else:
+                    r = ctx.per_align_pairs_full(wl.params, a, b, niter=10, nthreads=nthr, want_perm=want_perm)
+                    d, nh = r[0], r[-1]
+                best = min(best, time.perf_counter() - t0)
+            print("%s full: %d pairs, %s buffers, perm %d, %d threads: %.1f ms -> %.0f aligned pairs/s "
+                  "(host LAP for %d, median distance %.4f)" % (name, P, "pinned" if pinned else "pageable",
+                                                               want_perm, nthr, best * 1e3, P / best, nh,
+                                                               float(np.median(d))), flush=True)
+    # the two steps apart, on a slice
+    n = min(P, 16384)
+    t0 = time.perf_counter()
+    if name == "lj38":
+        from fastoverlap_b200.utils import indtoEuler
+        fr = ctx.sph_align_pairs(A[:n], B[:n], 15, 0.3, invert=True)[2]
+        t1 = time.perf_counter()
+        _lib.host_refine_spherical(A[:n], B[:n], indtoEuler(fr.reshape(-1, 3), 32).reshape(fr.shape), None, nthr)
+    else:
+        fr = ctx.per_align_pairs(wl.params, A[:n], B[:n])[2]
+        t1 = time.perf_counter()
+        _lib.host_refine_periodic(wl.params, wl.perm, A[:n], B[:n], fr, 10, nthr)
+    t2 = time.perf_counter()
+    print("%s two-step on %d pairs: hot path %.1f ms, host pool on every pair %.1f ms (%.0f pairs/s of host pool)" % (
+        name, n, (t1 - t0) * 1e3, (t2 - t1) * 1e3, n / (t2 - t1)), flush=True)
+    ctx.profile_begin()
+    if name == "lj38":
+        ctx.sph_align_pairs_full(hA.numpy(), hB.numpy(), 15, 0.3, invert=True, nthreads=nthr)
+    else:
+        ctx.per_align_pairs_full(wl.params, hA.numpy(), hB.numpy(), niter=10, nthreads=nthr)
+    print(name, "kernel classes (ms, launches):", ctx.profile_end(), flush=True)

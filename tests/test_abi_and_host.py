@@ -296,89 +296,111 @@ def test_native_periodic_refine_randomized():
     assert (tot > 20).all(), tot   # all three paths took part
 
 
-class _StubCtx(object):
-    """Stands in for the GPU context in the pipeline test: the displacement of a translated, permuted copy is
-    the difference of the centroids."""
-
-    def __init__(self, box, F, fail_at=None):
-        self.box, self.F, self.fail_at, self.calls, self.active = box, F, fail_at, [], 0
-
-    def set_perm(self, perm, natoms):
-        pass
-
-    def per_align_pairs(self, p, pos1, pos2):
-        import threading
-        import time
-        self.active += 1
-        assert self.active == 1   # a context is not re-entrant
-        time.sleep(0.002)
-        self.calls.append((threading.current_thread().name, len(pos1)))
-        if self.fail_at is not None and len(self.calls) > self.fail_at:
-            self.active -= 1
-            raise RuntimeError("device stage failed")
-        fr = (pos2.mean(1) - pos1.mean(1)) / self.box * self.F
-        self.active -= 1
-        return None, None, fr, None, None
-
-
-def test_align_batch_overlaps_device_and_host_stages():
-    """PeriodicAlign.align_batch in chunks (batch.overlap_chunks: device stage on a worker thread, host pool
-    on the caller's): same results as in one piece, ragged last chunk, device-stage errors re-raised."""
-    from fastoverlap_b200.periodic import PeriodicAlign
-    rng = np.random.default_rng(3)
-    N, box, P = 40, np.array([4.0, 4.4, 4.8]), 300
-    groups = [np.arange(25), np.arange(25, 40)]
+def test_host_refine_periodic_subset_and_validation():
+    """fo_host_refine_periodic_subset (the host stage of fo_per_align_pairs_full for the pairs its device
+    screening flags) writes exactly the full call's results at the listed indices and leaves the rest alone;
+    malformed permutation groups are rejected with FO_ERR_INVALID instead of being dereferenced."""
+    import ctypes
+    from fastoverlap_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(5)
+    N, box, F, P = 45, np.array([4.0, 4.5, 5.0]), 24, 16
+    groups = [np.arange(30), np.arange(30, 45)]
     A = rng.uniform(-0.5, 0.5, size=(P, N, 3)) * box
-    B = A + rng.uniform(0, 1, size=(P, 1, 3)) * box + rng.normal(scale=0.03, size=A.shape)
+    shift = rng.uniform(0, 1, size=(P, 1, 3)) * box
+    B = A + shift + rng.normal(scale=0.2, size=A.shape)
     for i in range(P):
         B[i] = B[i][np.concatenate([g[0] + rng.permutation(len(g)) for g in groups])]
-    al = PeriodicAlign(N, box, groups, n=4, ctx=_StubCtx(box, 24))
-    al.fshape = (24, 24, 24)
-    d0, s0, p0 = al.align_batch(A, B, chunk=0, nthreads=2)
-    assert al.ctx.calls == [("MainThread", P)]
-    al._ctx = _StubCtx(box, 24)
-    d1, s1, p1 = al.align_batch(A, B, chunk=64, nthreads=2)
-    assert [c[1] for c in al.ctx.calls] == [64, 64, 64, 64, 44]
-    assert all(c[0] == "fastoverlap-device-stage" for c in al.ctx.calls)
-    assert np.array_equal(d0, d1) and np.array_equal(s0, s1) and np.array_equal(p0, p1)
-    assert np.median(d0) < 0.03 * np.sqrt(3 * N) * 1.5
-    al._ctx = _StubCtx(box, 24, fail_at=2)
-    with pytest.raises(RuntimeError, match="device stage failed"):
-        al.align_batch(A, B, chunk=64, nthreads=2)
+    frac = shift[:, 0, :] / box * F
+    pp = _lib.Context.per_params(N, box, 5, F, 0.3)
+    dist, pm, disp = _lib.host_refine_periodic(pp, groups, A, B, frac, nthreads=2)
+    off, idx, ng = _lib._group_arrays(groups, N)
+    which = np.array([11, 3, 7], np.int64)
+    d2 = np.full(P, -1.0)
+    p2 = np.full((P, N), -1, np.int32)
+    s2 = np.full((P, 3), -1.0)
+    rc = lib.fo_host_refine_periodic_subset(ctypes.byref(pp), _lib._ptr(off), ng, _lib._ptr(idx), _lib._ptr(A),
+                                            _lib._ptr(B), _lib._ptr(frac), _lib._ptr(which), len(which), 10, 2,
+                                            _lib._ptr(d2), _lib._ptr(p2), _lib._ptr(s2))
+    assert rc == 0
+    rest = np.setdiff1d(np.arange(P), which)
+    assert np.array_equal(d2[which], dist[which]) and np.array_equal(p2[which], pm[which])
+    assert np.array_equal(s2[which], disp[which])
+    assert (d2[rest] == -1).all() and (p2[rest] == -1).all()
+    # validation (ADVICE r1): out-of-range index, decreasing offsets, more grouped atoms than atoms
+    for bad_off, bad_idx in ((off, np.where(idx == 44, 45, idx).astype(np.int32)),
+                             (np.array([0, 30, 20], np.int32), idx),
+                             (np.array([0, 30, 50], np.int32), np.zeros(50, np.int32))):
+        rc = lib.fo_host_refine_periodic(ctypes.byref(pp), _lib._ptr(bad_off), ng, _lib._ptr(bad_idx), _lib._ptr(A),
+                                         _lib._ptr(B), _lib._ptr(frac), P, 10, 1, _lib._ptr(d2), None, None)
+        assert rc == -1
+        e = np.zeros((P, 1, 3))
+        rc = lib.fo_host_refine_spherical(_lib._ptr(A), _lib._ptr(B), P, N, _lib._ptr(bad_off), ng, _lib._ptr(bad_idx),
+                                          _lib._ptr(e), 1, 1, _lib._ptr(d2), None, None, None)
+        assert rc == -1
 
 
-def test_spherical_align_batch_chunks_match_one_piece():
-    """SphericalAlign.align_batch through batch.overlap_chunks (device stage stubbed with the known Euler
-    angles): distances and angles identical to the one-piece call, ragged last chunk."""
-    from fastoverlap_b200.spherical import SphericalAlign
+def test_host_refine_spherical_hints():
+    """fo_host_refine_spherical_hint: where hint_ok is set the given permutation is used as is (the device
+    screening proved it optimal), elsewhere the LAP runs; with the LAP's own permutations as hints the results
+    are bit-identical to the un-hinted call."""
+    import ctypes
+    from fastoverlap_b200 import _lib
     from fastoverlap_b200.utils import EulerM
+    lib = _lib.load_library()
     g = golden("spherical_lj38.npz")
     X = g["pos1"] - g["pos1"].mean(0)
-    N, P = len(X), 200
-    rng = np.random.default_rng(3)
+    N, P = len(X), 24
+    rng = np.random.default_rng(8)
     A = np.repeat(X[None], P, 0) + rng.normal(scale=0.05, size=(P, N, 3))
     A -= A.mean(1, keepdims=True)
-    eul, B = np.zeros((P, 2, 3)), np.empty_like(A)
+    B, eul = np.empty_like(A), np.zeros((P, 2, 3))
     for q in range(P):
         a, b, c = rng.uniform(0, 6), rng.uniform(0.2, 2.9), rng.uniform(0, 6)
         B[q] = (X @ EulerM(a, b, c).T)[rng.permutation(N)]
         eul[q, 0] = (a, b, c)
         eul[q, 1] = rng.uniform(0, 3, 3)
+    dist, orient, pm, rmat = _lib.host_refine_spherical(A, B, eul, nthreads=2)
+    assert (orient == 0).all() and abs(np.median(dist) - 0.05 * np.sqrt(3 * N)) < 0.05
+    off, idx, ng = _lib._group_arrays(None, N)
+    hint = np.zeros((P, 2, N), np.int32)
+    hint[:, 0] = pm
+    ok = np.zeros((P, 2), np.int32)
+    ok[::2, 0] = 1   # every other pair carries a hint for the normal orientation; the rest run the LAP
+    d2, o2, p2, r2 = np.empty(P), np.empty(P, np.int32), np.empty((P, N), np.int32), np.empty((P, 3, 3))
+    _lib.host_refine_counters(reset=True)
+    rc = lib.fo_host_refine_spherical_hint(_lib._ptr(A), _lib._ptr(B), P, N, _lib._ptr(off), ng, _lib._ptr(idx),
+                                           _lib._ptr(eul), 2, _lib._ptr(hint), _lib._ptr(ok), 2, _lib._ptr(d2),
+                                           _lib._ptr(o2), _lib._ptr(p2), _lib._ptr(r2))
+    assert rc == 0 and _lib.host_refine_counters()[1] == P // 2
+    assert np.array_equal(d2, dist) and np.array_equal(p2, pm) and np.array_equal(r2, rmat)
+    # a deliberately wrong hint is used as given (the caller vouches for it): the distance gets worse
+    hint[0, 0] = np.roll(pm[0], 1)
+    lib.fo_host_refine_spherical_hint(_lib._ptr(A), _lib._ptr(B), P, N, _lib._ptr(off), ng, _lib._ptr(idx),
+                                      _lib._ptr(eul), 2, _lib._ptr(hint), _lib._ptr(ok), 2, _lib._ptr(d2),
+                                      _lib._ptr(o2), _lib._ptr(p2), _lib._ptr(r2))
+    assert d2[0] > dist[0] + 0.1 and np.array_equal(d2[1:], dist[1:])
+
+
+def test_spherical_align_batch_default_scale():
+    """align_batch with the constructor's default scale=None computes the kernel width from the
+    batch (the reference's averageSeparation rule) instead of raising AttributeError or reusing a stale one."""
+    from fastoverlap_b200.spherical import SphericalAlign
+    g = golden("spherical_lj38.npz")
+    X = g["pos1"] - g["pos1"].mean(0)
     sa = SphericalAlign.__new__(SphericalAlign)
-    sa.orientation, sa.perm, sa.Jmax, sa.scale = "distance", None, 15, 0.3
-    calls = []
+    sa.calcScale, sa.orientation, sa.perm, sa.Jmax = True, "distance", None, 15
+    seen = {}
 
-    def grid_search(X1, X2, perm, invert, want_grid=False, calcCoeffs=None):
-        i = int(np.argmin(np.abs(A - X1[0]).sum((1, 2))))
-        calls.append((i, len(X1)))
-        return eul[i:i + len(X1)]
+    def full_batch(X1, X2, perm, invert, nthreads):   # stands in for the native call (no GPU here)
+        seen["scale"] = sa.scale
+        return np.zeros(len(X1)), np.zeros((len(X1), 2, 3))
 
-    sa._grid_search = grid_search
-    d0, R0 = sa.align_batch(A, B, chunk=0, nthreads=2)
-    d1, R1 = sa.align_batch(A, B, chunk=64, nthreads=2)
-    assert calls == [(0, 200), (0, 64), (64, 64), (128, 64), (192, 8)]
-    assert np.array_equal(d0, d1) and np.array_equal(R0, R1)
-    assert abs(np.median(d0) - 0.05 * np.sqrt(3 * N)) < 0.05
+    sa._full_batch = full_batch
+    A = np.repeat(X[None], 3, 0)
+    d, R = sa.align_batch(A, A, nthreads=1)
+    expect = 2 * sa.averageSeparation(X) / 6
+    assert abs(seen["scale"] - expect) < 1e-12 and d.shape == (3,)
 
 
 def test_native_spherical_refine_matches_reference_and_python():
