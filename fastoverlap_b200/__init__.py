@@ -10,7 +10,7 @@ from ._lib import Context, FastOverlapError, default_context, load_library, libr
 from .periodic import PeriodicAlign
 from .soft import SOFT
 from .spherical import SphericalAlign, SphericalHarmonicAlign
-from .fortran_wrappers import (SphericalAlignFortran, SphericalHarmonicAlignFortran,
+from .wrappers import (SphericalAlignFortran, SphericalHarmonicAlignFortran,
                                PeriodicAlignFortran)
 
 __all__ = ["SphericalAlign", "SphericalHarmonicAlign", "PeriodicAlign", "SOFT",

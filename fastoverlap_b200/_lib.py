@@ -141,6 +141,9 @@ SIGNATURES = {
     "fo_sph_align_pairs_screen_dev": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
                                                      ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_void_p,
                                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fo_host_best_permutation": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64,
+                                                c_void_p, c_void_p, c_void_p]),
+    "fo_host_kearsley": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_f64p, c_void_p]),
     "fo_host_refine_counters": (None, [c_void_p, ctypes.c_int]),
     "fo_host_refine_spherical": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
                                                 ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
@@ -224,6 +227,36 @@ def host_refine_periodic(params, perm, posA, posB, frac_idx, niter=10, nthreads=
     if rc != 0:
         raise FastOverlapError("fo_host_refine_periodic failed (%d)" % rc)
     return dist, pm, disp
+
+
+def host_best_permutation(posA, posB, perm=None, box=None):
+    """perm (N,) such that posB[perm] best matches posA group by group (fo_host_best_permutation; no GPU)."""
+    lib = load_library()
+    posA = _f64(posA).reshape(-1, 3)
+    posB = _f64(posB).reshape(-1, 3)
+    N = posA.shape[0]
+    off, idx, ng = _group_arrays(perm, N)
+    out = np.empty(N, np.int32)
+    b = None if box is None else _f64(box).reshape(3)
+    rc = lib.fo_host_best_permutation(_ptr(posA), _ptr(posB), N, _ptr(off), ng, _ptr(idx), _ptr(b), _ptr(out))
+    if rc != 0:
+        raise FastOverlapError("fo_host_best_permutation failed (%d): invalid permutation groups?" % rc)
+    return out
+
+
+def host_kearsley(x1, x2):
+    """(distance, rotation matrix (3,3)) of the Kearsley fit of x2 onto x1, both re-centred (fo_host_kearsley)."""
+    lib = load_library()
+    x1 = _f64(x1).reshape(-1, 3)
+    x2 = _f64(x2).reshape(-1, 3)
+    if x1.shape != x2.shape:
+        raise ValueError("dimension of arrays does not match")
+    d = ctypes.c_double()
+    R = np.empty((3, 3))
+    rc = lib.fo_host_kearsley(_ptr(x1), _ptr(x2), x1.shape[0], ctypes.byref(d), _ptr(R))
+    if rc != 0:
+        raise FastOverlapError("fo_host_kearsley failed (%d)" % rc)
+    return d.value, R
 
 
 def host_refine_counters(reset=False):

@@ -1005,3 +1005,29 @@ extern "C" int fo_host_refine_spherical_hint(const double* posA, const double* p
   return host_refine_spherical_impl(posA, posB, npairs, natoms, group_offsets, ngroups, atom_idx, euler, norient,
                                     perm_hint, hint_ok, nthreads, dist, orient_out, perm_out, rmat_out);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// The two host steps on their own, for the single-pair drop-in classes (Hungarian / findrotation of
+// utils.py:82-253): same code the pools above run per pair.
+
+extern "C" int fo_host_best_permutation(const double* posA, const double* posB, int64_t natoms,
+                                        const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                                        const double* box, int32_t* perm_out) {
+  if (!posA || !posB || !perm_out) return FO_ERR_INVALID;
+  if (!groups_valid(group_offsets, ngroups, atom_idx, natoms)) return FO_ERR_INVALID;
+  const Groups G = {group_offsets, ngroups, atom_idx};
+  Lap lap;
+  std::vector<double> cost;
+  std::vector<int> c4r, perm((size_t)natoms);
+  best_perm(G, (int)natoms, posA, posB, box, lap, cost, c4r, perm.data());
+  for (int64_t i = 0; i < natoms; ++i) perm_out[i] = perm[i];
+  return FO_OK;
+}
+
+extern "C" int fo_host_kearsley(const double* x1, const double* x2, int64_t natoms, double* dist, double* rmat) {
+  if (!x1 || !x2 || !dist || natoms < 1) return FO_ERR_INVALID;
+  std::vector<int> id((size_t)natoms);
+  for (int64_t i = 0; i < natoms; ++i) id[i] = (int)i;
+  *dist = kearsley((int)natoms, x1, x2, id.data(), rmat);
+  return FO_OK;
+}

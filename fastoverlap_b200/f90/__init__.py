@@ -114,16 +114,17 @@ class _BulkFastOverlap(object):
         pairs = np.array([(i, n1 + j) for i in range(n1) for j in range(n2) if not sym or j >= i])
         _, _, fr, _, _ = ctx.per_align_bank(p, bank, pairs)
         bank.close()
-        disps = fr * al.boxvec / np.array(al.fshape, float)
+        # host stage for all pairs at once (native pool), then the aligned images of the second structures
+        ia, ib = pairs[:, 0], pairs[:, 1] - n1
+        d, perms, disps = _lib.host_refine_periodic(p, al.perm, c1[ia], c2[ib], fr, 10, 0)
+        X2 = al.periodic(np.take_along_axis(c2[ib], perms[:, :, None].astype(int), axis=1) - disps[:, None, :])
         distmat = np.zeros((n1, n2))
         aligned = np.zeros((3 * natoms, n1, n2))
-        for k, (i, jj) in enumerate(pairs):
-            j = jj - n1
-            dist, X1, X2, perm, disp = al.refine(c1[i], c2[j], disps[k:k + 1])
-            distmat[i, j] = dist
-            aligned[:, i, j] = X2.ravel()
-            if sym and j < n1 and i < n2:
-                distmat[j, i] = dist
+        distmat[ia, ib] = d
+        aligned[:, ia, ib] = X2.reshape(len(pairs), -1).T
+        if sym:
+            lower = (ib < n1) & (ia < n2)
+            distmat[ib[lower], ia[lower]] = d[lower]
         return distmat, aligned
 
 

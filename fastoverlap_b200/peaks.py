@@ -1,57 +1,25 @@
-"""Host-side top-k peak extraction: iterative Gaussian fit-and-subtract on an overlap grid that
-the GPU produced (reference fastoverlap/utils.py:347-396; Fortran FINDPEAKS fastutils.f90:475-548).
-Only used on the nrot>1 / npeaks>1 fallback paths (sphericalAlignment.py:196-247,
-periodicAlignment.py:444-451); the arg-max itself comes from the kernels."""
+"""findPeaks -- the reference's top-k peak extraction (utils.py:366-396) on a host grid, run on the device:
+arg-max, Levenberg-Marquardt Gaussian fit on the periodic window, subtraction, repeated (fo_grid_find_peaks,
+csrc/fo_peaks.cu).  The alignment paths (findRotations, findDisps with npeaks > 1) use the fused forms that never
+copy the grid to the host; this entry point serves callers that already hold one."""
 import numpy as np
-from scipy.optimize import curve_fit
 
+from . import _lib
 from .utils import findMax
 
 
-def _gaussian(x, A, mu, *alphax0):
-    """A exp(-(x-x0)^T S (x-x0)) + mu with S upper-triangular packed (utils.py:347-353)."""
-    x = np.atleast_2d(x)
-    dim = len(x)
-    S = np.zeros((dim, dim))
-    S[np.triu_indices(dim)] = alphax0[:-dim]
-    x0 = x - np.array(alphax0[-dim:])[:, None]
-    return A * np.exp(-np.einsum("ik,jk,ij->k", x0, x0, S)) + mu
-
-
-def fitPeak(f, ind, n=2):
-    """Fit a Gaussian to the (2n+1)^dim periodic window around ind (utils.py:355-364)."""
-    dim = f.ndim
-    win = f[np.ix_(*[np.arange(i - n, i + n + 1) % s for i, s in zip(ind, f.shape)])]
-    coords = np.indices((2 * n + 1,) * dim).reshape((dim, -1)) - n
-    p0 = ([win[(n,) * dim], 0.] + [1. if i == j else 0. for i in range(dim) for j in range(i, dim)] +
-          [0.] * dim)
-    return curve_fit(_gaussian, coords, win.ravel(), p0=p0)
-
-
-def findPeaks(a, npeaks=10, width=2):
-    """Up to npeaks (fractional index, amplitude, mean, sigma) by fit-and-subtract (utils.py:366-396)."""
-    f = np.array(a, dtype=float)
-    f -= f.min()
-    dim = f.ndim
-    indices = np.indices(f.shape).reshape((dim, -1))
-    peaks, amplitude, mean, sigma = [], [], [], []
-    for _ in range(npeaks):
-        ind = np.unravel_index(f.argmax(), f.shape)
-        try:
-            popt = fitPeak(f, ind, width)[0]
-            peaks.append(popt[-dim:] + ind)
-            amplitude.append(popt[0])
-            mean.append(popt[1])
-            with np.errstate(invalid="ignore", divide="ignore"):
-                sigma.append((2 * popt[2:-dim]) ** -0.5)
-            popt[-dim:] += ind
-            f.ravel()[:] -= _gaussian(indices, *popt)
-        except (RuntimeError, ValueError):
-            break
-    peaks = np.array(peaks)
-    if len(peaks) == 0:
-        peaks = findMax(a)[None, :]
-        amplitude.append(np.max(a))
-        mean.append(0)
-        sigma.append(np.nan)
-    return peaks, amplitude, mean, sigma, f
+def findPeaks(a, npeaks=10, width=2, ctx=None):
+    """Up to npeaks (fractional indices (k, 3), amplitudes, means, sigmas, residual grid) of a 3-D array.
+    As in the reference a search that finds nothing returns the interpolated maximum (findMax)."""
+    a = np.asarray(a, float)
+    if a.ndim != 3:
+        raise NotImplementedError("the device peak search handles 3-D grids (what both alignment paths produce)")
+    ctx = ctx or _lib.default_context()
+    pk, amp, mean, alpha, nf, res = ctx.grid_find_peaks(a, min(int(npeaks), 64), min(int(width), 4),
+                                                        want_residual=True)
+    k = int(nf[0])
+    if k == 0:
+        return findMax(a)[None, :], [float(a.max())], [0], [np.nan], res[0]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sigma = [(2 * s) ** -0.5 for s in alpha[0, :k]]
+    return pk[0, :k], list(amp[0, :k]), list(mean[0, :k]), sigma, res[0]

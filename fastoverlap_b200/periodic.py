@@ -9,44 +9,40 @@ import numpy as np
 from numpy.linalg import norm
 
 from . import _lib
-from .utils import find_best_permutation, findMax, _next_fast_len
+from .utils import find_best_permutation, _next_fast_len
 
 
 class BasePeriodicAlignment(object):
-    """Host refinement shared by the periodic classes (reference periodicAlignment.py:19-110)."""
+    """Host steps shared by the periodic classes (the reference's base class, periodicAlignment.py:19-110), each a
+    call into the native host library: refine = fo_host_refine_periodic, Hungarian = fo_host_best_permutation."""
 
     def findDisps(self, pos1, pos2):
         raise NotImplementedError
 
     def align(self, pos1, pos2):
-        disps = self.findDisps(pos1, pos2)
-        return self.refine(pos1, pos2, disps)
+        return self.refine(pos1, pos2, self.findDisps(pos1, pos2))
+
 
     def refine(self, x, y, disps, niter=10):
-        """Permutational alignment <-> mean-displacement update (reference :27-80).
+        """Permutational alignment <-> mean-displacement iteration from every candidate displacement, in one
+        native call; the candidate with the smallest final distance is kept (the reference refines only the
+        candidate with the smallest initial distance, :42-45, which can never come out better).
         Returns (distance, X1, X2, perm, disp)."""
-        disps = np.atleast_2d(disps)
-        distperm = [self.Hungarian(x, y - disp[None, :]) + (disp,) for disp in disps]
-        dist, saveperm, disp = min(distperm, key=lambda t: t[0])
-        disp = np.array(disp, dtype=float)
-        perm = saveperm
-        for _ in range(niter):
-            dxs = self.get_disp(x, (y - disp)[saveperm])
-            disp -= dxs.mean(0)
-            perm = self.Hungarian(x, y - disp[None, :])[1]
-            if all(p1 == p2 for p1, p2 in zip(saveperm, perm)):
-                break
-            saveperm = perm
-        dxs = self.get_disp(x, (y - disp)[perm])
-        disp -= dxs.mean(0)
-        pos1 = self.periodic(x, True)
-        pos2 = self.periodic(y[perm] - disp)
-        dist = self.get_dist(pos1, pos2)
-        return dist, pos1, pos2, perm, disp
+        x = np.asarray(x, float).reshape(-1, 3)
+        y = np.asarray(y, float).reshape(-1, 3)
+        F = getattr(self, "fshape", (1,))[0]  # the native call takes displacements in units of box / F
+        frac = np.atleast_2d(np.asarray(disps, float)) / self.boxvec * F
+        k = len(frac)
+        p = _lib.Context.per_params(len(x), self.boxvec, 1, F, 1.0)
+        dist, perm, disp = _lib.host_refine_periodic(p, self.perm, np.broadcast_to(x, (k,) + x.shape),
+                                                     np.broadcast_to(y, (k,) + y.shape), frac, niter, 1)
+        b = int(np.argmin(dist))
+        return float(dist[b]), self.periodic(x, True), self.periodic(y[perm[b]] - disp[b]), perm[b].tolist(), disp[b]
 
     def periodic(self, x, copy=False):
+        """Wrap into the cell centred on the origin (in place unless copy)."""
         if copy:
-            x = x.copy()
+            x = np.array(x, float)
         x -= np.round(x / self.boxvec) * self.boxvec
         return x
 
@@ -57,18 +53,13 @@ class BasePeriodicAlignment(object):
         return norm(self.get_disp(X1, X2))
 
     def cost_matrix(self, X1, X2):
-        """cost[i, j] = minimum-image distance |X1[i] - X2[j]|.  The reference returns the
-        transpose (periodicAlignment.py:94-102) because it targets pele's LAP convention; with the
-        row = X1 convention used by utils.lap this is the orientation that reproduces the
-        reference's documented result."""
-        disps = X1[:, None, :] - X2[None, :, :]
-        disps -= np.round(disps / self.boxvec[None, None, :]) * self.boxvec[None, None, :]
-        return norm(disps, axis=2)
+        """cost[i, j] = minimum-image distance |X1[i] - X2[j]| (row = X1: the orientation that reproduces the
+        reference's documented result)."""
+        return norm(self.periodic(X1[:, None, :] - X2[None, :, :]), axis=2)
 
     def Hungarian(self, X1, X2):
-        _, permlist = find_best_permutation(X1, X2, self.perm, user_cost_matrix=self.cost_matrix)
-        dist = self.get_dist(X1, X2[permlist])
-        return dist, permlist
+        perm = find_best_permutation(X1, X2, self.perm, box=self.boxvec)[1]
+        return self.get_dist(X1, np.asarray(X2)[perm]), perm
 
     def __call__(self, pos1, pos2, *args, **kwargs):
         return self.align(pos1, pos2, *args, **kwargs)
@@ -119,11 +110,39 @@ class PeriodicAlign(BasePeriodicAlignment):
         self.absks = norm(self.ks, axis=0)
         shape = np.array(self.absks.shape) * 2 + 1
         self.fshape = tuple(_next_fast_len(int(d)) for d in shape)
-        self.C1 = None
-        self.C2 = None
-        self.C = None
-        self.f = None
+        self._C1 = self._C2 = None
         self.fabs = None
+
+    # Intermediates the reference keeps as attributes (:362-394, :433-440).  The device path never materialises
+    # them -- only `fabs` comes back -- so they are derived on first access: C1 / C2 on the device from the last
+    # positions, the rest from those on the host (a 19^3 product and one numpy FFT; not on the alignment path).
+    @property
+    def C1(self):
+        if self._C1 is None:
+            self._C1 = self.calcFourierCoeff(self.pos1)
+        return self._C1
+
+    @property
+    def C2(self):
+        if self._C2 is None:
+            self._C2 = self.calcFourierCoeff(self.pos2)
+        return self._C2
+
+    @property
+    def _damp(self):
+        return np.exp(-self.absks ** 2 * self.scale ** 2)
+
+    @property
+    def C(self):
+        return (self.C1 * self.C2.conj() * self._damp).sum(0)
+
+    @property
+    def Csum(self):
+        return float(((np.abs(self.C1) ** 2 + np.abs(self.C2) ** 2) * self._damp[None]).sum() * 0.5 * self.factor)
+
+    @property
+    def f(self):
+        return np.fft.fftn(self.C, self.fshape)
 
     def setScale(self, scale):
         self.scale = scale
@@ -148,18 +167,20 @@ class PeriodicAlign(BasePeriodicAlignment):
             self.pos2[:] = np.asanyarray(pos2)
         p = self._params()
         if Cs is None:
+            self._C1 = self._C2 = None
             bi, bv, fr, grid, st = self.ctx.per_align_pairs(p, self.pos1, self.pos2, want_grid=True)
         else:
-            self.C1, self.C2 = Cs
-            bi, bv, fr, grid, st = self.ctx.per_align_coeffs(p, self.C1, self.C2, want_grid=True)
+            self._C1, self._C2 = np.asarray(Cs[0]), np.asarray(Cs[1])
+            bi, bv, fr, grid, st = self.ctx.per_align_coeffs(p, self._C1, self._C2, want_grid=True)
         self.fabs = grid[0]
         self._best_idx, self._best_val, self._frac_idx = bi[0], bv[0], fr[0]
 
     def findDisps(self, pos1, pos2, Cs=None, npeaks=1, width=2):
         self.setPos(pos1, pos2, Cs)
         if npeaks > 1:
-            # top-k by fit-and-subtract on the device (fo_grid_find_peaks; reference :444-451)
-            pk, _, _, _, nf, _ = self.ctx.grid_find_peaks(self.fabs, npeaks, width)
+            # top-k by fit-and-subtract on the device (fo_grid_find_peaks; reference :444-451); the kernel's
+            # limits (64 peaks, window half-width 4) bound what the reference accepts without limit
+            pk, _, _, _, nf, _ = self.ctx.grid_find_peaks(self.fabs, min(int(npeaks), 64), min(int(width), 4))
             disps = pk[0, :int(nf[0])]
             if len(disps):
                 disps = disps * self.boxvec / self.fabs.shape
@@ -217,29 +238,34 @@ class PeriodicAlign(BasePeriodicAlignment):
         return dists, disps, perms
 
     def alignGroup(self, coords, keepCoords=False, npeaks=1, width=2):
-        """All-vs-all alignment of a list of structures (reference :462-479): structure factors
-        once per structure (device-resident bank), then cross-spectrum + DFT + arg-max per pair."""
+        """All-vs-all alignment of a list of structures (reference :462-479): structure factors once per
+        structure (device-resident bank), cross-spectrum + DFT + arg-max per pair, then the native host pool on
+        all pairs at once.  npeaks > 1: per pair through align (top-k displacements from the device)."""
         coords = np.asarray(coords, float).reshape(-1, self.Natoms, 3)
         nl = len(coords)
+        ii, jj = (a.ravel() for a in np.meshgrid(np.arange(nl), np.arange(nl), indexing="ij"))
         if npeaks > 1:
-            coeffs = [self.calcFourierCoeff(p) for p in coords]
-        p = self._params()
-        bank = self.ctx.per_bank_create(p, coords)
-        ii, jj = np.meshgrid(np.arange(nl), np.arange(nl), indexing="ij")
-        pairs = np.stack([ii.ravel(), jj.ravel()], axis=1)
-        _, _, fr, _, _ = self.ctx.per_align_bank(p, bank, pairs)
-        bank.close()
-        disps = fr * self.boxvec / np.array(self.fshape, float)
-        dists = np.zeros((nl, nl))
-        if keepCoords:
-            aligned = np.empty((2, nl, nl, self.Natoms, self.dim))
-        for k, (i, j) in enumerate(pairs):
-            if npeaks > 1:
-                dist, x1, x2 = self.align(coords[i], coords[j], [coeffs[i], coeffs[j]], npeaks, width)[:3]
-            else:
-                dist, x1, x2 = self.refine(coords[i], coords[j], disps[k:k + 1])[:3]
+            coeffs = [self.calcFourierCoeff(c) for c in coords]
+            res = [self.align(coords[i], coords[j], [coeffs[i], coeffs[j]], npeaks, width)[:3] for i, j in zip(ii, jj)]
+            dists = np.array([r[0] for r in res]).reshape(nl, nl)
+            x1 = np.array([r[1] for r in res])
+            x2 = np.array([r[2] for r in res])
+        else:
+            p = self._params()
+            bank = self.ctx.per_bank_create(p, coords)
+            try:
+                fr = self.ctx.per_align_bank(p, bank, np.stack([ii, jj], axis=1))[2]
+            finally:
+                bank.close()
+            d, perms, disps = _lib.host_refine_periodic(p, self.perm, coords[ii], coords[jj], fr, 10, 0)
+            dists = d.reshape(nl, nl)
             if keepCoords:
-                aligned[0, i, j] = x1
-                aligned[1, i, j] = x2
-            dists[i, j] = dist
-        return (dists, aligned) if keepCoords else dists
+                x1 = self.periodic(coords[ii], True)
+                x2 = self.periodic(np.take_along_axis(coords[jj], perms[:, :, None].astype(int), axis=1) -
+                                   disps[:, None, :])
+        if not keepCoords:
+            return dists
+        aligned = np.empty((2, nl, nl, self.Natoms, self.dim))
+        aligned[0] = x1.reshape(nl, nl, self.Natoms, self.dim)
+        aligned[1] = x2.reshape(nl, nl, self.Natoms, self.dim)
+        return dists, aligned

@@ -42,25 +42,22 @@ class SOFT(object):
 
     @classmethod
     def makeweights(cls, bw):
-        """Quadrature weights (soft.py:64-71)."""
-        j = np.arange(0, 2 * bw).astype(float)[:, None]
-        k = np.arange(0, bw).astype(float)[None, :]
-        fudge = pi / 4 / bw
-        return (2 / (2 * k + 1) * np.sin((2 * j + 1) * (2 * k + 1) * fudge) *
-                np.sin((2 * j + 1) * fudge) / bw).sum(1)
+        """Quadrature weights of the 2 bw beta nodes: w_j = (2 / bw) sin(b_j) sum_k sin((2k+1) b_j) / (2k+1),
+        b_j = pi (2j+1) / 4bw (the reference's makeweights, soft.py:64-71)."""
+        b = pi * (2 * np.arange(2 * bw) + 1.0) / (4 * bw)
+        odd = 2 * np.arange(bw) + 1.0
+        return 2.0 / bw * np.sin(b) * (np.sin(np.outer(b, odd)) / odd).sum(1)
 
     def SOFT(self, data):
-        """Forward transform (soft.py:98-113); host side, not on the alignment path."""
-        Jmax, bw = self.Jmax, self.bw
+        """Forward transform (the reference's round-trip self-check, soft.py:98-113; not on the alignment
+        path): 2-D FFT over (alpha, gamma), then the weighted Wigner-d quadrature over beta as one contraction
+        with the device-computed table (which is zero for l < max(|m1|, |m2|))."""
         data = np.asanyarray(data)
-        assert all(n == self.n for n in data.shape)
-        S2 = np.fft.fft(np.fft.fft(data, axis=0), axis=2) * (2. * bw) ** -2
-        flmm = np.zeros((bw, bw * 2 - 1, bw * 2 - 1), np.complex128)
-        for m1 in range(-Jmax, Jmax + 1):
-            for m2 in range(-Jmax, Jmax + 1):
-                l = max(abs(m1), abs(m2))
-                flmm[l:, m1, m2] = self.Ds[l:, m1, m2].dot(self.weights * S2[m1, :, m2])
-        return flmm
+        if data.shape != (self.n,) * 3:
+            raise ValueError("expected a (%d, %d, %d) grid" % ((self.n,) * 3))
+        S2 = np.fft.fft2(data, axes=(0, 2)) / self.n ** 2
+        m = np.r_[0:self.bw, -(self.bw - 1):0]  # the 2 bw - 1 orders in wrapped (negative-index) storage order
+        return np.einsum("lack,k,akc->lac", self.Ds, self.weights, S2[np.ix_(m % self.n, np.arange(self.n), m % self.n)])
 
     def iSOFT(self, flmm):
         """Inverse transform onto the (2bw)^3 Euler grid (soft.py:115-125) -- on the GPU."""
@@ -69,6 +66,5 @@ class SOFT(object):
         return self.ctx.sph_isoft(flmm, self.Jmax)[0]
 
     def indtoEuler(self, ind):
-        R = self.indFactor * np.atleast_2d(ind)
-        R[:, 1] += 0.5 * pi / self.n
-        return R.squeeze()
+        from .utils import indtoEuler
+        return indtoEuler(ind, self.n)

@@ -14,7 +14,7 @@ from numpy.linalg import norm
 
 from . import _lib
 from .soft import SOFT
-from .utils import find_best_permutation, EulerM, findMax, findrotation, indtoEuler
+from .utils import find_best_permutation, EulerM, indtoEuler
 
 
 def isoft_executed_flops(Jmax, invert=True):
@@ -71,12 +71,13 @@ class BaseSphericalAlignment(object):
         return X.dot(EulerM(*R))
 
     def refine(self, X1, X2, R, permlist=None):
-        """Rotate X2 by the Euler angles R, permute (Hungarian), then Kearsley (reference :118-127)."""
-        permlist = self._perm(len(X1), permlist)
-        X2 = np.dot(X2, EulerM(*R))
-        _, perm = self.Hungarian(X1, X2, permlist)
-        dist, MR = findrotation(X1, X2[perm])
-        return dist, X1, X2[perm].dot(MR.T)
+        """Rotate X2 by the Euler angles R, permute, Kearsley fit (reference :118-127) -- one call into the native
+        host library (fo_host_refine_spherical).  Returns (distance, X1, aligned X2)."""
+        X1 = np.asarray(X1, float)
+        X2 = np.asarray(X2, float)
+        dist, _, perm, rmat = _lib.host_refine_spherical(X1, X2, np.asarray(R, float).reshape(1, 1, 3),
+                                                         self._perm(len(X1), permlist), 1)
+        return float(dist[0]), X1, X2.dot(EulerM(*R))[perm[0]].dot(rmat[0].T)
 
     def sphHarm(self, theta, phi):
         """Y[l, m, j] = Y_lm(theta_j, phi_j) for l <= Jmax (reference :57-65: theta polar, phi azimuth,
@@ -95,36 +96,6 @@ class BaseSphericalAlignment(object):
         return X1, X2
 
     # -- continuous refinement of the rotation (reference :67-113) on the device (fo_refine.cu)
-    def calcWignerMatrices(self, rot):
-        """D^l_{m1m2}(rot) and its gradient as host arrays (reference :67-91).  API compatibility only:
-        the refinement itself (maxOverlap / getEnergyGradient) runs on the device."""
-        from scipy.special import eval_jacobi, gammaln
-        a, b, y = rot
-        Js, m1s, m2s = self.Js, self.m1s, self.m2s
-        Jmax = self.Jmax
-        mu, nu = abs(m1s - m2s), abs(m1s + m2s)
-        s = Js - (mu + nu) // 2
-        xi = np.where(m2s < m1s, (-1.0) ** (m1s - m2s), 1.0)
-        factor = np.exp(0.5 * (gammaln(s + 1) + gammaln(s + mu + nu + 1) - gammaln(s + mu + 1) -
-                               gammaln(s + nu + 1))) * xi
-        sb2, cb2, cb, sb = sin(b / 2), cos(b / 2), cos(b), sin(b)
-        jac = eval_jacobi(s, mu, nu, cb)
-        d = factor * jac * sb2 ** mu * cb2 ** nu
-        gfact = 0.5 * (mu + nu + s + 1.0)
-        gjac = np.where(s > 0, eval_jacobi(np.maximum(s - 1, 0), mu + 1, nu + 1, cb), 0.0) * gfact * -sb
-        with np.errstate(divide="ignore", invalid="ignore"):
-            gd = (factor * gjac * sb2 ** mu * cb2 ** nu +
-                  np.where(mu > 0, factor * jac * sb2 ** (mu - 1.0) * cb2 ** (nu + 1.0) * mu / 2, 0.0) -
-                  np.where(nu > 0, factor * jac * sb2 ** (mu + 1.0) * cb2 ** (nu - 1.0) * nu / 2, 0.0))
-        Ds = np.zeros((Jmax + 1, 2 * Jmax + 1, 2 * Jmax + 1), np.complex128)
-        grad = np.zeros((3,) + Ds.shape, np.complex128)
-        ph = exp(-1j * m1s * a) * exp(-1j * m2s * y)
-        Ds[Js, m1s, m2s] = ph * d
-        grad[0, Js, m1s, m2s] = -1j * m1s * Ds[Js, m1s, m2s]
-        grad[1, Js, m1s, m2s] = ph * gd
-        grad[2, Js, m1s, m2s] = -1j * m2s * Ds[Js, m1s, m2s]
-        return Ds, grad
-
     def getEnergyGradient(self, rot, Ilmm):
         """(E, dE/d(a,b,g)) of the reference's objective (:93-96), evaluated on the device
         (fo_sph_overlap_gradient).  Ilmm is the CONJUGATED coefficient array, as the reference passes it."""
@@ -358,43 +329,6 @@ class SphericalHarmonicAlign(BaseSphericalAlignment):
         self.setJ(Jmax)
         self.perm = perm
 
-    # -- the reference's radial helper functions (:287-329).  API compatibility only: the coefficient
-    # kernel evaluates d_nl(r) in closed form and uses none of these.
-    @classmethod
-    def radialIntegralHarmonic(cls, n, l, rj, sigma, r0):
-        """int_0^inf exp(-(r^2+rj^2)/2s^2) exp(-r^2/2r0^2) i_l(r rj/s^2) r^(n+2) dr (reference :288-299)."""
-        from scipy.special import hyp1f1, gamma
-        a = 0.5 * (3 + n + l)
-        return (sqrt(2.0 ** (3 + n - l) * pi ** 3) * rj ** l * (sigma ** -2 + r0 ** -2) ** (-a) * sigma ** (-2 * l) *
-                hyp1f1(a, 1.5 + l, 0.5 * rj ** 2 * r0 ** 2 / (r0 ** 2 * sigma ** 2 + sigma ** 4)) *
-                gamma(a) / gamma(1.5 + l) * exp(-0.5 * rj ** 2 / sigma ** 2))
-
-    @classmethod
-    def HarmCoeffs(cls, nmax, lmax, r0):
-        """coeffs[n, l, s]: power-series coefficients in r of N_nl r^l L_n^{l+1/2}(r^2/r0^2) (reference :313-319)."""
-        from .utils import coeffs_harmonicBasis
-        coeffs = np.zeros((nmax + 1, lmax + 1, 2 * nmax + lmax + 1))
-        for n in range(nmax + 1):
-            for l in range(lmax + 1):
-                coeffs[n, l, :2 * n + l + 1] = coeffs_harmonicBasis(n, l, r0)
-        return coeffs
-
-    @classmethod
-    def _radial_moments(cls, smax, r0):
-        from scipy.special import gamma
-        ns = np.arange(smax)
-        return gamma(0.5 * (ns + 3)) * 2 ** (0.5 * (ns + 1)) * r0 ** (3 + ns)
-
-    @classmethod
-    def HarmInt(cls, n, l, r0):
-        """int_0^inf N_nl r^l exp(-r^2/2r0^2) L_n^{l+1/2}(r^2/r0^2) r^2 dr (reference :301-311)."""
-        from .utils import coeffs_harmonicBasis
-        return coeffs_harmonicBasis(n, l, r0).dot(cls._radial_moments(2 * n + l + 1, r0))
-
-    @classmethod
-    def HarmInts(cls, nmax, lmax, r0):
-        return cls.HarmCoeffs(nmax, lmax, r0).dot(cls._radial_moments(2 * nmax + lmax + 1, r0))
-
     def setCoeffs(self, nmax=None, Jmax=None, harmscale=None):
         if nmax is not None:
             self.nmax = nmax
@@ -499,29 +433,27 @@ class SphericalHarmonicAlign(BaseSphericalAlignment):
                 maxoverlap / sqrt(dm[:, None] * dm[None, :]))
 
     def alignGroup(self, coords, keepCoords=False):
-        """All-vs-all alignment distances (reference :397-414)."""
+        """All-vs-all alignment distances (reference :397-414): coefficients once per structure in a device
+        bank, contraction + iSOFT + arg-max per pair, then the native host pool on all pairs at once."""
         coords = np.asarray(coords, float)
         nl, natoms = coords.shape[:2]
         X = coords - coords.mean(1)[:, None, :]
         perm = self._perm(natoms)
         self.ctx.set_perm(perm, natoms)
         bank = self.ctx.sph_bank_create(X, self.nmax, self.Jmax, self.harmscale, self.scale)
-        ii, jj = np.meshgrid(np.arange(nl), np.arange(nl), indexing="ij")
-        pairs = np.stack([ii.ravel(), jj.ravel()], axis=1)
+        ii, jj = (a.ravel() for a in np.meshgrid(np.arange(nl), np.arange(nl), indexing="ij"))
         try:
-            bi, bv, fr, avg, _ = self.ctx.sph_align_bank(bank, pairs, invert=True)
+            fr = self.ctx.sph_align_bank(bank, np.stack([ii, jj], axis=1), invert=True)[2]
         finally:
             bank.close()
         Rs = indtoEuler(fr.reshape(-1, 3), self.soft.n).reshape(fr.shape)
-        dists = np.zeros((nl, nl))
-        if keepCoords:
-            aligned = np.empty((2, nl, nl) + coords[0].shape)
-        for k, (i, j) in enumerate(pairs):
-            best = self.refine(X[i], X[j], Rs[k, 0], perm)
-            inv = self.refine(X[i], -X[j], Rs[k, 1], perm)
-            if inv[0] < best[0]:
-                best = inv
-            dists[i, j] = best[0]
-            if keepCoords:
-                aligned[0, i, j], aligned[1, i, j] = best[1], best[2]
-        return (dists, aligned) if keepCoords else dists
+        d, orient, perms, rmats = _lib.host_refine_spherical(X[ii], X[jj], Rs, perm, 0)
+        dists = d.reshape(nl, nl)
+        if not keepCoords:
+            return dists
+        aligned = np.empty((2, nl, nl) + coords[0].shape)
+        aligned[0] = X[ii].reshape((nl, nl) + coords[0].shape)
+        for k in range(len(ii)):
+            sg = -1.0 if orient[k] else 1.0
+            aligned[1, ii[k], jj[k]] = (sg * X[jj[k]]).dot(EulerM(*Rs[k, orient[k]]))[perms[k]].dot(rmats[k].T)
+        return dists, aligned

@@ -412,6 +412,17 @@ int fo_host_refine_spherical_hint(const double* posA, const double* posB, int64_
                                   const int32_t* hint_ok, int nthreads, double* dist, int32_t* orient,
                                   int32_t* perm, double* rmat);
 
+/* The two host steps on their own (one pair), for the single-pair drop-in classes.
+ * fo_host_best_permutation: perm [N] such that posB[perm] best matches posA group by group -- minimum-image
+ * distance costs when box != NULL (periodicAlignment.py:82-110), squared distances otherwise
+ * (find_best_permutation, utils.py:82-167).
+ * fo_host_kearsley: distance after the optimal rotation of x2 onto x1 (both re-centred) and the rotation
+ * matrix rmat [9] (nullable), aligned = x2 . rmat^T (findrotation, utils.py:169-253; alignutils.f90:304-379). */
+int fo_host_best_permutation(const double* posA, const double* posB, int64_t natoms,
+                             const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                             const double* box /*[3] or NULL*/, int32_t* perm);
+int fo_host_kearsley(const double* x1, const double* x2, int64_t natoms, double* dist, double* rmat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@
  * overlap-maximisation path.  Nothing under fastoverlap_b200/ may call this; it is used by
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs only.
  *
- * Parity status: PINNED.  tests/test_oracle_golden.py checks every function here against
+ * Parity status: PINNED.  tests/test_oracle_periodic.py checks every function here against
  * vectors produced by the unmodified reference (oracle/make_golden.py -> tests/golden/), incl.
  * the reference's own known answer for examples/BLJ256 (periodicAlignment.py:609: 1.559).
  *

@@ -1,6 +1,6 @@
 """GPU parity of row a8 (top-k peak extraction by Gaussian fit-and-subtract): grid_peaks_kernel
 through the C ABI vs golden vectors from the unmodified reference's findPeaks (utils.py:366-396,
-scipy curve_fit) and vs the host restatement fastoverlap_b200.peaks.findPeaks.
+scipy curve_fit) and vs the host restatement oracle/peaks_host.py.
 
 Tolerance: the reference's fit stops at MINPACK's ftol = xtol = 1.5e-8; the device solver iterates to
 the local optimum, so positions agree to 1e-4 grid cells and amplitudes to 1e-5 relative (later peaks
@@ -91,9 +91,10 @@ def test_blj256_displacements(ctx):
 
 
 def test_batch_vs_host_restatement(ctx):
-    """P grids in one launch vs scipy curve_fit on the host (fastoverlap_b200.peaks, a restatement of
-    utils.py:347-396)."""
-    from fastoverlap_b200.peaks import findPeaks
+    """P grids in one launch vs scipy curve_fit on the host (oracle/peaks_host.py, a restatement of
+    utils.py:347-396); and the product's findPeaks(host grid) wrapper returns the device result."""
+    from peaks_host import findPeaks
+    from fastoverlap_b200.peaks import findPeaks as dev_find_peaks
     grids = np.array([planted_grid(seed=s, n=(16, 18, 20), k=3) for s in (11, 12, 13)])
     pk, amp, mean, alpha, nf, res = ctx.grid_find_peaks(grids, npeaks=3, width=2, want_residual=True)
     for i in range(3):
@@ -104,6 +105,8 @@ def test_batch_vs_host_restatement(ctx):
         assert np.allclose(amp[i, :k], ha, rtol=AMP_RTOL)
         if nf[i] == k:
             assert np.abs(res[i] - hf).max() < 1e-4 * np.abs(grids[i]).max()
+        dp, da, dm, ds, df = dev_find_peaks(grids[i], npeaks=3, width=2, ctx=ctx)
+        assert np.array_equal(dp, pk[i, :nf[i]]) and np.array_equal(df, res[i])
 
 
 def test_edge_cases(ctx):

@@ -111,6 +111,32 @@ def test_batch_vs_oracle(ctx, N, n, groups):
     assert np.array_equal(bi, bi2) and np.array_equal(bv, bv2) and np.array_equal(fr, fr2)
 
 
+def test_bench_configuration_vs_oracle(ctx):
+    """The bench workload itself (bench.py Blj256: 256 atoms [204, 52], box 5.975206329, n = 9, F = 40, partner
+    = translated + N(0, 0.05^2) + permuted within species): P = 64 pairs in one call -- arg-max, peak value and
+    interpolated maximum of every pair against the oracle, the full 40^3 grid on a subsample."""
+    from fastoverlap_b200 import PeriodicAlign
+    import bench
+    wl = bench.Blj256()
+    A, B, shift = wl.make(64, 5)
+    al = PeriodicAlign(256, wl.box, wl.perm, ctx=ctx)
+    p = al._params()
+    bi, bv, fr, _, st = ctx.per_align_pairs(p, A, B)
+    obi, obv, ofr, _, _ = oracle.per_align_pairs(A, B, wl.box, 9, 40, al.scale, wl.perm, nthreads=0)
+    assert np.all(st == 0)
+    assert np.array_equal(bi, obi)
+    assert np.allclose(bv, obv, rtol=1e-12)
+    assert np.allclose(fr, ofr, atol=1e-7)
+    sub = [0, 17, 42, 63]
+    grids = ctx.per_align_pairs(p, A[sub], B[sub], want_grid=True)[3]
+    ogrids = oracle.per_align_pairs(A[sub], B[sub], wl.box, 9, 40, al.scale, wl.perm, want_grid=True)[3]
+    for i in range(len(sub)):
+        assert rel(grids[i], ogrids[i]) < GRID_RTOL
+    d = fr * wl.box / 40 - shift
+    d -= np.round(d / wl.box) * wl.box
+    assert np.abs(d).max() < wl.box[0] / 40
+
+
 def test_translation_recovery_full_size(ctx):
     """Size-independent property at BASELINE size (N=256, n=9, F=40): a pure translation plus a
     permutation within species is recovered; the overlap peak sits at the translation."""

@@ -157,6 +157,28 @@ def test_batch_vs_oracle(ctx, N, J, sigma, groups):
     ctx.set_perm([np.arange(N)], N)
 
 
+def test_bench_configuration_vs_oracle(ctx):
+    """The bench workload itself (bench.py Lj38: perturbed LJ38 minima, random rotation + permutation, Jmax = 15,
+    sigma = 0.3, both orientations): P = 64 pairs in one call -- arg-max, peak value and interpolated maximum of
+    every (pair, orientation) against the oracle, the full 32^3 grids on a subsample."""
+    import bench
+    wl = bench.Lj38()
+    A, B, _ = wl.make(64, 3)
+    ctx.set_perm([np.arange(38)], 38)
+    bi, bv, fr, _, st = ctx.sph_align_pairs(A, B, 15, 0.3, invert=True)
+    obi, obv, ofr, _, _ = oracle.sph_align_pairs(A, B, 15, 0.3, True, None, nthreads=0)
+    assert np.all(st == 0)
+    assert np.array_equal(bi, obi)
+    assert np.allclose(bv, obv, rtol=1e-11)
+    assert np.allclose(fr, ofr, atol=1e-6)
+    sub = [0, 21, 63]
+    grid = ctx.sph_align_pairs(A[sub], B[sub], 15, 0.3, invert=True, want_grid=True)[3]
+    ogrid = oracle.sph_align_pairs(A[sub], B[sub], 15, 0.3, True, None, want_grid=True)[3]
+    for p in range(len(sub)):
+        for o_ in range(2):
+            assert rel(grid[p, o_], ogrid[p, o_]) < GRID_RTOL
+
+
 def test_rotation_recovery(ctx):
     """sphericalAlignment.py:711-732: random cloud vs rotated + permuted copy, distance ~ 0,
     also for the inverted copy; batched API; BruteOverlap cross-check of the coefficients."""
