@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libfastoverlap_b200.so"
 SOURCES = ["fo_context.cu", "fo_periodic.cu", "fo_spherical.cu", "fo_refine.cu", "fo_peaks.cu", "fo_assign.cu", "fo_host.cu"]
 HOST_ONLY = {"fo_host.cu"}
-HEADERS = [os.path.join(CSRC, "fo_internal.h"), os.path.join(CSRC, "fo_symdft.cuh"),
+HEADERS = [os.path.join(CSRC, "fo_internal.h"), os.path.join(CSRC, "fo_symdft.cuh"), os.path.join(CSRC, "fo_async.cuh"),
            os.path.join(HERE, "..", "include", "fastoverlap_b200.h")]
 
 NVCC_FLAGS = [

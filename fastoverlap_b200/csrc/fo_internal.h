@@ -59,6 +59,8 @@ struct fo_ctx {
 
   // testing hook: force the generic (any-size) kernels instead of the shared-memory fast paths
   bool force_generic = false;
+  // A/B hook: 0 = default transform kernel, 4 = per_xf4_kernel (shared-memory Y -> Z hand-over)
+  int xf_variant = 0;
   // clusters with at least this many atoms use the tensor-core GEMM form of the direct coefficients
   int64_t direct_gemm_min = 64;
 

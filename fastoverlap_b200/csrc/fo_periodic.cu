@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "fo_internal.h"
+#include "fo_async.cuh"
 #include "fo_symdft.cuh"
 
 namespace {
@@ -309,27 +310,7 @@ per_sf2_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   }
 }
 
-// mbarrier primitives (shared::cta): init / arrive by every participating thread / wait on a phase parity
-__device__ __forceinline__ void fo_mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count)
-               : "memory");
-}
-__device__ __forceinline__ void fo_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void fo_mbar_wait(uint64_t* bar, int parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "FO_MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra FO_MBAR_DONE;\n"
-      "bra FO_MBAR_WAIT;\n"
-      "FO_MBAR_DONE:\n"
-      "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-      "r"(parity)
-      : "memory");
-}
+// mbarrier primitives: fo_async.cuh
 
 // ------------------------------------------------------------------------------------------
 // per_sf3_kernel: per_sf2 for n = 9 (M = 10, the default k-grid of a 256-atom cell) without the
@@ -1312,6 +1293,326 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
 }
 
 // ------------------------------------------------------------------------------------------
+// per_xf6_kernel: the transform of per_xf4_kernel with stages Y and Z chained in REGISTERS.
+//
+// A warp owns whole slabs dx.  Stage Y runs transposed: the twiddles are the A operand (rows dy), the slab's
+// E / O data the B operand (columns (l, part)), so a lane's C fragment of row tile mt holds
+//     P, Q at (row dy = 8 mt + g, columns 2 t, 2 t + 1 of column tile ct)  =  (l-slot 4 ct + t + 1, re | im)
+// and V[dy] = P - iQ, V[F - dy] = P + iQ are formed inside the lane (re / im are adjacent columns).  That is
+// exactly the A fragment (row g, k = t) of stage Z's k-step ks = ct: the Z-stage DMMAs take the Y-stage
+// accumulators as operands directly.  Nothing is written to shared memory between Y and Z, no warp ever waits
+// for another one in the slab phase (per_xf4: 14 half-CTA barriers per pair around phases of 18-36 DMMA), and
+// the 40 KB Z-input buffers are gone.  l-slot s = 1..n is harmonic l = s; l = 0 rides in slot n + 1, whose
+// X / Y twiddles are zero (m > K) and whose Z twiddle is the weight of the l = 0 term, so stage X (B
+// operand), stage Y (A operand) and stage Z (B operand) all use ONE register-resident twiddle table
+// (cos / sin (2 pi m d / F) at m = 4 ks + t + 1, d = 8 nt + g is symmetric in the roles of m and d).
+// Twelve warps (three per scheduler, 168 registers each): the F NT (slab, row tile) work items of the slab phase are
+// dealt round-robin, 10 per warp at n = 9, F = 40.
+// The stage-X image of the next pair arrives by one bulk asynchronous copy (cp.async.bulk, SASS UBLKCP)
+// completing on an mbarrier: no thread spends issue slots on it.
+// ------------------------------------------------------------------------------------------
+constexpr int X6_WARPS = 12;
+constexpr int X6_THREADS = X6_WARPS * 32;
+
+struct X6Offsets {
+  int o_red, o_tw, o_x, o_yin, total;  // in doubles
+  X6Offsets() {}
+  X6Offsets(const X4Layout& L, int F) {
+    o_red = 0;                                // 64 doubles: reduction scratch, running maximum, mbarrier
+    o_tw = 64;                                // F double2: twiddles of the parabola neighbours
+    o_x = o_tw + 2 * F;                       // stage-X image [E | O][M][RXp]
+    o_yin = o_x + L.ximg_doubles();           // YIN [F][K2][RY]
+    total = o_yin + F * L.K2 * L.RY;
+  }
+};
+
+template <int KS, int NT, bool WANT_GRID>
+__global__ void __launch_bounds__(X6_THREADS, 1)
+per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Offsets O,
+               const double* __restrict__ ximg, int npairs, int n, int F, XfOut out) {
+  extern __shared__ double sm6[];
+  const int M = L.M, H = L.H, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
+  double* red = sm6 + O.o_red;
+  double2* twz = reinterpret_cast<double2*>(sm6 + O.o_tw);
+  double* XE = sm6 + O.o_x;           // [M][RXp] (index 0: c0)
+  double* XO = XE + (size_t)M * RXp;  // [M][RXp] (index 0 unused)
+  double* YIN = sm6 + O.o_yin;        // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
+  int* sbest = reinterpret_cast<int*>(red + 48);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(red + 56);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const unsigned ximg_bytes = (unsigned)L.ximg_doubles() * 8u;
+
+  if (tid == 0) {
+    fo_mbar_init(xbar, 1);
+    fo_mbar_fence_init();
+    fo_mbar_arrive_expect_tx(xbar, ximg_bytes);
+    fo_bulk_g2s(XE, ximg + (size_t)blockIdx.x * L.ximg_doubles(), ximg_bytes, xbar);
+  }
+  for (int t = tid; t < F; t += X6_THREADS) {
+    double sn, cs;
+    sincospi(2.0 * (double)t / (double)F, &sn, &cs);
+    twz[t] = make_double2(cs, sn);
+  }
+  SymMma<KS, NT> mm;
+  mm.init(n, F, H, lane);
+  // stage-Z cos fragment of the k-step that carries l = 0 (slot n + 1): weight 1/2 at half scale
+  const int ks0 = n >> 2, t0 = n & 3;
+  double bcz[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    bcz[nt] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      if (ks == ks0) bcz[nt] = (t4 == t0 && nt * 8 + g < H) ? 0.5 : mm.bc[ks][nt];
+  }
+  // per-lane geometry of stage Y: B-fragment column (ct, g) and C-init column pair (ct, t4), rows (ks, t4)
+  int ycol[KS], ycol0[KS], yrow[KS];
+#pragma unroll
+  for (int ct = 0; ct < KS; ++ct) {
+    const int sb = 4 * ct + (g >> 1) + 1, sc = 4 * ct + t4 + 1;
+    ycol[ct] = 2 * (sb <= n ? sb : 0) + (g & 1);
+    ycol0[ct] = 2 * (sc <= n ? sc : 0);
+    const int j = 4 * ct + t4 + 1;
+    yrow[ct] = (j <= n ? j : n) * RY;
+  }
+  int xph = 0;
+  __syncthreads();  // the initialised mbarrier is visible to every waiter
+
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    if (tid == 0) *sbest = 0;  // high word of +0.0: |f| >= 0, and only strictly smaller tiles are filtered
+    fo_mbar_wait(xbar, xph);
+    xph ^= 1;
+    __syncthreads();
+    // ---- stage X; tile = 8 rows; row bits: 0 = part, 1 = s  (partners: lane ^ 4, lane ^ 8)
+    for (int tile = warp; tile * 8 < RX; tile += X6_WARPS) {
+      const int row = tile * 8 + g;
+      const bool valid = row < RX;
+      const int r = valid ? row : 0;
+      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
+      const int j = jl / M, l = jl - j * M;
+      const double sgn = part ? -1.0 : 1.0;
+      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
+      const bool store = valid && !(j == 0 && s == 1);
+      double P[NT][2], Q[NT][2];
+      mm.run(XE + RXp + r - g, XO + RXp + r - g, RXp, n, XE[r], lane, P, Q);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = nt * 8 + t4 * 2 + q;
+          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
+          const double ud = fma(sgn, qx, P[nt][q]);   // U[d]   = P - iQ
+          const double um = fma(-sgn, qx, P[nt][q]);  // U[F-d] = P + iQ
+          const double xd = __shfl_xor_sync(0xffffffffu, ud, 8);
+          const double xm = __shfl_xor_sync(0xffffffffu, um, 8);
+          const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
+          const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
+          if (store && d < H) {
+            YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
+            if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
+          }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && pair + (int)gridDim.x < npairs) {  // next pair's image lands during the slab phase
+      fo_fence_proxy_async();
+      fo_mbar_arrive_expect_tx(xbar, ximg_bytes);
+      fo_bulk_g2s(XE, ximg + (size_t)(pair + gridDim.x) * L.ximg_doubles(), ximg_bytes, xbar);
+    }
+    // ---- slabs: stage Y -> stage Z in registers, arg-max at half scale (see per_xf4_kernel).
+    // Work item = (slab dx, row tile mt): F NT items dealt round-robin to the warps (n = 9, F = 40: 120 items,
+    // 10 per warp, the same number on every scheduler).  The running maximum is filtered on the high word
+    // only: sbest holds the high word of a lower bound of the CTA's maximum (native 32-bit shared atomic).
+    double bvh = -1.0;
+    int bi = 0x7fffffff;
+    int thr = 0;  // high word of max(bvh, CTA lower bound): tiles strictly below it cannot hold the maximum
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      const int dy0 = 8 * mt + g;
+      const bool valid0 = dy0 < H, valid1 = valid0 && dy0 != 0 && 2 * dy0 != F;
+      for (int dx = (warp + X6_WARPS - (mt * F) % X6_WARPS) % X6_WARPS; dx < F; dx += X6_WARPS) {
+        const double* Y = YIN + (size_t)dx * K2 * RY;
+        double P[KS][2], Q[KS][2];
+        {
+          double be[KS][KS], bo[KS][KS];
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int ct = 0; ct < KS; ++ct) {
+              be[ks][ct] = Y[yrow[ks] + ycol[ct]];
+              bo[ks][ct] = Y[yrow[ks] + n * RY + ycol[ct]];
+            }
+#pragma unroll
+          for (int ct = 0; ct < KS; ++ct) {
+            const double2 c = *reinterpret_cast<const double2*>(Y + ycol0[ct]);
+            fo_dmma3(P[ct], mm.bc[0][mt], be[0][ct], c.x, c.y);
+            fo_dmma3(Q[ct], mm.bs[0][mt], bo[0][ct], 0.0, 0.0);
+          }
+#pragma unroll
+          for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+            for (int ct = 0; ct < KS; ++ct) {
+              fo_dmma(P[ct], mm.bc[ks][mt], be[ks][ct]);
+              fo_dmma(Q[ct], mm.bs[ks][mt], bo[ks][ct]);
+            }
+        }
+        thr = max(thr, *sbest);
+        // V[dy] = P - iQ (tile 0), V[F - dy] = P + iQ (tile 1): A fragments of stage Z
+        double ar[2][KS], ai[2][KS];
+#pragma unroll
+        for (int ct = 0; ct < KS; ++ct) {
+          ar[0][ct] = P[ct][0] + Q[ct][1];
+          ai[0][ct] = P[ct][1] - Q[ct][0];
+          ar[1][ct] = P[ct][0] - Q[ct][1];
+          ai[1][ct] = P[ct][1] + Q[ct][0];
+        }
+        double A[2][NT][2], B[2][NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            fo_dmma3(A[h][nt], ar[h][0], (0 == ks0) ? bcz[nt] : mm.bc[0][nt], 0.0, 0.0);
+            fo_dmma3(B[h][nt], ai[h][0], mm.bs[0][nt], 0.0, 0.0);
+          }
+#pragma unroll
+        for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const double zc = (ks == ks0) ? bcz[nt] : mm.bc[ks][nt];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              fo_dmma(A[h][nt], ar[h][ks], zc);
+              fo_dmma(B[h][nt], ai[h][ks], mm.bs[ks][nt]);
+            }
+          }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool valid = h == 0 ? valid0 : valid1;
+          const int dy = h == 0 ? dy0 : F - dy0;
+          const int base = (dx * F + dy) * F;
+          // |A| + |B| = max(|A + B|, |A - B|) bit for bit.  Columns d >= H carry zero twiddles (A = B = 0), so
+          // the filter needs no column test: one DADD + one integer max per column.  A tile within 2^-20 of
+          // the running maximum (or holding a NaN) falls through to the exact column-by-column comparison.
+          int chi = 0;
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              chi = max(chi, __double2hiint(fabs(A[h][nt][q]) + fabs(B[h][nt][q])));
+              if (WANT_GRID) {
+                const int d = nt * 8 + t4 * 2 + q;
+                if (valid && d < H) {
+                  double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
+                  grow[d] = 2.0 * fabs(A[h][nt][q] + B[h][nt][q]);
+                  if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * fabs(A[h][nt][q] - B[h][nt][q]);
+                }
+              }
+            }
+          if (valid && chi >= thr) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int d = nt * 8 + t4 * 2 + q;
+                const double g1 = d < H ? fabs(A[h][nt][q] + B[h][nt][q]) : -2.0;
+                const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[h][nt][q] - B[h][nt][q]) : -2.0;
+                better32(bvh, bi, g1, base + d);
+                better32(bvh, bi, g2, base + (F - d));
+              }
+            const int bh = __double2hiint(bvh);
+            if (bh > thr) {
+              thr = bh;
+              atomicMax(sbest, bh);
+            }
+          }
+        }
+      }
+    }
+    double bv = 2.0 * bvh;
+    if (bvh < 0.0) bv = -1.0;
+    // ---- block arg-max (numpy order) and parabola neighbours
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      better32(bv, bi, ov, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red + 32);
+    if (lane == 0) {
+      red[warp] = bv;
+      redi[warp] = bi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      bv = (tid < X6_WARPS) ? red[tid] : -1.0;
+      bi = (tid < X6_WARPS) ? redi[tid] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        better32(bv, bi, ov, oi);
+      }
+      if (tid == 0) {
+        red[16] = bv;
+        *reinterpret_cast<int*>(red + 17) = bi;
+      }
+    }
+    __syncthreads();
+    bv = red[16];
+    bi = *reinterpret_cast<const int*>(red + 17);
+    const bool ok = (bi != 0x7fffffff) && isfinite(bv);
+    const int bx = ok ? bi / (F * F) : 0;
+    const int by = ok ? (bi / F) % F : 0;
+    const int bz = ok ? bi % F : 0;
+    if (warp < 6) {
+      const int ax = warp >> 1, sgn = (warp & 1) ? -1 : 1;
+      int px = bx, py = by, pz = bz;
+      if (ax == 0) px = (bx + sgn + F) % F;
+      if (ax == 1) py = (by + sgn + F) % F;
+      if (ax == 2) pz = (bz + sgn + F) % F;
+      const double* Y = YIN + (size_t)px * K2 * RY;
+      double acc = 0.0;
+      for (int e = lane; e < M * M; e += 32) {
+        const int j = e / M, l = e - j * M;
+        const double2 wj = twz[(j * py) % F], wl = twz[(l * pz) % F];
+        const double sj = wj.y, cj = wj.x, sl_ = wl.y, cl = wl.x;
+        double vr, vi;
+        if (j == 0) {
+          vr = Y[l * 2];
+          vi = Y[l * 2 + 1];
+        } else {
+          const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
+          const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
+          vr = er * cj + oi * sj;   // Re(E cos - i O sin)
+          vi = ei * cj - orr * sj;  // Im
+        }
+        const double term = vr * cl + vi * sl_;
+        acc += (l == 0) ? term : 2.0 * term;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+      if (lane == 0) red[20 + warp] = fabs(acc);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      out.best_idx[3 * (size_t)pair + 0] = bx;
+      out.best_idx[3 * (size_t)pair + 1] = by;
+      out.best_idx[3 * (size_t)pair + 2] = bz;
+      out.best_val[pair] = bv;
+      const int b3[3] = {bx, by, bz};
+      for (int ax = 0; ax < 3; ++ax) {
+        const double y1 = red[20 + 2 * ax], y3 = red[20 + 2 * ax + 1], y2 = bv;
+        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
+        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
+      }
+      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
+    }
+    // no barrier here: the barrier at the top of the loop orders the reuse of red / YIN
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K_xf for fine k-grids (per_xf5_kernel<NT>): the stages of per_xf4_kernel when neither the stage-X
 // image nor YIN (646 KB per pair at n = 16, 4.6 MB at n = 32) fit in shared memory.
 //   * stage X reads its E / O fragments straight from the image per_cross_kernel wrote (L2) and writes
@@ -1767,6 +2068,44 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   int blocks = ctx->prop.multiProcessorCount;
   if ((int64_t)blocks > npairs) blocks = (int)npairs;
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  {  // tensor-core path, stages Y -> Z chained in registers (per_xf6_kernel): n <= 11, F <= 46
+    const X4Layout lay4(n, F, optin);
+    const X6Offsets off6(lay4, F);
+    const size_t smem6 = (size_t)off6.total * 8;
+    const int KS = n / 4 + 1, NT = (lay4.H + 7) / 8;
+    const int code = KS * 10 + NT;
+#define FO_X6_LAUNCH(KS_, NT_)                                                                           \
+  do {                                                                                                   \
+    if (out.grid) {                                                                                      \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, true>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
+      per_xf6_kernel<KS_, NT_, true><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                        \
+          lay4, off6, (const double*)ximg, (int)npairs, n, F, out);                                      \
+    } else {                                                                                             \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, false>,                                 \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
+      per_xf6_kernel<KS_, NT_, false><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                       \
+          lay4, off6, (const double*)ximg, (int)npairs, n, F, out);                                      \
+    }                                                                                                    \
+  } while (0)
+    if (smem6 <= optin && !ctx->force_generic && ctx->xf_variant != 4 && 2 * n + 1 <= 129 &&
+        (code == 11 || code == 12 || code == 22 || code == 23 || code == 33)) {
+      void* ximg = nullptr;
+      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay4.ximg_doubles() * 8, &ximg));
+      fo_prof_scope prof(ctx, FO_PROF_PER_XF);
+      per_cross_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay4, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
+                                                                ky, kz, p->sigma, (double*)ximg);
+      FO_LAUNCH_CHECK(ctx);
+      if (code == 11) FO_X6_LAUNCH(1, 1);
+      else if (code == 12) FO_X6_LAUNCH(1, 2);
+      else if (code == 22) FO_X6_LAUNCH(2, 2);
+      else if (code == 23) FO_X6_LAUNCH(2, 3);
+      else FO_X6_LAUNCH(3, 3);
+      FO_LAUNCH_CHECK(ctx);
+      return FO_OK;
+    }
+#undef FO_X6_LAUNCH
+  }
   {  // tensor-core path: everything resident in shared memory, 1-D transforms as DMMA tiles
     const X4Layout lay4(n, F, optin);
     const size_t smem4 = (size_t)lay4.total * 8;

@@ -30,6 +30,13 @@ __device__ __forceinline__ void fo_dmma(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// d = a b + (c0, c1): the first k-step of a chain takes its initial value as the C operand (no register moves)
+__device__ __forceinline__ void fo_dmma3(double (&d)[2], double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d[0]), "=d"(d[1])
+               : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
 template <int KS, int NT>
 struct SymMma {
   double bc[KS][NT], bs[KS][NT];

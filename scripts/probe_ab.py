@@ -1,5 +1,5 @@
 """A/B probe on one box: device-resident hot-path rate and per-kernel-class CUDA-event times.
-    python scripts/probe_ab.py [blj256|lj38] [pairs] [reps]
+    python scripts/probe_ab.py [blj256|lj38] [pairs] [reps] [option=value ...]
 Library under test: FASTOVERLAP_B200_LIB (default: the in-tree build)."""
 import sys, os
 import numpy as np
@@ -12,6 +12,9 @@ P = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 ctx = fob.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+for kv in sys.argv[4:]:  # library options, e.g. per_xf_variant=4
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 gold = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
 rng = np.random.default_rng(256)
 if wl == "blj256":

@@ -154,8 +154,10 @@ def test_spherical_full_matches_two_step(ctx, jitter, P):
         assert np.median(dist) < 3 * max(jitter, 1e-9) * np.sqrt(3 * 38)
     sa = SphericalAlign(0.3, 15, ctx=ctx)
     db, Rb = sa.align_batch(A, B, nthreads=4)
-    # align_batch re-centres the (already centred) structures: last-bit differences in the coordinates
-    assert np.allclose(db, dist, atol=1e-12) and np.allclose(Rb, eul, atol=1e-9) and np.array_equal(sa.last_perms, pm)
+    # align_batch re-centres the (already centred) structures: last-bit differences in the coordinates.  An exact
+    # copy (jitter 0) has distance sqrt(rounding residue) ~ 1e-9: only the noise level can be compared there
+    assert np.allclose(db, dist, atol=1e-12 if jitter > 0 else 1e-7)
+    assert np.allclose(Rb, eul, atol=1e-9) and np.array_equal(sa.last_perms, pm)
 
 
 def test_spherical_full_groups_and_reference_pair(ctx):
