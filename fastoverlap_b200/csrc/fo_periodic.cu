@@ -1293,50 +1293,140 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
 }
 
 // ------------------------------------------------------------------------------------------
-// per_xf6_kernel: the transform of per_xf4_kernel with stages Y and Z chained in REGISTERS.
+// per_cross6_kernel + per_xf6_kernel: the transform of per_xf4_kernel with every stage in the "transposed" DMMA
+// form (twiddles = A operand, data = B operand) and stages Y and Z chained in REGISTERS.
 //
-// A warp owns whole slabs dx.  Stage Y runs transposed: the twiddles are the A operand (rows dy), the slab's
-// E / O data the B operand (columns (l, part)), so a lane's C fragment of row tile mt holds
-//     P, Q at (row dy = 8 mt + g, columns 2 t, 2 t + 1 of column tile ct)  =  (l-slot 4 ct + t + 1, re | im)
-// and V[dy] = P - iQ, V[F - dy] = P + iQ are formed inside the lane (re / im are adjacent columns).  That is
-// exactly the A fragment (row g, k = t) of stage Z's k-step ks = ct: the Z-stage DMMAs take the Y-stage
-// accumulators as operands directly.  Nothing is written to shared memory between Y and Z, no warp ever waits
-// for another one in the slab phase (per_xf4: 14 half-CTA barriers per pair around phases of 18-36 DMMA), and
-// the 40 KB Z-input buffers are gone.  l-slot s = 1..n is harmonic l = s; l = 0 rides in slot n + 1, whose
-// X / Y twiddles are zero (m > K) and whose Z twiddle is the weight of the l = 0 term, so stage X (B
-// operand), stage Y (A operand) and stage Z (B operand) all use ONE register-resident twiddle table
-// (cos / sin (2 pi m d / F) at m = 4 ks + t + 1, d = 8 nt + g is symmetric in the roles of m and d).
-// Twelve warps (three per scheduler, 168 registers each): the F NT (slab, row tile) work items of the slab phase are
-// dealt round-robin, 10 per warp at n = 9, F = 40.
-// The stage-X image of the next pair arrives by one bulk asynchronous copy (cp.async.bulk, SASS UBLKCP)
-// completing on an mbarrier: no thread spends issue slots on it.
+// * Transposed form.  The C fragment of a tile holds (row d = 8 mt + g, columns 2 t, 2 t + 1) = (re, im) of ONE
+//   complex entry, so P - iQ is formed inside a lane -- and it is never formed by FP64 adds: the previous stage
+//   stores the odd part already multiplied by -i (O' = -iO, a swap and a sign folded into a subtraction order),
+//       U[d] = c0 + sum_m cos(m d) E[m] + sin(m d) O'[m]        (one DMMA chain: P, then V = P + sin O')
+//       U[F - d] = 2 P - U[d]                                   (one DFMA per element)
+//   ncu on the first version (profiles/r02_summary.md): a scalar FP64 instruction issued while other warps stream
+//   DMMAs waits ~45 cycles for the shared FP64 pipe, 28 % of all warp time; what is left are those DFMAs.
+// * The +-ky pairing of stage Y's input is linear, so it is applied to the cross-spectrum (per_cross6_kernel writes
+//   C_E = C(+ky) + C(-ky), C_O = -i (C(+ky) - C(-ky)) in the +-kx-paired form): stage X is a plain GEMM
+//   [F/2+1 rows dx] x [K2 RY columns = YIN slab] with no shuffles, its C fragments go to YIN as 16-byte stores.
+// * Stage Y -> Z: a lane's C fragment of row tile mt, column tile ct holds V at (row dy, l-slot 4 ct + t + 1, re | im)
+//   = exactly the A fragment (row g, k = t) of stage Z's k-step ks = ct.  The Z-stage DMMAs take the Y-stage
+//   accumulators as operands: nothing is written to shared memory between Y and Z, no warp waits for another one
+//   in the slab phase (per_xf4: 14 half-CTA barriers per pair), and the 40 KB Z-input buffers are gone.  l-slot
+//   s = 1..n is harmonic l = s; l = 0 rides in slot n + 1, whose X / Y twiddles are zero (m > K) and whose Z
+//   twiddle is the weight of the l = 0 term, so all three stages use ONE register-resident twiddle table
+//   (cos / sin (2 pi m d / F) at m = 4 ks + t + 1, d = 8 nt + g is symmetric in the roles of m and d).
+// * Arg-max filter on integer pipes: max(|A + B|, |A - B|) = |A| + |B| <= 2 max(|A|, |B|), so a tile whose largest
+//   |A|, |B| high word (sign shifted out) is more than one binade below the running maximum is skipped without
+//   touching the FP64 pipe; the running maximum is shared as a high word (native 32-bit shared atomic).
+// * Twelve warps (three per scheduler, 168 registers): stage-X items (pair of column tiles, row tile) and slab
+//   items (slab, row tile) are dealt round-robin -- n = 9, F = 40: 72 and 120 items, 6 and 10 per warp.
+// * The image of the next pair arrives by one bulk asynchronous copy (cp.async.bulk, SASS UBLKCP) completing on
+//   an mbarrier: no thread spends issue slots on it.
 // ------------------------------------------------------------------------------------------
 constexpr int X6_WARPS = 12;
 constexpr int X6_THREADS = X6_WARPS * 32;
 
-struct X6Offsets {
+struct X6Layout {
+  int M, H, RY, K2, NC, NCP, RXp, SP;
   int o_red, o_tw, o_x, o_yin, total;  // in doubles
-  X6Offsets() {}
-  X6Offsets(const X4Layout& L, int F) {
-    o_red = 0;                                // 64 doubles: reduction scratch, running maximum, mbarrier
-    o_tw = 64;                                // F double2: twiddles of the parabola neighbours
-    o_x = o_tw + 2 * F;                       // stage-X image [E | O][M][RXp]
-    o_yin = o_x + L.ximg_doubles();           // YIN [F][K2][RY]
-    total = o_yin + F * L.K2 * L.RY;
+  X6Layout() {}
+  X6Layout(int n, int F) {
+    M = n + 1;
+    H = F / 2 + 1;
+    RY = 2 * M;
+    K2 = 2 * n + 1;
+    NC = K2 * RY;                // columns of stage X = doubles of one YIN slab [K2][RY]
+    NCP = (NC + 15) / 16;        // pairs of 8-column tiles
+    RXp = 16 * NCP + 8;          // image row pitch, == 8 (mod 16): conflict-free B fragments
+    SP = RXp;                    // YIN slab pitch, == 8 (mod 16): conflict-free 16-byte C-fragment stores
+    o_red = 0;                   // 64 doubles: reduction scratch, running maximum, mbarrier
+    o_tw = 64;                   // F double2: twiddles of the parabola neighbours
+    o_x = o_tw + 2 * F;          // image [E | O'][M][RXp]
+    o_yin = o_x + ximg_doubles();
+    total = o_yin + F * SP;
   }
+  __host__ __device__ int ximg_doubles() const { return 2 * M * RXp; }
 };
+
+// Cross-spectrum of one pair in the form stage X of per_xf6_kernel consumes (a10, periodicAlignment.py:433-438 /
+// fastbulk.f90:441-454,667-683): C[k] = sum_g SA_g[k] conj(SB_g[k]) exp(-|k|^2 sigma^2); paired over +-ky into
+// C_E = C(+j) + C(-j) (row j), C_O = -i (C(+j) - C(-j)) (row n + j), each then paired over +-kx into
+// E[m] = C_s(+m) + C_s(-m), O'[m] = -i (C_s(+m) - C_s(-m)); image [E | O'][m = 0..n][RXp], column = offset in a
+// YIN slab = (row, l, re | im).
+__global__ void __launch_bounds__(256, 3)
+per_cross6_kernel(const __grid_constant__ X6Layout L, const double2* __restrict__ bankA,
+                  const double2* __restrict__ bankB, const long long* __restrict__ pairs, int ngroups, int n,
+                  double kx, double ky, double kz, double sigma, double* __restrict__ ximg) {
+  __shared__ double damp[3 * 129];
+  const int M = L.M, W = 2 * n + 1, RXp = L.RXp, RY = L.RY;
+  const int tid = threadIdx.x;
+  const size_t pair = blockIdx.x;
+  for (int t = tid; t < 3 * W; t += blockDim.x) {
+    const int ax = t / W, m = t - ax * W - n;
+    const double k = (ax == 0 ? kx : (ax == 1 ? ky : kz)) * (double)m;
+    damp[t] = exp(-(k * k) * (sigma * sigma));
+  }
+  __syncthreads();
+  const size_t c_elems = (size_t)W * W * M;
+  const size_t bank_stride = (size_t)ngroups * c_elems;
+  const long long ia = pairs ? pairs[2 * pair] : (long long)pair;
+  const long long ib = pairs ? pairs[2 * pair + 1] : (long long)pair;
+  const double2* SA = bankA + (size_t)ia * bank_stride;
+  const double2* SB = bankB + (size_t)ib * bank_stride;
+  double* XE = ximg + pair * (size_t)L.ximg_doubles();
+  double* XO = XE + (size_t)M * RXp;
+  auto cross = [&](int ix, int iy, int l) {
+    const size_t e = ((size_t)ix * W + iy) * M + l;
+    double re = 0.0, im = 0.0;
+    for (int gq = 0; gq < ngroups; ++gq) {
+      const double2 a = SA[(size_t)gq * c_elems + e], b = SB[(size_t)gq * c_elems + e];
+      re += a.x * b.x + a.y * b.y;
+      im += a.y * b.x - a.x * b.y;
+    }
+    const double dmp = damp[ix] * damp[W + iy] * damp[2 * W + n + l];
+    return make_double2(re * dmp, im * dmp);
+  };
+  for (int item = tid; item < M * M * M; item += blockDim.x) {
+    const int l = item % M;
+    const int j = (item / M) % M;
+    const int m = item / (M * M);
+    const double2 pp = cross(n + m, n + j, l);
+    double2 pm = pp, mp = pp, mm = pp;  // (kx sign, ky sign)
+    if (j) pm = cross(n + m, n - j, l);
+    if (m) mp = cross(n - m, n + j, l);
+    if (m && j) mm = cross(n - m, n - j, l);
+    // ky pairing at kx = +m (cp) and kx = -m (cm): s = E, O
+    double2 ep = pp, em = mp, op = make_double2(0.0, 0.0), om = op;
+    if (j) {
+      ep = make_double2(pp.x + pm.x, pp.y + pm.y);
+      em = make_double2(mp.x + mm.x, mp.y + mm.y);
+      op = make_double2(pp.y - pm.y, pm.x - pp.x);  // -i (pp - pm)
+      om = make_double2(mp.y - mm.y, mm.x - mp.x);
+    }
+    const int colE = j * RY + 2 * l, colO = (n + j) * RY + 2 * l;
+    if (m == 0) {
+      *reinterpret_cast<double2*>(XE + colE) = ep;
+      if (j) *reinterpret_cast<double2*>(XE + colO) = op;
+    } else {
+      *reinterpret_cast<double2*>(XE + (size_t)m * RXp + colE) = make_double2(ep.x + em.x, ep.y + em.y);
+      *reinterpret_cast<double2*>(XO + (size_t)m * RXp + colE) = make_double2(ep.y - em.y, em.x - ep.x);
+      if (j) {
+        *reinterpret_cast<double2*>(XE + (size_t)m * RXp + colO) = make_double2(op.x + om.x, op.y + om.y);
+        *reinterpret_cast<double2*>(XO + (size_t)m * RXp + colO) = make_double2(op.y - om.y, om.x - op.x);
+      }
+    }
+  }
+}
 
 template <int KS, int NT, bool WANT_GRID>
 __global__ void __launch_bounds__(X6_THREADS, 1)
-per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Offsets O,
-               const double* __restrict__ ximg, int npairs, int n, int F, XfOut out) {
+per_xf6_kernel(const __grid_constant__ X6Layout L, const double* __restrict__ ximg, int npairs, int n, int F,
+               XfOut out) {
   extern __shared__ double sm6[];
-  const int M = L.M, H = L.H, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
-  double* red = sm6 + O.o_red;
-  double2* twz = reinterpret_cast<double2*>(sm6 + O.o_tw);
-  double* XE = sm6 + O.o_x;           // [M][RXp] (index 0: c0)
-  double* XO = XE + (size_t)M * RXp;  // [M][RXp] (index 0 unused)
-  double* YIN = sm6 + O.o_yin;        // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
+  const int M = L.M, H = L.H, RXp = L.RXp, RY = L.RY, SP = L.SP, NCP = L.NCP;
+  double* red = sm6 + L.o_red;
+  double2* twz = reinterpret_cast<double2*>(sm6 + L.o_tw);
+  double* XE = sm6 + L.o_x;           // [M][RXp] (row 0: c0)
+  double* XO = XE + (size_t)M * RXp;  // [M][RXp] (row 0 unused)
+  double* YIN = sm6 + L.o_yin;        // [F][SP]: slab = [K2][RY], row j: c0 / E, row n + j: O'
   int* sbest = reinterpret_cast<int*>(red + 48);
   uint64_t* xbar = reinterpret_cast<uint64_t*>(red + 56);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1366,8 +1456,9 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
     for (int ks = 0; ks < KS; ++ks)
       if (ks == ks0) bcz[nt] = (t4 == t0 && nt * 8 + g < H) ? 0.5 : mm.bc[ks][nt];
   }
-  // per-lane geometry of stage Y: B-fragment column (ct, g) and C-init column pair (ct, t4), rows (ks, t4)
-  int ycol[KS], ycol0[KS], yrow[KS];
+  // per-lane geometry: B-fragment rows (ks, t4) of stages X / Y, stage-Y B-fragment column (ct, g) and C-init
+  // column pair (ct, t4)
+  int ycol[KS], ycol0[KS], yrow[KS], xrow[KS];
 #pragma unroll
   for (int ct = 0; ct < KS; ++ct) {
     const int sb = 4 * ct + (g >> 1) + 1, sc = 4 * ct + t4 + 1;
@@ -1375,6 +1466,7 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
     ycol0[ct] = 2 * (sc <= n ? sc : 0);
     const int j = 4 * ct + t4 + 1;
     yrow[ct] = (j <= n ? j : n) * RY;
+    xrow[ct] = (j <= n ? j : n) * RXp;
   }
   int xph = 0;
   __syncthreads();  // the initialised mbarrier is visible to every waiter
@@ -1384,35 +1476,46 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
     fo_mbar_wait(xbar, xph);
     xph ^= 1;
     __syncthreads();
-    // ---- stage X; tile = 8 rows; row bits: 0 = part, 1 = s  (partners: lane ^ 4, lane ^ 8)
-    for (int tile = warp; tile * 8 < RX; tile += X6_WARPS) {
-      const int row = tile * 8 + g;
-      const bool valid = row < RX;
-      const int r = valid ? row : 0;
-      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
-      const int j = jl / M, l = jl - j * M;
-      const double sgn = part ? -1.0 : 1.0;
-      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
-      const bool store = valid && !(j == 0 && s == 1);
-      double P[NT][2], Q[NT][2];
-      mm.run(XE + RXp + r - g, XO + RXp + r - g, RXp, n, XE[r], lane, P, Q);
+    // ---- stage X: item = (pair of column tiles cp, row tile mt); rows dx = 8 mt + g and their mirrors F - dx
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
+    for (int mt = 0; mt < NT; ++mt) {
+      const int dx0 = 8 * mt + g;
+      const bool v0 = dx0 < H, v1 = v0 && dx0 != 0 && 2 * dx0 != F;
+      for (int cp = (warp + X6_WARPS - (mt * NCP) % X6_WARPS) % X6_WARPS; cp < NCP; cp += X6_WARPS) {
+        const double* xe = XE + 16 * cp;
+        const double* xo = XO + 16 * cp;
+        double be[KS][2], bo[KS][2], P[2][2], V[2][2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int d = nt * 8 + t4 * 2 + q;
-          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
-          const double ud = fma(sgn, qx, P[nt][q]);   // U[d]   = P - iQ
-          const double um = fma(-sgn, qx, P[nt][q]);  // U[F-d] = P + iQ
-          const double xd = __shfl_xor_sync(0xffffffffu, ud, 8);
-          const double xm = __shfl_xor_sync(0xffffffffu, um, 8);
-          const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
-          const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
-          if (store && d < H) {
-            YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
-            if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            be[ks][c] = xe[xrow[ks] + 8 * c + g];
+            bo[ks][c] = xo[xrow[ks] + 8 * c + g];
           }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const double2 z = *reinterpret_cast<const double2*>(xe + 8 * c + 2 * t4);
+          fo_dmma3(P[c], mm.bc[0][mt], be[0][c], z.x, z.y);
         }
+#pragma unroll
+        for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) fo_dmma(P[c], mm.bc[ks][mt], be[ks][c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) fo_dmma3(V[c], mm.bs[0][mt], bo[0][c], P[c][0], P[c][1]);
+#pragma unroll
+        for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) fo_dmma(V[c], mm.bs[ks][mt], bo[ks][c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 16 * cp + 8 * c + 2 * t4;
+          if (v0) *reinterpret_cast<double2*>(YIN + (size_t)dx0 * SP + col) = make_double2(V[c][0], V[c][1]);
+          if (v1)
+            *reinterpret_cast<double2*>(YIN + (size_t)(F - dx0) * SP + col) =
+                make_double2(fma(2.0, P[c][0], -V[c][0]), fma(2.0, P[c][1], -V[c][1]));
+        }
+      }
     }
     __syncthreads();
     if (tid == 0 && pair + (int)gridDim.x < npairs) {  // next pair's image lands during the slab phase
@@ -1421,9 +1524,7 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
       fo_bulk_g2s(XE, ximg + (size_t)(pair + gridDim.x) * L.ximg_doubles(), ximg_bytes, xbar);
     }
     // ---- slabs: stage Y -> stage Z in registers, arg-max at half scale (see per_xf4_kernel).
-    // Work item = (slab dx, row tile mt): F NT items dealt round-robin to the warps (n = 9, F = 40: 120 items,
-    // 10 per warp, the same number on every scheduler).  The running maximum is filtered on the high word
-    // only: sbest holds the high word of a lower bound of the CTA's maximum (native 32-bit shared atomic).
+    // Work item = (slab dx, row tile mt), dealt round-robin to the warps.
     double bvh = -1.0;
     int bi = 0x7fffffff;
     int thr = 0;  // high word of max(bvh, CTA lower bound): tiles strictly below it cannot hold the maximum
@@ -1432,8 +1533,8 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
       const int dy0 = 8 * mt + g;
       const bool valid0 = dy0 < H, valid1 = valid0 && dy0 != 0 && 2 * dy0 != F;
       for (int dx = (warp + X6_WARPS - (mt * F) % X6_WARPS) % X6_WARPS; dx < F; dx += X6_WARPS) {
-        const double* Y = YIN + (size_t)dx * K2 * RY;
-        double P[KS][2], Q[KS][2];
+        const double* Y = YIN + (size_t)dx * SP;
+        double P[KS][2], V[KS][2];
         {
           double be[KS][KS], bo[KS][KS];
 #pragma unroll
@@ -1447,83 +1548,105 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
           for (int ct = 0; ct < KS; ++ct) {
             const double2 c = *reinterpret_cast<const double2*>(Y + ycol0[ct]);
             fo_dmma3(P[ct], mm.bc[0][mt], be[0][ct], c.x, c.y);
-            fo_dmma3(Q[ct], mm.bs[0][mt], bo[0][ct], 0.0, 0.0);
           }
 #pragma unroll
           for (int ks = 1; ks < KS; ++ks)
 #pragma unroll
-            for (int ct = 0; ct < KS; ++ct) {
-              fo_dmma(P[ct], mm.bc[ks][mt], be[ks][ct]);
-              fo_dmma(Q[ct], mm.bs[ks][mt], bo[ks][ct]);
-            }
+            for (int ct = 0; ct < KS; ++ct) fo_dmma(P[ct], mm.bc[ks][mt], be[ks][ct]);
+#pragma unroll
+          for (int ct = 0; ct < KS; ++ct) fo_dmma3(V[ct], mm.bs[0][mt], bo[0][ct], P[ct][0], P[ct][1]);
+#pragma unroll
+          for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+            for (int ct = 0; ct < KS; ++ct) fo_dmma(V[ct], mm.bs[ks][mt], bo[ks][ct]);
         }
         thr = max(thr, *sbest);
-        // V[dy] = P - iQ (tile 0), V[F - dy] = P + iQ (tile 1): A fragments of stage Z
-        double ar[2][KS], ai[2][KS];
+        // V[dy] (tile 0) and V[F - dy] = 2 P - V[dy] (tile 1) are the A fragments of stage Z
+        double W2[KS][2];
 #pragma unroll
         for (int ct = 0; ct < KS; ++ct) {
-          ar[0][ct] = P[ct][0] + Q[ct][1];
-          ai[0][ct] = P[ct][1] - Q[ct][0];
-          ar[1][ct] = P[ct][0] - Q[ct][1];
-          ai[1][ct] = P[ct][1] + Q[ct][0];
+          W2[ct][0] = fma(2.0, P[ct][0], -V[ct][0]);
+          W2[ct][1] = fma(2.0, P[ct][1], -V[ct][1]);
         }
         double A[2][NT][2], B[2][NT][2];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            fo_dmma3(A[h][nt], ar[h][0], (0 == ks0) ? bcz[nt] : mm.bc[0][nt], 0.0, 0.0);
-            fo_dmma3(B[h][nt], ai[h][0], mm.bs[0][nt], 0.0, 0.0);
-          }
+        for (int nt = 0; nt < NT; ++nt) {
+          const double zc = (0 == ks0) ? bcz[nt] : mm.bc[0][nt];
+          fo_dmma3(A[0][nt], V[0][0], zc, 0.0, 0.0);
+          fo_dmma3(B[0][nt], V[0][1], mm.bs[0][nt], 0.0, 0.0);
+          fo_dmma3(A[1][nt], W2[0][0], zc, 0.0, 0.0);
+          fo_dmma3(B[1][nt], W2[0][1], mm.bs[0][nt], 0.0, 0.0);
+        }
 #pragma unroll
         for (int ks = 1; ks < KS; ++ks)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             const double zc = (ks == ks0) ? bcz[nt] : mm.bc[ks][nt];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              fo_dmma(A[h][nt], ar[h][ks], zc);
-              fo_dmma(B[h][nt], ai[h][ks], mm.bs[ks][nt]);
-            }
+            fo_dmma(A[0][nt], V[ks][0], zc);
+            fo_dmma(B[0][nt], V[ks][1], mm.bs[ks][nt]);
+            fo_dmma(A[1][nt], W2[ks][0], zc);
+            fo_dmma(B[1][nt], W2[ks][1], mm.bs[ks][nt]);
           }
+        if (WANT_GRID) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const bool valid = h == 0 ? valid0 : valid1;
-          const int dy = h == 0 ? dy0 : F - dy0;
-          const int base = (dx * F + dy) * F;
-          // |A| + |B| = max(|A + B|, |A - B|) bit for bit.  Columns d >= H carry zero twiddles (A = B = 0), so
-          // the filter needs no column test: one DADD + one integer max per column.  A tile within 2^-20 of
-          // the running maximum (or holding a NaN) falls through to the exact column-by-column comparison.
-          int chi = 0;
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              chi = max(chi, __double2hiint(fabs(A[h][nt][q]) + fabs(B[h][nt][q])));
-              if (WANT_GRID) {
-                const int d = nt * 8 + t4 * 2 + q;
-                if (valid && d < H) {
-                  double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
-                  grow[d] = 2.0 * fabs(A[h][nt][q] + B[h][nt][q]);
-                  if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * fabs(A[h][nt][q] - B[h][nt][q]);
-                }
-              }
-            }
-          if (valid && chi >= thr) {
+          for (int h = 0; h < 2; ++h) {
+            const bool valid = h == 0 ? valid0 : valid1;
+            const int dy = h == 0 ? dy0 : F - dy0;
+            double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)(dx * F + dy) * F);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const int d = nt * 8 + t4 * 2 + q;
-                const double g1 = d < H ? fabs(A[h][nt][q] + B[h][nt][q]) : -2.0;
-                const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[h][nt][q] - B[h][nt][q]) : -2.0;
-                better32(bvh, bi, g1, base + d);
-                better32(bvh, bi, g2, base + (F - d));
+                if (valid && d < H) {
+                  grow[d] = 2.0 * fabs(A[h][nt][q] + B[h][nt][q]);
+                  if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * fabs(A[h][nt][q] - B[h][nt][q]);
+                }
               }
-            const int bh = __double2hiint(bvh);
-            if (bh > thr) {
-              thr = bh;
-              atomicMax(sbest, bh);
+          }
+        }
+        // Integer pre-filter: largest |A|, |B| of the lane's 24 accumulators as a high word with the sign shifted
+        // out; |A| + |B| <= 2 max(|A|, |B|), i.e. one binade (0x100000 in the high word) above it at most.
+        unsigned mk = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              mk = __vimax3_u32(mk, (unsigned)__double2hiint(A[h][nt][q]) << 1,
+                                (unsigned)__double2hiint(B[h][nt][q]) << 1);
+        const unsigned thrk = (unsigned)thr << 1;
+        if (mk >= (thrk > 0x200000u ? thrk - 0x200000u : 0u)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const bool valid = h == 0 ? valid0 : valid1;
+            const int dy = h == 0 ? dy0 : F - dy0;
+            const int base = (dx * F + dy) * F;
+            // |A| + |B| = max(|A + B|, |A - B|) bit for bit; columns d >= H carry zero twiddles (A = B = 0).  A
+            // tile within 2^-20 of the running maximum (or holding a NaN) goes on to the exact comparison.
+            int chi = 0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                chi = max(chi, __double2hiint(fabs(A[h][nt][q]) + fabs(B[h][nt][q])));
+            if (valid && chi >= thr) {
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const int d = nt * 8 + t4 * 2 + q;
+                  const double g1 = d < H ? fabs(A[h][nt][q] + B[h][nt][q]) : -2.0;
+                  const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[h][nt][q] - B[h][nt][q]) : -2.0;
+                  better32(bvh, bi, g1, base + d);
+                  better32(bvh, bi, g2, base + (F - d));
+                }
+              const int bh = __double2hiint(bvh);
+              if (bh > thr) {
+                thr = bh;
+                atomicMax(sbest, bh);
+              }
             }
           }
         }
@@ -1571,23 +1694,18 @@ per_xf6_kernel(const __grid_constant__ X4Layout L, const __grid_constant__ X6Off
       if (ax == 0) px = (bx + sgn + F) % F;
       if (ax == 1) py = (by + sgn + F) % F;
       if (ax == 2) pz = (bz + sgn + F) % F;
-      const double* Y = YIN + (size_t)px * K2 * RY;
+      const double* Y = YIN + (size_t)px * SP;
       double acc = 0.0;
       for (int e = lane; e < M * M; e += 32) {
         const int j = e / M, l = e - j * M;
         const double2 wj = twz[(j * py) % F], wl = twz[(l * pz) % F];
-        const double sj = wj.y, cj = wj.x, sl_ = wl.y, cl = wl.x;
-        double vr, vi;
-        if (j == 0) {
-          vr = Y[l * 2];
-          vi = Y[l * 2 + 1];
-        } else {
-          const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
-          const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
-          vr = er * cj + oi * sj;   // Re(E cos - i O sin)
-          vi = ei * cj - orr * sj;  // Im
+        double2 v = *reinterpret_cast<const double2*>(Y + l * 2);  // j = 0: U(ky = 0)
+        if (j) {  // V = E cos + O' sin
+          const double2 ev = *reinterpret_cast<const double2*>(Y + (size_t)j * RY + l * 2);
+          const double2 ov = *reinterpret_cast<const double2*>(Y + (size_t)(n + j) * RY + l * 2);
+          v = make_double2(ev.x * wj.x + ov.x * wj.y, ev.y * wj.x + ov.y * wj.y);
         }
-        const double term = vr * cl + vi * sl_;
+        const double term = v.x * wl.x + v.y * wl.y;
         acc += (l == 0) ? term : 2.0 * term;
       }
 #pragma unroll
@@ -2069,10 +2187,9 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   if ((int64_t)blocks > npairs) blocks = (int)npairs;
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
   {  // tensor-core path, stages Y -> Z chained in registers (per_xf6_kernel): n <= 11, F <= 46
-    const X4Layout lay4(n, F, optin);
-    const X6Offsets off6(lay4, F);
-    const size_t smem6 = (size_t)off6.total * 8;
-    const int KS = n / 4 + 1, NT = (lay4.H + 7) / 8;
+    const X6Layout lay6(n, F);
+    const size_t smem6 = (size_t)lay6.total * 8;
+    const int KS = n / 4 + 1, NT = (lay6.H + 7) / 8;
     const int code = KS * 10 + NT;
 #define FO_X6_LAUNCH(KS_, NT_)                                                                           \
   do {                                                                                                   \
@@ -2080,21 +2197,21 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
       FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, true>,                                  \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
       per_xf6_kernel<KS_, NT_, true><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                        \
-          lay4, off6, (const double*)ximg, (int)npairs, n, F, out);                                      \
+          lay6, (const double*)ximg, (int)npairs, n, F, out);                                            \
     } else {                                                                                             \
       FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, false>,                                 \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
       per_xf6_kernel<KS_, NT_, false><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                       \
-          lay4, off6, (const double*)ximg, (int)npairs, n, F, out);                                      \
+          lay6, (const double*)ximg, (int)npairs, n, F, out);                                            \
     }                                                                                                    \
   } while (0)
     if (smem6 <= optin && !ctx->force_generic && ctx->xf_variant != 4 && 2 * n + 1 <= 129 &&
         (code == 11 || code == 12 || code == 22 || code == 23 || code == 33)) {
       void* ximg = nullptr;
-      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay4.ximg_doubles() * 8, &ximg));
+      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay6.ximg_doubles() * 8, &ximg));
       fo_prof_scope prof(ctx, FO_PROF_PER_XF);
-      per_cross_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay4, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
-                                                                ky, kz, p->sigma, (double*)ximg);
+      per_cross6_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay6, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
+                                                                 ky, kz, p->sigma, (double*)ximg);
       FO_LAUNCH_CHECK(ctx);
       if (code == 11) FO_X6_LAUNCH(1, 1);
       else if (code == 12) FO_X6_LAUNCH(1, 2);
