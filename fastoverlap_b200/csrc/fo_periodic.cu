@@ -1525,7 +1525,7 @@ per_xf6_kernel(const __grid_constant__ X6Layout L, const double* __restrict__ xi
     }
     // ---- slabs: stage Y -> stage Z in registers, arg-max at half scale (see per_xf4_kernel).
     // Work item = (slab dx, row tile mt), dealt round-robin to the warps.
-    double bvh = -1.0;
+    long long bbits = __double_as_longlong(-1.0);  // running maximum (half scale) as a bit pattern
     int bi = 0x7fffffff;
     int thr = 0;  // high word of max(bvh, CTA lower bound): tiles strictly below it cannot hold the maximum
 #pragma unroll
@@ -1605,44 +1605,55 @@ per_xf6_kernel(const __grid_constant__ X6Layout L, const double* __restrict__ xi
               }
           }
         }
-        // Integer pre-filter: largest |A|, |B| of the lane's 24 accumulators as a high word with the sign shifted
-        // out; |A| + |B| <= 2 max(|A|, |B|), i.e. one binade (0x100000 in the high word) above it at most.
-        unsigned mk = 0;
+        // Arg-max filter off the FP64 pipe (a scalar FP64 instruction issued among other warps' DMMAs waits ~45
+        // cycles for the pipe).  Non-negative doubles order like their bit patterns, so:
+        //  1. the largest |A| and the largest |B| of the lane's 24 accumulators are found as high words with the
+        //     sign shifted out (integer max); ONE addition of their upper bounds (high word + 1) bounds every
+        //     |A| + |B| = max(|A + B|, |A - B|) of the item from above;
+        //  2. an item that may reach the running maximum (high word thr) forms |A| + |B| per column (bit for bit
+        //     the larger of the two outputs) and compares bit patterns: the larger output is |A + B| (index d)
+        //     when A and B have the same sign or B = 0, else |A - B| (index F - d); ties take the smaller index.
+        unsigned ma = 0, mb = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              mk = __vimax3_u32(mk, (unsigned)__double2hiint(A[h][nt][q]) << 1,
-                                (unsigned)__double2hiint(B[h][nt][q]) << 1);
-        const unsigned thrk = (unsigned)thr << 1;
-        if (mk >= (thrk > 0x200000u ? thrk - 0x200000u : 0u)) {
+          for (int q = 0; q < 2; ++q) {
+            ma = __vimax3_u32(ma, (unsigned)__double2hiint(A[0][nt][q]) << 1, (unsigned)__double2hiint(A[1][nt][q]) << 1);
+            mb = __vimax3_u32(mb, (unsigned)__double2hiint(B[0][nt][q]) << 1, (unsigned)__double2hiint(B[1][nt][q]) << 1);
+          }
+        const double ubound = __hiloint2double(min((int)(ma >> 1) + 1, 0x7ff00000), 0) +
+                              __hiloint2double(min((int)(mb >> 1) + 1, 0x7ff00000), 0);
+        if (__double2hiint(ubound) >= thr) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const bool valid = h == 0 ? valid0 : valid1;
             const int dy = h == 0 ? dy0 : F - dy0;
             const int base = (dx * F + dy) * F;
-            // |A| + |B| = max(|A + B|, |A - B|) bit for bit; columns d >= H carry zero twiddles (A = B = 0).  A
-            // tile within 2^-20 of the running maximum (or holding a NaN) goes on to the exact comparison.
+            double c[NT][2];
             int chi = 0;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-              for (int q = 0; q < 2; ++q)
-                chi = max(chi, __double2hiint(fabs(A[h][nt][q]) + fabs(B[h][nt][q])));
+              for (int q = 0; q < 2; ++q) {
+                c[nt][q] = fabs(A[h][nt][q]) + fabs(B[h][nt][q]);  // columns d >= H: zero twiddles, A = B = 0
+                chi = max(chi, __double2hiint(c[nt][q]));
+              }
             if (valid && chi >= thr) {
 #pragma unroll
               for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                   const int d = nt * 8 + t4 * 2 + q;
-                  const double g1 = d < H ? fabs(A[h][nt][q] + B[h][nt][q]) : -2.0;
-                  const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[h][nt][q] - B[h][nt][q]) : -2.0;
-                  better32(bvh, bi, g1, base + d);
-                  better32(bvh, bi, g2, base + (F - d));
+                  const long long cb = __double_as_longlong(c[nt][q]);
+                  const bool plus = ((__double2hiint(A[h][nt][q]) ^ __double2hiint(B[h][nt][q])) >= 0) ||
+                                    ((__double_as_longlong(B[h][nt][q]) << 1) == 0);
+                  const int idx = base + (plus ? d : F - d);
+                  if (d < H && (cb > bbits || (cb == bbits && idx < bi))) {
+                    bbits = cb;
+                    bi = idx;
+                  }
                 }
-              const int bh = __double2hiint(bvh);
+              const int bh = (int)(bbits >> 32);
               if (bh > thr) {
                 thr = bh;
                 atomicMax(sbest, bh);
@@ -1652,6 +1663,7 @@ per_xf6_kernel(const __grid_constant__ X6Layout L, const double* __restrict__ xi
         }
       }
     }
+    const double bvh = __longlong_as_double(bbits);
     double bv = 2.0 * bvh;
     if (bvh < 0.0) bv = -1.0;
     // ---- block arg-max (numpy order) and parabola neighbours
