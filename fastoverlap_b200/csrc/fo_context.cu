@@ -190,6 +190,10 @@ extern "C" int fo_set_option(fo_ctx* ctx, const char* name, int64_t value) {
     ctx->force_generic = value != 0;
     return FO_OK;
   }
+  if (strcmp(name, "per_pairs_fused") == 0) {
+    ctx->pairs_fused = value != 0;
+    return FO_OK;
+  }
   if (strcmp(name, "per_xf_variant") == 0) {
     ctx->xf_variant = (int)value;
     return FO_OK;

@@ -61,6 +61,8 @@ struct fo_ctx {
   bool force_generic = false;
   // A/B hook: 0 = default transform kernel, 4 = per_xf4_kernel (shared-memory Y -> Z hand-over)
   int xf_variant = 0;
+  // independent pairs at n = 9: fused structure factors + cross-spectrum (no bank); 0 = bank path (A/B, tests)
+  bool pairs_fused = true;
   // clusters with at least this many atoms use the tensor-core GEMM form of the direct coefficients
   int64_t direct_gemm_min = 64;
 

@@ -536,6 +536,289 @@ per_sf3_kernel(const double* __restrict__ pos, const int32_t* __restrict__ goff,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// per_sfx_kernel: structure factors of BOTH structures of a pair + damped cross-spectrum, written directly as the
+// stage-X image of per_xf6_kernel -- the independent-pairs path never materialises the structure-factor bank
+// (per_sf3 wrote 2 x 116 KB per pair, per_cross6 read them back: a pure HBM pass, 10 % of the step).
+//
+// One CTA per pair runs the tile pipeline of per_sf3_kernel over the units (A, g0), (B, g0), (A, g1), (B, g1), ...
+// A lane's epilogue of per_sf3 yields 13 complex values S(rho i, sig j, l); the same lane holds the same k for
+// every unit, so the cross-spectrum is elementwise per lane:
+//   unit (A, g): S_A -> the lane's stash in TENSOR MEMORY (tcgen05.st; TMEM is otherwise idle in this FP64 path:
+//                13 x 16 bytes per thread = 52 columns per warp in the warp's own lane quarter, 256 columns per
+//                CTA, two CTAs per SM; reading it back costs ~12 cycles where an L2 stash cost ~700);
+//   unit (B, g): C_g = S_A conj(S_B) exp(-|k|^2 sigma^2), paired over +-ky and +-kx by two warp shuffles with the
+//                lanes that hold the other signs (C_E = C(+) + C(-), C_O' = -i (C(+) - C(-))): stored to the
+//                image by the first group, added by the later ones with fire-and-forget reductions (red.add.f64;
+//                always the same thread per address, so the sum has a fixed order).
+// ------------------------------------------------------------------------------------------
+constexpr int SFX_NVAL = 13;
+constexpr int SFX_TMEM_COLS = 256;  // >= 3 warps x 52 columns per lane quarter, power of two
+
+__device__ __forceinline__ void fo_tmem_st_d2(uint32_t taddr, double x, double y) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
+               "r"((uint32_t)__double2loint(x)), "r"((uint32_t)__double2hiint(x)), "r"((uint32_t)__double2loint(y)),
+               "r"((uint32_t)__double2hiint(y))
+               : "memory");
+}
+__device__ __forceinline__ double2 fo_tmem_ld_d2(uint32_t taddr) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return make_double2(__hiloint2double((int)r1, (int)r0), __hiloint2double((int)r3, (int)r2));
+}
+
+__global__ void __launch_bounds__(320, 2)
+per_sfx_kernel(const double* __restrict__ posA, const double* __restrict__ posB, const int32_t* __restrict__ goff,
+               const int32_t* __restrict__ gidx, int ngroups, int natoms, int TA, double kx, double ky, double kz,
+               double sigma, int RXp, double* __restrict__ ximg, size_t ximg_stride) {
+  extern __shared__ double2 sm_phx[];
+  constexpr int n = 9, M = 10, MT = 5, NT = 2, NTL = 3, RY = 2 * M;
+  constexpr int Mp = sf_pitch(M);
+  constexpr int My = sf_pitch(4 * NTL);
+  constexpr int Mz = sf_pitch(M);
+  const size_t pair = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const double* sposA = posA + pair * natoms * 3;
+  const double* sposB = posB + pair * natoms * 3;
+  const double kax[3] = {kx, ky, kz};
+
+  const int offx0 = warp * 2 + ((g >> 1) & 1);
+  int offy[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) offy[mt] = (2 * mt + (g >> 2)) * 2 + (g & 1);
+  const int offxl = warp * 2 + (g >> 2), offzl = 16 + (g & 3);
+
+  const size_t buf_elems = (size_t)TA * (Mp + My + Mz);
+  double2* phx = sm_phx;
+  double2* phy = phx + (size_t)TA * Mp;
+  double2* phz = phy + (size_t)TA * My;
+  auto build_phasors = [&](const double* spos, int a0, int a_end, int buf) {
+    const int ta = min(TA, a_end - a0);
+    const int ta4 = (ta + 3) & ~3;
+    double2* bx = phx + buf * buf_elems;
+    double2* by = phy + buf * buf_elems;
+    double2* bz = phz + buf * buf_elems;
+    for (int t = tid; t < 3 * ta4; t += blockDim.x) {
+      const int a = t / 3, ax = t - 3 * a;
+      const int pitch = ax == 0 ? Mp : (ax == 1 ? My : Mz);
+      double2* row = (ax == 0 ? bx : (ax == 1 ? by : bz)) + a * pitch;
+      if (a < ta) {
+        const int atom = gidx[a0 + a];
+        const double th = kax[ax] * spos[atom * 3 + ax];
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        double c = 1.0, sv = 0.0;
+        row[0] = make_double2(1.0, 0.0);
+        for (int m = 1; m <= n; ++m) {
+          const double cn = c * cs - sv * sn;
+          const double snn = sv * cs + c * sn;
+          c = cn;
+          sv = snn;
+          row[m] = make_double2(c, sv);
+        }
+        for (int m = M; m < pitch; ++m) row[m] = make_double2(0.0, 0.0);
+      } else {
+        for (int m = 0; m < pitch; ++m) row[m] = make_double2(0.0, 0.0);
+      }
+    }
+  };
+  // units u = 2 group + structure (0 = A, 1 = B); empty groups are skipped (they contribute nothing)
+  const int nunits = 2 * ngroups;
+  auto next_unit = [&](int u) {
+    while (u < nunits && goff[(u >> 1) + 1] == goff[u >> 1]) ++u;
+    return u;
+  };
+  __shared__ uint64_t mbar[4];  // full[0], full[1], empty[0], empty[1]
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_done;
+  __shared__ double s_damp[3 * M];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fo_smem_addr(&s_tmem)),
+                 "n"(SFX_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) fo_mbar_init(&mbar[i], blockDim.x);
+    s_done = 0;
+  }
+  if (tid >= 32 && tid < 32 + 3 * M) {
+    const int ax = (tid - 32) / M, m = (tid - 32) - ax * M;
+    const double k = kax[ax] * (double)m;
+    s_damp[tid - 32] = exp(-(k * k) * (sigma * sigma));
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // the warp's stash: its own lane quarter (warp % 4), 52 columns per warp of the quarter
+  const uint32_t tstash = s_tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (4 * SFX_NVAL);
+  const int u_first = next_unit(0);
+  if (u_first < nunits) build_phasors(sposA, goff[u_first >> 1], goff[(u_first >> 1) + 1], 0);
+  fo_mbar_arrive(&mbar[0]);
+  int buf = 0, tile = 0;
+  double* XE = ximg + pair * ximg_stride;
+  double* XO = XE + (size_t)M * RXp;
+  for (int u = u_first; u < nunits; u = next_unit(u + 1)) {
+    const int gq = u >> 1, st = u & 1;
+    const int a_begin = goff[gq], a_end = goff[gq + 1];
+    double acc[MT][NT][2], accl[NTL][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) accl[nt][0] = accl[nt][1] = 0.0;
+    for (int a0 = a_begin; a0 < a_end; a0 += TA, buf ^= 1, ++tile) {
+      const int ta = min(TA, a_end - a0);
+      const int ta4 = (ta + 3) & ~3;
+      // next tile (CTA-uniform): same unit, or the first tile of the next non-empty unit
+      int nb = -1, ne = 0;
+      const double* nspos = st ? sposB : sposA;
+      if (a0 + TA < a_end) {
+        nb = a0 + TA;
+        ne = a_end;
+      } else {
+        const int q = next_unit(u + 1);
+        if (q < nunits) {
+          nb = goff[q >> 1];
+          ne = goff[(q >> 1) + 1];
+          nspos = (q & 1) ? sposB : sposA;
+        }
+      }
+      const bool more = nb >= 0;
+      fo_mbar_wait(&mbar[buf], (tile >> 1) & 1);
+      const double* dx_ = reinterpret_cast<const double*>(phx + buf * buf_elems);
+      const double* dy_ = reinterpret_cast<const double*>(phy + buf * buf_elems);
+      const double* dz_ = reinterpret_cast<const double*>(phz + buf * buf_elems);
+      auto mma_ksteps = [&](int kb, int ke) {
+        for (int k0 = kb; k0 < ke; k0 += 4) {
+          const int a = k0 + t4;
+          const double* xr = dx_ + (size_t)a * Mp * 2;
+          const double* yr = dy_ + (size_t)a * My * 2;
+          const double* zr = dz_ + (size_t)a * Mz * 2;
+          double bz[NT];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) bz[nt] = zr[nt * 8 + g];
+          const double xv = xr[offx0];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const double av = xv * yr[offy[mt]];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) fo_dmma(acc[mt][nt], av, bz[nt]);
+          }
+          const double avl = xr[offxl] * zr[offzl];
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt) fo_dmma(accl[nt], avl, yr[nt * 8 + g]);
+        }
+      };
+      const int kh = ((ta4 >> 2) >> 1) << 2;  // first half of the k-steps
+      mma_ksteps(0, kh);
+      if (more) {
+        if (tile >= 1) fo_mbar_wait(&mbar[2 + (buf ^ 1)], ((tile - 1) >> 1) & 1);
+        build_phasors(nspos, nb, ne, buf ^ 1);
+        fo_mbar_arrive(&mbar[buf ^ 1]);
+      }
+      mma_ksteps(kh, ta4);
+      fo_mbar_arrive(&mbar[2 + buf]);
+    }
+    // ---- epilogue of the unit: S of this lane's 13 k-points -> stash (A) / cross-spectrum into the image (B)
+    const bool firstB = (u == u_first + 1);
+#pragma unroll
+    for (int vi = 0; vi < SFX_NVAL; ++vi) {
+      // value vi: S = (re, im) at k = (rho i, sig j, l); rmask: lane xor to the opposite kx sign (ky: lane ^ 4)
+      double re, im;
+      int i, j, l, rmask;
+      bool rneg, sneg, ok;
+      if (vi < MT * NT) {
+        // main block: lanes g = 4 u + c4 of one (i, j); this lane takes the signs of its own c4
+        const int mt = vi / NT, nt = vi % NT;
+        const int r = (warp * MT + mt) * 8 + g;
+        const int c4 = r & 3, ij = r >> 2;
+        i = ij / M;
+        j = ij - i * M;
+        double v[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int src = (((g & 4) | q) << 2) | t4;
+          v[q][0] = __shfl_sync(0xffffffffu, acc[mt][nt][0], src);
+          v[q][1] = __shfl_sync(0xffffffffu, acc[mt][nt][1], src);
+        }
+        l = nt * 4 + t4;
+        const double rho = (c4 & 2) ? -1.0 : 1.0, sig = (c4 & 1) ? -1.0 : 1.0;
+        re = v[0][0] - rho * sig * v[3][0] - sig * v[1][1] - rho * v[2][1];
+        im = -sig * v[1][0] - rho * v[2][0] - v[0][1] + rho * sig * v[3][1];
+        rneg = (c4 & 2) != 0;
+        sneg = (c4 & 1) != 0;
+        ok = !((rneg && i == 0) || (sneg && j == 0));
+        rmask = 8;
+      } else {
+        // left-over block: i = warp; lane (g, t4) of column tile nt holds (j = 4 nt + t4; cy = 0, 1) of row
+        // (cx = g >> 2, l = 8 + ((g >> 1) & 1), cz = g & 1); the four lanes (cx, cz) of one (j, l) gather all
+        // eight sums v[cx][cy][cz]; this lane takes rho = (cx ? - : +), sig = (cz ? - : +)
+        const int nt = vi - MT * NT;
+        i = warp;
+        const int cxw = g >> 2, lb = (g >> 1) & 1, czw = g & 1;
+        l = 8 + lb;
+        double v[2][2][2];  // [cx][cy][cz]
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+          for (int cz = 0; cz < 2; ++cz) {
+            const int src = ((cx * 4 + lb * 2 + cz) << 2) | t4;
+            v[cx][0][cz] = __shfl_sync(0xffffffffu, accl[nt][0], src);
+            v[cx][1][cz] = __shfl_sync(0xffffffffu, accl[nt][1], src);
+          }
+        const int jj = nt * 4 + t4;
+        const double rho = cxw ? -1.0 : 1.0, sig = czw ? -1.0 : 1.0;
+        re = v[0][0][0] - rho * sig * v[1][1][0] - sig * v[0][1][1] - rho * v[1][0][1];
+        im = -sig * v[0][1][0] - rho * v[1][0][0] - v[0][0][1] + rho * sig * v[1][1][1];
+        rneg = cxw != 0;
+        sneg = czw != 0;
+        ok = jj < M && !((rneg && i == 0) || (sneg && jj == 0));
+        j = jj < M ? jj : M - 1;
+        rmask = 16;
+      }
+      if (st == 0) {
+        fo_tmem_st_d2(tstash + 4 * vi, re, im);
+        continue;
+      }
+      const double2 sa = fo_tmem_ld_d2(tstash + 4 * vi);
+      const double dmp = s_damp[i] * s_damp[M + j] * s_damp[2 * M + l];
+      const double2 c = make_double2((sa.x * re + sa.y * im) * dmp, (sa.y * re - sa.x * im) * dmp);  // S_A conj(S_B)
+      const double wx = __shfl_xor_sync(0xffffffffu, c.x, 4), wy = __shfl_xor_sync(0xffffffffu, c.y, 4);
+      double2 a = c;
+      if (j > 0) a = sneg ? make_double2(wy - c.y, c.x - wx) : make_double2(c.x + wx, c.y + wy);
+      const double px = __shfl_xor_sync(0xffffffffu, a.x, rmask), py = __shfl_xor_sync(0xffffffffu, a.y, rmask);
+      double2 r = a;
+      if (i > 0) r = rneg ? make_double2(py - a.y, a.x - px) : make_double2(a.x + px, a.y + py);
+      if (ok) {
+        double* dst = (rneg ? XO : XE) + (size_t)i * RXp + ((sneg ? n + j : j) * RY + 2 * l);
+        if (firstB) {
+          *reinterpret_cast<double2*>(dst) = r;
+        } else {
+          atomicAdd(dst, r.x);
+          atomicAdd(dst + 1, r.y);
+        }
+      }
+    }
+    if (st == 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  // the last warp to finish returns the CTA's tensor memory (no CTA-wide barrier: warps drift by half a tile)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  int last = 0;
+  if (lane == 0) last = atomicAdd(&s_done, 1) == (int)(blockDim.x >> 5) - 1;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(SFX_TMEM_COLS) : "memory");
+  }
+}
+
 // Expand the half-grid bank to the reference's full (2n+1)^3 layout (calcFourierCoeff output).
 __global__ void per_expand_kernel(const double2* __restrict__ bank, double2* __restrict__ full,
                                   int n, size_t nsg) {
@@ -2189,6 +2472,47 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
   return FO_OK;
 }
 
+// per_xf6_kernel applies: n <= 11, F <= 46, everything resident in shared memory
+bool xf6_applies(fo_ctx* ctx, int n, int F, X6Layout* lay, int* code_out) {
+  const X6Layout lay6(n, F);
+  const int KS = n / 4 + 1, NT = (lay6.H + 7) / 8;
+  const int code = KS * 10 + NT;
+  if (lay) *lay = lay6;
+  if (code_out) *code_out = code;
+  return (size_t)lay6.total * 8 <= ctx->prop.sharedMemPerBlockOptin && !ctx->force_generic && ctx->xf_variant != 4 &&
+         2 * n + 1 <= 129 && (code == 11 || code == 12 || code == 22 || code == 23 || code == 33);
+}
+
+// transform + arg-max of npairs stage-X images (per_cross6_kernel / per_sfx_kernel wrote them)
+int launch_xf6_image(fo_ctx* ctx, const X6Layout& lay6, int code, const double* ximg, int64_t npairs, int n, int F,
+                     XfOut out) {
+  const size_t smem6 = (size_t)lay6.total * 8;
+  int blocks = ctx->prop.multiProcessorCount;
+  if ((int64_t)blocks > npairs) blocks = (int)npairs;
+#define FO_X6_LAUNCH(KS_, NT_)                                                                           \
+  do {                                                                                                   \
+    if (out.grid) {                                                                                      \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, true>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
+      per_xf6_kernel<KS_, NT_, true><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                        \
+          lay6, ximg, (int)npairs, n, F, out);                                                           \
+    } else {                                                                                             \
+      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, false>,                                 \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
+      per_xf6_kernel<KS_, NT_, false><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                       \
+          lay6, ximg, (int)npairs, n, F, out);                                                           \
+    }                                                                                                    \
+  } while (0)
+  if (code == 11) FO_X6_LAUNCH(1, 1);
+  else if (code == 12) FO_X6_LAUNCH(1, 2);
+  else if (code == 22) FO_X6_LAUNCH(2, 2);
+  else if (code == 23) FO_X6_LAUNCH(2, 3);
+  else FO_X6_LAUNCH(3, 3);
+#undef FO_X6_LAUNCH
+  FO_LAUNCH_CHECK(ctx);
+  return FO_OK;
+}
+
 int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const double2* d_bankB,
               const long long* d_pairs, int64_t npairs, XfOut out) {
   if (npairs == 0) return FO_OK;
@@ -2198,42 +2522,18 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   int blocks = ctx->prop.multiProcessorCount;
   if ((int64_t)blocks > npairs) blocks = (int)npairs;
   const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
-  {  // tensor-core path, stages Y -> Z chained in registers (per_xf6_kernel): n <= 11, F <= 46
-    const X6Layout lay6(n, F);
-    const size_t smem6 = (size_t)lay6.total * 8;
-    const int KS = n / 4 + 1, NT = (lay6.H + 7) / 8;
-    const int code = KS * 10 + NT;
-#define FO_X6_LAUNCH(KS_, NT_)                                                                           \
-  do {                                                                                                   \
-    if (out.grid) {                                                                                      \
-      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, true>,                                  \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
-      per_xf6_kernel<KS_, NT_, true><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                        \
-          lay6, (const double*)ximg, (int)npairs, n, F, out);                                            \
-    } else {                                                                                             \
-      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf6_kernel<KS_, NT_, false>,                                 \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));       \
-      per_xf6_kernel<KS_, NT_, false><<<blocks, X6_THREADS, smem6, ctx->stream>>>(                       \
-          lay6, (const double*)ximg, (int)npairs, n, F, out);                                            \
-    }                                                                                                    \
-  } while (0)
-    if (smem6 <= optin && !ctx->force_generic && ctx->xf_variant != 4 && 2 * n + 1 <= 129 &&
-        (code == 11 || code == 12 || code == 22 || code == 23 || code == 33)) {
+  {  // tensor-core path, stages Y -> Z chained in registers (per_xf6_kernel)
+    X6Layout lay6;
+    int code = 0;
+    if (xf6_applies(ctx, n, F, &lay6, &code)) {
       void* ximg = nullptr;
       FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay6.ximg_doubles() * 8, &ximg));
       fo_prof_scope prof(ctx, FO_PROF_PER_XF);
       per_cross6_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay6, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
                                                                  ky, kz, p->sigma, (double*)ximg);
       FO_LAUNCH_CHECK(ctx);
-      if (code == 11) FO_X6_LAUNCH(1, 1);
-      else if (code == 12) FO_X6_LAUNCH(1, 2);
-      else if (code == 22) FO_X6_LAUNCH(2, 2);
-      else if (code == 23) FO_X6_LAUNCH(2, 3);
-      else FO_X6_LAUNCH(3, 3);
-      FO_LAUNCH_CHECK(ctx);
-      return FO_OK;
+      return launch_xf6_image(ctx, lay6, code, (const double*)ximg, npairs, n, F, out);
     }
-#undef FO_X6_LAUNCH
   }
   {  // tensor-core path: everything resident in shared memory, 1-D transforms as DMMA tiles
     const X4Layout lay4(n, F, optin);
@@ -2346,6 +2646,43 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
   return FO_OK;
 }
 
+// Independent pairs at the default k-grid of a 256-atom cell (n = 9): per_sfx_kernel (structure factors of both
+// structures + cross-spectrum, no bank) -> per_xf6_kernel.
+bool pairs_fused_applies(fo_ctx* ctx, const fo_per_params* p) {
+  return p->nwave == 9 && ctx->pairs_fused && xf6_applies(ctx, (int)p->nwave, (int)p->nfspace, nullptr, nullptr);
+}
+
+int launch_pairs_fused(fo_ctx* ctx, const fo_per_params* p, const double* d_posA, const double* d_posB,
+                       int64_t npairs, XfOut out) {
+  if (npairs == 0) return FO_OK;
+  const int n = (int)p->nwave, F = (int)p->nfspace;
+  const int ngroups = (int)ctx->h_goff.size() - 1;
+  X6Layout lay6;
+  int code = 0;
+  xf6_applies(ctx, n, F, &lay6, &code);
+  // atom tile as in launch_sf (per_sf3_kernel): two CTAs per SM, evened out over the tiles of the largest group
+  const size_t row_bytes = (size_t)(sf_pitch(10) + sf_pitch(12) + sf_pitch(10)) * 16;
+  int TA = (int)((size_t)113 * 1024 / (2 * row_bytes)) & ~3;
+  int gmax = 1;
+  for (int q = 0; q < ngroups; ++q) gmax = std::max(gmax, (int)(ctx->h_goff[q + 1] - ctx->h_goff[q]));
+  const int ntile = (gmax + TA - 1) / TA;
+  TA = std::max(16, std::min(TA, (((gmax + ntile - 1) / ntile) + 3) & ~3));
+  const size_t smem = (size_t)2 * TA * row_bytes;
+  void* ximg = nullptr;
+  FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay6.ximg_doubles() * 8, &ximg));
+  const double kx = kTwoPi / p->box[0], ky = kTwoPi / p->box[1], kz = kTwoPi / p->box[2];
+  {
+    fo_prof_scope prof(ctx, FO_PROF_PER_SF);
+    FO_CUDA(ctx, cudaFuncSetAttribute(per_sfx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    per_sfx_kernel<<<(unsigned)npairs, 320, smem, ctx->stream>>>(
+        d_posA, d_posB, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, TA, kx, ky, kz, p->sigma, lay6.RXp,
+        (double*)ximg, (size_t)lay6.ximg_doubles());
+    FO_LAUNCH_CHECK(ctx);
+  }
+  fo_prof_scope prof(ctx, FO_PROF_PER_XF);
+  return launch_xf6_image(ctx, lay6, code, (const double*)ximg, npairs, n, F, out);
+}
+
 size_t bank_elems_per_struct(fo_ctx* ctx, const fo_per_params* p) {
   const size_t W = 2 * p->nwave + 1, M = p->nwave + 1;
   return (ctx->h_goff.size() - 1) * W * W * M;
@@ -2389,21 +2726,27 @@ extern "C" int fo_per_align_pairs_dev(fo_ctx* ctx, const fo_per_params* p, const
   // device-resident input: no copies to overlap, so the chunks only bound the scratch -- three times the bank
   // budget of the host-buffer pipeline (fewer kernel boundaries: BLJ256 9.80 -> 9.63 ms per 16384 pairs)
   const int64_t chunk = chunk_pairs(ctx, p, npairs, false, 2304);
+  const bool fused = pairs_fused_applies(ctx, p);  // no bank: structure factors -> cross-spectrum in one kernel
   void* bank = nullptr;
-  if (npairs > 0) FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
+  if (npairs > 0 && !fused) FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
   double2* bankA = (double2*)bank;
   double2* bankB = bankA + (size_t)chunk * per_struct;
   const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
   for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
     const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
-    FO_CHECK(launch_sf(ctx, p, d_posA + (size_t)p0 * p->natoms * 3, np, bankA));
-    FO_CHECK(launch_sf(ctx, p, d_posB + (size_t)p0 * p->natoms * 3, np, bankB));
     XfOut out;
     out.best_idx = (long long*)d_best_idx + 3 * p0;
     out.best_val = d_best_val + p0;
     out.frac_idx = d_frac_idx + 3 * p0;
     out.grid = d_grid_out ? d_grid_out + (size_t)p0 * F3 : nullptr;
     out.status = d_status ? d_status + p0 : nullptr;
+    if (fused) {
+      FO_CHECK(launch_pairs_fused(ctx, p, d_posA + (size_t)p0 * p->natoms * 3, d_posB + (size_t)p0 * p->natoms * 3,
+                                  np, out));
+      continue;
+    }
+    FO_CHECK(launch_sf(ctx, p, d_posA + (size_t)p0 * p->natoms * 3, np, bankA));
+    FO_CHECK(launch_sf(ctx, p, d_posB + (size_t)p0 * p->natoms * 3, np, bankB));
     FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
   }
   return FO_OK;
@@ -2500,7 +2843,9 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
   const size_t pos_bytes = (size_t)chunk * N * 3 * 8;
   const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
   void *bank, *dA, *dB, *dOut, *dGrid = nullptr, *hA, *hB, *dFull = nullptr;
-  FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
+  const bool fused = pairs_fused_applies(ctx, p);  // no bank: structure factors -> cross-spectrum in one kernel
+  bank = nullptr;
+  if (!fused) FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
   // two position buffers per side so the copy of chunk c+1 overlaps the kernels of chunk c
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSA, 2 * pos_bytes, &dA));
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
@@ -2585,11 +2930,16 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
     const double* cA = (const double*)((char*)dA + buf * pos_bytes);
     const double* cB = (const double*)((char*)dB + buf * pos_bytes);
     FO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[buf], 0));
-    FO_CHECK(launch_sf(ctx, p, cA, np, bankA));
-    FO_CHECK(launch_sf(ctx, p, cB, np, bankB));
-    if (!full) FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
     XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
-    FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+    if (fused) {
+      FO_CHECK(launch_pairs_fused(ctx, p, cA, cB, np, out));
+      if (!full) FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+    } else {
+      FO_CHECK(launch_sf(ctx, p, cA, np, bankA));
+      FO_CHECK(launch_sf(ctx, p, cB, np, bankB));
+      if (!full) FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
+      FO_CHECK(launch_xf(ctx, p, bankA, bankB, nullptr, np, out));
+    }
     if (full) {  // screening + permutation <-> displacement loop on the device (reads the positions again)
       char* f = (char*)dFull;
       FO_CHECK(fo_per_assign_run_dev(ctx, p, cA, cB, out.frac_idx, np, full->niter, (double*)f,
