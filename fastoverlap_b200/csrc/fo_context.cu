@@ -138,6 +138,7 @@ extern "C" void fo_destroy(fo_ctx* ctx) {
   if (ctx->d_gidx) cudaFree(ctx->d_gidx);
   if (ctx->wig.d_table) cudaFree(ctx->wig.d_table);
   if (ctx->wig.d_packed) cudaFree(ctx->wig.d_packed);
+  if (ctx->wig.d_packed4) cudaFree(ctx->wig.d_packed4);
   if (ctx->refine_tab.ptr) cudaFree(ctx->refine_tab.ptr);
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -192,6 +193,10 @@ extern "C" int fo_set_option(fo_ctx* ctx, const char* name, int64_t value) {
   }
   if (strcmp(name, "per_pairs_fused") == 0) {
     ctx->pairs_fused = value != 0;
+    return FO_OK;
+  }
+  if (strcmp(name, "sph_isoft_variant") == 0) {
+    ctx->isoft_variant = (int)value;
     return FO_OK;
   }
   if (strcmp(name, "per_xf_variant") == 0) {

@@ -20,6 +20,7 @@ struct fo_wigner_cache {
   double* d_table = nullptr;   // dense Dt[m2][m1][l][k], see fo_spherical.cu
   double* d_packed = nullptr;  // per-chunk shell-ordered slices for sph_isoft3_kernel
   int packed_kc = 0;           // beta planes per chunk of d_packed (0: none)
+  double* d_packed4 = nullptr; // slices of four planes (sph_isoft4_kernel<4, ...>, odd Jmax <= 15)
   size_t bytes = 0;
   bool kmajor = false;         // large bandwidths: plane-major layout DtK[k][m2][m1][l]
 };
@@ -61,6 +62,8 @@ struct fo_ctx {
   bool force_generic = false;
   // A/B hook: 0 = default transform kernel, 4 = per_xf4_kernel (shared-memory Y -> Z hand-over)
   int xf_variant = 0;
+  // A/B hook: 0 = default iSOFT kernel, 3 = sph_isoft3_kernel (stage A -> shared memory -> stage B)
+  int isoft_variant = 0;
   // independent pairs at n = 9: fused structure factors + cross-spectrum (no bank); 0 = bank path (A/B, tests)
   bool pairs_fused = true;
   // clusters with at least this many atoms use the tensor-core GEMM form of the direct coefficients

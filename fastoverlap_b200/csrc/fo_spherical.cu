@@ -1704,6 +1704,430 @@ sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// sph_isoft4_kernel<KC, KS, NT, NYQ, WANT_GRID>: sph_isoft3_kernel with stages A and B chained in registers
+// (the scheme of per_xf6_kernel, fo_periodic.cu).  Per pair a CTA (KC beta planes in mirror pairs; 4 KC warps):
+//   phase 1  K5 (Wigner contraction) in registers; E = S(+a) + S(-a) and O'' = i (S(+a) - S(-a)) of both
+//            orientations go into the plane's S block in shared memory, rows [c0 | E_a | O''_a], columns
+//            (m2, re | im) -- the layout of a YIN slab of per_xf6_kernel.
+//            KC = 4 (odd Jmax; one CTA of 16 warps per SM): one lane per (|m1| = a, m2, level parity) in shell
+//            order -- a warp's lanes have the same number of levels to within one -- carrying all four planes:
+//            the table entry of a level is one 32-byte load (two planes and their mirrors, which supply -a), the
+//            two coefficients I(+a), I(-a) another, for 16 DFMA.  sph_isoft3's K5 (one lane per (plane, m2, a
+//            mod 4)) read 12 bytes of shared memory per DFMA: ~60 k wavefronts per pair and SM, more cycles than
+//            all the DMMAs; this one reads 4.
+//            KC = 2 (even Jmax): K5 exactly as in sph_isoft3_kernel;
+//   phase 2  one work item (plane, orientation, alpha row tile) per warp: stage A transposed (twiddles = A
+//            operand, S block = B operand): V[alpha] = c0 + sum_a cos E_a + sin O''_a as ONE DMMA chain per column
+//            tile (P, then V = P + sin O''), V[F - alpha] = 2 P - V; a lane's C fragment of column tile ct is the A
+//            fragment (row alpha, k = m2 slot) of stage B's k-step ks = ct, so stage B consumes the accumulators
+//            of stage A directly: no BR / BI arrays (sph_isoft3: 2 x 33 KB written and re-read per pair), no
+//            shuffles, no scalar FP64 between the stages.  m2 = 0 rides in slot L + 1 with weight 1/2 (half
+//            scale).  NYQ (F/2 = 8 NT, Jmax = 7, 15): the row alpha = F/2 is one extra DMMA chain with the
+//            twiddle (-1)^a in row 0 and takes the free slot of the mirror tile (the mirror of alpha = 0); the
+//            column gamma = F/2 is a one-column tile with the twiddle (-1)^m2.
+//   arg-max  the larger output of a column is A + |B|: bounded from above for the whole item by one addition of
+//            integer-found maxima; only items that may beat the running maximum are examined exactly.
+// ------------------------------------------------------------------------------------------
+struct I4Layout {
+  int SPc, sblk, o4_s, o4_red, total4;  // S block: [kk][o][2 L + 1 rows][SPc]
+  I4Layout() {}
+  I4Layout(const I2Layout& Y) {
+    const int cols = 2 * Y.L1;
+    SPc = ((cols + 11) / 16) * 16 + 4;  // == 4 (mod 16): conflict-free B fragments (rows t4 32 bytes apart mod 128)
+    sblk = (2 * Y.L + 1) * SPc;
+    o4_s = Y.o3_br;                     // in place of BR / BI
+    o4_red = (o4_s + 2 * Y.KC * sblk + 1) & ~1;
+    total4 = o4_red + 96;
+  }
+};
+
+template <int KC, int KS, int NT, bool NYQ, bool WANT_GRID>
+__global__ void __launch_bounds__(KC * 128, 4 / KC)
+sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4Layout Z,
+                  const double2* __restrict__ Ipk, const double* __restrict__ DtP, int npairs, int norient,
+                  Iso2Out out) {
+  extern __shared__ double smk[];
+  constexpr int NTHREADS = KC * 128, NW = KC * 4;
+  const int L = Y.L, L1 = Y.L1, F = Y.F;
+  const int SPc = Z.SPc;
+  double* DtS = smk + Y.o_dts;
+  double2* IkS = reinterpret_cast<double2*>(smk + Y.o3_iks);
+  double* SB = smk + Z.o4_s;  // [kk][o] blocks
+  double* red = smk + Z.o4_red;
+  int* sbest = reinterpret_cast<int*>(red + 80);  // [o]: high word (signed key) of a lower bound of the maximum
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int chunk = blockIdx.x % Y.nchunk;
+  const int jstart = blockIdx.x / Y.nchunk, jstride = gridDim.x / Y.nchunk;
+  const int nvalid = NYQ ? F / 2 : F / 2 + 1;  // alpha / gamma values covered by the 8-wide tiles
+  for (int e = tid; e < Y.dts; e += NTHREADS) DtS[e] = DtP[(size_t)chunk * Y.dts + e];
+  auto stage_coeffs = [&](int pr) {
+    const double2* src = Ipk + (size_t)pr * Y.ipk;
+    for (int e = tid; e < Y.ipk; e += NTHREADS) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(IkS + e);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (jstart < npairs) stage_coeffs(jstart);
+  SymMma<KS, NT> mm;
+  mm.init(L, F, nvalid, lane);
+  // stage-B cos fragment of the k-step that carries m2 = 0 (slot L + 1): weight 1/2 at half scale
+  const int ks0 = L >> 2, t0 = L & 3;
+  double bcz[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    bcz[nt] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      if (ks == ks0) bcz[nt] = (t4 == t0 && nt * 8 + g < nvalid) ? 0.5 : mm.bc[ks][nt];
+  }
+  // NYQ: A fragment of the row alpha = F/2 ((-1)^a in row 0), B fragment of the column gamma = F/2 ((-1)^m2 in
+  // column 0, 1/2 for m2 = 0)
+  double nyqa[KS], nyqz[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int a = 4 * ks + t4 + 1;
+    nyqa[ks] = (NYQ && g == 0 && a <= L) ? ((a & 1) ? -1.0 : 1.0) : 0.0;
+    nyqz[ks] = (NYQ && g == 0) ? (a <= L ? ((a & 1) ? -1.0 : 1.0) : (a == L + 1 ? 0.5 : 0.0)) : 0.0;
+  }
+
+  // ---- K5 geometry, KC = 2 (as sph_isoft3_kernel): this warp's 4 (kk, m2) lines x (re | im)
+  const int part = g & 1;
+  const bool lane_on = warp * 4 + (g >> 1) < KC * L1;
+  const int line = lane_on ? warp * 4 + (g >> 1) : 0;
+  const int kkA = line % KC, m2A = line / KC;
+  const double sm2 = (m2A & 1) ? -1.0 : 1.0;
+  int e_tt[KS + 1], e_l0[KS + 1];
+#pragma unroll
+  for (int ks = 0; ks <= KS; ++ks) {
+    const int a = ks < KS ? 4 * ks + t4 + 1 : 0;
+    const bool on = lane_on && a <= L && (ks < KS || t4 == 0);
+    const int sh = a > m2A ? a : m2A;
+    e_tt[ks] = m2A >= a ? m2A * m2A + a : a * a + a + 1 + m2A;
+    e_l0[ks] = on ? sh + ((sh ^ part) & 1) : L + 1;  // L + 1: empty level loop
+  }
+  // ---- K5 geometry, KC = 4: lane = (shell-ordered entry t = (a, m2), level parity)
+  const int k5t = tid >> 1, k5par = tid & 1;
+  int k5s = (int)sqrtf((float)k5t);
+  while ((k5s + 1) * (k5s + 1) <= k5t) ++k5s;
+  while (k5s * k5s > k5t) --k5s;
+  const int k5q = k5t - k5s * k5s;
+  const int k5a = k5q <= k5s ? k5q : k5s, k5m2 = k5q <= k5s ? k5s : k5q - k5s - 1;
+  const bool k5on = k5t < L1 * L1;
+  const int k5l0 = k5on ? k5s + ((k5s ^ k5par) & 1) : L + 1;  // first level >= max(a, m2) of this lane's parity
+  // ---- phase-2 geometry: item (kk, o, mt) of this warp; B-fragment rows / columns of the lane
+  int ycol[KS], ycol0[KS], yrow[KS];
+#pragma unroll
+  for (int ct = 0; ct < KS; ++ct) {
+    const int sb = 4 * ct + (g >> 1) + 1, sc = 4 * ct + t4 + 1;
+    ycol[ct] = 2 * (sb <= L ? sb : 0) + (g & 1);
+    ycol0[ct] = 2 * (sc <= L ? sc : 0);
+    const int j = 4 * ct + t4 + 1;
+    yrow[ct] = (j <= L ? j : L) * SPc;
+  }
+  const int nq = KC * norient;  // (kk, o) combinations; items = nq NT
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  for (int pair = jstart; pair < npairs; pair += jstride) {
+    if (tid < 2) sbest[tid] = (int)0x80000000;
+    // ---- phase 1: K5 in registers -> S blocks
+    if (KC == 2 && warp * 4 < KC * L1) {
+      double2 Ps[KS + 1], Ms[KS + 1];
+#pragma unroll
+      for (int ks = 0; ks <= KS; ++ks) Ps[ks] = Ms[ks] = make_double2(0.0, 0.0);
+      {
+        int base = Y.o_ent[part];  // entries below level lv
+        for (int lv = part; lv <= L; lv += 2) {
+#pragma unroll
+          for (int ks = 0; ks <= KS; ++ks) {
+            if (lv >= e_l0[ks]) {
+              const int idx = base + e_tt[ks];
+              const double2 dd = *reinterpret_cast<const double2*>(DtS + idx * 2);  // plane and its mirror
+              const double dp = kkA ? dd.y : dd.x, dm = kkA ? dd.x : dd.y;
+              const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
+              Ps[ks].x = fma(dp, cp.x, Ps[ks].x);
+              Ps[ks].y = fma(dp, cp.y, Ps[ks].y);
+              Ms[ks].x = fma(dm, cm.x, Ms[ks].x);
+              Ms[ks].y = fma(dm, cm.y, Ms[ks].y);
+            }
+          }
+          base += (lv + 1) * (lv + 1) + (lv + 2) * (lv + 2);
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks <= KS; ++ks) {
+        const double2 P = Ps[ks], Mn = Ms[ks];
+        // component c = part of the even / odd sums: own one, partner (lane ^ 4) supplies the other
+        const double sendP = part ? P.x : P.y, sendM = part ? Mn.x : Mn.y;
+        const double recvP = __shfl_xor_sync(0xffffffffu, sendP, 4);
+        const double recvM = __shfl_xor_sync(0xffffffffu, sendM, 4);
+        const double pe = part ? recvP : P.x, po = part ? P.y : recvP;
+        const double me = part ? recvM : Mn.x, mo = part ? Mn.y : recvM;
+        const int a = ks < KS ? 4 * ks + t4 + 1 : 0;
+        const bool on = lane_on && a <= L && (ks < KS || t4 == 0);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (o >= norient) break;
+          const double so = o ? -1.0 : 1.0;
+          // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
+          const double sp = fma(so, po, pe), sn = sm2 * fma(-so, mo, me);
+          double* blk = SB + (kkA * 2 + o) * Z.sblk;
+          if (on) {
+            if (ks < KS) {
+              blk[a * SPc + 2 * m2A + part] = sp + sn;                                      // E
+              blk[(L + a) * SPc + 2 * m2A + (part ^ 1)] = part ? (sn - sp) : (sp - sn);   // O'' = i O
+            } else {
+              blk[2 * m2A + part] = sp;  // c0 = S(0, m2)
+            }
+          }
+        }
+      }
+    }
+    if (KC == 4) {
+      // partial sums over the levels of this lane's parity for the four planes: P = sum d(+a) I(+a),
+      // Mn = sum d_mirror I(-a)  (d^l_{-a,m2}(beta_kk) = (-1)^(l + m2) d^l_{a,m2}(beta_{3 - kk}))
+      double2 Pp[4], Mp[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) Pp[kk] = Mp[kk] = make_double2(0.0, 0.0);
+      for (int lv = k5l0; lv <= L; lv += 2) {
+        const int idx = Y.o_ent[lv] + k5t;
+        const double2 d01 = *reinterpret_cast<const double2*>(DtS + idx * 4);
+        const double2 d23 = *reinterpret_cast<const double2*>(DtS + idx * 4 + 2);
+        const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
+        const double dd[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          Pp[kk].x = fma(dd[kk], cp.x, Pp[kk].x);
+          Pp[kk].y = fma(dd[kk], cp.y, Pp[kk].y);
+          Mp[kk].x = fma(dd[3 - kk], cm.x, Mp[kk].x);
+          Mp[kk].y = fma(dd[3 - kk], cm.y, Mp[kk].y);
+        }
+      }
+      // the lane keeps component c = parity of every sum and gets that component of the other parity's sums
+      // from its partner (lane ^ 1): then it holds the even (e) and odd (o) level sums of component c
+      const double sm2q = (k5m2 & 1) ? -1.0 : 1.0;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const double sendP = k5par ? Pp[kk].x : Pp[kk].y, sendM = k5par ? Mp[kk].x : Mp[kk].y;
+        const double recvP = __shfl_xor_sync(0xffffffffu, sendP, 1);
+        const double recvM = __shfl_xor_sync(0xffffffffu, sendM, 1);
+        const double pe = k5par ? recvP : Pp[kk].x, po = k5par ? Pp[kk].y : recvP;
+        const double me = k5par ? recvM : Mp[kk].x, mo = k5par ? Mp[kk].y : recvM;
+        if (k5on) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            if (o >= norient) break;
+            const double so = o ? -1.0 : 1.0;
+            // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
+            const double sp = fma(so, po, pe), sn = sm2q * fma(-so, mo, me);
+            double* blk = SB + (kk * 2 + o) * Z.sblk;
+            if (k5a > 0) {
+              blk[k5a * SPc + 2 * k5m2 + k5par] = sp + sn;                                        // E
+              blk[(L + k5a) * SPc + 2 * k5m2 + (k5par ^ 1)] = k5par ? (sn - sp) : (sp - sn);   // O'' = i O
+            } else {
+              blk[2 * k5m2 + k5par] = sp;  // c0 = S(0, m2)
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during phase 2
+    // ---- phase 2: item = (kk, o, mt): stage A -> stage B in registers
+    double bv[2] = {-1e300, -1e300};
+    int bix[2] = {0x7fffffff, 0x7fffffff};
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      const int q4 = warp - mt * 2 * KC;  // warps 2 KC mt .. 2 KC mt + nq - 1 take row tile mt
+      if (q4 < 0 || q4 >= nq) continue;
+      const int kk = q4 % KC, o = q4 / KC;
+      const double* S = SB + (kk * 2 + o) * Z.sblk;
+      const int plane = i2_plane(F, KC, chunk, kk);
+      const int al0 = 8 * mt + g;
+      const bool valid0 = al0 < nvalid;
+      // mirror tile: alpha = F - al0; NYQ: the free slot (mirror of alpha = 0) carries alpha = F/2
+      const bool nyqrow = NYQ && mt == 0 && g == 0;
+      const bool valid1 = nyqrow || (valid0 && al0 != 0 && 2 * al0 != F);
+      const int al1 = nyqrow ? F / 2 : F - al0;
+      double A[2][NT][2], B[2][NT][2], An[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        An[h][0] = An[h][1] = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) A[h][nt][0] = A[h][nt][1] = B[h][nt][0] = B[h][nt][1] = 0.0;
+      }
+#pragma unroll
+      for (int c2 = 0; c2 < KS; c2 += 2) {  // two column tiles (m2 slots 4 ct + 1 .. 4 ct + 4) at a time
+        double P[2][2], V[2][2], Vn[2][2];
+        {
+          double be[KS][2], bo[KS][2];
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int ct = (c2 + c < KS) ? c2 + c : KS - 1;
+              be[ks][c] = S[yrow[ks] + ycol[ct]];
+              bo[ks][c] = S[yrow[ks] + L * SPc + ycol[ct]];
+            }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int ct = (c2 + c < KS) ? c2 + c : KS - 1;
+            const double2 z = *reinterpret_cast<const double2*>(S + ycol0[ct]);
+            fo_dmma3(P[c], mm.bc[0][mt], be[0][c], z.x, z.y);
+            if (NYQ && mt == 0) fo_dmma3(Vn[c], nyqa[0], be[0][c], z.x, z.y);
+          }
+#pragma unroll
+          for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              fo_dmma(P[c], mm.bc[ks][mt], be[ks][c]);
+              if (NYQ && mt == 0) fo_dmma(Vn[c], nyqa[ks], be[ks][c]);
+            }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) fo_dmma3(V[c], mm.bs[0][mt], bo[0][c], P[c][0], P[c][1]);
+#pragma unroll
+          for (int ks = 1; ks < KS; ++ks)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) fo_dmma(V[c], mm.bs[ks][mt], bo[ks][c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c2 + c >= KS) break;
+          const int ks = c2 + c;  // stage-B k-step fed by this column tile
+          double wr = fma(2.0, P[c][0], -V[c][0]), wi = fma(2.0, P[c][1], -V[c][1]);  // V[F - alpha]
+          if (NYQ && mt == 0 && g == 0) {
+            wr = Vn[c][0];
+            wi = Vn[c][1];
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const double zc = (ks == ks0) ? bcz[nt] : mm.bc[ks][nt];
+            fo_dmma(A[0][nt], V[c][0], zc);
+            fo_dmma(B[0][nt], V[c][1], mm.bs[ks][nt]);
+            fo_dmma(A[1][nt], wr, zc);
+            fo_dmma(B[1][nt], wi, mm.bs[ks][nt]);
+          }
+          if (NYQ) {
+            fo_dmma(An[0], V[c][0], nyqz[ks]);
+            fo_dmma(An[1], wr, nyqz[ks]);
+          }
+        }
+      }
+      // outputs (half scale): g[gam] = A - B, g[F - gam] = A + B, gam = 8 nt + 2 t4 + q; NYQ: g[F/2] = An (t4 = 0, q = 0)
+      if (WANT_GRID) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool valid = h == 0 ? valid0 : valid1;
+          const int al = h == 0 ? al0 : al1;
+          double* grow = out.grid + (((size_t)pair * norient + o) * F * F * F + (size_t)(al * F + plane) * F);
+          if (valid) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int d = nt * 8 + t4 * 2 + q;
+                if (d < nvalid) {
+                  grow[d] = 2.0 * (A[h][nt][q] - B[h][nt][q]);
+                  if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * (A[h][nt][q] + B[h][nt][q]);
+                }
+              }
+            if (NYQ && t4 == 0) grow[F / 2] = 2.0 * An[h][0];
+          }
+        }
+      }
+      // Filter off the FP64 pipe: signed keys of the high words (monotone in the value), largest A (and An) and
+      // largest |B| of the lane's accumulators; one addition of their upper bounds bounds every A + |B|.
+      int ka = (int)0x80000000;
+      unsigned kb = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int ha = __double2hiint(A[h][nt][q]);
+            ka = max(ka, ha ^ ((ha >> 31) & 0x7fffffff));
+            kb = max(kb, (unsigned)__double2hiint(B[h][nt][q]) << 1);
+          }
+        if (NYQ) {
+          const int ha = __double2hiint(An[h][0]);
+          ka = max(ka, ha ^ ((ha >> 31) & 0x7fffffff));
+        }
+      }
+      // upper bounds as doubles: A <= ua (0 for a negative maximum), |B| <= ub
+      const double ua = ka >= 0 ? __hiloint2double(min(ka + 1, 0x7ff00000), 0) : 0.0;
+      const double ub = __hiloint2double(min((int)(kb >> 1) + 1, 0x7ff00000), 0);
+      const int hs = __double2hiint(ua + ub);
+      const int thr = max(sbest[o], (int)(__double_as_longlong(bv[o]) >> 32) ^
+                                        (((int)(__double_as_longlong(bv[o]) >> 63)) & 0x7fffffff));
+      if ((hs ^ ((hs >> 31) & 0x7fffffff)) >= thr) {
+        double tbv = bv[o];
+        int tbi = bix[o];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool valid = h == 0 ? valid0 : valid1;
+          const int al = h == 0 ? al0 : al1;
+          const int base = (al * F + plane) * F;
+          if (valid) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int d = nt * 8 + t4 * 2 + q;
+                const bool in = d < nvalid;
+                const double g1 = in ? A[h][nt][q] - B[h][nt][q] : -1e300;
+                const double g2 = (in && d != 0 && 2 * d != F) ? A[h][nt][q] + B[h][nt][q] : -1e300;
+                if (g1 > tbv || (g1 == tbv && base + d < tbi)) { tbv = g1; tbi = base + d; }
+                if (g2 > tbv || (g2 == tbv && base + F - d < tbi)) { tbv = g2; tbi = base + F - d; }
+              }
+            if (NYQ && t4 == 0) {
+              const double gn = An[h][0];
+              if (gn > tbv || (gn == tbv && base + F / 2 < tbi)) { tbv = gn; tbi = base + F / 2; }
+            }
+          }
+        }
+        if (tbv > bv[o] || tbi != bix[o]) {
+          bv[o] = tbv;
+          bix[o] = tbi;
+          const int hb = __double2hiint(tbv);
+          atomicMax(&sbest[o], hb ^ ((hb >> 31) & 0x7fffffff));
+        }
+      }
+    }
+    int* redi = reinterpret_cast<int*>(red + 48);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      double m = bv[o];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+      const int cand = (bv[o] == m) ? bix[o] : 0x7fffffff;
+      const int imin = __reduce_min_sync(0xffffffffu, cand);
+      if (lane == 0) {
+        red[o * 16 + warp] = m;
+        redi[o * 16 + warp] = imin;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // next pair's coefficients: visible after the barrier
+    __syncthreads();
+    if (tid < norient) {
+      double v = red[tid * 16];
+      int i = redi[tid * 16];
+      for (int w = 1; w < NW; ++w) {
+        const double ov = red[tid * 16 + w];
+        const int oi = redi[tid * 16 + w];
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+      }
+      out.part_val[((size_t)pair * norient + tid) * Y.nchunk + chunk] = 2.0 * v;
+      out.part_idx[((size_t)pair * norient + tid) * Y.nchunk + chunk] = i;
+    }
+    // no barrier: red / sbest are rewritten only after the next pair's phase-1 barrier... sbest is reset at the
+    // top of the loop by tid < 2, read in phase 2 (after the barrier)
+  }
+}
+
 // One CTA per (pair, orientation): best chunk, then findMax's parabola (utils.py:319-338).  The six
 // neighbours are evaluated from the coefficients: one pass over the (m1, m2 >= 0) entries forms
 // S_k(m1, m2) for the three planes k0-1, k0, k0+1 (adjacent table columns) and accumulates the four
@@ -2227,6 +2651,10 @@ int ensure_wigner(fo_ctx* ctx, int L) {
     ctx->wig.d_packed = nullptr;
   }
   ctx->wig.packed_kc = 0;
+  if (ctx->wig.d_packed4) {
+    cudaFree(ctx->wig.d_packed4);
+    ctx->wig.d_packed4 = nullptr;
+  }
   if (L <= 15 && !ctx->wig.kmajor) {  // bandwidths of the fast iSOFT kernel (one stage-A tile per warp)
     ctx->wig.packed_kc = FO_I3_KC;
     const I2Layout Y(L, FO_I3_KC);
@@ -2235,6 +2663,14 @@ int ensure_wigner(fo_ctx* ctx, int L) {
     sph_wigner_pack_kernel<<<grid_for((size_t)Y.nchunk * Y.dts, 256), 256, 0, ctx->stream>>>(
         ctx->wig.d_table, Y, ctx->wig.d_packed);
     FO_LAUNCH_CHECK(ctx);
+    if ((L & 1) && L >= 1) {  // four planes per chunk (sph_isoft4_kernel<4, ...>): 2 (L + 1) divisible by 4
+      const I2Layout Y4(L, 4);
+      if (cudaMalloc(&ctx->wig.d_packed4, (size_t)Y4.nchunk * Y4.dts * 8) != cudaSuccess)
+        return fo_fail(ctx, FO_ERR_NOMEM, "cudaMalloc of the packed Wigner table failed");
+      sph_wigner_pack_kernel<<<grid_for((size_t)Y4.nchunk * Y4.dts, 256), 256, 0, ctx->stream>>>(
+          ctx->wig.d_table, Y4, ctx->wig.d_packed4);
+      FO_LAUNCH_CHECK(ctx);
+    }
   }
   return FO_OK;
 }
@@ -2285,6 +2721,59 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       sph_ipack_kernel<<<grid_for((size_t)npairs * Y.ipk, 256), 256, 0, ctx->stream>>>(d_Ihalf, Y, (size_t)npairs,
                                                                                         (double2*)ipk);
       FO_LAUNCH_CHECK(ctx);
+      {  // stages A -> B chained in registers (sph_isoft4_kernel); four planes per CTA when 2 (L + 1) % 4 == 0
+        const int KC4 = (ctx->wig.d_packed4 && ctx->isoft_variant != 42) ? 4 : 2;
+        const I2Layout Y4(L, KC4);
+        const I4Layout Z4(Y4);
+        const size_t smem4 = (size_t)Z4.total4 * 8;
+        const int KS4 = L / 4 + 1;
+        const int code4 = KS4 * 100 + NTq * 10 + (nyq ? 1 : 0);
+        const bool have4 = code4 == 421 || code4 == 420 || code4 == 320 || code4 == 211 || code4 == 210 || code4 == 110;
+        if (KC == 2 && have4 && ctx->isoft_variant != 3 && smem4 <= ctx->prop.sharedMemPerBlockOptin) {
+          const int nch4 = Y4.nchunk;
+          if (KC4 == 4) FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)npairs * norient * nch * (8 + 4) + 64, &part));
+          o2.part_val = (double*)part;
+          o2.part_idx = (int*)(o2.part_val + (size_t)npairs * norient * nch4);
+          int per4 = ctx->prop.multiProcessorCount * (4 / KC4) / nch4;
+          if (per4 < 1) per4 = 1;
+          if ((int64_t)per4 > npairs) per4 = (int)npairs;
+          const unsigned blocks4 = (unsigned)(per4 * nch4);
+          const double* dtp = KC4 == 4 ? ctx->wig.d_packed4 : ctx->wig.d_packed;
+#define FO_I4_GO(KC_, KS_, NT_, NYQ_, G_)                                                                     \
+  do {                                                                                                        \
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft4_kernel<KC_, KS_, NT_, NYQ_, G_>,                             \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));              \
+    sph_isoft4_kernel<KC_, KS_, NT_, NYQ_, G_><<<blocks4, KC_ * 128, smem4, ctx->stream>>>(                   \
+        Y4, Z4, d_Ipk, dtp, (int)npairs, norient, o2);                                                        \
+  } while (0)
+#define FO_I4_LAUNCH(KS_, NT_, NYQ_)                      \
+  do {                                                    \
+    if (KC4 == 4) {                                       \
+      if (d_grid) FO_I4_GO(4, KS_, NT_, NYQ_, true);      \
+      else FO_I4_GO(4, KS_, NT_, NYQ_, false);            \
+    } else {                                              \
+      if (d_grid) FO_I4_GO(2, KS_, NT_, NYQ_, true);      \
+      else FO_I4_GO(2, KS_, NT_, NYQ_, false);            \
+    }                                                     \
+  } while (0)
+          switch (code4) {
+            case 421: FO_I4_LAUNCH(4, 2, true); break;    // Jmax 15
+            case 420: FO_I4_LAUNCH(4, 2, false); break;   // Jmax 12 .. 14
+            case 320: FO_I4_LAUNCH(3, 2, false); break;   // Jmax 8 .. 11
+            case 211: FO_I4_LAUNCH(2, 1, true); break;    // Jmax 7
+            case 210: FO_I4_LAUNCH(2, 1, false); break;   // Jmax 4 .. 6
+            default: FO_I4_LAUNCH(1, 1, false); break;    // Jmax 1 .. 3
+          }
+#undef FO_I4_LAUNCH
+#undef FO_I4_GO
+          FO_LAUNCH_CHECK(ctx);
+          sph_final2_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+              d_Ihalf, ctx->wig.d_table, L, norient, nch4, o2.part_val, o2.part_idx, d_best_idx,
+              d_best_val, d_frac);
+          FO_LAUNCH_CHECK(ctx);
+          return FO_OK;
+        }
+      }
 #define FO_I3_GO(KC_, KS_, NT_, NYQ_, G_)                                                                    \
   do {                                                                                                       \
     FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft3_kernel<KC_, KS_, NT_, NYQ_, G_>,                            \
