@@ -1729,6 +1729,15 @@ sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
 //   arg-max  the larger output of a column is A + |B|: bounded from above for the whole item by one addition of
 //            integer-found maxima; only items that may beat the running maximum are examined exactly.
 // ------------------------------------------------------------------------------------------
+// signed-comparable integer key of a double (monotone: a < b <=> key(a) < key(b); -0 < +0) and its inverse
+__device__ __forceinline__ long long fo_dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double fo_dunkey(long long k) {
+  return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL));
+}
+
 struct I4Layout {
   int SPc, sblk, o4_s, o4_red, total4;  // S block: [kk][o][2 L + 1 rows][SPc]
   I4Layout() {}
@@ -1937,7 +1946,8 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
     __syncthreads();
     if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during phase 2
     // ---- phase 2: item = (kk, o, mt): stage A -> stage B in registers
-    double bv[2] = {-1e300, -1e300};
+    // running maximum per orientation as a signed-comparable 64-bit key (monotone in the value)
+    long long bkey[2] = {fo_dkey(-1e300), fo_dkey(-1e300)};
     int bix[2] = {0x7fffffff, 0x7fffffff};
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt) {
@@ -2061,52 +2071,56 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
       const double ua = ka >= 0 ? __hiloint2double(min(ka + 1, 0x7ff00000), 0) : 0.0;
       const double ub = __hiloint2double(min((int)(kb >> 1) + 1, 0x7ff00000), 0);
       const int hs = __double2hiint(ua + ub);
-      const int thr = max(sbest[o], (int)(__double_as_longlong(bv[o]) >> 32) ^
-                                        (((int)(__double_as_longlong(bv[o]) >> 63)) & 0x7fffffff));
+      const int thr = max(sbest[o], (int)(bkey[o] >> 32));
       if ((hs ^ ((hs >> 31) & 0x7fffffff)) >= thr) {
-        double tbv = bv[o];
+        // the larger output of a column is A + |B| (bit for bit A - B or A + B): at gamma = d when B < 0 or
+        // B = 0 (a tie of the two outputs: the smaller index), at F - d when B > 0; compared as integer keys
+        long long tk = bkey[o];
         int tbi = bix[o];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const bool valid = h == 0 ? valid0 : valid1;
           const int al = h == 0 ? al0 : al1;
           const int base = (al * F + plane) * F;
-          if (valid) {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+          for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int d = nt * 8 + t4 * 2 + q;
-                const bool in = d < nvalid;
-                const double g1 = in ? A[h][nt][q] - B[h][nt][q] : -1e300;
-                const double g2 = (in && d != 0 && 2 * d != F) ? A[h][nt][q] + B[h][nt][q] : -1e300;
-                if (g1 > tbv || (g1 == tbv && base + d < tbi)) { tbv = g1; tbi = base + d; }
-                if (g2 > tbv || (g2 == tbv && base + F - d < tbi)) { tbv = g2; tbi = base + F - d; }
+            for (int q = 0; q < 2; ++q) {
+              const int d = nt * 8 + t4 * 2 + q;
+              const long long ck = fo_dkey(A[h][nt][q] + fabs(B[h][nt][q]));
+              const int idx = base + (__double_as_longlong(B[h][nt][q]) > 0 ? F - d : d);  // > 0 as integers: B > +0
+              if (valid && d < nvalid && (ck > tk || (ck == tk && idx < tbi))) {
+                tk = ck;
+                tbi = idx;
               }
-            if (NYQ && t4 == 0) {
-              const double gn = An[h][0];
-              if (gn > tbv || (gn == tbv && base + F / 2 < tbi)) { tbv = gn; tbi = base + F / 2; }
+            }
+          if (NYQ && valid && t4 == 0) {
+            const long long ck = fo_dkey(An[h][0]);
+            if (ck > tk || (ck == tk && base + F / 2 < tbi)) {
+              tk = ck;
+              tbi = base + F / 2;
             }
           }
         }
-        if (tbv > bv[o] || tbi != bix[o]) {
-          bv[o] = tbv;
+        if (tk != bkey[o] || tbi != bix[o]) {
+          bkey[o] = tk;
           bix[o] = tbi;
-          const int hb = __double2hiint(tbv);
-          atomicMax(&sbest[o], hb ^ ((hb >> 31) & 0x7fffffff));
+          atomicMax(&sbest[o], (int)(tk >> 32));
         }
       }
     }
     int* redi = reinterpret_cast<int*>(red + 48);
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
-      double m = bv[o];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-      const int cand = (bv[o] == m) ? bix[o] : 0x7fffffff;
-      const int imin = __reduce_min_sync(0xffffffffu, cand);
+      // warp maximum of the keys: high words by REDUX, then the low words among the lanes that hold it
+      const int hi = (int)(bkey[o] >> 32);
+      const int mhi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned lo = hi == mhi ? (unsigned)bkey[o] : 0u;
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+      const bool top = hi == mhi && (unsigned)bkey[o] == mlo;
+      const int imin = __reduce_min_sync(0xffffffffu, top ? bix[o] : 0x7fffffff);
       if (lane == 0) {
-        red[o * 16 + warp] = m;
+        red[o * 16 + warp] = fo_dunkey(((long long)mhi << 32) | (long long)mlo);
         redi[o * 16 + warp] = imin;
       }
     }
