@@ -1716,7 +1716,7 @@ sph_isoft3_kernel(const __grid_constant__ I2Layout Y, const double2* __restrict_
 //            two coefficients I(+a), I(-a) another, for 16 DFMA.  sph_isoft3's K5 (one lane per (plane, m2, a
 //            mod 4)) read 12 bytes of shared memory per DFMA: ~60 k wavefronts per pair and SM, more cycles than
 //            all the DMMAs; this one reads 4.
-//            KC = 2 (even Jmax): K5 exactly as in sph_isoft3_kernel;
+//            KC = 2 (even Jmax; two CTAs of 8 warps per SM): the same with two planes per lane;
 //   phase 2  one work item (plane, orientation, alpha row tile) per warp: stage A transposed (twiddles = A
 //            operand, S block = B operand): V[alpha] = c0 + sum_a cos E_a + sin O''_a as ONE DMMA chain per column
 //            tile (P, then V = P + sin O''), V[F - alpha] = 2 P - V; a lane's C fragment of column tile ct is the A
@@ -1802,28 +1802,19 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
     nyqz[ks] = (NYQ && g == 0) ? (a <= L ? ((a & 1) ? -1.0 : 1.0) : (a == L + 1 ? 0.5 : 0.0)) : 0.0;
   }
 
-  // ---- K5 geometry, KC = 2 (as sph_isoft3_kernel): this warp's 4 (kk, m2) lines x (re | im)
-  const int part = g & 1;
-  const bool lane_on = warp * 4 + (g >> 1) < KC * L1;
-  const int line = lane_on ? warp * 4 + (g >> 1) : 0;
-  const int kkA = line % KC, m2A = line / KC;
-  const double sm2 = (m2A & 1) ? -1.0 : 1.0;
-  int e_tt[KS + 1], e_l0[KS + 1];
-#pragma unroll
-  for (int ks = 0; ks <= KS; ++ks) {
-    const int a = ks < KS ? 4 * ks + t4 + 1 : 0;
-    const bool on = lane_on && a <= L && (ks < KS || t4 == 0);
-    const int sh = a > m2A ? a : m2A;
-    e_tt[ks] = m2A >= a ? m2A * m2A + a : a * a + a + 1 + m2A;
-    e_l0[ks] = on ? sh + ((sh ^ part) & 1) : L + 1;  // L + 1: empty level loop
-  }
-  // ---- K5 geometry, KC = 4: lane = (shell-ordered entry t = (a, m2), level parity)
-  const int k5t = tid >> 1, k5par = tid & 1;
-  int k5s = (int)sqrtf((float)k5t);
-  while ((k5s + 1) * (k5s + 1) <= k5t) ++k5s;
-  while (k5s * k5s > k5t) --k5s;
-  const int k5q = k5t - k5s * k5s;
-  const int k5a = k5q <= k5s ? k5q : k5s, k5m2 = k5q <= k5s ? k5s : k5q - k5s - 1;
+  // ---- K5 geometry: task = (shell-ordered entry t = (a, m2), level parity); KC = 4: one task per thread, hoisted
+  auto k5_geom = [&](int task, int& t, int& sq, int& a, int& m2) {
+    t = task >> 1;
+    sq = (int)sqrtf((float)t);
+    while ((sq + 1) * (sq + 1) <= t) ++sq;
+    while (sq * sq > t) --sq;
+    const int q = t - sq * sq;
+    a = q <= sq ? q : sq;
+    m2 = q <= sq ? sq : q - sq - 1;
+  };
+  int k5t, k5s, k5a, k5m2;
+  k5_geom(tid, k5t, k5s, k5a, k5m2);
+  const int k5par = tid & 1;
   const bool k5on = k5t < L1 * L1;
   const int k5l0 = k5on ? k5s + ((k5s ^ k5par) & 1) : L + 1;  // first level >= max(a, m2) of this lane's parity
   // ---- phase-2 geometry: item (kk, o, mt) of this warp; B-fragment rows / columns of the lane
@@ -1842,90 +1833,43 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
 
   for (int pair = jstart; pair < npairs; pair += jstride) {
     if (tid < 2) sbest[tid] = (int)0x80000000;
-    // ---- phase 1: K5 in registers -> S blocks
-    if (KC == 2 && warp * 4 < KC * L1) {
-      double2 Ps[KS + 1], Ms[KS + 1];
+    // ---- phase 1: K5 in registers -> S blocks.  Task = (shell-ordered entry t = (a, m2), level parity): the
+    // lanes of a warp have the same number of levels to within one
+    auto k5_task = [&](int t, int a, int m2, int l0, bool on) {
+      // partial sums over the levels of this lane's parity for the KC planes: P = sum d(+a) I(+a),
+      // Mn = sum d_mirror I(-a)  (d^l_{-a,m2}(beta_kk) = (-1)^(l + m2) d^l_{a,m2}(beta_{KC - 1 - kk}))
+      double2 Pp[KC], Mp[KC];
 #pragma unroll
-      for (int ks = 0; ks <= KS; ++ks) Ps[ks] = Ms[ks] = make_double2(0.0, 0.0);
-      {
-        int base = Y.o_ent[part];  // entries below level lv
-        for (int lv = part; lv <= L; lv += 2) {
+      for (int kk = 0; kk < KC; ++kk) Pp[kk] = Mp[kk] = make_double2(0.0, 0.0);
+      for (int lv = l0; lv <= L; lv += 2) {
+        const int idx = Y.o_ent[lv] + t;
+        double dd[KC];
 #pragma unroll
-          for (int ks = 0; ks <= KS; ++ks) {
-            if (lv >= e_l0[ks]) {
-              const int idx = base + e_tt[ks];
-              const double2 dd = *reinterpret_cast<const double2*>(DtS + idx * 2);  // plane and its mirror
-              const double dp = kkA ? dd.y : dd.x, dm = kkA ? dd.x : dd.y;
-              const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
-              Ps[ks].x = fma(dp, cp.x, Ps[ks].x);
-              Ps[ks].y = fma(dp, cp.y, Ps[ks].y);
-              Ms[ks].x = fma(dm, cm.x, Ms[ks].x);
-              Ms[ks].y = fma(dm, cm.y, Ms[ks].y);
-            }
-          }
-          base += (lv + 1) * (lv + 1) + (lv + 2) * (lv + 2);
+        for (int kk = 0; kk < KC; kk += 2) {
+          const double2 d2 = *reinterpret_cast<const double2*>(DtS + idx * KC + kk);
+          dd[kk] = d2.x;
+          dd[kk + 1] = d2.y;
         }
-      }
-#pragma unroll
-      for (int ks = 0; ks <= KS; ++ks) {
-        const double2 P = Ps[ks], Mn = Ms[ks];
-        // component c = part of the even / odd sums: own one, partner (lane ^ 4) supplies the other
-        const double sendP = part ? P.x : P.y, sendM = part ? Mn.x : Mn.y;
-        const double recvP = __shfl_xor_sync(0xffffffffu, sendP, 4);
-        const double recvM = __shfl_xor_sync(0xffffffffu, sendM, 4);
-        const double pe = part ? recvP : P.x, po = part ? P.y : recvP;
-        const double me = part ? recvM : Mn.x, mo = part ? Mn.y : recvM;
-        const int a = ks < KS ? 4 * ks + t4 + 1 : 0;
-        const bool on = lane_on && a <= L && (ks < KS || t4 == 0);
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          if (o >= norient) break;
-          const double so = o ? -1.0 : 1.0;
-          // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
-          const double sp = fma(so, po, pe), sn = sm2 * fma(-so, mo, me);
-          double* blk = SB + (kkA * 2 + o) * Z.sblk;
-          if (on) {
-            if (ks < KS) {
-              blk[a * SPc + 2 * m2A + part] = sp + sn;                                      // E
-              blk[(L + a) * SPc + 2 * m2A + (part ^ 1)] = part ? (sn - sp) : (sp - sn);   // O'' = i O
-            } else {
-              blk[2 * m2A + part] = sp;  // c0 = S(0, m2)
-            }
-          }
-        }
-      }
-    }
-    if (KC == 4) {
-      // partial sums over the levels of this lane's parity for the four planes: P = sum d(+a) I(+a),
-      // Mn = sum d_mirror I(-a)  (d^l_{-a,m2}(beta_kk) = (-1)^(l + m2) d^l_{a,m2}(beta_{3 - kk}))
-      double2 Pp[4], Mp[4];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) Pp[kk] = Mp[kk] = make_double2(0.0, 0.0);
-      for (int lv = k5l0; lv <= L; lv += 2) {
-        const int idx = Y.o_ent[lv] + k5t;
-        const double2 d01 = *reinterpret_cast<const double2*>(DtS + idx * 4);
-        const double2 d23 = *reinterpret_cast<const double2*>(DtS + idx * 4 + 2);
         const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
-        const double dd[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < KC; ++kk) {
           Pp[kk].x = fma(dd[kk], cp.x, Pp[kk].x);
           Pp[kk].y = fma(dd[kk], cp.y, Pp[kk].y);
-          Mp[kk].x = fma(dd[3 - kk], cm.x, Mp[kk].x);
-          Mp[kk].y = fma(dd[3 - kk], cm.y, Mp[kk].y);
+          Mp[kk].x = fma(dd[KC - 1 - kk], cm.x, Mp[kk].x);
+          Mp[kk].y = fma(dd[KC - 1 - kk], cm.y, Mp[kk].y);
         }
       }
       // the lane keeps component c = parity of every sum and gets that component of the other parity's sums
       // from its partner (lane ^ 1): then it holds the even (e) and odd (o) level sums of component c
-      const double sm2q = (k5m2 & 1) ? -1.0 : 1.0;
+      const double sm2q = (m2 & 1) ? -1.0 : 1.0;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
+      for (int kk = 0; kk < KC; ++kk) {
         const double sendP = k5par ? Pp[kk].x : Pp[kk].y, sendM = k5par ? Mp[kk].x : Mp[kk].y;
         const double recvP = __shfl_xor_sync(0xffffffffu, sendP, 1);
         const double recvM = __shfl_xor_sync(0xffffffffu, sendM, 1);
         const double pe = k5par ? recvP : Pp[kk].x, po = k5par ? Pp[kk].y : recvP;
         const double me = k5par ? recvM : Mp[kk].x, mo = k5par ? Mp[kk].y : recvM;
-        if (k5on) {
+        if (on) {
 #pragma unroll
           for (int o = 0; o < 2; ++o) {
             if (o >= norient) break;
@@ -1933,15 +1877,22 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
             // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-
             const double sp = fma(so, po, pe), sn = sm2q * fma(-so, mo, me);
             double* blk = SB + (kk * 2 + o) * Z.sblk;
-            if (k5a > 0) {
-              blk[k5a * SPc + 2 * k5m2 + k5par] = sp + sn;                                        // E
-              blk[(L + k5a) * SPc + 2 * k5m2 + (k5par ^ 1)] = k5par ? (sn - sp) : (sp - sn);   // O'' = i O
+            if (a > 0) {
+              blk[a * SPc + 2 * m2 + k5par] = sp + sn;                                     // E
+              blk[(L + a) * SPc + 2 * m2 + (k5par ^ 1)] = k5par ? (sn - sp) : (sp - sn);   // O'' = i O
             } else {
-              blk[2 * k5m2 + k5par] = sp;  // c0 = S(0, m2)
+              blk[2 * m2 + k5par] = sp;  // c0 = S(0, m2)
             }
           }
         }
       }
+    };
+    k5_task(k5t, k5a, k5m2, k5l0, k5on);
+    if (KC == 2) {  // 512 tasks on 256 threads: the second one (warp-uniform: the partner shuffles need every lane)
+      int t2, s2, a2, m22;
+      k5_geom(tid + NTHREADS, t2, s2, a2, m22);
+      const bool on2 = t2 < L1 * L1;
+      k5_task(t2, a2, m22, on2 ? s2 + ((s2 ^ k5par) & 1) : L + 1, on2);
     }
     __syncthreads();
     if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during phase 2
