@@ -29,6 +29,7 @@
 #include <algorithm>
 
 #include "fo_internal.h"
+#include "fo_async.cuh"
 #include "fo_symdft.cuh"
 
 namespace {
@@ -1771,14 +1772,22 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
   const int jstart = blockIdx.x / Y.nchunk, jstride = gridDim.x / Y.nchunk;
   const int nvalid = NYQ ? F / 2 : F / 2 + 1;  // alpha / gamma values covered by the 8-wide tiles
   for (int e = tid; e < Y.dts; e += NTHREADS) DtS[e] = DtP[(size_t)chunk * Y.dts + e];
+  // the packed coefficients of a pair (48 KB at Jmax = 15) arrive by one bulk asynchronous copy (cp.async.bulk,
+  // SASS UBLKCP) completing on an mbarrier: issued by one thread, no LDGSTS slots, no issue slots of the others
+  uint64_t* cbar = reinterpret_cast<uint64_t*>(red + 88);
+  const unsigned ipk_bytes = (unsigned)Y.ipk * 16u;
   auto stage_coeffs = [&](int pr) {
-    const double2* src = Ipk + (size_t)pr * Y.ipk;
-    for (int e = tid; e < Y.ipk; e += NTHREADS) {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(IkS + e);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + e) : "memory");
+    if (tid == 0) {
+      fo_fence_proxy_async();
+      fo_mbar_arrive_expect_tx(cbar, ipk_bytes);
+      fo_bulk_g2s(IkS, Ipk + (size_t)pr * Y.ipk, ipk_bytes, cbar);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  if (tid == 0) {
+    fo_mbar_init(cbar, 1);
+    fo_mbar_fence_init();
+  }
+  int cph = 0;
   if (jstart < npairs) stage_coeffs(jstart);
   SymMma<KS, NT> mm;
   mm.init(L, F, nvalid, lane);
@@ -1828,11 +1837,12 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
     yrow[ct] = (j <= L ? j : L) * SPc;
   }
   const int nq = KC * norient;  // (kk, o) combinations; items = nq NT
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
+  __syncthreads();  // the initialised mbarrier is visible to every waiter
 
   for (int pair = jstart; pair < npairs; pair += jstride) {
     if (tid < 2) sbest[tid] = (int)0x80000000;
+    fo_mbar_wait(cbar, cph);  // this pair's coefficients have landed
+    cph ^= 1;
     // ---- phase 1: K5 in registers -> S blocks.  Task = (shell-ordered entry t = (a, m2), level parity): the
     // lanes of a warp have the same number of levels to within one
     auto k5_task = [&](int t, int a, int m2, int l0, bool on) {
@@ -2075,7 +2085,6 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
         redi[o * 16 + warp] = imin;
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");  // next pair's coefficients: visible after the barrier
     __syncthreads();
     if (tid < norient) {
       double v = red[tid * 16];
