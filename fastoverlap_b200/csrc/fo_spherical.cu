@@ -2102,93 +2102,124 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
   }
 }
 
-// One CTA per (pair, orientation): best chunk, then findMax's parabola (utils.py:319-338).  The six
+// One CTA per pair (all orientations): best chunk, then findMax's parabola (utils.py:319-338).  The six
 // neighbours are evaluated from the coefficients: one pass over the (m1, m2 >= 0) entries forms
-// S_k(m1, m2) for the three planes k0-1, k0, k0+1 (adjacent table columns) and accumulates the four
-// in-plane neighbours and the two out-of-plane ones; all 256 threads share the pass.
+// S_k(m1, m2) for the three planes k0-1, k0, k0+1 (adjacent table columns) of each orientation and accumulates
+// the four in-plane neighbours and the two out-of-plane ones; all 256 threads share the pass, and both
+// orientations share the coefficient loads (the pass is bound by reading the pair's coefficients: one CTA per
+// (pair, orientation) read them twice -- 248 -> ~150 us per 2236 LJ38 pairs).
 __global__ void __launch_bounds__(256)
 sph_final2_kernel(const double2* __restrict__ Ihalf, const double* __restrict__ Dt, int L, int norient,
                   int nchunk, const double* __restrict__ part_val, const int* __restrict__ part_idx,
                   long long* __restrict__ best_idx, double* __restrict__ best_val,
                   double* __restrict__ frac_idx) {
   __shared__ double2 tw[128];
-  __shared__ double nbs[8][6];
-  const size_t po = blockIdx.x;
-  const size_t p = po / norient;
-  const int o = (int)(po % norient);
+  __shared__ double nbs[8][12];
+  const size_t p = blockIdx.x;
   const int L1 = L + 1, W = 2 * L + 1, F = 2 * L1;
-  const double so = o ? -1.0 : 1.0;
   for (int t = threadIdx.x; t < F; t += blockDim.x) {
     double sn, cs;
     sincospi(2.0 * (double)t / (double)F, &sn, &cs);
     tw[t] = make_double2(cs, sn);
   }
-  double bv = -1e300;
-  int bi = 0x7fffffff;
-  for (int c = 0; c < nchunk; ++c) {
-    const double v = part_val[po * nchunk + c];
-    const int i = part_idx[po * nchunk + c];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  double bv[2];
+  int a0[2], k0[2], g0[2], km[2], kp[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    bv[o] = -1e300;
+    int bi = 0x7fffffff;
+    if (o < norient) {
+      const size_t po = p * norient + o;
+      for (int c = 0; c < nchunk; ++c) {
+        const double v = part_val[po * nchunk + c];
+        const int i = part_idx[po * nchunk + c];
+        if (v > bv[o] || (v == bv[o] && i < bi)) { bv[o] = v; bi = i; }
+      }
+    }
+    const bool ok = bi != 0x7fffffff;
+    a0[o] = ok ? bi / (F * F) : 0;
+    k0[o] = ok ? (bi / F) % F : 0;
+    g0[o] = ok ? bi % F : 0;
+    km[o] = (k0[o] + F - 1) % F;
+    kp[o] = (k0[o] + 1) % F;
   }
-  const bool ok = bi != 0x7fffffff;
-  const int a0 = ok ? bi / (F * F) : 0, k0 = ok ? (bi / F) % F : 0, g0 = ok ? bi % F : 0;
-  const int km = (k0 + F - 1) % F, kp = (k0 + 1) % F;
   __syncthreads();
-  // accumulators: 0,1 = a0 -+ 1; 2,3 = k0 -+ 1; 4,5 = g0 -+ 1   (order of the parabola below)
-  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  // accumulators per orientation: 0,1 = a0 -+ 1; 2,3 = k0 -+ 1; 4,5 = g0 -+ 1   (order of the parabola below)
+  double acc[2][6];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) acc[o][q] = 0.0;
   const double2* Ip = Ihalf + p * (size_t)L1 * W * L1;
   for (int item = threadIdx.x; item < L1 * W; item += blockDim.x) {
     const int m1i = item % W, m2 = item / W;
     const int m1 = m1i - L;
     const int am1 = m1 < 0 ? -m1 : m1;
     const int l0 = am1 > m2 ? am1 : m2;
-    double sr[3] = {0.0, 0.0, 0.0}, si[3] = {0.0, 0.0, 0.0};
+    double sr[2][3], si[2][3];
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) sr[o][j] = si[o][j] = 0.0;
     const double2* ip = Ip + (size_t)item * L1;
     const double* dp = Dt + (size_t)item * L1 * F;
     for (int l = l0; l <= L; ++l) {
-      const double sg = (l & 1) ? so : 1.0;
       const double2 c = ip[l];
       const double* d = dp + (size_t)l * F;
-      const double cx = sg * c.x, cy = sg * c.y;
-      const double d0 = d[km], d1 = d[k0], d2 = d[kp];
-      sr[0] = fma(d0, cx, sr[0]); si[0] = fma(d0, cy, si[0]);
-      sr[1] = fma(d1, cx, sr[1]); si[1] = fma(d1, cy, si[1]);
-      sr[2] = fma(d2, cx, sr[2]); si[2] = fma(d2, cy, si[2]);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        if (o >= norient) break;
+        const double sg = ((l & 1) && o) ? -1.0 : 1.0;
+        const double cx = sg * c.x, cy = sg * c.y;
+        const double d0 = d[km[o]], d1 = d[k0[o]], d2 = d[kp[o]];
+        sr[o][0] = fma(d0, cx, sr[o][0]); si[o][0] = fma(d0, cy, si[o][0]);
+        sr[o][1] = fma(d1, cx, sr[o][1]); si[o][1] = fma(d1, cy, si[o][1]);
+        sr[o][2] = fma(d2, cx, sr[o][2]); si[o][2] = fma(d2, cy, si[o][2]);
+      }
     }
     const double wgt = (m2 == 0) ? 1.0 : 2.0;
-    const int e0 = ((m1 * a0 + m2 * g0) % F + F) % F;
-    // term(plane j, phase e) = S_r cos - S_i sin
-    auto term = [&](int j, int e) {
-      const double2 w = tw[e];
-      return wgt * (sr[j] * w.x - si[j] * w.y);
-    };
-    acc[0] += term(1, ((e0 - m1) % F + F) % F);
-    acc[1] += term(1, ((e0 + m1) % F + F) % F);
-    acc[2] += term(0, e0);
-    acc[3] += term(2, e0);
-    acc[4] += term(1, ((e0 - m2) % F + F) % F);
-    acc[5] += term(1, (e0 + m2) % F);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      if (o >= norient) break;
+      const int e0 = ((m1 * a0[o] + m2 * g0[o]) % F + F) % F;
+      // term(plane j, phase e) = S_r cos - S_i sin
+      auto term = [&](int j, int e) {
+        const double2 w = tw[e];
+        return wgt * (sr[o][j] * w.x - si[o][j] * w.y);
+      };
+      acc[o][0] += term(1, ((e0 - m1) % F + F) % F);
+      acc[o][1] += term(1, ((e0 + m1) % F + F) % F);
+      acc[o][2] += term(0, e0);
+      acc[o][3] += term(2, e0);
+      acc[o][4] += term(1, ((e0 - m2) % F + F) % F);
+      acc[o][5] += term(1, (e0 + m2) % F);
+    }
   }
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
+  for (int o = 0; o < 2; ++o)
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], off);
-    if (lane == 0) nbs[w][q] = acc[q];
-  }
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[o][q] += __shfl_down_sync(0xffffffffu, acc[o][q], off);
+      if (lane == 0) nbs[w][o * 6 + q] = acc[o][q];
+    }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if ((int)threadIdx.x < norient) {
+    const int o = threadIdx.x;
+    const size_t po = p * norient + o;
     double nb[6];
     for (int q = 0; q < 6; ++q) {
       double s = 0.0;
-      for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) s += nbs[ww][q];
+      for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) s += nbs[ww][o * 6 + q];
       nb[q] = fabs(s);
     }
-    best_val[po] = bv;
-    const int b3[3] = {a0, k0, g0};
+    const double bvo = o ? bv[1] : bv[0];
+    best_val[po] = bvo;
+    const int b3[3] = {o ? a0[1] : a0[0], o ? k0[1] : k0[0], o ? g0[1] : g0[0]};
     for (int ax = 0; ax < 3; ++ax) {
       best_idx[po * 3 + ax] = b3[ax];
-      const double y1 = nb[2 * ax + 1], y3 = nb[2 * ax], y2 = fabs(bv);
+      const double y1 = nb[2 * ax + 1], y3 = nb[2 * ax], y2 = fabs(bvo);
       frac_idx[po * 3 + ax] = (double)b3[ax] - (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
     }
   }
@@ -2741,7 +2772,7 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
 #undef FO_I4_LAUNCH
 #undef FO_I4_GO
           FO_LAUNCH_CHECK(ctx);
-          sph_final2_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+          sph_final2_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(
               d_Ihalf, ctx->wig.d_table, L, norient, nch4, o2.part_val, o2.part_idx, d_best_idx,
               d_best_val, d_frac);
           FO_LAUNCH_CHECK(ctx);
@@ -2772,7 +2803,7 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
 #undef FO_I3_LAUNCH
 #undef FO_I3_GO
       FO_LAUNCH_CHECK(ctx);
-      sph_final2_kernel<<<(unsigned)(npairs * norient), 256, 0, ctx->stream>>>(
+      sph_final2_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(
           d_Ihalf, ctx->wig.d_table, L, norient, nch, o2.part_val, o2.part_idx, d_best_idx,
           d_best_val, d_frac);
       FO_LAUNCH_CHECK(ctx);
