@@ -199,10 +199,6 @@ extern "C" int fo_set_option(fo_ctx* ctx, const char* name, int64_t value) {
     ctx->isoft_variant = (int)value;
     return FO_OK;
   }
-  if (strcmp(name, "per_xf_variant") == 0) {
-    ctx->xf_variant = (int)value;
-    return FO_OK;
-  }
   if (strcmp(name, "direct_gemm_min_atoms") == 0) {
     ctx->direct_gemm_min = value < 1 ? 1 : value;
     return FO_OK;

@@ -60,8 +60,6 @@ struct fo_ctx {
 
   // testing hook: force the generic (any-size) kernels instead of the shared-memory fast paths
   bool force_generic = false;
-  // A/B hook: 0 = default transform kernel, 4 = per_xf4_kernel (shared-memory Y -> Z hand-over)
-  int xf_variant = 0;
   // A/B hook: 0 = default iSOFT kernel, 3 = sph_isoft3_kernel (stage A -> shared memory -> stage B)
   int isoft_variant = 0;
   // independent pairs at n = 9: fused structure factors + cross-spectrum (no bank); 0 = bank path (A/B, tests)

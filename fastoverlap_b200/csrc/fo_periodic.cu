@@ -1197,58 +1197,28 @@ per_xf_kernel(const double2* __restrict__ bankA, const double2* __restrict__ ban
 }
 
 // ------------------------------------------------------------------------------------------
-// K_xf tensor-core path (per_xf4_kernel): the stages of per_xf_kernel with every 1-D transform done
-// per REAL row (re / im parts are separate rows, inputs in E / O form) by SymMma (fo_symdft.cuh): a
-// warp owns 8 consecutive rows and all outputs, the products run on the FP64 tensor pipe
-// (DMMA.8x8x4), E/O inputs are read once per tile from k-major shared arrays, the twiddle fragments
-// live in registers.  The stage-X pitch is padded to RXp == 8 (mod 16) doubles (the four k rows of an
-// A fragment then fall into two disjoint 64-byte bank halves).  Earlier forms of this kernel (scalar
-// register tiles fed from shared memory; twiddles as uniform constant-bank operands) were limited by
-// operand delivery and issue slots, not by the FP64 pipe: profiles/r01_summary.md.
+// K_xf tensor-core paths: the stages of per_xf_kernel with every 1-D transform done per REAL row (re / im
+// parts are separate rows, inputs in E / O form) on the FP64 tensor pipe (DMMA.8x8x4, SymMma in fo_symdft.cuh),
+// twiddle fragments in registers.  per_xf6_kernel (below) is the resident form for the default k-grids,
+// per_xf5_kernel the form for fine k-grids.  (per_xf4_kernel, the round-1 form with a shared-memory hand-over
+// between stages Y and Z on named half-CTA barriers, was removed: per_xf6 covers every grid it covered and
+// is 1.5x faster.  Earlier scalar forms were limited by operand delivery and issue slots, not by the FP64
+// pipe: profiles/r01_summary.md.)
 // ------------------------------------------------------------------------------------------
-constexpr int X4_THREADS = 512;
-constexpr int X4_WARPS = X4_THREADS / 32;
-constexpr int X4_YS = 3, X4_ZS = 4;  // tiles per warp and slab group in stages Y / Z (upper bounds)
-
+// geometry of the +-kx-paired stage-X image of per_cross_kernel (read by per_xf5_kernel): pitch RXp == 8 (mod 16)
 struct X4Layout {
-  int M, W, H, FP, RX, RXp, RY, K2, SPI;
-  int o_red, o_x, o_yin, o_z, total;  // in doubles
+  int M, W, RXp;
   X4Layout() {}
-  X4Layout(int n, int F, size_t smem_limit_bytes) {
-    M = n + 1;
-    W = 2 * n + 1;
-    H = F / 2 + 1;
-    FP = ((F + 3) / 4) * 4 + 2;
-    RX = M * M * 4;
-    RXp = ((RX + 7) / 16) * 16 + 8;
-    RY = 2 * M;
-    K2 = 2 * n + 1;
-    o_red = 0;
-    o_x = 64;
-    o_yin = o_x + 2 * M * RXp;
-    o_z = o_yin + F * K2 * RY;
-    // slabs per iteration: as many as fit (at most 10), without a short last iteration
-    SPI = 10;
-    while (SPI > 1 && (size_t)(o_z + zin_per_slab() * SPI) * 8 > smem_limit_bytes) --SPI;
-    SPI &= ~1;  // two half-CTA pipelines of SPI / 2 slabs each
-    if (SPI < 2) SPI = 2;
-    while (SPI > 2 && (F + SPI / 2 - 1) / (SPI / 2) == (F + SPI / 2 - 2) / (SPI / 2 - 1)) SPI -= 2;  // same #groups
-    // tiles per warp (8 warps per half) must fit the unrolled slots: X4_YS = 3, X4_ZS = 4
-    while (SPI > 2 && ((SPI / 2) * RY > 3 * 64 || (SPI / 2) * F > 4 * 64)) SPI -= 2;
-    total = o_z + zin_per_slab() * SPI;
-    if ((SPI / 2) * RY > 3 * 64 || (SPI / 2) * F > 4 * 64) total = 1 << 30;  // does not fit: other kernels
-  }
-  __host__ __device__ int zin_per_slab() const { return 2 * M * FP; }
   __host__ __device__ int ximg_doubles() const { return 2 * M * RXp; }
 };
 
 // Cross-spectrum of one pair in the E/O form stage X consumes (a10, periodicAlignment.py:433-438 /
 // fastbulk.f90:441-454,667-683): C[k] = sum_g SA_g[k] conj(SB_g[k]) exp(-|k|^2 sigma^2), then for
 // +-kx: E = C(+) + C(-), O = C(+) - C(-), written as the shared-memory image [E | O][kx = 0..n][RXp]
-// of per_xf4_kernel.  This is the only phase that reads the structure-factor bank (231 KB per
+// of per_xf5_kernel.  This is the only phase that reads the structure-factor bank (231 KB per
 // BLJ256 pair from HBM); it used to be phase 1 of the transform kernel, where ncu showed its load
 // latency exposed (one CTA per SM) -- as a separate kernel it runs at full occupancy and the
-// transform kernel prefetches the 65 KB image of its next pair with cp.async.
+// transform kernel reads the image of its next pair from L2.
 __global__ void __launch_bounds__(256, 4)
 per_cross_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__ bankA,
                  const double2* __restrict__ bankB, const long long* __restrict__ pairs, int ngroups, int n,
@@ -1307,276 +1277,8 @@ per_cross_kernel(const __grid_constant__ X4Layout L, const double2* __restrict__
   }
 }
 
-template <int KS, int NT, bool WANT_GRID>
-__global__ void __launch_bounds__(X4_THREADS, 1)
-per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ ximg, int npairs, int n, int F,
-               XfOut out) {
-  extern __shared__ double sm4[];
-  const int M = L.M, H = L.H, FP = L.FP, RX = L.RX, RXp = L.RXp, RY = L.RY, K2 = L.K2;
-  const int SPI = L.SPI;
-  double* red = sm4 + L.o_red;
-  double* XE = sm4 + L.o_x;             // [M][RXp] (index 0: c0)
-  double* XO = XE + (size_t)M * RXp;    // [M][RXp] (index 0 unused)
-  double* YIN = sm4 + L.o_yin;          // [F][K2][RY]: k = j (c0 / E), k = n + j (O)
-  double* ZIN = sm4 + L.o_z;            // [SPI][2][M][FP]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t4 = lane & 3;
-
-  // stage-X input image of a pair (per_cross_kernel) -> shared memory, asynchronously
-  auto stage_x = [&](int pr) {
-    const double2* src = reinterpret_cast<const double2*>(ximg + (size_t)pr * L.ximg_doubles());
-    double2* dst = reinterpret_cast<double2*>(XE);
-    for (int e = tid; e < M * RXp; e += X4_THREADS) {
-      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + e);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + e) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  if ((int)blockIdx.x < npairs) stage_x(blockIdx.x);
-  SymMma<KS, NT> mm;
-  mm.init(n, F, H, lane);
-  // phase-3 geometry of this warp's tiles (the same for every slab group and pair)
-  const int half = warp >> 3, wq = warp & 7;
-  const int SPH = SPI >> 1;  // slabs per group of one half (the layout keeps SPI even)
-  double* Zh = ZIN + (size_t)half * SPH * L.zin_per_slab();
-  unsigned long long* sbest = reinterpret_cast<unsigned long long*>(red + 48);
-  int y_off[X4_YS], zrow_off[X4_YS], z_off[X4_ZS];
-#pragma unroll
-  for (int sI = 0; sI < X4_YS; ++sI) {
-    int r = (wq + 8 * sI) * 8 + g;
-    if (r >= SPH * RY) r = 0;
-    const int sl = r / RY, lp = r - sl * RY;
-    y_off[sI] = sl * K2 * RY + lp;
-    zrow_off[sI] = sl * L.zin_per_slab() + (lp & 1) * M * FP + (lp >> 1) * FP;
-  }
-#pragma unroll
-  for (int sI = 0; sI < X4_ZS; ++sI) {
-    int r = (wq + 8 * sI) * 8 + g;
-    if (r >= SPH * F) r = (wq + 8 * sI) * 8 < SPH * F ? (wq + 8 * sI) * 8 : 0;
-    const int sl = r / F, dy = r - sl * F;
-    z_off[sI] = sl * L.zin_per_slab() + dy;
-  }
-
-  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-    if (tid == 0) *sbest = 0ull;  // +0.0: |f| >= 0, and only strictly smaller tiles are filtered
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    // ---- phase 2: stage X; tile = 8 rows; row bits: 0 = part, 1 = s  (partners: lane ^ 4, lane ^ 8)
-    for (int tile = warp; tile * 8 < RX; tile += X4_WARPS) {
-      const int row = tile * 8 + g;
-      const bool valid = row < RX;
-      const int r = valid ? row : 0;
-      const int part = r & 1, s = (r >> 1) & 1, jl = r >> 2;
-      const int j = jl / M, l = jl - j * M;
-      const double sgn = part ? -1.0 : 1.0;
-      const int krow = (s == 0) ? j : n + j;  // s = 0 lanes store c0 / E, s = 1 lanes store O
-      const bool store = valid && !(j == 0 && s == 1);
-      double P[NT][2], Q[NT][2];
-      mm.run(XE + RXp + r - g, XO + RXp + r - g, RXp, n, XE[r], lane, P, Q);
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int d = nt * 8 + t4 * 2 + q;
-          const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
-          const double ud = fma(sgn, qx, P[nt][q]);   // U[d]   = P - iQ
-          const double um = fma(-sgn, qx, P[nt][q]);  // U[F-d] = P + iQ
-          const double xd = __shfl_xor_sync(0xffffffffu, ud, 8);
-          const double xm = __shfl_xor_sync(0xffffffffu, um, 8);
-          const double vd = (j == 0) ? ud : (s == 0 ? ud + xd : xd - ud);
-          const double vm = (j == 0) ? um : (s == 0 ? um + xm : xm - um);
-          if (store && d < H) {
-            YIN[((size_t)d * K2 + krow) * RY + l * 2 + part] = vd;
-            if (d != 0 && 2 * d != F) YIN[((size_t)(F - d) * K2 + krow) * RY + l * 2 + part] = vm;
-          }
-        }
-    }
-    __syncthreads();
-    if (pair + (int)gridDim.x < npairs) stage_x(pair + gridDim.x);  // lands during phase 3
-    // ---- phase 3: slabs.  The two halves of the CTA (8 warps each, named barriers 1 and 2) run their
-    // own Y -> Z pipelines on alternating groups of SPH slabs, each in its own half of ZIN: a half
-    // waiting at its barrier leaves the tensor pipe to the other one (ncu on the single-pipeline
-    // version: 20 % of the samples at CTA-wide barriers).
-    // Arg-max at half scale: accumulators start at v0/2, the two outputs of a column are
-    // 2 |A + B| and 2 |A - B|, their maximum is 2 (|A| + |B|): one DADD + one max per column.  Only a
-    // tile that beats both the thread's and the CTA's running maximum (sbest: shared, monotone,
-    // read early as a filter) is examined column by column.
-    double bvh = -1.0;
-    int bi = 0x7fffffff;
-    for (int x0 = half * SPH; x0 < F; x0 += 2 * SPH) {
-      const int ns = min(SPH, F - x0);
-      // stage Y: rows (slab, l, part)
-#pragma unroll
-      for (int sI = 0; sI < X4_YS; ++sI) {
-        const int row = (wq + 8 * sI) * 8 + g;
-        if ((wq + 8 * sI) * 8 >= ns * RY) break;
-        const bool valid = row < ns * RY;
-        const int part = y_off[sI] & 1;
-        const double* Y = YIN + (size_t)x0 * K2 * RY + y_off[sI];
-        double* Zrow = Zh + zrow_off[sI];
-        const double sgn = part ? -1.0 : 1.0;
-        double P[NT][2], Q[NT][2];
-        mm.run(Y + RY - g, Y + (size_t)(n + 1) * RY - g, RY, n, Y[0], lane, P, Q);
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int d = nt * 8 + t4 * 2 + q;
-            // V[d] = P - iQ, V[F-d] = P + iQ: re rows need the partner's Q_im, im rows its Q_re
-            const double qx = __shfl_xor_sync(0xffffffffu, Q[nt][q], 4);
-            if (valid && d < H) {
-              Zrow[d] = fma(sgn, qx, P[nt][q]);
-              if (d != 0 && 2 * d != F) Zrow[F - d] = fma(-sgn, qx, P[nt][q]);
-            }
-          }
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(X4_THREADS / 2) : "memory");
-      // stage Z: rows (slab, dy)
-#pragma unroll
-      for (int sI = 0; sI < X4_ZS; ++sI) {
-        const int r0 = (wq + 8 * sI) * 8;
-        if (r0 >= ns * F) break;
-        const bool valid = r0 + g < ns * F;
-        const int r = valid ? r0 + g : r0;
-        const double sb = __longlong_as_double(*sbest);
-        const double* ZR = Zh + z_off[sI];
-        const double* ZI = ZR + (size_t)M * FP;
-        const int base = (x0 * F + r) * F;
-        const double v0h = 0.5 * ZR[0];
-        double A[NT][2], B[NT][2];
-        mm.run(ZR + FP - g, ZI + FP - g, FP, n, v0h, lane, A, B);
-        // Filter on the high word of |A| + |B| (non-negative doubles order like their bit patterns): one
-        // DADD + one integer max per column, off the FP64 pipe; a tile within 2^-20 of the running
-        // maximum (or holding a NaN) falls through to the exact column-by-column comparison.
-        int chi = 0;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int d = nt * 8 + t4 * 2 + q;
-            const double c = fabs(A[nt][q]) + fabs(B[nt][q]);
-            if ((nt + 1) * 8 <= H || d < H) chi = max(chi, __double2hiint(c));
-            if (WANT_GRID) {
-              if (valid && d < H) {
-                double* grow = out.grid + ((size_t)pair * F * F * F + (size_t)base);
-                grow[d] = 2.0 * fabs(A[nt][q] + B[nt][q]);
-                if (d != 0 && 2 * d != F) grow[F - d] = 2.0 * fabs(A[nt][q] - B[nt][q]);
-              }
-            }
-          }
-        if (valid && chi >= __double2hiint(fmax(sb, bvh))) {
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int d = nt * 8 + t4 * 2 + q;
-              const double g1 = d < H ? fabs(A[nt][q] + B[nt][q]) : -2.0;
-              const double g2 = (d < H && d != 0 && 2 * d != F) ? fabs(A[nt][q] - B[nt][q]) : -2.0;
-              better32(bvh, bi, g1, base + d);
-              better32(bvh, bi, g2, base + (F - d));
-            }
-          if (bvh > sb) atomicMax(sbest, (unsigned long long)__double_as_longlong(bvh));
-        }
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(X4_THREADS / 2) : "memory");
-    }
-    double bv = 2.0 * bvh;
-    if (bvh < 0.0) bv = -1.0;
-    // ---- phase 4: block arg-max (numpy order) and parabola neighbours
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_down_sync(0xffffffffu, bv, off);
-      const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-      better32(bv, bi, ov, oi);
-    }
-    int* redi = reinterpret_cast<int*>(red + 32);
-    if ((tid & 31) == 0) {
-      red[tid >> 5] = bv;
-      redi[tid >> 5] = bi;
-    }
-    __syncthreads();
-    // twiddle table for the parabola neighbours in the (now dead) ZIN region, built by warps 1.. while
-    // warp 0 finishes the arg-max
-    double2* twz = reinterpret_cast<double2*>(ZIN);
-    for (int t = tid - 32; t >= 0 && t < F; t += X4_THREADS - 32) {
-      double sn, cs;
-      sincospi(2.0 * (double)t / (double)F, &sn, &cs);
-      twz[t] = make_double2(cs, sn);
-    }
-    if (tid < 32) {
-      bv = (tid < X4_THREADS / 32) ? red[tid] : -1.0;
-      bi = (tid < X4_THREADS / 32) ? redi[tid] : 0x7fffffff;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-        better32(bv, bi, ov, oi);
-      }
-      if (tid == 0) {
-        red[0] = bv;
-        redi[0] = bi;
-      }
-    }
-    __syncthreads();
-    bv = red[0];
-    bi = redi[0];
-    const bool ok = (bi != 0x7fffffff) && isfinite(bv);
-    const int bx = ok ? bi / (F * F) : 0;
-    const int by = ok ? (bi / F) % F : 0;
-    const int bz = ok ? bi % F : 0;
-    __syncthreads();
-    {
-      const int w = tid >> 5, lane = tid & 31;
-      if (w < 6) {
-        const int ax = w >> 1, sgn = (w & 1) ? -1 : 1;
-        int px = bx, py = by, pz = bz;
-        if (ax == 0) px = (bx + sgn + F) % F;
-        if (ax == 1) py = (by + sgn + F) % F;
-        if (ax == 2) pz = (bz + sgn + F) % F;
-        const double* Y = YIN + (size_t)px * K2 * RY;
-        double acc = 0.0;
-        for (int e = lane; e < M * M; e += 32) {
-          const int j = e / M, l = e - j * M;
-          const double2 wj = twz[(j * py) % F], wl = twz[(l * pz) % F];
-          const double sj = wj.y, cj = wj.x, sl_ = wl.y, cl = wl.x;
-          double vr, vi;
-          if (j == 0) {
-            vr = Y[l * 2];
-            vi = Y[l * 2 + 1];
-          } else {
-            const double er = Y[(size_t)j * RY + l * 2], ei = Y[(size_t)j * RY + l * 2 + 1];
-            const double orr = Y[(size_t)(n + j) * RY + l * 2], oi = Y[(size_t)(n + j) * RY + l * 2 + 1];
-            vr = er * cj + oi * sj;   // Re(E cos - i O sin)
-            vi = ei * cj - orr * sj;  // Im
-          }
-          const double term = vr * cl + vi * sl_;
-          acc += (l == 0) ? term : 2.0 * term;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-        if (lane == 0) red[2 + w] = fabs(acc);
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      out.best_idx[3 * (size_t)pair + 0] = bx;
-      out.best_idx[3 * (size_t)pair + 1] = by;
-      out.best_idx[3 * (size_t)pair + 2] = bz;
-      out.best_val[pair] = bv;
-      const int b3[3] = {bx, by, bz};
-      for (int ax = 0; ax < 3; ++ax) {
-        const double y1 = red[2 + 2 * ax], y3 = red[2 + 2 * ax + 1], y2 = bv;
-        const double d = (y3 - y1) / (2.0 * (2.0 * y2 - y1 - y3));
-        out.frac_idx[3 * (size_t)pair + ax] = (double)b3[ax] - d;
-      }
-      if (out.status) out.status[pair] = ok ? FO_STATUS_OK : FO_STATUS_NONFINITE;
-    }
-    // no barrier here: the barrier at the top of the loop orders the reuse of red / YIN
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// per_cross6_kernel + per_xf6_kernel: the transform of per_xf4_kernel with every stage in the "transposed" DMMA
+// per_cross6_kernel + per_xf6_kernel: the pruned 3-D DFT + |.| + arg-max with every stage in the "transposed" DMMA
 // form (twiddles = A operand, data = B operand) and stages Y and Z chained in REGISTERS.
 //
 // * Transposed form.  The C fragment of a tile holds (row d = 8 mt + g, columns 2 t, 2 t + 1) = (re, im) of ONE
@@ -1592,7 +1294,7 @@ per_xf4_kernel(const __grid_constant__ X4Layout L, const double* __restrict__ xi
 // * Stage Y -> Z: a lane's C fragment of row tile mt, column tile ct holds V at (row dy, l-slot 4 ct + t + 1, re | im)
 //   = exactly the A fragment (row g, k = t) of stage Z's k-step ks = ct.  The Z-stage DMMAs take the Y-stage
 //   accumulators as operands: nothing is written to shared memory between Y and Z, no warp waits for another one
-//   in the slab phase (per_xf4: 14 half-CTA barriers per pair), and the 40 KB Z-input buffers are gone.  l-slot
+//   in the slab phase (round 1: 14 half-CTA barriers per pair), and the 40 KB Z-input buffers are gone.  l-slot
 //   s = 1..n is harmonic l = s; l = 0 rides in slot n + 1, whose X / Y twiddles are zero (m > K) and whose Z
 //   twiddle is the weight of the l = 0 term, so all three stages use ONE register-resident twiddle table
 //   (cos / sin (2 pi m d / F) at m = 4 ks + t + 1, d = 8 nt + g is symmetric in the roles of m and d).
@@ -1806,7 +1508,8 @@ per_xf6_kernel(const __grid_constant__ X6Layout L, const double* __restrict__ xi
       fo_mbar_arrive_expect_tx(xbar, ximg_bytes);
       fo_bulk_g2s(XE, ximg + (size_t)(pair + gridDim.x) * L.ximg_doubles(), ximg_bytes, xbar);
     }
-    // ---- slabs: stage Y -> stage Z in registers, arg-max at half scale (see per_xf4_kernel).
+    // ---- slabs: stage Y -> stage Z in registers, arg-max at half scale: the two outputs of a column are
+    // 2 |A + B| and 2 |A - B|, their maximum is 2 (|A| + |B|).
     // Work item = (slab dx, row tile mt), dealt round-robin to the warps.
     long long bbits = __double_as_longlong(-1.0);  // running maximum (half scale) as a bit pattern
     int bi = 0x7fffffff;
@@ -2026,12 +1729,12 @@ per_xf6_kernel(const __grid_constant__ X6Layout L, const double* __restrict__ xi
 }
 
 // ------------------------------------------------------------------------------------------
-// K_xf for fine k-grids (per_xf5_kernel<NT>): the stages of per_xf4_kernel when neither the stage-X
+// K_xf for fine k-grids (per_xf5_kernel<NT>): the stages with a shared-memory hand-over when neither the stage-X
 // image nor YIN (646 KB per pair at n = 16, 4.6 MB at n = 32) fit in shared memory.
 //   * stage X reads its E / O fragments straight from the image per_cross_kernel wrote (L2) and writes
 //     YIN[dx][ky][l] to a per-CTA global scratch;
 //   * slabs: YIN[dx] (K2 RY doubles) is staged into shared memory with cp.async, double buffered, SPI
-//     slabs at a time; stages Y and Z as in per_xf4_kernel; arg-max with the high-word filter;
+//     slabs at a time; stages Y and Z as SymMma row tiles; arg-max with the high-word filter;
 //   * the twiddle matrices live in shared memory (B fragments: one 8-byte load per DMMA) -- with up to
 //     8 x 9 fragment pairs they do not fit the register file.
 // One persistent 512-thread CTA per SM.  NT = ceil((F/2+1)/8) column tiles (template), any n.
@@ -2479,7 +2182,7 @@ bool xf6_applies(fo_ctx* ctx, int n, int F, X6Layout* lay, int* code_out) {
   const int code = KS * 10 + NT;
   if (lay) *lay = lay6;
   if (code_out) *code_out = code;
-  return (size_t)lay6.total * 8 <= ctx->prop.sharedMemPerBlockOptin && !ctx->force_generic && ctx->xf_variant != 4 &&
+  return (size_t)lay6.total * 8 <= ctx->prop.sharedMemPerBlockOptin && !ctx->force_generic &&
          2 * n + 1 <= 129 && (code == 11 || code == 12 || code == 22 || code == 23 || code == 33);
 }
 
@@ -2534,43 +2237,6 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
       FO_LAUNCH_CHECK(ctx);
       return launch_xf6_image(ctx, lay6, code, (const double*)ximg, npairs, n, F, out);
     }
-  }
-  {  // tensor-core path: everything resident in shared memory, 1-D transforms as DMMA tiles
-    const X4Layout lay4(n, F, optin);
-    const size_t smem4 = (size_t)lay4.total * 8;
-    const int KS = (n + 3) / 4, NT = (lay4.H + 7) / 8;
-#define FO_X4_LAUNCH(KS_, NT_)                                                                           \
-  do {                                                                                                   \
-    if (out.grid) {                                                                                      \
-      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<KS_, NT_, true>,                                  \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));       \
-      per_xf4_kernel<KS_, NT_, true><<<blocks, X4_THREADS, smem4, ctx->stream>>>(                        \
-          lay4, (const double*)ximg, (int)npairs, n, F, out);                                            \
-    } else {                                                                                             \
-      FO_CUDA(ctx, cudaFuncSetAttribute(per_xf4_kernel<KS_, NT_, false>,                                 \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));       \
-      per_xf4_kernel<KS_, NT_, false><<<blocks, X4_THREADS, smem4, ctx->stream>>>(                       \
-          lay4, (const double*)ximg, (int)npairs, n, F, out);                                            \
-    }                                                                                                    \
-  } while (0)
-    const int code = KS * 10 + NT;
-    if (smem4 <= optin && !ctx->force_generic && 2 * n + 1 <= 129 &&
-        (code == 11 || code == 12 || code == 22 || code == 23 || code == 33)) {
-      void* ximg = nullptr;
-      FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay4.ximg_doubles() * 8, &ximg));
-      fo_prof_scope prof(ctx, FO_PROF_PER_XF);
-      per_cross_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay4, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
-                                                                ky, kz, p->sigma, (double*)ximg);
-      FO_LAUNCH_CHECK(ctx);
-      if (code == 11) FO_X4_LAUNCH(1, 1);
-      else if (code == 12) FO_X4_LAUNCH(1, 2);
-      else if (code == 22) FO_X4_LAUNCH(2, 2);
-      else if (code == 23) FO_X4_LAUNCH(2, 3);
-      else FO_X4_LAUNCH(3, 3);
-      FO_LAUNCH_CHECK(ctx);
-      return FO_OK;
-    }
-#undef FO_X4_LAUNCH
   }
   {  // tensor-core path for fine k-grids: stage-X image and YIN in global memory (L2), slabs staged
     const int NT5 = (F / 2 + 1 + 7) / 8;

@@ -1,8 +1,9 @@
 """Small-shape pass through every kernel family, meant to run under compute-sanitizer:
     compute-sanitizer --tool memcheck  python scripts/sanitize_small.py
     compute-sanitizer --tool racecheck python scripts/sanitize_small.py
-(the mbarrier hand-over of per_sf3_kernel, the named barriers of per_xf4_kernel, the cp.async / bulk-copy staging
-and the shared-memory reductions of the screening kernels are what racecheck is pointed at)."""
+(the mbarrier hand-over of per_sf3_kernel / per_sfx_kernel and its tensor-memory stash, the bulk-copy staging of
+per_xf6_kernel / sph_isoft4_kernel, the cp.async staging and the shared-memory
+reductions of the screening kernels are what racecheck is pointed at)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -64,3 +65,20 @@ X -= X.mean(1, keepdims=True)
 ctx.set_perm([np.arange(70)], 70)
 print("N 70", ctx.sph_align_pairs(X, X[::-1].copy(), 12, 0.45, invert=True)[1][0], flush=True)
 print("launches", ctx.launch_count(), flush=True)
+
+# older kernel variants kept for A/B and for grids outside the fast paths: bank path (per_sf3 + per_cross6 + per_xf6),
+# sph_isoft3 (stage A -> shared memory -> stage B), even Jmax (two planes per CTA)
+wl = bench.Blj256()
+wl.setup(ctx)
+A, B, _ = wl.make(4, 1)
+ctx.set_option("per_pairs_fused", 0)
+print("blj256 bank path", ctx.per_align_pairs(wl.params, A, B)[1][:2], flush=True)
+ctx.set_option("per_pairs_fused", 1)
+wl = bench.Lj38()
+wl.setup(ctx)
+A, B, _ = wl.make(4, 1)
+ctx.set_option("sph_isoft_variant", 3)
+print("lj38 isoft3", ctx.sph_align_pairs(A, B, 15, 0.3, invert=True)[1][0], flush=True)
+ctx.set_option("sph_isoft_variant", 0)
+print("lj38 Jmax 14", ctx.sph_align_pairs(A, B, 14, 0.3, invert=True)[1][0], flush=True)
+print("lj38 Jmax 7", ctx.sph_align_pairs(A, B, 7, 0.3, invert=True)[1][0], flush=True)
