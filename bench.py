@@ -82,9 +82,9 @@ class Blj256:
                             "configs[4] batching)", "natoms": 256, "species": [204, 52],
                 "nwave": self.n, "nfspace": self.F, "pairs_per_step_per_gpu": pairs,
                 "seed": 256, "l2_policy": "inputs + intermediates per step exceed L2 "
-                "(coords %.0f MB per step, structure-factor bank %.0f MB per chunk of 3256 pairs through host "
-                "buffers, up to three times that device-resident)" % (
-                    2 * pairs * 256 * 24 / 1e6, 3256 * 2 * 2 * 3610 * 16 / 1e6)}
+                "(coords %.0f MB per step, stage-X images %.0f MB per chunk of 3256 pairs through host "
+                "buffers, up to three times that device-resident; no structure-factor bank on this path)" % (
+                    2 * pairs * 256 * 24 / 1e6, 3256 * 2 * 10 * 392 * 8 / 1e6)}
 
     def make(self, pairs, rank):
         rng = np.random.default_rng(256 + 7919 * rank)

@@ -65,6 +65,9 @@ SIGNATURES = {
     "fo_per_align_bank": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p,
                                          ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p]),
+    "fo_per_align_bank_ops": (ctypes.c_int, [c_void_p, ctypes.POINTER(PerParams), c_void_p, c_void_p, c_void_p,
+                                             ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p]),
     "fo_bank_destroy": (None, [c_void_p, c_void_p]),
     "fo_sph_ylm": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void_p,
                                   c_void_p, c_void_p]),
@@ -504,6 +507,25 @@ class Context(object):
         self._check(self._lib.fo_per_align_bank(self._h, ctypes.byref(params), bank._h, _ptr(pairs),
                                                 P, _ptr(bi), _ptr(bv), _ptr(fr), _ptr(grid),
                                                 _ptr(st)), "fo_per_align_bank")
+        return bi, bv, fr, grid, st
+
+    def per_align_bank_ops(self, params, bank, pairs, ops, want_grid=False):
+        """per_align_bank with a signed permutation matrix per pair (ops: (P, 3, 3), cubic box): structure B of
+        pair i is taken as ops[i] @ B -- an index permutation of its bank entry, no new structure factors."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        P = pairs.shape[0]
+        ops = np.asarray(ops, float).reshape(P, 3, 3)
+        codes = np.zeros(P, np.int32)
+        for i in range(3):  # (R r)_i = s_i r_{p_i}
+            pi = np.argmax(np.abs(ops[:, i, :]), axis=1)
+            si = ops[np.arange(P), i, pi]
+            if not np.allclose(np.abs(ops[:, i, :]).sum(1), 1.0) or not np.allclose(np.abs(si), 1.0):
+                raise ValueError("ops must be signed permutation matrices")
+            codes |= (pi.astype(np.int32) << (2 * i)) | ((si < 0).astype(np.int32) << (6 + i))
+        bi, bv, fr, grid, st = self._per_outputs(P, params.nfspace, want_grid)
+        self._check(self._lib.fo_per_align_bank_ops(self._h, ctypes.byref(params), bank._h, _ptr(pairs), _ptr(codes),
+                                                    P, _ptr(bi), _ptr(bv), _ptr(fr), _ptr(grid), _ptr(st)),
+                    "fo_per_align_bank_ops")
         return bi, bv, fr, grid, st
 
     # -- spherical

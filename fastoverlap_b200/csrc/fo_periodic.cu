@@ -1338,8 +1338,9 @@ struct X6Layout {
 // YIN slab = (row, l, re | im).
 __global__ void __launch_bounds__(256, 3)
 per_cross6_kernel(const __grid_constant__ X6Layout L, const double2* __restrict__ bankA,
-                  const double2* __restrict__ bankB, const long long* __restrict__ pairs, int ngroups, int n,
-                  double kx, double ky, double kz, double sigma, double* __restrict__ ximg) {
+                  const double2* __restrict__ bankB, const long long* __restrict__ pairs,
+                  const int32_t* __restrict__ ops, int ngroups, int n, double kx, double ky, double kz, double sigma,
+                  double* __restrict__ ximg) {
   __shared__ double damp[3 * 129];
   const int M = L.M, W = 2 * n + 1, RXp = L.RXp, RY = L.RY;
   const int tid = threadIdx.x;
@@ -1358,11 +1359,40 @@ per_cross6_kernel(const __grid_constant__ X6Layout L, const double2* __restrict_
   const double2* SB = bankB + (size_t)ib * bank_stride;
   double* XE = ximg + pair * (size_t)L.ximg_doubles();
   double* XO = XE + (size_t)M * RXp;
+  // Cell symmetry of a cubic box (O_h, fastbulk.f90:863-1380 OHTRANSFORMCOEFFS): structure B is taken as R B with
+  // the signed permutation (R r)_i = s_i r_{p_i}.  S_{RB}(k) = S_B(R^T k), (R^T k)_{p_i} = s_i k_i: an index
+  // permutation of B's bank entry (conjugated where the image has kz < 0: the bank holds kz >= 0), no new
+  // structure factors.  op = p_0 | p_1 << 2 | p_2 << 4 | (s_i < 0) << (6 + i); 0x24 = identity.
+  const int op = ops ? ops[pair] : 0x24;
+  const int opp[3] = {op & 3, (op >> 2) & 3, (op >> 4) & 3};
+  const int ops_[3] = {(op >> 6) & 1, (op >> 7) & 1, (op >> 8) & 1};
   auto cross = [&](int ix, int iy, int l) {
     const size_t e = ((size_t)ix * W + iy) * M + l;
+    size_t eb = e;
+    double cj = 1.0;
+    if (ops) {
+      const int k[3] = {ix - n, iy - n, l};
+      int kb[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int v = ops_[i] ? -k[i] : k[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (opp[i] == j) kb[j] = v;
+      }
+      if (kb[2] < 0) {
+        kb[0] = -kb[0];
+        kb[1] = -kb[1];
+        kb[2] = -kb[2];
+        cj = -1.0;
+      }
+      eb = ((size_t)(kb[0] + n) * W + (kb[1] + n)) * M + kb[2];
+    }
     double re = 0.0, im = 0.0;
     for (int gq = 0; gq < ngroups; ++gq) {
-      const double2 a = SA[(size_t)gq * c_elems + e], b = SB[(size_t)gq * c_elems + e];
+      const double2 a = SA[(size_t)gq * c_elems + e];
+      double2 b = SB[(size_t)gq * c_elems + eb];
+      b.y *= cj;
       re += a.x * b.x + a.y * b.y;
       im += a.y * b.x - a.x * b.y;
     }
@@ -2217,7 +2247,7 @@ int launch_xf6_image(fo_ctx* ctx, const X6Layout& lay6, int code, const double* 
 }
 
 int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const double2* d_bankB,
-              const long long* d_pairs, int64_t npairs, XfOut out) {
+              const long long* d_pairs, int64_t npairs, XfOut out, const int32_t* d_ops = nullptr) {
   if (npairs == 0) return FO_OK;
   const int n = (int)p->nwave, F = (int)p->nfspace;
   const int ngroups = (int)ctx->h_goff.size() - 1;
@@ -2232,12 +2262,14 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
       void* ximg = nullptr;
       FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay6.ximg_doubles() * 8, &ximg));
       fo_prof_scope prof(ctx, FO_PROF_PER_XF);
-      per_cross6_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay6, d_bankA, d_bankB, d_pairs, ngroups, n, kx,
-                                                                 ky, kz, p->sigma, (double*)ximg);
+      per_cross6_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(lay6, d_bankA, d_bankB, d_pairs, d_ops, ngroups, n,
+                                                                 kx, ky, kz, p->sigma, (double*)ximg);
       FO_LAUNCH_CHECK(ctx);
       return launch_xf6_image(ctx, lay6, code, (const double*)ximg, npairs, n, F, out);
     }
   }
+  if (d_ops)
+    return fo_fail(ctx, FO_ERR_UNSUPPORTED, "cell-symmetry operations need the resident transform (nwave <= 11)");
   {  // tensor-core path for fine k-grids: stage-X image and YIN in global memory (L2), slabs staged
     const int NT5 = (F / 2 + 1 + 7) / 8;
     const X5Layout lay5(n, F, NT5, optin);
@@ -2859,11 +2891,30 @@ extern "C" int fo_per_bank_create(fo_ctx* ctx, const fo_per_params* p, const dou
   return FO_OK;
 }
 
+extern "C" int fo_per_align_bank_ops(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank, const int64_t* pairs,
+                                     const int32_t* ops, int64_t npairs, int64_t* best_idx, double* best_val,
+                                     double* frac_idx, double* grid_out, int32_t* status);
+
 extern "C" int fo_per_align_bank(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank,
                                  const int64_t* pairs, int64_t npairs, int64_t* best_idx,
                                  double* best_val, double* frac_idx, double* grid_out,
                                  int32_t* status) {
+  return fo_per_align_bank_ops(ctx, p, bank, pairs, nullptr, npairs, best_idx, best_val, frac_idx, grid_out, status);
+}
+
+extern "C" int fo_per_align_bank_ops(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank, const int64_t* pairs,
+                                     const int32_t* ops, int64_t npairs, int64_t* best_idx, double* best_val,
+                                     double* frac_idx, double* grid_out, int32_t* status) {
   FO_CHECK(check_params(ctx, p));
+  if (ops) {
+    if (!(p->box[0] == p->box[1] && p->box[1] == p->box[2]))
+      return fo_fail(ctx, FO_ERR_INVALID, "cell-symmetry operations need a cubic box");
+    for (int64_t i = 0; i < npairs; ++i) {
+      const int o = ops[i], a = o & 3, b = (o >> 2) & 3, c = (o >> 4) & 3;
+      if (o < 0 || o >= 512 || a > 2 || b > 2 || c > 2 || a == b || a == c || b == c)
+        return fo_fail(ctx, FO_ERR_INVALID, "operation %lld is not a signed permutation code", (long long)i);
+    }
+  }
   if (!bank || bank->kind != 1) return fo_fail(ctx, FO_ERR_INVALID, "not a periodic bank");
   if (bank->nwave != p->nwave || bank->ngroups != (int64_t)ctx->h_goff.size() - 1)
     return fo_fail(ctx, FO_ERR_INVALID, "bank was built with different nwave / perm groups");
@@ -2883,16 +2934,19 @@ extern "C" int fo_per_align_bank(fo_ctx* ctx, const fo_per_params* p, const fo_b
   if (chunk > npairs) chunk = npairs;
   void *dOut, *dGrid = nullptr, *dPairs;
   FO_CHECK(fo_scratch(ctx, FO_SCR_OUT, (size_t)chunk * 64, &dOut));
-  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 16, &dPairs));
+  FO_CHECK(fo_scratch(ctx, FO_SCR_MISC, (size_t)chunk * 20, &dPairs));
+  int32_t* dOps = ops ? (int32_t*)((char*)dPairs + (size_t)chunk * 16) : nullptr;
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
   HostOut h = {best_idx, best_val, frac_idx, grid_out, status};
   for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
     const int64_t np = (npairs - p0 < chunk) ? npairs - p0 : chunk;
     FO_CUDA(ctx, cudaMemcpyAsync(dPairs, pairs + 2 * p0, (size_t)np * 16, cudaMemcpyHostToDevice,
                                  ctx->stream));
+    if (ops)
+      FO_CUDA(ctx, cudaMemcpyAsync(dOps, ops + p0, (size_t)np * 4, cudaMemcpyHostToDevice, ctx->stream));
     XfOut out = make_out((char*)dOut, np, (double*)dGrid, status != nullptr);
     FO_CHECK(launch_xf(ctx, p, (const double2*)bank->d_data, (const double2*)bank->d_data,
-                       (const long long*)dPairs, np, out));
+                       (const long long*)dPairs, np, out, dOps));
     FO_CHECK(copy_out(ctx, p, p0, np, (const char*)dOut, (const double*)dGrid, h));
     FO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }

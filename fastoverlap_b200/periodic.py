@@ -209,10 +209,26 @@ class PeriodicAlign(BasePeriodicAlignment):
         ops = oh_operations()
         X2s = np.einsum("oij,aj->oai", ops, pos2)
         X1s = np.broadcast_to(pos1, X2s.shape).copy()
-        dists, disps, perms = self.align_batch(X1s, X2s, nthreads=nthreads)
+        p = self._params()
+        if self.n <= 11:
+            # structure factors once per structure; the 48 images of pos2 are index permutations of its bank entry
+            # inside the cross-spectrum (OHTRANSFORMCOEFFS, fastbulk.f90:863-1380), then the host pool refines
+            bank = self.ctx.per_bank_create(p, np.stack([pos1, pos2]))
+            try:
+                fr = self.ctx.per_align_bank_ops(p, bank, np.tile([0, 1], (len(ops), 1)), ops)[2]
+            finally:
+                bank.close()
+            dists = _lib.host_refine_periodic(p, self.perm, X1s, X2s, fr, niter=10, nthreads=nthreads)[0]
+        else:  # fine k-grids: the images go through the batched hot path as independent pairs
+            dists, disps, perms = self.align_batch(X1s, X2s, nthreads=nthreads)
+            fr = None
         best = int(np.argmin(dists))
-        bi, bv, fr, _, st = self.ctx.per_align_pairs(self._params(), pos1, X2s[best])
-        res = self.refine(pos1, X2s[best], (fr[0] * self.boxvec / np.array(self.fshape, float))[None, :])
+        if fr is None:
+            fr = self.ctx.per_align_pairs(p, pos1, X2s[best])[2]
+            best_fr = fr[0]
+        else:
+            best_fr = fr[best]
+        res = self.refine(pos1, X2s[best], (best_fr * self.boxvec / np.array(self.fshape, float))[None, :])
         return tuple(res) + (ops[best],)
 
     # -- batched, additive API

@@ -199,6 +199,15 @@ int fo_per_bank_create(fo_ctx* ctx, const fo_per_params* p, const double* pos /*
 int fo_per_align_bank(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank,
                       const int64_t* pairs, int64_t npairs, int64_t* best_idx, double* best_val,
                       double* frac_idx, double* grid_out, int32_t* status);
+/* fo_per_align_bank with a cell-symmetry operation per pair (cubic box; the reference's OHCELLT branch: ALIGN1
+ * fastbulk.f90:458-480, OHTRANSFORMCOEFFS fastbulk.f90:863-1380).  Pair i aligns structure A with R_i B, where
+ * (R r)_j = s_j r_{p_j} is a signed permutation, encoded as ops[i] = p_0 | p_1 << 2 | p_2 << 4 | (s_j < 0) << (6 + j).
+ * The structure factors of R B are an index permutation of B's bank entry (S_RB(k) = S_B(R^T k)), so the 48
+ * octahedral images of a structure cost 48 cross-spectra + transforms and no structure-factor pass.
+ * ops = NULL: identity for every pair.  FO_ERR_UNSUPPORTED for nwave > 11. */
+int fo_per_align_bank_ops(fo_ctx* ctx, const fo_per_params* p, const fo_bank* bank, const int64_t* pairs,
+                          const int32_t* ops /*[P] or NULL*/, int64_t npairs, int64_t* best_idx, double* best_val,
+                          double* frac_idx, double* grid_out, int32_t* status);
 void fo_bank_destroy(fo_ctx* ctx, fo_bank* bank);
 
 /* ---------------------------------------------------------------- spherical (fastclusters) */

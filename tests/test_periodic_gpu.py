@@ -288,3 +288,40 @@ def test_oh_cell_symmetries(ctx):
         assert abs(fw.align(pos1, pos2, ohcell=True)[0] - dist) < 1e-9
     with pytest.raises(ValueError):
         PeriodicAlign(N, [5.0, 5.0, 6.0], groups, ctx=ctx).align_oh(pos1, pos1)
+
+
+@pytest.mark.parametrize("N,n,groups", [(40, None, [np.arange(30), np.arange(30, 40)]), (256, 9, None)])
+def test_oh_index_permutation_matches_transformed_coordinates(ctx, N, n, groups):
+    """fo_per_align_bank_ops (OHTRANSFORMCOEFFS, fastbulk.f90:863-1380): the structure factors of the 48 images
+    R B as index permutations of B's bank entry, against the hot path on the explicitly transformed coordinates:
+    same arg-max, same overlap value and interpolated maximum; a non-cubic box and a bad code are refused."""
+    from fastoverlap_b200 import PeriodicAlign, _lib
+    from fastoverlap_b200.utils import oh_operations
+    rng = np.random.default_rng(4848 + N)
+    box = np.array([5.3, 5.3, 5.3])
+    if groups is None:
+        groups = [np.arange(204), np.arange(204, 256)]
+    al = PeriodicAlign(N, box, groups, ctx=ctx) if n is None else PeriodicAlign(N, box, groups, n=n, ctx=ctx)
+    p = al._params()
+    pos1 = rng.uniform(-0.5, 0.5, size=(N, 3)) * box
+    pos2 = pos1.dot(oh_operations()[29].T) + 0.37 + rng.normal(scale=0.02, size=(N, 3))
+    ops = oh_operations()
+    X2s = np.einsum("oij,aj->oai", ops, pos2)
+    ref = ctx.per_align_pairs(p, np.broadcast_to(pos1, X2s.shape).copy(), X2s)
+    bank = ctx.per_bank_create(p, np.stack([pos1, pos2]))
+    got = ctx.per_align_bank_ops(p, bank, np.tile([0, 1], (48, 1)), ops)
+    assert np.array_equal(got[0], ref[0])
+    assert np.allclose(got[1], ref[1], rtol=1e-11)
+    assert np.allclose(got[2], ref[2], atol=1e-6)
+    ident = ctx.per_align_bank(p, bank, [[0, 1]])
+    assert np.array_equal(ident[0][0], got[0][0]) and ident[1][0] == got[1][0]
+    bad = ops.copy()
+    bad[3] = 0.5
+    with pytest.raises(ValueError):
+        ctx.per_align_bank_ops(p, bank, np.tile([0, 1], (48, 1)), bad)
+    bank.close()
+    al2 = PeriodicAlign(N, [5.3, 5.3, 6.0], groups, ctx=ctx)
+    bank2 = ctx.per_bank_create(al2._params(), np.stack([pos1, pos2]))
+    with pytest.raises(_lib.FastOverlapError):
+        ctx.per_align_bank_ops(al2._params(), bank2, [[0, 1]], ops[:1])
+    bank2.close()
