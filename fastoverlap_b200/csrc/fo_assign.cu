@@ -29,6 +29,7 @@ struct PerAssignParams {
   double box[3], ibox[3];
   double F;       // nfspace
   double tolgap;  // smallest accepted gap between a column's nearest and second nearest row
+  float tol32;    // relative bound on the error of a single-precision gap: tol32 (max |coordinate| + max box)
   int natoms, ncols, ngroups, niter;
 };
 
@@ -50,6 +51,7 @@ __device__ __forceinline__ double canon_sum(const double* t, int n, int lane) {
 
 struct PerAssignSmem {
   double *xa, *yb, *xg, *term;  // [3][N] atom order, [3][N], [3][ncols] group order, [3][N]
+  float* xf;                    // [3][ncols] group order, single precision (the nearest-partner search)
   int *perm, *save, *cnt, *cs, *ce;
   double* sc;  // disp[3] dref[3] margin red[8]
 };
@@ -68,10 +70,11 @@ __device__ __forceinline__ PerAssignSmem per_assign_carve(unsigned char* base, i
   s.cnt = s.save + N;
   s.cs = s.cnt + ncols;
   s.ce = s.cs + ncols;
+  s.xf = reinterpret_cast<float*>(s.ce + ncols);
   return s;
 }
 
-size_t per_assign_smem(int N, int ncols) { return ((size_t)9 * N + 3 * ncols + 16) * 8 + ((size_t)2 * N + 3 * ncols) * 4; }
+size_t per_assign_smem(int N, int ncols) { return ((size_t)9 * N + 3 * ncols + 16) * 8 + ((size_t)2 * N + 6 * ncols) * 4; }
 
 // One nearest-partner solve at the displacement in S.sc[0..2]: fills pm (grouped atoms only), returns
 // (block-uniform) whether the column minima form a permutation with every gap > tolgap; S.sc[6] = margin.
@@ -80,32 +83,38 @@ __device__ bool per_assign_solve(const PerAssignParams& P, const PerAssignSmem& 
   const int tid = threadIdx.x, N = P.natoms;
   for (int r = tid; r < P.ncols; r += AS_THREADS) S.cnt[r] = 0;
   __syncthreads();
+  // The search runs in SINGLE precision (the FP32 pipes have twice the FP64 rate and are otherwise idle), like the
+  // host pool's screening pass (colmin_periodic_f32, fo_host.cu): coordinates and the shifted structure are rounded
+  // to float once, every distance carries an absolute error below tol32 / 4, so nearest partners whose runner-up is
+  // more than tol32 further away are the exact nearest partners, and gap - tol32 is a lower bound of the exact gap.
   const double d0 = S.sc[0], d1 = S.sc[1], d2 = S.sc[2];
-  const double b0 = P.box[0], b1 = P.box[1], b2 = P.box[2];
-  const double i0 = P.ibox[0], i1 = P.ibox[1], i2 = P.ibox[2];
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  double mygap = inf;
+  const float b0 = (float)P.box[0], b1 = (float)P.box[1], b2 = (float)P.box[2];
+  const float i0 = (float)P.ibox[0], i1 = (float)P.ibox[1], i2 = (float)P.ibox[2];
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (t + MAGIC) - MAGIC == rintf(t) for |t| < 2^22
+  const float inf = __int_as_float(0x7f800000);
+  const float tol32 = (float)S.sc[7];
+  double mygap = __longlong_as_double(0x7ff0000000000000LL);
   int bad = 0;
   for (int c = tid; c < P.ncols; c += AS_THREADS) {
     const int j = gidx[c];
     // the shifted structure of the host loop: ys = y - disp
-    const double y0 = __dsub_rn(S.yb[j], d0), y1 = __dsub_rn(S.yb[N + j], d1), y2 = __dsub_rn(S.yb[2 * N + j], d2);
+    const float y0 = (float)__dsub_rn(S.yb[j], d0), y1 = (float)__dsub_rn(S.yb[N + j], d1),
+                y2 = (float)__dsub_rn(S.yb[2 * N + j], d2);
     const int r0 = S.cs[c], r1 = S.ce[c];
-    double best = inf, second = inf;
+    float best = inf, second = inf;
     int br = -1;
-    const double* x0 = S.xg;
-    const double* x1 = S.xg + P.ncols;
-    const double* x2 = S.xg + 2 * P.ncols;
+    const float* x0 = S.xf;
+    const float* x1 = S.xf + P.ncols;
+    const float* x2 = S.xf + 2 * P.ncols;
 #pragma unroll 4
     for (int r = r0; r < r1; ++r) {
-      double dx = x0[r] - y0, dy = x1[r] - y1, dz = x2[r] - y2;
-      dx -= (__dadd_rn(dx * i0, MAGIC) - MAGIC) * b0;
-      dy -= (__dadd_rn(dy * i1, MAGIC) - MAGIC) * b1;
-      dz -= (__dadd_rn(dz * i2, MAGIC) - MAGIC) * b2;
-      const double d = dx * dx + dy * dy + dz * dz;
+      float dx = x0[r] - y0, dy = x1[r] - y1, dz = x2[r] - y2;
+      dx -= (__fadd_rn(dx * i0, MAGIC) - MAGIC) * b0;
+      dy -= (__fadd_rn(dy * i1, MAGIC) - MAGIC) * b1;
+      dz -= (__fadd_rn(dz * i2, MAGIC) - MAGIC) * b2;
+      const float d = dx * dx + dy * dy + dz * dz;
       const bool lt = d < best;
-      const double hi = lt ? best : d;
+      const float hi = lt ? best : d;
       second = hi < second ? hi : second;
       best = lt ? d : best;
       br = lt ? r : br;
@@ -115,7 +124,8 @@ __device__ bool per_assign_solve(const PerAssignParams& P, const PerAssignSmem& 
     } else {
       atomicAdd(&S.cnt[br], 1);
       pm[gidx[br]] = j;  // X atom of row br <- Y atom of this column
-      const double gap = sqrt(second) - sqrt(best);
+      const float gapf = sqrtf(second) - sqrtf(best) - tol32;  // lower bound of the exact gap
+      const double gap = (double)gapf;
       mygap = gap < mygap ? gap : mygap;
       if (!(gap > P.tolgap)) bad = 1;
     }
@@ -170,11 +180,17 @@ per_assign_kernel(const __grid_constant__ PerAssignParams P, const double* __res
   const size_t pair = blockIdx.x;
   const double* xA = posA + pair * (size_t)N * 3;
   const double* yB = posB + pair * (size_t)N * 3;
+  double amax = 0.0;
   for (int e = tid; e < 3 * N; e += AS_THREADS) {
     const int i = e / 3, k = e - 3 * i;
-    S.xa[k * N + i] = xA[e];
-    S.yb[k * N + i] = yB[e];
+    const double xv = xA[e], yv = yB[e];
+    S.xa[k * N + i] = xv;
+    S.yb[k * N + i] = yv;
+    amax = fmax(amax, fmax(fabs(xv), fabs(yv)));
   }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if ((tid & 31) == 0) S.sc[8 + (tid >> 5)] = amax;
   for (int c = tid; c < P.ncols; c += AS_THREADS) {
     int lo = 0, hi = P.ngroups;  // group g with goff[g] <= c < goff[g+1]
     while (hi - lo > 1) {
@@ -187,11 +203,19 @@ per_assign_kernel(const __grid_constant__ PerAssignParams P, const double* __res
   for (int i = tid; i < N; i += AS_THREADS) S.perm[i] = S.save[i] = i;
   if (tid < 3) S.sc[tid] = __ddiv_rn(__dmul_rn(frac[pair * 3 + tid], P.box[tid]), P.F);
   __syncthreads();
+  if (tid == 0) {  // error bound of the single-precision search for this pair's coordinate range
+    double m = S.sc[8];
+    for (int w = 1; w < AS_THREADS / 32; ++w) m = fmax(m, S.sc[8 + w]);
+    S.sc[7] = (double)P.tol32 * (m + fmax(P.box[0], fmax(P.box[1], P.box[2])));
+  }
   for (int r = tid; r < P.ncols; r += AS_THREADS) {
     const int i = gidx[r];
     S.xg[r] = S.xa[i];
     S.xg[P.ncols + r] = S.xa[N + i];
     S.xg[2 * P.ncols + r] = S.xa[2 * N + i];
+    S.xf[r] = (float)S.xa[i];
+    S.xf[P.ncols + r] = (float)S.xa[N + i];
+    S.xf[2 * P.ncols + r] = (float)S.xa[2 * N + i];
   }
   __syncthreads();
   bool ok = per_assign_solve(P, S, gidx, S.save);
@@ -370,6 +394,9 @@ int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_p
   }
   P.F = (double)p->nfspace;
   P.tolgap = 1e-7 * bmax;
+  // float rounding of the coordinates, their differences and the minimum images: a component is off by less than
+  // 8 x 2^-24 M (M = max |coordinate| + box), a distance by 1.1e-6 M, a gap by 2.2e-6 M; 3.8e-6 M is subtracted
+  P.tol32 = 3.8e-6f;
   P.natoms = N;
   P.ncols = ncols;
   P.ngroups = ng;
