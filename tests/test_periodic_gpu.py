@@ -137,6 +137,31 @@ def test_bench_configuration_vs_oracle(ctx):
     assert np.abs(d).max() < wl.box[0] / 40
 
 
+@pytest.mark.parametrize("ngroups", [1, 2, 3])
+def test_fused_pairs_path_matches_bank_path(ctx, ngroups):
+    """per_sfx_kernel (structure factors of both structures + cross-spectrum in one kernel, S_A stashed in tensor
+    memory, groups accumulated into the image by red.add) against the bank path (per_sf3 x 2 + per_cross6) at the
+    bench k-grid: same arg-max, overlap values and grids to rounding, for one, two and three permutation groups
+    (an empty leading group included) and odd pair counts."""
+    from fastoverlap_b200 import PeriodicAlign
+    import bench
+    wl = bench.Blj256()
+    A, B, _ = wl.make(37, 11)
+    perm = {1: [np.arange(256)], 2: wl.perm, 3: [np.arange(0), np.arange(120), np.arange(120, 256)]}[ngroups]
+    al = PeriodicAlign(256, wl.box, perm, ctx=ctx)
+    p = al._params()
+    fused = ctx.per_align_pairs(p, A, B, want_grid=True)
+    ctx.set_option("per_pairs_fused", 0)
+    try:
+        bank = ctx.per_align_pairs(p, A, B, want_grid=True)
+    finally:
+        ctx.set_option("per_pairs_fused", 1)
+    assert np.array_equal(fused[0], bank[0])
+    assert np.allclose(fused[1], bank[1], rtol=1e-13)
+    assert np.allclose(fused[2], bank[2], atol=1e-9)
+    assert rel(fused[3], bank[3]) < 1e-13
+
+
 def test_translation_recovery_full_size(ctx):
     """Size-independent property at BASELINE size (N=256, n=9, F=40): a pure translation plus a
     permutation within species is recovered; the overlap peak sits at the translation."""

@@ -291,6 +291,33 @@ def test_fast_and_generic_isoft_agree(ctx, N, J):
     assert rel(fast[3], gen[3]) < 1e-12
 
 
+@pytest.mark.parametrize("J,invert", [(15, True), (15, False), (13, True), (7, True), (11, True), (3, True), (14, True), (8, False)])
+def test_isoft_kernel_variants_agree(ctx, J, invert):
+    """sph_isoft4_kernel (stages A -> B chained in registers; four planes per CTA for odd Jmax, two for even) against
+    sph_isoft3_kernel (stage A -> shared memory -> stage B) and, for odd Jmax, its own two-plane form: same arg-max
+    and interpolated maximum, grids to rounding."""
+    rng = np.random.default_rng(100 + J)
+    N = 38
+    A = rng.normal(size=(5, N, 3))
+    B = rng.normal(size=(5, N, 3))
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    ctx.set_perm([np.arange(N)], N)
+    new = ctx.sph_align_pairs(A, B, J, 0.45, invert=invert, want_grid=True)
+    res = []
+    for variant in (3, 42):
+        ctx.set_option("sph_isoft_variant", variant)
+        try:
+            res.append(ctx.sph_align_pairs(A, B, J, 0.45, invert=invert, want_grid=True))
+        finally:
+            ctx.set_option("sph_isoft_variant", 0)
+    for old in res:
+        assert np.array_equal(new[0], old[0])
+        assert np.allclose(new[1], old[1], rtol=1e-12)
+        assert np.allclose(new[2], old[2], atol=1e-7)
+        assert rel(new[3], old[3]) < 1e-12
+
+
 @pytest.mark.parametrize("N,J", [(10, 33), (12, 40), (9, 63)])
 def test_large_bandwidth_isoft(ctx, N, J):
     """Jmax > 32 (grids up to 128^3, BASELINE.json configs[3]): sph_isoft_big_kernel with the
