@@ -2423,8 +2423,9 @@ extern "C" int fo_per_align_pairs_dev(fo_ctx* ctx, const fo_per_params* p, const
   const size_t per_struct = bank_elems_per_struct(ctx, p);
   // device-resident input: no copies to overlap, so the chunks only bound the scratch -- three times the bank
   // budget of the host-buffer pipeline (fewer kernel boundaries: BLJ256 9.80 -> 9.63 ms per 16384 pairs)
-  const int64_t chunk = chunk_pairs(ctx, p, npairs, false, 2304);
   const bool fused = pairs_fused_applies(ctx, p);  // no bank: structure factors -> cross-spectrum in one kernel
+  // (the fused path keeps only the 62.7 KB image per pair: four times the pairs per chunk, 31.9 -> 31.6 ms per 65536)
+  const int64_t chunk = chunk_pairs(ctx, p, npairs, false, fused ? 9216 : 2304);
   void* bank = nullptr;
   if (npairs > 0 && !fused) FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
   double2* bankA = (double2*)bank;
@@ -2536,12 +2537,14 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
   FO_CUDA(ctx, cudaSetDevice(ctx->device));
   FO_CHECK(fo_ensure_perm(ctx, p->natoms));
   const size_t per_struct = bank_elems_per_struct(ctx, p);
-  const int64_t chunk = chunk_pairs(ctx, p, npairs, grid_out != nullptr);
+  const bool fused = pairs_fused_applies(ctx, p);  // no bank: structure factors -> cross-spectrum in one kernel
+  // chunk of the host pipeline: 3256 BLJ256 pairs on the bank path; the fused path takes four times as many
+  // (measured 1628 / 3256 / 6512 / 13024 / 26048 pairs per chunk: 1.52 / 1.60 / 1.66 / 1.68 / 1.66 M aligned pairs/s)
+  const int64_t chunk = chunk_pairs(ctx, p, npairs, grid_out != nullptr, fused ? 3072 : 768);
   const int64_t N = p->natoms;
   const size_t pos_bytes = (size_t)chunk * N * 3 * 8;
   const size_t F3 = (size_t)p->nfspace * p->nfspace * p->nfspace;
   void *bank, *dA, *dB, *dOut, *dGrid = nullptr, *hA, *hB, *dFull = nullptr;
-  const bool fused = pairs_fused_applies(ctx, p);  // no bank: structure factors -> cross-spectrum in one kernel
   bank = nullptr;
   if (!fused) FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, 2 * (size_t)chunk * per_struct * 16, &bank));
   // two position buffers per side so the copy of chunk c+1 overlaps the kernels of chunk c

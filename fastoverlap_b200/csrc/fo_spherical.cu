@@ -2978,10 +2978,14 @@ size_t direct_work_bytes(const fo_ctx* ctx, int64_t np, int64_t natoms, int L) {
   return b;
 }
 
-int64_t direct_chunk(const fo_ctx* ctx, int64_t npairs, int64_t natoms, int L, bool want_grid) {
+int64_t direct_chunk(const fo_ctx* ctx, int64_t npairs, int64_t natoms, int L, bool want_grid,
+                     bool device_resident = false) {
   const size_t per = direct_work_bytes(ctx, 1, natoms, L) + ihalf_elems(L) * 16;
-  // 1 GB of scratch per chunk; large clusters / bandwidths (> 256 MB per pair) get 4 GB
-  const size_t budget = per > ((size_t)256 << 20) ? (size_t)4 << 30 : (size_t)1 << 30;
+  // 2 GB of scratch per chunk through host buffers (LJ38: 4472 pairs; measured 1 / 2 / 4 GB: 0.987 / 1.006 / 1.002 M
+  // aligned pairs/s end to end), 4 GB when the input is device-resident (no copies to overlap: fewer launch tails)
+  // and for large clusters / bandwidths (> 256 MB per pair)
+  size_t budget = (per > ((size_t)256 << 20) || device_resident) ? (size_t)4 << 30 : (size_t)2 << 30;
+  if (const char* e = getenv("FO_SPH_CHUNK_MB")) budget = (size_t)atol(e) << 20;  // tuning hook of the A/B scripts
   int64_t c = (int64_t)(budget / per);
   if (want_grid) {
     const size_t g = (size_t)8 * 2 * (2 * L + 2) * (2 * L + 2) * (2 * L + 2);
@@ -2989,7 +2993,7 @@ int64_t direct_chunk(const fo_ctx* ctx, int64_t npairs, int64_t natoms, int L, b
     if (cg < c) c = cg;
   }
   if (c > 65535) c = 65535;  // gridDim.y
-  if (c * (L + 1) > 65535) c = 65535 / (L + 1);  // gridDim.z of the GEMM kernels
+  if (natoms >= ctx->direct_gemm_min && c * (L + 1) > 65535) c = 65535 / (L + 1);  // gridDim.z of the GEMM kernels
   if (c < 1) c = 1;
   if (c > npairs) c = npairs;
   return c;
@@ -3242,7 +3246,7 @@ int align_pairs_dev_impl(fo_ctx* ctx, const double* d_posA, const double* d_posB
   int* d_gid = nullptr;
   FO_CHECK(upload_gid(ctx, natoms, &d_gid));
   const size_t G3 = (size_t)(2 * L + 2) * (2 * L + 2) * (2 * L + 2);
-  const int64_t chunk = direct_chunk(ctx, npairs, natoms, L, false);
+  const int64_t chunk = direct_chunk(ctx, npairs, natoms, L, false, true);
   void *work, *dhalf;
   FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(ctx, chunk, natoms, L), &work));
   FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));

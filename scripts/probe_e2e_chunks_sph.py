@@ -1,0 +1,24 @@
+"""End-to-end (host buffers, full alignment) step time of LJ38 against the chunk budget (FO_SPH_CHUNK_MB, default 1024)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+import fastoverlap_b200 as fob
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+wl = bench.Lj38()
+ctx = fob.Context(0)
+wl.setup(ctx)
+A, B, _ = wl.make(P, 0)
+hA, hB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
+for _ in range(2):
+    wl.run_host_full(ctx, hA.numpy(), hB.numpy(), 16)
+ctx.profile_begin()
+t0 = time.perf_counter()
+n = 4
+for _ in range(n):
+    wl.run_host_full(ctx, hA.numpy(), hB.numpy(), 16)
+wall = (time.perf_counter() - t0) / n * 1e3
+prof = ctx.profile_end()
+print("FO_SPH_CHUNK_MB=%s: %.2f ms per %d pairs (%.0f pairs/s); kernels %.2f ms %s" % (
+    os.environ.get("FO_SPH_CHUNK_MB", "1024"), wall, P, P / wall * 1e3, sum(v[0] for v in prof.values()) / n,
+    {k: round(v[0] / n, 2) for k, v in prof.items()}))
