@@ -494,29 +494,49 @@ sph_direct_mma_kernel(const double2* __restrict__ YA, const double2* __restrict_
   // the register-staged loads of the first version as 46 % long-scoreboard stalls); the zero padding
   // (rows r >= R, atoms >= natoms) is written with ordinary stores to disjoint addresses.
   {
-    const int tx = tid & 15, ty = tid >> 4;  // 16 x 8 threads
+    // flat loops (the first version walked (row, 16-lane column group) nests: 36 % of the kernel's stall samples
+    // sat in their index arithmetic and in the half-empty zero-fill loops, profiles/r02_summary.md)
     const int nm = l + 1;
-    for (int j = ty; j < N8; j += DS_THREADS / 16) {
-      if (j < natoms) {
-        for (int m = tx; m < nm; m += 16) {
-          const unsigned da = (unsigned)__cvta_generic_to_shared(A1 + j * LDR + 2 * m);
-          const unsigned db = (unsigned)__cvta_generic_to_shared(B2 + j * LDR + 2 * m);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(ya + (size_t)j * 2 * NLM + 2 * m)
-                       : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db), "l"(yb + (size_t)j * 2 * NLM + 2 * m)
-                       : "memory");
-        }
-        for (int r = R + tx; r < R8; r += 16) A1[j * LDR + r] = B2[j * LDR + r] = 0.0;
-        for (int k = tx; k < natoms; k += 16) {
-          const unsigned d1 = (unsigned)__cvta_generic_to_shared(B1 + j * LDN + k);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(Bl + (size_t)j * natoms + k)
-                       : "memory");
-        }
-        for (int k = natoms + tx; k < N8; k += 16) B1[j * LDN + k] = 0.0;
-      } else {
-        for (int r = tx; r < R8; r += 16) A1[j * LDR + r] = B2[j * LDR + r] = 0.0;
-        for (int k = tx; k < N8; k += 16) B1[j * LDN + k] = 0.0;
+    for (int e = tid; e < natoms * nm; e += DS_THREADS) {
+      const int j = e / nm, m = e - j * nm;
+      const unsigned da = (unsigned)__cvta_generic_to_shared(A1 + j * LDR + 2 * m);
+      const unsigned db = (unsigned)__cvta_generic_to_shared(B2 + j * LDR + 2 * m);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(ya + (size_t)j * 2 * NLM + 2 * m)
+                   : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db), "l"(yb + (size_t)j * 2 * NLM + 2 * m)
+                   : "memory");
+    }
+    if ((natoms & 1) == 0) {  // rows of B_l are 16-byte multiples: half as many copies
+      const int nh = natoms >> 1;
+      for (int e = tid; e < natoms * nh; e += DS_THREADS) {
+        const int j = e / nh, k = 2 * (e - j * nh);
+        const unsigned d1 = (unsigned)__cvta_generic_to_shared(B1 + j * LDN + k);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(Bl + (size_t)j * natoms + k) : "memory");
       }
+    } else {
+      for (int e = tid; e < natoms * natoms; e += DS_THREADS) {
+        const int j = e / natoms, k = e - j * natoms;
+        const unsigned d1 = (unsigned)__cvta_generic_to_shared(B1 + j * LDN + k);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(Bl + (size_t)j * natoms + k) : "memory");
+      }
+    }
+    // zero padding: columns r >= R / k >= natoms of the atom rows, and the rows j >= natoms
+    const int pr = R8 - R, pk = N8 - natoms;
+    for (int e = tid; e < natoms * pr; e += DS_THREADS) {
+      const int j = e / pr, r = R + e - j * pr;
+      A1[j * LDR + r] = B2[j * LDR + r] = 0.0;
+    }
+    for (int e = tid; e < natoms * pk; e += DS_THREADS) {
+      const int j = e / pk, k = natoms + e - j * pk;
+      B1[j * LDN + k] = 0.0;
+    }
+    for (int e = tid; e < pk * R8; e += DS_THREADS) {
+      const int j = natoms + e / R8, r = e % R8;
+      A1[j * LDR + r] = B2[j * LDR + r] = 0.0;
+    }
+    for (int e = tid; e < pk * N8; e += DS_THREADS) {
+      const int j = natoms + e / N8, k = e % N8;
+      B1[j * LDN + k] = 0.0;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
