@@ -159,6 +159,12 @@ class Blj256:
     def algorithmic_flops_per_pair(self):
         return 2 * 256 * 6859 * 8
 
+    # useful FP64 of the whole hot path: structure factors + cross-spectrum (3610 k x 2 groups x 8) + the
+    # symmetric pruned DFT stages (X: 400 rows x 21 outputs x 9 harmonics x 4; Y: 40 x 20 x 21 x 9 x 4;
+    # Z: 40 x 40 x 21 x 9 x 4 real FMA-flops; tile padding not counted)
+    def hot_path_flops_per_pair(self):
+        return self.dominant_flops_per_pair() + 3610 * 2 * 8 + (400 + 800 + 1600) * 21 * 9 * 4
+
     # -- CPU arms
     def run_oracle(self, oracle, A, B, nthreads=0):
         return oracle.per_align_pairs(A, B, self.box, self.n, self.F, self.sigma, self.perm,
@@ -260,6 +266,13 @@ class Lj38:
         # iSOFT, both orientations (DESIGN.md "K_isoft"): executed real FMA count x 2
         from fastoverlap_b200.spherical import isoft_executed_flops
         return isoft_executed_flops(self.Jmax, True)
+
+    # useful FP64 of the whole hot path: iSOFT + the direct coefficients (per l: T = Y_A^H B_l and T Y_B as real
+    # GEMMs on interleaved re / im rows, 2 x 2(l+1) x N x N and 2 x 2(l+1) x 2(l+1) x N flop; Bessel / Y_lm not counted)
+    def hot_path_flops_per_pair(self):
+        N = 38
+        coef = sum(2 * 2 * (l + 1) * N * N + 2 * 2 * (l + 1) * 2 * (l + 1) * N for l in range(self.Jmax + 1))
+        return self.dominant_flops_per_pair() + coef
 
     def algorithmic_flops_per_pair(self):
         L = self.Jmax
@@ -615,6 +628,11 @@ def measure(h, wl, P, steps, warmup, peaks, want_cpu):
                 "kernel_ms_per_launch": dom_ms / dom_n, "kernel_share_of_step": dom_ms / total_prof,
                 "kernel_shares": {k: v[0] / total_prof for k, v in prof.items()},
                 "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items()},
+                # the whole hot path (every kernel class but the screening): useful FP64 flop / summed CUDA-event time
+                "hot_path_useful_tflops": wl.hot_path_flops_per_pair() * pairs_timed /
+                (sum(v[0] for k, v in prof.items() if k != "assign") * 1e-3) / 1e12,
+                "hot_path_frac": wl.hot_path_flops_per_pair() * pairs_timed /
+                (sum(v[0] for k, v in prof.items() if k != "assign") * 1e-3) / 1e12 / peak,
                 "traffic": None, "hbm_frac_of_measured": None}
         try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
             tr = None
