@@ -125,12 +125,12 @@ class Blj256:
     def run_host_hot(self, ctx, A, B):
         return ctx.per_align_pairs(self.params, A, B)
 
-    def run_host_full(self, ctx, A, B, nthreads):
+    def run_host_full(self, ctx, A, B, nthreads, out=None):
         """(dist, perm, disp, frac, status, nhost)"""
-        return ctx.per_align_pairs_full(self.params, A, B, niter=10, nthreads=nthreads)
+        return ctx.per_align_pairs_full(self.params, A, B, niter=10, nthreads=nthreads, out=out)
 
     def d2h_bytes(self, P):
-        return P * (60 + 40 + 4 * 256)
+        return P * (60 + 40 + 1 * 256)  # arg-max record + dist / disp / flag + permutation (one byte per atom on the wire)
 
     def checks(self, full, dev, shift):
         """Positive controls on the aligned result: the known translation is recovered to within a grid cell,
@@ -240,9 +240,9 @@ class Lj38:
     def run_host_hot(self, ctx, A, B):
         return ctx.sph_align_pairs(A, B, self.Jmax, self.sigma, invert=True)
 
-    def run_host_full(self, ctx, A, B, nthreads):
+    def run_host_full(self, ctx, A, B, nthreads, out=None):
         """(dist, orient, perm, rmat, euler, status, nhost)"""
-        return ctx.sph_align_pairs_full(A, B, self.Jmax, self.sigma, invert=True, nthreads=nthreads)
+        return ctx.sph_align_pairs_full(A, B, self.Jmax, self.sigma, invert=True, nthreads=nthreads, out=out)
 
     def d2h_bytes(self, P):
         return P * (2 * 88 + 4 + 2 * 4 * (1 + 38))
@@ -340,6 +340,24 @@ def dist_env():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     return rank, local, world
+
+
+def bind_to_gpu_cpus(local):
+    """CPU affinity of the calling thread := the CPUs NVML reports as local to GPU `local` (its NUMA node), when
+    that set has at least 2 CPUs inside the current mask.  Returns the sorted CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
 
 
 def host_cores():
@@ -511,11 +529,16 @@ class Harness:
         else:
             self.dist = None
             torch.cuda.set_device(self.local)
+        # host threads of this rank's pool: the box's cores shared evenly between the ranks
+        self.nthreads = max(1, host_cores() // self.world)
+        # Several ranks on one host: bind this rank (its pinned buffers are allocated and first touched from here on,
+        # and its host pool threads inherit the mask) to the CPUs next to its GPU.  Round 1 lost 11 % of the 8-GPU
+        # end-to-end rate to eight processes pulling their coordinates across the host's memory / PCIe paths.
+        self.affinity_all = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+        self.bound = bind_to_gpu_cpus(self.local) if (self.world > 1 and not os.environ.get("FO_BENCH_NO_BIND")) else None
         self.ctx = fob.Context(self.local)
         self.stream = torch.cuda.current_stream()
         self.ctx.set_stream(self.stream.cuda_stream)
-        # host threads of this rank's pool: the box's cores shared evenly between the ranks
-        self.nthreads = max(1, host_cores() // self.world)
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -584,7 +607,10 @@ def measure(h, wl, P, steps, warmup, peaks, want_cpu):
     host_res = [None]
 
     def e2e_full():
-        host_res[0] = wl.run_host_full(ctx, hA.numpy(), hB.numpy(), h.nthreads)
+        # the caller keeps its result arrays from step to step (fresh 70 MB arrays per call are page-fault bound,
+        # eight processes on one host even more so); FO_BENCH_FRESH_OUT=1 allocates them per call as round 1 did
+        host_res[0] = wl.run_host_full(ctx, hA.numpy(), hB.numpy(), h.nthreads,
+                                       out=None if os.environ.get("FO_BENCH_FRESH_OUT") else host_res[0])
 
     e2e_hot = lambda: wl.run_host_hot(ctx, hA.numpy(), hB.numpy())
     e2e_steps = max(3, steps // 4)
@@ -680,8 +706,10 @@ def measure(h, wl, P, steps, warmup, peaks, want_cpu):
            "e2e": {"value": world * P * e2e_steps / (wall_full * 1e-3), "unit": "pairs/s",
                    "h2d_bytes_per_step": int(2 * P * wl.natoms * 24), "d2h_bytes_per_step": int(wl.d2h_bytes(P)),
                    "steps": e2e_steps, "api": wl.api + " (host buffers): aligned pairs, final distance + "
-                   "permutation + displacement / rotation per pair", "buffers": "pinned caller buffers",
-                   "host_threads_per_rank": h.nthreads, "host_cores": host_cores()},
+                   "permutation + displacement / rotation per pair", "buffers": "pinned caller input buffers, result arrays reused from step to step",
+                   "host_threads_per_rank": h.nthreads,
+                   "host_cores": len(h.affinity_all) if h.affinity_all else host_cores(),
+                   "rank0_cpu_binding": ("%d CPUs local to the GPU (NVML)" % len(h.bound)) if h.bound else None},
            "e2e_hot_path": {"value": world * P * 3 / (wall_hot * 1e-3), "unit": "pairs/s",
                             "api": wl.api.replace("_full", "") + " (host buffers, round-1 definition of e2e)"},
            "e2e_pageable": pageable,

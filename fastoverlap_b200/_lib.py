@@ -454,21 +454,27 @@ class Context(object):
             c_void_p(d_perm or 0), c_void_p(d_disp), c_void_p(d_flag), c_void_p(d_best_idx), c_void_p(d_best_val),
             c_void_p(d_frac), c_void_p(d_status or 0)), "fo_per_align_pairs_full_dev")
 
-    def per_align_pairs_full(self, params, posA, posB, niter=10, nthreads=0, want_perm=True):
+    def per_align_pairs_full(self, params, posA, posB, niter=10, nthreads=0, want_perm=True, out=None):
         """Hot path + device screening of the assignment + host LAP pool for the flagged pairs
         (fo_per_align_pairs_full).  Returns (dist (P,), perm (P,N)|None, disp (P,3), frac_idx (P,3),
-        status (P,), nhost)."""
+        status (P,), nhost).  out: a previous return tuple of the same batch size whose arrays are written again
+        (a caller that aligns batch after batch keeps its result buffers: fresh 67 MB arrays per call cost page
+        faults, which eight processes on one host pay dearly)."""
         self._ensure_perm(params.natoms)
         posA = _f64(posA).reshape(-1, params.natoms, 3)
         posB = _f64(posB).reshape(-1, params.natoms, 3)
         if posA.shape != posB.shape:
             raise ValueError("posA and posB must have the same shape")
         P = posA.shape[0]
-        dist = np.empty(P)
-        perm = np.empty((P, params.natoms), np.int32) if want_perm else None
-        disp = np.empty((P, 3))
-        frac = np.empty((P, 3))
-        st = np.zeros(P, np.int32)
+        if out is not None and out[0].shape == (P,) and (out[1] is not None) == bool(want_perm):
+            dist, perm, disp, frac, st = out[:5]
+            st[:] = 0
+        else:
+            dist = np.empty(P)
+            perm = np.empty((P, params.natoms), np.int32) if want_perm else None
+            disp = np.empty((P, 3))
+            frac = np.empty((P, 3))
+            st = np.zeros(P, np.int32)
         nhost = ctypes.c_int64(0)
         self._check(self._lib.fo_per_align_pairs_full(self._h, ctypes.byref(params), _ptr(posA), _ptr(posB), P,
                                                       int(niter), int(nthreads), _ptr(dist), _ptr(perm),
@@ -665,10 +671,11 @@ class Context(object):
             int(bool(invert)), c_void_p(d_best_idx), c_void_p(d_best_val), c_void_p(d_frac), c_void_p(d_perm),
             c_void_p(d_ok), c_void_p(d_status or 0)), "fo_sph_align_pairs_screen_dev")
 
-    def sph_align_pairs_full(self, posA, posB, Jmax, sigma, invert=True, nthreads=0, want_perm=True):
+    def sph_align_pairs_full(self, posA, posB, Jmax, sigma, invert=True, nthreads=0, want_perm=True, out=None):
         """Hot path + device screening of the assignment + host pool (LAP where needed, Kearsley)
         (fo_sph_align_pairs_full).  Structures must be centred.  Returns (dist (P,), orient (P,),
-        perm (P,N)|None, rmat (P,3,3), euler (P,O,3), status (P,), nhost)."""
+        perm (P,N)|None, rmat (P,3,3), euler (P,O,3), status (P,), nhost).  out: a previous return tuple of the
+        same batch size whose arrays are written again."""
         posA = _f64(posA)
         posB = _f64(posB)
         if posA.ndim == 2:
@@ -677,12 +684,17 @@ class Context(object):
         P, N, _ = posA.shape
         self._ensure_perm(N)
         O = 2 if invert else 1
-        dist = np.empty(P)
-        orient = np.empty(P, np.int32)
-        perm = np.empty((P, N), np.int32) if want_perm else None
-        rmat = np.empty((P, 3, 3))
-        euler = np.empty((P, O, 3))
-        st = np.zeros(P, np.int32)
+        if (out is not None and out[0].shape == (P,) and out[4].shape == (P, O, 3) and
+                (out[2] is not None) == bool(want_perm)):
+            dist, orient, perm, rmat, euler, st = out[:6]
+            st[:] = 0
+        else:
+            dist = np.empty(P)
+            orient = np.empty(P, np.int32)
+            perm = np.empty((P, N), np.int32) if want_perm else None
+            rmat = np.empty((P, 3, 3))
+            euler = np.empty((P, O, 3))
+            st = np.zeros(P, np.int32)
         nhost = ctypes.c_int64(0)
         self._check(self._lib.fo_sph_align_pairs_full(self._h, _ptr(posA), _ptr(posB), P, N, int(Jmax), float(sigma),
                                                       int(bool(invert)), int(nthreads), _ptr(dist), _ptr(orient),

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(AS_THREADS)
 per_assign_kernel(const __grid_constant__ PerAssignParams P, const double* __restrict__ posA,
                   const double* __restrict__ posB, const double* __restrict__ frac,
                   const int* __restrict__ goff, const int* __restrict__ gidx, double* __restrict__ dist,
-                  double* __restrict__ disp_out, int* __restrict__ perm_out, int* __restrict__ flag) {
+                  double* __restrict__ disp_out, void* __restrict__ perm_out, int perm_elt, int* __restrict__ flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.natoms, tid = threadIdx.x;
   const PerAssignSmem S = per_assign_carve(smem_raw, N, P.ncols);
@@ -260,7 +260,12 @@ per_assign_kernel(const __grid_constant__ PerAssignParams P, const double* __res
       s = k == 0 ? __dmul_rn(d, d) : __dadd_rn(s, __dmul_rn(d, d));
     }
     S.term[i] = s;
-    if (perm_out) perm_out[pair * (size_t)N + i] = j;
+    if (perm_out) {  // element width of the output: 4 (int32), 2 or 1 bytes (the host pipeline's D2H format)
+      const size_t e = pair * (size_t)N + i;
+      if (perm_elt == 4) static_cast<int*>(perm_out)[e] = j;
+      else if (perm_elt == 2) static_cast<unsigned short*>(perm_out)[e] = (unsigned short)j;
+      else static_cast<unsigned char*>(perm_out)[e] = (unsigned char)j;
+    }
   }
   __syncthreads();
   if (tid < 32) {
@@ -377,7 +382,7 @@ sph_assign_kernel(const __grid_constant__ SphAssignParams P, const double* __res
 // Launchers (declared in fo_internal.h).  d_flag [np]: 0 = settled on the device, 1 = host LAP needed.
 int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA, const double* d_posB,
                           const double* d_frac, int64_t np, int niter, double* d_dist, double* d_disp,
-                          int32_t* d_perm, int32_t* d_flag) {
+                          void* d_perm, int32_t* d_flag, int perm_elt) {
   if (np == 0) return FO_OK;
   const int N = (int)p->natoms, ng = (int)ctx->h_goff.size() - 1, ncols = ctx->h_goff[ng];
   const size_t smem = per_assign_smem(N, ncols);
@@ -404,7 +409,7 @@ int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_p
   fo_prof_scope prof(ctx, FO_PROF_ASSIGN);
   FO_CUDA(ctx, cudaFuncSetAttribute(per_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   per_assign_kernel<<<(unsigned)np, AS_THREADS, smem, ctx->stream>>>(P, d_posA, d_posB, d_frac, ctx->d_goff,
-                                                                     ctx->d_gidx, d_dist, d_disp, d_perm, d_flag);
+                                                                     ctx->d_gidx, d_dist, d_disp, d_perm, perm_elt, d_flag);
   FO_LAUNCH_CHECK(ctx);
   return FO_OK;
 }

@@ -1,5 +1,6 @@
 // Context, error handling, scratch memory, permutation groups, small utilities.
 #include <stdarg.h>
+#include <omp.h>
 #include <string.h>
 
 #include "fo_internal.h"
@@ -76,14 +77,19 @@ bool fo_is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-void fo_host_copy(void* dst, const void* src, size_t bytes) {
+// memcpy in 1 MB blocks on a few threads.  nthreads = the host threads the caller granted this call (0: whatever
+// OpenMP allows, i.e. OMP_NUM_THREADS); half of them copy, at most 8.  (A fixed team of 8 per process was what
+// collapsed the 8-GPU end-to-end rate: 64 copy threads, spinning after every region, on 32 cores.)
+void fo_host_copy(void* dst, const void* src, size_t bytes, int nthreads) {
   const size_t blk = (size_t)1 << 20;
   const long nblk = (long)((bytes + blk - 1) / blk);
-  if (nblk <= 2) {
+  int nt = nthreads > 0 ? nthreads / 2 : omp_get_max_threads() / 2;
+  nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+  if (nblk <= 2 || nt == 1) {
     memcpy(dst, src, bytes);
     return;
   }
-#pragma omp parallel for schedule(static) num_threads(8)
+#pragma omp parallel for schedule(static) num_threads(nt)
   for (long b = 0; b < nblk; ++b) {
     const size_t off = (size_t)b * blk;
     memcpy((char*)dst + off, (const char*)src + off, bytes - off < blk ? bytes - off : blk);

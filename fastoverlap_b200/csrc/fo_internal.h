@@ -107,20 +107,45 @@ int fo_pinned(fo_ctx* ctx, int slot, size_t bytes, void** out);
 // true when `p` is page-locked (cudaMallocHost / cudaHostRegister): it can be DMA'd directly
 bool fo_is_pinned(const void* p);
 // parallel host memcpy (staging of pageable buffers into the pinned ring)
-void fo_host_copy(void* dst, const void* src, size_t bytes);
+void fo_host_copy(void* dst, const void* src, size_t bytes, int nthreads = 0);
 // Chunk boundaries of the double-buffered host-buffer pipelines: [0, s1, s2, ..., npairs], every
 // chunk <= chunk pairs.  With more than one chunk the sizes ramp up geometrically (chunk / 8, x2, x2, ...):
 // the first H2D copy is the only one no kernel overlaps, and the kernels of chunk c must last at least
 // as long as the copy of chunk c + 1 (BLJ256: 0.25 us / pair of PCIe against 0.65 us / pair of compute).
 inline std::vector<int64_t> fo_chunk_starts(int64_t npairs, int64_t chunk) {
+  // Chunk boundaries of the host pipelines: short chunks at BOTH ends -- the H2D copy of the first chunk and the
+  // D2H + delivery of the last one are the only transfers nothing can hide -- ramping by factors of two to the
+  // full chunk size in between.
   std::vector<int64_t> s(1, 0);
-  int64_t size = chunk;
-  if (npairs > chunk && chunk >= 64) size = chunk / 8;
+  if (npairs <= chunk || chunk < 64) {
+    for (int64_t p0 = 0; p0 < npairs;) {
+      p0 = std::min(p0 + chunk, npairs);
+      s.push_back(p0);
+    }
+    return s;
+  }
+  const int64_t ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
+  const int64_t ends = 2 * (ramp[0] + ramp[1] + ramp[2]);
+  std::vector<int64_t> sizes;
+  if (npairs >= ends + chunk / 2) {
+    for (int i = 0; i < 3; ++i) sizes.push_back(ramp[i]);
+    const int64_t mid = npairs - ends;
+    const int64_t nmid = (mid + chunk - 1) / chunk;
+    for (int64_t i = 0; i < nmid; ++i) sizes.push_back(mid / nmid + (i < mid % nmid ? 1 : 0));
+    for (int i = 2; i >= 0; --i) sizes.push_back(ramp[i]);
+  } else {  // a few chunks only: ramp up as far as it goes
+    int64_t size = chunk / 8, left = npairs;
+    while (left > 0) {
+      const int64_t n = std::min(size, left);
+      sizes.push_back(n);
+      left -= n;
+      size = std::min(2 * size, chunk);
+    }
+  }
   int64_t p0 = 0;
-  while (p0 < npairs) {
-    p0 = std::min(p0 + size, npairs);
+  for (int64_t n : sizes) {
+    p0 += n;
     s.push_back(p0);
-    size = std::min(2 * size, chunk);
   }
   return s;
 }
@@ -148,7 +173,7 @@ int fo_refine_run_dev(fo_ctx* ctx, const void* d_Ihalf, int64_t np, int L, int n
 // Clusters: d_perm [np, norient, natoms], d_ok [np, norient] = 1 where the permutation is the proven optimum.
 int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_posA, const double* d_posB,
                           const double* d_frac, int64_t np, int niter, double* d_dist, double* d_disp,
-                          int32_t* d_perm, int32_t* d_flag);
+                          void* d_perm, int32_t* d_flag, int perm_elt = 4);  // perm_elt: bytes per index (4, 2, 1)
 int fo_sph_assign_run_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB, const double* d_frac,
                           int64_t np, int64_t natoms, int L, int norient, int32_t* d_perm, int32_t* d_ok);
 

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include <string.h>
+#include <omp.h>
 
 #include "fo_internal.h"
 #include "fo_async.cuh"
@@ -2554,7 +2555,10 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * F3 * 8, &dGrid));
   // full alignment: dist[np] | disp[3 np] | flag[np] i32 (padded to 8 np) | perm[np N] i32, per chunk
   const bool want_perm = full && full->perm;
-  const size_t full_stride = 40 + (want_perm ? (size_t)N * 4 : 0);
+  // permutations travel device -> host in the narrowest index type that holds natoms (BLJ256: one byte per atom
+  // instead of four: the D2H of the permutations was 94 % of the result bytes) and are widened on delivery
+  const int pelt = N <= 256 ? 1 : (N <= 65536 ? 2 : 4);
+  const size_t full_stride = 40 + (want_perm ? (size_t)N * pelt : 0);
   if (full) FO_CHECK(fo_scratch(ctx, FO_SCR_FULL, (size_t)chunk * full_stride, &dFull));
   const bool pinnedA = fo_is_pinned(posA), pinnedB = fo_is_pinned(posB);
   hA = hB = nullptr;
@@ -2578,11 +2582,11 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
     const char* srcA = (const char*)(posA + (size_t)p0 * N * 3);
     const char* srcB = (const char*)(posB + (size_t)p0 * N * 3);
     if (!pinnedA) {
-      fo_host_copy((char*)hA + buf * pos_bytes, srcA, nb);
+      fo_host_copy((char*)hA + buf * pos_bytes, srcA, nb, full ? full->nthreads : 0);
       srcA = (const char*)hA + buf * pos_bytes;
     }
     if (!pinnedB) {
-      fo_host_copy((char*)hB + buf * pos_bytes, srcB, nb);
+      fo_host_copy((char*)hB + buf * pos_bytes, srcB, nb, full ? full->nthreads : 0);
       srcB = (const char*)hB + buf * pos_bytes;
     }
     // device buffer `buf` was last read by the kernels of chunk c-2
@@ -2609,7 +2613,26 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
     const int32_t* flag = (const int32_t*)(src + (size_t)np * 32);
     memcpy(full->dist + p0, src, (size_t)np * 8);
     if (full->disp) memcpy(full->disp + 3 * p0, src + (size_t)np * 8, (size_t)np * 24);
-    if (want_perm) fo_host_copy(full->perm + (size_t)p0 * N, src + (size_t)np * 40, (size_t)np * N * 4);
+    if (want_perm) {
+      int32_t* dstp = full->perm + (size_t)p0 * N;
+      const size_t ne = (size_t)np * N;
+      if (pelt == 4) {
+        fo_host_copy(dstp, src + (size_t)np * 40, ne * 4, full->nthreads);
+      } else {
+        int nt = full->nthreads > 0 ? full->nthreads / 2 : omp_get_max_threads() / 2;
+        nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+        const unsigned char* s1 = (const unsigned char*)(src + (size_t)np * 40);
+        const unsigned short* s2 = (const unsigned short*)s1;
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1)
+        for (long long b = 0; b < (long long)((ne + 65535) >> 16); ++b) {
+          const size_t e0 = (size_t)b << 16, e1 = std::min(ne, e0 + 65536);
+          if (pelt == 1)
+            for (size_t e = e0; e < e1; ++e) dstp[e] = s1[e];
+          else
+            for (size_t e = e0; e < e1; ++e) dstp[e] = s2[e];
+        }
+      }
+    }
     hard.clear();
     for (int64_t q = 0; q < np; ++q)
       if (flag[q]) hard.push_back(p0 + q);
@@ -2644,8 +2667,8 @@ int per_align_pairs_impl(fo_ctx* ctx, const fo_per_params* p, const double* posA
     if (full) {  // screening + permutation <-> displacement loop on the device (reads the positions again)
       char* f = (char*)dFull;
       FO_CHECK(fo_per_assign_run_dev(ctx, p, cA, cB, out.frac_idx, np, full->niter, (double*)f,
-                                     (double*)(f + (size_t)np * 8), want_perm ? (int32_t*)(f + (size_t)np * 40) : nullptr,
-                                     (int32_t*)(f + (size_t)np * 32)));
+                                     (double*)(f + (size_t)np * 8), want_perm ? (void*)(f + (size_t)np * 40) : nullptr,
+                                     (int32_t*)(f + (size_t)np * 32), pelt));
       FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
     }
     if (grid_out) {  // test / single-pair path: large grids straight into the caller's array
