@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(128)
 sph_assign_kernel(const __grid_constant__ SphAssignParams P, const double* __restrict__ posA,
                   const double* __restrict__ posB, const double* __restrict__ frac,
                   const int* __restrict__ goff, const int* __restrict__ gidx, int* __restrict__ perm_out,
-                  int* __restrict__ ok_out) {
+                  int* __restrict__ ok_out, double* __restrict__ kdist, double* __restrict__ krot) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.natoms, tid = threadIdx.x, T = blockDim.x;
   double* xg = reinterpret_cast<double*>(smem_raw);  // [3][ncols] rows (structure A) in group order
@@ -375,6 +375,109 @@ sph_assign_kernel(const __grid_constant__ SphAssignParams P, const double* __res
     if (cnt[r] != 1) s_bad = 1;
   __syncthreads();
   if (tid == 0) ok_out[po] = s_bad ? 0 : 1;
+  // Kearsley fit of the settled assignment (utils.py:169-253 findrotation_kearsley; kearsley() in fo_host.cu): the
+  // rotated structure is already in shared memory, the 4 x 4 quaternion matrix is 16 sums over the atoms, its
+  // smallest eigenpair comes from cyclic Jacobi in one thread.  Round 2 measured the host pool as the limit of
+  // the end-to-end LJ38 rate at 8 GPUs (32 cores: 3.7 M pairs/s of fits for 8.9 M pairs/s of hot path); with the
+  // fit here the host only picks the orientation and copies.
+  if (kdist == nullptr || s_bad || tid >= 32) return;
+  const int lane = tid;
+  // x1 = structure A (atom order, global), x2[i] = rotated B atom perm[i]
+  const int* pm = perm_out + po * (size_t)N;
+  auto wsum = [&](double v) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  };
+  double c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+  for (int i = lane; i < N; i += 32) {
+    const int j = pm[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      c1[k] += xA[3 * i + k];
+      c2[k] += yr[k * N + j];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    c1[k] = wsum(c1[k]) / (double)N;
+    c2[k] = wsum(c2[k]) / (double)N;
+  }
+  double q[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // Q00 Q01 Q02 Q03 Q11 Q12 Q13 Q22 Q23 Q33
+  for (int i = lane; i < N; i += 32) {
+    const int j = pm[i];
+    const double a0 = xA[3 * i] - c1[0], a1 = xA[3 * i + 1] - c1[1], a2 = xA[3 * i + 2] - c1[2];
+    const double b0 = yr[j] - c2[0], b1 = yr[N + j] - c2[1], b2 = yr[2 * N + j] - c2[2];
+    const double xm = a0 - b0, ym = a1 - b1, zm = a2 - b2;
+    const double xp = a0 + b0, yp = a1 + b1, zp = a2 + b2;
+    q[0] += xm * xm + ym * ym + zm * zm;
+    q[1] += ym * zp - yp * zm;
+    q[2] += xp * zm - xm * zp;
+    q[3] += xm * yp - xp * ym;
+    q[4] += yp * yp + zp * zp + xm * xm;
+    q[5] += xm * ym - xp * yp;
+    q[6] += xm * zm - xp * zp;
+    q[7] += xp * xp + zp * zp + ym * ym;
+    q[8] += ym * zm - yp * zp;
+    q[9] += xp * xp + yp * yp + zm * zm;
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) q[k] = wsum(q[k]);
+  if (lane != 0) return;
+  double A[4][4] = {{q[0], q[1], q[2], q[3]}, {q[1], q[4], q[5], q[6]}, {q[2], q[5], q[7], q[8]}, {q[3], q[6], q[8], q[9]}};
+  double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, diag = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      diag += A[a][a] * A[a][a];
+#pragma unroll
+      for (int r = a + 1; r < 4; ++r) off += A[a][r] * A[a][r];
+    }
+    if (off <= 1e-36 * diag) break;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int r = a + 1; r < 4; ++r) {
+        if (fabs(A[a][r]) < 1e-300) continue;
+        const double theta = (A[r][r] - A[a][a]) / (2 * A[a][r]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+        const double c = 1 / sqrt(t * t + 1), sn = t * c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double akp = A[k][a], akr = A[k][r];
+          A[k][a] = c * akp - sn * akr;
+          A[k][r] = sn * akp + c * akr;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double apk = A[a][k], ark = A[r][k];
+          A[a][k] = c * apk - sn * ark;
+          A[r][k] = sn * apk + c * ark;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = V[k][a], vkr = V[k][r];
+          V[k][a] = c * vkp - sn * vkr;
+          V[k][r] = sn * vkp + c * vkr;
+        }
+      }
+  }
+  double eig = A[0][0], qv[4] = {V[0][0], V[1][0], V[2][0], V[3][0]};
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (A[k][k] < eig) {
+      eig = A[k][k];
+      qv[0] = V[0][k]; qv[1] = V[1][k]; qv[2] = V[2][k]; qv[3] = V[3][k];
+    }
+  if (eig < 0) eig = fabs(eig) < 1e-6 ? 0.0 : -eig;
+  const double nq = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2] + qv[3] * qv[3]);
+  const double q0 = qv[0] / nq, q1 = qv[1] / nq, q2 = qv[2] / nq, q3 = qv[3] / nq;
+  double* R = krot + po * 9;
+  R[0] = 2 * (0.5 - q2 * q2 - q3 * q3); R[1] = 2 * (q1 * q2 - q0 * q3); R[2] = 2 * (q1 * q3 + q0 * q2);
+  R[3] = 2 * (q1 * q2 + q0 * q3); R[4] = 2 * (0.5 - q1 * q1 - q3 * q3); R[5] = 2 * (q2 * q3 - q0 * q1);
+  R[6] = 2 * (q1 * q3 - q0 * q2); R[7] = 2 * (q2 * q3 + q0 * q1); R[8] = 2 * (0.5 - q1 * q1 - q2 * q2);
+  kdist[po] = sqrt(eig);
 }
 
 }  // namespace
@@ -416,7 +519,8 @@ int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_p
 
 // d_perm [np, norient, natoms], d_ok [np, norient] (1 = the permutation is the proven optimum)
 int fo_sph_assign_run_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB, const double* d_frac,
-                          int64_t np, int64_t natoms, int L, int norient, int32_t* d_perm, int32_t* d_ok) {
+                          int64_t np, int64_t natoms, int L, int norient, int32_t* d_perm, int32_t* d_ok,
+                          double* d_kdist, double* d_krot) {
   if (np == 0) return FO_OK;
   const int N = (int)natoms, ng = (int)ctx->h_goff.size() - 1, ncols = ctx->h_goff[ng];
   const size_t smem = ((size_t)3 * ncols + 3 * N + 10) * 8 + (size_t)3 * ncols * 4;
@@ -435,7 +539,7 @@ int fo_sph_assign_run_dev(fo_ctx* ctx, const double* d_posA, const double* d_pos
   fo_prof_scope prof(ctx, FO_PROF_ASSIGN);
   FO_CUDA(ctx, cudaFuncSetAttribute(sph_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sph_assign_kernel<<<(unsigned)(np * norient), threads, smem, ctx->stream>>>(P, d_posA, d_posB, d_frac, ctx->d_goff,
-                                                                             ctx->d_gidx, d_perm, d_ok);
+                                                                             ctx->d_gidx, d_perm, d_ok, d_kdist, d_krot);
   FO_LAUNCH_CHECK(ctx);
   return FO_OK;
 }

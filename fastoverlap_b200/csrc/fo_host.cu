@@ -926,7 +926,11 @@ int host_refine_spherical_impl(const double* posA, const double* posB, int64_t n
                                const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
                                const double* euler, int norient, const int32_t* perm_hint,
                                const int32_t* hint_ok, int nthreads, double* dist, int32_t* orient_out,
-                               int32_t* perm_out, double* rmat_out) {
+                               int32_t* perm_out, double* rmat_out, const int64_t* pair_idx = nullptr,
+                               const double* pre_dist = nullptr, const double* pre_rot = nullptr) {
+  // pair_idx: npairs indices into the arrays (a subset of a larger batch), or null for pairs 0 .. npairs - 1
+  // pre_dist [P, norient] / pre_rot [P, norient, 9]: Kearsley distance and rotation the device already computed for
+  // the orientations whose hint_ok is set (sph_assign_kernel): those orientations cost nothing here
   if (!posA || !posB || !euler || !dist || npairs < 0 || natoms < 1 || norient < 1 || norient > 2)
     return FO_ERR_INVALID;
   if (!groups_valid(group_offsets, ngroups, atom_idx, natoms)) return FO_ERR_INVALID;
@@ -946,12 +950,25 @@ int host_refine_spherical_impl(const double* posA, const double* posB, int64_t n
     std::vector<double> cost, xr((size_t)3 * N);
     std::vector<int> c4r, perm(N), bestperm(N);
 #pragma omp for schedule(dynamic, 8)
-    for (int64_t q = 0; q < npairs; ++q) {
+    for (int64_t qi = 0; qi < npairs; ++qi) {
+      const int64_t q = pair_idx ? pair_idx[qi] : qi;
       const double* x1 = posA + (size_t)q * N * 3;
       const double* x2 = posB + (size_t)q * N * 3;
       double best = std::numeric_limits<double>::infinity(), bestR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
       int besto = 0;
       for (int o = 0; o < norient; ++o) {
+        if (pre_dist && hint_ok && hint_ok[q * norient + o]) {  // settled and fitted on the device
+          const double d = pre_dist[q * norient + o];
+          count(1);
+          if (d < best) {
+            best = d;
+            besto = o;
+            const int32_t* h = perm_hint + ((size_t)q * norient + o) * N;
+            for (int i = 0; i < N; ++i) bestperm[i] = h[i];
+            memcpy(bestR, pre_rot + ((size_t)q * norient + o) * 9, sizeof(bestR));
+          }
+          continue;
+        }
         const double* e = euler + ((size_t)q * norient + o) * 3;
         double M[9], R[9];
         euler_m(e[0], e[1], e[2], M);
@@ -1004,6 +1021,19 @@ extern "C" int fo_host_refine_spherical_hint(const double* posA, const double* p
                                              double* rmat_out) {
   return host_refine_spherical_impl(posA, posB, npairs, natoms, group_offsets, ngroups, atom_idx, euler, norient,
                                     perm_hint, hint_ok, nthreads, dist, orient_out, perm_out, rmat_out);
+}
+
+// the pairs pair_idx[0 .. nidx) of a batch (the ones the device did not settle)
+int fo_host_refine_spherical_subset(const double* posA, const double* posB, int64_t natoms,
+                                    const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                                    const double* euler, int norient, const int32_t* perm_hint, const int32_t* hint_ok,
+                                    const int64_t* pair_idx, int64_t nidx, int nthreads, double* dist,
+                                    int32_t* orient_out, int32_t* perm_out, double* rmat_out, const double* pre_dist,
+                                    const double* pre_rot) {
+  if (nidx > 0 && !pair_idx) return FO_ERR_INVALID;
+  return host_refine_spherical_impl(posA, posB, nidx, natoms, group_offsets, ngroups, atom_idx, euler, norient,
+                                    perm_hint, hint_ok, nthreads, dist, orient_out, perm_out, rmat_out, pair_idx,
+                                    pre_dist, pre_rot);
 }
 
 // ---------------------------------------------------------------------------------------------------------

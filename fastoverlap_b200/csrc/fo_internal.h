@@ -150,6 +150,14 @@ inline std::vector<int64_t> fo_chunk_starts(int64_t npairs, int64_t chunk) {
   return s;
 }
 
+// host pool on a subset of a batch of cluster pairs (fo_host.cu; internal)
+int fo_host_refine_spherical_subset(const double* posA, const double* posB, int64_t natoms,
+                                    const int32_t* group_offsets, int64_t ngroups, const int32_t* atom_idx,
+                                    const double* euler, int norient, const int32_t* perm_hint, const int32_t* hint_ok,
+                                    const int64_t* pair_idx, int64_t nidx, int nthreads, double* dist,
+                                    int32_t* orient_out, int32_t* perm_out, double* rmat_out,
+                                    const double* pre_dist = nullptr, const double* pre_rot = nullptr);
+
 // make sure a permutation (at least the trivial one) exists for natoms atoms
 int fo_ensure_perm(fo_ctx* ctx, int64_t natoms);
 
@@ -175,7 +183,8 @@ int fo_per_assign_run_dev(fo_ctx* ctx, const fo_per_params* p, const double* d_p
                           const double* d_frac, int64_t np, int niter, double* d_dist, double* d_disp,
                           void* d_perm, int32_t* d_flag, int perm_elt = 4);  // perm_elt: bytes per index (4, 2, 1)
 int fo_sph_assign_run_dev(fo_ctx* ctx, const double* d_posA, const double* d_posB, const double* d_frac,
-                          int64_t np, int64_t natoms, int L, int norient, int32_t* d_perm, int32_t* d_ok);
+                          int64_t np, int64_t natoms, int L, int norient, int32_t* d_perm, int32_t* d_ok,
+                          double* d_kdist = nullptr, double* d_krot = nullptr);  // Kearsley fit of settled assignments
 
 int fo_refine_eval_dev(fo_ctx* ctx, const void* d_Ihalf, int64_t np, int L, const double* d_euler, double* d_value,
                        double* d_grad, double* d_hess);

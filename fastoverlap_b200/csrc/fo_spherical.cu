@@ -3351,9 +3351,9 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
   FO_CHECK(fo_scratch(ctx, FO_SCR_POSB, 2 * pos_bytes, &dB));
   FO_CHECK(fo_scratch(ctx, FO_SCR_COEF, (size_t)chunk * (O * 88 + 8) + 256, &dout));
   if (grid_out) FO_CHECK(fo_scratch(ctx, FO_SCR_GRID, (size_t)chunk * O * G3 * 8, &dgrid));
-  // full alignment: ok[np O] i32 | perm[np O N] i32 per chunk
+  // full alignment, per chunk: kdist[np O] f64 | krot[np O 9] f64 | ok[np O] i32 | perm[np O N] i32
   void *dfull = nullptr, *hFull = nullptr;
-  const size_t full_stride = (size_t)O * 4 * (1 + natoms);
+  const size_t full_stride = (size_t)O * (80 + 4 * (1 + natoms));
   if (full) {
     FO_CHECK(fo_ensure_perm(ctx, natoms));
     FO_CHECK(fo_scratch(ctx, FO_SCR_FULL, (size_t)chunk * full_stride, &dfull));
@@ -3416,14 +3416,38 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
       eul[3 * i + 2] = (2 * kPi / n2) * fr[3 * i + 2];
     }
     if (full->euler_grid) memcpy(full->euler_grid + (size_t)p0 * O * 3, eul.data(), (size_t)np * O * 24);
-    const int32_t* ok = (const int32_t*)((const char*)hFull + (c & 1) * (size_t)chunk * full_stride);
+    const char* fsrc = (const char*)hFull + (c & 1) * (size_t)chunk * full_stride;
+    const double* kd = (const double*)fsrc;
+    const double* kR = kd + (size_t)np * O;
+    const int32_t* ok = (const int32_t*)(kR + (size_t)np * O * 9);
     const int32_t* hint = ok + (size_t)np * O;
-    for (int64_t i = 0; i < np * O; ++i) full->nhost += ok[i] ? 0 : 1;
-    const int rc = fo_host_refine_spherical_hint(
-        posA + (size_t)p0 * natoms * 3, posB + (size_t)p0 * natoms * 3, np, natoms, ctx->h_goff.data(),
-        (int64_t)ctx->h_goff.size() - 1, ctx->h_gidx.data(), eul.data(), O, hint, ok, full->nthreads,
-        full->dist + p0, full->orient ? full->orient + p0 : nullptr,
-        full->perm ? full->perm + (size_t)p0 * natoms : nullptr, full->rmat ? full->rmat + 9 * p0 : nullptr);
+    // pairs whose orientations were all settled on the device (assignment proven optimal, Kearsley fit done there):
+    // pick the orientation with the smaller distance, first one on ties (the host loop's rule), and copy; the
+    // others go through the host pool (LAP where the screening failed + Kearsley)
+    std::vector<int64_t> hard;
+    for (int64_t q = 0; q < np; ++q) {
+      bool all = true;
+      for (int o = 0; o < O; ++o) all = all && ok[q * O + o];
+      if (!all) {
+        for (int o = 0; o < O; ++o) full->nhost += ok[q * O + o] ? 0 : 1;
+        hard.push_back(q);
+        continue;
+      }
+      int bo = 0;
+      for (int o = 1; o < O; ++o)
+        if (kd[q * O + o] < kd[q * O + bo]) bo = o;
+      full->dist[p0 + q] = kd[q * O + bo];
+      if (full->orient) full->orient[p0 + q] = bo;
+      if (full->perm) memcpy(full->perm + (size_t)(p0 + q) * natoms, hint + ((size_t)q * O + bo) * natoms, (size_t)natoms * 4);
+      if (full->rmat) memcpy(full->rmat + 9 * (p0 + q), kR + ((size_t)q * O + bo) * 9, 72);
+    }
+    int rc = FO_OK;
+    if (!hard.empty())
+      rc = fo_host_refine_spherical_subset(
+          posA + (size_t)p0 * natoms * 3, posB + (size_t)p0 * natoms * 3, natoms, ctx->h_goff.data(),
+          (int64_t)ctx->h_goff.size() - 1, ctx->h_gidx.data(), eul.data(), O, hint, ok, hard.data(), (int64_t)hard.size(),
+          full->nthreads, full->dist + p0, full->orient ? full->orient + p0 : nullptr,
+          full->perm ? full->perm + (size_t)p0 * natoms : nullptr, full->rmat ? full->rmat + 9 * p0 : nullptr, kd, kR);
     if (rc != FO_OK) return fo_fail(ctx, rc, "host refinement of chunk %lld failed", (long long)c);
     return FO_OK;
   };
@@ -3446,7 +3470,9 @@ int align_pairs_impl(fo_ctx* ctx, const double* posA, const double* posB, int64_
     if (full)  // nearest-partner screening of both orientations on the device (reads the positions again)
       FO_CHECK(fo_sph_assign_run_dev(ctx, (const double*)((char*)dA + buf * pos_bytes),
                                      (const double*)((char*)dB + buf * pos_bytes), d_fr, np, natoms, L, O,
-                                     (int32_t*)dfull + (size_t)np * O, (int32_t*)dfull));
+                                     (int32_t*)((double*)dfull + (size_t)np * O * 10) + (size_t)np * O,
+                                     (int32_t*)((double*)dfull + (size_t)np * O * 10), (double*)dfull,
+                                     (double*)dfull + (size_t)np * O));
     FO_CUDA(ctx, cudaEventRecord(ctx->ev[2 + buf], ctx->stream));
     if (grid_out) {  // test / single-pair path: straight into the caller's arrays
       if (euler) {

@@ -135,8 +135,11 @@ def _lj38_pairs(P, jitter, seed=20171013):
 
 @pytest.mark.parametrize("jitter,P", [(0.05, 256), (0.0, 64), (0.25, 96)])
 def test_spherical_full_matches_two_step(ctx, jitter, P):
-    """Bench configuration (LJ38, Jmax = 15, sigma = 0.3, both orientations): the full path against the hot
-    path + fo_host_refine_spherical on every (pair, orientation): bit-identical."""
+    """Bench configuration (LJ38, Jmax = 15, sigma = 0.3, both orientations): the full path (screening AND
+    Kearsley fit of the settled pairs on the device, host pool for the rest) against the hot path +
+    fo_host_refine_spherical on every (pair, orientation): same orientation and permutation, distance and rotation
+    matrix to rounding (the device sums the quaternion matrix in a different order and rotates with its own
+    sincos; an exact copy has distance sqrt(rounding residue) ~ 1e-8, compared at that level)."""
     from fastoverlap_b200 import SphericalAlign, _lib
     from fastoverlap_b200.utils import indtoEuler
     A, B = _lj38_pairs(P, jitter)
@@ -146,8 +149,8 @@ def test_spherical_full_matches_two_step(ctx, jitter, P):
     d_ref, o_ref, pm_ref, r_ref = _lib.host_refine_spherical(A, B, eul, None, 4)
     dist, orient, pm, rmat, eu, st2, nhost = ctx.sph_align_pairs_full(A, B, 15, 0.3, invert=True, nthreads=4)
     assert np.array_equal(eu, eul)
-    assert np.array_equal(dist, d_ref) and np.array_equal(orient, o_ref)
-    assert np.array_equal(pm, pm_ref) and np.array_equal(rmat, r_ref)
+    assert np.allclose(dist, d_ref, rtol=1e-11, atol=1e-12 if jitter > 0 else 1e-6) and np.array_equal(orient, o_ref)
+    assert np.array_equal(pm, pm_ref) and np.allclose(rmat, r_ref, atol=1e-9 if jitter > 0 else 1e-6)
     if jitter <= 0.05:
         # the correct orientation of a perturbed copy is always settled by the screening
         assert nhost <= P
@@ -185,5 +188,5 @@ def test_spherical_full_groups_and_reference_pair(ctx):
     eul = indtoEuler(fr.reshape(-1, 3), 20).reshape(fr.shape)
     d_ref, o_ref, pm_ref, r_ref = _lib.host_refine_spherical(A, B, eul, groups, 2)
     dist, orient, pm, rmat, eu, st, nhost = ctx.sph_align_pairs_full(A, B, 9, 0.5, invert=True, nthreads=2)
-    assert np.array_equal(dist, d_ref) and np.array_equal(pm, pm_ref) and np.array_equal(orient, o_ref)
+    assert np.allclose(dist, d_ref, rtol=1e-11, atol=1e-12) and np.array_equal(pm, pm_ref) and np.array_equal(orient, o_ref)
     assert np.median(dist) < 3 * 0.02 * np.sqrt(3 * N)
