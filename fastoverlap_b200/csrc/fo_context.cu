@@ -209,6 +209,14 @@ extern "C" int fo_set_option(fo_ctx* ctx, const char* name, int64_t value) {
     ctx->direct_gemm_min = value < 1 ? 1 : value;
     return FO_OK;
   }
+  static const char* const tuning[] = {"per_sf_scalar", "per_sf_padded", "per_sf_tile_atoms", "per_sf_syncthreads",
+                                       "per_xf_generic", "per_chunk_mb", "sph_chunk_mb"};
+  for (const char* t : tuning)
+    if (strcmp(name, t) == 0) {
+      if (value == 0) ctx->tune.erase(t);
+      else ctx->tune[t] = value;
+      return FO_OK;
+    }
   return fo_fail(ctx, FO_ERR_INVALID, "unknown option '%s'", name);
 }
 

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <algorithm>
 #include <string>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/fastoverlap_b200.h"
@@ -64,6 +66,13 @@ struct fo_ctx {
   int isoft_variant = 0;
   // independent pairs at n = 9: fused structure factors + cross-spectrum (no bank); 0 = bank path (A/B, tests)
   bool pairs_fused = true;
+  // tuning / A-B hooks set through fo_set_option (no environment variables): per_sf_scalar, per_sf_padded,
+  // per_sf_tile_atoms, per_sf_syncthreads, per_xf_generic, per_chunk_mb, sph_chunk_mb
+  std::map<std::string, int64_t> tune;
+  int64_t opt(const char* name, int64_t dflt = 0) const {
+    const auto it = tune.find(name);
+    return it == tune.end() ? dflt : it->second;
+  }
   // clusters with at least this many atoms use the tensor-core GEMM form of the direct coefficients
   int64_t direct_gemm_min = 64;
 

@@ -2108,7 +2108,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
     const int NTq = (2 * M + 7) / 8;
     const int mtiles = (M * M * 4 + 7) / 8;
     static const int mt_for_nt[10] = {0, 5, 5, 5, 4, 3, 2, 2, 2, 2};
-    if (NTq <= 9 && !ctx->force_generic && !getenv("FO_SF_SCALAR")) {  // n <= 35; beyond, the scalar kernel
+    if (NTq <= 9 && !ctx->force_generic && !ctx->opt("per_sf_scalar")) {  // n <= 35; beyond, the scalar kernel
       const int MTq = mt_for_nt[NTq];
       int warps = (mtiles + MTq - 1) / MTq;
       if (warps > 10) warps = 10;
@@ -2117,7 +2117,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
       // double-buffered phasor tables of TA atoms.  Every tile costs one CTA barrier (measured ~2.5 % of the
       // kernel each at n = 9), so TA is the largest tile that still lets two CTAs share an SM (113 KB each),
       // then evened out over the tiles of the largest group: 204 atoms -> 2 tiles of 104 (64-atom tiles: 4)
-      const bool sf3 = M == 10 && warps == 10 && !getenv("FO_SF_PADDED");  // per_sf3_kernel: no column padding
+      const bool sf3 = M == 10 && warps == 10 && !ctx->opt("per_sf_padded");  // per_sf3_kernel: no column padding
       const size_t row_bytes = (sf3 ? sf_pitch(10) + sf_pitch(12) + sf_pitch(10) : 2 * Mp + Mz) * (size_t)16;
       int TA = (int)((size_t)113 * 1024 / (2 * row_bytes)) & ~3;
       TA = TA < 16 ? 16 : (TA > 128 ? 128 : TA);
@@ -2125,8 +2125,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
       for (int q = 0; q < ngroups; ++q) gmax = std::max(gmax, (int)(ctx->h_goff[q + 1] - ctx->h_goff[q]));
       const int ntile = (gmax + TA - 1) / TA;
       TA = std::min(TA, (((gmax + ntile - 1) / ntile) + 3) & ~3);
-      if (const char* e = getenv("FO_SF_TA")) {  // tuning override (multiple of 4)
-        const int v = atoi(e);
+      if (const int v = (int)ctx->opt("per_sf_tile_atoms")) {  // tuning override (multiple of 4)
         if (v >= 4 && v <= 256 && v % 4 == 0) TA = v;
       }
       const size_t smem = (size_t)2 * TA * row_bytes;
@@ -2142,7 +2141,7 @@ int launch_sf(fo_ctx* ctx, const fo_per_params* p, const double* d_pos, int64_t 
         d_pos, ctx->d_goff, ctx->d_gidx, ngroups, (int)p->natoms, n, TA, kx, ky, kz, d_bank);                \
   } while (0)
         if (sf3) {  // default k-grid of 256 atoms
-          if (!getenv("FO_SF_SYNCTHREADS")) {  // tile hand-over through mbarriers (default)
+          if (!ctx->opt("per_sf_syncthreads")) {  // tile hand-over through mbarriers (default)
             FO_CUDA(ctx, cudaFuncSetAttribute(per_sf3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem));
             per_sf3_kernel<true><<<(unsigned)nstruct, 320, smem, ctx->stream>>>(
@@ -2275,7 +2274,7 @@ int launch_xf(fo_ctx* ctx, const fo_per_params* p, const double2* d_bankA, const
     const int NT5 = (F / 2 + 1 + 7) / 8;
     const X5Layout lay5(n, F, NT5, optin);
     const size_t smem5 = (size_t)lay5.total * 8;
-    if (NT5 >= 3 && NT5 <= 9 && smem5 <= optin && !ctx->force_generic && 2 * n + 1 <= 129 && !getenv("FO_XF_GENERIC")) {
+    if (NT5 >= 3 && NT5 <= 9 && smem5 <= optin && !ctx->force_generic && 2 * n + 1 <= 129 && !ctx->opt("per_xf_generic")) {
       void *ximg = nullptr, *yin = nullptr;
       FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)npairs * lay5.ximg_doubles() * 8, &ximg));
       FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, (size_t)blocks * lay5.yin_doubles(F) * 8, &yin));
@@ -2392,7 +2391,7 @@ int64_t chunk_pairs(fo_ctx* ctx, const fo_per_params* p, int64_t npairs, bool wa
                     size_t budget_mb = 768) {
   const size_t per_pair = 2 * bank_elems_per_struct(ctx, p) * 16;
   size_t budget = budget_mb << 20;
-  if (const char* e = getenv("FO_PER_BANK_MB")) budget = (size_t)atol(e) << 20;
+  if (const int64_t mb = ctx->opt("per_chunk_mb")) budget = (size_t)mb << 20;  // tuning hook of the A/B scripts
   int64_t c = (int64_t)(budget / per_pair);
   if (want_grid) {
     const size_t g = (size_t)p->nfspace * p->nfspace * p->nfspace * 8;

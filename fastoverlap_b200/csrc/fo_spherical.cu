@@ -3005,7 +3005,7 @@ int64_t direct_chunk(const fo_ctx* ctx, int64_t npairs, int64_t natoms, int L, b
   // aligned pairs/s end to end), 4 GB when the input is device-resident (no copies to overlap: fewer launch tails)
   // and for large clusters / bandwidths (> 256 MB per pair)
   size_t budget = (per > ((size_t)256 << 20) || device_resident) ? (size_t)4 << 30 : (size_t)2 << 30;
-  if (const char* e = getenv("FO_SPH_CHUNK_MB")) budget = (size_t)atol(e) << 20;  // tuning hook of the A/B scripts
+  if (const int64_t mb = ctx->opt("sph_chunk_mb")) budget = (size_t)mb << 20;  // tuning hook of the A/B scripts
   int64_t c = (int64_t)(budget / per);
   if (want_grid) {
     const size_t g = (size_t)8 * 2 * (2 * L + 2) * (2 * L + 2) * (2 * L + 2);

@@ -1,5 +1,5 @@
 """End-to-end (host buffers, full alignment) step time of BLJ256 against the chunk size of the host pipeline.
-    python scripts/probe_e2e_chunks.py [pairs]        (FO_PER_BANK_MB sets the chunk budget: 768 MB = 3256 pairs)"""
+    python scripts/probe_e2e_chunks.py [pairs]        [chunk budget in MB -> option per_chunk_mb]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,6 +9,9 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 wl = bench.Blj256()
 ctx = fob.Context(0)
 wl.setup(ctx)
+MB = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # chunk budget in MB (0: the library's default)
+if MB:
+    ctx.set_option("per_chunk_mb", MB)
 A, B, _ = wl.make(P, 0)
 hA, hB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
 for _ in range(2):
@@ -20,6 +23,6 @@ for _ in range(n):
     wl.run_host_full(ctx, hA.numpy(), hB.numpy(), 16)
 wall = (time.perf_counter() - t0) / n * 1e3
 prof = ctx.profile_end()
-print("FO_PER_BANK_MB=%s: %.2f ms per %d pairs (%.0f pairs/s); kernels %.2f ms %s" % (
-    os.environ.get("FO_PER_BANK_MB", "768"), wall, P, P / wall * 1e3, sum(v[0] for v in prof.values()) / n,
+print("per_chunk_mb=%s MB: %.2f ms per %d pairs (%.0f pairs/s); kernels %.2f ms %s" % (
+    (MB or "default"), wall, P, P / wall * 1e3, sum(v[0] for v in prof.values()) / n,
     {k: round(v[0] / n, 2) for k, v in prof.items()}))
