@@ -30,60 +30,190 @@ namespace {
 long long g_counters[3] = {0, 0, 0};
 inline void count(int k) { __atomic_fetch_add(&g_counters[k], 1LL, __ATOMIC_RELAXED); }
 
-#if defined(__GNUC__) && !defined(__CUDACC__)
-#define FO_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
-#else
-#define FO_CLONES
-#endif
+// ---------------------------------------------------------------------------------------------------------
+// Inner loops of the assignment, written with GCC vector extensions (one vector of the widest native type per
+// statement; a 64-byte vector type on a narrower ISA is scalarised, so every kernel is stamped out per ISA and
+// picked once at load time).  The auto-vectorised forms of these loops kept their running minima on the stack
+// and ran at 4-5 cycles per matrix entry; the search for the minimising column was a scalar pass with a branch
+// per column and took most of a hard assignment (profiles/r02_summary.md, "Host pool").
+//
+// lap_pad(n): row pitch of the cost matrix and length of the padded column arrays (a multiple of the widest
+// vector).  Padding columns repeat the last real column; nothing reads their results.
+constexpr int LAPW = 8;
+inline int lap_pad(int n) { return (n + LAPW - 1) / LAPW * LAPW; }
 
-// One row scan of the shortest-augmenting-path search (Lap::solve): relaxes every column through row i and
-// returns the smallest tentative distance.  cd: tentative distances (+inf for closed columns), cl: 0 / +inf
-// for open / closed columns, pd: predecessor row (as a double, one lane type).
-FO_CLONES double lap_scan(int n, const double* ci, const double* v, const double* cl, double* cd, double* pd,
-                          double minVal, double ui, double di) {
-  double lowest = std::numeric_limits<double>::infinity();
-#pragma omp simd reduction(min : lowest)
-  for (int j = 0; j < n; ++j) {
-    const double r = minVal + ci[j] - ui - v[j] + cl[j];
-    const bool lt = r < cd[j];
-    const double c = lt ? r : cd[j];
-    cd[j] = c;
-    pd[j] = lt ? di : pd[j];
-    lowest = c < lowest ? c : lowest;
+// Horizontal (value, index) minimum of a vector pair: smallest value, on ties the smallest index, as log2(W)
+// shuffle / compare / blend steps (the scalar form compiles into a data-dependent branch per lane, and the lane
+// of the minimum is as good as random).  V / I are overwritten; afterwards every lane holds the result.
+#define FO_HSTEP(V, I, ...)                                          \
+  {                                                                  \
+    const vd sv_ = __builtin_shufflevector(V, V, __VA_ARGS__);       \
+    const vd si_ = __builtin_shufflevector(I, I, __VA_ARGS__);       \
+    const vl t_ = (sv_ < V) | ((sv_ == V) & (si_ < I));              \
+    V = t_ ? sv_ : V;                                                \
+    I = t_ ? si_ : I;                                                \
   }
-  return lowest;
-}
+#define FO_HMIN8(V, I) FO_HSTEP(V, I, 4, 5, 6, 7, 0, 1, 2, 3) FO_HSTEP(V, I, 2, 3, 0, 1, 6, 7, 4, 5) FO_HSTEP(V, I, 1, 0, 3, 2, 5, 4, 7, 6)
+#define FO_HMIN4(V, I) FO_HSTEP(V, I, 2, 3, 0, 1) FO_HSTEP(V, I, 1, 0, 3, 2)
+#define FO_HMIN2(V, I) FO_HSTEP(V, I, 1, 0)
 
-// Dense n x n linear assignment (minimise), cost row-major.  col4row[i] = column assigned to row i.
+// FO_LAP_KERNELS(S, W, HMIN, ATTR) defines, for vectors of W doubles:
+//  scan_S   one row scan of the shortest-augmenting-path search (Lap::solve): relaxes every column through row
+//           i, returns the smallest tentative distance and picks its column -- on ties an unassigned column
+//           first, then the lowest index (scipy's rule).  cd: tentative distances (+inf for closed columns),
+//           cl: 0 / +inf for open / closed columns, asg: 0 / +inf for unassigned / assigned columns, pd:
+//           predecessor row (as a double, one lane type).  The arithmetic of r is scipy's, term by term.  All
+//           column arrays have nl = lap_pad(n) entries; v = -inf in the padding keeps those columns at +inf.
+//  cost_S   squared (minimum-image, box != null) distances between the rows xs and the columns ys (structure
+//           of arrays, ys padded to lap_pad(n)), with the running minimum of every column, its row and the
+//           second smallest entry (the column reduction of the LAP and the gap test of best_perm) kept in
+//           registers over the sweep down the rows.  rint(t) = (t + 1.5 * 2^52) - 1.5 * 2^52 in round-to-nearest.
+#define FO_LAP_KERNELS(S, W, HMIN, ATTR)                                                                       \
+  ATTR double scan_##S(int nl, const double* ci, const double* v, const double* cl, const double* asg,        \
+                       double* cd, double* pd, double minVal, double ui, double di, int* pick) {              \
+    typedef double vd __attribute__((vector_size(8 * W)));                                                    \
+    typedef long long vl __attribute__((vector_size(8 * W)));                                                 \
+    const double inf = std::numeric_limits<double>::infinity();                                               \
+    vd vlo = (vd){} + inf, vlou = vlo, vli = (vd){}, vliu = (vd){}, jv;                                       \
+    {                                                                                                         \
+      double t_[W];                                                                                           \
+      for (int l = 0; l < W; ++l) t_[l] = (double)l;                                                          \
+      memcpy(&jv, t_, sizeof(vd));                                                                            \
+    }                                                                                                         \
+    for (int j = 0; j < nl; j += W) {                                                                         \
+      vd c_, v_, l_, d_, p_, a_;                                                                              \
+      memcpy(&c_, ci + j, sizeof(vd));                                                                        \
+      memcpy(&v_, v + j, sizeof(vd));                                                                         \
+      memcpy(&l_, cl + j, sizeof(vd));                                                                        \
+      memcpy(&d_, cd + j, sizeof(vd));                                                                        \
+      memcpy(&p_, pd + j, sizeof(vd));                                                                        \
+      memcpy(&a_, asg + j, sizeof(vd));                                                                       \
+      const vd r = minVal + c_ - ui - v_ + l_;                                                                \
+      const vl lt = r < d_;                                                                                   \
+      const vd c = lt ? r : d_;                                                                               \
+      p_ = lt ? (vd){} + di : p_;                                                                             \
+      memcpy(cd + j, &c, sizeof(vd));                                                                         \
+      memcpy(pd + j, &p_, sizeof(vd));                                                                        \
+      const vl m = c < vlo;                                                                                   \
+      vli = m ? jv : vli;                                                                                     \
+      vlo = m ? c : vlo;                                                                                      \
+      const vd cu = c + a_;                                                                                   \
+      const vl mu = cu < vlou;                                                                                \
+      vliu = mu ? jv : vliu;                                                                                  \
+      vlou = mu ? cu : vlou;                                                                                  \
+      jv += (double)W;                                                                                        \
+    }                                                                                                         \
+    HMIN(vlo, vli)                                                                                            \
+    HMIN(vlou, vliu)                                                                                          \
+    const double lo = vlo[0], lou = vlou[0], li = vli[0], liu = vliu[0];                                      \
+    *pick = lo == inf ? -1 : (lou == lo ? (int)liu : (int)li);                                                \
+    return lo;                                                                                                \
+  }                                                                                                           \
+  ATTR void cost_##S(int n, int ld, const double* xs, const double* ys, const double* box, double* cost,      \
+                     double* vmin, int* imin, double* vmin2) {                                                \
+    typedef double vd __attribute__((vector_size(8 * W)));                                                    \
+    typedef long long vl __attribute__((vector_size(8 * W)));                                                 \
+    const double inf = std::numeric_limits<double>::infinity(), M = 6755399441055744.0;                       \
+    const double b0 = box ? box[0] : 1.0, b1 = box ? box[1] : 1.0, b2 = box ? box[2] : 1.0;                   \
+    const double i0 = 1.0 / b0, i1 = 1.0 / b1, i2 = 1.0 / b2;                                                 \
+    for (int jb = 0; jb < ld; jb += W) {                                                                      \
+      vd y0, y1, y2;                                                                                          \
+      memcpy(&y0, ys + jb, sizeof(vd));                                                                       \
+      memcpy(&y1, ys + ld + jb, sizeof(vd));                                                                  \
+      memcpy(&y2, ys + 2 * ld + jb, sizeof(vd));                                                              \
+      vd vm = (vd){} + inf, v2 = vm, im = (vd){};                                                             \
+      if (box) {                                                                                              \
+        for (int i = 0; i < n; ++i) {                                                                         \
+          vd dx = xs[i] - y0, dy = xs[n + i] - y1, dz = xs[2 * n + i] - y2;                                   \
+          dx -= ((dx * i0 + M) - M) * b0;                                                                     \
+          dy -= ((dy * i1 + M) - M) * b1;                                                                     \
+          dz -= ((dz * i2 + M) - M) * b2;                                                                     \
+          const vd d = dx * dx + dy * dy + dz * dz;                                                           \
+          memcpy(cost + (size_t)i * ld + jb, &d, sizeof(vd));                                                 \
+          const vl lt = d < vm;                                                                               \
+          const vd hi = lt ? vm : d; /* the larger of the entry and the running minimum */                    \
+          v2 = hi < v2 ? hi : v2;                                                                             \
+          vm = lt ? d : vm;                                                                                   \
+          im = lt ? (vd){} + (double)i : im;                                                                  \
+        }                                                                                                     \
+      } else {                                                                                                \
+        for (int i = 0; i < n; ++i) {                                                                         \
+          const vd dx = xs[i] - y0, dy = xs[n + i] - y1, dz = xs[2 * n + i] - y2;                             \
+          const vd d = dx * dx + dy * dy + dz * dz;                                                           \
+          memcpy(cost + (size_t)i * ld + jb, &d, sizeof(vd));                                                 \
+          const vl lt = d < vm;                                                                               \
+          const vd hi = lt ? vm : d;                                                                          \
+          v2 = hi < v2 ? hi : v2;                                                                             \
+          vm = lt ? d : vm;                                                                                   \
+          im = lt ? (vd){} + (double)i : im;                                                                  \
+        }                                                                                                     \
+      }                                                                                                       \
+      double tv_[W], t2_[W], ti_[W];                                                                          \
+      memcpy(tv_, &vm, sizeof(tv_));                                                                          \
+      memcpy(t2_, &v2, sizeof(t2_));                                                                          \
+      memcpy(ti_, &im, sizeof(ti_));                                                                          \
+      for (int l = 0; l < W && jb + l < n; ++l) {                                                             \
+        vmin[jb + l] = tv_[l];                                                                                \
+        vmin2[jb + l] = t2_[l];                                                                               \
+        imin[jb + l] = (int)ti_[l];                                                                           \
+      }                                                                                                       \
+    }                                                                                                         \
+  }                                                                                                           \
+  ATTR void sqrt_##S(int n, double* c) {                                                                      \
+    for (int j = 0; j < n; ++j) c[j] = __builtin_sqrt(c[j]);                                                  \
+  }
+
+struct LapKernels {
+  double (*scan)(int, const double*, const double*, const double*, const double*, double*, double*, double, double,
+                 double, int*);
+  void (*cost)(int, int, const double*, const double*, const double*, double*, double*, int*, double*);
+  void (*sqrt_row)(int, double*);
+};
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(__CUDACC__)
+FO_LAP_KERNELS(avx512, 8, FO_HMIN8, __attribute__((target("avx512f"))))
+FO_LAP_KERNELS(avx2, 4, FO_HMIN4, __attribute__((target("avx2"))))
+FO_LAP_KERNELS(base, 2, FO_HMIN2, )
+LapKernels pick_lap_kernels() {
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f")) return {scan_avx512, cost_avx512, sqrt_avx512};
+  if (__builtin_cpu_supports("avx2")) return {scan_avx2, cost_avx2, sqrt_avx2};
+  return {scan_base, cost_base, sqrt_base};
+}
+#else
+FO_LAP_KERNELS(base, 2, FO_HMIN2, )
+LapKernels pick_lap_kernels() { return {scan_base, cost_base, sqrt_base}; }
+#endif
+const LapKernels LK = pick_lap_kernels();
+
+// Dense n x n linear assignment (minimise), cost row-major with pitch ld.  col4row[i] = column assigned to row i.
 struct Lap {
-  std::vector<double> u, v, shortest, cand, closed, pathd;
-  std::vector<int> path, row4col, remaining, colmin;
-  std::vector<char> SR, SC, rowdone;
+  std::vector<double> u, v, shortest, cand, closed, pathd, asg;
+  std::vector<int> path, row4col, colmin, srows, scols;
+  std::vector<char> rowdone;
   // colmin_in / vmin_in (optional): per-column minimum and its row, when the caller already has them.
   // lazy_sqrt: cost (and vmin_in) hold SQUARED costs; the LAP runs on their square roots, taken row by row
   // only for the rows an augmentation actually scans.  The column reduction needs no roots but those of
   // the column minima (sqrt is monotone), and after a good alignment it already assigns almost every row,
   // so a 204 x 204 periodic cost matrix costs ~200 square roots instead of 41616 (the vector sqrt was
   // 2/3 of the whole host refinement of a BLJ256 pair).
-  void solve(int n, double* cost, int* col4row, const int* colmin_in = nullptr,
+  // ld = lap_pad(n): the column arrays are padded to whole vectors (v = -inf there: a padding column stays
+  // at +inf in every scan), the matrix rows are read up to ld.
+  void solve(int n, int ld, double* cost, int* col4row, const int* colmin_in = nullptr,
              const double* vmin_in = nullptr, bool lazy_sqrt = false) {
     if (lazy_sqrt) rowdone.assign(n, 0);
     auto row_of = [&](int i) -> const double* {
-      double* ci = cost + (size_t)i * n;
+      double* ci = cost + (size_t)i * ld;
       if (lazy_sqrt && !rowdone[i]) {
-        for (int j = 0; j < n; ++j) ci[j] = __builtin_sqrt(ci[j]);
+        LK.sqrt_row(n, ci);
         rowdone[i] = 1;
       }
       return ci;
     };
     u.assign(n, 0.0);
-    v.assign(n, 0.0);
+    v.assign(ld, -std::numeric_limits<double>::infinity());
     shortest.resize(n);
     path.resize(n);
     row4col.assign(n, -1);
-    remaining.resize(n);
-    SR.resize(n);
-    SC.resize(n);
     for (int i = 0; i < n; ++i) col4row[i] = -1;
     const double inf = std::numeric_limits<double>::infinity();
     // Column reduction (the initialisation phase of Jonker-Volgenant, JOVOSAP alignutils.f90:1041-1075):
@@ -96,7 +226,7 @@ struct Lap {
         for (int j = 0; j < n; ++j) v[j] = lazy_sqrt ? __builtin_sqrt(vmin_in[j]) : vmin_in[j];
       } else {
         colmin.assign(n, 0);
-        for (int j = 0; j < n; ++j) v[j] = row_of(0)[j];
+        for (int j = 0; j < n; ++j) v[j] = row_of(0)[j];  // (all of v[0 .. n) is set on both branches)
         for (int i = 1; i < n; ++i) {
           const double* ci = row_of(i);
           for (int j = 0; j < n; ++j)
@@ -115,132 +245,59 @@ struct Lap {
         }
       }
     }
-    // Augmenting row reduction (second initialisation phase of Jonker-Volgenant, JOVOSAP alignutils.f90:1077-
-    // 1135): a free row i takes the column j1 of its smallest reduced cost c[i][j] - v[j]; v[j1] is lowered by
-    // the distance to the second smallest, which keeps j1 the row's minimum, and the row that held j1 becomes
-    // free (and is treated next, or left for the augmentation when the two minima tie).  Every assigned row
-    // keeps its column at its own minimum reduced cost, so u[i] = c[i][col4row[i]] - v[col4row[i]] (0 for the
-    // rows the column reduction placed) gives feasible duals, tight on the assigned pairs, for the augmentation.  Two passes, with a cap
-    // on the number of row scans; on hard assignments this leaves a few rows instead of a third of them to
-    // the shortest-path search.  The optimum is the same (it is unique up to exact ties).  Only used when the
-    // column reduction left at most a quarter of the rows free (partially aligned structures: BLJ256 pairs
-    // with a jitter of a fifth of the neighbour distance 185 -> 141 us); on unrelated point sets, where a third
-    // and more are free, it was measured 20-50 % slower than going straight to the search (n = 38, 100, 204).
-    {
-      bool finite = true;
-      for (int j = 0; j < n; ++j) finite = finite && v[j] == v[j];
-      remaining.clear();
-      for (int i = 0; i < n; ++i)
-        if (col4row[i] == -1) remaining.push_back(i);
-      if (finite && !remaining.empty() && n > 1 && 4 * (int)remaining.size() <= n) {
-        std::vector<int>& fr = remaining;  // free rows
-        int budget = 6 * n;
-        for (int pass = 0; pass < 2 && !fr.empty(); ++pass) {
-          const int prev = (int)fr.size();
-          int k = 0, nfree = 0;
-          while (k < prev && budget > 0) {
-            const int i = fr[k++];
-            --budget;
-            const double* ci = row_of(i);
-            double umin = ci[0] - v[0], usub = inf;
-            int j1 = 0, j2 = 0;
-            for (int j = 1; j < n; ++j) {
-              const double h = ci[j] - v[j];
-              if (h < usub) {
-                if (h >= umin) {
-                  usub = h;
-                  j2 = j;
-                } else {
-                  usub = umin;
-                  umin = h;
-                  j2 = j1;
-                  j1 = j;
-                }
-              }
-            }
-            if (!(umin == umin) || !(usub == usub)) {  // NaN in the row: leave it to the search below
-              fr[nfree++] = i;
-              continue;
-            }
-            int i0 = row4col[j1];
-            const bool strict = umin < usub;
-            if (strict)
-              v[j1] -= usub - umin;
-            else if (i0 >= 0) {
-              j1 = j2;
-              i0 = row4col[j2];
-            }
-            col4row[i] = j1;
-            row4col[j1] = i;
-            u[i] = ci[j1] - v[j1];
-            if (i0 >= 0) {
-              col4row[i0] = -1;
-              u[i0] = 0.0;
-              if (strict)
-                fr[--k] = i0;  // treated next
-              else
-                fr[nfree++] = i0;
-            }
-          }
-          for (; k < prev; ++k) fr[nfree++] = fr[k];  // budget exhausted: the rest stays free
-          fr.resize(nfree);
-        }
-      }
-    }
+    // (The augmenting row reduction of Jonker-Volgenant, JOVOSAP alignutils.f90:1077-1135, was used here in
+    // round 1 for partially aligned pairs; with the vector scan below a search step costs what a reduction step
+    // costs and the reduction needs more of them -- LJ38 inverted orientation 18.4 -> 11.3 us, BLJ256 at a
+    // jitter of 0.3: 328 -> 234 us per pair without it -- so the free rows go straight to the search.)
     // Shortest augmenting path per free row.  The scan of a row runs over ALL columns without branches or
-    // index indirection so that it vectorises: cand[j] is the tentative distance of an open column and +inf
-    // once the column is closed (then shortest[j] keeps its final distance for the dual update), closed[j] =
-    // +inf keeps a closed column from being reopened; the arithmetic of r is scipy's, term by term.
-    cand.resize(n);
-    closed.resize(n);
-    pathd.resize(n);
+    // index indirection (LK.scan): cand[j] is the tentative distance of an open column and +inf once the
+    // column is closed (then shortest[j] keeps its final distance for the dual update), closed[j] = +inf keeps
+    // a closed column from being reopened, asg[j] = +inf marks the assigned columns for the tie rule.  The rows
+    // and columns an augmentation touches are kept as lists: the dual update costs the length of the search
+    // tree, not n.
+    cand.resize(ld);
+    closed.resize(ld);
+    pathd.resize(ld);
+    asg.assign(ld, inf);
+    for (int j = 0; j < n; ++j) asg[j] = row4col[j] == -1 ? 0.0 : inf;
     for (int cur = 0; cur < n; ++cur) {
       if (col4row[cur] != -1) continue;
-      std::fill(SR.begin(), SR.end(), 0);
-      std::fill(SC.begin(), SC.end(), 0);
+      srows.clear();
+      scols.clear();
       double* cd = cand.data();
       double* cl = closed.data();
       double* pd = pathd.data();
       const double* vv = v.data();
-      for (int j = 0; j < n; ++j) {
+      for (int j = 0; j < ld; ++j) {
         cd[j] = inf;
         cl[j] = 0.0;
       }
       int sink = -1, i = cur;
       double minVal = 0.0;
       while (sink == -1) {
-        SR[i] = 1;
+        srows.push_back(i);
         const double* ci = row_of(i);
-        const double ui = u[i], di = (double)i;
-        const double lowest = lap_scan(n, ci, vv, cl, cd, pd, minVal, ui, di);
-        if (lowest == inf) return;  // infeasible (NaN costs): leave -1s
-        int index = -1;
-        for (int j = 0; j < n; ++j)
-          if (cd[j] == lowest) {  // ties: an unassigned column first
-            if (row4col[j] == -1) {
-              index = j;
-              break;
-            }
-            if (index < 0) index = j;
-          }
-        if (index < 0) return;  // NaN
+        int j;
+        const double lowest = LK.scan(ld, ci, vv, cl, asg.data(), cd, pd, minVal, u[i], (double)i, &j);
+        if (lowest == inf || j < 0) return;  // infeasible (NaN costs): leave -1s
         minVal = lowest;
-        const int j = index;
         shortest[j] = lowest;
         path[j] = (int)pd[j];
         cd[j] = inf;
         cl[j] = inf;
-        SC[j] = 1;
+        scols.push_back(j);
         if (row4col[j] == -1)
           sink = j;
         else
           i = row4col[j];
       }
       u[cur] += minVal;
-      for (int r = 0; r < n; ++r)
-        if (SR[r] && r != cur) u[r] += minVal - shortest[col4row[r]];
-      for (int j = 0; j < n; ++j)
-        if (SC[j]) v[j] -= minVal - shortest[j];
+      for (size_t k = 1; k < srows.size(); ++k) {
+        const int r = srows[k];
+        u[r] += minVal - shortest[col4row[r]];
+      }
+      for (const int j : scols) v[j] -= minVal - shortest[j];
+      asg[sink] = inf;
       int j = sink;
       while (true) {
         const int r = path[j];
@@ -296,134 +353,6 @@ struct Groups {
 // branch-free so that gcc vectorises them (function multiversioning picks the AVX2 clone at run time).
 // d * (1/box) instead of d / box can move the rounding only at exact half-box separations, where both
 // images give the same distance.
-
-// vmin / imin: running minimum of every column and its row (the column reduction of the LAP), kept in
-// the same pass that writes the matrix.  Both kernels write SQUARED distances; the periodic LAP is on the
-// distances themselves (periodicAlignment.py:94-102) and takes the square roots lazily.
-// vmin2: the second smallest entry of every column (squared), for the gap test of best_perm.
-// Columns are processed in blocks of CB: the block's y coordinates, running minima and their rows stay in
-// registers over the whole sweep down the rows (the row-by-row form reloaded and stored vmin / imin for
-// every element and ran at ~18 cycles per 4-wide vector); the row index is carried as a double so that all
-// lanes have one type.
-constexpr int CB = 8;
-
-FO_CLONES void cost_periodic(int n, const double* xs, const double* ys, const double* box, double* cost,
-                             double* vmin, int* imin, double* vmin2) {
-  const double b0 = box[0], b1 = box[1], b2 = box[2];
-  const double i0 = 1.0 / b0, i1 = 1.0 / b1, i2 = 1.0 / b2;
-  const double inf = std::numeric_limits<double>::infinity();
-  for (int jb = 0; jb < n; jb += CB) {
-    const int w = n - jb < CB ? n - jb : CB;
-    double y0[CB], y1[CB], y2[CB], vm[CB], v2[CB], im[CB];
-    for (int jj = 0; jj < CB; ++jj) {
-      const int j = jb + (jj < w ? jj : w - 1);  // the tail block repeats its last column
-      y0[jj] = ys[j];
-      y1[jj] = ys[n + j];
-      y2[jj] = ys[2 * n + j];
-      vm[jj] = inf;
-      v2[jj] = inf;
-      im[jj] = 0.0;
-    }
-    if (w == CB) {
-      for (int i = 0; i < n; ++i) {
-        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
-        double* c = cost + (size_t)i * n + jb;
-#pragma omp simd
-        for (int jj = 0; jj < CB; ++jj) {
-          double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
-          dx -= __builtin_rint(dx * i0) * b0;
-          dy -= __builtin_rint(dy * i1) * b1;
-          dz -= __builtin_rint(dz * i2) * b2;
-          const double d = dx * dx + dy * dy + dz * dz;  // squared: Lap::solve(lazy_sqrt) takes the roots it needs
-          c[jj] = d;
-          const bool lt = d < vm[jj];
-          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
-          v2[jj] = hi < v2[jj] ? hi : v2[jj];
-          vm[jj] = lt ? d : vm[jj];
-          im[jj] = lt ? di : im[jj];
-        }
-      }
-    } else {
-      for (int i = 0; i < n; ++i) {
-        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
-        double* c = cost + (size_t)i * n + jb;
-        for (int jj = 0; jj < w; ++jj) {
-          double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
-          dx -= __builtin_rint(dx * i0) * b0;
-          dy -= __builtin_rint(dy * i1) * b1;
-          dz -= __builtin_rint(dz * i2) * b2;
-          const double d = dx * dx + dy * dy + dz * dz;
-          c[jj] = d;
-          const bool lt = d < vm[jj];
-          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
-          v2[jj] = hi < v2[jj] ? hi : v2[jj];
-          vm[jj] = lt ? d : vm[jj];
-          im[jj] = lt ? di : im[jj];
-        }
-      }
-    }
-    for (int jj = 0; jj < w; ++jj) {
-      vmin[jb + jj] = vm[jj];
-      vmin2[jb + jj] = v2[jj];
-      imin[jb + jj] = (int)im[jj];
-    }
-  }
-}
-
-FO_CLONES void cost_free(int n, const double* xs, const double* ys, double* cost, double* vmin, int* imin,
-                         double* vmin2) {
-  const double inf = std::numeric_limits<double>::infinity();
-  for (int jb = 0; jb < n; jb += CB) {
-    const int w = n - jb < CB ? n - jb : CB;
-    double y0[CB], y1[CB], y2[CB], vm[CB], v2[CB], im[CB];
-    for (int jj = 0; jj < CB; ++jj) {
-      const int j = jb + (jj < w ? jj : w - 1);
-      y0[jj] = ys[j];
-      y1[jj] = ys[n + j];
-      y2[jj] = ys[2 * n + j];
-      vm[jj] = inf;
-      v2[jj] = inf;
-      im[jj] = 0.0;
-    }
-    if (w == CB) {
-      for (int i = 0; i < n; ++i) {
-        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
-        double* c = cost + (size_t)i * n + jb;
-#pragma omp simd
-        for (int jj = 0; jj < CB; ++jj) {
-          const double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
-          const double d = dx * dx + dy * dy + dz * dz;
-          c[jj] = d;
-          const bool lt = d < vm[jj];
-          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
-          v2[jj] = hi < v2[jj] ? hi : v2[jj];
-          vm[jj] = lt ? d : vm[jj];
-          im[jj] = lt ? di : im[jj];
-        }
-      }
-    } else {
-      for (int i = 0; i < n; ++i) {
-        const double x0 = xs[i], x1 = xs[n + i], x2 = xs[2 * n + i], di = (double)i;
-        double* c = cost + (size_t)i * n + jb;
-        for (int jj = 0; jj < w; ++jj) {
-          const double dx = x0 - y0[jj], dy = x1 - y1[jj], dz = x2 - y2[jj];
-          const double d = dx * dx + dy * dy + dz * dz;
-          c[jj] = d;
-          const bool lt = d < vm[jj];
-          const double hi = lt ? vm[jj] : d;  // the larger of the entry and the running minimum
-          v2[jj] = hi < v2[jj] ? hi : v2[jj];
-          vm[jj] = lt ? d : vm[jj];
-          im[jj] = lt ? di : im[jj];
-        }
-      }
-    }
-    for (int jj = 0; jj < w; ++jj) {
-      vmin[jb + jj] = vm[jj];
-      vmin2[jb + jj] = v2[jj];
-      imin[jb + jj] = (int)im[jj];
-    }
-  }
-}
 
 // Single-precision screening pass of the periodic assignment: smallest and second smallest min-image
 // distance (squared) of every column and the row of the smallest, 16 columns at a time, nothing stored.
@@ -504,8 +433,8 @@ FO_COLMIN_F32(colmin_periodic_f32, 4, )
 // distance to the half box), so a distance is off by less than 2e-6 b.  tol = 1e-5 b is used: row i_j is
 // certainly the strict minimum of column j when sqrt(second) - sqrt(first) > 2 tol in single precision, and
 // the true gap is at least that difference - 2 tol.
-bool screen_periodic(int n, const double* xs, const double* ys, const double* box, int* imin, int* c4r,
-                     double* margin) {
+bool screen_periodic(int n, const double* xs, const double* ys, int ldy, const double* box, int* imin,
+                     int* c4r, double* margin) {
   static thread_local std::vector<float> f;
   static thread_local std::vector<int> iw;
   static thread_local std::vector<char> seen;
@@ -553,7 +482,7 @@ bool screen_periodic(int n, const double* xs, const double* ys, const double* bo
   {
     const double b = box[ax], ib = 1.0 / b;
     for (int i = 0; i < n; ++i) {
-      const double x = xs[ax * n + i], y = ys[ax * n + i];
+      const double x = xs[ax * n + i], y = ys[ax * ldy + i];
       wx[i] = (float)(x - __builtin_rint(x * ib) * b);
       wy[i] = (float)(y - __builtin_rint(y * ib) * b);
     }
@@ -607,7 +536,7 @@ bool screen_periodic(int n, const double* xs, const double* ys, const double* bo
   for (int k = 0; k < 3; ++k) {
     const double b = box[k], ib = 1.0 / b;
     for (int i = 0; i < n; ++i) {
-      const double x = xs[k * n + xord[i]], y = ys[k * n + yord[i]];
+      const double x = xs[k * n + xord[i]], y = ys[k * ldy + yord[i]];
       xf[k * n + i] = (float)(x - __builtin_rint(x * ib) * b);
       yf[k * npad + i] = (float)(y - __builtin_rint(y * ib) * b);
     }
@@ -653,23 +582,26 @@ double best_perm(const Groups& G, int natoms, const double* X, const double* Y, 
     if (n == 0) continue;
     const int32_t* idx = G.gidx + G.goff[g];
     // grow only: shrinking for a small group and growing again would zero-fill the matrix every time
-    if (cost.size() < (size_t)n * n) cost.resize((size_t)n * n);
+    const int ld = lap_pad(n);  // row pitch of the matrix = padded number of columns
+    if (cost.size() < (size_t)n * ld) cost.resize((size_t)n * ld);
     if (c4r.size() < (size_t)n) c4r.resize(n);
-    if (soa.size() < (size_t)6 * n) soa.resize((size_t)6 * n);
+    if (soa.size() < (size_t)3 * n + 3 * ld) soa.resize((size_t)3 * n + 3 * ld);
     double* xs = soa.data();
-    double* ys = xs + 3 * n;
+    double* ys = xs + 3 * n;  // pitch ld, the padding repeats the last column
     for (int i = 0; i < n; ++i)
       for (int k = 0; k < 3; ++k) {
         xs[k * n + i] = X[3 * idx[i] + k];
-        ys[k * n + i] = Y[3 * idx[i] + k];
+        ys[k * ld + i] = Y[3 * idx[i] + k];
       }
+    for (int i = n; i < ld; ++i)
+      for (int k = 0; k < 3; ++k) ys[k * ld + i] = ys[k * ld + n - 1];
     if (vmin.size() < (size_t)n) {
       vmin.resize(n);
       vmin2.resize(n);
       imin.resize(n);
     }
     if (box && screen && screen[g] && n >= 2 && n < (1 << 24)) {
-      if (screen_periodic(n, xs, ys, box, imin.data(), c4r.data(), &margin)) {
+      if (screen_periodic(n, xs, ys, ld, box, imin.data(), c4r.data(), &margin)) {
         for (int i = 0; i < n; ++i) perm[idx[i]] = idx[c4r[i]];
         count(1);
         continue;
@@ -677,11 +609,8 @@ double best_perm(const Groups& G, int natoms, const double* X, const double* Y, 
       screen[g] = 0;
     }
     if (box) count(0);
-    if (box)
-      cost_periodic(n, xs, ys, box, cost.data(), vmin.data(), imin.data(), vmin2.data());
-    else
-      cost_free(n, xs, ys, cost.data(), vmin.data(), imin.data(), vmin2.data());
-    lap.solve(n, cost.data(), c4r.data(), imin.data(), vmin.data(), /*lazy_sqrt=*/box != nullptr);
+    LK.cost(n, ld, xs, ys, box, cost.data(), vmin.data(), imin.data(), vmin2.data());
+    lap.solve(n, ld, cost.data(), c4r.data(), imin.data(), vmin.data(), /*lazy_sqrt=*/box != nullptr);
     for (int i = 0; i < n; ++i) perm[idx[i]] = c4r[i] >= 0 ? idx[c4r[i]] : idx[i];
     if (margin >= 0) {
       seen.assign(n, 0);
