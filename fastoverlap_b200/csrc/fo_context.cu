@@ -210,7 +210,7 @@ extern "C" int fo_set_option(fo_ctx* ctx, const char* name, int64_t value) {
     return FO_OK;
   }
   static const char* const tuning[] = {"per_sf_scalar", "per_sf_padded", "per_sf_tile_atoms", "per_sf_syncthreads",
-                                       "per_xf_generic", "per_chunk_mb", "sph_chunk_mb"};
+                                       "per_xf_generic", "per_chunk_mb", "sph_chunk_mb", "sph_direct_ring"};
   for (const char* t : tuning)
     if (strcmp(name, t) == 0) {
       if (value == 0) ctx->tune.erase(t);

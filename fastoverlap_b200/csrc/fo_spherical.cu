@@ -138,6 +138,55 @@ sph_prep_kernel(const double* __restrict__ pos, int natoms, int L, size_t nstruc
 // Pairs of atoms in different permutation groups get 0 (the reference sums calcSO3Coeffs over
 // groups, sphericalAlignment.py:175).
 // ------------------------------------------------------------------------------------------
+// exp(-x) i_l(x) g for l = 0..L into out[l * ls] (see sph_bessel_kernel)
+__device__ __forceinline__ void bessel_levels(double ra, double rb, int L, double fact, double inv2s2,
+                                              double* __restrict__ out, size_t ls) {
+  const double x = ra * rb * inv2s2;
+  const double dr = ra - rb;
+  const double g = fact * exp(-0.5 * dr * dr * inv2s2);
+  if (!(x >= 1e-100)) {  // also catches NaN
+    out[0] = (x == x) ? g : x;
+    for (int l = 1; l <= L; ++l) out[(size_t)l * ls] = (x == x) ? 0.0 : x;
+    return;
+  }
+  if (x < 1.0) {
+    // i_l(x) = x^l/(2l+1)!! sum_q (x^2/2)^q / (q! (2l+3)(2l+5)...(2l+2q+1))
+    const double emx = exp(-x), h = 0.5 * x * x;
+    double pref = emx;  // e^{-x} x^l/(2l+1)!!
+    for (int l = 0; l <= L; ++l) {
+      double term = 1.0, sum = 1.0;
+      for (int q = 1; q <= 14; ++q) {
+        term *= h / ((double)q * (2.0 * l + 2.0 * q + 1.0));
+        sum += term;
+      }
+      out[(size_t)l * ls] = g * pref * sum;
+      pref *= x / (2.0 * l + 3.0);
+    }
+    return;
+  }
+  const double si0 = -expm1(-2.0 * x) / (2.0 * x);
+  const int mstart = 16 + (int)sqrt(50.0 * x + (double)L * L);
+  const double invx = 1.0 / x;
+  double f0 = 0.0, f1 = 1e-100, f = 0.0;
+  for (int q = mstart; q > L; --q) {
+    f = (2.0 * q + 3.0) * f1 * invx + f0;
+    f0 = f1;
+    f1 = f;
+    if (f > 1e150) {
+      f0 *= 1e-150;
+      f1 *= 1e-150;
+    }
+  }
+  for (int q = L; q >= 0; --q) {
+    f = (2.0 * q + 3.0) * f1 * invx + f0;
+    out[(size_t)q * ls] = f;
+    f0 = f1;
+    f1 = f;
+  }
+  const double cs = g * si0 / f;
+  for (int q = 0; q <= L; ++q) out[(size_t)q * ls] *= cs;
+}
+
 __global__ void sph_bessel_kernel(const double* __restrict__ RA, const double* __restrict__ RB,
                                   const int* __restrict__ gid, int natoms, int L, double sigma,
                                   size_t npairs, double* __restrict__ Bes) {
@@ -155,51 +204,7 @@ __global__ void sph_bessel_kernel(const double* __restrict__ RA, const double* _
       for (int l = 0; l <= L; ++l) out[(size_t)l * NN] = 0.0;
       continue;
     }
-    const double ra = RA[p * natoms + j], rb = RB[p * natoms + k];
-    const double x = ra * rb * inv2s2;
-    const double dr = ra - rb;
-    const double g = fact * exp(-0.5 * dr * dr * inv2s2);
-    if (!(x >= 1e-100)) {  // also catches NaN
-      out[0] = (x == x) ? g : x;
-      for (int l = 1; l <= L; ++l) out[(size_t)l * NN] = (x == x) ? 0.0 : x;
-      continue;
-    }
-    if (x < 1.0) {
-      // i_l(x) = x^l/(2l+1)!! sum_q (x^2/2)^q / (q! (2l+3)(2l+5)...(2l+2q+1))
-      const double emx = exp(-x), h = 0.5 * x * x;
-      double pref = emx;  // e^{-x} x^l/(2l+1)!!
-      for (int l = 0; l <= L; ++l) {
-        double term = 1.0, sum = 1.0;
-        for (int q = 1; q <= 14; ++q) {
-          term *= h / ((double)q * (2.0 * l + 2.0 * q + 1.0));
-          sum += term;
-        }
-        out[(size_t)l * NN] = g * pref * sum;
-        pref *= x / (2.0 * l + 3.0);
-      }
-      continue;
-    }
-    const double si0 = -expm1(-2.0 * x) / (2.0 * x);
-    const int mstart = 16 + (int)sqrt(50.0 * x + (double)L * L);
-    const double invx = 1.0 / x;
-    double f0 = 0.0, f1 = 1e-100, f = 0.0;
-    for (int q = mstart; q > L; --q) {
-      f = (2.0 * q + 3.0) * f1 * invx + f0;
-      f0 = f1;
-      f1 = f;
-      if (f > 1e150) {
-        f0 *= 1e-150;
-        f1 *= 1e-150;
-      }
-    }
-    for (int q = L; q >= 0; --q) {
-      f = (2.0 * q + 3.0) * f1 * invx + f0;
-      out[(size_t)q * NN] = f;
-      f0 = f1;
-      f1 = f;
-    }
-    const double cs = g * si0 / f;
-    for (int q = 0; q <= L; ++q) out[(size_t)q * NN] *= cs;
+    bessel_levels(RA[p * natoms + j], RB[p * natoms + k], L, fact, inv2s2, out, NN);
   }
 }
 
@@ -576,6 +581,305 @@ sph_direct_mma_kernel(const double2* __restrict__ YA, const double2* __restrict_
 size_t direct_mma_smem(int64_t natoms, int L) {
   const int N8 = (int)((natoms + 7) & ~7);
   return ((size_t)3 * N8 * fo_ld8((2 * (L + 1) + 7) & ~7) + (size_t)N8 * fo_ld8(N8)) * 8;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a for small clusters, streaming form (sph_direct2_kernel; the pairs API of the flagship configuration).
+// sph_direct_mma_kernel spends 97 % of its instructions on moving operands (one CTA per (pair, l): 16-byte
+// cp.async with an integer division each, zero fill, two CTA barriers, T through shared memory, two shared loads
+// per DMMA).  Here the PRODUCERS write the operands as the shared-memory images the DMMA fragments want:
+//   Ysw [structure][l][row 0..N8)[8 nrt(l) doubles]   Y_l: row = atom, column r = 2 m + (re | im), zero padded to
+//                                                     whole 8 x 8 tiles (sph_prep2_kernel)
+//   Bsw [pair][l][row j 0..N8)[N8 doubles]            B_l[j][k], zero padded (sph_bessel2_kernel)
+// with the 8-column groups of a row xor-swizzled by the row (d2_pos) so that the four k rows of any fragment
+// fall into disjoint bank groups at pitch 8 ntiles (no padding columns), and the rows of the second structure
+// permuted within groups of eight (d2_rowperm) for the chained second product.  A persistent CTA then streams
+// (pair, l) items through a ring of shared-memory slots: one elected thread fetches the three operands of an item
+// with three bulk copies (cp.async.bulk, 2.5 - 12.8 KB each) completing on the slot's mbarrier, four consumer
+// warps take the item's row tiles:
+//   T[r][k]   = sum_j YA[j][r] B_l[j][k]     50 DMMA per row tile (N = 38), one A fragment per five B fragments;
+//   C2[r][r'] = sum_k T[r][k] YB[k][r']      the C fragments of T ARE the A fragments of this product when a k-step is
+//                                            taken as the columns {2 t + h} of a tile (t = lane & 3, h = 0 | 1): T never
+//                                            leaves the registers, YB's rows are stored in that order;
+// and I[l, +-m1, m2] is formed in the C fragments as in sph_direct_mma_kernel.  No CTA barrier, no generic-proxy
+// store to shared memory, 1.1 shared loads per DMMA.
+// ------------------------------------------------------------------------------------------
+constexpr int D2_CONS = 4;                       // consumer warps
+constexpr int D2_THREADS = (D2_CONS + 1) * 32;   // + the producer warp
+constexpr int D2_MAXL = 64;
+
+__host__ __device__ __forceinline__ int d2_sw(int ntiles, int p) {
+  const int m = ntiles & 3;
+  return m == 0 ? (p & 3) : (m == 2 ? ((p >> 1) & 1) : 0);
+}
+// element (row p, column c) of a block with ntiles 8-column groups per row
+__host__ __device__ __forceinline__ int d2_pos(int ntiles, int p, int c) {
+  return p * 8 * ntiles + (((c >> 3) ^ d2_sw(ntiles, p)) << 3) + (c & 7);
+}
+// row of atom k in the second structure's blocks: the k-step (tile ct, h) of the chained product has lane t at
+// column 8 ct + 2 t + h of T, i.e. at row 8 ct + 4 h + t here
+__host__ __device__ __forceinline__ int d2_rowperm(int k) { return (k & ~7) | ((k & 1) << 2) | ((k & 7) >> 1); }
+
+struct D2Layout {
+  int natoms, N8, NCT, L, CW;  // CW = 4 nrt(L): complex columns per row
+  int ysz, bsz, ymax, slot;    // doubles: per structure, per (pair, l) of B, largest Y_l block, ring slot
+  int nrt[D2_MAXL], yoff[D2_MAXL];
+  D2Layout() {}
+  D2Layout(int natoms_, int L_) {
+    natoms = natoms_;
+    L = L_;
+    N8 = (natoms + 7) & ~7;
+    NCT = N8 >> 3;
+    int off = 0;
+    for (int l = 0; l <= L && l < D2_MAXL; ++l) {
+      nrt[l] = (2 * (l + 1) + 7) >> 3;
+      yoff[l] = off;
+      off += N8 * 8 * nrt[l];
+    }
+    ysz = off;
+    bsz = N8 * N8;
+    ymax = N8 * 8 * nrt[L < D2_MAXL ? L : D2_MAXL - 1];
+    CW = 4 * nrt[L < D2_MAXL ? L : D2_MAXL - 1];
+    slot = 2 * ymax + bsz;
+  }
+};
+
+// K1 in the operand layout: one thread per (structure, row, complex column); rows >= natoms and the columns
+// beyond m = l of a level are the zero padding.
+template <bool BSIDE>
+__global__ void __launch_bounds__(128)
+sph_prep2_kernel(const double* __restrict__ pos, const __grid_constant__ D2Layout Y, size_t nstruct,
+                 double* __restrict__ Ysw, double* __restrict__ R, int* status) {
+  extern __shared__ double sm_prep[];
+  const int L = Y.L, NLM = nlm_of(L), natoms = Y.natoms;
+  double* ca = sm_prep;    // [NLM]
+  double* cb = ca + NLM;   // [NLM]
+  double* cmm = cb + NLM;  // [L + 1]
+  for (int e = threadIdx.x; e < NLM; e += blockDim.x) {
+    int l = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while ((l + 1) * (l + 2) / 2 <= e) ++l;
+    while (l * (l + 1) / 2 > e) --l;
+    const int m = e - l * (l + 1) / 2;
+    double a = 0.0, b = 0.0;
+    if (l >= m + 2) {
+      a = sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
+      b = sqrt((((double)(l - 1) * (l - 1)) - (double)m * m) / (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
+    }
+    ca[e] = a;
+    cb[e] = b;
+  }
+  if (threadIdx.x == 0) {
+    double c = 0.28209479177387814347403972578039;  // sqrt(1/(4 pi))
+    cmm[0] = c;
+    for (int q = 1; q <= L; ++q) {
+      c *= -sqrt((2.0 * q + 1.0) / (2.0 * q));
+      cmm[q] = c;
+    }
+  }
+  __syncthreads();
+  const size_t total = nstruct * (size_t)Y.N8 * Y.CW;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(t % Y.CW);
+    const size_t sr = t / Y.CW;
+    const int atom = (int)(sr % Y.N8);
+    const size_t st_ = sr / Y.N8;
+    const int rp = BSIDE ? d2_rowperm(atom) : atom;
+    double* out = Ysw + st_ * (size_t)Y.ysz;
+    const bool real = atom < natoms && m <= L;
+    double ct = 1.0, cm = 1.0, sm = 0.0, pmm = 0.0;
+    if (real) {
+      const size_t sa = st_ * natoms + atom;
+      const double x = pos[sa * 3 + 0], y = pos[sa * 3 + 1], z = pos[sa * 3 + 2];
+      const double r = sqrt(x * x + y * y + z * z);
+      const bool fin = isfinite(r);
+      double st = 0.0, cph = 1.0, sph = 0.0;
+      if (r > 0.0 && fin) {
+        ct = z / r;
+        const double rho = sqrt(x * x + y * y);
+        st = rho / r;
+        if (rho > 0.0) {
+          cph = x / rho;
+          sph = y / rho;
+        }
+      }
+      if (m == 0) {
+        R[sa] = r;
+        if (status) {
+          if (!fin) atomicOr(&status[st_], FO_STATUS_NONFINITE);
+          if (r == 0.0) atomicOr(&status[st_], FO_STATUS_ATOM_AT_ORIGIN);
+        }
+      }
+      // exp(i m phi) = (cos phi + i sin phi)^m and sin^m(theta) by m multiplications
+      double stm = 1.0;
+      for (int q = 0; q < m; ++q) {
+        const double c2 = cm * cph - sm * sph;
+        sm = sm * cph + cm * sph;
+        cm = c2;
+        stm *= st;
+      }
+      pmm = cmm[m] * stm;
+    }
+    double pl2 = 0.0, pl1 = 0.0;
+    for (int l = 0; l <= L; ++l) {
+      const int nt = Y.nrt[l];
+      if (m >= 4 * nt) continue;  // no such column at this level
+      double2 v = make_double2(0.0, 0.0);
+      if (real && l >= m) {
+        double pv;
+        if (l == m)
+          pv = pmm;
+        else if (l == m + 1)
+          pv = sqrt(2.0 * m + 3.0) * ct * pmm;
+        else {
+          const int lm = l * (l + 1) / 2 + m;
+          pv = ca[lm] * (ct * pl1 - cb[lm] * pl2);
+        }
+        pl2 = pl1;
+        pl1 = pv;
+        v = make_double2(pv * cm, pv * sm);
+      }
+      *reinterpret_cast<double2*>(out + Y.yoff[l] + d2_pos(nt, rp, 2 * m)) = v;
+    }
+  }
+}
+
+// K2a part 1 in the operand layout: one thread per (pair, row j, column k) of the padded matrix
+__global__ void sph_bessel2_kernel(const double* __restrict__ RA, const double* __restrict__ RB,
+                                   const int* __restrict__ gid, const __grid_constant__ D2Layout Y, double sigma,
+                                   size_t npairs, double* __restrict__ Bsw) {
+  const int natoms = Y.natoms, L = Y.L;
+  const size_t NN = (size_t)Y.bsz;
+  const size_t total = npairs * NN;
+  const double fact = 4.0 * pow(kPi, 2.5) * sigma * sigma * sigma;
+  const double inv2s2 = 0.5 / (sigma * sigma);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = t / NN;
+    const int jk = (int)(t - p * NN);
+    const int j = jk / Y.N8, k = jk - j * Y.N8;
+    double* out = Bsw + p * (size_t)(L + 1) * NN + d2_pos(Y.NCT, j, k);
+    if (j >= natoms || k >= natoms || gid[j] != gid[k]) {
+      for (int l = 0; l <= L; ++l) out[(size_t)l * NN] = 0.0;
+      continue;
+    }
+    bessel_levels(RA[p * natoms + j], RB[p * natoms + k], L, fact, inv2s2, out, NN);
+  }
+}
+
+template <int NCT>
+__global__ void __launch_bounds__(D2_THREADS)
+sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB, const double* __restrict__ Bsw,
+                   const __grid_constant__ D2Layout Y, int nslots, size_t npairs, double2* __restrict__ Ihalf) {
+  extern __shared__ __align__(128) double smq[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smq);  // [8]
+  uint64_t* empty = full + 8;                         // [8]
+  double* slots = smq + 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = Y.L, L1 = L + 1, W = 2 * L + 1, N8 = 8 * NCT;
+  if (tid == 0) {
+    for (int s_ = 0; s_ < nslots; ++s_) {
+      fo_mbar_init(full + s_, 1);
+      fo_mbar_init(empty + s_, D2_CONS);
+    }
+    fo_mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == D2_CONS) {  // producer: one thread feeds the ring
+    if (lane == 0) {
+      unsigned it = 0;
+      const unsigned bytesB = (unsigned)Y.bsz * 8;
+      for (size_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+        for (int l = L; l >= 0; --l, ++it) {
+          const int sl = (int)(it % (unsigned)nslots);
+          const unsigned use = it / (unsigned)nslots;
+          if (use > 0) fo_mbar_wait(empty + sl, (int)((use - 1) & 1));
+          const unsigned bytesY = (unsigned)(N8 * 8 * Y.nrt[l]) * 8;
+          fo_mbar_arrive_expect_tx(full + sl, 2 * bytesY + bytesB);
+          double* dst = slots + (size_t)sl * Y.slot;
+          fo_bulk_g2s(dst, YA + pair * (size_t)Y.ysz + Y.yoff[l], bytesY, full + sl);
+          fo_bulk_g2s(dst + Y.ymax, YB + pair * (size_t)Y.ysz + Y.yoff[l], bytesY, full + sl);
+          fo_bulk_g2s(dst + 2 * Y.ymax, Bsw + (pair * L1 + l) * (size_t)Y.bsz, bytesB, full + sl);
+        }
+    }
+    return;
+  }
+  const int g = lane >> 2, t4 = lane & 3;
+  const int swB = d2_sw(NCT, t4);  // (4 ks + t4) & 3 == t4 and ((4 ks + t4) >> 1) & 1 == (t4 >> 1) & 1
+  unsigned it = 0;
+  for (size_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    double2* out = Ihalf + pair * (size_t)L1 * W * L1;
+    for (int l = L; l >= 0; --l, ++it) {
+      const int sl = (int)(it % (unsigned)nslots);
+      const unsigned use = it / (unsigned)nslots;
+      fo_mbar_wait(full + sl, (int)(use & 1));
+      const double* A1 = slots + (size_t)sl * Y.slot;
+      const double* B2 = A1 + Y.ymax;
+      const double* B1 = B2 + Y.ymax;
+      const int nrt = Y.nrt[l], R8 = 8 * nrt;
+      const int swY = d2_sw(nrt, t4);
+      // the row tiles of an item go to the warps in an order rotated by the item: every warp gets a quarter of
+      // the row tiles of a pair (L = 15: 10 of 40)
+      for (int rt1 = (warp - (int)it) & 3; rt1 < nrt; rt1 += D2_CONS) {
+        double c1[NCT][2];
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct) c1[ct][0] = c1[ct][1] = 0.0;
+        {
+          const double* a = A1 + t4 * R8 + ((rt1 ^ swY) << 3) + g;
+          const double* b = B1 + t4 * N8 + g;
+#pragma unroll 2
+          for (int ks = 0; ks < 2 * NCT; ++ks) {
+            const double av = a[ks * 4 * R8];
+#pragma unroll
+            for (int ct = 0; ct < NCT; ++ct) fo_dmma(c1[ct], av, b[ks * 4 * N8 + ((ct ^ swB) << 3)]);
+          }
+        }
+        for (int rb = 0; rb < nrt; rb += 4) {
+          double c2[4][2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c2[q][0] = c2[q][1] = 0.0;
+#pragma unroll
+          for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double* b = B2 + (8 * ct + 4 * h + t4) * R8 + g;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (rb + q < nrt) fo_dmma(c2[q], c1[ct][h], b[((rb + q) ^ swY) << 3]);
+            }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (rb + q >= nrt) break;  // warp-uniform
+            // this lane: row r1 = 8 rt1 + g (m1 = r1 / 2, part g & 1), columns (re, im) of m2 = 4 rt2 + t4
+            const double px0 = __shfl_xor_sync(0xffffffffu, c2[q][0], 4);
+            const double px1 = __shfl_xor_sync(0xffffffffu, c2[q][1], 4);
+            const int m1 = (rt1 * 8 + g) >> 1, m2 = (rb + q) * 4 + t4;
+            if (m1 > l || m2 > l) continue;
+            if ((g & 1) == 0) {  // rr, ri here; ir, ii in the partner: I(+m1, m2)
+              out[((size_t)m2 * W + (L + m1)) * L1 + l] = make_double2(c2[q][0] + px1, px0 - c2[q][1]);
+            } else if (m1 > 0) {  // ir, ii here; rr, ri in the partner: I(-m1, m2) = (-1)^m1 (rr - ii, -ir - ri)
+              const double sg = (m1 & 1) ? -1.0 : 1.0;
+              out[((size_t)m2 * W + (L - m1)) * L1 + l] = make_double2(sg * (px0 - c2[q][1]), sg * (-c2[q][0] - px1));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) fo_mbar_arrive(empty + sl);
+    }
+  }
+}
+
+// ring slots of sph_direct2_kernel that fit two CTAs per SM (0: the kernel does not apply)
+int direct2_slots(const fo_ctx* ctx, int64_t natoms, int L) {
+  if (ctx->force_generic || ctx->opt("sph_direct_ring") < 0 || natoms >= ctx->direct_gemm_min || natoms > 64 ||
+      L >= D2_MAXL)
+    return 0;
+  const D2Layout Y((int)natoms, L);
+  const size_t budget = 108 * 1024 - 128;
+  int n = (int)(budget / ((size_t)Y.slot * 8));
+  if (const int64_t o = ctx->opt("sph_direct_ring")) n = std::min<int>(n, (int)o);
+  return n >= 2 ? std::min(n, 8) : 0;
 }
 
 // The (m2, m1, l < max(|m1|, m2)) entries are never read; no need to clear Ihalf.
@@ -2938,6 +3242,40 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
                double sigma, const int* d_gid, double2* d_Ihalf, int* d_status, char* work) {
   if (np == 0) return FO_OK;
   const int NLM = nlm_of(L);
+  if (const int nslots = direct2_slots(ctx, natoms, L)) {
+    // streaming form: operands in the fragment layouts (work: YswA | YswB | RA | RB | Bsw)
+    const D2Layout Y((int)natoms, L);
+    double* YswA = (double*)work;
+    double* YswB = YswA + (size_t)np * Y.ysz;
+    double* RA = YswB + (size_t)np * Y.ysz;
+    double* RB = RA + (size_t)np * natoms;
+    double* Bsw = RB + (size_t)np * natoms;
+    fo_prof_scope prof(ctx, FO_PROF_SPH_COEF);
+    const size_t tot = (size_t)np * Y.N8 * Y.CW;
+    const size_t smem_prep = ((size_t)2 * NLM + L + 1) * 8;
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+    sph_prep2_kernel<false><<<grid_for(tot, 128, 148 * 16), 128, smem_prep, ctx->stream>>>(d_posA, Y, (size_t)np, YswA, RA, d_status);
+    FO_LAUNCH_CHECK(ctx);
+    sph_prep2_kernel<true><<<grid_for(tot, 128, 148 * 16), 128, smem_prep, ctx->stream>>>(d_posB, Y, (size_t)np, YswB, RB, d_status);
+    FO_LAUNCH_CHECK(ctx);
+    sph_bessel2_kernel<<<grid_for((size_t)np * Y.bsz, 128), 128, 0, ctx->stream>>>(RA, RB, d_gid, Y, sigma, (size_t)np, Bsw);
+    FO_LAUNCH_CHECK(ctx);
+    const size_t smem = 128 + (size_t)nslots * Y.slot * 8;
+    const int blocks = (int)std::min<int64_t>(np, 2 * (int64_t)ctx->prop.multiProcessorCount);
+#define FO_D2_CASE(N_)                                                                                              \
+  case N_:                                                                                                          \
+    FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct2_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sph_direct2_kernel<N_><<<blocks, D2_THREADS, smem, ctx->stream>>>(YswA, YswB, Bsw, Y, nslots, (size_t)np, d_Ihalf); \
+    break;
+    switch (Y.NCT) {
+      FO_D2_CASE(1) FO_D2_CASE(2) FO_D2_CASE(3) FO_D2_CASE(4) FO_D2_CASE(5) FO_D2_CASE(6) FO_D2_CASE(7) FO_D2_CASE(8)
+      default: return fo_fail(ctx, FO_ERR_UNSUPPORTED, "sph_direct2: %d atoms", (int)natoms);
+    }
+#undef FO_D2_CASE
+    FO_LAUNCH_CHECK(ctx);
+    return FO_OK;
+  }
   // work: YA | YB | RA | RB | Bes
   double2* YA = (double2*)work;
   double2* YB = YA + (size_t)np * natoms * NLM;
@@ -2991,6 +3329,10 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
 size_t direct_work_bytes(const fo_ctx* ctx, int64_t np, int64_t natoms, int L) {
   const size_t NLM = nlm_of(L);
   // YA, YB | RA, RB | Bes | T, C2 (GEMM path for large clusters only)
+  if (direct2_slots(ctx, natoms, L)) {
+    const D2Layout Y((int)natoms, L);
+    return (size_t)np * Y.ysz * 16 + (size_t)np * natoms * 16 + (size_t)np * (L + 1) * Y.bsz * 8 + 256;
+  }
   size_t b = (size_t)np * natoms * NLM * 32 + (size_t)np * natoms * 16 +
              (size_t)np * (L + 1) * natoms * natoms * 8 + 256;
   if (natoms >= ctx->direct_gemm_min)
