@@ -35,6 +35,7 @@
 namespace {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kPi25 = 17.49341832762486284626282167987155377876;  // pi^2.5 (pow() in a kernel is ~150 instructions per thread)
 
 __host__ __device__ __forceinline__ int nlm_of(int L) { return (L + 1) * (L + 2) / 2; }
 
@@ -167,24 +168,49 @@ __device__ __forceinline__ void bessel_levels(double ra, double rb, int L, doubl
   const double si0 = -expm1(-2.0 * x) / (2.0 * x);
   const int mstart = 16 + (int)sqrt(50.0 * x + (double)L * L);
   const double invx = 1.0 / x;
+  // Miller: f_{q} = (2 q + 3) f_{q+1} / x + f_{q+2} downwards from an arbitrary small start; the values are the
+  // recurrence's times i_0(x) / f_0.  First pass: down to q = 0 keeping only the state at q = L + 1; second pass:
+  // the L + 1 wanted levels again, already scaled (16 more FMAs instead of a read-modify-write of the output).
+  // The rescaling test runs every fourth step: a step grows f by less than (2 q + 3) / x + 1 < 300, so four
+  // steps after 1e150 stay far below the overflow threshold.
   double f0 = 0.0, f1 = 1e-100, f = 0.0;
-  for (int q = mstart; q > L; --q) {
-    f = (2.0 * q + 3.0) * f1 * invx + f0;
-    f0 = f1;
-    f1 = f;
+  int q = mstart;
+  for (; q > L + 3; q -= 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      f = (2.0 * (q - u) + 3.0) * f1 * invx + f0;
+      f0 = f1;
+      f1 = f;
+    }
     if (f > 1e150) {
       f0 *= 1e-150;
       f1 *= 1e-150;
     }
   }
-  for (int q = L; q >= 0; --q) {
+  for (; q > L; --q) {
+    f = (2.0 * q + 3.0) * f1 * invx + f0;
+    f0 = f1;
+    f1 = f;
+  }
+  if (f1 > 1e150) {
+    f0 *= 1e-150;
+    f1 *= 1e-150;
+  }
+  const double s0 = f0, s1 = f1;  // f_{L+2}, f_{L+1}
+  for (q = L; q >= 0; --q) {
+    f = (2.0 * q + 3.0) * f1 * invx + f0;
+    f0 = f1;
+    f1 = f;
+  }
+  const double cs = g * si0 / f;
+  f0 = s0 * cs;
+  f1 = s1 * cs;
+  for (q = L; q >= 0; --q) {
     f = (2.0 * q + 3.0) * f1 * invx + f0;
     out[(size_t)q * ls] = f;
     f0 = f1;
     f1 = f;
   }
-  const double cs = g * si0 / f;
-  for (int q = 0; q <= L; ++q) out[(size_t)q * ls] *= cs;
 }
 
 __global__ void sph_bessel_kernel(const double* __restrict__ RA, const double* __restrict__ RB,
@@ -192,7 +218,7 @@ __global__ void sph_bessel_kernel(const double* __restrict__ RA, const double* _
                                   size_t npairs, double* __restrict__ Bes) {
   const size_t NN = (size_t)natoms * natoms;
   const size_t total = npairs * NN;
-  const double fact = 4.0 * pow(kPi, 2.5) * sigma * sigma * sigma;
+  const double fact = 4.0 * kPi25 * sigma * sigma * sigma;
   const double inv2s2 = 0.5 / (sigma * sigma);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
@@ -751,7 +777,7 @@ __global__ void sph_bessel2_kernel(const double* __restrict__ RA, const double* 
   const int natoms = Y.natoms, L = Y.L;
   const size_t NN = (size_t)Y.bsz;
   const size_t total = npairs * NN;
-  const double fact = 4.0 * pow(kPi, 2.5) * sigma * sigma * sigma;
+  const double fact = 4.0 * kPi25 * sigma * sigma * sigma;
   const double inv2s2 = 0.5 / (sigma * sigma);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
@@ -870,7 +896,8 @@ sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB,
   }
 }
 
-// ring slots of sph_direct2_kernel that fit two CTAs per SM (0: the kernel does not apply)
+// ring slots of sph_direct2_kernel that fit two CTAs per SM (0: the kernel does not apply); option
+// sph_direct_ring: -1 = sph_direct_mma_kernel instead, n > 0 = at most n slots (fewer slots, more CTAs per SM)
 int direct2_slots(const fo_ctx* ctx, int64_t natoms, int L) {
   if (ctx->force_generic || ctx->opt("sph_direct_ring") < 0 || natoms >= ctx->direct_gemm_min || natoms > 64 ||
       L >= D2_MAXL)
@@ -881,6 +908,7 @@ int direct2_slots(const fo_ctx* ctx, int64_t natoms, int L) {
   if (const int64_t o = ctx->opt("sph_direct_ring")) n = std::min<int>(n, (int)o);
   return n >= 2 ? std::min(n, 8) : 0;
 }
+size_t direct2_smem(const D2Layout& Y, int nslots) { return 128 + (size_t)nslots * Y.slot * 8; }
 
 // The (m2, m1, l < max(|m1|, m2)) entries are never read; no need to clear Ihalf.
 
@@ -2426,6 +2454,351 @@ sph_isoft4_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I4
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// sph_isoft5_kernel<WANT_GRID> (Jmax = 15: F = 32): the two inverse transforms of a beta plane as radix FFTs on
+// the FP64 vector pipe instead of DFT matrices on the tensor pipe.  On B200 the two pipes have the same FP64 peak
+// (DFMA 34 TFLOP/s, DMMA.8x8x4 37 TFLOP/s, bench.py `fp64_peaks`) and share the same units; a 32-point FFT needs a
+// tenth of the operations of the 32 x 31 DFT product, so the transform that takes 1280 DMMA (41 k cycles of the
+// pipe per pair and SM for all 16 plane quartets) becomes ~123 FP64 instructions per thread and transform step.
+// Same frame as sph_isoft4_kernel<4, ...>: persistent CTA of 512 threads per (chunk of four planes), Wigner slice
+// resident, coefficients by bulk copy, phase 1 = K5 (one lane per (a, m2, level parity) carrying four planes),
+// which here stores S(+a, m2) and S(-a, m2) themselves: block (kk, o) = [row m1 mod 32][m2 = 0..15] complex.
+//   step A  per column m2:  V[al][m2] = sum_m1 S(m1, m2) e^{+2 pi i m1 al / 32}, in place;
+//   step B  per pair of rows (al, al + 16):  Z(m2) = Vh_al(m2) + i Vh_al'(m2) over m2 = -15 .. 15 with
+//           Vh(-m2) = conj V(m2); one complex transform yields g(al, .) in its real and g(al', .) in its
+//           imaginary parts (the grid is real);
+// each 32-point transform by FOUR lanes: lane n1 takes the inputs 4 n2 + n1, an 8-point DFT in registers, the
+// twiddles e^{2 pi i n1 k2 / 32}, a 4 x 8 -> 8 x 4 exchange by two rounds of xor shuffles, two 4-point DFTs: lane t
+// ends with the outputs k2 + 8 k1, k2 = 2 t, 2 t + 1.  All 512 threads have a task in both steps (8 blocks x 16
+// transforms x 4 lanes); one CTA barrier between K5, step A and step B.  The arg-max runs on integer keys.
+// ------------------------------------------------------------------------------------------
+struct I5Layout {
+  int SP, sblk, o5_s, o5_red, total5;
+  I5Layout() {}
+  I5Layout(const I2Layout& Y) {
+    SP = 36;  // doubles per row: 16-byte accesses of the four lanes of a transform (rows n1 apart) and of two
+              // neighbouring columns fall into eight distinct 16-byte bank groups
+    sblk = 32 * SP;
+    o5_s = Y.o3_br;
+    o5_red = (o5_s + 2 * Y.KC * sblk + 1) & ~1;
+    total5 = o5_red + 96;
+  }
+};
+
+__device__ __forceinline__ double2 fo_cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 fo_csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 fo_cmul(double2 a, double2 t) {
+  return make_double2(fma(a.x, t.x, -a.y * t.y), fma(a.x, t.y, a.y * t.x));
+}
+__device__ __forceinline__ double2 fo_csel(bool c, double2 a, double2 b) { return make_double2(c ? a.x : b.x, c ? a.y : b.y); }
+__device__ __forceinline__ double2 fo_cshx(double2 v, int m) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+// X[k] = sum_n x[n] i^{n k} (sign +), in place
+__device__ __forceinline__ void fo_fft4(double2& a, double2& b, double2& c, double2& d) {
+  const double2 s0 = fo_cadd(a, c), d0 = fo_csub(a, c), s1 = fo_cadd(b, d), d1 = fo_csub(b, d);
+  a = fo_cadd(s0, s1);
+  c = fo_csub(s0, s1);
+  b = make_double2(d0.x - d1.y, d0.y + d1.x);
+  d = make_double2(d0.x + d1.y, d0.y - d1.x);
+}
+// y[k] = sum_n x[n] e^{+2 pi i n k / 8}, in place
+__device__ __forceinline__ void fo_fft8(double2 (&x)[8]) {
+  fo_fft4(x[0], x[2], x[4], x[6]);  // E[0..3] in x[0], x[2], x[4], x[6]
+  fo_fft4(x[1], x[3], x[5], x[7]);  // O[0..3] in x[1], x[3], x[5], x[7]
+  const double r = 0.70710678118654752440084436210485;
+  const double2 e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
+  const double2 o0 = x[1];
+  const double2 o1 = make_double2((x[3].x - x[3].y) * r, (x[3].x + x[3].y) * r);    // (1 + i) / sqrt 2
+  const double2 o2 = make_double2(-x[5].y, x[5].x);                                 // i
+  const double2 o3 = make_double2((-x[7].x - x[7].y) * r, (x[7].x - x[7].y) * r);   // (-1 + i) / sqrt 2
+  x[0] = fo_cadd(e0, o0);
+  x[4] = fo_csub(e0, o0);
+  x[1] = fo_cadd(e1, o1);
+  x[5] = fo_csub(e1, o1);
+  x[2] = fo_cadd(e2, o2);
+  x[6] = fo_csub(e2, o2);
+  x[3] = fo_cadd(e3, o3);
+  x[7] = fo_csub(e3, o3);
+}
+// The second half of a 32-point transform spread over the four lanes n1 = lane & 3: y[k2] (8-point DFT of the
+// inputs 4 n2 + n1) -> out[j][k1] = X[(2 t + j) + 8 k1], t = this lane's n1.
+__device__ __forceinline__ void fo_fft32_finish(double2 (&y)[8], const double2 (&tw)[8], bool b0, bool b1,
+                                                double2 (&out)[2][4]) {
+#pragma unroll
+  for (int k = 1; k < 8; ++k) y[k] = fo_cmul(y[k], tw[k]);
+  // round 1 (xor 2): keep the half k2 = 4 b1 + j, get the same half of lane n1 ^ 2
+  double2 K[4], R[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double2 send = fo_csel(b1, y[j], y[j + 4]);
+    K[j] = fo_csel(b1, y[j + 4], y[j]);
+    R[j] = fo_cshx(send, 2);
+  }
+  // round 2 (xor 1): keep k2 = 4 b1 + 2 b0 + jj; sources: keepK = lane n1, recvK = n1 ^ 1, keepR = n1 ^ 2,
+  // recvR = n1 ^ 3
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const double2 c0 = fo_csel(b0, K[jj + 2], K[jj]);
+    const double2 c1 = fo_cshx(fo_csel(b0, K[jj], K[jj + 2]), 1);
+    const double2 c2 = fo_csel(b0, R[jj + 2], R[jj]);
+    const double2 c3 = fo_cshx(fo_csel(b0, R[jj], R[jj + 2]), 1);
+    // z[i] = c[i ^ n1]: the xor with bit 0 by selects; the xor with bit 1 (z2, z3 <-> z0, z1) only changes the sign of
+    // the odd outputs of the 4-point DFT
+    double2 z0 = fo_csel(b0, c1, c0), z1 = fo_csel(b0, c0, c1), z2 = fo_csel(b0, c3, c2), z3 = fo_csel(b0, c2, c3);
+    fo_fft4(z0, z1, z2, z3);
+    const double sg = b1 ? -1.0 : 1.0;
+    out[jj][0] = z0;
+    out[jj][1] = make_double2(sg * z1.x, sg * z1.y);
+    out[jj][2] = z2;
+    out[jj][3] = make_double2(sg * z3.x, sg * z3.y);
+  }
+}
+
+template <bool WANT_GRID>
+__global__ void __launch_bounds__(512, 1)
+sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5Layout Z,
+                  const double2* __restrict__ Ipk, const double* __restrict__ DtP, int npairs, int norient,
+                  Iso2Out out) {
+  extern __shared__ double smk[];
+  constexpr int KC = 4, NTHREADS = 512, NW = 16, F = 32;
+  const int L = Y.L, L1 = Y.L1, SP = Z.SP;
+  double* DtS = smk + Y.o_dts;
+  double2* IkS = reinterpret_cast<double2*>(smk + Y.o3_iks);
+  double* SB = smk + Z.o5_s;  // [kk][o] blocks
+  double* red = smk + Z.o5_red;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = blockIdx.x % Y.nchunk;
+  const int jstart = blockIdx.x / Y.nchunk, jstride = gridDim.x / Y.nchunk;
+  for (int e = tid; e < Y.dts; e += NTHREADS) DtS[e] = DtP[(size_t)chunk * Y.dts + e];
+  uint64_t* cbar = reinterpret_cast<uint64_t*>(red + 88);
+  const unsigned ipk_bytes = (unsigned)Y.ipk * 16u;
+  auto stage_coeffs = [&](int pr) {
+    if (tid == 0) {
+      fo_fence_proxy_async();
+      fo_mbar_arrive_expect_tx(cbar, ipk_bytes);
+      fo_bulk_g2s(IkS, Ipk + (size_t)pr * Y.ipk, ipk_bytes, cbar);
+    }
+  };
+  if (tid == 0) {
+    fo_mbar_init(cbar, 1);
+    fo_mbar_fence_init();
+  }
+  int cph = 0;
+  if (jstart < npairs) stage_coeffs(jstart);
+  // ---- K5 geometry (as sph_isoft4_kernel<4, ...>): task = (shell-ordered entry t = (a, m2), level parity)
+  int k5t = tid >> 1, k5s, k5a, k5m2;
+  {
+    k5s = (int)sqrtf((float)k5t);
+    while ((k5s + 1) * (k5s + 1) <= k5t) ++k5s;
+    while (k5s * k5s > k5t) --k5s;
+    const int q = k5t - k5s * k5s;
+    k5a = q <= k5s ? q : k5s;
+    k5m2 = q <= k5s ? k5s : q - k5s - 1;
+  }
+  const int k5par = tid & 1;
+  const bool k5on = k5t < L1 * L1;
+  const int k5l0 = k5on ? k5s + ((k5s ^ k5par) & 1) : L + 1;
+  // ---- transform geometry: block (kk, o) = tid >> 6, transform f = (tid >> 2) & 15, lane n1 = tid & 3
+  const int blk = tid >> 6, kk = blk >> 1, o = blk & 1;
+  const int f = (tid >> 2) & 15, n1 = tid & 3;
+  const bool b0 = n1 & 1, b1 = (n1 >> 1) & 1;
+  double2 tw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double sn, cs;
+    sincospi((double)(n1 * k) / 16.0, &sn, &cs);
+    tw[k] = make_double2(cs, sn);
+  }
+  double* S = SB + blk * Z.sblk;
+  const int plane = i2_plane(F, KC, chunk, kk);
+  // step B: rows al = (f with bits 0 and 1 swapped) and al + 16 -- two neighbouring transforms are two rows apart
+  const int alB = (f & ~3) | ((f & 1) << 1) | ((f >> 1) & 1);
+  const bool active = o < norient;
+  __syncthreads();  // the initialised mbarrier is visible to every waiter
+
+  // combine the 16 warp results of pair pr (buffer pb) and write the chunk's partial maximum
+  auto flush = [&](int pr, int pb) {
+    if (pr >= 0 && tid < norient) {
+      const double* rv = red + 16 * pb;
+      const int* ri = reinterpret_cast<const int*>(red + 48 + 8 * pb);
+      double bv = -1e300;
+      int bi = 0x7fffffff;
+      for (int w = 0; w < NW; ++w) {
+        if (((w >> 1) & 1) != tid) continue;
+        const double ov = rv[w];
+        const int oi = ri[w];
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      out.part_val[((size_t)pr * norient + tid) * Y.nchunk + chunk] = bv;
+      out.part_idx[((size_t)pr * norient + tid) * Y.nchunk + chunk] = bi;
+    }
+  };
+  int prev = -1, par = 0;
+  for (int pair = jstart; pair < npairs; pair += jstride) {
+    fo_mbar_wait(cbar, cph);  // this pair's coefficients have landed
+    cph ^= 1;
+    // ---- phase 1: K5 in registers -> S blocks
+    {
+      double2 Pp[KC], Mp[KC];
+#pragma unroll
+      for (int q = 0; q < KC; ++q) Pp[q] = Mp[q] = make_double2(0.0, 0.0);
+      for (int lv = k5l0; lv <= L; lv += 2) {
+        const int idx = Y.o_ent[lv] + k5t;
+        double dd[KC];
+#pragma unroll
+        for (int q = 0; q < KC; q += 2) {
+          const double2 d2 = *reinterpret_cast<const double2*>(DtS + idx * KC + q);
+          dd[q] = d2.x;
+          dd[q + 1] = d2.y;
+        }
+        const double2 cp = IkS[idx * 2], cm = IkS[idx * 2 + 1];
+#pragma unroll
+        for (int q = 0; q < KC; ++q) {
+          Pp[q].x = fma(dd[q], cp.x, Pp[q].x);
+          Pp[q].y = fma(dd[q], cp.y, Pp[q].y);
+          Mp[q].x = fma(dd[KC - 1 - q], cm.x, Mp[q].x);
+          Mp[q].y = fma(dd[KC - 1 - q], cm.y, Mp[q].y);
+        }
+      }
+      const double sm2q = (k5m2 & 1) ? -1.0 : 1.0;
+      double pe[KC], po[KC], me[KC], mo[KC];
+#pragma unroll
+      for (int q = 0; q < KC; ++q) {
+        const double sendP = k5par ? Pp[q].x : Pp[q].y, sendM = k5par ? Mp[q].x : Mp[q].y;
+        const double recvP = __shfl_xor_sync(0xffffffffu, sendP, 1);
+        const double recvM = __shfl_xor_sync(0xffffffffu, sendM, 1);
+        pe[q] = k5par ? recvP : Pp[q].x;
+        po[q] = k5par ? Pp[q].y : recvP;
+        me[q] = k5par ? recvM : Mp[q].x;
+        mo[q] = k5par ? Mp[q].y : recvM;
+      }
+      // the S blocks are free once every warp has finished step B of the previous pair (whose results are combined
+      // behind the same barrier); the sums above did not need them
+      __syncthreads();
+      flush(prev, par ^ 1);
+#pragma unroll
+      for (int q = 0; q < KC; ++q) {
+        if (k5on) {
+#pragma unroll
+          for (int oo = 0; oo < 2; ++oo) {
+            if (oo >= norient) break;
+            const double so = oo ? -1.0 : 1.0;
+            // S(+a) = sum_l so^l d I ; S(-a) = (-1)^m2 sum_l (-so)^l d_mirror I_-   (component k5par of each)
+            const double sp = fma(so, po[q], pe[q]), sn = sm2q * fma(-so, mo[q], me[q]);
+            double* bq = SB + (q * 2 + oo) * Z.sblk;
+            bq[k5a * SP + 2 * k5m2 + k5par] = sp;
+            if (k5a > 0) bq[(F - k5a) * SP + 2 * k5m2 + k5par] = sn;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during the transforms
+    // ---- step A: column m2 = f, in place (row 16 of the input is zero: |m1| <= 15)
+    if (active) {
+      double2 y[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) y[n2] = *reinterpret_cast<const double2*>(S + (4 * n2 + n1) * SP + 2 * f);
+      if (n1 == 0) y[4] = make_double2(0.0, 0.0);
+      fo_fft8(y);
+      double2 v[2][4];
+      fo_fft32_finish(y, tw, b0, b1, v);
+      // (every lane of the transform has loaded its inputs before any of them can have received all it stores)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1)
+          *reinterpret_cast<double2*>(S + (2 * n1 + jj + 8 * k1) * SP + 2 * f) = v[jj][k1];
+    }
+    // step B of a block needs step A of the same block only: the two warps of the block meet on a named barrier
+    asm volatile("bar.sync %0, 64;" ::"r"(blk + 1) : "memory");
+    // ---- step B: rows alB, alB + 16; arg-max on integer keys
+    long long bkey = fo_dkey(-1e300);
+    int bix = 0x7fffffff;
+    if (active) {
+      const double* ra = S + alB * SP;
+      const double* rb = ra + 16 * SP;
+      double2 y[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        const double2 va = *reinterpret_cast<const double2*>(ra + 2 * (4 * n2 + n1));
+        const double2 vb = *reinterpret_cast<const double2*>(rb + 2 * (4 * n2 + n1));
+        y[n2] = make_double2(va.x - vb.y, va.y + vb.x);  // V_al + i V_al'
+      }
+#pragma unroll
+      for (int n2 = 4; n2 < 8; ++n2) {
+        const int mneg = 32 - (4 * n2 + n1);  // 1 .. 16
+        const double2 va = *reinterpret_cast<const double2*>(ra + 2 * (mneg & 15));
+        const double2 vb = *reinterpret_cast<const double2*>(rb + 2 * (mneg & 15));
+        y[n2] = make_double2(va.x + vb.y, vb.x - va.y);  // conj V_al + i conj V_al'
+      }
+      if (n1 == 0) y[4] = make_double2(0.0, 0.0);  // m2 = 16
+      fo_fft8(y);
+      double2 v[2][4];
+      fo_fft32_finish(y, tw, b0, b1, v);
+      // v[jj][k1] = g(alB, d) + i g(alB + 16, d), d = 2 n1 + jj + 8 k1
+      if (WANT_GRID) {
+        double* g0 = out.grid + (((size_t)pair * norient + o) * F * F * F + (size_t)(alB * F + plane) * F);
+        double* g1 = g0 + (size_t)16 * F * F;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int k1 = 0; k1 < 4; ++k1) {
+            g0[2 * n1 + jj + 8 * k1] = v[jj][k1].x;
+            g1[2 * n1 + jj + 8 * k1] = v[jj][k1].y;
+          }
+      }
+      // thread maximum in index order (row alB before row alB + 16, d increasing): a strict > keeps the smallest
+      // index of equal values
+      double bv = v[0][0].x;
+      int bd = 2 * n1;
+#pragma unroll
+      for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          if ((k1 | jj) && v[jj][k1].x > bv) {
+            bv = v[jj][k1].x;
+            bd = 2 * n1 + jj + 8 * k1;
+          }
+#pragma unroll
+      for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          if (v[jj][k1].y > bv) {
+            bv = v[jj][k1].y;
+            bd = 2 * n1 + jj + 8 * k1 + 16 * F * F;
+          }
+      bkey = fo_dkey(bv);
+      bix = (alB * F + plane) * F + bd;
+    }
+    // ---- reduction: a warp belongs to one orientation (o = (warp >> 1) & 1)
+    double* redv = red + 16 * par;
+    int* redi = reinterpret_cast<int*>(red + 48 + 8 * par);
+    {
+      const int hi = (int)(bkey >> 32);
+      const int mhi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned lo = hi == mhi ? (unsigned)bkey : 0u;
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+      const bool top = hi == mhi && (unsigned)bkey == mlo;
+      const int imin = __reduce_min_sync(0xffffffffu, top ? bix : 0x7fffffff);
+      if (lane == 0) {
+        redv[warp] = fo_dunkey(((long long)mhi << 32) | (long long)mlo);
+        redi[warp] = imin;
+      }
+    }
+    // the warps' results are combined behind the NEXT CTA barrier (the one in the next pair's K5, or the final one):
+    // no barrier of its own; the scratch alternates between two buffers
+    prev = pair;
+    par ^= 1;
+  }
+  __syncthreads();
+  flush(prev, par ^ 1);
+}
+
 // One CTA per pair (all orientations): best chunk, then findMax's parabola (utils.py:319-338).  The six
 // neighbours are evaluated from the coefficients: one pass over the (m1, m2 >= 0) entries forms
 // S_k(m1, m2) for the three planes k0-1, k0, k0+1 (adjacent table columns) of each orientation and accumulates
@@ -3085,6 +3458,21 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       else FO_I4_GO(2, KS_, NT_, NYQ_, false);            \
     }                                                     \
   } while (0)
+          const I5Layout Z5(Y4);
+          const size_t smem5 = (size_t)Z5.total5 * 8;
+          if (KC4 == 4 && L == 15 && ctx->isoft_variant == 5 && smem5 <= ctx->prop.sharedMemPerBlockOptin) {
+            // the transforms as FFTs on the FP64 vector pipe (sph_isoft5_kernel)
+            int per5 = ctx->prop.multiProcessorCount / nch4;
+            if (per5 < 1) per5 = 1;
+            if ((int64_t)per5 > npairs) per5 = (int)npairs;
+            if (d_grid) {
+              FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+              sph_isoft5_kernel<true><<<(unsigned)(per5 * nch4), 512, smem5, ctx->stream>>>(Y4, Z5, d_Ipk, dtp, (int)npairs, norient, o2);
+            } else {
+              FO_CUDA(ctx, cudaFuncSetAttribute(sph_isoft5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+              sph_isoft5_kernel<false><<<(unsigned)(per5 * nch4), 512, smem5, ctx->stream>>>(Y4, Z5, d_Ipk, dtp, (int)npairs, norient, o2);
+            }
+          } else
           switch (code4) {
             case 421: FO_I4_LAUNCH(4, 2, true); break;    // Jmax 15
             case 420: FO_I4_LAUNCH(4, 2, false); break;   // Jmax 12 .. 14
@@ -3255,14 +3643,15 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
     const size_t smem_prep = ((size_t)2 * NLM + L + 1) * 8;
     FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
     FO_CUDA(ctx, cudaFuncSetAttribute(sph_prep2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
-    sph_prep2_kernel<false><<<grid_for(tot, 128, 148 * 16), 128, smem_prep, ctx->stream>>>(d_posA, Y, (size_t)np, YswA, RA, d_status);
+    sph_prep2_kernel<false><<<grid_for(tot, 128, 148 * 8), 128, smem_prep, ctx->stream>>>(d_posA, Y, (size_t)np, YswA, RA, d_status);
     FO_LAUNCH_CHECK(ctx);
-    sph_prep2_kernel<true><<<grid_for(tot, 128, 148 * 16), 128, smem_prep, ctx->stream>>>(d_posB, Y, (size_t)np, YswB, RB, d_status);
+    sph_prep2_kernel<true><<<grid_for(tot, 128, 148 * 8), 128, smem_prep, ctx->stream>>>(d_posB, Y, (size_t)np, YswB, RB, d_status);
     FO_LAUNCH_CHECK(ctx);
     sph_bessel2_kernel<<<grid_for((size_t)np * Y.bsz, 128), 128, 0, ctx->stream>>>(RA, RB, d_gid, Y, sigma, (size_t)np, Bsw);
     FO_LAUNCH_CHECK(ctx);
-    const size_t smem = 128 + (size_t)nslots * Y.slot * 8;
-    const int blocks = (int)std::min<int64_t>(np, 2 * (int64_t)ctx->prop.multiProcessorCount);
+    const size_t smem = direct2_smem(Y, nslots);
+    const int per_sm = (int)std::min<size_t>(4, ((size_t)227 * 1024) / (smem + 1024));
+    const int blocks = (int)std::min<int64_t>(np, (int64_t)per_sm * ctx->prop.multiProcessorCount);
 #define FO_D2_CASE(N_)                                                                                              \
   case N_:                                                                                                          \
     FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct2_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

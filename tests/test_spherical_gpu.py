@@ -305,7 +305,7 @@ def test_isoft_kernel_variants_agree(ctx, J, invert):
     ctx.set_perm([np.arange(N)], N)
     new = ctx.sph_align_pairs(A, B, J, 0.45, invert=invert, want_grid=True)
     res = []
-    for variant in (3, 42):
+    for variant in (3, 42, 4, 5):   # 4: sph_isoft4_kernel, 5: sph_isoft5_kernel (FFT form; Jmax = 15, else the default)
         ctx.set_option("sph_isoft_variant", variant)
         try:
             res.append(ctx.sph_align_pairs(A, B, J, 0.45, invert=invert, want_grid=True))
