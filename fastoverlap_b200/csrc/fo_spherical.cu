@@ -2679,7 +2679,6 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
       // the S blocks are free once every warp has finished step B of the previous pair (whose results are combined
       // behind the same barrier); the sums above did not need them
       __syncthreads();
-      flush(prev, par ^ 1);
 #pragma unroll
       for (int q = 0; q < KC; ++q) {
         if (k5on) {
@@ -2698,6 +2697,7 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
     }
     __syncthreads();
     if (pair + jstride < npairs) stage_coeffs(pair + jstride);  // lands during the transforms
+    flush(prev, par ^ 1);  // (behind the second barrier: the other warps do not wait for it)
     // ---- step A: column m2 = f, in place (row 16 of the input is zero: |m1| <= 15)
     if (active) {
       double2 y[8];
@@ -3460,7 +3460,7 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
   } while (0)
           const I5Layout Z5(Y4);
           const size_t smem5 = (size_t)Z5.total5 * 8;
-          if (KC4 == 4 && L == 15 && ctx->isoft_variant == 5 && smem5 <= ctx->prop.sharedMemPerBlockOptin) {
+          if (KC4 == 4 && L == 15 && ctx->isoft_variant != 4 && smem5 <= ctx->prop.sharedMemPerBlockOptin) {
             // the transforms as FFTs on the FP64 vector pipe (sph_isoft5_kernel)
             int per5 = ctx->prop.multiProcessorCount / nch4;
             if (per5 < 1) per5 = 1;
