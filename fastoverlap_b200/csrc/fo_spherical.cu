@@ -2502,58 +2502,78 @@ __device__ __forceinline__ void fo_fft4(double2& a, double2& b, double2& c, doub
   b = make_double2(d0.x - d1.y, d0.y + d1.x);
   d = make_double2(d0.x + d1.y, d0.y - d1.x);
 }
-// y[k] = sum_n x[n] e^{+2 pi i n k / 8}, in place
-__device__ __forceinline__ void fo_fft8(double2 (&x)[8]) {
-  fo_fft4(x[0], x[2], x[4], x[6]);  // E[0..3] in x[0], x[2], x[4], x[6]
-  fo_fft4(x[1], x[3], x[5], x[7]);  // O[0..3] in x[1], x[3], x[5], x[7]
-  const double r = 0.70710678118654752440084436210485;
-  const double2 e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
-  const double2 o0 = x[1];
-  const double2 o1 = make_double2((x[3].x - x[3].y) * r, (x[3].x + x[3].y) * r);    // (1 + i) / sqrt 2
-  const double2 o2 = make_double2(-x[5].y, x[5].x);                                 // i
-  const double2 o3 = make_double2((-x[7].x - x[7].y) * r, (x[7].x - x[7].y) * r);   // (-1 + i) / sqrt 2
-  x[0] = fo_cadd(e0, o0);
-  x[4] = fo_csub(e0, o0);
-  x[1] = fo_cadd(e1, o1);
-  x[5] = fo_csub(e1, o1);
-  x[2] = fo_cadd(e2, o2);
-  x[6] = fo_csub(e2, o2);
-  x[3] = fo_cadd(e3, o3);
-  x[7] = fo_csub(e3, o3);
+// sign flips on the integer pipe: m = 0 or 0x80000000
+__device__ __forceinline__ double fo_flip(double v, unsigned m) {
+  return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v));
 }
-// The second half of a 32-point transform spread over the four lanes n1 = lane & 3: y[k2] (8-point DFT of the
-// inputs 4 n2 + n1) -> out[j][k1] = X[(2 t + j) + 8 k1], t = this lane's n1.
-__device__ __forceinline__ void fo_fft32_finish(double2 (&y)[8], const double2 (&tw)[8], bool b0, bool b1,
-                                                double2 (&out)[2][4]) {
+__device__ __forceinline__ double2 fo_cflip(double2 v, unsigned m) { return make_double2(fo_flip(v.x, m), fo_flip(v.y, m)); }
+
+// One 32-point transform X[k] = sum_n x[n] e^{+2 pi i n k / 32} on the four lanes n1 = lane & 3 = 2 b1 + b0 of a
+// quad; lane n1 brings x[n2] = input 4 n2 + n1 and ends with out[jj][k1] = X[(2 n1 + jj) + 8 k1].
+//  * 8-point DFT of the lane's inputs, with its outputs in the order z[k] = y[k ^ r], r = 2 b0 + 4 b1, so that the
+//    exchange below keeps and sends the same registers on every lane: negating the odd inputs swaps y[k] and
+//    y[k + 4], negating the inputs 2, 3, 6, 7 swaps y[k] and y[k ^ 2] up to the constants (1, w, i, w^3) <->
+//    (i, w^3, 1, w), w = e^{i pi / 4}, that multiply the odd half.  The negations are xors of the sign bits.
+//  * twiddles e^{2 pi i n1 k2 / 32} (per-lane table in the same order), exchange by xor shuffles over 2 and 1
+//    (the lane keeps z[0], z[1] of itself and of lane n1 ^ 2 and receives the same from n1 ^ 1, n1 ^ 3),
+//  * 4-point DFT F over the sources (n1, n1 ^ 1, n1 ^ 2, n1 ^ 3): X[k1] = (-1)^{b1 k1} F[k1] for b0 = 0 and
+//    (-1)^{b1 k1} i^{k1} F[-k1] for b0 = 1.
+struct FftLane {
+  bool b0;
+  unsigned mb0, mb1;   // sign masks of b0, b1
+  double a1;           // b0 ? -1/sqrt 2 : 1/sqrt 2
+  double2 tw[8];       // tw[k] = e^{2 pi i n1 (k ^ r) / 32}
+  __device__ __forceinline__ void init(int n1) {
+    b0 = n1 & 1;
+    mb0 = (unsigned)(n1 & 1) << 31;
+    mb1 = (unsigned)((n1 >> 1) & 1) << 31;
+    a1 = b0 ? -0.70710678118654752440084436210485 : 0.70710678118654752440084436210485;
+    const int r = 2 * (n1 & 1) + 4 * ((n1 >> 1) & 1);
 #pragma unroll
-  for (int k = 1; k < 8; ++k) y[k] = fo_cmul(y[k], tw[k]);
-  // round 1 (xor 2): keep the half k2 = 4 b1 + j, get the same half of lane n1 ^ 2
-  double2 K[4], R[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const double2 send = fo_csel(b1, y[j], y[j + 4]);
-    K[j] = fo_csel(b1, y[j + 4], y[j]);
-    R[j] = fo_cshx(send, 2);
+    for (int k = 0; k < 8; ++k) {
+      double sn, cs;
+      sincospi((double)(n1 * (k ^ r)) / 16.0, &sn, &cs);
+      tw[k] = make_double2(cs, sn);
+    }
   }
-  // round 2 (xor 1): keep k2 = 4 b1 + 2 b0 + jj; sources: keepK = lane n1, recvK = n1 ^ 1, keepR = n1 ^ 2,
-  // recvR = n1 ^ 3
+  __device__ __forceinline__ void run(double2 (&x)[8], double2 (&out)[2][4]) const {
+    const double r = 0.70710678118654752440084436210485;
+    x[1] = fo_cflip(x[1], mb1);
+    x[2] = fo_cflip(x[2], mb0);
+    x[3] = fo_cflip(x[3], mb0 ^ mb1);
+    x[5] = fo_cflip(x[5], mb1);
+    x[6] = fo_cflip(x[6], mb0);
+    x[7] = fo_cflip(x[7], mb0 ^ mb1);
+    fo_fft4(x[0], x[2], x[4], x[6]);
+    fo_fft4(x[1], x[3], x[5], x[7]);
+    // odd half times (1, w, i, w^3) or (i, w^3, 1, w)
+    const double2 o0 = make_double2(b0 ? -x[1].y : x[1].x, b0 ? x[1].x : x[1].y);
+    const double2 o2 = make_double2(b0 ? x[5].x : -x[5].y, b0 ? x[5].y : x[5].x);
+    const double2 o1 = make_double2(fma(a1, x[3].x, -r * x[3].y), fma(r, x[3].x, a1 * x[3].y));
+    const double2 o3 = make_double2(fma(-a1, x[7].x, -r * x[7].y), fma(r, x[7].x, -a1 * x[7].y));
+    double2 z[8];
+    z[0] = fo_cmul(fo_cadd(x[0], o0), tw[0]);
+    z[4] = fo_cmul(fo_csub(x[0], o0), tw[4]);
+    z[1] = fo_cmul(fo_cadd(x[2], o1), tw[1]);
+    z[5] = fo_cmul(fo_csub(x[2], o1), tw[5]);
+    z[2] = fo_cmul(fo_cadd(x[4], o2), tw[2]);
+    z[6] = fo_cmul(fo_csub(x[4], o2), tw[6]);
+    z[3] = fo_cmul(fo_cadd(x[6], o3), tw[3]);
+    z[7] = fo_cmul(fo_csub(x[6], o3), tw[7]);
+    double2 R[4];
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const double2 c0 = fo_csel(b0, K[jj + 2], K[jj]);
-    const double2 c1 = fo_cshx(fo_csel(b0, K[jj], K[jj + 2]), 1);
-    const double2 c2 = fo_csel(b0, R[jj + 2], R[jj]);
-    const double2 c3 = fo_cshx(fo_csel(b0, R[jj], R[jj + 2]), 1);
-    // z[i] = c[i ^ n1]: the xor with bit 0 by selects; the xor with bit 1 (z2, z3 <-> z0, z1) only changes the sign of
-    // the odd outputs of the 4-point DFT
-    double2 z0 = fo_csel(b0, c1, c0), z1 = fo_csel(b0, c0, c1), z2 = fo_csel(b0, c3, c2), z3 = fo_csel(b0, c2, c3);
-    fo_fft4(z0, z1, z2, z3);
-    const double sg = b1 ? -1.0 : 1.0;
-    out[jj][0] = z0;
-    out[jj][1] = make_double2(sg * z1.x, sg * z1.y);
-    out[jj][2] = z2;
-    out[jj][3] = make_double2(sg * z3.x, sg * z3.y);
+    for (int j = 0; j < 4; ++j) R[j] = fo_cshx(z[j + 4], 2);
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      double2 f0 = z[jj], f1 = fo_cshx(z[jj + 2], 1), f2 = R[jj], f3 = fo_cshx(R[jj + 2], 1);
+      fo_fft4(f0, f1, f2, f3);
+      out[jj][0] = f0;
+      out[jj][1] = make_double2(fo_flip(b0 ? f3.y : f1.x, mb1 ^ mb0), fo_flip(b0 ? f3.x : f1.y, mb1));
+      out[jj][2] = fo_cflip(f2, mb0);
+      out[jj][3] = make_double2(fo_flip(b0 ? f1.y : f3.x, mb1), fo_flip(b0 ? f1.x : f3.y, mb1 ^ mb0));
+    }
   }
-}
+};
 
 template <bool WANT_GRID>
 __global__ void __launch_bounds__(512, 1)
@@ -2602,14 +2622,8 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
   // ---- transform geometry: block (kk, o) = tid >> 6, transform f = (tid >> 2) & 15, lane n1 = tid & 3
   const int blk = tid >> 6, kk = blk >> 1, o = blk & 1;
   const int f = (tid >> 2) & 15, n1 = tid & 3;
-  const bool b0 = n1 & 1, b1 = (n1 >> 1) & 1;
-  double2 tw[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    double sn, cs;
-    sincospi((double)(n1 * k) / 16.0, &sn, &cs);
-    tw[k] = make_double2(cs, sn);
-  }
+  FftLane fl;
+  fl.init(n1);
   double* S = SB + blk * Z.sblk;
   const int plane = i2_plane(F, KC, chunk, kk);
   // step B: rows al = (f with bits 0 and 1 swapped) and al + 16 -- two neighbouring transforms are two rows apart
@@ -2704,9 +2718,8 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) y[n2] = *reinterpret_cast<const double2*>(S + (4 * n2 + n1) * SP + 2 * f);
       if (n1 == 0) y[4] = make_double2(0.0, 0.0);
-      fo_fft8(y);
       double2 v[2][4];
-      fo_fft32_finish(y, tw, b0, b1, v);
+      fl.run(y, v);
       // (every lane of the transform has loaded its inputs before any of them can have received all it stores)
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj)
@@ -2737,9 +2750,8 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
         y[n2] = make_double2(va.x + vb.y, vb.x - va.y);  // conj V_al + i conj V_al'
       }
       if (n1 == 0) y[4] = make_double2(0.0, 0.0);  // m2 = 16
-      fo_fft8(y);
       double2 v[2][4];
-      fo_fft32_finish(y, tw, b0, b1, v);
+      fl.run(y, v);
       // v[jj][k1] = g(alB, d) + i g(alB + 16, d), d = 2 n1 + jj + 8 k1
       if (WANT_GRID) {
         double* g0 = out.grid + (((size_t)pair * norient + o) * F * F * F + (size_t)(alB * F + plane) * F);
