@@ -799,27 +799,28 @@ sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB,
                    const __grid_constant__ D2Layout Y, int nslots, size_t npairs, double2* __restrict__ Ihalf) {
   extern __shared__ __align__(128) double smq[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smq);  // [8]
-  uint64_t* empty = full + 8;                         // [8]
   double* slots = smq + 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = Y.L, L1 = L + 1, W = 2 * L + 1, N8 = 8 * NCT;
   if (tid == 0) {
-    for (int s_ = 0; s_ < nslots; ++s_) {
-      fo_mbar_init(full + s_, 1);
-      fo_mbar_init(empty + s_, D2_CONS);
-    }
+    for (int s_ = 0; s_ < nslots; ++s_) fo_mbar_init(full + s_, 1);
     fo_mbar_fence_init();
   }
   __syncthreads();
-  if (warp == D2_CONS) {  // producer: one thread feeds the ring
-    if (lane == 0) {
-      unsigned it = 0;
-      const unsigned bytesB = (unsigned)Y.bsz * 8;
-      for (size_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
-        for (int l = L; l >= 0; --l, ++it) {
-          const int sl = (int)(it % (unsigned)nslots);
-          const unsigned use = it / (unsigned)nslots;
-          if (use > 0) fo_mbar_wait(empty + sl, (int)((use - 1) & 1));
+  if (warp == D2_CONS) {  // producer warp: lane 0 feeds the ring
+    unsigned it = 0;
+    const unsigned bytesB = (unsigned)Y.bsz * 8;
+    for (size_t pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+      for (int l = L; l >= 0; --l, ++it) {
+        const int sl = (int)(it % (unsigned)nslots);
+        const unsigned use = it / (unsigned)nslots;
+        if (use > 0) {
+          // the four consumer warps have released the slot: named barrier 1 + slot, on which they only arrive
+          // (after their last fragment load, whose values the DMMAs before it have consumed) and this warp waits
+          asm volatile("bar.sync %0, %1;" ::"r"(sl + 1), "r"(D2_THREADS) : "memory");
+        }
+        if (lane == 0) {
+          fo_fence_proxy_async();  // the bulk copies below are async-proxy writes
           const unsigned bytesY = (unsigned)(N8 * 8 * Y.nrt[l]) * 8;
           fo_mbar_arrive_expect_tx(full + sl, 2 * bytesY + bytesB);
           double* dst = slots + (size_t)sl * Y.slot;
@@ -827,10 +828,12 @@ sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB,
           fo_bulk_g2s(dst + Y.ymax, YB + pair * (size_t)Y.ysz + Y.yoff[l], bytesY, full + sl);
           fo_bulk_g2s(dst + 2 * Y.ymax, Bsw + (pair * L1 + l) * (size_t)Y.bsz, bytesB, full + sl);
         }
-    }
+        __syncwarp();
+      }
     return;
   }
   const int g = lane >> 2, t4 = lane & 3;
+  const size_t nitems = blockIdx.x < npairs ? ((npairs - 1 - blockIdx.x) / gridDim.x + 1) * (size_t)L1 : 0;
   const int swB = d2_sw(NCT, t4);  // (4 ks + t4) & 3 == t4 and ((4 ks + t4) >> 1) & 1 == (t4 >> 1) & 1
   unsigned it = 0;
   for (size_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -890,8 +893,8 @@ sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB,
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) fo_mbar_arrive(empty + sl);
+      // release the slot -- unless it is never refilled (the producer does not wait for the last nslots items)
+      if ((size_t)it + nslots < nitems) asm volatile("bar.arrive %0, %1;" ::"r"(sl + 1), "r"(D2_THREADS) : "memory");
     }
   }
 }
@@ -2720,7 +2723,9 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
       if (n1 == 0) y[4] = make_double2(0.0, 0.0);
       double2 v[2][4];
       fl.run(y, v);
-      // (every lane of the transform has loaded its inputs before any of them can have received all it stores)
+      // every lane of the transform has loaded its inputs before any of them can have received all it stores (the
+      // shuffles carry the dependence); the warp barrier states that order for the tools
+      __syncwarp();
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj)
 #pragma unroll

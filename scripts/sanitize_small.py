@@ -2,8 +2,10 @@
     compute-sanitizer --tool memcheck  python scripts/sanitize_small.py
     compute-sanitizer --tool racecheck python scripts/sanitize_small.py
 (the mbarrier hand-over of per_sf3_kernel / per_sfx_kernel and its tensor-memory stash, the bulk-copy staging of
-per_xf6_kernel / sph_isoft4_kernel, the cp.async staging and the shared-memory
-reductions of the screening kernels are what racecheck is pointed at)."""
+per_xf6_kernel / sph_isoft4_kernel / sph_isoft5_kernel, the mbarrier ring of sph_direct2_kernel, the in-place
+transforms and named barriers of sph_isoft5_kernel, the cp.async staging and the shared-memory reductions of the
+screening kernels are what racecheck is pointed at).  `python scripts/sanitize_small.py sph` runs the cluster
+part only."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,35 +15,37 @@ import fastoverlap_b200 as fob
 
 ctx = fob.Context(0)
 rng = np.random.default_rng(0)
+SPH_ONLY = len(sys.argv) > 1 and sys.argv[1] == "sph"
 
-# periodic: bench configuration (per_sf3, per_cross, per_xf4, per_assign) incl. the grid output
-wl = bench.Blj256()
-wl.setup(ctx)
-A, B, _ = wl.make(6, 0)
-r = ctx.per_align_pairs_full(wl.params, A, B, niter=10, nthreads=2)
-print("blj256 full", r[0][:3], "host", r[-1], flush=True)
-g = ctx.per_align_pairs(wl.params, A[:2], B[:2], want_grid=True)
-print("blj256 grid max", g[3].max(), flush=True)
-# fine k-grid (per_sf2, per_xf5) and a small generic case (per_sf, per_xf), ragged groups
-for N, n, groups in ((36, 16, [np.arange(20), np.arange(20, 36)]), (17, 3, None), (40, 6, [np.arange(23), np.arange(23, 40)])):
-    box = np.array([4.0, 4.5, 5.1])
-    al = fob.PeriodicAlign(N, box, groups, n=n, ctx=ctx)
-    p1 = rng.uniform(-0.5, 0.5, size=(3, N, 3)) * box
-    p2 = p1 + rng.uniform(0, 1, size=(3, 1, 3)) * box + rng.normal(scale=0.03, size=p1.shape)
-    d = al.align_batch(p1, p2, nthreads=2)[0]
-    gg = ctx.per_align_pairs(al._params(), p1[:1], p2[:1], want_grid=True)
-    print("periodic N %d n %d dist" % (N, n), d, flush=True)
-ctx.set_option("force_generic", 1)
-al = fob.PeriodicAlign(17, np.array([4.0, 4.5, 5.1]), None, n=3, ctx=ctx)
-p1 = rng.uniform(-0.5, 0.5, size=(2, 17, 3)) * 4
-print("generic periodic", al.align_batch(p1, p1 + 0.3, nthreads=1)[0], flush=True)
-ctx.set_option("force_generic", 0)
-# all-vs-all through the structure-factor bank + top-k peaks
-al = wl.al
-print("alignGroup", al.alignGroup(A[:3, :, :].copy())[0, 1], flush=True)
-print("npeaks", al(A[0], B[0], npeaks=3)[0], flush=True)
+if not SPH_ONLY:
+    # periodic: bench configuration (per_sf3, per_cross, per_xf4, per_assign) incl. the grid output
+    wl = bench.Blj256()
+    wl.setup(ctx)
+    A, B, _ = wl.make(6, 0)
+    r = ctx.per_align_pairs_full(wl.params, A, B, niter=10, nthreads=2)
+    print("blj256 full", r[0][:3], "host", r[-1], flush=True)
+    g = ctx.per_align_pairs(wl.params, A[:2], B[:2], want_grid=True)
+    print("blj256 grid max", g[3].max(), flush=True)
+    # fine k-grid (per_sf2, per_xf5) and a small generic case (per_sf, per_xf), ragged groups
+    for N, n, groups in ((36, 16, [np.arange(20), np.arange(20, 36)]), (17, 3, None), (40, 6, [np.arange(23), np.arange(23, 40)])):
+        box = np.array([4.0, 4.5, 5.1])
+        al = fob.PeriodicAlign(N, box, groups, n=n, ctx=ctx)
+        p1 = rng.uniform(-0.5, 0.5, size=(3, N, 3)) * box
+        p2 = p1 + rng.uniform(0, 1, size=(3, 1, 3)) * box + rng.normal(scale=0.03, size=p1.shape)
+        d = al.align_batch(p1, p2, nthreads=2)[0]
+        gg = ctx.per_align_pairs(al._params(), p1[:1], p2[:1], want_grid=True)
+        print("periodic N %d n %d dist" % (N, n), d, flush=True)
+    ctx.set_option("force_generic", 1)
+    al = fob.PeriodicAlign(17, np.array([4.0, 4.5, 5.1]), None, n=3, ctx=ctx)
+    p1 = rng.uniform(-0.5, 0.5, size=(2, 17, 3)) * 4
+    print("generic periodic", al.align_batch(p1, p1 + 0.3, nthreads=1)[0], flush=True)
+    ctx.set_option("force_generic", 0)
+    # all-vs-all through the structure-factor bank + top-k peaks
+    al = wl.al
+    print("alignGroup", al.alignGroup(A[:3, :, :].copy())[0, 1], flush=True)
+    print("npeaks", al(A[0], B[0], npeaks=3)[0], flush=True)
 
-# clusters: LJ38 bench configuration (prep, bessel, direct_mma, isoft3, final2, assign), generic Jmax, harmonic bank
+# clusters: LJ38 bench configuration (prep2, bessel2, direct2, isoft5, final2, assign), generic Jmax, harmonic bank
 wl = bench.Lj38()
 wl.setup(ctx)
 A, B, _ = wl.make(6, 0)
@@ -68,17 +72,23 @@ print("launches", ctx.launch_count(), flush=True)
 
 # older kernel variants kept for A/B and for grids outside the fast paths: bank path (per_sf3 + per_cross6 + per_xf6),
 # sph_isoft3 (stage A -> shared memory -> stage B), even Jmax (two planes per CTA)
-wl = bench.Blj256()
-wl.setup(ctx)
-A, B, _ = wl.make(4, 1)
-ctx.set_option("per_pairs_fused", 0)
-print("blj256 bank path", ctx.per_align_pairs(wl.params, A, B)[1][:2], flush=True)
-ctx.set_option("per_pairs_fused", 1)
+if not SPH_ONLY:
+    wl = bench.Blj256()
+    wl.setup(ctx)
+    A, B, _ = wl.make(4, 1)
+    ctx.set_option("per_pairs_fused", 0)
+    print("blj256 bank path", ctx.per_align_pairs(wl.params, A, B)[1][:2], flush=True)
+    ctx.set_option("per_pairs_fused", 1)
 wl = bench.Lj38()
 wl.setup(ctx)
 A, B, _ = wl.make(4, 1)
 ctx.set_option("sph_isoft_variant", 3)
 print("lj38 isoft3", ctx.sph_align_pairs(A, B, 15, 0.3, invert=True)[1][0], flush=True)
+ctx.set_option("sph_isoft_variant", 4)
+print("lj38 isoft4", ctx.sph_align_pairs(A, B, 15, 0.3, invert=True)[1][0], flush=True)
 ctx.set_option("sph_isoft_variant", 0)
+ctx.set_option("sph_direct_ring", -1)
+print("lj38 direct_mma", ctx.sph_align_pairs(A, B, 15, 0.3, invert=True)[1][0], flush=True)
+ctx.set_option("sph_direct_ring", 0)
 print("lj38 Jmax 14", ctx.sph_align_pairs(A, B, 14, 0.3, invert=True)[1][0], flush=True)
 print("lj38 Jmax 7", ctx.sph_align_pairs(A, B, 7, 0.3, invert=True)[1][0], flush=True)
