@@ -18,7 +18,8 @@ Per workload:
                fo_sph_align_pairs_full): H2D of every step's coordinates, D2H of distances / displacements /
                permutations, and the host pool (LAP for flagged pairs, Kearsley for clusters) inside the
                timed region; wall clock, max over ranks; host threads per rank = cores / ranks
-  roofline     dominant kernel: useful FP64 flop / CUDA-event duration vs the FP64 tensor peak measured in the run
+  roofline     dominant kernel: useful FP64 flop / CUDA-event duration vs the FP64 peak of its pipe measured in the run
+               (BLJ256: tensor pipe, DMMA; LJ38: vector pipe, the transforms are FFTs)
   cpu_baseline the C oracle (port of the reference algorithm) on a bounded sample, all host cores;
   cpu_baseline_numpy  the UNMODIFIED reference numpy classes (when the reference tree is present: baseline/_ref,
                $FASTOVERLAP_REFERENCE or /root/reference), 1 core and all cores
@@ -261,9 +262,17 @@ class Lj38:
                 "orientations_settled_on_device": float(ok.mean()), "assignments_through_host_lap": int(nhost)}
 
     dominant = "sph_isoft"
+    pipe = "vector"   # sph_isoft5_kernel: FFTs on the FP64 vector pipe (DFMA / DADD / DMUL)
 
     def dominant_flops_per_pair(self):
-        # iSOFT, both orientations (DESIGN.md "K_isoft"): executed real FMA count x 2
+        # iSOFT, both orientations, in the form the kernel executes it (sph_isoft5_kernel: Wigner contraction +
+        # 32-point FFTs, 5 N log2 N flop per transform)
+        from fastoverlap_b200.spherical import isoft_fft_flops
+        return isoft_fft_flops(self.Jmax, True)
+
+    def dft_matrix_flops_per_pair(self):
+        # the same transforms as DFT-matrix products (what sph_isoft3 / sph_isoft4 execute on the tensor pipe and
+        # what the rounds before reported): for comparison only
         from fastoverlap_b200.spherical import isoft_executed_flops
         return isoft_executed_flops(self.Jmax, True)
 
@@ -638,14 +647,21 @@ def measure(h, wl, P, steps, warmup, peaks, want_cpu):
     if dom_n:
         pairs_timed = P * steps
         achieved = wl.dominant_flops_per_pair() * pairs_timed / (dom_ms * 1e-3) / 1e12
-        peak = peaks["tensor"]
-        roof = {"bound": "tensor", "pipe": "fp64 tensor pipe (DMMA.8x8x4); the path is FP64 throughout, so the "
-                "peak is the measured FP64 tensor throughput, not the bf16 figure of MEASURED_PEAKS.json",
+        vector = getattr(wl, "pipe", "tensor") == "vector"
+        peak = peaks["vector"] if vector else peaks["tensor"]
+        roof = {"bound": "tensor", "pipe": ("fp64 vector pipe (DFMA): the dominant kernel runs the transforms as FFTs; on "
+                                            "B200 the FP64 vector and tensor pipes have the same peak and share the units"
+                                            if vector else
+                                            "fp64 tensor pipe (DMMA.8x8x4); the path is FP64 throughout, so the "
+                                            "peak is the measured FP64 tensor throughput, not the bf16 figure of "
+                                            "MEASURED_PEAKS.json"),
                 "kernel": wl.dominant, "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": "measured in this run: FP64 tensor pipe (mma.sync.m8n8k4.f64 "
-                               "microbenchmark, fo_measure_fp64_tensor_peak); MEASURED_PEAKS.json has no "
-                               "FP64 figure",
+                "peak_source": ("measured in this run: FP64 vector pipe (DFMA microbenchmark, fo_measure_fp64_peak)"
+                                if vector else
+                                "measured in this run: FP64 tensor pipe (mma.sync.m8n8k4.f64 "
+                                "microbenchmark, fo_measure_fp64_tensor_peak)") +
+                               "; MEASURED_PEAKS.json has no FP64 figure",
                 "peak_fp64_vector_tflops": peaks["vector"], "peak_fp64_tensor_tflops": peaks["tensor"],
                 "flops_counted": "useful FP64 of the symmetry-reduced algorithm (FMA=2, MUL=1); "
                                  "tile padding executed by the kernel is not counted",
@@ -660,6 +676,11 @@ def measure(h, wl, P, steps, warmup, peaks, want_cpu):
                 "hot_path_frac": wl.hot_path_flops_per_pair() * pairs_timed /
                 (sum(v[0] for k, v in prof.items() if k != "assign") * 1e-3) / 1e12 / peak,
                 "traffic": None, "hbm_frac_of_measured": None}
+        if hasattr(wl, "dft_matrix_flops_per_pair"):
+            roof["dft_matrix_equivalent_tflops"] = wl.dft_matrix_flops_per_pair() * pairs_timed / (dom_ms * 1e-3) / 1e12
+            roof["dft_matrix_equivalent_note"] = ("the flop the same transforms cost as DFT-matrix products on the tensor "
+                                                  "pipe (sph_isoft4, the rounds before) over this kernel's time: above the "
+                                                  "tensor peak means the FFT form is faster than any DFT-matrix kernel could be")
         try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
             tr = None
             for name in ("r02_traffic.json", "r01_traffic.json"):

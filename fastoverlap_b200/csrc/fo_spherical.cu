@@ -906,8 +906,8 @@ int direct2_slots(const fo_ctx* ctx, int64_t natoms, int L) {
       L >= D2_MAXL)
     return 0;
   const D2Layout Y((int)natoms, L);
-  const size_t budget = 108 * 1024 - 128;
-  int n = (int)(budget / ((size_t)Y.slot * 8));
+  int n = (int)(((size_t)108 * 1024 - 128) / ((size_t)Y.slot * 8));             // two CTAs per SM
+  if (n < 2) n = (int)(((size_t)220 * 1024 - 128) / ((size_t)Y.slot * 8));      // large clusters / bandwidths: one
   if (const int64_t o = ctx->opt("sph_direct_ring")) n = std::min<int>(n, (int)o);
   return n >= 2 ? std::min(n, 8) : 0;
 }

@@ -30,6 +30,18 @@ def isoft_executed_flops(Jmax, invert=True):
     return 2 * (k5 + O * (stage_a + stage_b))
 
 
+def isoft_fft_flops(Jmax, invert=True):
+    """FP64 flop of the FFT form of the iSOFT (sph_isoft5_kernel, Jmax = 15): the Wigner contraction as above and,
+    per orientation and beta plane, F/2 complex transforms of length F = 2 Jmax + 2 along alpha (the columns
+    m2 >= 0) and F/2 along gamma (two real-output rows per complex transform), 5 F log2 F flop each."""
+    L = Jmax
+    F = 2 * L + 2
+    nnz_half = sum((2 * l + 1) * (l + 1) for l in range(L + 1))
+    k5 = 2 * nnz_half * F
+    O = 2 if invert else 1
+    return 2 * k5 + O * F * F * 5.0 * F * np.log2(F)
+
+
 class BaseSphericalAlignment(object):
     calcScale = True
     orientation = "distance"

@@ -318,6 +318,43 @@ def test_isoft_kernel_variants_agree(ctx, J, invert):
         assert rel(new[3], old[3]) < 1e-12
 
 
+@pytest.mark.parametrize("N,J,groups", [(38, 15, None), (13, 7, None), (55, 20, [30, 25]), (8, 3, None), (63, 15, None),
+                                        (24, 31, [10, 14]), (3, 2, None)])
+def test_direct_coefficient_kernels_agree(ctx, N, J, groups):
+    """sph_prep2 / sph_bessel2 / sph_direct2 (operands in the DMMA fragment layouts: swizzled 8-column groups for
+    every tile count mod 4, row-permuted second structure, mbarrier ring, chained second product) against
+    sph_prep / sph_bessel / sph_direct_mma (option sph_direct_ring = -1) and against the oracle."""
+    rng = np.random.default_rng(1000 + N + J)
+    P = 6
+    A = rng.normal(size=(P, N, 3)) * 1.1
+    B = rng.normal(size=(P, N, 3)) * 1.1
+    A -= A.mean(1, keepdims=True)
+    B -= B.mean(1, keepdims=True)
+    perm = None
+    if groups:
+        o = np.cumsum([0] + groups)
+        perm = [np.arange(o[i], o[i + 1]) for i in range(len(groups))]
+    ctx.set_perm(perm if perm else [np.arange(N)], N)
+    new, st = ctx.sph_coeffs_direct(A, B, J, 0.45)
+    ctx.set_option("sph_direct_ring", -1)
+    try:
+        old, _ = ctx.sph_coeffs_direct(A, B, J, 0.45)
+    finally:
+        ctx.set_option("sph_direct_ring", 0)
+    assert (st == 0).all()
+    for p in range(P):
+        assert rel(new[p], old[p]) < 1e-13
+    assert rel(new[0], oracle.sph_coeffs_direct(A[0], B[0], J, 0.45, perm)) < 1e-12
+    # two ring slots (three CTAs per SM) give the same numbers bit for bit
+    ctx.set_option("sph_direct_ring", 2)
+    try:
+        two, _ = ctx.sph_coeffs_direct(A, B, J, 0.45)
+    finally:
+        ctx.set_option("sph_direct_ring", 0)
+    assert np.array_equal(new, two)
+    ctx.set_perm([np.arange(N)], N)
+
+
 @pytest.mark.parametrize("N,J", [(10, 33), (12, 40), (9, 63)])
 def test_large_bandwidth_isoft(ctx, N, J):
     """Jmax > 32 (grids up to 128^3, BASELINE.json configs[3]): sph_isoft_big_kernel with the
