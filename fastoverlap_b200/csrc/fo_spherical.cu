@@ -796,7 +796,10 @@ __global__ void sph_bessel2_kernel(const double* __restrict__ RA, const double* 
 template <int NCT>
 __global__ void __launch_bounds__(D2_THREADS)
 sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB, const double* __restrict__ Bsw,
-                   const __grid_constant__ D2Layout Y, int nslots, size_t npairs, double2* __restrict__ Ihalf) {
+                   const __grid_constant__ D2Layout Y, int nslots, size_t npairs, double2* __restrict__ Ihalf,
+                   double2* __restrict__ Ipk) {
+  // Ipk (optional): the same coefficients in the packed layout of the fast iSOFT kernels as well
+  // ([pair][level][shell-ordered entry (a, m2)][+-a], sph_ipack_kernel), saving that kernel's pass over Ihalf
   extern __shared__ __align__(128) double smq[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smq);  // [8]
   double* slots = smq + 16;
@@ -838,7 +841,9 @@ sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB,
   unsigned it = 0;
   for (size_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
     double2* out = Ihalf + pair * (size_t)L1 * W * L1;
+    double2* opk = Ipk ? Ipk + pair * (size_t)((L + 1) * (L + 2) * (2 * L + 3) / 3) : nullptr;
     for (int l = L; l >= 0; --l, ++it) {
+      double2* opl = opk ? opk + (size_t)(l * (l + 1) * (2 * l + 1) / 6) * 2 : nullptr;  // entries below level l
       const int sl = (int)(it % (unsigned)nslots);
       const unsigned use = it / (unsigned)nslots;
       fo_mbar_wait(full + sl, (int)(use & 1));
@@ -884,11 +889,21 @@ sph_direct2_kernel(const double* __restrict__ YA, const double* __restrict__ YB,
             const double px1 = __shfl_xor_sync(0xffffffffu, c2[q][1], 4);
             const int m1 = (rt1 * 8 + g) >> 1, m2 = (rb + q) * 4 + t4;
             if (m1 > l || m2 > l) continue;
+            // packed entry of (a = m1, m2): shell s = max(a, m2), t = s^2 + (m2 == s ? a : s + 1 + m2)
+            const int sh = m1 > m2 ? m1 : m2;
+            const int tpk = 2 * (sh * sh + (m2 == sh ? m1 : sh + 1 + m2));
             if ((g & 1) == 0) {  // rr, ri here; ir, ii in the partner: I(+m1, m2)
-              out[((size_t)m2 * W + (L + m1)) * L1 + l] = make_double2(c2[q][0] + px1, px0 - c2[q][1]);
+              const double2 v = make_double2(c2[q][0] + px1, px0 - c2[q][1]);
+              out[((size_t)m2 * W + (L + m1)) * L1 + l] = v;
+              if (opl) {
+                opl[tpk] = v;
+                if (m1 == 0) opl[tpk + 1] = v;
+              }
             } else if (m1 > 0) {  // ir, ii here; rr, ri in the partner: I(-m1, m2) = (-1)^m1 (rr - ii, -ir - ri)
               const double sg = (m1 & 1) ? -1.0 : 1.0;
-              out[((size_t)m2 * W + (L - m1)) * L1 + l] = make_double2(sg * (px0 - c2[q][1]), sg * (-c2[q][0] - px1));
+              const double2 v = make_double2(sg * (px0 - c2[q][1]), sg * (-c2[q][0] - px1));
+              out[((size_t)m2 * W + (L - m1)) * L1 + l] = v;
+              if (opl) opl[tpk + 1] = v;
             }
           }
         }
@@ -3405,8 +3420,23 @@ size_t isoft_smem(int L, int KC) {
 }
 
 // iSOFT + arg-max for npairs coefficient sets already in the Ihalf layout (device).
+// whether run_isoft takes a kernel that reads the packed coefficients (call after ensure_wigner)
+bool isoft_packed_applies(const fo_ctx* ctx, int L) {
+  if (!ctx->wig.d_packed || ctx->force_generic || L < 1) return false;
+  const I2Layout Y(L, ctx->wig.packed_kc);
+  const int KSq = (L + 3) / 4;
+  const bool nyq = (Y.H % 8) == 1;
+  const int NTq = nyq ? (Y.H - 1) / 8 : (Y.H + 7) / 8;
+  const int code = KSq * 100 + NTq * 10 + (nyq ? 1 : 0);
+  const bool have = code == 421 || code == 420 || code == 320 || code == 220 || code == 211 || code == 210 ||
+                    code == 110;
+  return have && (size_t)Y.total3 * 8 <= ctx->prop.sharedMemPerBlockOptin;
+}
+
+// ipk_ready: the packed coefficients of these pairs are already in the FO_SCR_IPK scratch (written by
+// sph_direct2_kernel): sph_ipack_kernel is skipped
 int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int norient,
-              long long* d_best_idx, double* d_best_val, double* d_frac, double* d_grid) {
+              long long* d_best_idx, double* d_best_val, double* d_frac, double* d_grid, bool ipk_ready = false) {
   if (npairs == 0) return FO_OK;
   FO_CHECK(ensure_wigner(ctx, L));
   const int F = 2 * (L + 1);
@@ -3437,9 +3467,11 @@ int run_isoft(fo_ctx* ctx, const double2* d_Ihalf, int64_t npairs, int L, int no
       if ((int64_t)per > npairs) per = (int)npairs;
       const unsigned blocks = (unsigned)(per * nch);
       fo_prof_scope prof(ctx, FO_PROF_SPH_ISOFT);
-      sph_ipack_kernel<<<grid_for((size_t)npairs * Y.ipk, 256), 256, 0, ctx->stream>>>(d_Ihalf, Y, (size_t)npairs,
-                                                                                        (double2*)ipk);
-      FO_LAUNCH_CHECK(ctx);
+      if (!ipk_ready) {
+        sph_ipack_kernel<<<grid_for((size_t)npairs * Y.ipk, 256), 256, 0, ctx->stream>>>(d_Ihalf, Y, (size_t)npairs,
+                                                                                          (double2*)ipk);
+        FO_LAUNCH_CHECK(ctx);
+      }
       {  // stages A -> B chained in registers (sph_isoft4_kernel); four planes per CTA when 2 (L + 1) % 4 == 0
         const int KC4 = (ctx->wig.d_packed4 && ctx->isoft_variant != 42) ? 4 : 2;
         const I2Layout Y4(L, KC4);
@@ -3643,8 +3675,10 @@ int upload_gid(fo_ctx* ctx, int64_t natoms, int** d_gid) {
 }
 
 // direct coefficients of np pairs (device positions) into d_Ihalf
+// d_Ipk (optional; only honoured by the streaming form, see ipk_fused_applies): packed copy for run_isoft
 int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t np, int64_t natoms, int L,
-               double sigma, const int* d_gid, double2* d_Ihalf, int* d_status, char* work) {
+               double sigma, const int* d_gid, double2* d_Ihalf, int* d_status, char* work,
+               double2* d_Ipk = nullptr) {
   if (np == 0) return FO_OK;
   const int NLM = nlm_of(L);
   if (const int nslots = direct2_slots(ctx, natoms, L)) {
@@ -3672,7 +3706,7 @@ int run_direct(fo_ctx* ctx, const double* d_posA, const double* d_posB, int64_t 
 #define FO_D2_CASE(N_)                                                                                              \
   case N_:                                                                                                          \
     FO_CUDA(ctx, cudaFuncSetAttribute(sph_direct2_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sph_direct2_kernel<N_><<<blocks, D2_THREADS, smem, ctx->stream>>>(YswA, YswB, Bsw, Y, nslots, (size_t)np, d_Ihalf); \
+    sph_direct2_kernel<N_><<<blocks, D2_THREADS, smem, ctx->stream>>>(YswA, YswB, Bsw, Y, nslots, (size_t)np, d_Ihalf, d_Ipk); \
     break;
     switch (Y.NCT) {
       FO_D2_CASE(1) FO_D2_CASE(2) FO_D2_CASE(3) FO_D2_CASE(4) FO_D2_CASE(5) FO_D2_CASE(6) FO_D2_CASE(7) FO_D2_CASE(8)
@@ -4019,13 +4053,19 @@ int align_pairs_dev_impl(fo_ctx* ctx, const double* d_posA, const double* d_posB
   FO_CHECK(fo_scratch(ctx, FO_SCR_WORK, direct_work_bytes(ctx, chunk, natoms, L), &work));
   FO_CHECK(fo_scratch(ctx, FO_SCR_BANK, (size_t)chunk * ihalf_elems(L) * 16, &dhalf));
   if (d_status) FO_CUDA(ctx, cudaMemsetAsync(d_status, 0, (size_t)npairs * 4, ctx->stream));
+  // the streaming coefficient kernel also writes the packed copy the fast iSOFT kernels read (no sph_ipack pass)
+  FO_CHECK(ensure_wigner(ctx, L));
+  const bool fuse_ipk = isoft_packed_applies(ctx, L) && direct2_slots(ctx, natoms, L) > 0;
   for (int64_t p0 = 0; p0 < npairs; p0 += chunk) {
     const int64_t np = std::min(chunk, npairs - p0);
+    void* ipk = nullptr;
+    if (fuse_ipk) FO_CHECK(fo_scratch(ctx, FO_SCR_IPK, (size_t)np * I2Layout(L, ctx->wig.packed_kc).ipk * 16, &ipk));
     FO_CHECK(run_direct(ctx, d_posA + (size_t)p0 * natoms * 3, d_posB + (size_t)p0 * natoms * 3, np, natoms,
-                        L, sigma, d_gid, (double2*)dhalf, d_status ? d_status + p0 : nullptr, (char*)work));
+                        L, sigma, d_gid, (double2*)dhalf, d_status ? d_status + p0 : nullptr, (char*)work,
+                        (double2*)ipk));
     FO_CHECK(run_isoft(ctx, (const double2*)dhalf, np, L, O, (long long*)d_best_idx + (size_t)p0 * O * 3,
                        d_best_val + (size_t)p0 * O, d_frac_idx + (size_t)p0 * O * 3,
-                       d_grid_out ? d_grid_out + (size_t)p0 * O * G3 : nullptr));
+                       d_grid_out ? d_grid_out + (size_t)p0 * O * G3 : nullptr, ipk != nullptr));
     if (d_euler)
       FO_CHECK(fo_refine_run_dev(ctx, dhalf, np, L, O, d_frac_idx + (size_t)p0 * O * 3, 1,
                                  d_euler + (size_t)p0 * O * 3, d_overlap + (size_t)p0 * O, nullptr));
