@@ -2678,6 +2678,7 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
       double2 Pp[KC], Mp[KC];
 #pragma unroll
       for (int q = 0; q < KC; ++q) Pp[q] = Mp[q] = make_double2(0.0, 0.0);
+#pragma unroll 2
       for (int lv = k5l0; lv <= L; lv += 2) {
         const int idx = Y.o_ent[lv] + k5t;
         double dd[KC];
