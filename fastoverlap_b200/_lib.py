@@ -148,6 +148,7 @@ SIGNATURES = {
                                                 c_void_p, c_void_p, c_void_p]),
     "fo_host_kearsley": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_f64p, c_void_p]),
     "fo_host_refine_counters": (None, [c_void_p, ctypes.c_int]),
+    "fo_host_lap_isa": (ctypes.c_int, [ctypes.c_int]),
     "fo_host_refine_spherical": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
                                                 ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int,
                                                 c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -245,6 +246,11 @@ def host_best_permutation(posA, posB, perm=None, box=None):
     if rc != 0:
         raise FastOverlapError("fo_host_best_permutation failed (%d): invalid permutation groups?" % rc)
     return out
+
+
+def host_lap_isa(isa=-1):
+    """Test hook (fo_host_lap_isa): select / query the instruction set of the host assignment kernels."""
+    return int(load_library().fo_host_lap_isa(int(isa)))
 
 
 def host_kearsley(x1, x2):

@@ -169,21 +169,34 @@ struct LapKernels {
   void (*cost)(int, int, const double*, const double*, const double*, double*, double*, int*, double*);
   void (*sqrt_row)(int, double*);
 };
+// isa: 1 = 2-wide vectors (SSE2 / generic), 2 = AVX2, 3 = AVX-512; 0 = the widest the CPU has.  -> false: not available
 #if defined(__GNUC__) && defined(__x86_64__) && !defined(__CUDACC__)
 FO_LAP_KERNELS(avx512, 8, FO_HMIN8, __attribute__((target("avx512f"))))
 FO_LAP_KERNELS(avx2, 4, FO_HMIN4, __attribute__((target("avx2"))))
 FO_LAP_KERNELS(base, 2, FO_HMIN2, )
-LapKernels pick_lap_kernels() {
+bool pick_lap_kernels(int isa, LapKernels* k, int* picked) {
   __builtin_cpu_init();
-  if (__builtin_cpu_supports("avx512f")) return {scan_avx512, cost_avx512, sqrt_avx512};
-  if (__builtin_cpu_supports("avx2")) return {scan_avx2, cost_avx2, sqrt_avx2};
-  return {scan_base, cost_base, sqrt_base};
+  const bool a512 = __builtin_cpu_supports("avx512f"), a2 = __builtin_cpu_supports("avx2");
+  if (isa == 0) isa = a512 ? 3 : (a2 ? 2 : 1);
+  if (isa == 3 && a512) *k = {scan_avx512, cost_avx512, sqrt_avx512};
+  else if (isa == 2 && a2) *k = {scan_avx2, cost_avx2, sqrt_avx2};
+  else if (isa == 1) *k = {scan_base, cost_base, sqrt_base};
+  else return false;
+  *picked = isa;
+  return true;
 }
 #else
 FO_LAP_KERNELS(base, 2, FO_HMIN2, )
-LapKernels pick_lap_kernels() { return {scan_base, cost_base, sqrt_base}; }
+bool pick_lap_kernels(int isa, LapKernels* k, int* picked) {
+  if (isa > 1) return false;
+  *k = {scan_base, cost_base, sqrt_base};
+  *picked = 1;
+  return true;
+}
 #endif
-const LapKernels LK = pick_lap_kernels();
+LapKernels LK;
+int g_lap_isa = 0;
+const bool g_lap_init = pick_lap_kernels(0, &LK, &g_lap_isa);
 
 // Dense n x n linear assignment (minimise), cost row-major with pitch ld.  col4row[i] = column assigned to row i.
 struct Lap {
@@ -735,6 +748,18 @@ void euler_m(double a, double b, double y, double M[9]) {
 }
 
 }  // namespace
+
+// Test hook: selects the instruction set of the assignment kernels (see pick_lap_kernels; not thread safe: call
+// while no refinement runs).  Returns the active one, or -1 when the requested one is not available on this CPU.
+extern "C" int fo_host_lap_isa(int isa) {
+  if (isa < 0) return g_lap_isa;
+  LapKernels k;
+  int picked = 0;
+  if (!pick_lap_kernels(isa, &k, &picked)) return -1;
+  LK = k;
+  g_lap_isa = picked;
+  return picked;
+}
 
 extern "C" void fo_host_refine_counters(int64_t out[3], int reset) {
   for (int k = 0; k < 3; ++k) {

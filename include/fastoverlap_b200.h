@@ -403,6 +403,11 @@ int fo_host_refine_periodic_subset(const fo_per_params* p, const int32_t* group_
  * the stability margin of the last assignment.  reset != 0 zeroes them after reading. */
 void fo_host_refine_counters(int64_t out[3], int reset);
 
+/* Test hook of the host pool: instruction set of the assignment kernels (cost matrix, row scan).  isa: 0 = the widest
+ * the CPU has (the default), 1 = 2-wide vectors, 2 = AVX2, 3 = AVX-512, < 0 = query only.  Returns the active one, or
+ * -1 when the requested one is not available.  Results do not depend on it.  Not thread safe. */
+int fo_host_lap_isa(int isa);
+
 /* Clusters: for each orientation o < norient rotate (o = 1: -posB) by the Euler angles
  * euler[P,norient,3], permute (LAP on squared distances per group), Kearsley quaternion fit; keep
  * the orientation with the smaller distance.  Replaces BaseSphericalAlignment.refine

@@ -120,6 +120,40 @@ def test_kearsley_and_lap():
     assert d < 1e-7 and np.allclose(X.dot(R).dot(M.T), X, atol=1e-7)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 38, 63, 64, 65, 100, 204])
+def test_lap_vector_kernels_all_sizes(n):
+    """The per-ISA cost / row-scan kernels of the assignment (padded column arrays, in-register column pick) against
+    scipy.optimize.linear_sum_assignment on unrelated point sets (many free rows after the column reduction: long
+    augmenting paths), free and periodic costs, every size around the vector widths; and on integer coordinates
+    (exact ties: any optimal assignment, equal cost)."""
+    from scipy.optimize import linear_sum_assignment
+    from fastoverlap_b200 import _lib
+    rng = np.random.default_rng(4000 + n)
+    box = np.array([3.0, 3.5, 4.0])
+    for trial in range(3):
+        # every instruction set this CPU has (2-wide, AVX2, AVX-512), the widest one last = the default again
+        isa = _lib.host_lap_isa(trial + 1)
+        if isa < 0:
+            isa = _lib.host_lap_isa(0)
+        X = rng.uniform(-2, 2, size=(n, 3))
+        Y = rng.uniform(-2, 2, size=(n, 3))
+        c = ((X[:, None, :] - Y[None, :, :]) ** 2).sum(2)
+        r, cc = linear_sum_assignment(c)
+        assert np.array_equal(_lib.host_best_permutation(X, Y), cc)
+        d = X[:, None, :] - Y[None, :, :]
+        d -= np.rint(d / box) * box
+        cp = np.sqrt((d ** 2).sum(2))
+        r, cc = linear_sum_assignment(cp)
+        assert np.array_equal(_lib.host_best_permutation(X, Y, None, box), cc)
+    Xi = rng.integers(0, 3, size=(n, 3)).astype(float)
+    Yi = rng.integers(0, 3, size=(n, 3)).astype(float)
+    c = ((Xi[:, None, :] - Yi[None, :, :]) ** 2).sum(2)
+    r, cc = linear_sum_assignment(c)
+    p = _lib.host_best_permutation(Xi, Yi)
+    assert sorted(p) == list(range(n)) and c[np.arange(n), p].sum() == c[r, cc].sum()
+    assert _lib.host_lap_isa(0) >= 1
+
+
 def test_findpeaks_recovers_planted_gaussians():
     """The scipy restatement of the reference's findPeaks (oracle/peaks_host.py), the checker of the device kernel."""
     from peaks_host import findPeaks
