@@ -3784,10 +3784,12 @@ size_t direct_work_bytes(const fo_ctx* ctx, int64_t np, int64_t natoms, int L) {
 int64_t direct_chunk(const fo_ctx* ctx, int64_t npairs, int64_t natoms, int L, bool want_grid,
                      bool device_resident = false) {
   const size_t per = direct_work_bytes(ctx, 1, natoms, L) + ihalf_elems(L) * 16;
-  // 2 GB of scratch per chunk through host buffers (LJ38: 4472 pairs; measured 1 / 2 / 4 GB: 0.987 / 1.006 / 1.002 M
-  // aligned pairs/s end to end), 4 GB when the input is device-resident (no copies to overlap: fewer launch tails)
-  // and for large clusters / bandwidths (> 256 MB per pair)
-  size_t budget = (per > ((size_t)256 << 20) || device_resident) ? (size_t)4 << 30 : (size_t)2 << 30;
+  // 4 GB of scratch per chunk (LJ38: ~7800 pairs).  Through host buffers, end of round 2 (1 / 2 / 3 / 4 / 6 GB):
+  // 1.32 / 1.39 / 1.42 / 1.44 / 1.41 M aligned pairs/s -- with the kernels of the last session the per-chunk tails
+  // weigh more than the copy / compute overlap gains from shorter chunks (the 2 GB of the first sessions: 0.987 / 1.006 /
+  // 1.002 M at 1 / 2 / 4 GB); the device-resident path has no copies to overlap at all
+  (void)device_resident;
+  size_t budget = (size_t)4 << 30;
   if (const int64_t mb = ctx->opt("sph_chunk_mb")) budget = (size_t)mb << 20;  // tuning hook of the A/B scripts
   int64_t c = (int64_t)(budget / per);
   if (want_grid) {
