@@ -2508,7 +2508,6 @@ __device__ __forceinline__ double2 fo_csub(double2 a, double2 b) { return make_d
 __device__ __forceinline__ double2 fo_cmul(double2 a, double2 t) {
   return make_double2(fma(a.x, t.x, -a.y * t.y), fma(a.x, t.y, a.y * t.x));
 }
-__device__ __forceinline__ double2 fo_csel(bool c, double2 a, double2 b) { return make_double2(c ? a.x : b.x, c ? a.y : b.y); }
 __device__ __forceinline__ double2 fo_cshx(double2 v, int m) {
   return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
@@ -2625,7 +2624,11 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
   int cph = 0;
   if (jstart < npairs) stage_coeffs(jstart);
   // ---- K5 geometry (as sph_isoft4_kernel<4, ...>): task = (shell-ordered entry t = (a, m2), level parity)
-  int k5t = tid >> 1, k5s, k5a, k5m2;
+  // The shell-ordered groups of 16 entries take (8, 6, 5, 5, 4, 4, 4, 3, 3, 3, 2, 2, 2, 2, 1, 1) level trips; they are
+  // dealt to the warps so that the four warps of an SM sub-partition (warp & 3) get 14, 14, 14 and 13 of them
+  // (in warp order sub-partition 0 had 17 and sub-partition 3 had 11)
+  const int k5grp = (int)((0xfdce98ba65473210ull >> (4 * warp)) & 15);
+  int k5t = (k5grp * 32 + lane) >> 1, k5s, k5a, k5m2;
   {
     k5s = (int)sqrtf((float)k5t);
     while ((k5s + 1) * (k5s + 1) <= k5t) ++k5s;
