@@ -2624,9 +2624,9 @@ sph_isoft5_kernel(const __grid_constant__ I2Layout Y, const __grid_constant__ I5
   int cph = 0;
   if (jstart < npairs) stage_coeffs(jstart);
   // ---- K5 geometry (as sph_isoft4_kernel<4, ...>): task = (shell-ordered entry t = (a, m2), level parity)
-  // The shell-ordered groups of 16 entries take (8, 6, 5, 5, 4, 4, 4, 3, 3, 3, 2, 2, 2, 2, 1, 1) level trips; they are
-  // dealt to the warps so that the four warps of an SM sub-partition (warp & 3) get 14, 14, 14 and 13 of them
-  // (in warp order sub-partition 0 had 17 and sub-partition 3 had 11)
+  // The shell-ordered groups of 16 entries take (8, 6, 6, 5, 4, 4, 4, 3, 3, 2, 2, 2, 2, 1, 1, 1) level trips; they are
+  // dealt to the warps so that the four warps of an SM sub-partition (warp & 3) get 14, 14, 14 and 12 of them
+  // (in warp order: 17, 13, 13, 11; tests/test_lane_emulation.py)
   const int k5grp = (int)((0xfdce98ba65473210ull >> (4 * warp)) & 15);
   int k5t = (k5grp * 32 + lane) >> 1, k5s, k5a, k5m2;
   {
