@@ -627,8 +627,11 @@ size_t direct_mma_smem(int64_t natoms, int L) {
 //   C2[r][r'] = sum_k T[r][k] YB[k][r']      the C fragments of T ARE the A fragments of this product when a k-step is
 //                                            taken as the columns {2 t + h} of a tile (t = lane & 3, h = 0 | 1): T never
 //                                            leaves the registers, YB's rows are stored in that order;
-// and I[l, +-m1, m2] is formed in the C fragments as in sph_direct_mma_kernel.  No CTA barrier, no generic-proxy
-// store to shared memory, 1.1 shared loads per DMMA.
+// and I[l, +-m1, m2] is formed in the C fragments as in sph_direct_mma_kernel and written both in the Ihalf layout
+// and (optionally) in the packed layout of the fast iSOFT kernels.  No CTA barrier, no generic-proxy store to shared
+// memory, 1.1 shared loads per DMMA.  A slot is handed back on a named barrier (the consumer warps bar.arrive after
+// their last fragment load, the producer warp bar.sync before it refills the slot): compute-sanitizer's racecheck
+// follows that, it did not follow an "empty" mbarrier from generic-proxy reads to the async-proxy writes of the copy.
 // ------------------------------------------------------------------------------------------
 constexpr int D2_CONS = 4;                       // consumer warps
 constexpr int D2_THREADS = (D2_CONS + 1) * 32;   // + the producer warp
